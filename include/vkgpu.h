@@ -1,0 +1,176 @@
+/* vkgpu.h — C-ABI of the B200-native vector-search core (libvkgpu.so).
+ *
+ * This is the drop-in boundary for ONE hot path of valkey-io/valkey-search: the distance-bound loops under
+ * `valkey_search::indexes::VectorBase` (src/indexes/vector_base.h:129-282), i.e. what
+ * third_party/hnswlib + third_party/simsimd do today behind src/indexes/vector_{flat,hnsw}.{h,cc}.
+ * The module has no FFI; the seam is the VectorBase virtuals plus the two concrete Search() methods that
+ * src/query/search.cc:146-166 calls.  Each entry point below names the reference interface it replaces.
+ * INTEGRATION.md shows the adapter a maintainer would put in vector_flat.cc / vector_hnsw.cc.
+ *
+ * Conventions
+ *  - plain C, no exceptions across the boundary; every call returns a vkgpu_status (0 = ok) and the
+ *    message of the last failure on the calling thread is available from vkgpu_last_error()
+ *    (the reference catches std::runtime_error at the adapter: vector_flat.cc:68-72,165-176,238-242).
+ *  - all input pointers are borrowed for the duration of the call; outputs are caller-allocated.
+ *  - labels are the module's monotonically assigned 64-bit internal ids (vector_base.cc:347);
+ *    `hnswlib::labeltype` = size_t (hnswlib.h:141).
+ *  - vectors are FLOAT32 (vector_base.h:112-114), `dim` floats each; for COSINE the caller passes
+ *    already-normalised vectors and queries (vector_base.cc:157-164, vector_flat.cc:244-249) — the core
+ *    treats COSINE as IP exactly like CreateSpace does (vector_base.cc:61-76).
+ *  - results are ascending by (distance, label) — VectorBase::CreateReply (vector_base.cc:259-277).
+ *  - thread safety: any number of concurrent searches; concurrent mutations; the caller guarantees
+ *    mutations never overlap searches (the module's time-sliced MRMW lock, src/query/search.cc:856,
+ *    src/index_schema.cc:1004) — the library still serialises them internally.
+ *  - there is no CPU fallback: without a CUDA device every compute call fails with VKGPU_ERR_CUDA.
+ */
+#ifndef VKGPU_H_
+#define VKGPU_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VKGPU_ABI_VERSION 1
+
+typedef enum vkgpu_status {
+  VKGPU_OK = 0,
+  VKGPU_ERR_INVALID = 1,      /* bad argument (absl::InvalidArgumentError)                          */
+  VKGPU_ERR_NOT_FOUND = 2,    /* unknown label (absl::NotFoundError, vector_base.cc:203-210)        */
+  VKGPU_ERR_EXISTS = 3,       /* label already present (AddRecord on tracked key, vector_base.cc:168-191) */
+  VKGPU_ERR_CUDA = 4,         /* CUDA runtime / driver failure, or no device                        */
+  VKGPU_ERR_OOM = 5,          /* HBM exhausted                                                      */
+  VKGPU_ERR_CANCELLED = 6,    /* deadline passed (absl::CancelledError, vector_hnsw.cc:327-329)     */
+  VKGPU_ERR_UNSUPPORTED = 7,  /* valid request the core does not implement yet                      */
+  VKGPU_ERR_INTERNAL = 8      /* absl::InternalError                                                */
+} vkgpu_status;
+
+typedef enum vkgpu_metric { VKGPU_L2 = 0, VKGPU_IP = 1, VKGPU_COSINE = 2 } vkgpu_metric; /* vector_base.h:105-110 */
+typedef enum vkgpu_algo { VKGPU_FLAT = 0, VKGPU_HNSW = 1 } vkgpu_algo;
+
+/* FLAT batched-search strategy.  AUTO picks EXACT_FMA for small batches (HBM-bound corpus pass in the
+ * reference's own summation order) and TENSOR for large ones (tcgen05 candidate pass + exact re-rank);
+ * both return bit-identical ids/ranks/distances. */
+typedef enum vkgpu_flat_path { VKGPU_PATH_AUTO = 0, VKGPU_PATH_EXACT_FMA = 1, VKGPU_PATH_TENSOR = 2 } vkgpu_flat_path;
+
+/* data_model::VectorIndex (src/index_schema.proto:87-120) + VectorFlat/VectorHNSW::Create
+ * (vector_flat.cc:53-73, vector_hnsw.cc:84-107). */
+typedef struct vkgpu_config {
+  uint32_t struct_size;     /* sizeof(vkgpu_config), for ABI evolution                               */
+  int32_t algo;             /* vkgpu_algo                                                            */
+  int32_t metric;           /* vkgpu_metric                                                          */
+  uint32_t dim;             /* dimension_count, 1..64000 (ft_create_parser.cc:63-73)                 */
+  uint64_t initial_cap;     /* initial_cap                                                           */
+  uint32_t block_size;      /* FLAT block_size / search.hnsw-block-size growth quantum (0 = 10240)   */
+  uint32_t m;               /* HNSW M               (default 16,  ft_create_parser.h:73-76)          */
+  uint32_t ef_construction; /* HNSW EF_CONSTRUCTION (default 200)                                    */
+  uint32_t ef_runtime;      /* HNSW EF_RUNTIME      (default 10)                                     */
+  int32_t allow_replace_deleted; /* search.hnsw-allow-replace-deleted                               */
+  int32_t device;           /* CUDA device ordinal holding this index (shard)                        */
+  uint32_t max_batch;       /* largest B the caller will pass to *_batch (0 = 1024)                  */
+  uint32_t reserved;
+} vkgpu_config;
+
+typedef struct vkgpu_index vkgpu_index; /* opaque; owns its HBM */
+
+/* Optional candidate restriction for a search, the device-side form of what
+ * EvaluateFilterAsPrimary / InlineVectorFilter hand to the index (src/query/search.cc:103-134,301-394). */
+typedef struct vkgpu_filter {
+  const uint64_t *labels;   /* explicit candidate label list (pre-filter path, vector_base.cc:509-530), or NULL */
+  uint64_t n_labels;
+  const uint8_t *label_bitmap; /* bit i set => label i allowed (inline filter, hnswalg.h:515-518), or NULL */
+  uint64_t bitmap_bits;
+} vkgpu_filter;
+
+typedef struct vkgpu_stats {
+  uint64_t count;            /* live vectors          (GetTrackedKeyCount, vector_base.cc:385-409)     */
+  uint64_t capacity;         /* GetCapacity                                                            */
+  uint64_t deleted;          /* HNSW tombstones (num_deleted_, hnswalg.h:57)                           */
+  uint64_t hbm_bytes;        /* device memory owned by the index                                       */
+  uint64_t searches;         /* queries answered                                                       */
+  uint64_t kernels_launched; /* CUDA kernels launched by this handle (bench.py "gpu_launches")         */
+  uint64_t distance_evals;   /* HNSW: metric_distance_computations analog (hnswalg.h:98-99)            */
+  uint64_t hops;             /* HNSW: metric_hops analog                                               */
+  uint64_t tensor_fallbacks; /* TENSOR-path queries whose candidate margin was too thin and that were
+                                re-run on the exact FMA path (still on the GPU)                        */
+  int32_t max_level;         /* HNSW maxlevel_                                                         */
+  int32_t dim;
+  uint32_t last_qt;          /* FLAT: query-tile width of the last exact pass                          */
+  uint32_t last_passes;      /* FLAT: corpus passes of the last search                                 */
+} vkgpu_stats;
+
+/* ---- lifecycle ------------------------------------------------------------------------------------- */
+int vkgpu_abi_version(void);
+int vkgpu_device_count(void);
+const char *vkgpu_last_error(void);
+
+/* VectorFlat<float>::Create / VectorHNSW<float>::Create (vector_flat.cc:53-73, vector_hnsw.cc:84-107) */
+int vkgpu_index_create(const vkgpu_config *cfg, vkgpu_index **out);
+void vkgpu_index_destroy(vkgpu_index *h);
+
+/* ---- mutation: VectorBase::{Add,Modify,Remove}RecordImpl (vector_base.h:216-221) ------------------ */
+/* AddRecordImpl (vector_flat.cc:158-179, vector_hnsw.cc:177-199): grows by block_size when full. */
+int vkgpu_add(vkgpu_index *h, uint64_t label, const float *vec);
+/* bulk ingest of n rows (backfill, src/index_schema.cc:1026-1092); vecs is [n,dim] row-major on the HOST */
+int vkgpu_add_batch(vkgpu_index *h, const uint64_t *labels, const float *vecs, uint64_t n);
+/* same, vecs already in DEVICE memory of cfg.device (labels on host; NULL => labels = count..count+n-1) */
+int vkgpu_add_batch_device(vkgpu_index *h, const uint64_t *labels, const float *d_vecs, uint64_t n);
+/* ModifyRecordImpl (vector_flat.cc:181-198, vector_hnsw.cc:201-236) */
+int vkgpu_modify(vkgpu_index *h, uint64_t label, const float *vec);
+/* RemoveRecordImpl: FLAT swap-delete (bruteforce.h:92-113); HNSW tombstone (hnswalg.h:1173-1209) */
+int vkgpu_remove(vkgpu_index *h, uint64_t label);
+/* GetValueImpl (vector_base.h:232): copies the stored row back */
+int vkgpu_get(vkgpu_index *h, uint64_t label, float *out_vec);
+
+/* ---- search ----------------------------------------------------------------------------------------- */
+/* VectorFlat::Search / VectorHNSW::Search (vector_flat.cc:224-254, vector_hnsw.cc:313-347) for ONE query.
+ * ef = 0 => index default.  deadline_ns: absolute CLOCK_MONOTONIC ns, 0 = none (cancel::Token).
+ * out_dist/out_labels hold k entries; *out_n <= k receives the count (FLAT: min(k,count)). */
+int vkgpu_search(vkgpu_index *h, const float *q, uint32_t k, uint32_t ef, const vkgpu_filter *filter,
+                 uint64_t deadline_ns, float *out_dist, uint64_t *out_labels, uint32_t *out_n);
+/* B queries at once — Q is [B,dim] row-major; outputs are [B,k] / [B]; filters is NULL, or B entries.
+ * This is the entry a dynamic batcher in the reader pool (src/query/search.cc:886-910) would call. */
+int vkgpu_search_batch(vkgpu_index *h, const float *Q, uint32_t B, uint32_t k, uint32_t ef,
+                       const vkgpu_filter *filters, uint64_t deadline_ns, float *out_dist, uint64_t *out_labels,
+                       uint32_t *out_n);
+/* Same with Q and all outputs in DEVICE memory (no host copies); asynchronous on `cuda_stream`
+ * (a cudaStream_t, NULL = the library's stream for this call, synchronised before return). */
+int vkgpu_search_batch_device(vkgpu_index *h, const float *d_Q, uint32_t B, uint32_t k, uint32_t ef,
+                              float *d_out_dist, uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream);
+/* ComputeDistanceFromRecordImpl (vector_base.h:239-241, vector_flat.cc:257-271, vector_hnsw.cc:370-383):
+ * distance from q to each listed label; unknown labels yield NaN. */
+int vkgpu_distances(vkgpu_index *h, const float *q, const uint64_t *labels, uint64_t n, float *out_dist);
+
+/* ---- multi-GPU: merge of per-shard results (semantic analog of src/query/fanout.cc:159-220) -------- */
+/* d_dist/d_labels/d_n are the allgathered per-shard results, laid out [G][B][k] / [G][B], in device
+ * memory of `device`; writes the merged ascending top-k [B][k] / [B]. */
+int vkgpu_merge_topk_device(int device, const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
+                            uint32_t G, uint32_t B, uint32_t k, float *d_out_dist, uint64_t *d_out_labels,
+                            uint32_t *d_out_n, void *cuda_stream);
+
+/* ---- HNSW graph interchange (hnswlib in-memory layout, hnswalg.h:152-176; "next" row N3) ----------- */
+/* Import a complete graph: n nodes, per-node level, label, deleted flag, level-0 lists [n][2M] + counts,
+ * upper lists concatenated per node (levels[i] blocks of M ids + counts), then vectors [n,dim]. */
+int vkgpu_hnsw_import(vkgpu_index *h, uint64_t n, const int32_t *levels, const uint64_t *labels,
+                      const uint8_t *deleted, const uint32_t *links0, const uint32_t *cnt0,
+                      const uint32_t *upper_links, const uint32_t *upper_cnt, const uint64_t *upper_offset,
+                      int32_t max_level, uint32_t enterpoint, const float *vecs);
+/* Export in the same layout; call once with NULL buffers to get sizes in *n / *upper_blocks. */
+int vkgpu_hnsw_export(vkgpu_index *h, uint64_t *n, uint64_t *upper_blocks, int32_t *levels, uint64_t *labels,
+                      uint8_t *deleted, uint32_t *links0, uint32_t *cnt0, uint32_t *upper_links,
+                      uint32_t *upper_cnt, uint64_t *upper_offset, int32_t *max_level, uint32_t *enterpoint);
+
+/* ---- introspection / tuning ----------------------------------------------------------------------- */
+/* GetCapacity / GetTrackedKeyCount / RespondWithInfoImpl (vector_base.cc:385-409) */
+int vkgpu_get_stats(vkgpu_index *h, vkgpu_stats *out);
+/* FLAT strategy override (tests and bench pin a path; AUTO in production) */
+int vkgpu_set_flat_path(vkgpu_index *h, int path);
+/* device pointer + row stride (floats) of the resident corpus, for zero-copy tooling */
+int vkgpu_device_corpus(vkgpu_index *h, const float **d_rows, uint64_t *row_stride, uint64_t *n_rows);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VKGPU_H_ */

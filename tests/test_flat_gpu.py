@@ -1,0 +1,188 @@
+"""FLAT parity on the GPU: CUDA path (through the C-ABI) vs the CPU oracle, bit-exact ids, ranks, distances.
+
+Reference behaviour under test: hnswlib::BruteforceSearch::searchKnn (third_party/hnswlib/bruteforce.h:116-145)
+behind VectorFlat<float>::Search (src/indexes/vector_flat.cc:224-254); fixtures follow testing/vector_test.cc.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+METRICS = {"L2": O.L2, "IP": O.IP}
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _mk(dim, metric, cap=1024, **kw):
+    import valkey_search_b200 as V
+    return V.VectorFlat(dim, V.DistanceMetric[metric], initial_cap=cap, **kw)
+
+
+def _check_batch(ix, orc, Q, k):
+    dist, labels, n = ix.SearchBatchRaw(Q, k)
+    for b in range(Q.shape[0]):
+        d, l = orc.search(Q[b], k)
+        assert n[b] == d.size, (b, n[b], d.size)
+        assert np.array_equal(labels[b, : n[b]], l), (b, labels[b, : n[b]][:8], l[:8])
+        assert np.array_equal(_bits(dist[b, : n[b]]), _bits(d)), (b, dist[b, :4], d[:4])
+
+
+@pytest.mark.parametrize("metric", ["L2", "IP"])
+@pytest.mark.parametrize("N,D,k", [(10000, 128, 10), (1, 16, 5), (257, 3, 10), (5000, 100, 100), (3000, 768, 100),
+                                    (700, 1536, 7), (129, 17, 129)])
+def test_flat_matches_oracle(built, metric, N, D, k):
+    rng = np.random.default_rng(N * 7 + D)
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    if N > 300:
+        X[100:140] = X[100]  # exact duplicate rows => equal distances => label tie-break
+    ix = _mk(D, metric, cap=N)
+    ix.AddRecordsBulk([f"k{i}" for i in range(N)], X)
+    orc = O.PortFlat(D, METRICS[metric])
+    orc.add_many(X)
+    for B in (1, 2, 3, 5, 8, 19):
+        Q = rng.standard_normal((B, D)).astype(np.float32)
+        if N > 300:
+            Q[0] = X[100]
+        _check_batch(ix, orc, Q, k)
+    ix.close()
+
+
+def test_flat_config1_shape_single_query(built):
+    """BASELINE config 1: 10k x 128 fp32, k=10, single query."""
+    rng = np.random.default_rng(1234)
+    X = rng.standard_normal((10000, 128)).astype(np.float32)
+    ix = _mk(128, "L2", cap=10000)
+    ix.AddRecordsBulk(list(range(1, 10001)), X)
+    orc = O.PortFlat(128, O.L2)
+    orc.add_many(X)
+    for t in range(20):
+        q = rng.standard_normal(128).astype(np.float32)
+        res = ix.Search(q, 10)
+        d, l = orc.search(q, 10)
+        assert [r.external_id for r in res] == [int(x) + 1 for x in l]
+        assert np.array_equal(_bits([r.distance for r in res]), _bits(d))
+
+
+def test_flat_empty_and_k_larger_than_count(built):
+    ix = _mk(8, "L2")
+    assert ix.Search(np.zeros(8, np.float32), 5) == []
+    X = np.eye(8, dtype=np.float32)[:3]
+    for i in range(3):
+        assert ix.AddRecord(f"a{i}", X[i].tobytes()).name == "kAdded"
+    res = ix.Search(X[1], 10)  # k = min(k, count), vector_flat.cc:236
+    assert len(res) == 3 and res[0].external_id == "a1" and res[0].distance == 0.0
+
+
+def test_flat_swap_delete_and_readd(built):
+    """bruteforce.h:92-113 swap-delete perturbs slot order; results must not depend on it."""
+    rng = np.random.default_rng(5)
+    N, D = 2000, 64
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    X[500:700] = X[500]
+    ix = _mk(D, "L2", cap=100, block_size=128)  # forces growth
+    orc = O.PortFlat(D, O.L2)
+    order = rng.permutation(N)
+    key_to_id = {}
+    for j, i in enumerate(order):
+        assert ix.AddRecord(f"k{i}", X[i]).name == "kAdded"
+        key_to_id[i] = j  # internal ids are handed out in insertion order (vector_base.cc:347)
+        orc.add(X[i], j)
+    for i in rng.choice(N, 600, replace=False):
+        assert ix.RemoveRecord(f"k{i}") is True
+        orc.remove(key_to_id[i])
+    assert ix.RemoveRecord("nope") is False
+    assert ix.GetTrackedKeyCount() == orc.count() == 1400
+    Q = rng.standard_normal((6, D)).astype(np.float32)
+    Q[0] = X[500]
+    _check_batch(ix, orc, Q, 10)
+    # dup add = error, wrong dim = kInvalidData, unchanged modify = kMissing (testing/vector_test.cc:238-291)
+    live = next(i for i in range(N) if ix.IsTracked(f"k{i}"))
+    with pytest.raises(Exception):
+        ix.AddRecord(f"k{live}", X[live])
+    assert ix.AddRecord("short", X[0][:10]).name == "kInvalidData"
+    assert ix.ModifyRecord(f"k{live}", X[live]).name == "kMissing"
+    assert ix.ModifyRecord(f"k{live}", X[live] + 1).name == "kAdded"
+    orc.add(X[live] + 1, key_to_id[live])
+    _check_batch(ix, orc, Q, 10)
+
+
+def test_flat_cosine_matches_reference_goldens(built):
+    """testing/integration/vector_search_integration_test.py:19-23,144-166: vectors [1, i, 0...] D=100 COSINE,
+    query [1,0,...], k=3 => keys 0,1,2 with scores 0, 0.292893230915, 0.552786409855 (%.12g of the float)."""
+    import valkey_search_b200 as V
+    D = 100
+    ix = V.VectorFlat(D, V.DistanceMetric.COSINE, initial_cap=100)
+    for i in range(10):
+        v = np.zeros(D, np.float32)
+        v[0], v[1] = 1.0, float(i)
+        ix.AddRecord(str(i), v)
+    q = np.zeros(D, np.float32)
+    q[0] = 1.0
+    res = ix.Search(q, 3)
+    assert [r.external_id for r in res] == ["0", "1", "2"]
+    assert ["%.12g" % r.distance for r in res] == ["0", "0.292893230915", "0.552786409855"]
+
+
+def test_flat_prefilter_subset(built):
+    """VectorBase::AddPrefilteredKey (vector_base.cc:509-530) via CalcBestMatchingPrefilteredKeys."""
+    rng = np.random.default_rng(11)
+    N, D, k = 4000, 96, 10
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    ix = _mk(D, "L2", cap=N)
+    ix.AddRecordsBulk([f"k{i}" for i in range(N)], X)
+    orc = O.PortFlat(D, O.L2)
+    orc.add_many(X)
+    for sel in (0.01, 0.3):
+        cand = np.flatnonzero(rng.random(N) < sel)
+        q = rng.standard_normal(D).astype(np.float32)
+        res = ix.Search(q, k, filter=[f"k{i}" for i in cand] + ["missing-key"])
+        d, l = orc.search_subset(q, k, cand.astype(np.uint64))
+        assert [r.external_id for r in res] == [f"k{int(i)}" for i in l]
+        assert np.array_equal(_bits([r.distance for r in res]), _bits(d))
+
+
+def test_distances_from_record(built):
+    rng = np.random.default_rng(3)
+    D = 200
+    X = rng.standard_normal((50, D)).astype(np.float32)
+    for metric in ("L2", "IP"):
+        ix = _mk(D, metric)
+        ix.AddRecordsBulk([f"k{i}" for i in range(50)], X)
+        p = O.port()
+        q = rng.standard_normal(D).astype(np.float32)
+        for i in (0, 7, 49):
+            d, _ = ix.ComputeDistanceFromRecord(f"k{i}", q)
+            want = p.vko_l2sq(q, X[i], D) if metric == "L2" else p.vko_ip(q, X[i], D)
+            assert np.float32(d).tobytes() == np.float32(want).tobytes()
+
+
+def test_flat_large_property_checks(built):
+    """Size-independent properties at a size the oracle cannot scan quickly: results sorted, distances equal
+    the oracle's for the returned rows, and no row of a random sample beats the k-th result."""
+    rng = np.random.default_rng(99)
+    N, D, k, B = 300_000, 768, 100, 16
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    ix = _mk(D, "L2", cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    dist, labels, n = ix.SearchBatchRaw(Q, k)
+    p = O.port()
+    sample = rng.choice(N, 3000, replace=False)
+    for b in range(B):
+        assert n[b] == k
+        keys = list(zip(dist[b].tolist(), labels[b].tolist()))
+        assert keys == sorted(keys)
+        for j in (0, 1, k // 2, k - 1):
+            want = p.vko_l2sq(Q[b], X[int(labels[b, j])], D)
+            assert np.float32(dist[b, j]).tobytes() == np.float32(want).tobytes()
+        kth = (float(dist[b, k - 1]), int(labels[b, k - 1]))
+        got = set(labels[b].tolist())
+        for s in sample:
+            ds = p.vko_l2sq(Q[b], X[s], D)
+            assert (ds, int(s)) > kth or int(s) in got

@@ -1,0 +1,59 @@
+// Exact-order distance of one (row, query) pair by a 4-thread group reading straight from global/L2.
+// Same arithmetic as flat_scan.cu (reference order: 16 fma lanes, combine 8,4,2,1;
+// third_party/simsimd/include/simsimd/{dot.h:1183-1204,spatial.h:1131-1154}, hnswlib/simsimd.h:16-34).
+// Used where rows are visited irregularly: HNSW hops, re-rank of tensor-path candidates, vkgpu_distances.
+#pragma once
+#include "common.cuh"
+
+namespace vkgpu {
+
+// `u` = lane & 3 inside the group (all 4 lanes of the group must call, with `active` uniform in the
+// group; inactive groups still take part in the shuffles).  q may be global or shared; Dp % 16 == 0 and
+// both pointers are 16-B aligned.  Returns the distance in all 4 lanes.
+template <bool L2>
+__device__ __forceinline__ float exact_dist_group(const float *__restrict__ row, const float *__restrict__ q,
+                                                  uint32_t Dp, uint32_t u, bool active) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    const float4 *r4 = reinterpret_cast<const float4 *>(row) + u;
+    const float4 *q4 = reinterpret_cast<const float4 *>(q) + u;
+    const uint32_t steps = Dp >> 4;
+    uint32_t s = 0;
+    // 4 independent 16-B loads in flight per thread before the dependent fma chain consumes them
+    for (; s + 4 <= steps; s += 4) {
+      float4 x0 = __ldg(r4 + (s + 0) * 4), x1 = __ldg(r4 + (s + 1) * 4);
+      float4 x2 = __ldg(r4 + (s + 2) * 4), x3 = __ldg(r4 + (s + 3) * 4);
+      float4 y0 = q4[(s + 0) * 4], y1 = q4[(s + 1) * 4], y2 = q4[(s + 2) * 4], y3 = q4[(s + 3) * 4];
+#define VK_STEP(X, Y)                                                                 \
+  if (L2) {                                                                           \
+    float d;                                                                          \
+    d = __fsub_rn(Y.x, X.x); acc.x = __fmaf_rn(d, d, acc.x);                           \
+    d = __fsub_rn(Y.y, X.y); acc.y = __fmaf_rn(d, d, acc.y);                           \
+    d = __fsub_rn(Y.z, X.z); acc.z = __fmaf_rn(d, d, acc.z);                           \
+    d = __fsub_rn(Y.w, X.w); acc.w = __fmaf_rn(d, d, acc.w);                           \
+  } else {                                                                            \
+    acc.x = __fmaf_rn(Y.x, X.x, acc.x); acc.y = __fmaf_rn(Y.y, X.y, acc.y);           \
+    acc.z = __fmaf_rn(Y.z, X.z, acc.z); acc.w = __fmaf_rn(Y.w, X.w, acc.w);           \
+  }
+      VK_STEP(x0, y0) VK_STEP(x1, y1) VK_STEP(x2, y2) VK_STEP(x3, y3)
+    }
+    for (; s < steps; s++) {
+      float4 x0 = __ldg(r4 + s * 4);
+      float4 y0 = q4[s * 4];
+      VK_STEP(x0, y0)
+    }
+#undef VK_STEP
+  }
+  acc.x = __fadd_rn(acc.x, __shfl_xor_sync(0xffffffffu, acc.x, 2));
+  acc.y = __fadd_rn(acc.y, __shfl_xor_sync(0xffffffffu, acc.y, 2));
+  acc.z = __fadd_rn(acc.z, __shfl_xor_sync(0xffffffffu, acc.z, 2));
+  acc.w = __fadd_rn(acc.w, __shfl_xor_sync(0xffffffffu, acc.w, 2));
+  acc.x = __fadd_rn(acc.x, __shfl_xor_sync(0xffffffffu, acc.x, 1));
+  acc.y = __fadd_rn(acc.y, __shfl_xor_sync(0xffffffffu, acc.y, 1));
+  acc.z = __fadd_rn(acc.z, __shfl_xor_sync(0xffffffffu, acc.z, 1));
+  acc.w = __fadd_rn(acc.w, __shfl_xor_sync(0xffffffffu, acc.w, 1));
+  const float sum = __fadd_rn(__fadd_rn(acc.x, acc.z), __fadd_rn(acc.y, acc.w));
+  return L2 ? sum : (float)(1.0 - (double)sum);
+}
+
+}  // namespace vkgpu

@@ -1,0 +1,370 @@
+// K1+K2: exact-order FLAT / gather scan with fused threshold-gated top-k (sm_100a).
+//
+// Replaces the hot loop of hnswlib::BruteforceSearch::searchKnn (third_party/hnswlib/bruteforce.h:116-145)
+// and of VectorBase::AddPrefilteredKey (src/indexes/vector_base.cc:509-530), with the distance arithmetic of
+// simsimd_{l2sq,dot}_f32_skylake (third_party/simsimd/include/simsimd/spatial.h:1131-1154, dot.h:1183-1204)
+// reproduced bit for bit:
+//
+//   * the reference sums in 16 SIMD lanes — lane j folds elements j, j+16, ... with one fma each — and then
+//     combines lanes pairwise at strides 8,4,2,1.  Here a group of 4 threads owns one (row, query) pair;
+//     thread u holds SIMD lanes 4u..4u+3 in a float4, so one LDS.128 feeds four chains; the stride-8 and
+//     stride-4 combines are __shfl_xor 2 and 1, the stride-2/1 combines are in-register adds.
+//   * each thread register-tiles 2 rows x QT queries (QT = 1,2,4,8), so one staged corpus tile is used by
+//     QT queries: bytes moved per FMA fall with QT until the FMA pipe, not HBM, is the limit.
+//
+// Data movement: one copy-issuing warp streams [128 rows + QT queries] x 64-float chunks into a ring of
+// shared-memory stages with cp.async.bulk (TMA engine, mbarrier complete_tx); 8 compute warps consume them.
+// Smem rows are padded to 272 B and a warp's 8 row-groups are permuted so every LDS.128 phase is
+// bank-conflict free.  Top-k: a candidate is appended to the CTA's per-query buffer (global, L2-resident)
+// only if dist <= the running k-th distance — the reference's `dist <= lastdist` gate (bruteforce.h:131);
+// when a buffer could overflow on the next tile the CTA bitonic-sorts it in smem and keeps the k best.
+#include "flat_scan.cuh"
+
+namespace vkgpu {
+
+namespace {
+
+constexpr int TR = kScanTileRows;
+constexpr int DC = kScanChunkFloats;
+constexpr int ROWB = kScanRowBytes;
+constexpr int NCOMPUTE = 256;
+
+template <int QT, bool L2>
+__global__ void __launch_bounds__(kScanThreads, 1) flat_scan_kernel(const ScanParams p) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  const uint32_t S = p.stages;
+  const uint32_t stage_bytes = (TR + QT) * ROWB;
+  uint8_t *stages = smem;
+  Cand *scratch = reinterpret_cast<Cand *>(smem + (size_t)S * stage_bytes);
+  uint8_t *tail = reinterpret_cast<uint8_t *>(scratch + p.cap);
+  uint64_t *full = reinterpret_cast<uint64_t *>(tail);  // [S]
+  uint64_t *empty = full + 16;                          // [S]   (S <= 16)
+  uint32_t *thr = reinterpret_cast<uint32_t *>(empty + 16);  // [QT]
+  uint32_t *cnt = thr + kScanMaxQt;                          // [QT]
+  uint32_t *mask = cnt + kScanMaxQt;
+
+  const uint32_t tid = threadIdx.x;
+  const uint32_t warp = tid >> 5, lane = tid & 31;
+  const uint32_t qtile = blockIdx.x, slab = blockIdx.y, slabs = gridDim.y;
+
+  // rows this CTA scans
+  uint64_t list_base = 0, n_rows = p.n_rows;
+  if (p.list_off) {
+    list_base = p.list_off[qtile];
+    n_rows = p.list_off[qtile + 1] - list_base;
+  }
+  const uint32_t total_tiles = (uint32_t)((n_rows + TR - 1) / TR);
+  const uint32_t nchunks = (p.Dp + DC - 1) / DC;
+
+  if (tid == 0) {
+    for (uint32_t s = 0; s < S; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], NCOMPUTE / 32);
+    }
+    fence_mbar_init();
+  }
+  if (tid < QT) {
+    thr[tid] = kOrdInf;
+    cnt[tid] = 0;
+  }
+  __syncthreads();
+
+  Cand *my_ws = p.ws + ((size_t)qtile * slabs + slab) * QT * p.cap;
+
+  if (warp == NCOMPUTE / 32) {
+    // ------------------------------------------------------------------ copy-issuing warp
+    const float *Qt = p.Q + (size_t)qtile * QT * p.Dp;
+    uint32_t stage = 0, phase = 0;
+    for (uint32_t tile = slab; tile < total_tiles; tile += slabs) {
+      const uint64_t row0 = (uint64_t)tile * TR;
+      const uint32_t nrows = (uint32_t)min((uint64_t)TR, n_rows - row0);
+      // resolve this lane's 4 rows once per tile
+      const float *src[TR / 32];
+#pragma unroll
+      for (int j = 0; j < TR / 32; j++) {
+        uint32_t r = lane + 32 * j;
+        uint64_t slot = 0;
+        if (r < nrows) slot = p.row_ids ? (uint64_t)p.row_ids[list_base + row0 + r] : row0 + r;
+        src[j] = p.X + slot * p.Dp;
+      }
+      for (uint32_t c = 0; c < nchunks; c++) {
+        const uint32_t cf = min((uint32_t)DC, p.Dp - c * DC);
+        const uint32_t bytes = cf * 4;
+        mbar_wait(&empty[stage], phase ^ 1);
+        if (lane == 0) mbar_arrive_expect_tx(&full[stage], (nrows + QT) * bytes);
+        __syncwarp();
+        uint8_t *sb = stages + (size_t)stage * stage_bytes;
+#pragma unroll
+        for (int j = 0; j < TR / 32; j++) {
+          uint32_t r = lane + 32 * j;
+          if (r < nrows) bulk_g2s(sb + r * ROWB, src[j] + c * DC, bytes, &full[stage]);
+        }
+        if (lane < QT) bulk_g2s(sb + (TR + lane) * ROWB, Qt + (size_t)lane * p.Dp + c * DC, bytes, &full[stage]);
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1;
+        }
+      }
+    }
+    return;
+  }
+
+  // -------------------------------------------------------------------- compute warps
+  const uint32_t g = lane >> 2, u = lane & 3;
+  // quarter-warp = groups (2t, 2t+1); give them rows t and t+4 so their 64-B segments fall in
+  // opposite halves of the 128-B bank window (row stride 272 B => +4 rows = +64 B mod 128).
+  const uint32_t prow = (g >> 1) | ((g & 1) << 2);
+  const uint32_t rowA = warp * 16 + prow, rowB = rowA + 8;
+  const uint32_t xoffA = rowA * ROWB + u * 16, xoffB = rowB * ROWB + u * 16;
+  const uint32_t qoff = TR * ROWB + u * 16;
+
+  uint32_t stage = 0, phase = 0;
+  for (uint32_t tile = slab; tile < total_tiles; tile += slabs) {
+    float4 accA[QT], accB[QT];
+#pragma unroll
+    for (int q = 0; q < QT; q++) {
+      accA[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+      accB[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (uint32_t c = 0; c < nchunks; c++) {
+      const uint32_t steps = min((uint32_t)DC, p.Dp - c * DC) >> 4;
+      mbar_wait(&full[stage], phase);
+      const uint8_t *sb = stages + (size_t)stage * stage_bytes;
+      auto step = [&](uint32_t s) {
+        const float4 xa = *reinterpret_cast<const float4 *>(sb + xoffA + s * 64);
+        const float4 xb = *reinterpret_cast<const float4 *>(sb + xoffB + s * 64);
+#pragma unroll
+        for (int q = 0; q < QT; q++) {
+          const float4 qv = *reinterpret_cast<const float4 *>(sb + qoff + q * ROWB + s * 64);
+          if (L2) {
+            // reference: d = a - b with a = query, b = row (bruteforce.h:122), then fma(d,d,acc)
+            float d;
+            d = __fsub_rn(qv.x, xa.x); accA[q].x = __fmaf_rn(d, d, accA[q].x);
+            d = __fsub_rn(qv.y, xa.y); accA[q].y = __fmaf_rn(d, d, accA[q].y);
+            d = __fsub_rn(qv.z, xa.z); accA[q].z = __fmaf_rn(d, d, accA[q].z);
+            d = __fsub_rn(qv.w, xa.w); accA[q].w = __fmaf_rn(d, d, accA[q].w);
+            d = __fsub_rn(qv.x, xb.x); accB[q].x = __fmaf_rn(d, d, accB[q].x);
+            d = __fsub_rn(qv.y, xb.y); accB[q].y = __fmaf_rn(d, d, accB[q].y);
+            d = __fsub_rn(qv.z, xb.z); accB[q].z = __fmaf_rn(d, d, accB[q].z);
+            d = __fsub_rn(qv.w, xb.w); accB[q].w = __fmaf_rn(d, d, accB[q].w);
+          } else {
+            accA[q].x = __fmaf_rn(qv.x, xa.x, accA[q].x);
+            accA[q].y = __fmaf_rn(qv.y, xa.y, accA[q].y);
+            accA[q].z = __fmaf_rn(qv.z, xa.z, accA[q].z);
+            accA[q].w = __fmaf_rn(qv.w, xa.w, accA[q].w);
+            accB[q].x = __fmaf_rn(qv.x, xb.x, accB[q].x);
+            accB[q].y = __fmaf_rn(qv.y, xb.y, accB[q].y);
+            accB[q].z = __fmaf_rn(qv.z, xb.z, accB[q].z);
+            accB[q].w = __fmaf_rn(qv.w, xb.w, accB[q].w);
+          }
+        }
+      };
+      if (steps == 4) {
+#pragma unroll
+        for (uint32_t s = 0; s < 4; s++) step(s);
+      } else {
+        for (uint32_t s = 0; s < steps; s++) step(s);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == S) {
+        stage = 0;
+        phase ^= 1;
+      }
+    }
+
+    // ---- lane combine in the reference order (strides 8,4 across threads; 2,1 in registers)
+    const uint64_t row0 = (uint64_t)tile * TR;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+      const uint64_t r = row0 + (half ? rowB : rowA);
+#pragma unroll
+      for (int q = 0; q < QT; q++) {
+        float4 v = half ? accB[q] : accA[q];
+        v.x = __fadd_rn(v.x, __shfl_xor_sync(0xffffffffu, v.x, 2));
+        v.y = __fadd_rn(v.y, __shfl_xor_sync(0xffffffffu, v.y, 2));
+        v.z = __fadd_rn(v.z, __shfl_xor_sync(0xffffffffu, v.z, 2));
+        v.w = __fadd_rn(v.w, __shfl_xor_sync(0xffffffffu, v.w, 2));
+        v.x = __fadd_rn(v.x, __shfl_xor_sync(0xffffffffu, v.x, 1));
+        v.y = __fadd_rn(v.y, __shfl_xor_sync(0xffffffffu, v.y, 1));
+        v.z = __fadd_rn(v.z, __shfl_xor_sync(0xffffffffu, v.z, 1));
+        v.w = __fadd_rn(v.w, __shfl_xor_sync(0xffffffffu, v.w, 1));
+        const float sum = __fadd_rn(__fadd_rn(v.x, v.z), __fadd_rn(v.y, v.w));
+        // hnswlib/simsimd.h:16-34: L2 returns the sum; IP returns (float)(1.0 - (double)dot)
+        const float dist = L2 ? sum : (float)(1.0 - (double)sum);
+        if ((q & 3) == (int)u && r < n_rows) {
+          const uint32_t o = f32_to_ord(dist);
+          if (o <= thr[q]) {
+            const uint32_t pos = atomicAdd(&cnt[q], 1u);
+            const uint32_t slot = p.row_ids ? p.row_ids[list_base + r] : (uint32_t)r;
+            Cand cd;
+            cd.ord = o;
+            cd.slot = slot;
+            cd.label = p.labels[slot];
+            my_ws[(size_t)q * p.cap + pos] = cd;  // pos < cap: guaranteed by the shrink rule below
+          }
+        }
+      }
+    }
+
+    // ---- keep every buffer able to take a whole tile (<= TR appends per query per tile)
+    named_bar_sync(1, NCOMPUTE);
+    if (tid == 0) {
+      uint32_t m = 0;
+#pragma unroll
+      for (int q = 0; q < QT; q++)
+        if (cnt[q] + TR > p.cap) m |= 1u << q;
+      *mask = m;
+    }
+    named_bar_sync(1, NCOMPUTE);
+    uint32_t m = *mask;
+    while (m) {
+      const int q = __ffs(m) - 1;
+      m &= m - 1;
+      const uint32_t n = cnt[q];
+      Cand *buf = my_ws + (size_t)q * p.cap;
+      for (uint32_t i = tid; i < p.cap; i += NCOMPUTE) {
+        Cand cd;
+        if (i < n) {
+          cd = buf[i];
+        } else {
+          cd.ord = kOrdInf;
+          cd.slot = 0xffffffffu;
+          cd.label = ~0ull;
+        }
+        scratch[i] = cd;
+      }
+      named_bar_sync(1, NCOMPUTE);
+      bitonic_sort_cands(scratch, p.cap, tid, NCOMPUTE, [] { named_bar_sync(1, NCOMPUTE); });
+      const uint32_t keep = min(n, p.k);
+      for (uint32_t i = tid; i < keep; i += NCOMPUTE) buf[i] = scratch[i];
+      if (tid == 0) {
+        cnt[q] = keep;
+        if (keep == p.k) thr[q] = scratch[p.k - 1].ord;
+      }
+      named_bar_sync(1, NCOMPUTE);
+    }
+  }
+
+  named_bar_sync(1, NCOMPUTE);
+  if (tid < QT) p.ws_cnt[((size_t)qtile * slabs + slab) * QT + tid] = cnt[tid];
+}
+
+template <int QT, bool L2>
+void launch_one(dim3 grid, size_t smem, cudaStream_t stream, const ScanParams &p) {
+  flat_scan_kernel<QT, L2><<<grid, kScanThreads, smem, stream>>>(p);
+}
+
+template <int QT, bool L2>
+void set_attr_one(size_t max_smem) {
+  VK_CUDA(cudaFuncSetAttribute(flat_scan_kernel<QT, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+}
+
+}  // namespace
+
+void flat_scan_set_smem_attr(size_t max_smem) {
+  set_attr_one<1, true>(max_smem);
+  set_attr_one<2, true>(max_smem);
+  set_attr_one<4, true>(max_smem);
+  set_attr_one<8, true>(max_smem);
+  set_attr_one<1, false>(max_smem);
+  set_attr_one<2, false>(max_smem);
+  set_attr_one<4, false>(max_smem);
+  set_attr_one<8, false>(max_smem);
+}
+
+void launch_flat_scan(int qt, bool l2, dim3 grid, size_t smem, cudaStream_t stream, const ScanParams &p) {
+  if (l2) {
+    switch (qt) {
+      case 1: launch_one<1, true>(grid, smem, stream, p); break;
+      case 2: launch_one<2, true>(grid, smem, stream, p); break;
+      case 4: launch_one<4, true>(grid, smem, stream, p); break;
+      default: launch_one<8, true>(grid, smem, stream, p); break;
+    }
+  } else {
+    switch (qt) {
+      case 1: launch_one<1, false>(grid, smem, stream, p); break;
+      case 2: launch_one<2, false>(grid, smem, stream, p); break;
+      case 4: launch_one<4, false>(grid, smem, stream, p); break;
+      default: launch_one<8, false>(grid, smem, stream, p); break;
+    }
+  }
+  VK_CUDA(cudaGetLastError());
+}
+
+// ------------------------------------------------------------------------------------------------
+// Top-k merge: one CTA per query folds `slabs` unsorted candidate lists into the ascending k best by
+// (distance, label) — the order VectorBase::CreateReply produces (src/indexes/vector_base.cc:259-277).
+// Also the single-GPU half of the multi-GPU merge (fanout.cc:159-220 analog).
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int MERGE_THREADS = 256;
+
+__global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const MergeParams p) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  Cand *buf = reinterpret_cast<Cand *>(msm);  // [sort_n]
+  __shared__ uint32_t fill;
+  const uint32_t b = blockIdx.x, tid = threadIdx.x;
+  const uint32_t qtile = b / p.qt, qi = b % p.qt;
+  const uint32_t N = p.sort_n, K = p.k;
+  auto sync = [] { __syncthreads(); };
+
+  if (tid == 0) fill = 0;
+  for (uint32_t i = tid; i < N; i += MERGE_THREADS) {
+    buf[i].ord = kOrdInf;
+    buf[i].slot = 0xffffffffu;
+    buf[i].label = ~0ull;
+  }
+  __syncthreads();
+
+  uint32_t have = 0;  // uniform: valid entries currently in buf[0..have)
+  for (uint32_t s = 0; s < p.slabs; s++) {
+    const size_t li = ((size_t)qtile * p.slabs + s) * p.qt + qi;
+    const uint32_t n = min(p.ws_cnt[li], p.cap);
+    const Cand *src = p.ws + li * p.cap;
+    uint32_t done = 0;
+    while (done < n) {
+      const uint32_t room = N - have;
+      const uint32_t take = min(room, n - done);
+      for (uint32_t i = tid; i < take; i += MERGE_THREADS) buf[have + i] = src[done + i];
+      done += take;
+      have += take;
+      __syncthreads();
+      if (have == N) {
+        bitonic_sort_cands(buf, N, tid, MERGE_THREADS, sync);
+        for (uint32_t i = K + tid; i < N; i += MERGE_THREADS) {
+          buf[i].ord = kOrdInf;
+          buf[i].slot = 0xffffffffu;
+          buf[i].label = ~0ull;
+        }
+        have = min(have, K);
+        __syncthreads();
+      }
+    }
+  }
+  bitonic_sort_cands(buf, N, tid, MERGE_THREADS, sync);
+  uint32_t kk = K;
+  if (p.k_limit) kk = min(kk, p.k_limit[b]);
+  const uint32_t nout = min(have, kk);
+  for (uint32_t i = tid; i < K; i += MERGE_THREADS) {
+    const bool ok = i < nout;
+    p.out_dist[(size_t)b * K + i] = ok ? ord_to_f32(buf[i].ord) : __int_as_float(0x7f800000);
+    p.out_labels[(size_t)b * K + i] = ok ? buf[i].label : ~0ull;
+    if (p.out_slots) p.out_slots[(size_t)b * K + i] = ok ? buf[i].slot : 0xffffffffu;
+  }
+  if (tid == 0) p.out_n[b] = nout;
+}
+}  // namespace
+
+void launch_topk_merge(uint32_t B, cudaStream_t stream, const MergeParams &p) {
+  size_t smem = (size_t)p.sort_n * sizeof(Cand);
+  static bool attr_set = false;
+  if (!attr_set) {
+    VK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  topk_merge_kernel<<<B, MERGE_THREADS, smem, stream>>>(p);
+  VK_CUDA(cudaGetLastError());
+}
+
+}  // namespace vkgpu

@@ -1,0 +1,55 @@
+// Exact-order FLAT scan: launch parameters shared by flat_scan.cu and the host side (index.cu).
+#pragma once
+#include "common.cuh"
+
+namespace vkgpu {
+
+// Geometry of the exact scan kernel (see flat_scan.cu for the derivation).
+static constexpr int kScanTileRows = 128;    // corpus rows per CTA tile (8 warps x 8 row-groups x 2 rows)
+static constexpr int kScanChunkFloats = 64;  // floats of each row staged per pipeline stage (256 B)
+static constexpr int kScanRowBytes = kScanChunkFloats * 4 + 16;  // padded smem row stride (272 B)
+static constexpr int kScanThreads = 288;     // 8 compute warps + 1 copy-issuing warp
+static constexpr int kScanMaxQt = 8;
+
+struct ScanParams {
+  const float *X;            // corpus rows, row stride = Dp floats (zero padded past dim)
+  const uint64_t *labels;    // slot -> label
+  const uint32_t *row_ids;   // optional gather list of slots (nullptr => rows [0, n_rows))
+  const uint64_t *list_off;  // optional [qtiles+1] offsets into row_ids: one list per query tile
+  uint64_t n_rows;           // rows in the range / shared list (ignored when list_off != nullptr)
+  const float *Q;            // zero-padded queries [qtiles*QT][Dp]
+  uint32_t Dp;               // padded dim, multiple of 16
+  uint32_t k;                // candidates kept per (CTA, query) after a shrink
+  uint32_t cap;              // candidate buffer capacity per (CTA, query): pow2 >= k + kScanTileRows
+  uint32_t stages;           // pipeline depth
+  Cand *ws;                  // [qtiles][slabs][QT][cap]
+  uint32_t *ws_cnt;          // [qtiles][slabs][QT]
+};
+
+// bytes of dynamic shared memory the scan kernel needs
+inline size_t scan_smem_bytes(int qt, uint32_t cap, uint32_t stages) {
+  return (size_t)stages * (kScanTileRows + qt) * kScanRowBytes + (size_t)cap * sizeof(Cand) + 512;
+}
+
+// qt in {1,2,4,8}; metric_l2: true => squared L2, false => 1 - dot.  grid = (qtiles, slabs).
+void launch_flat_scan(int qt, bool metric_l2, dim3 grid, size_t smem, cudaStream_t stream, const ScanParams &p);
+void flat_scan_set_smem_attr(size_t max_smem);
+
+// Per-query merge of `nlists` unsorted candidate lists into the ascending top-k.
+struct MergeParams {
+  const Cand *ws;          // lists; list j of query b starts at ws + list_index(b,j)*cap
+  const uint32_t *ws_cnt;  // entries in each list
+  uint32_t qt;             // queries per tile in the ws layout
+  uint32_t slabs;          // lists per query
+  uint32_t cap;            // list stride
+  uint32_t k;              // results wanted
+  uint32_t sort_n;         // pow2 >= 2*k (and >= 512): size of the smem sort buffer
+  float *out_dist;         // [B][k]
+  uint64_t *out_labels;    // [B][k]
+  uint32_t *out_slots;     // optional [B][k]
+  uint32_t *out_n;         // [B]
+  const uint32_t *k_limit; // optional per-query cap on results (nullptr => k)
+};
+void launch_topk_merge(uint32_t B, cudaStream_t stream, const MergeParams &p);
+
+}  // namespace vkgpu

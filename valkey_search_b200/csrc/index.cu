@@ -1,0 +1,758 @@
+// libvkgpu C-ABI (include/vkgpu.h): handle lifecycle, corpus residency in HBM, FLAT search drivers.
+// Host-side mirror of VectorFlat / VectorBase behaviour: src/indexes/vector_flat.cc, vector_base.cc.
+#include "index.h"
+
+#include <time.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "hnsw.h"
+#include "tensor_path.h"
+
+namespace vkgpu {
+
+// ------------------------------------------------------------------------------------------ errors
+static thread_local std::string g_last_error;
+void set_last_error(const std::string &msg) { g_last_error = msg; }
+
+template <typename F>
+static int guarded(F &&fn) {
+  try {
+    fn();
+    return VKGPU_OK;
+  } catch (const StatusError &e) {
+    set_last_error(e.msg);
+    return e.code;
+  } catch (const CudaFail &f) {
+    cudaGetLastError();  // clear sticky-free errors
+    set_last_error(std::string("CUDA error ") + cudaGetErrorName(f.err) + " (" + cudaGetErrorString(f.err) +
+                   ") at " + f.file + ":" + std::to_string(f.line) + ": " + f.what);
+    return f.err == cudaErrorMemoryAllocation ? VKGPU_ERR_OOM : VKGPU_ERR_CUDA;
+  } catch (const std::bad_alloc &) {
+    set_last_error("host allocation failed");
+    return VKGPU_ERR_OOM;
+  } catch (const std::exception &e) {
+    set_last_error(std::string("internal error: ") + e.what());
+    return VKGPU_ERR_INTERNAL;
+  }
+}
+#define VK_REQUIRE(cond, code, msg) \
+  do {                              \
+    if (!(cond)) throw StatusError{code, msg}; \
+  } while (0)
+
+// ------------------------------------------------------------------------------------------ buffers
+void DevBuf::reserve(size_t need, bool keep, cudaStream_t s) {
+  if (need <= bytes) return;
+  size_t nb = std::max(need, bytes + bytes / 2);
+  nb = (nb + 255) & ~size_t(255);
+  void *np = nullptr;
+  cudaError_t e = cudaMalloc(&np, nb);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    nb = (need + 255) & ~size_t(255);
+    VK_CUDA(cudaMalloc(&np, nb));
+  }
+  if (keep && p && bytes) {
+    VK_CUDA(cudaMemcpyAsync(np, p, bytes, cudaMemcpyDeviceToDevice, s));
+    VK_CUDA(cudaStreamSynchronize(s));
+  }
+  if (p) VK_CUDA(cudaFree(p));
+  p = np;
+  bytes = nb;
+}
+void DevBuf::release() {
+  if (p) cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+void PinnedBuf::reserve(size_t need) {
+  if (need <= bytes) return;
+  size_t nb = std::max(need, bytes * 2);
+  if (p) VK_CUDA(cudaFreeHost(p));
+  p = nullptr;
+  bytes = 0;
+  VK_CUDA(cudaMallocHost(&p, nb));
+  bytes = nb;
+}
+void PinnedBuf::release() {
+  if (p) cudaFreeHost(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+// ------------------------------------------------------------------------------------------ contexts
+SearchCtx *vkgpu_index_impl::acquire_ctx() {
+  std::unique_lock<std::mutex> lk(ctx_mu);
+  for (;;) {
+    for (auto &c : ctxs)
+      if (!c->busy) {
+        c->busy = true;
+        return c.get();
+      }
+    if (ctxs.size() < 16) {
+      auto c = std::make_unique<SearchCtx>();
+      VK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      c->busy = true;
+      ctxs.push_back(std::move(c));
+      return ctxs.back().get();
+    }
+    ctx_cv.wait(lk);
+  }
+}
+void vkgpu_index_impl::release_ctx(SearchCtx *c) {
+  {
+    std::lock_guard<std::mutex> lk(ctx_mu);
+    c->busy = false;
+  }
+  ctx_cv.notify_one();
+}
+
+size_t vkgpu_index_impl::hbm_bytes() const {
+  size_t b = dX.bytes + dLabels.bytes + dXh.bytes + dNorm.bytes;
+  for (auto &c : ctxs)
+    b += c->q_pad.bytes + c->ws.bytes + c->ws_cnt.bytes + c->out_dist.bytes + c->out_labels.bytes +
+         c->out_n.bytes + c->out_slots.bytes + c->lists.bytes + c->list_off.bytes + c->scratch0.bytes +
+         c->scratch1.bytes + c->scratch2.bytes + c->scratch3.bytes;
+  if (hnsw) b += hnsw_hbm_bytes(hnsw);
+  return b;
+}
+
+// Logical capacity follows the reference: grow by block_size whenever full (vector_flat.cc:136-155,
+// vector_hnsw.cc:239-271).  Physical HBM grows geometrically so that growth copies stay amortised.
+void vkgpu_index_impl::ensure_rows(uint64_t need) {
+  const uint64_t block = cfg.block_size ? cfg.block_size : 10240;
+  while (capacity < need) capacity += block;
+  if (need <= phys_cap) return;
+  uint64_t np = std::max<uint64_t>(need, std::max<uint64_t>(capacity, phys_cap + phys_cap / 2));
+  dX.reserve(np * Dp * sizeof(float), true, mut_stream);
+  dLabels.reserve(np * sizeof(uint64_t), true, mut_stream);
+  if (tensor_ready) tensor_reserve(this, np);
+  if (hnsw) hnsw_reserve(this, np);
+  phys_cap = np;
+}
+
+static uint64_t now_ns() {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
+}
+
+static uint32_t next_pow2(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// ------------------------------------------------------------------------------------------ FLAT exact driver
+static constexpr uint32_t kMaxFusedK = 1024;
+
+void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff,
+                              const uint32_t *d_row_ids, const uint64_t *d_list_off, bool per_query_lists,
+                              uint64_t n_rows) {
+  VK_REQUIRE(k_eff >= 1 && k_eff <= kMaxFusedK, VKGPU_ERR_UNSUPPORTED,
+             "k > 1024 is not implemented on the fused top-k path yet");
+  int qt = per_query_lists ? 1 : (B == 1 ? 1 : B == 2 ? 2 : B <= 4 ? 4 : 8);
+  const uint32_t qtiles = (B + qt - 1) / qt;
+  const uint32_t cap = std::max<uint32_t>(256, next_pow2(k_eff + kScanTileRows));
+  const uint64_t max_rows = n_rows;  // for per-query lists this is the longest list
+  const uint32_t total_tiles = (uint32_t)std::max<uint64_t>(1, (max_rows + kScanTileRows - 1) / kScanTileRows);
+  uint32_t slabs;
+  if (qtiles == 1)
+    slabs = ix->num_sms;
+  else
+    slabs = (4 * ix->num_sms + qtiles - 1) / qtiles;
+  slabs = std::max<uint32_t>(1, std::min<uint32_t>(slabs, total_tiles));
+
+  const size_t stage_bytes = (size_t)(kScanTileRows + qt) * kScanRowBytes;
+  uint32_t stages = (uint32_t)std::min<size_t>(16, (ix->smem_max - (size_t)cap * sizeof(Cand) - 512) / stage_bytes);
+  VK_REQUIRE(stages >= 2, VKGPU_ERR_INTERNAL, "not enough shared memory for the scan pipeline");
+  const size_t smem = scan_smem_bytes(qt, cap, stages);
+
+  const size_t nlists = (size_t)qtiles * slabs * qt;
+  c->ws.reserve(nlists * cap * sizeof(Cand));
+  c->ws_cnt.reserve(nlists * sizeof(uint32_t));
+  c->out_dist.reserve((size_t)B * k_eff * sizeof(float));
+  c->out_labels.reserve((size_t)B * k_eff * sizeof(uint64_t));
+  c->out_slots.reserve((size_t)B * k_eff * sizeof(uint32_t));
+  c->out_n.reserve((size_t)B * sizeof(uint32_t));
+
+  ScanParams sp{};
+  sp.X = ix->dX.as<float>();
+  sp.labels = ix->dLabels.as<uint64_t>();
+  sp.row_ids = d_row_ids;
+  sp.list_off = d_list_off;
+  sp.n_rows = n_rows;
+  sp.Q = c->q_pad.as<float>();
+  sp.Dp = ix->Dp;
+  sp.k = k_eff;
+  sp.cap = cap;
+  sp.stages = stages;
+  sp.ws = c->ws.as<Cand>();
+  sp.ws_cnt = c->ws_cnt.as<uint32_t>();
+  launch_flat_scan(qt, ix->metric_l2, dim3(qtiles, slabs), smem, c->stream, sp);
+
+  MergeParams mp{};
+  mp.ws = sp.ws;
+  mp.ws_cnt = sp.ws_cnt;
+  mp.qt = qt;
+  mp.slabs = slabs;
+  mp.cap = cap;
+  mp.k = k_eff;
+  mp.sort_n = std::max<uint32_t>(512, next_pow2(2 * k_eff));
+  mp.out_dist = c->out_dist.as<float>();
+  mp.out_labels = c->out_labels.as<uint64_t>();
+  mp.out_slots = c->out_slots.as<uint32_t>();
+  mp.out_n = c->out_n.as<uint32_t>();
+  mp.k_limit = nullptr;
+  launch_topk_merge(B, c->stream, mp);
+  ix->kernels += 2;
+  ix->last_qt = qt;
+  ix->last_passes = qtiles;
+}
+
+// copy B host/device queries [B,dim] into the zero-padded device tile buffer [Bpad8][Dp]
+static void stage_queries(vkgpu_index_impl *ix, SearchCtx *c, const float *Q, uint32_t B, bool on_device) {
+  const uint32_t Bpad = (B + kScanMaxQt - 1) / kScanMaxQt * kScanMaxQt;
+  const size_t bytes = (size_t)Bpad * ix->Dp * sizeof(float);
+  c->q_pad.reserve(bytes);
+  if (ix->Dp != ix->dim || Bpad != B) VK_CUDA(cudaMemsetAsync(c->q_pad.p, 0, bytes, c->stream));
+  if (on_device) {
+    VK_CUDA(cudaMemcpy2DAsync(c->q_pad.p, (size_t)ix->Dp * 4, Q, (size_t)ix->dim * 4, (size_t)ix->dim * 4, B,
+                              cudaMemcpyDeviceToDevice, c->stream));
+  } else {
+    c->h_q.reserve((size_t)B * ix->dim * 4);
+    std::memcpy(c->h_q.p, Q, (size_t)B * ix->dim * 4);
+    VK_CUDA(cudaMemcpy2DAsync(c->q_pad.p, (size_t)ix->Dp * 4, c->h_q.p, (size_t)ix->dim * 4, (size_t)ix->dim * 4,
+                              B, cudaMemcpyHostToDevice, c->stream));
+  }
+}
+
+// results in c->out_* (device) -> caller's buffers
+static void fetch_results(SearchCtx *c, uint32_t B, uint32_t k_dev, uint32_t k_user, float *out_dist,
+                          uint64_t *out_labels, uint32_t *out_n) {
+  c->h_dist.reserve((size_t)B * k_dev * 4);
+  c->h_labels.reserve((size_t)B * k_dev * 8);
+  c->h_n.reserve((size_t)B * 4);
+  VK_CUDA(cudaMemcpyAsync(c->h_dist.p, c->out_dist.p, (size_t)B * k_dev * 4, cudaMemcpyDeviceToHost, c->stream));
+  VK_CUDA(cudaMemcpyAsync(c->h_labels.p, c->out_labels.p, (size_t)B * k_dev * 8, cudaMemcpyDeviceToHost, c->stream));
+  VK_CUDA(cudaMemcpyAsync(c->h_n.p, c->out_n.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
+  VK_CUDA(cudaStreamSynchronize(c->stream));
+  const float *hd = c->h_dist.as<float>();
+  const uint64_t *hl = c->h_labels.as<uint64_t>();
+  const uint32_t *hn = c->h_n.as<uint32_t>();
+  for (uint32_t b = 0; b < B; b++) {
+    const uint32_t n = std::min(hn[b], k_user);
+    std::memcpy(out_dist + (size_t)b * k_user, hd + (size_t)b * k_dev, n * sizeof(float));
+    std::memcpy(out_labels + (size_t)b * k_user, hl + (size_t)b * k_dev, n * sizeof(uint64_t));
+    out_n[b] = n;
+  }
+}
+
+// FLAT search over the whole shard (vector_flat.cc:224-254: k = min(k,count); empty index => empty reply)
+static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_t B, uint32_t k,
+                        const vkgpu_filter *filters, float *out_dist, uint64_t *out_labels, uint32_t *out_n,
+                        bool out_on_device, cudaStream_t user_stream) {
+  (void)user_stream;
+  if (ix->n == 0 || k == 0) {
+    if (out_on_device) {
+      VK_CUDA(cudaMemset(out_n, 0, (size_t)B * 4));
+    } else {
+      for (uint32_t b = 0; b < B; b++) out_n[b] = 0;
+    }
+    return;
+  }
+  CtxLease lease(ix);
+  SearchCtx *c = lease.c;
+  stage_queries(ix, c, Q, B, q_on_device);
+
+  uint32_t k_eff;
+  if (filters) {
+    // pre-filter path (VectorBase::AddPrefilteredKey, vector_base.cc:509-530): labels -> slots on the host
+    // (unknown labels skipped, vector_base.cc:513-516; duplicates collapse), one gather list per query.
+    VK_REQUIRE(!out_on_device, VKGPU_ERR_UNSUPPORTED, "filtered search needs host outputs");
+    std::vector<uint32_t> slots;
+    std::vector<uint64_t> off(B + 1, 0);
+    uint64_t longest = 0;
+    for (uint32_t b = 0; b < B; b++) {
+      const vkgpu_filter &f = filters[b];
+      size_t start = slots.size();
+      if (f.labels) {
+        for (uint64_t i = 0; i < f.n_labels; i++) {
+          auto it = ix->slot_of.find(f.labels[i]);
+          if (it != ix->slot_of.end()) slots.push_back(it->second);
+        }
+      } else if (f.label_bitmap) {
+        for (uint64_t s = 0; s < ix->n; s++) {
+          const uint64_t lab = ix->h_labels[s];
+          if (lab < f.bitmap_bits && ((f.label_bitmap[lab >> 3] >> (lab & 7)) & 1)) slots.push_back((uint32_t)s);
+        }
+      } else {
+        for (uint64_t s = 0; s < ix->n; s++) slots.push_back((uint32_t)s);
+      }
+      std::sort(slots.begin() + start, slots.end());
+      slots.erase(std::unique(slots.begin() + start, slots.end()), slots.end());
+      off[b + 1] = slots.size();
+      longest = std::max<uint64_t>(longest, slots.size() - start);
+    }
+    k_eff = (uint32_t)std::min<uint64_t>(k, std::max<uint64_t>(longest, 1));
+    const size_t slots_bytes = (slots.size() * 4 + 7) & ~size_t(7);
+    c->lists.reserve(std::max<size_t>(slots_bytes, 8));
+    c->list_off.reserve(off.size() * 8);
+    c->h_misc.reserve(slots_bytes + off.size() * 8);
+    uint8_t *off_host = c->h_misc.as<uint8_t>() + slots_bytes;
+    std::memcpy(c->h_misc.p, slots.data(), slots.size() * 4);
+    std::memcpy(off_host, off.data(), off.size() * 8);
+    if (!slots.empty())
+      VK_CUDA(cudaMemcpyAsync(c->lists.p, c->h_misc.p, slots.size() * 4, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->list_off.p, off_host, off.size() * 8, cudaMemcpyHostToDevice, c->stream));
+    flat_exact_search_device(ix, c, B, k_eff, c->lists.as<uint32_t>(), c->list_off.as<uint64_t>(), true, longest);
+  } else {
+    k_eff = (uint32_t)std::min<uint64_t>(k, ix->n);
+    bool use_tensor = false;
+    if (ix->flat_path == VKGPU_PATH_TENSOR) use_tensor = true;
+    if (ix->flat_path == VKGPU_PATH_AUTO) use_tensor = tensor_path_profitable(ix, B, k_eff);
+    if (use_tensor && tensor_path_supported(ix, B, k_eff))
+      tensor_search_device(ix, c, B, k_eff);
+    else
+      flat_exact_search_device(ix, c, B, k_eff, nullptr, nullptr, false, ix->n);
+  }
+
+  if (out_on_device) {
+    // [B][k_eff] -> caller's [B][k] device arrays
+    VK_CUDA(cudaMemcpy2DAsync(out_dist, (size_t)k * 4, c->out_dist.p, (size_t)k_eff * 4, (size_t)k_eff * 4, B,
+                              cudaMemcpyDeviceToDevice, c->stream));
+    VK_CUDA(cudaMemcpy2DAsync(out_labels, (size_t)k * 8, c->out_labels.p, (size_t)k_eff * 8, (size_t)k_eff * 8, B,
+                              cudaMemcpyDeviceToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(out_n, c->out_n.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, c->stream));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+  } else {
+    fetch_results(c, B, k_eff, k, out_dist, out_labels, out_n);
+  }
+  ix->searches += B;
+}
+
+// ------------------------------------------------------------------------------------------ ingest
+static void upload_rows(vkgpu_index_impl *ix, uint64_t first_slot, const float *vecs, uint64_t n, bool on_device) {
+  float *dst = ix->dX.as<float>() + first_slot * ix->Dp;
+  if (on_device) {
+    if (ix->Dp == ix->dim) {
+      VK_CUDA(cudaMemcpyAsync(dst, vecs, n * ix->dim * 4, cudaMemcpyDeviceToDevice, ix->mut_stream));
+    } else {
+      launch_pad_rows(vecs, ix->dim, dst, ix->Dp, n, ix->mut_stream);
+      ix->kernels++;
+    }
+  } else {
+    if (ix->Dp != ix->dim) VK_CUDA(cudaMemsetAsync(dst, 0, n * ix->Dp * 4, ix->mut_stream));
+    // pageable source: cudaMemcpy2DAsync stages internally; rows land at the padded stride
+    VK_CUDA(cudaMemcpy2DAsync(dst, (size_t)ix->Dp * 4, vecs, (size_t)ix->dim * 4, (size_t)ix->dim * 4, n,
+                              cudaMemcpyHostToDevice, ix->mut_stream));
+  }
+  if (ix->tensor_ready) tensor_refresh_rows(ix, first_slot, n);
+}
+
+static void flat_add_rows(vkgpu_index_impl *ix, const uint64_t *labels, const float *vecs, uint64_t n,
+                          bool on_device) {
+  // fast path: all labels new (bulk backfill); otherwise fall back to per-row upsert
+  bool all_new = true;
+  if (labels) {
+    for (uint64_t i = 0; i < n && all_new; i++) all_new = ix->slot_of.find(labels[i]) == ix->slot_of.end();
+    if (all_new && n > 1) {
+      std::vector<uint64_t> tmp(labels, labels + n);
+      std::sort(tmp.begin(), tmp.end());
+      all_new = std::adjacent_find(tmp.begin(), tmp.end()) == tmp.end();
+    }
+  }
+  VK_REQUIRE(ix->n + n < 0xffffffffull, VKGPU_ERR_UNSUPPORTED, "more than 2^32-1 rows per shard");
+  if (all_new) {
+    const uint64_t first = ix->n;
+    ix->ensure_rows(first + n);
+    upload_rows(ix, first, vecs, n, on_device);
+    ix->h_labels.resize(first + n);
+    if (labels) {
+      for (uint64_t i = 0; i < n; i++) {
+        ix->h_labels[first + i] = labels[i];
+        ix->slot_of.emplace(labels[i], (uint32_t)(first + i));
+      }
+      VK_CUDA(cudaMemcpyAsync(ix->dLabels.as<uint64_t>() + first, labels, n * 8, cudaMemcpyHostToDevice,
+                              ix->mut_stream));
+    } else {
+      // labels = first..first+n-1 (VectorBase::TrackKey hands out inc_id_++, vector_base.cc:340-358)
+      for (uint64_t i = 0; i < n; i++) {
+        VK_REQUIRE(ix->slot_of.find(first + i) == ix->slot_of.end(), VKGPU_ERR_EXISTS, "implicit label in use");
+        ix->h_labels[first + i] = first + i;
+        ix->slot_of.emplace(first + i, (uint32_t)(first + i));
+      }
+      launch_iota_labels(ix->dLabels.as<uint64_t>() + first, first, n, ix->mut_stream);
+      ix->kernels++;
+    }
+    ix->n = first + n;
+  } else {
+    VK_REQUIRE(labels != nullptr, VKGPU_ERR_INVALID, "labels required");
+    for (uint64_t i = 0; i < n; i++) {
+      auto it = ix->slot_of.find(labels[i]);
+      if (it != ix->slot_of.end()) {
+        // bruteforce.h:66-82: addPoint on a known label rewrites that slot in place
+        upload_rows(ix, it->second, vecs + i * ix->dim, 1, on_device);
+      } else {
+        flat_add_rows(ix, labels + i, vecs + i * ix->dim, 1, on_device);
+      }
+    }
+  }
+  VK_CUDA(cudaStreamSynchronize(ix->mut_stream));
+}
+
+// removePoint bruteforce.h:92-113: last slot moves into the hole
+static void flat_remove(vkgpu_index_impl *ix, uint64_t label) {
+  auto it = ix->slot_of.find(label);
+  if (it == ix->slot_of.end()) return;  // the reference returns silently
+  const uint32_t cur = it->second;
+  ix->slot_of.erase(it);
+  const uint64_t last = ix->n - 1;
+  if (cur != last) {
+    const uint64_t moved = ix->h_labels[last];
+    ix->slot_of[moved] = cur;
+    ix->h_labels[cur] = moved;
+    VK_CUDA(cudaMemcpyAsync(ix->dX.as<float>() + (size_t)cur * ix->Dp, ix->dX.as<float>() + last * ix->Dp,
+                            (size_t)ix->Dp * 4, cudaMemcpyDeviceToDevice, ix->mut_stream));
+    VK_CUDA(cudaMemcpyAsync(ix->dLabels.as<uint64_t>() + cur, ix->dLabels.as<uint64_t>() + last, 8,
+                            cudaMemcpyDeviceToDevice, ix->mut_stream));
+    if (ix->tensor_ready) tensor_move_row(ix, last, cur);
+    VK_CUDA(cudaStreamSynchronize(ix->mut_stream));
+  }
+  ix->h_labels.pop_back();
+  ix->n = last;
+}
+
+}  // namespace vkgpu
+
+// =============================================================================================== C-ABI
+using namespace vkgpu;
+
+extern "C" {
+
+int vkgpu_abi_version(void) { return VKGPU_ABI_VERSION; }
+
+int vkgpu_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+const char *vkgpu_last_error(void) { return g_last_error.c_str(); }
+
+int vkgpu_index_create(const vkgpu_config *cfg, vkgpu_index **out) {
+  if (out) *out = nullptr;
+  vkgpu_index *ix = nullptr;
+  int rc = guarded([&] {
+    VK_REQUIRE(cfg && out, VKGPU_ERR_INVALID, "null argument");
+    VK_REQUIRE(cfg->struct_size == sizeof(vkgpu_config), VKGPU_ERR_INVALID, "vkgpu_config size mismatch");
+    VK_REQUIRE(cfg->dim >= 1 && cfg->dim <= 64000, VKGPU_ERR_INVALID, "dim out of range");
+    VK_REQUIRE(cfg->algo == VKGPU_FLAT || cfg->algo == VKGPU_HNSW, VKGPU_ERR_INVALID, "bad algo");
+    VK_REQUIRE(cfg->metric >= VKGPU_L2 && cfg->metric <= VKGPU_COSINE, VKGPU_ERR_INVALID, "bad metric");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+      cudaGetLastError();
+      throw StatusError{VKGPU_ERR_CUDA, "no CUDA device: libvkgpu has no CPU fallback"};
+    }
+    VK_REQUIRE(cfg->device >= 0 && cfg->device < ndev, VKGPU_ERR_INVALID, "bad device ordinal");
+    VK_CUDA(cudaSetDevice(cfg->device));
+    cudaDeviceProp prop{};
+    VK_CUDA(cudaGetDeviceProperties(&prop, cfg->device));
+    VK_REQUIRE(prop.major == 10, VKGPU_ERR_CUDA, "libvkgpu is built for sm_100a (B200) only");
+    ix = new vkgpu_index();
+    ix->cfg = *cfg;
+    if (ix->cfg.block_size == 0) ix->cfg.block_size = 10240;
+    if (ix->cfg.max_batch == 0) ix->cfg.max_batch = 1024;
+    if (ix->cfg.m == 0) ix->cfg.m = 16;
+    if (ix->cfg.ef_construction == 0) ix->cfg.ef_construction = 200;
+    if (ix->cfg.ef_runtime == 0) ix->cfg.ef_runtime = 10;
+    ix->device = cfg->device;
+    ix->num_sms = prop.multiProcessorCount;
+    ix->smem_max = prop.sharedMemPerBlockOptin;
+    ix->dim = cfg->dim;
+    ix->Dp = (cfg->dim + 15) / 16 * 16;
+    ix->metric_l2 = cfg->metric == VKGPU_L2;
+    VK_CUDA(cudaStreamCreateWithFlags(&ix->mut_stream, cudaStreamNonBlocking));
+    flat_scan_set_smem_attr(ix->smem_max);
+    ix->capacity = cfg->initial_cap;
+    if (cfg->algo == VKGPU_HNSW) hnsw_create(ix);
+    if (cfg->initial_cap) {
+      ix->capacity = 0;
+      // allocate exactly initial_cap rows up front (reference: max_elements = initial_cap)
+      const uint64_t want = cfg->initial_cap;
+      ix->dX.reserve(want * ix->Dp * sizeof(float));
+      ix->dLabels.reserve(want * sizeof(uint64_t));
+      ix->phys_cap = want;
+      ix->capacity = want;
+      if (ix->hnsw) hnsw_reserve(ix, want);
+    }
+    *out = ix;
+  });
+  if (rc != VKGPU_OK && ix) {
+    vkgpu_index_destroy(ix);
+    if (out) *out = nullptr;
+  }
+  return rc;
+}
+
+void vkgpu_index_destroy(vkgpu_index *ix) {
+  if (!ix) return;
+  cudaSetDevice(ix->device);
+  cudaDeviceSynchronize();
+  if (ix->hnsw) hnsw_destroy(ix);
+  tensor_release(ix);
+  for (auto &c : ix->ctxs) {
+    if (c->stream) cudaStreamDestroy(c->stream);
+    for (DevBuf *b : {&c->q_pad, &c->ws, &c->ws_cnt, &c->out_dist, &c->out_labels, &c->out_n, &c->out_slots,
+                      &c->lists, &c->list_off, &c->klimit, &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3})
+      b->release();
+    for (PinnedBuf *b : {&c->h_q, &c->h_dist, &c->h_labels, &c->h_n, &c->h_misc}) b->release();
+  }
+  ix->dX.release();
+  ix->dLabels.release();
+  ix->h_stage.release();
+  if (ix->mut_stream) cudaStreamDestroy(ix->mut_stream);
+  delete ix;
+}
+
+int vkgpu_add_batch(vkgpu_index *ix, const uint64_t *labels, const float *vecs, uint64_t n) {
+  return guarded([&] {
+    VK_REQUIRE(ix && vecs, VKGPU_ERR_INVALID, "null argument");
+    if (n == 0) return;
+    std::unique_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    if (ix->cfg.algo == VKGPU_FLAT)
+      flat_add_rows(ix, labels, vecs, n, false);
+    else
+      hnsw_add_rows(ix, labels, vecs, n, false);
+  });
+}
+
+int vkgpu_add_batch_device(vkgpu_index *ix, const uint64_t *labels, const float *d_vecs, uint64_t n) {
+  return guarded([&] {
+    VK_REQUIRE(ix && d_vecs, VKGPU_ERR_INVALID, "null argument");
+    if (n == 0) return;
+    std::unique_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    if (ix->cfg.algo == VKGPU_FLAT)
+      flat_add_rows(ix, labels, d_vecs, n, true);
+    else
+      hnsw_add_rows(ix, labels, d_vecs, n, true);
+  });
+}
+
+int vkgpu_add(vkgpu_index *ix, uint64_t label, const float *vec) { return vkgpu_add_batch(ix, &label, vec, 1); }
+
+int vkgpu_modify(vkgpu_index *ix, uint64_t label, const float *vec) {
+  return guarded([&] {
+    VK_REQUIRE(ix && vec, VKGPU_ERR_INVALID, "null argument");
+    std::unique_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    // vector_flat.cc:181-198 / vector_hnsw.cc:201-236: unknown id => InternalError "Couldn't find internal id"
+    VK_REQUIRE(ix->slot_of.count(label), VKGPU_ERR_NOT_FOUND, "Couldn't find internal id: " + std::to_string(label));
+    if (ix->cfg.algo == VKGPU_FLAT)
+      flat_add_rows(ix, &label, vec, 1, false);
+    else
+      hnsw_modify(ix, label, vec);
+  });
+}
+
+int vkgpu_remove(vkgpu_index *ix, uint64_t label) {
+  return guarded([&] {
+    VK_REQUIRE(ix, VKGPU_ERR_INVALID, "null argument");
+    std::unique_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    if (ix->cfg.algo == VKGPU_FLAT)
+      flat_remove(ix, label);
+    else
+      hnsw_remove(ix, label);
+  });
+}
+
+int vkgpu_get(vkgpu_index *ix, uint64_t label, float *out_vec) {
+  return guarded([&] {
+    VK_REQUIRE(ix && out_vec, VKGPU_ERR_INVALID, "null argument");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    auto it = ix->slot_of.find(label);
+    VK_REQUIRE(it != ix->slot_of.end(), VKGPU_ERR_NOT_FOUND, "unknown label");
+    VK_CUDA(cudaMemcpy(out_vec, ix->dX.as<float>() + (size_t)it->second * ix->Dp, (size_t)ix->dim * 4,
+                       cudaMemcpyDeviceToHost));
+  });
+}
+
+int vkgpu_search_batch(vkgpu_index *ix, const float *Q, uint32_t B, uint32_t k, uint32_t ef,
+                       const vkgpu_filter *filters, uint64_t deadline_ns, float *out_dist, uint64_t *out_labels,
+                       uint32_t *out_n) {
+  return guarded([&] {
+    VK_REQUIRE(ix && Q && out_dist && out_labels && out_n, VKGPU_ERR_INVALID, "null argument");
+    VK_REQUIRE(B >= 1, VKGPU_ERR_INVALID, "empty batch");
+    // cancel::Token analog: the reference polls per row/hop (bruteforce.h:129, hnswalg.h:400); a GPU
+    // launch is milliseconds, so the deadline is checked at the launch boundary.
+    VK_REQUIRE(deadline_ns == 0 || now_ns() < deadline_ns, VKGPU_ERR_CANCELLED, "Search operation cancelled due to timeout");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    if (ix->cfg.algo == VKGPU_FLAT)
+      flat_search(ix, Q, false, B, k, filters, out_dist, out_labels, out_n, false, nullptr);
+    else
+      hnsw_search(ix, Q, false, B, k, ef, filters, out_dist, out_labels, out_n, false);
+    VK_REQUIRE(deadline_ns == 0 || now_ns() < deadline_ns, VKGPU_ERR_CANCELLED, "Search operation cancelled due to timeout");
+  });
+}
+
+int vkgpu_search(vkgpu_index *ix, const float *q, uint32_t k, uint32_t ef, const vkgpu_filter *filter,
+                 uint64_t deadline_ns, float *out_dist, uint64_t *out_labels, uint32_t *out_n) {
+  return vkgpu_search_batch(ix, q, 1, k, ef, filter, deadline_ns, out_dist, out_labels, out_n);
+}
+
+int vkgpu_search_batch_device(vkgpu_index *ix, const float *d_Q, uint32_t B, uint32_t k, uint32_t ef,
+                              float *d_out_dist, uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream) {
+  return guarded([&] {
+    VK_REQUIRE(ix && d_Q && d_out_dist && d_out_labels && d_out_n, VKGPU_ERR_INVALID, "null argument");
+    VK_REQUIRE(B >= 1, VKGPU_ERR_INVALID, "empty batch");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    if (cuda_stream) VK_CUDA(cudaStreamSynchronize((cudaStream_t)cuda_stream));  // inputs produced on it
+    if (ix->cfg.algo == VKGPU_FLAT)
+      flat_search(ix, d_Q, true, B, k, nullptr, d_out_dist, d_out_labels, d_out_n, true, (cudaStream_t)cuda_stream);
+    else
+      hnsw_search(ix, d_Q, true, B, k, ef, nullptr, d_out_dist, d_out_labels, d_out_n, true);
+  });
+}
+
+int vkgpu_distances(vkgpu_index *ix, const float *q, const uint64_t *labels, uint64_t n, float *out) {
+  return guarded([&] {
+    VK_REQUIRE(ix && q && (labels || n == 0) && (out || n == 0), VKGPU_ERR_INVALID, "null argument");
+    if (n == 0) return;
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    CtxLease lease(ix);
+    SearchCtx *c = lease.c;
+    stage_queries(ix, c, q, 1, false);
+    c->h_misc.reserve(n * 4);
+    uint32_t *hs = c->h_misc.as<uint32_t>();
+    for (uint64_t i = 0; i < n; i++) {
+      auto it = ix->slot_of.find(labels[i]);
+      hs[i] = it == ix->slot_of.end() ? 0xffffffffu : it->second;
+    }
+    c->lists.reserve(n * 4);
+    c->out_dist.reserve(n * 4);
+    VK_CUDA(cudaMemcpyAsync(c->lists.p, hs, n * 4, cudaMemcpyHostToDevice, c->stream));
+    launch_exact_distances(ix->dX.as<float>(), ix->Dp, ix->metric_l2, c->q_pad.as<float>(), c->lists.as<uint32_t>(),
+                           n, c->out_dist.as<float>(), c->stream);
+    ix->kernels++;
+    VK_CUDA(cudaMemcpyAsync(out, c->out_dist.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
+    VK_CUDA(cudaStreamSynchronize(c->stream));
+  });
+}
+
+int vkgpu_merge_topk_device(int device, const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
+                            uint32_t G, uint32_t B, uint32_t k, float *d_out_dist, uint64_t *d_out_labels,
+                            uint32_t *d_out_n, void *cuda_stream) {
+  return guarded([&] {
+    VK_REQUIRE(d_dist && d_labels && d_n && d_out_dist && d_out_labels && d_out_n, VKGPU_ERR_INVALID, "null argument");
+    VK_REQUIRE(G >= 1 && B >= 1 && k >= 1 && k <= kMaxFusedK, VKGPU_ERR_INVALID, "bad merge shape");
+    VK_CUDA(cudaSetDevice(device));
+    cudaStream_t s = (cudaStream_t)cuda_stream;
+    // per-process scratch, grown on demand (one process per GPU)
+    static DevBuf ws, ws_cnt;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lk(mu);
+    ws.reserve((size_t)G * B * k * sizeof(Cand));
+    ws_cnt.reserve((size_t)G * B * 4);
+    launch_pack_shard_results(d_dist, d_labels, d_n, G, B, k, ws.as<Cand>(), ws_cnt.as<uint32_t>(), s);
+    MergeParams mp{};
+    mp.ws = ws.as<Cand>();
+    mp.ws_cnt = ws_cnt.as<uint32_t>();
+    mp.qt = 1;
+    mp.slabs = G;
+    mp.cap = k;
+    mp.k = k;
+    mp.sort_n = std::max<uint32_t>(512, next_pow2(2 * k));
+    mp.out_dist = d_out_dist;
+    mp.out_labels = d_out_labels;
+    mp.out_slots = nullptr;
+    mp.out_n = d_out_n;
+    launch_topk_merge(B, s, mp);
+    VK_CUDA(cudaStreamSynchronize(s));
+  });
+}
+
+int vkgpu_get_stats(vkgpu_index *ix, vkgpu_stats *out) {
+  return guarded([&] {
+    VK_REQUIRE(ix && out, VKGPU_ERR_INVALID, "null argument");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    std::memset(out, 0, sizeof(*out));
+    out->count = ix->cfg.algo == VKGPU_FLAT ? ix->n : hnsw_live_count(ix);
+    out->capacity = ix->capacity;
+    out->deleted = ix->hnsw ? hnsw_deleted_count(ix) : 0;
+    out->hbm_bytes = ix->hbm_bytes();
+    out->searches = ix->searches;
+    out->kernels_launched = ix->kernels;
+    out->distance_evals = ix->dist_evals;
+    out->hops = ix->hops;
+    out->tensor_fallbacks = ix->tensor_fallbacks;
+    out->max_level = ix->hnsw ? hnsw_max_level(ix) : 0;
+    out->dim = (int32_t)ix->dim;
+    out->last_qt = ix->last_qt;
+    out->last_passes = ix->last_passes;
+  });
+}
+
+int vkgpu_set_flat_path(vkgpu_index *ix, int path) {
+  return guarded([&] {
+    VK_REQUIRE(ix, VKGPU_ERR_INVALID, "null argument");
+    VK_REQUIRE(path >= VKGPU_PATH_AUTO && path <= VKGPU_PATH_TENSOR, VKGPU_ERR_INVALID, "bad path");
+    std::unique_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    if (path == VKGPU_PATH_TENSOR) {
+      VK_REQUIRE(ix->cfg.algo == VKGPU_FLAT, VKGPU_ERR_INVALID, "tensor path is FLAT only");
+      tensor_prepare(ix);
+    }
+    ix->flat_path = path;
+  });
+}
+
+int vkgpu_device_corpus(vkgpu_index *ix, const float **d_rows, uint64_t *row_stride, uint64_t *n_rows) {
+  return guarded([&] {
+    VK_REQUIRE(ix && d_rows && row_stride && n_rows, VKGPU_ERR_INVALID, "null argument");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    *d_rows = ix->dX.as<float>();
+    *row_stride = ix->Dp;
+    *n_rows = ix->n;
+  });
+}
+
+int vkgpu_hnsw_import(vkgpu_index *ix, uint64_t n, const int32_t *levels, const uint64_t *labels,
+                      const uint8_t *deleted, const uint32_t *links0, const uint32_t *cnt0,
+                      const uint32_t *upper_links, const uint32_t *upper_cnt, const uint64_t *upper_offset,
+                      int32_t max_level, uint32_t enterpoint, const float *vecs) {
+  return guarded([&] {
+    VK_REQUIRE(ix && ix->hnsw, VKGPU_ERR_INVALID, "not an HNSW index");
+    std::unique_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    hnsw_import(ix, n, levels, labels, deleted, links0, cnt0, upper_links, upper_cnt, upper_offset, max_level,
+                enterpoint, vecs);
+  });
+}
+
+int vkgpu_hnsw_export(vkgpu_index *ix, uint64_t *n, uint64_t *upper_blocks, int32_t *levels, uint64_t *labels,
+                      uint8_t *deleted, uint32_t *links0, uint32_t *cnt0, uint32_t *upper_links,
+                      uint32_t *upper_cnt, uint64_t *upper_offset, int32_t *max_level, uint32_t *enterpoint) {
+  return guarded([&] {
+    VK_REQUIRE(ix && ix->hnsw && n && upper_blocks, VKGPU_ERR_INVALID, "not an HNSW index");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    hnsw_export(ix, n, upper_blocks, levels, labels, deleted, links0, cnt0, upper_links, upper_cnt, upper_offset,
+                max_level, enterpoint);
+  });
+}
+
+}  // extern "C"

@@ -1,0 +1,126 @@
+// Host-side state behind a vkgpu_index handle (internal to libvkgpu).
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/vkgpu.h"
+#include "common.cuh"
+#include "flat_scan.cuh"
+
+namespace vkgpu {
+
+struct StatusError {
+  int code;
+  std::string msg;
+};
+
+// Device buffer that only ever grows; contents are NOT preserved across a grow unless asked.
+struct DevBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  void reserve(size_t need, bool keep = false, cudaStream_t s = nullptr);
+  void release();
+  template <typename T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+struct PinnedBuf {
+  void *p = nullptr;
+  size_t bytes = 0;
+  void reserve(size_t need);
+  void release();
+  template <typename T>
+  T *as() const {
+    return reinterpret_cast<T *>(p);
+  }
+};
+
+// Everything one in-flight search needs; searches on different contexts run concurrently.
+struct SearchCtx {
+  cudaStream_t stream = nullptr;
+  DevBuf q_pad;      // zero-padded queries [Bpad][Dp]
+  DevBuf ws;         // candidate lists
+  DevBuf ws_cnt;
+  DevBuf out_dist, out_labels, out_n, out_slots;
+  DevBuf lists, list_off;  // gather lists (pre-filter)
+  DevBuf klimit;
+  DevBuf scratch0, scratch1, scratch2, scratch3;  // path-specific (tensor / hnsw)
+  PinnedBuf h_q, h_dist, h_labels, h_n, h_misc;
+  bool busy = false;
+};
+
+struct vkgpu_index_impl {
+  vkgpu_config cfg{};
+  int device = 0;
+  int num_sms = 148;
+  size_t smem_max = 0;
+  uint32_t dim = 0, Dp = 0;
+  bool metric_l2 = true;
+  int flat_path = VKGPU_PATH_AUTO;
+
+  // ---- corpus (both algos): slot-major rows in HBM
+  DevBuf dX;       // [phys_cap][Dp] fp32
+  DevBuf dLabels;  // [phys_cap] u64
+  uint64_t n = 0;          // live slots (FLAT) / allocated node ids (HNSW)
+  uint64_t capacity = 0;   // logical capacity as the reference reports it (initial_cap + j*block)
+  uint64_t phys_cap = 0;   // rows physically allocated
+  std::vector<uint64_t> h_labels;                   // slot -> label
+  std::unordered_map<uint64_t, uint32_t> slot_of;   // label -> slot
+
+  // ---- tensor path side data (bf16 mirror + row norms), maintained on ingest
+  DevBuf dXh;      // [phys_cap][Dp] bf16
+  DevBuf dNorm;    // [phys_cap] fp32 squared norms (of the bf16-rounded rows)
+  bool tensor_ready = false;
+
+  // ---- HNSW graph (device) + host mirror of the small per-node state
+  struct Hnsw *hnsw = nullptr;
+
+  std::shared_mutex rw;  // searches shared, mutations exclusive
+  std::mutex ctx_mu;
+  std::condition_variable ctx_cv;
+  std::vector<std::unique_ptr<SearchCtx>> ctxs;
+  cudaStream_t mut_stream = nullptr;
+  PinnedBuf h_stage;  // staging for single-row uploads
+
+  std::atomic<uint64_t> searches{0}, kernels{0}, dist_evals{0}, hops{0}, tensor_fallbacks{0};
+  std::atomic<uint32_t> last_qt{0}, last_passes{0};
+
+  SearchCtx *acquire_ctx();
+  void release_ctx(SearchCtx *c);
+  void ensure_rows(uint64_t need_rows);  // grows logical + physical capacity
+  size_t hbm_bytes() const;
+};
+
+// RAII context lease
+struct CtxLease {
+  vkgpu_index_impl *ix;
+  SearchCtx *c;
+  explicit CtxLease(vkgpu_index_impl *i) : ix(i), c(i->acquire_ctx()) {}
+  ~CtxLease() { ix->release_ctx(c); }
+};
+
+// ---- FLAT search drivers (flat_host.cu)
+// Runs the exact scan + merge for B padded queries already in c->q_pad; leaves results in c->out_*.
+void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff,
+                              const uint32_t *d_row_ids, const uint64_t *d_list_off, bool per_query_lists,
+                              uint64_t n_rows);
+
+// ---- small kernels (misc_kernels.cu)
+void launch_exact_distances(const float *X, uint32_t Dp, bool l2, const float *q_pad, const uint32_t *slots,
+                            uint64_t n, float *out, cudaStream_t s);
+void launch_pad_rows(const float *src, uint32_t dim, float *dst, uint32_t Dp, uint64_t n, cudaStream_t s);
+void launch_iota_labels(uint64_t *dst, uint64_t start, uint64_t n, cudaStream_t s);
+void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n, uint32_t G,
+                               uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt, cudaStream_t s);
+
+}  // namespace vkgpu
+
+struct vkgpu_index : public vkgpu::vkgpu_index_impl {};

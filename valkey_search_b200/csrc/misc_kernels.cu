@@ -1,0 +1,92 @@
+// Small support kernels: exact per-row distances, row padding on ingest, label iota, shard-result packing.
+#include "exact_dist.cuh"
+#include "index.h"
+
+namespace vkgpu {
+
+namespace {
+
+// ComputeDistanceFromRecordImpl (src/indexes/vector_flat.cc:257-271, vector_hnsw.cc:370-383): one exact
+// distance per listed slot.  4 threads per row, 8 rows per warp; slot 0xffffffff => NaN (unknown label).
+template <bool L2>
+__global__ void __launch_bounds__(256) exact_distances_kernel(const float *__restrict__ X, uint32_t Dp,
+                                                              const float *__restrict__ q,
+                                                              const uint32_t *__restrict__ slots, uint64_t n,
+                                                              float *__restrict__ out) {
+  const uint64_t grp = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 2;
+  const uint32_t u = threadIdx.x & 3;
+  const bool valid = grp < n;
+  const uint32_t slot = valid ? slots[grp] : 0xffffffffu;
+  const bool known = slot != 0xffffffffu;
+  const float *row = X + (size_t)(known ? slot : 0) * Dp;
+  float d = exact_dist_group<L2>(row, q, Dp, u, known);
+  if (valid && u == 0) out[grp] = known ? d : __int_as_float(0x7fc00000);
+}
+
+__global__ void pad_rows_kernel(const float *__restrict__ src, uint32_t dim, float *__restrict__ dst, uint32_t Dp,
+                                uint64_t n) {
+  const uint64_t total = n * Dp;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t r = i / Dp;
+    const uint32_t c = (uint32_t)(i - r * Dp);
+    dst[i] = c < dim ? src[r * dim + c] : 0.0f;
+  }
+}
+
+__global__ void iota_kernel(uint64_t *dst, uint64_t start, uint64_t n) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    dst[i] = start + i;
+}
+
+// [G][B][k] (dist,label) + [G][B] counts  ->  candidate lists ws[b][g][k] / ws_cnt[b][g]   (qt = 1 layout)
+__global__ void pack_shard_results_kernel(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
+                                          uint32_t G, uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt) {
+  const uint64_t total = (uint64_t)G * B * k;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t j = (uint32_t)(i % k);
+    const uint64_t gb = i / k;
+    const uint32_t b = (uint32_t)(gb % B), g = (uint32_t)(gb / B);
+    Cand c;
+    c.ord = f32_to_ord(d_dist[i]);
+    c.slot = g;
+    c.label = d_labels[i];
+    ws[((size_t)b * G + g) * k + j] = c;
+    if (j == 0) ws_cnt[(size_t)b * G + g] = min(d_n[gb], k);
+  }
+}
+
+}  // namespace
+
+void launch_exact_distances(const float *X, uint32_t Dp, bool l2, const float *q_pad, const uint32_t *slots,
+                            uint64_t n, float *out, cudaStream_t s) {
+  if (n == 0) return;
+  const uint64_t threads = n * 4;
+  const uint32_t blocks = (uint32_t)((threads + 255) / 256);
+  if (l2)
+    exact_distances_kernel<true><<<blocks, 256, 0, s>>>(X, Dp, q_pad, slots, n, out);
+  else
+    exact_distances_kernel<false><<<blocks, 256, 0, s>>>(X, Dp, q_pad, slots, n, out);
+  VK_CUDA(cudaGetLastError());
+}
+
+void launch_pad_rows(const float *src, uint32_t dim, float *dst, uint32_t Dp, uint64_t n, cudaStream_t s) {
+  if (n == 0) return;
+  pad_rows_kernel<<<1184, 256, 0, s>>>(src, dim, dst, Dp, n);
+  VK_CUDA(cudaGetLastError());
+}
+
+void launch_iota_labels(uint64_t *dst, uint64_t start, uint64_t n, cudaStream_t s) {
+  if (n == 0) return;
+  iota_kernel<<<296, 256, 0, s>>>(dst, start, n);
+  VK_CUDA(cudaGetLastError());
+}
+
+void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n, uint32_t G,
+                               uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt, cudaStream_t s) {
+  pack_shard_results_kernel<<<296, 256, 0, s>>>(d_dist, d_labels, d_n, G, B, k, ws, ws_cnt);
+  VK_CUDA(cudaGetLastError());
+}
+
+}  // namespace vkgpu

@@ -1,0 +1,17 @@
+// FLAT batched search on the tensor cores: tcgen05 candidate pass over a bf16 mirror of the corpus +
+// exact re-rank in the reference's fp32 order (tensor_path.cu).
+#pragma once
+#include "index.h"
+
+namespace vkgpu {
+
+bool tensor_path_profitable(const vkgpu_index_impl *ix, uint32_t B, uint32_t k);
+bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k);
+void tensor_prepare(vkgpu_index_impl *ix);                       // build the bf16 mirror + norms
+void tensor_reserve(vkgpu_index_impl *ix, uint64_t rows);        // grow mirror with the corpus
+void tensor_refresh_rows(vkgpu_index_impl *ix, uint64_t first, uint64_t n);  // after uploads
+void tensor_move_row(vkgpu_index_impl *ix, uint64_t from, uint64_t to);      // FLAT swap-delete
+void tensor_release(vkgpu_index_impl *ix);
+void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff);
+
+}  // namespace vkgpu
