@@ -1,0 +1,382 @@
+#!/usr/bin/env python
+"""bench.py — kNN QPS on BASELINE.json's headline configuration, one JSON line on stdout.
+
+Workload (configs[1]): FLAT brute-force kNN, 10M x 768 fp32, k=100, batch=1024, L2 — one "step" is one batch
+of 1024 queries answered against the whole corpus.  With --gpus N the same 10M-row corpus is row-sharded over
+N ranks (strong scaling), each rank answers every query on its rows, and the per-rank top-k lists are merged
+after one NCCL all-gather.
+
+  value        QPS with queries and results resident in HBM (CUDA events, max over ranks)
+  e2e          QPS through the host-buffer C-ABI call (vkgpu_search_batch): H2D of the queries and D2H of the
+               results inside the timed region
+  roofline     for the dominant kernel, from CUDA events recorded inside the library on the launching stream
+  cpu_baseline the reference's own CPU implementation (oracle/_ref when built, else the C port) timed on this
+               box's host cores on a bounded sample
+  --impl reference   times only that CPU arm
+
+Synthetic data: N(0,1) fp32 generated on the device with torch (seed 1234 + 1M-row block index; queries seed
+4321); there is no dataset on the box.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "kNN QPS @ recall (10M x 768 fp32, k=100) FLAT batch=1024; % HBM roofline"
+UNIT = "queries/s"
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"),
+                    source="measured")
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception as e:  # pragma: no cover
+            log("clock sampler unavailable:", e)
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return None
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_reference_arm(X_sample, Q, k, n_total, threads, nq):
+    """Times the reference's CPU FLAT search (its own hnswlib+simsimd if oracle/_ref was built, else the C
+    port) on `X_sample` with `threads` host threads, one query per thread at a time (the module's model,
+    src/query/search.cc:886-910), and scales QPS linearly to n_total rows."""
+    import numpy as np
+    import oracle_lib as O
+
+    ref = O.ref()
+    kind = "reference" if ref is not None else "port"
+    S, D = X_sample.shape
+    if ref is not None:
+        ix = O.RefFlat(D, O.L2, initial_cap=S)
+        info = f"simsimd skylake={ref.vkref_uses_skylake()} haswell={ref.vkref_uses_haswell()}"
+    else:
+        ix = O.PortFlat(D, O.L2)
+        info = "C port"
+    t0 = time.perf_counter()
+    ix.add_many(X_sample)
+    log(f"[cpu arm] {kind} ({info}): indexed {S} rows in {time.perf_counter() - t0:.1f}s")
+    Qs = np.ascontiguousarray(Q[:nq])
+    secs, d, l, n = ix.search_mt(Qs, k, threads)
+    qps_sample = nq / secs
+    qps_full = qps_sample * (S / float(n_total))
+    sample = (f"{nq} queries x {S} rows x {D} dims, k={k}, {threads} threads, {secs:.2f}s wall; "
+              f"QPS scaled linearly by {S}/{n_total} rows ({info})")
+    return dict(value=qps_full, unit=UNIT, cores=threads, kind=kind, sample=sample), secs, (d, l, n)
+
+
+def gen_block(torch, dev, block, rows, D):
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + block)
+    return torch.randn((rows, D), generator=g, device=dev, dtype=torch.float32)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--dim", type=int, default=768)
+    ap.add_argument("--k", type=int, default=100)
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--path", default="auto", choices=["auto", "exact", "tensor"])
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--cpu-queries", type=int, default=64)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    import numpy as np
+    import torch
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    N, D, k, B = args.rows, args.dim, args.k, args.batch
+    W = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    K = args.steps
+    cfg = {"workload": f"FLAT brute-force kNN {N}x{D} fp32 L2, k={k}, batch={B} (BASELINE configs[1])",
+           "rows": N, "dim": D, "k": k, "batch": B,
+           "l2_flush": "inputs larger than L2: every step streams the corpus shard (>= 3.8 GB) from HBM"}
+
+    # ------------------------------------------------------------------ reference arm (CPU only)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = host_threads()
+        S = min(args.cpu_sample_rows, N)
+        if torch.cuda.is_available():
+            dev = torch.device("cuda", local_rank)
+            Xs = gen_block(torch, dev, 0, S, D).cpu().numpy()
+            g = torch.Generator(device=dev)
+            g.manual_seed(4321)
+            Q = torch.randn((B, D), generator=g, device=dev, dtype=torch.float32).cpu().numpy()
+        else:
+            rng = np.random.default_rng(1234)
+            Xs = rng.standard_normal((S, D), dtype=np.float32)
+            Q = np.random.default_rng(4321).standard_normal((B, D), dtype=np.float32)
+        nq = max(threads, min(args.cpu_queries, B))
+        import oracle_lib as O
+        ref = O.ref()
+        ix = O.RefFlat(D, O.L2, initial_cap=S) if ref is not None else O.PortFlat(D, O.L2)
+        kind = "reference" if ref is not None else "port"
+        ix.add_many(Xs)
+        Qs = np.ascontiguousarray(Q[:nq])
+        times = []
+        for it in range(W + K):
+            secs, _, _, _ = ix.search_mt(Qs, k, threads)
+            if it >= W:
+                times.append(secs)
+        total = sum(times)
+        qps = (nq * K / total) * (S / float(N))
+        sample = (f"each step = {nq} queries x {S} rows x {D} dims, k={k}, {threads} host threads "
+                  f"(one query per thread at a time); QPS scaled linearly by {S}/{N} rows")
+        line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
+                "warmup": W, "ms_per_step": 1000.0 * total / K, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic N(0,1)", "config": cfg,
+                "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+                "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    # ------------------------------------------------------------------ our arm
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    import valkey_search_b200 as V
+    from valkey_search_b200 import _lib as L
+    from valkey_search_b200.sharded import ShardedFlat, shard_bounds
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    peaks = load_peaks()
+
+    lo, hi = shard_bounds(N, world, rank)
+    n_local = hi - lo
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=n_local, max_batch=B)
+    lib = L.lib()
+    t0 = time.perf_counter()
+    BLK = 1_000_000
+    X_sample = None
+    S = min(args.cpu_sample_rows, N)
+    for blk in range(lo // BLK, (hi + BLK - 1) // BLK):
+        b_lo, b_hi = blk * BLK, min((blk + 1) * BLK, N)
+        Xb = gen_block(torch, dev, blk, b_hi - b_lo, D)
+        if blk == 0 and rank == 0 and not args.no_cpu_baseline:
+            X_sample = Xb[:S].cpu().numpy()
+        s_lo, s_hi = max(lo, b_lo), min(hi, b_hi)
+        part = Xb[s_lo - b_lo: s_hi - b_lo].contiguous()
+        labels = np.arange(s_lo, s_hi, dtype=np.uint64)
+        torch.cuda.synchronize()
+        L.check(lib.vkgpu_add_batch_device(ix.handle(), labels.ctypes.data, part.data_ptr(), s_hi - s_lo))
+        del Xb, part
+    torch.cuda.synchronize()
+    log(f"[rank {rank}] corpus rows [{lo},{hi}) resident in HBM after {time.perf_counter() - t0:.1f}s")
+    if args.path != "auto":
+        ix.SetSearchPath({"exact": V.PATH_EXACT_FMA, "tensor": V.PATH_TENSOR}[args.path])
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321)
+    dQ = torch.randn((B, D), generator=g, device=dev, dtype=torch.float32)
+    hQ = dQ.cpu().numpy()
+    sh = ShardedFlat(ix, dist, dev)
+    out = sh.alloc_out(B, k, dev)
+    stream = torch.cuda.current_stream()
+    sptr = stream.cuda_stream
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up steps, then exactly K timed steps
+    for _ in range(W):
+        sh.search_device(dQ, k, sptr, out)
+    barrier()
+    L.check(lib.vkgpu_set_profiling(ix.handle(), 1))
+    k0 = ix.stats().kernels_launched
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for _ in range(K):
+        res = sh.search_device(dQ, k, sptr, out)
+    e1.record(stream)
+    barrier()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    tm = L.Timings()
+    L.check(lib.vkgpu_get_timings(ix.handle(), C.byref(tm)))
+    L.check(lib.vkgpu_set_profiling(ix.handle(), 0))
+    st = ix.stats()
+    launches = st.kernels_launched - k0 + (K if world > 1 else 0) * 2  # + pack/merge of the shard merge
+    t = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / K
+    value = B * K / (ms_total / 1e3)
+
+    # ---- end to end through the host-buffer C-ABI (every rank answers on its shard; merge on the host)
+    out_d = np.empty((B, k), np.float32)
+    out_l = np.empty((B, k), np.uint64)
+    out_n = np.empty(B, np.uint32)
+
+    def e2e_step():
+        L.check(lib.vkgpu_search_batch(ix.handle(), hQ.ctypes.data, B, k, 0, None, 0, out_d.ctypes.data,
+                                       out_l.ctypes.data, out_n.ctypes.data))
+        if world > 1:
+            td = torch.from_numpy(out_d).to(dev)
+            tl = torch.from_numpy(out_l.view(np.int64)).to(dev)
+            tn = torch.from_numpy(out_n.view(np.int32)).to(dev)
+            dist.all_gather_into_tensor(out[3], td)
+            dist.all_gather_into_tensor(out[4], tl)
+            dist.all_gather_into_tensor(out[5], tn)
+            L.check(lib.vkgpu_merge_topk_device(dev.index, out[3].data_ptr(), out[4].data_ptr(), out[5].data_ptr(),
+                                                world, B, k, out[6].data_ptr(), out[7].data_ptr(), out[8].data_ptr(),
+                                                sptr))
+            out[6].cpu(), out[7].cpu(), out[8].cpu()
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        e2e_step()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_qps = B * K / float(te.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- roofline of the dominant kernel (CUDA events recorded by the library on the launching stream)
+    kinds = L.KERNEL_KINDS
+    per_kind = {kinds[i]: (tm.ms[i], int(tm.launches[i])) for i in range(len(kinds)) if tm.launches[i]}
+    dom = max(per_kind, key=lambda n: per_kind[n][0]) if per_kind else None
+    roofline = None
+    if dom:
+        dms, dn = per_kind[dom]
+        avg_s = dms / dn / 1e3
+        if dom == "tensor":
+            flops = 2.0 * B * n_local * D
+            ach = flops / avg_s / 1e12
+            peak = peaks["bf16_sustained"] or peaks["bf16"]
+            roofline = {"bound": "tensor", "kernel": "flat_tensor_candidates (tcgen05 bf16)", "achieved": ach,
+                        "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+                        "peak_source": f"{peaks['source']} bf16 sustained", "flops_per_launch": flops,
+                        "single_pass_hbm_floor_ms": n_local * D * 2 / (peaks["hbm"] * 1e9) * 1e3}
+        else:
+            qt = st.last_qt or 8
+            passes = st.last_passes or ((B + qt - 1) // qt)
+            bytes_algo = passes * n_local * D * 4.0 + B * D * 4.0 + B * k * 12.0
+            ach = bytes_algo / avg_s / 1e9
+            roofline = {"bound": "hbm", "kernel": f"flat_scan_kernel<QT={qt},L2> (exact fp32 order)", "achieved": ach,
+                        "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
+                        "peak_source": f"{peaks['source']} copy bandwidth", "Qt": qt, "passes": passes,
+                        "bytes_per_launch": bytes_algo, "single_pass_floor_bytes": n_local * D * 4,
+                        "fma_tflops": (3.0 * B * n_local * D) / avg_s / 1e12}
+        roofline["kernel_ms_avg"] = dms / dn
+        roofline["share_of_step"] = (dms / K) / ms_step
+        roofline["kernels_ms_per_step"] = {n: v[0] / K for n, v in per_kind.items()}
+
+    cpu_base = None
+    if not args.no_cpu_baseline and X_sample is not None:
+        threads = host_threads()
+        nq = max(threads, min(args.cpu_queries, B))
+        cpu_base, secs, (cd, cl, cn) = cpu_reference_arm(X_sample, hQ, k, N, threads, nq)
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic N(0,1) fp32, torch generator seeds 1234+block / 4321", "config": cfg,
+            "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": B * D * 4,
+                    "d2h_bytes_per_step": B * k * 12 + B * 4},
+            "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
+            "path": {0: "auto", 1: "exact", 2: "tensor"}.get(0 if args.path == "auto" else (1 if args.path == "exact" else 2)),
+            "tensor_fallback_queries": int(st.tensor_fallbacks), "rows_per_gpu": n_local}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

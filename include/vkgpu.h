@@ -165,6 +165,16 @@ int vkgpu_hnsw_export(vkgpu_index *h, uint64_t *n, uint64_t *upper_blocks, int32
 /* ---- introspection / tuning ----------------------------------------------------------------------- */
 /* GetCapacity / GetTrackedKeyCount / RespondWithInfoImpl (vector_base.cc:385-409) */
 int vkgpu_get_stats(vkgpu_index *h, vkgpu_stats *out);
+/* CUDA-event timing of the library's own kernels, accumulated per kernel kind since the last
+ * vkgpu_set_profiling call: 0 exact scan, 1 top-k merge, 2 tensor candidate pass, 3 exact re-rank,
+ * 4 HNSW search.  The reference's analog is the latency sampler around the index call
+ * (src/query/search.cc:149-165). */
+typedef struct vkgpu_timings {
+  double ms[8];        /* summed device time per kind */
+  uint64_t launches[8];
+} vkgpu_timings;
+int vkgpu_set_profiling(vkgpu_index *h, int enable);
+int vkgpu_get_timings(vkgpu_index *h, vkgpu_timings *out);
 /* FLAT strategy override (tests and bench pin a path; AUTO in production) */
 int vkgpu_set_flat_path(vkgpu_index *h, int path);
 /* device pointer + row stride (floats) of the resident corpus, for zero-copy tooling */

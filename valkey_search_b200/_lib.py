@@ -61,6 +61,12 @@ class Stats(C.Structure):
     ]
 
 
+class Timings(C.Structure):
+    _fields_ = [("ms", C.c_double * 8), ("launches", C.c_uint64 * 8)]
+
+
+KERNEL_KINDS = ("scan", "merge", "tensor", "rerank", "hnsw")
+
 # every symbol include/vkgpu.h declares: name -> (restype, argtypes)
 _P = C.c_void_p
 SYMBOLS = {
@@ -85,6 +91,8 @@ SYMBOLS = {
     "vkgpu_hnsw_export": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "vkgpu_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "vkgpu_set_flat_path": (C.c_int, [_P, C.c_int]),
+    "vkgpu_set_profiling": (C.c_int, [_P, C.c_int]),
+    "vkgpu_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "vkgpu_device_corpus": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
 }
 

@@ -7,10 +7,16 @@
 
 namespace vkgpu {
 
+template <bool ROW_GLOBAL>
+__device__ __forceinline__ float4 ldrow(const float4 *p) {
+  if (ROW_GLOBAL) return __ldg(p);
+  return *p;
+}
+
 // `u` = lane & 3 inside the group (all 4 lanes of the group must call, with `active` uniform in the
 // group; inactive groups still take part in the shuffles).  q may be global or shared; Dp % 16 == 0 and
 // both pointers are 16-B aligned.  Returns the distance in all 4 lanes.
-template <bool L2>
+template <bool L2, bool ROW_GLOBAL = true>
 __device__ __forceinline__ float exact_dist_group(const float *__restrict__ row, const float *__restrict__ q,
                                                   uint32_t Dp, uint32_t u, bool active) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -21,8 +27,8 @@ __device__ __forceinline__ float exact_dist_group(const float *__restrict__ row,
     uint32_t s = 0;
     // 4 independent 16-B loads in flight per thread before the dependent fma chain consumes them
     for (; s + 4 <= steps; s += 4) {
-      float4 x0 = __ldg(r4 + (s + 0) * 4), x1 = __ldg(r4 + (s + 1) * 4);
-      float4 x2 = __ldg(r4 + (s + 2) * 4), x3 = __ldg(r4 + (s + 3) * 4);
+      float4 x0 = ldrow<ROW_GLOBAL>(r4 + (s + 0) * 4), x1 = ldrow<ROW_GLOBAL>(r4 + (s + 1) * 4);
+      float4 x2 = ldrow<ROW_GLOBAL>(r4 + (s + 2) * 4), x3 = ldrow<ROW_GLOBAL>(r4 + (s + 3) * 4);
       float4 y0 = q4[(s + 0) * 4], y1 = q4[(s + 1) * 4], y2 = q4[(s + 2) * 4], y3 = q4[(s + 3) * 4];
 #define VK_STEP(X, Y)                                                                 \
   if (L2) {                                                                           \
@@ -38,7 +44,7 @@ __device__ __forceinline__ float exact_dist_group(const float *__restrict__ row,
       VK_STEP(x0, y0) VK_STEP(x1, y1) VK_STEP(x2, y2) VK_STEP(x3, y3)
     }
     for (; s < steps; s++) {
-      float4 x0 = __ldg(r4 + s * 4);
+      float4 x0 = ldrow<ROW_GLOBAL>(r4 + s * 4);
       float4 y0 = q4[s * 4];
       VK_STEP(x0, y0)
     }

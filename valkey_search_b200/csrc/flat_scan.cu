@@ -20,6 +20,8 @@
 // when a buffer could overflow on the next tile the CTA bitonic-sorts it in smem and keeps the k best.
 #include "flat_scan.cuh"
 
+#include <cstring>
+
 namespace vkgpu {
 
 namespace {
@@ -29,11 +31,31 @@ constexpr int DC = kScanChunkFloats;
 constexpr int ROWB = kScanRowBytes;
 constexpr int NCOMPUTE = 256;
 
-template <int QT, bool L2>
-__global__ void __launch_bounds__(kScanThreads, 1) flat_scan_kernel(const ScanParams p) {
-  extern __shared__ __align__(128) uint8_t smem[];
+// Stage layouts.
+//  TMA2D (contiguous scan): two 32-float boxes per 64-float chunk, each landed by ONE cp.async.bulk.tensor
+//    with the 128-byte swizzle: [x box0 128x128B][x box1][q box0 QTx128B (padded to 1 KB)][q box1].
+//    The 16-byte unit j of row r sits at unit j ^ (r & 7), so the LDS.128 of a quarter-warp (rows r and r+4,
+//    4 units each) touches 8 distinct units = all 32 banks once.
+//  gather (row-id lists): one 1-D cp.async.bulk per row chunk into rows padded to 272 B.
+constexpr uint32_t XBOX_BYTES = TR * 128;                     // 16 KB
+constexpr uint32_t QBOX_BYTES = 1024;
+constexpr uint32_t TMA_STAGE_BYTES = 2 * XBOX_BYTES + 2 * QBOX_BYTES;
+
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tm, int32_t c0, int32_t c1,
+                                            uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+template <int QT, bool L2, bool TMA2D>
+__global__ void __launch_bounds__(kScanThreads, 1)
+    flat_scan_kernel(const ScanParams p, const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ) {
+  extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t S = p.stages;
-  const uint32_t stage_bytes = (TR + QT) * ROWB;
+  const uint32_t stage_bytes = TMA2D ? TMA_STAGE_BYTES : (TR + QT) * ROWB;
   uint8_t *stages = smem;
   Cand *scratch = reinterpret_cast<Cand *>(smem + (size_t)S * stage_bytes);
   uint8_t *tail = reinterpret_cast<uint8_t *>(scratch + p.cap);
@@ -91,9 +113,26 @@ __global__ void __launch_bounds__(kScanThreads, 1) flat_scan_kernel(const ScanPa
         const uint32_t cf = min((uint32_t)DC, p.Dp - c * DC);
         const uint32_t bytes = cf * 4;
         mbar_wait(&empty[stage], phase ^ 1);
+        uint8_t *sb = stages + (size_t)stage * stage_bytes;
+        if (TMA2D) {
+          if (lane == 0) {
+            const uint32_t nbox = (cf + 31) / 32;
+            mbar_arrive_expect_tx(&full[stage], nbox * (XBOX_BYTES + QT * 128));
+            for (uint32_t bx = 0; bx < nbox; bx++) {
+              tma_load_2d(sb + bx * XBOX_BYTES, &tmX, (int32_t)(c * DC + bx * 32), (int32_t)row0, &full[stage]);
+              tma_load_2d(sb + 2 * XBOX_BYTES + bx * QBOX_BYTES, &tmQ, (int32_t)(c * DC + bx * 32),
+                          (int32_t)(qtile * QT), &full[stage]);
+            }
+          }
+          __syncwarp();
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+          continue;
+        }
         if (lane == 0) mbar_arrive_expect_tx(&full[stage], (nrows + QT) * bytes);
         __syncwarp();
-        uint8_t *sb = stages + (size_t)stage * stage_bytes;
 #pragma unroll
         for (int j = 0; j < TR / 32; j++) {
           uint32_t r = lane + 32 * j;
@@ -117,6 +156,7 @@ __global__ void __launch_bounds__(kScanThreads, 1) flat_scan_kernel(const ScanPa
   const uint32_t rowA = warp * 16 + prow, rowB = rowA + 8;
   const uint32_t xoffA = rowA * ROWB + u * 16, xoffB = rowB * ROWB + u * 16;
   const uint32_t qoff = TR * ROWB + u * 16;
+  const uint32_t swA = rowA & 7, swB = rowB & 7;  // TMA2D: 128-B swizzle phase of this thread's rows
 
   uint32_t stage = 0, phase = 0;
   for (uint32_t tile = slab; tile < total_tiles; tile += slabs) {
@@ -131,11 +171,21 @@ __global__ void __launch_bounds__(kScanThreads, 1) flat_scan_kernel(const ScanPa
       mbar_wait(&full[stage], phase);
       const uint8_t *sb = stages + (size_t)stage * stage_bytes;
       auto step = [&](uint32_t s) {
-        const float4 xa = *reinterpret_cast<const float4 *>(sb + xoffA + s * 64);
-        const float4 xb = *reinterpret_cast<const float4 *>(sb + xoffB + s * 64);
+        float4 xa, xb;
+        const uint32_t unit = (s & 1) * 4 + u;  // 16-B unit inside the 128-B box row
+        const uint8_t *xbox = sb + (s >> 1) * XBOX_BYTES;
+        const uint8_t *qbox = sb + 2 * XBOX_BYTES + (s >> 1) * QBOX_BYTES;
+        if (TMA2D) {
+          xa = *reinterpret_cast<const float4 *>(xbox + rowA * 128 + ((unit ^ swA) << 4));
+          xb = *reinterpret_cast<const float4 *>(xbox + rowB * 128 + ((unit ^ swB) << 4));
+        } else {
+          xa = *reinterpret_cast<const float4 *>(sb + xoffA + s * 64);
+          xb = *reinterpret_cast<const float4 *>(sb + xoffB + s * 64);
+        }
 #pragma unroll
         for (int q = 0; q < QT; q++) {
-          const float4 qv = *reinterpret_cast<const float4 *>(sb + qoff + q * ROWB + s * 64);
+          const float4 qv = TMA2D ? *reinterpret_cast<const float4 *>(qbox + q * 128 + ((unit ^ (uint32_t)(q & 7)) << 4))
+                                  : *reinterpret_cast<const float4 *>(sb + qoff + q * ROWB + s * 64);
           if (L2) {
             // reference: d = a - b with a = query, b = row (bruteforce.h:122), then fma(d,d,acc)
             float d;
@@ -251,13 +301,21 @@ __global__ void __launch_bounds__(kScanThreads, 1) flat_scan_kernel(const ScanPa
 }
 
 template <int QT, bool L2>
-void launch_one(dim3 grid, size_t smem, cudaStream_t stream, const ScanParams &p) {
-  flat_scan_kernel<QT, L2><<<grid, kScanThreads, smem, stream>>>(p);
+void launch_one(dim3 grid, size_t smem, cudaStream_t stream, const ScanParams &p, const CUtensorMap *tmX,
+                const CUtensorMap *tmQ) {
+  if (tmX) {
+    flat_scan_kernel<QT, L2, true><<<grid, kScanThreads, smem, stream>>>(p, *tmX, *tmQ);
+  } else {
+    CUtensorMap dummy;
+    memset(&dummy, 0, sizeof(dummy));
+    flat_scan_kernel<QT, L2, false><<<grid, kScanThreads, smem, stream>>>(p, dummy, dummy);
+  }
 }
 
 template <int QT, bool L2>
 void set_attr_one(size_t max_smem) {
-  VK_CUDA(cudaFuncSetAttribute(flat_scan_kernel<QT, L2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  VK_CUDA(cudaFuncSetAttribute(flat_scan_kernel<QT, L2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  VK_CUDA(cudaFuncSetAttribute(flat_scan_kernel<QT, L2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
 }
 
 }  // namespace
@@ -273,20 +331,21 @@ void flat_scan_set_smem_attr(size_t max_smem) {
   set_attr_one<8, false>(max_smem);
 }
 
-void launch_flat_scan(int qt, bool l2, dim3 grid, size_t smem, cudaStream_t stream, const ScanParams &p) {
+void launch_flat_scan(int qt, bool l2, dim3 grid, size_t smem, cudaStream_t stream, const ScanParams &p,
+                      const CUtensorMap *tmX, const CUtensorMap *tmQ) {
   if (l2) {
     switch (qt) {
-      case 1: launch_one<1, true>(grid, smem, stream, p); break;
-      case 2: launch_one<2, true>(grid, smem, stream, p); break;
-      case 4: launch_one<4, true>(grid, smem, stream, p); break;
-      default: launch_one<8, true>(grid, smem, stream, p); break;
+      case 1: launch_one<1, true>(grid, smem, stream, p, tmX, tmQ); break;
+      case 2: launch_one<2, true>(grid, smem, stream, p, tmX, tmQ); break;
+      case 4: launch_one<4, true>(grid, smem, stream, p, tmX, tmQ); break;
+      default: launch_one<8, true>(grid, smem, stream, p, tmX, tmQ); break;
     }
   } else {
     switch (qt) {
-      case 1: launch_one<1, false>(grid, smem, stream, p); break;
-      case 2: launch_one<2, false>(grid, smem, stream, p); break;
-      case 4: launch_one<4, false>(grid, smem, stream, p); break;
-      default: launch_one<8, false>(grid, smem, stream, p); break;
+      case 1: launch_one<1, false>(grid, smem, stream, p, tmX, tmQ); break;
+      case 2: launch_one<2, false>(grid, smem, stream, p, tmX, tmQ); break;
+      case 4: launch_one<4, false>(grid, smem, stream, p, tmX, tmQ); break;
+      default: launch_one<8, false>(grid, smem, stream, p, tmX, tmQ); break;
     }
   }
   VK_CUDA(cudaGetLastError());
@@ -367,4 +426,42 @@ void launch_topk_merge(uint32_t B, cudaStream_t stream, const MergeParams &p) {
   VK_CUDA(cudaGetLastError());
 }
 
+}  // namespace vkgpu
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-map construction (host).  libcuda is not linked: the encoder is fetched through the runtime.
+namespace vkgpu {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    VK_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    if (!p || q != cudaDriverEntryPointSuccess) throw CudaFail{cudaErrorUnknown, "cuTensorMapEncodeTiled lookup", __FILE__, __LINE__};
+    fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+void make_tensor_map_2d(CUtensorMap *out, CUtensorMapDataType dt, uint32_t elem_bytes, const void *base, uint64_t inner,
+                        uint64_t rows, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows,
+                        CUtensorMapSwizzle sw) {
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  (void)elem_bytes;
+  CUresult r = get_encode_fn()(out, dt, 2, const_cast<void *>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw CudaFail{cudaErrorInvalidValue, "cuTensorMapEncodeTiled", __FILE__, __LINE__};
+}
+
+void make_tensor_map_2d_f32(CUtensorMap *out, const void *base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                            uint32_t box_inner, uint32_t box_rows, bool swizzle128) {
+  make_tensor_map_2d(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, base, inner, rows, row_stride_bytes, box_inner, box_rows,
+                     swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE);
+}
 }  // namespace vkgpu

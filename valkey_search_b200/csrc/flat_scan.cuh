@@ -1,5 +1,7 @@
 // Exact-order FLAT scan: launch parameters shared by flat_scan.cu and the host side (index.cu).
 #pragma once
+#include <cuda.h>
+
 #include "common.cuh"
 
 namespace vkgpu {
@@ -26,13 +28,22 @@ struct ScanParams {
   uint32_t *ws_cnt;          // [qtiles][slabs][QT]
 };
 
-// bytes of dynamic shared memory the scan kernel needs
-inline size_t scan_smem_bytes(int qt, uint32_t cap, uint32_t stages) {
-  return (size_t)stages * (kScanTileRows + qt) * kScanRowBytes + (size_t)cap * sizeof(Cand) + 512;
+// bytes per pipeline stage / of dynamic shared memory the scan kernel needs
+inline size_t scan_stage_bytes(int qt, bool tma2d) {
+  return tma2d ? (size_t)(2 * kScanTileRows * 128 + 2 * 1024) : (size_t)(kScanTileRows + qt) * kScanRowBytes;
+}
+inline size_t scan_smem_bytes(int qt, uint32_t cap, uint32_t stages, bool tma2d) {
+  return (size_t)stages * scan_stage_bytes(qt, tma2d) + (size_t)cap * sizeof(Cand) + 512;
 }
 
 // qt in {1,2,4,8}; metric_l2: true => squared L2, false => 1 - dot.  grid = (qtiles, slabs).
-void launch_flat_scan(int qt, bool metric_l2, dim3 grid, size_t smem, cudaStream_t stream, const ScanParams &p);
+// tmX/tmQ: 2-D tensor maps (box 32 floats x 128 rows / x qt rows, SWIZZLE_128B) for the contiguous scan,
+// or nullptr for the gather variant (row_ids).
+void launch_flat_scan(int qt, bool metric_l2, dim3 grid, size_t smem, cudaStream_t stream, const ScanParams &p,
+                      const CUtensorMap *tmX, const CUtensorMap *tmQ);
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency)
+void make_tensor_map_2d_f32(CUtensorMap *out, const void *base, uint64_t inner, uint64_t rows, uint64_t row_stride_bytes,
+                            uint32_t box_inner, uint32_t box_rows, bool swizzle128);
 void flat_scan_set_smem_attr(size_t max_smem);
 
 // Per-query merge of `nlists` unsorted candidate lists into the ascending top-k.

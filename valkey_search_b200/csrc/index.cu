@@ -90,11 +90,24 @@ SearchCtx *vkgpu_index_impl::acquire_ctx() {
     for (auto &c : ctxs)
       if (!c->busy) {
         c->busy = true;
+        lk.unlock();
+        prof_harvest(c.get());
+        if (c->done_pending) {  // previous call on this context ran asynchronously on a caller's stream
+          VK_CUDA(cudaEventSynchronize(c->done));
+          c->done_pending = false;
+        }
+        c->cur = c->stream;
         return c.get();
       }
     if (ctxs.size() < 16) {
       auto c = std::make_unique<SearchCtx>();
       VK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+      VK_CUDA(cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming));
+      for (int i = 0; i < kNumKernelKinds; i++) {
+        VK_CUDA(cudaEventCreate(&c->ev_beg[i]));
+        VK_CUDA(cudaEventCreate(&c->ev_end[i]));
+      }
+      c->cur = c->stream;
       c->busy = true;
       ctxs.push_back(std::move(c));
       return ctxs.back().get();
@@ -108,6 +121,29 @@ void vkgpu_index_impl::release_ctx(SearchCtx *c) {
     c->busy = false;
   }
   ctx_cv.notify_one();
+}
+
+void vkgpu_index_impl::prof_begin(SearchCtx *c, int kind) {
+  if (!profiling) return;
+  if (c->ev_pending[kind]) prof_harvest(c);
+  VK_CUDA(cudaEventRecord(c->ev_beg[kind], c->cur));
+}
+void vkgpu_index_impl::prof_end(SearchCtx *c, int kind) {
+  if (!profiling) return;
+  VK_CUDA(cudaEventRecord(c->ev_end[kind], c->cur));
+  c->ev_pending[kind] = true;
+}
+void vkgpu_index_impl::prof_harvest(SearchCtx *c) {
+  for (int i = 0; i < kNumKernelKinds; i++) {
+    if (!c->ev_pending[i]) continue;
+    VK_CUDA(cudaEventSynchronize(c->ev_end[i]));
+    float ms = 0.f;
+    VK_CUDA(cudaEventElapsedTime(&ms, c->ev_beg[i], c->ev_end[i]));
+    std::lock_guard<std::mutex> lk(prof_mu);
+    prof_ms[i] += ms;
+    prof_cnt[i]++;
+    c->ev_pending[i] = false;
+  }
 }
 
 size_t vkgpu_index_impl::hbm_bytes() const {
@@ -166,10 +202,13 @@ void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, ui
     slabs = (4 * ix->num_sms + qtiles - 1) / qtiles;
   slabs = std::max<uint32_t>(1, std::min<uint32_t>(slabs, total_tiles));
 
-  const size_t stage_bytes = (size_t)(kScanTileRows + qt) * kScanRowBytes;
-  uint32_t stages = (uint32_t)std::min<size_t>(16, (ix->smem_max - (size_t)cap * sizeof(Cand) - 512) / stage_bytes);
+  const bool tma2d = d_row_ids == nullptr;  // contiguous scan: 2-D tensor-map loads; gather: per-row bulk copies
+  const size_t stage_bytes = scan_stage_bytes(qt, tma2d);
+  // the dynamic smem base is 1024-B aligned by declaration; keep 1 KB of slack for that alignment
+  uint32_t stages =
+      (uint32_t)std::min<size_t>(16, (ix->smem_max - 1024 - (size_t)cap * sizeof(Cand) - 512) / stage_bytes);
   VK_REQUIRE(stages >= 2, VKGPU_ERR_INTERNAL, "not enough shared memory for the scan pipeline");
-  const size_t smem = scan_smem_bytes(qt, cap, stages);
+  const size_t smem = scan_smem_bytes(qt, cap, stages, tma2d);
 
   const size_t nlists = (size_t)qtiles * slabs * qt;
   c->ws.reserve(nlists * cap * sizeof(Cand));
@@ -192,7 +231,15 @@ void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, ui
   sp.stages = stages;
   sp.ws = c->ws.as<Cand>();
   sp.ws_cnt = c->ws_cnt.as<uint32_t>();
-  launch_flat_scan(qt, ix->metric_l2, dim3(qtiles, slabs), smem, c->stream, sp);
+  CUtensorMap tmX, tmQ;
+  if (tma2d) {
+    make_tensor_map_2d_f32(&tmX, ix->dX.p, ix->Dp, n_rows, (uint64_t)ix->Dp * 4, 32, kScanTileRows, true);
+    make_tensor_map_2d_f32(&tmQ, c->q_pad.p, ix->Dp, (uint64_t)qtiles * qt, (uint64_t)ix->Dp * 4, 32, qt, true);
+  }
+  ix->prof_begin(c, KK_SCAN);
+  launch_flat_scan(qt, ix->metric_l2, dim3(qtiles, slabs), smem, c->cur, sp, tma2d ? &tmX : nullptr,
+                   tma2d ? &tmQ : nullptr);
+  ix->prof_end(c, KK_SCAN);
 
   MergeParams mp{};
   mp.ws = sp.ws;
@@ -207,7 +254,9 @@ void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, ui
   mp.out_slots = c->out_slots.as<uint32_t>();
   mp.out_n = c->out_n.as<uint32_t>();
   mp.k_limit = nullptr;
-  launch_topk_merge(B, c->stream, mp);
+  ix->prof_begin(c, KK_MERGE);
+  launch_topk_merge(B, c->cur, mp);
+  ix->prof_end(c, KK_MERGE);
   ix->kernels += 2;
   ix->last_qt = qt;
   ix->last_passes = qtiles;
@@ -218,15 +267,15 @@ static void stage_queries(vkgpu_index_impl *ix, SearchCtx *c, const float *Q, ui
   const uint32_t Bpad = (B + kScanMaxQt - 1) / kScanMaxQt * kScanMaxQt;
   const size_t bytes = (size_t)Bpad * ix->Dp * sizeof(float);
   c->q_pad.reserve(bytes);
-  if (ix->Dp != ix->dim || Bpad != B) VK_CUDA(cudaMemsetAsync(c->q_pad.p, 0, bytes, c->stream));
+  if (ix->Dp != ix->dim || Bpad != B) VK_CUDA(cudaMemsetAsync(c->q_pad.p, 0, bytes, c->cur));
   if (on_device) {
     VK_CUDA(cudaMemcpy2DAsync(c->q_pad.p, (size_t)ix->Dp * 4, Q, (size_t)ix->dim * 4, (size_t)ix->dim * 4, B,
-                              cudaMemcpyDeviceToDevice, c->stream));
+                              cudaMemcpyDeviceToDevice, c->cur));
   } else {
     c->h_q.reserve((size_t)B * ix->dim * 4);
     std::memcpy(c->h_q.p, Q, (size_t)B * ix->dim * 4);
     VK_CUDA(cudaMemcpy2DAsync(c->q_pad.p, (size_t)ix->Dp * 4, c->h_q.p, (size_t)ix->dim * 4, (size_t)ix->dim * 4,
-                              B, cudaMemcpyHostToDevice, c->stream));
+                              B, cudaMemcpyHostToDevice, c->cur));
   }
 }
 
@@ -236,10 +285,10 @@ static void fetch_results(SearchCtx *c, uint32_t B, uint32_t k_dev, uint32_t k_u
   c->h_dist.reserve((size_t)B * k_dev * 4);
   c->h_labels.reserve((size_t)B * k_dev * 8);
   c->h_n.reserve((size_t)B * 4);
-  VK_CUDA(cudaMemcpyAsync(c->h_dist.p, c->out_dist.p, (size_t)B * k_dev * 4, cudaMemcpyDeviceToHost, c->stream));
-  VK_CUDA(cudaMemcpyAsync(c->h_labels.p, c->out_labels.p, (size_t)B * k_dev * 8, cudaMemcpyDeviceToHost, c->stream));
-  VK_CUDA(cudaMemcpyAsync(c->h_n.p, c->out_n.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->stream));
-  VK_CUDA(cudaStreamSynchronize(c->stream));
+  VK_CUDA(cudaMemcpyAsync(c->h_dist.p, c->out_dist.p, (size_t)B * k_dev * 4, cudaMemcpyDeviceToHost, c->cur));
+  VK_CUDA(cudaMemcpyAsync(c->h_labels.p, c->out_labels.p, (size_t)B * k_dev * 8, cudaMemcpyDeviceToHost, c->cur));
+  VK_CUDA(cudaMemcpyAsync(c->h_n.p, c->out_n.p, (size_t)B * 4, cudaMemcpyDeviceToHost, c->cur));
+  VK_CUDA(cudaStreamSynchronize(c->cur));
   const float *hd = c->h_dist.as<float>();
   const uint64_t *hl = c->h_labels.as<uint64_t>();
   const uint32_t *hn = c->h_n.as<uint32_t>();
@@ -255,7 +304,6 @@ static void fetch_results(SearchCtx *c, uint32_t B, uint32_t k_dev, uint32_t k_u
 static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_t B, uint32_t k,
                         const vkgpu_filter *filters, float *out_dist, uint64_t *out_labels, uint32_t *out_n,
                         bool out_on_device, cudaStream_t user_stream) {
-  (void)user_stream;
   if (ix->n == 0 || k == 0) {
     if (out_on_device) {
       VK_CUDA(cudaMemset(out_n, 0, (size_t)B * 4));
@@ -266,6 +314,7 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
   }
   CtxLease lease(ix);
   SearchCtx *c = lease.c;
+  if (user_stream) c->cur = user_stream;
   stage_queries(ix, c, Q, B, q_on_device);
 
   uint32_t k_eff;
@@ -306,8 +355,8 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     std::memcpy(c->h_misc.p, slots.data(), slots.size() * 4);
     std::memcpy(off_host, off.data(), off.size() * 8);
     if (!slots.empty())
-      VK_CUDA(cudaMemcpyAsync(c->lists.p, c->h_misc.p, slots.size() * 4, cudaMemcpyHostToDevice, c->stream));
-    VK_CUDA(cudaMemcpyAsync(c->list_off.p, off_host, off.size() * 8, cudaMemcpyHostToDevice, c->stream));
+      VK_CUDA(cudaMemcpyAsync(c->lists.p, c->h_misc.p, slots.size() * 4, cudaMemcpyHostToDevice, c->cur));
+    VK_CUDA(cudaMemcpyAsync(c->list_off.p, off_host, off.size() * 8, cudaMemcpyHostToDevice, c->cur));
     flat_exact_search_device(ix, c, B, k_eff, c->lists.as<uint32_t>(), c->list_off.as<uint64_t>(), true, longest);
   } else {
     k_eff = (uint32_t)std::min<uint64_t>(k, ix->n);
@@ -323,11 +372,16 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
   if (out_on_device) {
     // [B][k_eff] -> caller's [B][k] device arrays
     VK_CUDA(cudaMemcpy2DAsync(out_dist, (size_t)k * 4, c->out_dist.p, (size_t)k_eff * 4, (size_t)k_eff * 4, B,
-                              cudaMemcpyDeviceToDevice, c->stream));
+                              cudaMemcpyDeviceToDevice, c->cur));
     VK_CUDA(cudaMemcpy2DAsync(out_labels, (size_t)k * 8, c->out_labels.p, (size_t)k_eff * 8, (size_t)k_eff * 8, B,
-                              cudaMemcpyDeviceToDevice, c->stream));
-    VK_CUDA(cudaMemcpyAsync(out_n, c->out_n.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, c->stream));
-    VK_CUDA(cudaStreamSynchronize(c->stream));
+                              cudaMemcpyDeviceToDevice, c->cur));
+    VK_CUDA(cudaMemcpyAsync(out_n, c->out_n.p, (size_t)B * 4, cudaMemcpyDeviceToDevice, c->cur));
+    if (user_stream) {  // asynchronous: the caller synchronises its own stream
+      VK_CUDA(cudaEventRecord(c->done, c->cur));
+      c->done_pending = true;
+    } else {
+      VK_CUDA(cudaStreamSynchronize(c->cur));
+    }
   } else {
     fetch_results(c, B, k_eff, k, out_dist, out_labels, out_n);
   }
@@ -510,6 +564,11 @@ void vkgpu_index_destroy(vkgpu_index *ix) {
   tensor_release(ix);
   for (auto &c : ix->ctxs) {
     if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->done) cudaEventDestroy(c->done);
+    for (int i = 0; i < kNumKernelKinds; i++) {
+      if (c->ev_beg[i]) cudaEventDestroy(c->ev_beg[i]);
+      if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
+    }
     for (DevBuf *b : {&c->q_pad, &c->ws, &c->ws_cnt, &c->out_dist, &c->out_labels, &c->out_n, &c->out_slots,
                       &c->lists, &c->list_off, &c->klimit, &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3})
       b->release();
@@ -619,7 +678,6 @@ int vkgpu_search_batch_device(vkgpu_index *ix, const float *d_Q, uint32_t B, uin
     VK_REQUIRE(B >= 1, VKGPU_ERR_INVALID, "empty batch");
     std::shared_lock<std::shared_mutex> lk(ix->rw);
     VK_CUDA(cudaSetDevice(ix->device));
-    if (cuda_stream) VK_CUDA(cudaStreamSynchronize((cudaStream_t)cuda_stream));  // inputs produced on it
     if (ix->cfg.algo == VKGPU_FLAT)
       flat_search(ix, d_Q, true, B, k, nullptr, d_out_dist, d_out_labels, d_out_n, true, (cudaStream_t)cuda_stream);
     else
@@ -644,12 +702,12 @@ int vkgpu_distances(vkgpu_index *ix, const float *q, const uint64_t *labels, uin
     }
     c->lists.reserve(n * 4);
     c->out_dist.reserve(n * 4);
-    VK_CUDA(cudaMemcpyAsync(c->lists.p, hs, n * 4, cudaMemcpyHostToDevice, c->stream));
+    VK_CUDA(cudaMemcpyAsync(c->lists.p, hs, n * 4, cudaMemcpyHostToDevice, c->cur));
     launch_exact_distances(ix->dX.as<float>(), ix->Dp, ix->metric_l2, c->q_pad.as<float>(), c->lists.as<uint32_t>(),
-                           n, c->out_dist.as<float>(), c->stream);
+                           n, c->out_dist.as<float>(), c->cur);
     ix->kernels++;
-    VK_CUDA(cudaMemcpyAsync(out, c->out_dist.p, n * 4, cudaMemcpyDeviceToHost, c->stream));
-    VK_CUDA(cudaStreamSynchronize(c->stream));
+    VK_CUDA(cudaMemcpyAsync(out, c->out_dist.p, n * 4, cudaMemcpyDeviceToHost, c->cur));
+    VK_CUDA(cudaStreamSynchronize(c->cur));
   });
 }
 
@@ -717,6 +775,37 @@ int vkgpu_set_flat_path(vkgpu_index *ix, int path) {
       tensor_prepare(ix);
     }
     ix->flat_path = path;
+  });
+}
+
+int vkgpu_set_profiling(vkgpu_index *ix, int enable) {
+  return guarded([&] {
+    VK_REQUIRE(ix, VKGPU_ERR_INVALID, "null argument");
+    std::unique_lock<std::shared_mutex> lk(ix->rw);
+    ix->profiling = enable != 0;
+    std::lock_guard<std::mutex> pl(ix->prof_mu);
+    for (int i = 0; i < kNumKernelKinds; i++) {
+      ix->prof_ms[i] = 0;
+      ix->prof_cnt[i] = 0;
+    }
+  });
+}
+
+int vkgpu_get_timings(vkgpu_index *ix, vkgpu_timings *out) {
+  return guarded([&] {
+    VK_REQUIRE(ix && out, VKGPU_ERR_INVALID, "null argument");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    {
+      std::lock_guard<std::mutex> cl(ix->ctx_mu);
+      for (auto &c : ix->ctxs)
+        if (!c->busy) ix->prof_harvest(c.get());
+    }
+    std::lock_guard<std::mutex> pl(ix->prof_mu);
+    for (int i = 0; i < kNumKernelKinds; i++) {
+      out->ms[i] = ix->prof_ms[i];
+      out->launches[i] = ix->prof_cnt[i];
+    }
   });
 }
 

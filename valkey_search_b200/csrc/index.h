@@ -43,6 +43,8 @@ struct PinnedBuf {
   }
 };
 
+enum KernelKind { KK_SCAN = 0, KK_MERGE = 1, KK_TENSOR = 2, KK_RERANK = 3, KK_HNSW = 4, kNumKernelKinds = 5 };
+
 // Everything one in-flight search needs; searches on different contexts run concurrently.
 struct SearchCtx {
   cudaStream_t stream = nullptr;
@@ -55,6 +57,12 @@ struct SearchCtx {
   DevBuf scratch0, scratch1, scratch2, scratch3;  // path-specific (tensor / hnsw)
   PinnedBuf h_q, h_dist, h_labels, h_n, h_misc;
   bool busy = false;
+  cudaStream_t cur = nullptr;     // stream this call runs on (own stream, or the caller's)
+  cudaEvent_t done = nullptr;     // recorded at the end of a call that ran on a caller's stream
+  bool done_pending = false;
+  // per-kernel-kind CUDA-event timing (enabled by vkgpu_set_profiling)
+  cudaEvent_t ev_beg[kNumKernelKinds] = {}, ev_end[kNumKernelKinds] = {};
+  bool ev_pending[kNumKernelKinds] = {};
 };
 
 struct vkgpu_index_impl {
@@ -92,6 +100,13 @@ struct vkgpu_index_impl {
 
   std::atomic<uint64_t> searches{0}, kernels{0}, dist_evals{0}, hops{0}, tensor_fallbacks{0};
   std::atomic<uint32_t> last_qt{0}, last_passes{0};
+  bool profiling = false;
+  std::mutex prof_mu;
+  double prof_ms[kNumKernelKinds] = {};
+  uint64_t prof_cnt[kNumKernelKinds] = {};
+  void prof_begin(SearchCtx *c, int kind);
+  void prof_end(SearchCtx *c, int kind);
+  void prof_harvest(SearchCtx *c);
 
   SearchCtx *acquire_ctx();
   void release_ctx(SearchCtx *c);

@@ -1,0 +1,87 @@
+"""Row-sharded FLAT index across the GPUs of one box: one process per GPU (torch.distributed), each rank
+holds a contiguous block of rows in its own HBM and answers every query locally; one all-gather of the
+per-rank [B,k] results (NCCL over NVLink on GPUs, gloo in CPU tests) and a k-way merge with the same
+(distance,label) order give a result identical to the single-GPU one.
+
+Reference analog: the cluster fan-out + merge of src/query/fanout.cc:159-220 over gRPC
+(src/coordinator/coordinator.proto:127-157) — here without the network.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+
+def shard_bounds(n_rows, world_size, rank):
+    """Contiguous row block of `rank`: sizes differ by at most one row."""
+    base, rem = divmod(int(n_rows), int(world_size))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def merge_topk_host(dist, labels, counts, k):
+    """k-way merge of per-shard ascending results on the host (used by the gloo/CPU tests of the
+    multi-rank plumbing and as the specification of the GPU merge kernel).
+    dist/labels: [G,B,k]; counts: [G,B].  Returns ([B,k] dist, [B,k] labels, [B] n)."""
+    G, B, _ = dist.shape
+    out_d = np.full((B, k), np.inf, np.float32)
+    out_l = np.full((B, k), np.iinfo(np.uint64).max, np.uint64)
+    out_n = np.zeros(B, np.uint32)
+    for b in range(B):
+        items = []
+        for g in range(G):
+            c = int(counts[g, b])
+            items.extend(zip(dist[g, b, :c].tolist(), labels[g, b, :c].tolist()))
+        items.sort()
+        items = items[:k]
+        out_n[b] = len(items)
+        for j, (d, l) in enumerate(items):
+            out_d[b, j] = d
+            out_l[b, j] = l
+    return out_d, out_l, out_n
+
+
+class ShardedFlat:
+    """One rank's view of a row-sharded FLAT index.  `local` is a VectorFlat holding this rank's rows with
+    GLOBAL labels.  search_device() runs local search -> all_gather -> merge entirely on the device."""
+
+    def __init__(self, local_index, dist_module=None, device=None):
+        self.local = local_index
+        self.dist = dist_module
+        self.world = dist_module.get_world_size() if dist_module is not None and dist_module.is_initialized() else 1
+        self.rank = dist_module.get_rank() if self.world > 1 else 0
+        self.device = device
+        self._lib = L.lib()
+
+    def search_device(self, d_Q, k, stream_ptr, out=None):
+        """d_Q: torch CUDA tensor [B,dim] fp32.  Returns torch tensors (dist [B,k], labels [B,k] int64 view of
+        u64, n [B] int32) on the device, merged over all ranks (every rank gets the full result)."""
+        import torch
+
+        B = d_Q.shape[0]
+        dev = d_Q.device
+        if out is None:
+            out = self.alloc_out(B, k, dev)
+        loc_d, loc_l, loc_n, all_d, all_l, all_n, mer_d, mer_l, mer_n = out
+        L.check(self._lib.vkgpu_search_batch_device(self.local.handle(), d_Q.data_ptr(), B, k, 0, loc_d.data_ptr(),
+                                                    loc_l.data_ptr(), loc_n.data_ptr(), stream_ptr))
+        if self.world == 1:
+            return loc_d, loc_l, loc_n
+        # the single exchange step of the path: B*k*12 bytes per rank
+        self.dist.all_gather_into_tensor(all_d, loc_d)
+        self.dist.all_gather_into_tensor(all_l, loc_l)
+        self.dist.all_gather_into_tensor(all_n, loc_n)
+        L.check(self._lib.vkgpu_merge_topk_device(dev.index, all_d.data_ptr(), all_l.data_ptr(), all_n.data_ptr(),
+                                                  self.world, B, k, mer_d.data_ptr(), mer_l.data_ptr(),
+                                                  mer_n.data_ptr(), stream_ptr))
+        return mer_d, mer_l, mer_n
+
+    def alloc_out(self, B, k, dev):
+        import torch
+
+        G = self.world
+        mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+        return (mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32),
+                mk((G, B, k), torch.float32), mk((G, B, k), torch.int64), mk((G, B), torch.int32),
+                mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32))
