@@ -1,0 +1,99 @@
+"""FLAT tensor-core path (tcgen05 candidate pass + exact re-rank) must be bit-identical to the exact FMA scan
+and to the CPU oracle: same ids, same ranks, same distance bits (bruteforce.h:116-145 semantics)."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("metric,N,D,B,k", [("L2", 200_000, 768, 300, 100), ("IP", 150_000, 128, 70, 10),
+                                             ("L2", 50_000, 100, 257, 37), ("COSINE", 60_000, 256, 64, 100)])
+def test_tensor_path_equals_exact_path(built, metric, N, D, B, k):
+    import valkey_search_b200 as V
+    rng = np.random.default_rng(N + D + B)
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    X[1000:1040] = X[1000]  # exact duplicates: label tie-break must survive the candidate pass
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    Q[0] = X[1000]
+    ix = V.VectorFlat(D, V.DistanceMetric[metric], initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    ix.SetSearchPath(V.PATH_EXACT_FMA)
+    d0, l0, n0 = ix.SearchBatchRaw(Q, k)
+    ix.SetSearchPath(V.PATH_TENSOR)
+    d1, l1, n1 = ix.SearchBatchRaw(Q, k)
+    assert np.array_equal(n0, n1)
+    assert np.array_equal(l0, l1), np.argwhere(l0 != l1)[:5]
+    assert np.array_equal(_bits(d0), _bits(d1))
+    st = ix.stats()
+    assert st.tensor_fallbacks <= B // 4, "margin rule falls back far too often"
+    if metric != "COSINE":
+        orc_metric = O.L2 if metric == "L2" else O.IP
+        p = O.port()
+        for b in (0, 1, B - 1):  # spot-check against the oracle's arithmetic
+            for j in (0, k - 1):
+                row = X[int(l1[b, j])]
+                want = p.vko_l2sq(Q[b], row, D) if orc_metric == O.L2 else p.vko_ip(Q[b], row, D)
+                assert np.float32(d1[b, j]).tobytes() == np.float32(want).tobytes()
+
+
+def test_tensor_path_vs_oracle_small(built):
+    import valkey_search_b200 as V
+    rng = np.random.default_rng(5)
+    N, D, B, k = 20_000, 64, 128, 10
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    ix.SetSearchPath(V.PATH_TENSOR)
+    d1, l1, n1 = ix.SearchBatchRaw(Q, k)
+    orc = O.PortFlat(D, O.L2)
+    orc.add_many(X)
+    for b in range(0, B, 7):
+        d, l = orc.search(Q[b], k)
+        assert np.array_equal(l1[b], l) and np.array_equal(_bits(d1[b]), _bits(d))
+
+
+def test_tensor_path_thin_margin_falls_back_and_stays_exact(built):
+    """A cluster of near-identical rows makes approx[K'] - approx[k] smaller than the bf16 error bound: the
+    proof fails, the query is re-run on the exact scan, and the answer is still the reference's."""
+    import valkey_search_b200 as V
+    rng = np.random.default_rng(8)
+    N, D, B, k = 30_000, 128, 64, 50
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    centre = rng.standard_normal(D).astype(np.float32)
+    X[:3000] = centre + 1e-4 * rng.standard_normal((3000, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    Q[:8] = centre + 1e-4 * rng.standard_normal((8, D)).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    ix.SetSearchPath(V.PATH_EXACT_FMA)
+    d0, l0, _ = ix.SearchBatchRaw(Q, k)
+    ix.SetSearchPath(V.PATH_TENSOR)
+    d1, l1, _ = ix.SearchBatchRaw(Q, k)
+    assert np.array_equal(l0, l1) and np.array_equal(_bits(d0), _bits(d1))
+    assert ix.stats().tensor_fallbacks >= 8
+
+
+def test_tensor_path_after_mutations(built):
+    """The bf16 mirror follows adds and swap-deletes."""
+    import valkey_search_b200 as V
+    rng = np.random.default_rng(13)
+    N, D, B, k = 120_000, 96, 64, 10
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=1024, block_size=50_000)
+    ix.AddRecordsBulk(range(100_000), X[:100_000])
+    ix.SetSearchPath(V.PATH_TENSOR)
+    ix.AddRecordsBulk(range(100_000, N), X[100_000:])
+    for key in rng.choice(N, 300, replace=False):
+        assert ix.RemoveRecord(int(key))
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    d1, l1, _ = ix.SearchBatchRaw(Q, k)
+    ix.SetSearchPath(V.PATH_EXACT_FMA)
+    d0, l0, _ = ix.SearchBatchRaw(Q, k)
+    assert np.array_equal(l0, l1) and np.array_equal(_bits(d0), _bits(d1))

@@ -1,12 +1,636 @@
+// FLAT batched search on the 5th-gen tensor cores (sm_100a): tcgen05 candidate pass + exact re-rank.
+//
+// The batched-query x corpus-block distance computation of BruteforceSearch::searchKnn
+// (third_party/hnswlib/bruteforce.h:116-145) is a dense contraction.  The reference's fp32 summation order
+// cannot run on tensor cores, so this path splits the work:
+//   1. candidate pass  — bf16 mirror of the corpus x bf16 queries on tcgen05.mma (fp32 accumulate in TMEM),
+//      fused epilogue keeps, per query, every row whose APPROXIMATE score is within the running K'-th
+//      best (K' = k + margin);
+//   2. merge           — per-query top-K' by approximate score (topk_merge_kernel);
+//   3. exact re-rank   — the K' survivors are re-scored in the reference's exact fp32 order
+//      (exact_dist.cuh) and sorted by (distance,label);
+//   4. proof           — with e = a rigorous bound on |approx - exact score|, the result equals the
+//      reference's whenever approx[K'] > approx[k] + 2e (every row that could belong to the true top-k
+//      is then among the survivors).  Queries that fail the check are re-run on the exact FMA scan
+//      (flat_scan.cu) — still on the GPU, never on the CPU.
+// Output is therefore bit-identical to the exact path / the CPU oracle.
+//
+// Kernel anatomy (flat_tensor_kernel): 256 threads; warp 0 = TMA producer (cp.async.bulk.tensor, 128B
+// swizzle), warp 1 = single-thread tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
+// (tcgen05.ld 32x32b -> score -> threshold gate -> append).  Tile = 128 corpus rows (M) x 256 queries (N),
+// K streamed in 64-element (128 B) stages through a 4-deep smem ring; two 256-column TMEM accumulators
+// double-buffer MMA against the epilogue.  CTAs are persistent: (query tile, corpus slab) pairs.
 #include "tensor_path.h"
+
+#include <cuda_bf16.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "exact_dist.cuh"
+
 namespace vkgpu {
-struct StatusErrorT { int code; std::string msg; };
-bool tensor_path_profitable(const vkgpu_index_impl *, uint32_t, uint32_t) { return false; }
-bool tensor_path_supported(const vkgpu_index_impl *, uint32_t, uint32_t) { return false; }
-void tensor_prepare(vkgpu_index_impl *) { throw StatusError{VKGPU_ERR_UNSUPPORTED, "tensor path not built yet"}; }
-void tensor_reserve(vkgpu_index_impl *, uint64_t) {}
-void tensor_refresh_rows(vkgpu_index_impl *, uint64_t, uint64_t) {}
-void tensor_move_row(vkgpu_index_impl *, uint64_t, uint64_t) {}
-void tensor_release(vkgpu_index_impl *) {}
-void tensor_search_device(vkgpu_index_impl *, SearchCtx *, uint32_t, uint32_t) {}
+
+#define VK_REQUIRE(cond, code, msg) \
+  do {                              \
+    if (!(cond)) throw StatusError{code, msg}; \
+  } while (0)
+
+void make_tensor_map_2d(CUtensorMap *out, CUtensorMapDataType dt, uint32_t elem_bytes, const void *base, uint64_t inner,
+                        uint64_t rows, uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows,
+                        CUtensorMapSwizzle sw);
+
+namespace {
+
+constexpr int BM = 128;        // corpus rows per tile  (UMMA M)
+constexpr int BN = 256;        // queries per tile      (UMMA N)
+constexpr int BK = 64;         // bf16 elements per stage = 128 B = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int STAGES = 4;
+constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+constexpr int TC_THREADS = 256;
+constexpr int EPI_THREADS = 128;
+constexpr uint32_t TMEM_COLS = 512;
+
+struct TensorParams {
+  const float *xnorm;        // [n] fp32 squared row norms
+  uint64_t n_rows;
+  uint32_t kchunks;          // Dh / 64
+  uint32_t nq_tiles, slabs;
+  uint32_t kprime;           // K' kept per (CTA, query) after a shrink
+  uint32_t cap;              // candidate buffer capacity per (CTA, query): pow2 >= K' + 128
+  Cand *ws;                  // [nq_tiles][slabs][BN][cap]
+  uint32_t *ws_cnt;          // [nq_tiles][slabs][BN]
+  uint32_t *gthr;            // [nq_tiles*BN] shared running thresholds (ord), initialised to 0xffffffff
+  int metric_l2;
+};
+
+// ---------------------------------------------------------------- tcgen05 / TMA PTX wrappers
+__device__ __forceinline__ void tma_load_2d_bf16(void *smem_dst, const CUtensorMap *tm, int32_t c0, int32_t c1,
+                                                 uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+          smem_u32(smem_dst)),
+      "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M=128 N=256 K=16
+__device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// K-major operand tile, 128-byte swizzle: rows of 128 B, 8-row atoms 1024 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 | LBO<<16 | SBO<<32 | version=1<<46 | SWIZZLE_128B=2<<61)
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr & 0x3ffffu) >> 4) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) |
+         (2ull << 61);
+}
+// cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=BF16 (1<<7), b=BF16 (1<<10), K-major both, N>>3 @17, M>>4 @24
+constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// ---------------------------------------------------------------- the candidate kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+    flat_tensor_kernel(const TensorParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t *sA = smem;                                   // [STAGES][16 KB]
+  uint8_t *sB = smem + STAGES * A_STAGE_BYTES;          // [STAGES][32 KB]
+  uint8_t *tail = sB + STAGES * B_STAGE_BYTES;
+  Cand *scratch = reinterpret_cast<Cand *>(tail);       // [cap]  shrink sort buffer
+  uint8_t *ctl = tail + (size_t)p.cap * sizeof(Cand);
+  uint64_t *full = reinterpret_cast<uint64_t *>(ctl);   // [STAGES]
+  uint64_t *empty = full + STAGES;                      // [STAGES]
+  uint64_t *tfull = empty + STAGES;                     // [2]
+  uint64_t *tempty = tfull + 2;                         // [2]
+  uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
+  uint32_t *shrink_mask = tmem_slot + 4;                // [BN/32]
+  float *thrf = reinterpret_cast<float *>(shrink_mask + BN / 32);  // [BN] float thresholds (gate)
+  uint32_t *cnt = reinterpret_cast<uint32_t *>(thrf + BN);         // [BN]
+
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t qtile = blockIdx.x % p.nq_tiles, slab = blockIdx.x / p.nq_tiles;
+  const uint32_t total_tiles = (uint32_t)((p.n_rows + BM - 1) / BM);
+
+  if (tid == 0) {
+    for (int s = 0; s < STAGES; s++) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(&tfull[a], 1);
+      mbar_init(&tempty[a], EPI_THREADS);
+    }
+    fence_mbar_init();
+  }
+  for (uint32_t i = tid; i < BN; i += TC_THREADS) {
+    thrf[i] = __int_as_float(0x7f800000);
+    cnt[i] = 0;
+  }
+  if (tid < BN / 32) shrink_mask[tid] = 0;
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs) {
+        for (uint32_t kb = 0; kb < p.kchunks; kb++) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d_bf16(sA + stage * A_STAGE_BYTES, &tmA, (int32_t)(kb * BK), (int32_t)(tile * BM), &full[stage]);
+          tma_load_2d_bf16(sB + stage * B_STAGE_BYTES, &tmB, (int32_t)(kb * BK), (int32_t)(qtile * BN), &full[stage]);
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (one thread)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0, t = 0;
+      for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
+        const uint32_t a = t & 1;
+        mbar_wait(&tempty[a], ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t tmem_d = tmem_base + a * BN;
+        for (uint32_t kb = 0; kb < p.kchunks; kb++) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; k++) {
+            tc_mma_bf16(tmem_d, make_sw128_desc(a_addr + k * UMMA_K * 2), make_sw128_desc(b_addr + k * UMMA_K * 2),
+                        kIdescBf16, (kb | (uint32_t)k) != 0 ? 1u : 0u);
+          }
+          tc_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          if (++stage == STAGES) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+        tc_commit(&tfull[a]);  // accumulator complete
+      }
+    }
+  } else if (warp >= 4) {
+    // ------------------------------------------------------------ epilogue warps (TMEM lanes 32*(warp%4)..)
+    const uint32_t et = tid - 128;                 // 0..127 = row inside the tile = TMEM lane
+    const uint32_t lane_base = (warp & 3) * 32;
+    Cand *my_ws = p.ws + ((size_t)qtile * p.slabs + slab) * BN * p.cap;
+    uint32_t t = 0;
+    for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
+      // refresh the gate thresholds from the running global ones (other slabs tighten them too)
+      for (uint32_t c = et; c < BN; c += EPI_THREADS) {
+        const uint32_t go = *reinterpret_cast<volatile uint32_t *>(&p.gthr[qtile * BN + c]);
+        if (go != kOrdInf) thrf[c] = fminf(thrf[c], ord_to_f32(go));
+      }
+      named_bar_sync(2, EPI_THREADS);
+
+      const uint32_t a = t & 1;
+      const uint64_t slot = (uint64_t)tile * BM + et;
+      const bool valid = slot < p.n_rows;
+      const float xn = (valid && p.metric_l2) ? p.xnorm[slot] : 0.0f;
+      mbar_wait(&tfull[a], (t >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (uint32_t c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + (lane_base << 16) + a * BN + c0, r);
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+          const float dot = __uint_as_float(r[j]);
+          // approximate score: L2 -> |x|^2 - 2 x.q (the |q|^2 term is constant per query); IP -> -x.q
+          const float s = p.metric_l2 ? __fmaf_rn(-2.0f, dot, xn) : -dot;
+          if (valid && s <= thrf[c0 + j]) {
+            const uint32_t c = c0 + j;
+            const uint32_t pos = atomicAdd(&cnt[c], 1u);
+            Cand cd;
+            cd.ord = f32_to_ord(s);
+            cd.slot = (uint32_t)slot;
+            cd.label = slot;
+            my_ws[(size_t)c * p.cap + pos] = cd;  // pos < cap by the shrink rule below
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty[a]);  // accumulator may be overwritten
+
+      // ---- keep room for one more tile (<= BM appends per query per tile)
+      named_bar_sync(2, EPI_THREADS);
+      for (uint32_t c = et; c < BN; c += EPI_THREADS)
+        if (cnt[c] + BM > p.cap) atomicOr(&shrink_mask[c >> 5], 1u << (c & 31));
+      named_bar_sync(2, EPI_THREADS);
+      for (uint32_t w = 0; w < BN / 32; w++) {
+        uint32_t m = shrink_mask[w];
+        while (m) {
+          const uint32_t c = w * 32 + (__ffs(m) - 1);
+          m &= m - 1;
+          const uint32_t n = cnt[c];
+          Cand *buf = my_ws + (size_t)c * p.cap;
+          for (uint32_t i = et; i < p.cap; i += EPI_THREADS) {
+            Cand cd;
+            if (i < n) {
+              cd = buf[i];
+            } else {
+              cd.ord = kOrdInf;
+              cd.slot = 0xffffffffu;
+              cd.label = ~0ull;
+            }
+            scratch[i] = cd;
+          }
+          named_bar_sync(2, EPI_THREADS);
+          bitonic_sort_cands(scratch, p.cap, et, EPI_THREADS, [] { named_bar_sync(2, EPI_THREADS); });
+          const uint32_t keep = min(n, p.kprime);
+          for (uint32_t i = et; i < keep; i += EPI_THREADS) buf[i] = scratch[i];
+          if (et == 0) {
+            cnt[c] = keep;
+            if (keep == p.kprime) {
+              const uint32_t o = scratch[p.kprime - 1].ord;
+              thrf[c] = fminf(thrf[c], ord_to_f32(o));
+              atomicMin(&p.gthr[qtile * BN + c], o);
+            }
+          }
+          named_bar_sync(2, EPI_THREADS);
+        }
+      }
+      named_bar_sync(2, EPI_THREADS);
+      if (et < BN / 32) shrink_mask[et] = 0;
+    }
+    named_bar_sync(2, EPI_THREADS);
+    for (uint32_t c = et; c < BN; c += EPI_THREADS)
+      p.ws_cnt[((size_t)qtile * p.slabs + slab) * BN + c] = cnt[c];
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+  }
+}
+
+// ---------------------------------------------------------------- conversion kernels
+// fp32 rows [n][Dp] -> bf16 [n][Dh] (zero padded) + fp32 squared norms + running max norm (as uint bits)
+__global__ void __launch_bounds__(256) to_bf16_rows_kernel(const float *__restrict__ X, uint32_t Dp,
+                                                           __nv_bfloat16 *__restrict__ Xh, uint32_t Dh,
+                                                           float *__restrict__ norm, uint64_t first, uint64_t n,
+                                                           uint32_t *max_norm_bits) {
+  const uint32_t warps_per_block = blockDim.x >> 5;
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint64_t r = (uint64_t)blockIdx.x * warps_per_block + (threadIdx.x >> 5); r < n;
+       r += (uint64_t)gridDim.x * warps_per_block) {
+    const float *src = X + (first + r) * Dp;
+    __nv_bfloat16 *dst = Xh + (first + r) * Dh;
+    float acc = 0.f;
+    for (uint32_t i = lane; i < Dh; i += 32) {
+      const float v = i < Dp ? src[i] : 0.0f;
+      acc = fmaf(v, v, acc);
+      dst[i] = __float2bfloat16_rn(v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      if (norm) norm[first + r] = acc;
+      if (max_norm_bits) atomicMax(max_norm_bits, __float_as_uint(acc));
+    }
+  }
+}
+
+// ---------------------------------------------------------------- exact re-rank + proof kernel
+struct RerankParams {
+  const float *X;
+  uint32_t Dp;
+  const uint64_t *labels;
+  const float *Q;            // fp32 padded queries [B][Dp]
+  const float *qnorm;        // [B] squared norms of the queries
+  const uint32_t *max_norm_bits;
+  const float *approx;       // [B][kprime] merged approximate scores, ascending
+  const uint32_t *slots;     // [B][kprime]
+  const uint32_t *napprox;   // [B]
+  uint32_t kprime, k, sort_n;
+  uint64_t n_rows;
+  float err_coef;            // |approx - exact score| <= err_coef * |q| * max|x|  (+ tiny)
+  float *out_dist;           // [B][k]
+  uint64_t *out_labels;      // [B][k]
+  uint32_t *out_n;           // [B]
+  uint32_t *flags;           // [B]: 1 => margin too thin, re-run on the exact scan
+};
+
+template <bool L2>
+__global__ void __launch_bounds__(128) rerank_kernel(const RerankParams p) {
+  extern __shared__ __align__(16) uint8_t rsm[];
+  Cand *buf = reinterpret_cast<Cand *>(rsm);                       // [sort_n]
+  float *q = reinterpret_cast<float *>(rsm + (size_t)p.sort_n * sizeof(Cand));  // [Dp]
+  const uint32_t b = blockIdx.x, tid = threadIdx.x, gi = tid >> 2, u = tid & 3;
+  const uint32_t n = min(p.napprox[b], p.kprime);
+  for (uint32_t i = tid; i < p.Dp / 4; i += 128)
+    reinterpret_cast<float4 *>(q)[i] = reinterpret_cast<const float4 *>(p.Q + (size_t)b * p.Dp)[i];
+  for (uint32_t i = tid; i < p.sort_n; i += 128) {
+    buf[i].ord = kOrdInf;
+    buf[i].slot = 0xffffffffu;
+    buf[i].label = ~0ull;
+  }
+  __syncthreads();
+  for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+    const uint32_t j = j0 + gi;
+    const bool act = j < n;
+    const uint32_t slot = act ? p.slots[(size_t)b * p.kprime + j] : 0;
+    const float d = exact_dist_group<L2, true>(p.X + (size_t)slot * p.Dp, q, p.Dp, u, act);
+    if (act && u == 0) {
+      buf[j].ord = f32_to_ord(d);
+      buf[j].slot = slot;
+      buf[j].label = p.labels[slot];
+    }
+  }
+  __syncthreads();
+  bitonic_sort_cands(buf, p.sort_n, tid, 128, [] { __syncthreads(); });
+  const uint32_t nout = min(n, p.k);
+  for (uint32_t i = tid; i < p.k; i += 128) {
+    const bool ok = i < nout;
+    p.out_dist[(size_t)b * p.k + i] = ok ? ord_to_f32(buf[i].ord) : __int_as_float(0x7f800000);
+    p.out_labels[(size_t)b * p.k + i] = ok ? buf[i].label : ~0ull;
+  }
+  if (tid == 0) {
+    p.out_n[b] = nout;
+    uint32_t flag = 0;
+    if (n >= p.kprime && (uint64_t)p.kprime < p.n_rows) {
+      // survivors = the K' smallest approximate scores; rows outside have approx >= a[K'-1]
+      const float xmax = sqrtf(__uint_as_float(*p.max_norm_bits));
+      const float e = p.err_coef * sqrtf(p.qnorm[b]) * xmax + 1e-5f * xmax * xmax + 1e-30f;
+      const float gk = p.approx[(size_t)b * p.kprime + (p.k - 1)];
+      const float gK = p.approx[(size_t)b * p.kprime + (p.kprime - 1)];
+      if (!(gK > gk + 2.0f * e)) flag = 1;
+    }
+    p.flags[b] = flag;
+  }
+}
+
+struct TensorState {
+  uint32_t Dh = 0;
+  DevBuf max_norm;  // 1 x u32
+};
+
+TensorState *ts(vkgpu_index_impl *ix) { return reinterpret_cast<TensorState *>(ix->tensor_state); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------ host
+bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
+  (void)B;
+  return ix->tensor_ready && k <= 160 && ix->n >= 4096;
+}
+bool tensor_path_profitable(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
+  // one tensor pass costs about the same for 1..256 queries; the exact scan wins below ~64 queries
+  return ix->tensor_ready && B >= 64 && k <= 160 && ix->n >= 100000;
+}
+
+static uint32_t dh_of(uint32_t Dp) { return (Dp + 63) / 64 * 64; }
+
+void tensor_reserve(vkgpu_index_impl *ix, uint64_t rows) {
+  if (!ix->tensor_state) return;
+  const uint32_t Dh = ts(ix)->Dh;
+  ix->dXh.reserve(rows * (size_t)Dh * 2, true, ix->mut_stream);
+  ix->dNorm.reserve(rows * 4, true, ix->mut_stream);
+}
+
+void tensor_refresh_rows(vkgpu_index_impl *ix, uint64_t first, uint64_t n) {
+  if (!ix->tensor_state || n == 0) return;
+  TensorState *t = ts(ix);
+  const uint32_t blocks = (uint32_t)std::min<uint64_t>((n + 7) / 8, 148 * 16);
+  to_bf16_rows_kernel<<<blocks, 256, 0, ix->mut_stream>>>(ix->dX.as<float>(), ix->Dp, ix->dXh.as<__nv_bfloat16>(), t->Dh,
+                                                          ix->dNorm.as<float>(), first, n, t->max_norm.as<uint32_t>());
+  VK_CUDA(cudaGetLastError());
+  ix->kernels++;
+}
+
+void tensor_move_row(vkgpu_index_impl *ix, uint64_t from, uint64_t to) {
+  if (!ix->tensor_state) return;
+  const uint32_t Dh = ts(ix)->Dh;
+  VK_CUDA(cudaMemcpyAsync(ix->dXh.as<uint8_t>() + to * Dh * 2, ix->dXh.as<uint8_t>() + from * Dh * 2, (size_t)Dh * 2,
+                          cudaMemcpyDeviceToDevice, ix->mut_stream));
+  VK_CUDA(cudaMemcpyAsync(ix->dNorm.as<float>() + to, ix->dNorm.as<float>() + from, 4, cudaMemcpyDeviceToDevice,
+                          ix->mut_stream));
+}
+
+void tensor_prepare(vkgpu_index_impl *ix) {
+  if (ix->tensor_ready) return;
+  TensorState *t = new TensorState();
+  t->Dh = dh_of(ix->Dp);
+  ix->tensor_state = t;
+  t->max_norm.reserve(4);
+  VK_CUDA(cudaMemsetAsync(t->max_norm.p, 0, 4, ix->mut_stream));
+  const uint64_t rows = std::max<uint64_t>(ix->phys_cap, 1);
+  ix->dXh.reserve(rows * (size_t)t->Dh * 2);
+  ix->dNorm.reserve(rows * 4);
+  tensor_refresh_rows(ix, 0, ix->n);
+  VK_CUDA(cudaStreamSynchronize(ix->mut_stream));
+  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  VK_CUDA(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  ix->tensor_ready = true;
+}
+
+void tensor_release(vkgpu_index_impl *ix) {
+  ix->dXh.release();
+  ix->dNorm.release();
+  if (ix->tensor_state) {
+    ts(ix)->max_norm.release();
+    delete ts(ix);
+    ix->tensor_state = nullptr;
+  }
+  ix->tensor_ready = false;
+}
+
+static uint32_t next_pow2_u32(uint32_t v) {
+  uint32_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// Queries are already staged fp32 in c->q_pad ([Bpad8][Dp], zero padded).  Leaves final results in c->out_*.
+void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff) {
+  TensorState *t = ts(ix);
+  cudaStream_t s = c->cur;
+  const uint32_t Dh = t->Dh;
+  const uint32_t nq_tiles = (B + BN - 1) / BN;
+  const uint32_t Bpad = nq_tiles * BN;
+  const uint32_t kprime = (3 * k_eff + 64 + 127) / 128 * 128;  // survivors per query (k + margin)
+  const uint32_t cap = next_pow2_u32(kprime + BM + 1) < 1024 ? 1024 : next_pow2_u32(kprime + BM + 1);
+  const uint32_t total_tiles = (uint32_t)((ix->n + BM - 1) / BM);
+  uint32_t slabs = std::max<uint32_t>(1, ix->num_sms / nq_tiles);
+  slabs = std::min(slabs, total_tiles);
+
+  // bf16 queries [Bpad][Dh] + squared norms
+  c->scratch0.reserve((size_t)Bpad * Dh * 2);
+  c->scratch1.reserve((size_t)Bpad * 4);
+  VK_CUDA(cudaMemsetAsync(c->scratch0.p, 0, (size_t)Bpad * Dh * 2, s));
+  to_bf16_rows_kernel<<<std::max<uint32_t>(1, (B + 7) / 8), 256, 0, s>>>(c->q_pad.as<float>(), ix->Dp,
+                                                                        c->scratch0.as<__nv_bfloat16>(), Dh,
+                                                                        c->scratch1.as<float>(), 0, B, nullptr);
+  VK_CUDA(cudaGetLastError());
+
+  const size_t nlists = (size_t)nq_tiles * slabs * BN;
+  c->ws.reserve(nlists * cap * sizeof(Cand));
+  c->ws_cnt.reserve(nlists * 4);
+  c->scratch2.reserve((size_t)Bpad * 4 + (size_t)B * 4);  // gthr [Bpad] + flags [B]
+  VK_CUDA(cudaMemsetAsync(c->scratch2.p, 0xff, (size_t)Bpad * 4, s));
+
+  CUtensorMap tmA, tmB;
+  make_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ix->dXh.p, Dh, ix->n, (uint64_t)Dh * 2, BK, BM,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+  make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->scratch0.p, Dh, Bpad, (uint64_t)Dh * 2, BK, BN,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+
+  TensorParams tp{};
+  tp.xnorm = ix->dNorm.as<float>();
+  tp.n_rows = ix->n;
+  tp.kchunks = Dh / BK;
+  tp.nq_tiles = nq_tiles;
+  tp.slabs = slabs;
+  tp.kprime = kprime;
+  tp.cap = cap;
+  tp.ws = c->ws.as<Cand>();
+  tp.ws_cnt = c->ws_cnt.as<uint32_t>();
+  tp.gthr = c->scratch2.as<uint32_t>();
+  tp.metric_l2 = ix->metric_l2 ? 1 : 0;
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + (size_t)cap * sizeof(Cand) + 256 + BN * 8;
+  VK_REQUIRE(smem <= ix->smem_max, VKGPU_ERR_INTERNAL, "tensor kernel shared memory budget exceeded");
+  ix->prof_begin(c, KK_TENSOR);
+  flat_tensor_kernel<<<nq_tiles * slabs, TC_THREADS, smem, s>>>(tp, tmA, tmB);
+  VK_CUDA(cudaGetLastError());
+  ix->prof_end(c, KK_TENSOR);
+
+  // per-query top-K' by approximate score
+  c->scratch3.reserve((size_t)B * kprime * (4 + 8 + 4) + (size_t)B * 4);
+  float *ap_dist = c->scratch3.as<float>();
+  uint64_t *ap_lab = reinterpret_cast<uint64_t *>(ap_dist + (size_t)B * kprime);
+  uint32_t *ap_slot = reinterpret_cast<uint32_t *>(ap_lab + (size_t)B * kprime);
+  uint32_t *ap_n = ap_slot + (size_t)B * kprime;
+  MergeParams mp{};
+  mp.ws = tp.ws;
+  mp.ws_cnt = tp.ws_cnt;
+  mp.qt = BN;
+  mp.slabs = slabs;
+  mp.cap = cap;
+  mp.k = kprime;
+  mp.sort_n = std::max<uint32_t>(1024, next_pow2_u32(2 * kprime));
+  mp.out_dist = ap_dist;
+  mp.out_labels = ap_lab;
+  mp.out_slots = ap_slot;
+  mp.out_n = ap_n;
+  mp.k_limit = nullptr;
+  ix->prof_begin(c, KK_MERGE);
+  launch_topk_merge(B, s, mp);
+  ix->prof_end(c, KK_MERGE);
+
+  // exact re-rank + proof
+  c->out_dist.reserve((size_t)B * k_eff * 4);
+  c->out_labels.reserve((size_t)B * k_eff * 8);
+  c->out_n.reserve((size_t)B * 4);
+  RerankParams rp{};
+  rp.X = ix->dX.as<float>();
+  rp.Dp = ix->Dp;
+  rp.labels = ix->dLabels.as<uint64_t>();
+  rp.Q = c->q_pad.as<float>();
+  rp.qnorm = c->scratch1.as<float>();
+  rp.max_norm_bits = t->max_norm.as<uint32_t>();
+  rp.approx = ap_dist;
+  rp.slots = ap_slot;
+  rp.napprox = ap_n;
+  rp.kprime = kprime;
+  rp.k = k_eff;
+  rp.sort_n = next_pow2_u32(kprime);
+  rp.n_rows = ix->n;
+  // bf16 rounding of both operands: |x~.q~ - x.q| <= (2^-8 + 2^-16)|x||q|; tensor-core fp32 accumulation adds
+  // < 2e-4|x||q|.  L2 score = |x|^2 - 2 x.q doubles it.
+  const float dot_err = 0.00390625f * 1.02f + 2e-4f;
+  rp.err_coef = ix->metric_l2 ? 2.0f * dot_err : dot_err;
+  rp.out_dist = c->out_dist.as<float>();
+  rp.out_labels = c->out_labels.as<uint64_t>();
+  rp.out_n = c->out_n.as<uint32_t>();
+  rp.flags = c->scratch2.as<uint32_t>() + Bpad;
+  const size_t rsmem = (size_t)rp.sort_n * sizeof(Cand) + (size_t)ix->Dp * 4;
+  ix->prof_begin(c, KK_RERANK);
+  if (ix->metric_l2)
+    rerank_kernel<true><<<B, 128, rsmem, s>>>(rp);
+  else
+    rerank_kernel<false><<<B, 128, rsmem, s>>>(rp);
+  VK_CUDA(cudaGetLastError());
+  ix->prof_end(c, KK_RERANK);
+  ix->kernels += 4;
+  ix->last_qt = BN;
+  ix->last_passes = nq_tiles;
+
+  // queries whose margin was too thin are re-run on the exact scan (GPU), results patched in place
+  c->h_misc.reserve((size_t)B * 4);
+  VK_CUDA(cudaMemcpyAsync(c->h_misc.p, rp.flags, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  VK_CUDA(cudaStreamSynchronize(s));
+  std::vector<uint32_t> redo;
+  for (uint32_t b = 0; b < B; b++)
+    if (c->h_misc.as<uint32_t>()[b]) redo.push_back(b);
+  if (!redo.empty()) {
+    ix->tensor_fallbacks += redo.size();
+    CtxLease lease2(ix);
+    SearchCtx *c2 = lease2.c;
+    c2->cur = s;
+    const uint32_t R = (uint32_t)redo.size();
+    const uint32_t Rpad = (R + kScanMaxQt - 1) / kScanMaxQt * kScanMaxQt;
+    c2->q_pad.reserve((size_t)Rpad * ix->Dp * 4);
+    VK_CUDA(cudaMemsetAsync(c2->q_pad.p, 0, (size_t)Rpad * ix->Dp * 4, s));
+    for (uint32_t i = 0; i < R; i++)
+      VK_CUDA(cudaMemcpyAsync(c2->q_pad.as<float>() + (size_t)i * ix->Dp, c->q_pad.as<float>() + (size_t)redo[i] * ix->Dp,
+                              (size_t)ix->Dp * 4, cudaMemcpyDeviceToDevice, s));
+    flat_exact_search_device(ix, c2, R, k_eff, nullptr, nullptr, false, ix->n);
+    for (uint32_t i = 0; i < R; i++) {
+      VK_CUDA(cudaMemcpyAsync(c->out_dist.as<float>() + (size_t)redo[i] * k_eff, c2->out_dist.as<float>() + (size_t)i * k_eff,
+                              (size_t)k_eff * 4, cudaMemcpyDeviceToDevice, s));
+      VK_CUDA(cudaMemcpyAsync(c->out_labels.as<uint64_t>() + (size_t)redo[i] * k_eff,
+                              c2->out_labels.as<uint64_t>() + (size_t)i * k_eff, (size_t)k_eff * 8,
+                              cudaMemcpyDeviceToDevice, s));
+      VK_CUDA(cudaMemcpyAsync(c->out_n.as<uint32_t>() + redo[i], c2->out_n.as<uint32_t>() + i, 4,
+                              cudaMemcpyDeviceToDevice, s));
+    }
+    VK_CUDA(cudaStreamSynchronize(s));
+  }
+}
+
 }  // namespace vkgpu
