@@ -303,9 +303,9 @@ def main():
             td = torch.from_numpy(out_d).to(dev)
             tl = torch.from_numpy(out_l.view(np.int64)).to(dev)
             tn = torch.from_numpy(out_n.view(np.int32)).to(dev)
-            dist.all_gather_into_tensor(out[3], td)
-            dist.all_gather_into_tensor(out[4], tl)
-            dist.all_gather_into_tensor(out[5], tn)
+            dist.all_gather_into_tensor(out[3].view(world * B, k), td)
+            dist.all_gather_into_tensor(out[4].view(world * B, k), tl)
+            dist.all_gather_into_tensor(out[5].view(world * B), tn)
             L.check(lib.vkgpu_merge_topk_device(dev.index, out[3].data_ptr(), out[4].data_ptr(), out[5].data_ptr(),
                                                 world, B, k, out[6].data_ptr(), out[7].data_ptr(), out[8].data_ptr(),
                                                 sptr))

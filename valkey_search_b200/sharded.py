@@ -69,9 +69,10 @@ class ShardedFlat:
         if self.world == 1:
             return loc_d, loc_l, loc_n
         # the single exchange step of the path: B*k*12 bytes per rank
-        self.dist.all_gather_into_tensor(all_d, loc_d)
-        self.dist.all_gather_into_tensor(all_l, loc_l)
-        self.dist.all_gather_into_tensor(all_n, loc_n)
+        G = self.world
+        self.dist.all_gather_into_tensor(all_d.view(G * B, k), loc_d)
+        self.dist.all_gather_into_tensor(all_l.view(G * B, k), loc_l)
+        self.dist.all_gather_into_tensor(all_n.view(G * B), loc_n)
         L.check(self._lib.vkgpu_merge_topk_device(dev.index, all_d.data_ptr(), all_l.data_ptr(), all_n.data_ptr(),
                                                   self.world, B, k, mer_d.data_ptr(), mer_l.data_ptr(),
                                                   mer_n.data_ptr(), stream_ptr))
