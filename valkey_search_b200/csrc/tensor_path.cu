@@ -124,15 +124,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint8_t *sA = smem;                                   // [STAGES][16 KB]
   uint8_t *sB = smem + STAGES * A_STAGE_BYTES;          // [STAGES][32 KB]
   uint8_t *tail = sB + STAGES * B_STAGE_BYTES;
-  Cand *scratch = reinterpret_cast<Cand *>(tail);       // [cap]  shrink sort buffer
-  uint8_t *ctl = tail + (size_t)p.cap * sizeof(Cand);
+  Cand *scratch = reinterpret_cast<Cand *>(tail);       // [4 warps][kprime]  shrink compaction buffers
+  uint8_t *ctl = tail + (size_t)4 * p.kprime * sizeof(Cand);
   uint64_t *full = reinterpret_cast<uint64_t *>(ctl);   // [STAGES]
   uint64_t *empty = full + STAGES;                      // [STAGES]
   uint64_t *tfull = empty + STAGES;                     // [2]
   uint64_t *tempty = tfull + 2;                         // [2]
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
-  uint32_t *shrink_mask = tmem_slot + 4;                // [BN/32]
-  float *thrf = reinterpret_cast<float *>(shrink_mask + BN / 32);  // [BN] float thresholds (gate)
+  float *thrf = reinterpret_cast<float *>(tmem_slot + 4);          // [BN] float thresholds (gate)
   uint32_t *cnt = reinterpret_cast<uint32_t *>(thrf + BN);         // [BN]
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -154,7 +153,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     thrf[i] = __int_as_float(0x7f800000);
     cnt[i] = 0;
   }
-  if (tid < BN / 32) shrink_mask[tid] = 0;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(TMEM_COLS)
@@ -216,10 +214,59 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t et = tid - 128;                 // 0..127 = row inside the tile = TMEM lane
     const uint32_t lane_base = (warp & 3) * 32;
     Cand *my_ws = p.ws + ((size_t)qtile * p.slabs + slab) * BN * p.cap;
+    // One warp trims query c's candidate list to the K' best: radix-select the K'-th smallest score with the
+    // list's keys held 32 per lane in registers (32 bit-rounds of count + shuffle-reduce), then compact the
+    // survivors through a per-warp shared-memory buffer.
+    auto warp_shrink = [&](uint32_t c) {
+      const uint32_t n = cnt[c];
+      Cand *wscr = scratch + (size_t)(warp & 3) * p.kprime;
+      Cand *buf = my_ws + (size_t)c * p.cap;
+      uint32_t o[32];
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const uint32_t idx = i * 32 + lane;
+        o[i] = idx < n ? buf[idx].ord : kOrdInf;
+      }
+      uint32_t prefix = 0, rem = p.kprime;
+      for (int bit = 31; bit >= 0; bit--) {
+        const uint32_t hi_mask = bit == 31 ? 0u : ~((2u << bit) - 1u);
+        uint32_t c0n = 0;
+#pragma unroll
+        for (int i = 0; i < 32; i++) c0n += ((o[i] & hi_mask) == prefix && !((o[i] >> bit) & 1u)) ? 1u : 0u;
+#pragma unroll
+        for (int sft = 16; sft > 0; sft >>= 1) c0n += __shfl_xor_sync(0xffffffffu, c0n, sft);
+        if (rem > c0n) {
+          prefix |= 1u << bit;
+          rem -= c0n;
+        }
+      }
+      const uint32_t T = prefix;  // K'-th smallest ord; `rem` of the entries equal to T are still needed
+      uint32_t base = 0, ties_taken = 0;
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const uint32_t idx = i * 32 + lane;
+        const bool tie = o[i] == T && idx < n;
+        const uint32_t tb = __ballot_sync(0xffffffffu, tie);
+        const bool keep = (o[i] < T) || (tie && ties_taken + __popc(tb & ((1u << lane) - 1)) < rem);
+        ties_taken += __popc(tb);
+        const uint32_t kb = __ballot_sync(0xffffffffu, keep);
+        if (keep) wscr[base + __popc(kb & ((1u << lane) - 1))] = buf[idx];
+        base += __popc(kb);
+      }
+      __syncwarp();
+      for (uint32_t i = lane; i < p.kprime; i += 32) buf[i] = wscr[i];
+      if (lane == 0) {
+        cnt[c] = p.kprime;
+        thrf[c] = fminf(thrf[c], ord_to_f32(T));
+        atomicMin(&p.gthr[qtile * BN + c], T);
+      }
+      __syncwarp();
+    };
     uint32_t t = 0;
     for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
       // refresh the gate thresholds from the running global ones (other slabs tighten them too)
-      for (uint32_t c = et; c < BN; c += EPI_THREADS) {
+      // (query c belongs to epilogue warp c & 3 for refresh and shrink alike, so thrf[c]/cnt[c] have one writer)
+      for (uint32_t c = (warp & 3) + 4 * lane; c < BN; c += 128) {
         const uint32_t go = *reinterpret_cast<volatile uint32_t *>(&p.gthr[qtile * BN + c]);
         if (go != kOrdInf) thrf[c] = fminf(thrf[c], ord_to_f32(go));
       }
@@ -240,61 +287,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           const float dot = __uint_as_float(r[j]);
           // approximate score: L2 -> |x|^2 - 2 x.q (the |q|^2 term is constant per query); IP -> -x.q
           const float s = p.metric_l2 ? __fmaf_rn(-2.0f, dot, xn) : -dot;
-          if (valid && s <= thrf[c0 + j]) {
+          const bool pass = valid && s <= thrf[c0 + j];
+          // one shared-memory atomic per warp and column (not per lane): lanes that pass take consecutive slots
+          const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+          if (bal) {
             const uint32_t c = c0 + j;
-            const uint32_t pos = atomicAdd(&cnt[c], 1u);
-            Cand cd;
-            cd.ord = f32_to_ord(s);
-            cd.slot = (uint32_t)slot;
-            cd.label = slot;
-            my_ws[(size_t)c * p.cap + pos] = cd;  // pos < cap by the shrink rule below
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&cnt[c], (uint32_t)__popc(bal));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) {
+              Cand cd;
+              cd.ord = f32_to_ord(s);
+              cd.slot = (uint32_t)slot;
+              cd.label = slot;
+              my_ws[(size_t)c * p.cap + base + __popc(bal & ((1u << lane) - 1))] = cd;  // < cap by the shrink rule
+            }
           }
         }
       }
       tc_fence_before();
       mbar_arrive(&tempty[a]);  // accumulator may be overwritten
 
-      // ---- keep room for one more tile (<= BM appends per query per tile)
+      // ---- keep room for one more tile (<= BM appends per query per tile).  Each epilogue warp owns the
+      //      queries c = w, w+4, ...; a shrink is done by ONE warp: radix-select the K'-th smallest score
+      //      (32 keys per lane in registers, 32 ballot-free bit rounds), then compact the survivors.
       named_bar_sync(2, EPI_THREADS);
-      for (uint32_t c = et; c < BN; c += EPI_THREADS)
-        if (cnt[c] + BM > p.cap) atomicOr(&shrink_mask[c >> 5], 1u << (c & 31));
-      named_bar_sync(2, EPI_THREADS);
-      for (uint32_t w = 0; w < BN / 32; w++) {
-        uint32_t m = shrink_mask[w];
-        while (m) {
-          const uint32_t c = w * 32 + (__ffs(m) - 1);
-          m &= m - 1;
-          const uint32_t n = cnt[c];
-          Cand *buf = my_ws + (size_t)c * p.cap;
-          for (uint32_t i = et; i < p.cap; i += EPI_THREADS) {
-            Cand cd;
-            if (i < n) {
-              cd = buf[i];
-            } else {
-              cd.ord = kOrdInf;
-              cd.slot = 0xffffffffu;
-              cd.label = ~0ull;
-            }
-            scratch[i] = cd;
-          }
-          named_bar_sync(2, EPI_THREADS);
-          bitonic_sort_cands(scratch, p.cap, et, EPI_THREADS, [] { named_bar_sync(2, EPI_THREADS); });
-          const uint32_t keep = min(n, p.kprime);
-          for (uint32_t i = et; i < keep; i += EPI_THREADS) buf[i] = scratch[i];
-          if (et == 0) {
-            cnt[c] = keep;
-            if (keep == p.kprime) {
-              const uint32_t o = scratch[p.kprime - 1].ord;
-              thrf[c] = fminf(thrf[c], ord_to_f32(o));
-              atomicMin(&p.gthr[qtile * BN + c], o);
-            }
-          }
-          named_bar_sync(2, EPI_THREADS);
-        }
-      }
-      named_bar_sync(2, EPI_THREADS);
-      if (et < BN / 32) shrink_mask[et] = 0;
+      for (uint32_t c = warp & 3; c < BN; c += 4)
+        if (cnt[c] + BM > p.cap) warp_shrink(c);  // warp-uniform
     }
+    // final trim so the merge kernel reads at most K' entries per list
+    named_bar_sync(2, EPI_THREADS);
+    for (uint32_t c = warp & 3; c < BN; c += 4)
+      if (cnt[c] > p.kprime) warp_shrink(c);
     named_bar_sync(2, EPI_THREADS);
     for (uint32_t c = et; c < BN; c += EPI_THREADS)
       p.ws_cnt[((size_t)qtile * p.slabs + slab) * BN + c] = cnt[c];
@@ -416,11 +440,11 @@ TensorState *ts(vkgpu_index_impl *ix) { return reinterpret_cast<TensorState *>(i
 // ------------------------------------------------------------------------------------------------ host
 bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
   (void)B;
-  return ix->tensor_ready && k <= 160 && ix->n >= 4096;
+  return ix->tensor_ready && k <= 128 && ix->n >= 4096;  // K' = 3k+64 rounded to 128 <= 512
 }
 bool tensor_path_profitable(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
   // one tensor pass costs about the same for 1..256 queries; the exact scan wins below ~64 queries
-  return ix->tensor_ready && B >= 64 && k <= 160 && ix->n >= 100000;
+  return ix->tensor_ready && B >= 64 && k <= 128 && ix->n >= 100000;
 }
 
 static uint32_t dh_of(uint32_t Dp) { return (Dp + 63) / 64 * 64; }
@@ -494,7 +518,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   const uint32_t nq_tiles = (B + BN - 1) / BN;
   const uint32_t Bpad = nq_tiles * BN;
   const uint32_t kprime = (3 * k_eff + 64 + 127) / 128 * 128;  // survivors per query (k + margin)
-  const uint32_t cap = next_pow2_u32(kprime + BM + 1) < 1024 ? 1024 : next_pow2_u32(kprime + BM + 1);
+  const uint32_t cap = 1024;  // 32 keys per lane in the warp-level shrink
   const uint32_t total_tiles = (uint32_t)((ix->n + BM - 1) / BM);
   uint32_t slabs = std::max<uint32_t>(1, ix->num_sms / nq_tiles);
   slabs = std::min(slabs, total_tiles);
@@ -532,7 +556,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   tp.ws_cnt = c->ws_cnt.as<uint32_t>();
   tp.gthr = c->scratch2.as<uint32_t>();
   tp.metric_l2 = ix->metric_l2 ? 1 : 0;
-  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + (size_t)cap * sizeof(Cand) + 256 + BN * 8;
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + (size_t)4 * kprime * sizeof(Cand) + 256 + BN * 8;
   VK_REQUIRE(smem <= ix->smem_max, VKGPU_ERR_INTERNAL, "tensor kernel shared memory budget exceeded");
   ix->prof_begin(c, KK_TENSOR);
   flat_tensor_kernel<<<nq_tiles * slabs, TC_THREADS, smem, s>>>(tp, tmA, tmB);
