@@ -133,6 +133,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tempty + 2);
   float *thrf = reinterpret_cast<float *>(tmem_slot + 4);          // [BN] float thresholds (gate)
   uint32_t *cnt = reinterpret_cast<uint32_t *>(thrf + BN);         // [BN]
+  uint32_t *need = cnt + BN;                                       // [8] per-owner-warp shrink flags
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const uint32_t qtile = blockIdx.x % p.nq_tiles, slab = blockIdx.x / p.nq_tiles;
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     thrf[i] = __int_as_float(0x7f800000);
     cnt[i] = 0;
   }
+  if (tid < 8) need[tid] = 0;
   if (warp == 2) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"(TMEM_COLS)
@@ -262,15 +264,79 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       __syncwarp();
     };
+    // async TMEM -> register load of 32 accumulator columns (lane = tile row); completed by tmem_wait()
+    auto tmem_ld32_async = [&](uint32_t taddr, uint32_t (&r)[32]) {
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+            "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+            "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+            "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+          : "r"(taddr)
+          : "memory");
+    };
+    auto tmem_wait = [] { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); };
+
+    // Gate + append for 32 columns.  Fast path is branch-free: 32 scores against 32 thresholds -> a per-lane bit
+    // mask, ONE warp vote per 32 columns.  Only when some lane passes does the warp walk the set columns and
+    // append (one shared-memory atomic per warp and column; passing lanes take consecutive slots).
+    auto gate_chunk = [&](const uint32_t (&r)[32], uint32_t c0, float xn, bool valid, uint64_t slot) {
+      uint32_t m = 0;
+      const float4 *th4 = reinterpret_cast<const float4 *>(thrf + c0);
+#pragma unroll
+      for (int j4 = 0; j4 < 8; j4++) {
+        const float4 th = th4[j4];
+        // approximate score: L2 -> |x|^2 - 2 x.q (the |q|^2 term is constant per query); IP -> -x.q
+        const float s0 = p.metric_l2 ? __fmaf_rn(-2.0f, __uint_as_float(r[4 * j4 + 0]), xn) : -__uint_as_float(r[4 * j4 + 0]);
+        const float s1 = p.metric_l2 ? __fmaf_rn(-2.0f, __uint_as_float(r[4 * j4 + 1]), xn) : -__uint_as_float(r[4 * j4 + 1]);
+        const float s2 = p.metric_l2 ? __fmaf_rn(-2.0f, __uint_as_float(r[4 * j4 + 2]), xn) : -__uint_as_float(r[4 * j4 + 2]);
+        const float s3 = p.metric_l2 ? __fmaf_rn(-2.0f, __uint_as_float(r[4 * j4 + 3]), xn) : -__uint_as_float(r[4 * j4 + 3]);
+        m |= (s0 <= th.x ? 1u : 0u) << (4 * j4 + 0);
+        m |= (s1 <= th.y ? 1u : 0u) << (4 * j4 + 1);
+        m |= (s2 <= th.z ? 1u : 0u) << (4 * j4 + 2);
+        m |= (s3 <= th.w ? 1u : 0u) << (4 * j4 + 3);
+      }
+      if (!valid) m = 0;
+      const uint32_t any = __reduce_or_sync(0xffffffffu, m);
+      if (any == 0) return;
+#pragma unroll
+      for (int j = 0; j < 32; j++) {
+        if (!((any >> j) & 1u)) continue;  // warp-uniform
+        const bool pass = (m >> j) & 1u;
+        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+        const uint32_t c = c0 + j;
+        const uint32_t npass = __popc(bal);
+        uint32_t base = 0;
+        if (lane == 0) {
+          base = atomicAdd(&cnt[c], npass);
+          if (base + npass + BM > p.cap) atomicOr(&need[(c & 3) * 2 + (c >> 7)], 1u << ((c >> 2) & 31));
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (pass) {
+          const float dot = __uint_as_float(r[j]);
+          const float sc = p.metric_l2 ? __fmaf_rn(-2.0f, dot, xn) : -dot;
+          Cand cd;
+          cd.ord = f32_to_ord(sc);
+          cd.slot = (uint32_t)slot;
+          cd.label = slot;
+          my_ws[(size_t)c * p.cap + base + __popc(bal & ((1u << lane) - 1))] = cd;  // < cap by the shrink rule
+        }
+      }
+    };
+
     uint32_t t = 0;
     for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
-      // refresh the gate thresholds from the running global ones (other slabs tighten them too)
-      // (query c belongs to epilogue warp c & 3 for refresh and shrink alike, so thrf[c]/cnt[c] have one writer)
-      for (uint32_t c = (warp & 3) + 4 * lane; c < BN; c += 128) {
-        const uint32_t go = *reinterpret_cast<volatile uint32_t *>(&p.gthr[qtile * BN + c]);
-        if (go != kOrdInf) thrf[c] = fminf(thrf[c], ord_to_f32(go));
+      // every 8th tile: refresh the gate thresholds from the running global ones (other slabs tighten them too).
+      // Query c belongs to epilogue warp c & 3 for refresh and shrink alike, so thrf[c]/cnt[c] have one writer.
+      if ((t & 7) == 0) {
+        for (uint32_t c = (warp & 3) + 4 * lane; c < BN; c += 128) {
+          const uint32_t go = *reinterpret_cast<volatile uint32_t *>(&p.gthr[qtile * BN + c]);
+          if (go != kOrdInf) thrf[c] = fminf(thrf[c], ord_to_f32(go));
+        }
       }
-      named_bar_sync(2, EPI_THREADS);
+      named_bar_sync(2, EPI_THREADS);  // thresholds + previous tile's shrinks visible before any append
 
       const uint32_t a = t & 1;
       const uint64_t slot = (uint64_t)tile * BM + et;
@@ -278,42 +344,41 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const float xn = (valid && p.metric_l2) ? p.xnorm[slot] : 0.0f;
       mbar_wait(&tfull[a], (t >> 1) & 1);
       tc_fence_after();
+      const uint32_t tbase = tmem_base + (lane_base << 16) + a * BN;
+      uint32_t ra[32], rb[32];
+      tmem_ld32_async(tbase, ra);
+      tmem_wait();
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + (lane_base << 16) + a * BN + c0, r);
-#pragma unroll
-        for (int j = 0; j < 32; j++) {
-          const float dot = __uint_as_float(r[j]);
-          // approximate score: L2 -> |x|^2 - 2 x.q (the |q|^2 term is constant per query); IP -> -x.q
-          const float s = p.metric_l2 ? __fmaf_rn(-2.0f, dot, xn) : -dot;
-          const bool pass = valid && s <= thrf[c0 + j];
-          // one shared-memory atomic per warp and column (not per lane): lanes that pass take consecutive slots
-          const uint32_t bal = __ballot_sync(0xffffffffu, pass);
-          if (bal) {
-            const uint32_t c = c0 + j;
-            uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(&cnt[c], (uint32_t)__popc(bal));
-            base = __shfl_sync(0xffffffffu, base, 0);
-            if (pass) {
-              Cand cd;
-              cd.ord = f32_to_ord(s);
-              cd.slot = (uint32_t)slot;
-              cd.label = slot;
-              my_ws[(size_t)c * p.cap + base + __popc(bal & ((1u << lane) - 1))] = cd;  // < cap by the shrink rule
-            }
-          }
-        }
+      for (uint32_t c0 = 0; c0 < BN; c0 += 64) {
+        tmem_ld32_async(tbase + c0 + 32, rb);   // in flight while ra is gated
+        gate_chunk(ra, c0, xn, valid, slot);
+        tmem_wait();
+        if (c0 + 64 < BN) tmem_ld32_async(tbase + c0 + 64, ra);
+        gate_chunk(rb, c0 + 32, xn, valid, slot);
+        tmem_wait();
       }
       tc_fence_before();
       mbar_arrive(&tempty[a]);  // accumulator may be overwritten
 
-      // ---- keep room for one more tile (<= BM appends per query per tile).  Each epilogue warp owns the
-      //      queries c = w, w+4, ...; a shrink is done by ONE warp: radix-select the K'-th smallest score
-      //      (32 keys per lane in registers, 32 ballot-free bit rounds), then compact the survivors.
+      // ---- keep room for one more tile (<= BM appends per query per tile): the warp that owns a query trims
+      //      it when an append pushed it past cap - BM (flagged in `need` by the appender)
       named_bar_sync(2, EPI_THREADS);
-      for (uint32_t c = warp & 3; c < BN; c += 4)
-        if (cnt[c] + BM > p.cap) warp_shrink(c);  // warp-uniform
+      {
+        const uint32_t w = warp & 3;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          uint32_t bits = need[w * 2 + h];
+          if (bits == 0) continue;
+          if (lane == 0) need[w * 2 + h] = 0;
+          __syncwarp();
+          while (bits) {
+            const uint32_t i = __ffs(bits) - 1;
+            bits &= bits - 1;
+            const uint32_t c = ((h * 32 + i) << 2) | w;
+            if (cnt[c] + BM > p.cap) warp_shrink(c);
+          }
+        }
+      }
     }
     // final trim so the merge kernel reads at most K' entries per list
     named_bar_sync(2, EPI_THREADS);
@@ -556,7 +621,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   tp.ws_cnt = c->ws_cnt.as<uint32_t>();
   tp.gthr = c->scratch2.as<uint32_t>();
   tp.metric_l2 = ix->metric_l2 ? 1 : 0;
-  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + (size_t)4 * kprime * sizeof(Cand) + 256 + BN * 8;
+  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + (size_t)4 * kprime * sizeof(Cand) + 256 + BN * 8 + 64;
   VK_REQUIRE(smem <= ix->smem_max, VKGPU_ERR_INTERNAL, "tensor kernel shared memory budget exceeded");
   ix->prof_begin(c, KK_TENSOR);
   flat_tensor_kernel<<<nq_tiles * slabs, TC_THREADS, smem, s>>>(tp, tmA, tmB);
