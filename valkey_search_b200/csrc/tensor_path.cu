@@ -64,6 +64,8 @@ struct TensorParams {
   Cand *ws;                  // [nq_tiles][slabs][BN][cap]
   uint32_t *ws_cnt;          // [nq_tiles][slabs][BN]
   uint32_t *gthr;            // [nq_tiles*BN] shared running thresholds (ord), initialised to 0xffffffff
+  uint32_t *gsl;             // [nq_tiles*BN][slabs] per-slab upper bounds of the local j-th best score (ord)
+  uint32_t jrank;            // j = ceil(K'/slabs): slabs*j >= K' rows are <= max_s gsl[q][s]
   int metric_l2;
 };
 
@@ -231,10 +233,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       uint32_t prefix = 0, rem = p.kprime;
       for (int bit = 31; bit >= 0; bit--) {
-        const uint32_t hi_mask = bit == 31 ? 0u : ~((2u << bit) - 1u);
+        // prefix has zeros at `bit` and below: (o ^ prefix) >> bit == 0  <=>  high bits match and bit is 0
         uint32_t c0n = 0;
 #pragma unroll
-        for (int i = 0; i < 32; i++) c0n += ((o[i] & hi_mask) == prefix && !((o[i] >> bit) & 1u)) ? 1u : 0u;
+        for (int i = 0; i < 32; i++) c0n += (((o[i] ^ prefix) >> bit) == 0u) ? 1u : 0u;
 #pragma unroll
         for (int sft = 16; sft > 0; sft >>= 1) c0n += __shfl_xor_sync(0xffffffffu, c0n, sft);
         if (rem > c0n) {
@@ -278,6 +280,30 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           : "memory");
     };
     auto tmem_wait = [] { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); };
+
+    // Cheap upper bound of the j-th smallest score in query c's list: every lane takes the minimum of its
+    // strided share, the j-th smallest of the 32 lane minima bounds the j-th smallest overall from above.
+    // Published per slab; max over slabs bounds the GLOBAL K'-th best (slabs * j >= K'), so all CTAs gate on a
+    // threshold that tightens with the whole corpus seen so far, not just their own slab.
+    auto warp_publish = [&](uint32_t c) {
+      const uint32_t n = min(cnt[c], p.cap);
+      if (n < p.jrank || p.jrank > 32) return;  // warp-uniform
+      const Cand *buf = my_ws + (size_t)c * p.cap;
+      uint32_t m = kOrdInf;
+      for (uint32_t idx = lane; idx < n; idx += 32) m = min(m, buf[idx].ord);
+      uint32_t rank = 0;
+#pragma unroll
+      for (int l = 0; l < 32; l++) {
+        const uint32_t ml = __shfl_sync(0xffffffffu, m, l);
+        rank += (ml < m || (ml == m && (uint32_t)l < lane)) ? 1u : 0u;
+      }
+      const uint32_t who = __ballot_sync(0xffffffffu, rank == p.jrank - 1);
+      const uint32_t est = __shfl_sync(0xffffffffu, m, __ffs(who) - 1);
+      if (lane == 0 && est != kOrdInf) {
+        uint32_t *dst = &p.gsl[((size_t)qtile * BN + c) * p.slabs + slab];
+        if (est < *dst) *reinterpret_cast<volatile uint32_t *>(dst) = est;
+      }
+    };
 
     // Gate + append for 32 columns.  Fast path is branch-free: 32 scores against 32 thresholds -> a per-lane bit
     // mask, ONE warp vote per 32 columns.  Only when some lane passes does the warp walk the set columns and
@@ -330,9 +356,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
       // every 8th tile: refresh the gate thresholds from the running global ones (other slabs tighten them too).
       // Query c belongs to epilogue warp c & 3 for refresh and shrink alike, so thrf[c]/cnt[c] have one writer.
-      if ((t & 7) == 0) {
+      if ((t & 7) == 0 || ((t - 1) & t) == 0) {
         for (uint32_t c = (warp & 3) + 4 * lane; c < BN; c += 128) {
-          const uint32_t go = *reinterpret_cast<volatile uint32_t *>(&p.gthr[qtile * BN + c]);
+          uint32_t go = *reinterpret_cast<volatile uint32_t *>(&p.gthr[qtile * BN + c]);
+          const volatile uint32_t *gs = p.gsl + ((size_t)qtile * BN + c) * p.slabs;
+          uint32_t mx = 0;
+          for (uint32_t sidx = 0; sidx < p.slabs; sidx++) mx = max(mx, gs[sidx]);
+          go = min(go, mx);
           if (go != kOrdInf) thrf[c] = fminf(thrf[c], ord_to_f32(go));
         }
       }
@@ -378,6 +408,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (cnt[c] + BM > p.cap) warp_shrink(c);
           }
         }
+        // publish rounds at tiles 1,2,4,8,... and every 128th: bounds tighten while lists are still short
+        if (((t + 1) & t) == 0 || (t & 127) == 127)
+          for (uint32_t c = w; c < BN; c += 4) warp_publish(c);
       }
     }
     // final trim so the merge kernel reads at most K' entries per list
@@ -600,8 +633,10 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   const size_t nlists = (size_t)nq_tiles * slabs * BN;
   c->ws.reserve(nlists * cap * sizeof(Cand));
   c->ws_cnt.reserve(nlists * 4);
-  c->scratch2.reserve((size_t)Bpad * 4 + (size_t)B * 4);  // gthr [Bpad] + flags [B]
+  c->scratch2.reserve((size_t)Bpad * 4 + (size_t)B * 4 + (size_t)Bpad * slabs * 4);  // gthr [Bpad] + flags [B] + gsl
   VK_CUDA(cudaMemsetAsync(c->scratch2.p, 0xff, (size_t)Bpad * 4, s));
+  uint32_t *d_gsl = c->scratch2.as<uint32_t>() + Bpad + B;
+  VK_CUDA(cudaMemsetAsync(d_gsl, 0xff, (size_t)Bpad * slabs * 4, s));
 
   CUtensorMap tmA, tmB;
   make_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ix->dXh.p, Dh, ix->n, (uint64_t)Dh * 2, BK, BM,
@@ -620,6 +655,8 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   tp.ws = c->ws.as<Cand>();
   tp.ws_cnt = c->ws_cnt.as<uint32_t>();
   tp.gthr = c->scratch2.as<uint32_t>();
+  tp.gsl = d_gsl;
+  tp.jrank = (kprime + slabs - 1) / slabs;
   tp.metric_l2 = ix->metric_l2 ? 1 : 0;
   const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + (size_t)4 * kprime * sizeof(Cand) + 256 + BN * 8 + 64;
   VK_REQUIRE(smem <= ix->smem_max, VKGPU_ERR_INTERNAL, "tensor kernel shared memory budget exceeded");
