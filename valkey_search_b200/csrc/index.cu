@@ -362,7 +362,13 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     k_eff = (uint32_t)std::min<uint64_t>(k, ix->n);
     bool use_tensor = false;
     if (ix->flat_path == VKGPU_PATH_TENSOR) use_tensor = true;
-    if (ix->flat_path == VKGPU_PATH_AUTO) use_tensor = tensor_path_profitable(ix, B, k_eff);
+    if (ix->flat_path == VKGPU_PATH_AUTO && B >= 64 && k_eff <= 128 && ix->n >= 100000) {
+      // first large batch: build the bf16 mirror (searches only read the fp32 rows, so this is safe under
+      // the shared lock; tensor_mu makes it happen once)
+      std::lock_guard<std::mutex> tl(ix->tensor_mu);
+      if (!ix->tensor_ready) tensor_prepare(ix);
+      use_tensor = true;
+    }
     if (use_tensor && tensor_path_supported(ix, B, k_eff))
       tensor_search_device(ix, c, B, k_eff);
     else
