@@ -139,6 +139,127 @@ def gen_block(torch, dev, block, rows, D):
     return torch.randn((rows, D), generator=g, device=dev, dtype=torch.float32)
 
 
+def hnsw_workload(args):
+    """BASELINE configs[2] shape: HNSW M=16 efSearch=128, 768-d fp32, k=10, batch=512 on one B200.  The graph is
+    built on the GPU (single-GPU build, as the north star says); recall@10 is measured against exact FLAT ground
+    truth from the GPU FLAT path; the CPU arm searches the SAME graph (exported through vkgpu_hnsw_export and
+    loaded into the oracle) with all host threads, so QPS compares like for like and results must be identical."""
+    import numpy as np
+    import torch
+    import valkey_search_b200 as V
+    from valkey_search_b200 import _lib as L
+    import oracle_lib as O
+
+    N = args.rows if args.rows != 10_000_000 else 1_000_000
+    D, k, ef, M, efc = args.dim, (10 if args.k == 100 else args.k), args.ef, 16, 200
+    B = 512 if args.batch == 1024 else args.batch
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    peaks = load_peaks()
+    lib = L.lib()
+    g = torch.Generator(device=dev)
+    g.manual_seed(777)
+    centres = torch.randn((1024, D), generator=g, device=dev) * 1.0
+    assign = torch.randint(0, 1024, (N,), generator=g, device=dev)
+    X = centres[assign] + 0.3 * torch.randn((N, D), generator=g, device=dev)
+    qa = torch.randint(0, 1024, (B,), generator=g, device=dev)
+    dQ = (centres[qa] + 0.3 * torch.randn((B, D), generator=g, device=dev)).contiguous()
+    torch.cuda.synchronize()
+    ix = V.VectorHNSW(D, V.DistanceMetric.L2, initial_cap=N, m=M, ef_construction=efc, ef_runtime=ef, max_batch=B)
+    t0 = time.perf_counter()
+    L.check(lib.vkgpu_add_batch_device(ix.handle(), None, X.data_ptr(), N))
+    build_s = time.perf_counter() - t0
+    log(f"[hnsw] GPU build of {N} x {D}: {build_s:.1f}s ({N / build_s:.0f} inserts/s)")
+    flat = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+    L.check(lib.vkgpu_add_batch_device(flat.handle(), None, X.data_ptr(), N))
+    mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
+    od, ol, on = mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32)
+    td, tl, tn = mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32)
+    L.check(lib.vkgpu_search_batch_device(flat.handle(), dQ.data_ptr(), B, k, 0, td.data_ptr(), tl.data_ptr(),
+                                          tn.data_ptr(), None))
+    W, K = max(args.warmup, 3), args.steps
+    for _ in range(W):
+        L.check(lib.vkgpu_search_batch_device(ix.handle(), dQ.data_ptr(), B, k, ef, od.data_ptr(), ol.data_ptr(),
+                                              on.data_ptr(), None))
+    torch.cuda.synchronize()
+    L.check(lib.vkgpu_set_profiling(ix.handle(), 1))
+    st0 = ix.stats()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(K):
+        L.check(lib.vkgpu_search_batch_device(ix.handle(), dQ.data_ptr(), B, k, ef, od.data_ptr(), ol.data_ptr(),
+                                              on.data_ptr(), None))
+    e1.record()
+    torch.cuda.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    tm = L.Timings()
+    L.check(lib.vkgpu_get_timings(ix.handle(), C.byref(tm)))
+    st1 = ix.stats()
+    value = B * K / (ms_total / 1e3)
+    truth = tl.cpu().numpy()
+    got = ol.cpu().numpy()
+    recall = float(np.mean([len(set(got[b].tolist()) & set(truth[b].tolist())) / float(k) for b in range(B)]))
+    # e2e through host buffers
+    hQ = dQ.cpu().numpy()
+    hd, hl, hn = np.empty((B, k), np.float32), np.empty((B, k), np.uint64), np.empty(B, np.uint32)
+    t0 = time.perf_counter()
+    for _ in range(K):
+        L.check(lib.vkgpu_search_batch(ix.handle(), hQ.ctypes.data, B, k, ef, None, 0, hd.ctypes.data, hl.ctypes.data,
+                                       hn.ctypes.data))
+    e2e = B * K / (time.perf_counter() - t0)
+    hnsw_ms, hnsw_n = tm.ms[4], int(tm.launches[4])
+    evals = (st1.distance_evals) / max(B, 1)   # counters hold the last call's totals
+    bytes_algo = float(st1.distance_evals) * D * 4 + float(st1.hops) * 136
+    ach = bytes_algo / (hnsw_ms / max(hnsw_n, 1) / 1e3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "hnsw_search_kernel<L2> (one CTA per query, TMA-staged rows)",
+                "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": None,
+                "peak_source": f"{peaks['source']} copy bandwidth", "bytes_per_launch": bytes_algo,
+                "distance_evals_per_query": evals, "hops_per_query": st1.hops / max(B, 1),
+                "kernel_ms_avg": hnsw_ms / max(hnsw_n, 1)}
+    cpu_base = None
+    if not args.no_cpu_baseline:
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        from test_hnsw_gpu import export_graph
+        ix._m = M
+        gexp = export_graph(ix)
+        n = len(gexp["levels"])
+        off = np.zeros(n, np.uint64)
+        blocks = 0
+        for i in range(n):
+            off[i] = blocks
+            blocks += max(int(gexp["levels"][i]), 0)
+        upl = np.zeros((max(blocks, 1), M), np.uint32)
+        upc = np.zeros(max(blocks, 1), np.uint32)
+        for (i, lv), ids in gexp["upper"].items():
+            b = int(off[i]) + lv - 1
+            upc[b] = ids.size
+            upl[b, : ids.size] = ids
+        orc = O.PortHnsw(D, O.L2, M, efc, ef)
+        orc.import_arrays(gexp["levels"], gexp["labels"], gexp["deleted"], gexp["links0"], gexp["cnt0"], upl, upc, off,
+                          gexp["maxlevel"], gexp["enterpoint"], X.cpu().numpy())
+        threads = host_threads()
+        secs, cd, cl, cn = orc.search_mt(hQ, k, ef, threads)
+        same = bool(np.array_equal(cl, hl) and np.array_equal(cd.view(np.uint32), hd.view(np.uint32)))
+        cpu_base = {"value": B / secs, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": f"{B} queries, same GPU-built graph loaded into the CPU oracle, {threads} threads, "
+                              f"{secs:.2f}s; results identical to the GPU's: {same}"}
+    line = {"metric": f"kNN QPS @ recall (HNSW M=16 ef={ef}, {N}x{D} fp32, k={k}, batch={B})", "value": value,
+            "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
+            "scaling": "replicas only", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic clustered Gaussian (1024 centres, sigma 0.3), torch seed 777",
+            "config": {"workload": f"HNSW M=16 efc=200 ef={ef} {N}x{D} fp32 k={k} batch={B} (BASELINE configs[2] shape at "
+                                   f"{N} rows)", "rows": N},
+            "recall_at_k": recall, "build_seconds": build_s, "build_inserts_per_s": N / build_s,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 12 + B * 4},
+            "gpu_launches": int(st1.kernels_launched - st0.kernels_launched), "roofline": roofline,
+            "cpu_baseline": cpu_base, "clocks": clocks}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -153,7 +274,12 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--cpu-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="flat", choices=["flat", "hnsw"],
+                    help="flat = BASELINE configs[1] (the driver's default); hnsw = configs[2] at --rows")
+    ap.add_argument("--ef", type=int, default=128)
     args = ap.parse_args()
+    if args.workload == "hnsw":
+        return hnsw_workload(args)
 
     import numpy as np
     import torch

@@ -851,6 +851,37 @@ double vko_hnsw_search_mt(const vko_hnsw *g, const float *Q, size_t nq, size_t k
   return dt;
 }
 
+/* Loads a complete graph in the interchange layout of include/vkgpu.h (vkgpu_hnsw_export): lets the CPU
+ * oracle search a graph that was built elsewhere (e.g. by the GPU builder) — bench.py's HNSW cpu_baseline. */
+int vko_hnsw_import(vko_hnsw *g, uint64_t n, const int32_t *levels, const uint64_t *labels, const uint8_t *deleted,
+                    const uint32_t *links0, const uint32_t *cnt0, const uint32_t *upper_links,
+                    const uint32_t *upper_cnt, const uint64_t *upper_off, int32_t maxlevel, uint32_t enterpoint,
+                    const float *vecs) {
+  if (g->n != 0) return -1;
+  hnsw_reserve(g, n);
+  for (uint64_t i = 0; i < n; i++) {
+    g->levels[i] = levels[i];
+    g->labels[i] = labels[i];
+    g->flags[i] = deleted && deleted[i] ? 1 : 0;
+    if (g->flags[i]) g->num_deleted++;
+    g->cnt0[i] = (uint16_t)cnt0[i];
+    memcpy(g->link0 + i * g->maxM0, links0 + i * g->maxM0, g->maxM0 * 4);
+    memcpy(g->X + i * g->dim, vecs + i * g->dim, g->dim * sizeof(float));
+    g->up[i] = levels[i] > 0 ? (uint32_t *)calloc((size_t)levels[i] * (1 + g->maxM), 4) : NULL;
+    for (int lv = 0; lv < levels[i]; lv++) {
+      uint64_t b = upper_off[i] + (uint64_t)lv;
+      uint32_t *blk = g->up[i] + (size_t)lv * (1 + g->maxM);
+      blk[0] = upper_cnt[b];
+      memcpy(blk + 1, upper_links + b * g->maxM, upper_cnt[b] * 4);
+    }
+    map_put(&g->lookup, labels[i], (uint32_t)i);
+  }
+  g->n = n;
+  g->maxlevel = maxlevel;
+  g->enterpoint = (int32_t)enterpoint;
+  return 0;
+}
+
 void vko_hnsw_info(const vko_hnsw *g, int64_t *info) {
   info[0] = (int64_t)g->n;
   info[1] = g->maxlevel;

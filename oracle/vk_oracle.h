@@ -64,6 +64,11 @@ size_t vko_hnsw_search(const vko_hnsw *g, const float *q, size_t k, size_t ef, c
                        size_t allow_nbits, float *out_d, uint64_t *out_l);
 double vko_hnsw_search_mt(const vko_hnsw *g, const float *Q, size_t nq, size_t k, size_t ef, int threads,
                           float *out_d, uint64_t *out_l, uint32_t *out_n);
+/* load a graph in the interchange layout of include/vkgpu.h (vkgpu_hnsw_export) into an EMPTY oracle index */
+int vko_hnsw_import(vko_hnsw *g, uint64_t n, const int32_t *levels, const uint64_t *labels, const uint8_t *deleted,
+                    const uint32_t *links0, const uint32_t *cnt0, const uint32_t *upper_links,
+                    const uint32_t *upper_cnt, const uint64_t *upper_off, int32_t maxlevel, uint32_t enterpoint,
+                    const float *vecs);
 /* graph export: info = {count, maxlevel, enterpoint, M, maxM0, num_deleted} */
 void vko_hnsw_info(const vko_hnsw *g, int64_t *info);
 int vko_hnsw_level(const vko_hnsw *g, uint32_t id);

@@ -7,6 +7,7 @@
 import ctypes as C
 import os
 import subprocess
+import sys
 
 import numpy as np
 
@@ -25,8 +26,8 @@ def build(force=False):
     """Compile the port (always possible) and the reference (only where /root/reference exists)."""
     so = os.path.join(ORACLE_DIR, "libvkoracle.so")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(ORACLE_DIR, "vk_oracle.c")):
-        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"])
-    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"])
+        subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "port"], stdout=sys.stderr)
+    subprocess.check_call(["make", "-s", "-C", ORACLE_DIR, "ref"], stdout=sys.stderr)
 
 
 _port = None
@@ -76,6 +77,7 @@ def port():
         _sig(lib, "vko_hnsw_links", C.c_uint32, [C.c_void_p, C.c_uint32, C.c_int, _u32p])
         _sig(lib, "vko_hnsw_vector", C.POINTER(C.c_float), [C.c_void_p, C.c_uint32])
         _sig(lib, "vko_hnsw_last_stats", None, [C.c_void_p, _u64p])
+        _sig(lib, "vko_hnsw_import", C.c_int, [C.c_void_p, C.c_uint64] + [C.c_void_p] * 8 + [C.c_int32, C.c_uint32, C.c_void_p])
         _port = lib
     return _port
 
@@ -272,6 +274,17 @@ class PortHnsw(_HnswCommon):
         n = np.zeros(nq, np.uint32)
         secs = self.lib.vko_hnsw_search_mt(self.h, Q, nq, k, ef, threads, d, l, n)
         return secs, d, l, n
+
+    def import_arrays(self, levels, labels, deleted, links0, cnt0, up_links, up_cnt, up_off, maxlevel, enterpoint, vecs):
+        arrs = [np.ascontiguousarray(levels, np.int32), np.ascontiguousarray(labels, np.uint64),
+                np.ascontiguousarray(deleted, np.uint8), np.ascontiguousarray(links0, np.uint32),
+                np.ascontiguousarray(cnt0, np.uint32), np.ascontiguousarray(up_links, np.uint32),
+                np.ascontiguousarray(up_cnt, np.uint32), np.ascontiguousarray(up_off, np.uint64)]
+        v = np.ascontiguousarray(vecs, np.float32)
+        rc = self.lib.vko_hnsw_import(self.h, len(arrs[0]), *[a.ctypes.data for a in arrs], int(maxlevel),
+                                      int(enterpoint), v.ctypes.data)
+        assert rc == 0
+        return rc
 
     def last_stats(self):
         s = np.zeros(2, np.uint64)
