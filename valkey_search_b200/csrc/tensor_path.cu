@@ -290,7 +290,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (n < p.jrank || p.jrank > 32) return;  // warp-uniform
       const Cand *buf = my_ws + (size_t)c * p.cap;
       uint32_t m = kOrdInf;
-      for (uint32_t idx = lane; idx < n; idx += 32) m = min(m, buf[idx].ord);
+      uint32_t idx = lane;
+      for (; idx + 96 < n; idx += 128) {  // 4 independent loads in flight
+        const uint32_t a0 = buf[idx].ord, a1 = buf[idx + 32].ord, a2 = buf[idx + 64].ord, a3 = buf[idx + 96].ord;
+        m = min(min(m, a0), min(min(a1, a2), a3));
+      }
+      for (; idx < n; idx += 32) m = min(m, buf[idx].ord);
       uint32_t rank = 0;
 #pragma unroll
       for (int l = 0; l < 32; l++) {
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
       // every 8th tile: refresh the gate thresholds from the running global ones (other slabs tighten them too).
       // Query c belongs to epilogue warp c & 3 for refresh and shrink alike, so thrf[c]/cnt[c] have one writer.
-      if ((t & 7) == 0 || ((t - 1) & t) == 0) {
+      if ((t & 15) == 0 || (((t - 1) & t) == 0 && t <= 65)) {
         for (uint32_t c = (warp & 3) + 4 * lane; c < BN; c += 128) {
           uint32_t go = *reinterpret_cast<volatile uint32_t *>(&p.gthr[qtile * BN + c]);
           const volatile uint32_t *gs = p.gsl + ((size_t)qtile * BN + c) * p.slabs;
@@ -408,8 +413,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (cnt[c] + BM > p.cap) warp_shrink(c);
           }
         }
-        // publish rounds at tiles 1,2,4,8,... and every 128th: bounds tighten while lists are still short
-        if (((t + 1) & t) == 0 || (t & 127) == 127)
+        // publish rounds at tiles 1,2,4,...,64 and then every 256th: bounds tighten while lists are still short
+        if ((((t + 1) & t) == 0 && t < 64) || (t & 255) == 255)
           for (uint32_t c = w; c < BN; c += 4) warp_publish(c);
       }
     }
