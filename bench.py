@@ -351,7 +351,7 @@ def main():
 
     lo, hi = shard_bounds(N, world, rank)
     n_local = hi - lo
-    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=n_local, max_batch=B)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=n_local, max_batch=B, device=local_rank)
     lib = L.lib()
     t0 = time.perf_counter()
     BLK = 1_000_000

@@ -415,6 +415,116 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const MergePa
 }
 }  // namespace
 
+// Selection-based merge for APPROXIMATE scores (tensor path): the K best of all lists without sorting them —
+// a 3-pass (11/11/10-bit) radix select finds the K-th smallest score, entries below it (and just enough ties,
+// any of them) are gathered into shared memory and only those K are sorted.  Which of several equal-score rows
+// survives is immaterial there: the re-rank kernel's proof depends on score VALUES only.
+namespace {
+__global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const MergeParams p) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  Cand *buf = reinterpret_cast<Cand *>(msm);                                   // [sort_n]
+  uint32_t *hist = reinterpret_cast<uint32_t *>(msm + (size_t)p.sort_n * sizeof(Cand));  // [2048]
+  __shared__ uint32_t part[MERGE_THREADS];
+  __shared__ uint32_t s_prefix, s_rank, s_pos, s_tie, s_total;
+  const uint32_t b = blockIdx.x, tid = threadIdx.x;
+  const uint32_t qtile = b / p.qt, qi = b % p.qt;
+  const uint32_t K = p.k;
+  auto list_of = [&](uint32_t s, uint32_t &n) -> const Cand * {
+    const size_t li = ((size_t)qtile * p.slabs + s) * p.qt + qi;
+    n = min(p.ws_cnt[li], p.cap);
+    return p.ws + li * p.cap;
+  };
+  if (tid == 0) {
+    uint32_t tot = 0;
+    for (uint32_t s = 0; s < p.slabs; s++) {
+      uint32_t n;
+      list_of(s, n);
+      tot += n;
+    }
+    s_total = tot;
+    s_prefix = 0;
+    s_rank = K;
+    s_pos = 0;
+    s_tie = 0;
+  }
+  for (uint32_t i = tid; i < p.sort_n; i += MERGE_THREADS) {
+    buf[i].ord = kOrdInf;
+    buf[i].slot = 0xffffffffu;
+    buf[i].label = ~0ull;
+  }
+  __syncthreads();
+  const uint32_t total = s_total;
+  uint32_t T = kOrdInf, quota = 0;
+  if (total > K) {
+    const int shifts[3] = {21, 10, 0};
+    const uint32_t widths[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; pass++) {
+      for (uint32_t i = tid; i < 2048; i += MERGE_THREADS) hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      const uint32_t hi_mask = pass == 0 ? 0u : ~((1u << (shifts[pass] + widths[pass])) - 1u);
+      for (uint32_t s = 0; s < p.slabs; s++) {
+        uint32_t n;
+        const Cand *src = list_of(s, n);
+        for (uint32_t i = tid; i < n; i += MERGE_THREADS) {
+          const uint32_t o = src[i].ord;
+          if ((o & hi_mask) == prefix) atomicAdd(&hist[(o >> shifts[pass]) & ((1u << widths[pass]) - 1u)], 1u);
+        }
+      }
+      __syncthreads();
+      uint32_t sum = 0;
+      for (uint32_t i = 0; i < 8; i++) sum += hist[tid * 8 + i];
+      part[tid] = sum;
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t rank = s_rank, acc = 0, seg = 0;
+        for (; seg < MERGE_THREADS; seg++) {
+          if (acc + part[seg] >= rank) break;
+          acc += part[seg];
+        }
+        uint32_t bin = seg * 8;
+        for (;; bin++) {
+          if (acc + hist[bin] >= rank) break;
+          acc += hist[bin];
+        }
+        s_prefix = prefix | (bin << shifts[pass]);
+        s_rank = rank - acc;  // rank inside the chosen bin
+      }
+      __syncthreads();
+    }
+    T = s_prefix;
+    quota = s_rank;  // entries equal to T still needed
+  }
+  for (uint32_t s = 0; s < p.slabs; s++) {
+    uint32_t n;
+    const Cand *src = list_of(s, n);
+    for (uint32_t i = tid; i < n; i += MERGE_THREADS) {
+      const Cand c = src[i];
+      bool keep = c.ord < T;
+      if (!keep && c.ord == T && total > K) keep = atomicAdd(&s_tie, 1u) < quota;
+      if (total <= K) keep = true;
+      if (keep) buf[atomicAdd(&s_pos, 1u)] = c;
+    }
+  }
+  __syncthreads();
+  const uint32_t have = min(s_pos, K);
+  bitonic_sort_cands(buf, p.sort_n, tid, MERGE_THREADS, [] { __syncthreads(); });
+  for (uint32_t i = tid; i < K; i += MERGE_THREADS) {
+    const bool ok = i < have;
+    p.out_dist[(size_t)b * K + i] = ok ? ord_to_f32(buf[i].ord) : __int_as_float(0x7f800000);
+    p.out_labels[(size_t)b * K + i] = ok ? buf[i].label : ~0ull;
+    if (p.out_slots) p.out_slots[(size_t)b * K + i] = ok ? buf[i].slot : 0xffffffffu;
+  }
+  if (tid == 0) p.out_n[b] = have;
+}
+}  // namespace
+
+void launch_topk_select_merge(uint32_t B, cudaStream_t stream, const MergeParams &p) {
+  const size_t smem = (size_t)p.sort_n * sizeof(Cand) + 2048 * 4;
+  topk_select_merge_kernel<<<B, MERGE_THREADS, smem, stream>>>(p);
+  VK_CUDA(cudaGetLastError());
+}
+
 void launch_topk_merge(uint32_t B, cudaStream_t stream, const MergeParams &p) {
   size_t smem = (size_t)p.sort_n * sizeof(Cand);
   static bool attr_set = false;

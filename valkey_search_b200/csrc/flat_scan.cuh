@@ -62,5 +62,7 @@ struct MergeParams {
   const uint32_t *k_limit; // optional per-query cap on results (nullptr => k)
 };
 void launch_topk_merge(uint32_t B, cudaStream_t stream, const MergeParams &p);
+// same contract, for approximate scores: ties at the K-th score are broken arbitrarily; sort_n = pow2 >= k
+void launch_topk_select_merge(uint32_t B, cudaStream_t stream, const MergeParams &p);
 
 }  // namespace vkgpu

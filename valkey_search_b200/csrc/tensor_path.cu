@@ -361,7 +361,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
       // every 8th tile: refresh the gate thresholds from the running global ones (other slabs tighten them too).
       // Query c belongs to epilogue warp c & 3 for refresh and shrink alike, so thrf[c]/cnt[c] have one writer.
-      if ((t & 15) == 0 || (((t - 1) & t) == 0 && t <= 65)) {
+      if ((t & 7) == 0 || ((t - 1) & t) == 0) {
         for (uint32_t c = (warp & 3) + 4 * lane; c < BN; c += 128) {
           uint32_t go = *reinterpret_cast<volatile uint32_t *>(&p.gthr[qtile * BN + c]);
           const volatile uint32_t *gs = p.gsl + ((size_t)qtile * BN + c) * p.slabs;
@@ -413,8 +413,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             if (cnt[c] + BM > p.cap) warp_shrink(c);
           }
         }
-        // publish rounds at tiles 1,2,4,...,64 and then every 256th: bounds tighten while lists are still short
-        if ((((t + 1) & t) == 0 && t < 64) || (t & 255) == 255)
+        // publish rounds at tiles 1,2,4,8,... and every 128th: bounds tighten while lists are still short
+        if (((t + 1) & t) == 0 || (t & 127) == 127)
           for (uint32_t c = w; c < BN; c += 4) warp_publish(c);
       }
     }
@@ -683,14 +683,14 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   mp.slabs = slabs;
   mp.cap = cap;
   mp.k = kprime;
-  mp.sort_n = std::max<uint32_t>(1024, next_pow2_u32(2 * kprime));
+  mp.sort_n = next_pow2_u32(kprime);
   mp.out_dist = ap_dist;
   mp.out_labels = ap_lab;
   mp.out_slots = ap_slot;
   mp.out_n = ap_n;
   mp.k_limit = nullptr;
   ix->prof_begin(c, KK_MERGE);
-  launch_topk_merge(B, s, mp);
+  launch_topk_select_merge(B, s, mp);
   ix->prof_end(c, KK_MERGE);
 
   // exact re-rank + proof
