@@ -22,6 +22,8 @@
 
 #include <cstring>
 
+#include "exact_dist.cuh"
+
 namespace vkgpu {
 
 namespace {
@@ -303,19 +305,12 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 template <int QT, bool L2>
 void launch_one(dim3 grid, size_t smem, cudaStream_t stream, const ScanParams &p, const CUtensorMap *tmX,
                 const CUtensorMap *tmQ) {
-  if (tmX) {
-    flat_scan_kernel<QT, L2, true><<<grid, kScanThreads, smem, stream>>>(p, *tmX, *tmQ);
-  } else {
-    CUtensorMap dummy;
-    memset(&dummy, 0, sizeof(dummy));
-    flat_scan_kernel<QT, L2, false><<<grid, kScanThreads, smem, stream>>>(p, dummy, dummy);
-  }
+  flat_scan_kernel<QT, L2, true><<<grid, kScanThreads, smem, stream>>>(p, *tmX, *tmQ);
 }
 
 template <int QT, bool L2>
 void set_attr_one(size_t max_smem) {
   VK_CUDA(cudaFuncSetAttribute(flat_scan_kernel<QT, L2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
-  VK_CUDA(cudaFuncSetAttribute(flat_scan_kernel<QT, L2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
 }
 
 }  // namespace
@@ -348,6 +343,128 @@ void launch_flat_scan(int qt, bool l2, dim3 grid, size_t smem, cudaStream_t stre
       default: launch_one<8, false>(grid, smem, stream, p, tmX, tmQ); break;
     }
   }
+  VK_CUDA(cudaGetLastError());
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// K4: gather scan — exact kNN over an explicit list of rows per query (the pre-filter path,
+// VectorBase::AddPrefilteredKey src/indexes/vector_base.cc:509-530 driven by CalcBestMatchingPrefilteredKeys
+// src/query/search.cc:457-481).  grid = (query, slab); 128 threads.  Listed rows are pulled WHOLE into shared
+// memory, one cp.async.bulk (TMA engine) per row, double-buffered R rows at a time; 32 groups of 4 threads
+// compute the exact-order distances (exact_dist.cuh); top-k as in the tile kernel (threshold-gated append,
+// bitonic trim, topk_merge_kernel).  Rows padded to Dp*4+64 B so a quarter-warp's LDS.128 is conflict free.
+// ------------------------------------------------------------------------------------------------
+namespace {
+constexpr int GT = 128;
+
+template <bool L2>
+__global__ void __launch_bounds__(GT) gather_scan_kernel(const GatherParams p) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  const uint32_t R = p.rows_per_stage, stride = p.Dp * 4 + 64, row_bytes = p.Dp * 4;
+  float *q = reinterpret_cast<float *>(gsm);
+  uint8_t *stage0 = gsm + ((p.Dp * 4 + 127) & ~127u);
+  Cand *scratch = reinterpret_cast<Cand *>(stage0 + (size_t)2 * R * stride);
+  uint64_t *full = reinterpret_cast<uint64_t *>(scratch + p.cap);  // [2]
+  uint32_t *sh = reinterpret_cast<uint32_t *>(full + 2);            // [0]=thr [1]=cnt
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gi = tid >> 2, u = tid & 3;
+  const uint32_t b = blockIdx.x, slab = blockIdx.y, slabs = gridDim.y;
+  const uint64_t base = p.list_off[b];
+  const uint64_t n = p.list_off[b + 1] - base;
+  const uint32_t tiles = (uint32_t)((n + R - 1) / R);
+  Cand *my = p.ws + ((size_t)b * slabs + slab) * p.cap;
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+    sh[0] = kOrdInf;
+    sh[1] = 0;
+  }
+  for (uint32_t i = tid; i < p.Dp / 4; i += GT)
+    reinterpret_cast<float4 *>(q)[i] = reinterpret_cast<const float4 *>(p.Q + (size_t)b * p.Dp)[i];
+  __syncthreads();
+
+  auto issue = [&](uint32_t tile, uint32_t st) {  // warp 0: one bulk copy per listed row of the tile
+    const uint64_t r0 = (uint64_t)tile * R;
+    const uint32_t m = (uint32_t)min((uint64_t)R, n - r0);
+    if (lane == 0) mbar_arrive_expect_tx(&full[st], m * row_bytes);
+    __syncwarp();
+    for (uint32_t r = lane; r < m; r += 32)
+      bulk_g2s(stage0 + ((size_t)st * R + r) * stride, p.X + (size_t)p.row_ids[base + r0 + r] * p.Dp, row_bytes, &full[st]);
+  };
+
+  uint32_t it = 0;
+  if (slab < tiles && warp == 0) issue(slab, 0);
+  for (uint32_t tile = slab; tile < tiles; tile += slabs, it++) {
+    const uint32_t st = it & 1;
+    if (warp == 0 && tile + slabs < tiles) issue(tile + slabs, st ^ 1);  // other buffer was released by the sync below
+    mbar_wait(&full[st], (it >> 1) & 1);
+    const uint64_t r0 = (uint64_t)tile * R;
+    const uint32_t m = (uint32_t)min((uint64_t)R, n - r0);
+    for (uint32_t rr = 0; rr < m; rr += GT / 4) {
+      const uint32_t r = rr + gi;
+      const bool act = r < m;
+      const float d = exact_dist_group<L2, false>(
+          reinterpret_cast<const float *>(stage0 + ((size_t)st * R + (act ? r : 0)) * stride), q, p.Dp, u, act);
+      if (act && u == 0) {
+        const uint32_t o = f32_to_ord(d);
+        if (o <= sh[0]) {
+          const uint32_t pos = atomicAdd(&sh[1], 1u);
+          const uint32_t slot = p.row_ids[base + r0 + r];
+          Cand cd;
+          cd.ord = o;
+          cd.slot = slot;
+          cd.label = p.labels[slot];
+          my[pos] = cd;  // pos < cap by the trim rule below
+        }
+      }
+    }
+    __syncthreads();  // tile consumed (buffer reusable), appends visible
+    const uint32_t cntv = sh[1];
+    __syncthreads();  // everyone has read the count before anyone appends again
+    if (cntv + R > p.cap) {  // uniform
+      for (uint32_t i = tid; i < p.cap; i += GT) {
+        Cand cd;
+        if (i < cntv) {
+          cd = my[i];
+        } else {
+          cd.ord = kOrdInf;
+          cd.slot = 0xffffffffu;
+          cd.label = ~0ull;
+        }
+        scratch[i] = cd;
+      }
+      __syncthreads();
+      bitonic_sort_cands(scratch, p.cap, tid, GT, [] { __syncthreads(); });
+      const uint32_t keep = min(cntv, p.k);
+      for (uint32_t i = tid; i < keep; i += GT) my[i] = scratch[i];
+      if (tid == 0) {
+        sh[1] = keep;
+        if (keep == p.k) sh[0] = scratch[p.k - 1].ord;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (tid == 0) p.ws_cnt[(size_t)b * slabs + slab] = sh[1];
+}
+}  // namespace
+
+void gather_scan_set_smem_attr(size_t max_smem) {
+  VK_CUDA(cudaFuncSetAttribute(gather_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  VK_CUDA(cudaFuncSetAttribute(gather_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+}
+
+size_t gather_smem_bytes(uint32_t Dp, uint32_t rows_per_stage, uint32_t cap) {
+  return ((size_t)(Dp * 4 + 127) & ~size_t(127)) + (size_t)2 * rows_per_stage * (Dp * 4 + 64) + (size_t)cap * sizeof(Cand) + 64;
+}
+
+void launch_gather_scan(bool l2, dim3 grid, size_t smem, cudaStream_t stream, const GatherParams &p) {
+  if (l2)
+    gather_scan_kernel<true><<<grid, GT, smem, stream>>>(p);
+  else
+    gather_scan_kernel<false><<<grid, GT, smem, stream>>>(p);
   VK_CUDA(cudaGetLastError());
 }
 

@@ -46,6 +46,21 @@ void make_tensor_map_2d_f32(CUtensorMap *out, const void *base, uint64_t inner, 
                             uint32_t box_inner, uint32_t box_rows, bool swizzle128);
 void flat_scan_set_smem_attr(size_t max_smem);
 
+// Gather scan (pre-filter): one list of slots per query.
+struct GatherParams {
+  const float *X;
+  const uint64_t *labels;
+  const uint32_t *row_ids;   // concatenated slot lists
+  const uint64_t *list_off;  // [B+1]
+  const float *Q;            // zero-padded queries [B][Dp]
+  uint32_t Dp, k, cap, rows_per_stage;
+  Cand *ws;                  // [B][slabs][cap]
+  uint32_t *ws_cnt;          // [B][slabs]
+};
+void gather_scan_set_smem_attr(size_t max_smem);
+size_t gather_smem_bytes(uint32_t Dp, uint32_t rows_per_stage, uint32_t cap);
+void launch_gather_scan(bool metric_l2, dim3 grid, size_t smem, cudaStream_t stream, const GatherParams &p);
+
 // Per-query merge of `nlists` unsorted candidate lists into the ascending top-k.
 struct MergeParams {
   const Cand *ws;          // lists; list j of query b starts at ws + list_index(b,j)*cap

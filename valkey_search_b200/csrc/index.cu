@@ -185,12 +185,74 @@ static uint32_t next_pow2(uint32_t v) {
 // ------------------------------------------------------------------------------------------ FLAT exact driver
 static constexpr uint32_t kMaxFusedK = 1024;
 
+// pre-filter exact search: one slot list per query (longest list = n_rows)
+static void gather_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff,
+                                 const uint32_t *d_row_ids, const uint64_t *d_list_off, uint64_t n_rows) {
+  // rows per stage: as many as fit twice while leaving room for 2 CTAs per SM
+  const uint32_t stride = ix->Dp * 4 + 64;
+  const size_t budget = (ix->smem_max + 1024) / 2 - 1024;
+  uint32_t cap = 256;
+  while (cap < k_eff + 32) cap <<= 1;
+  const size_t fixed = gather_smem_bytes(ix->Dp, 0, cap);
+  uint32_t R = fixed < budget ? (uint32_t)((budget - fixed) / (2 * (size_t)stride)) : 0;
+  if (R < 4) R = fixed < ix->smem_max ? (uint32_t)((ix->smem_max - fixed) / (2 * (size_t)stride)) : 0;
+  R = std::min<uint32_t>(R, 32);
+  VK_REQUIRE(R >= 1, VKGPU_ERR_UNSUPPORTED, "vector too large for the gather staging buffer");
+  while (cap < k_eff + R) cap <<= 1;
+  const uint32_t tiles = (uint32_t)std::max<uint64_t>(1, (n_rows + R - 1) / R);
+  uint32_t slabs = std::max<uint32_t>(1, std::min<uint32_t>(tiles, (4 * ix->num_sms + B - 1) / B));
+  const size_t nlists = (size_t)B * slabs;
+  c->ws.reserve(nlists * cap * sizeof(Cand));
+  c->ws_cnt.reserve(nlists * sizeof(uint32_t));
+  c->out_dist.reserve((size_t)B * k_eff * sizeof(float));
+  c->out_labels.reserve((size_t)B * k_eff * sizeof(uint64_t));
+  c->out_slots.reserve((size_t)B * k_eff * sizeof(uint32_t));
+  c->out_n.reserve((size_t)B * sizeof(uint32_t));
+  GatherParams gp{};
+  gp.X = ix->dX.as<float>();
+  gp.labels = ix->dLabels.as<uint64_t>();
+  gp.row_ids = d_row_ids;
+  gp.list_off = d_list_off;
+  gp.Q = c->q_pad.as<float>();
+  gp.Dp = ix->Dp;
+  gp.k = k_eff;
+  gp.cap = cap;
+  gp.rows_per_stage = R;
+  gp.ws = c->ws.as<Cand>();
+  gp.ws_cnt = c->ws_cnt.as<uint32_t>();
+  ix->prof_begin(c, KK_SCAN);
+  launch_gather_scan(ix->metric_l2, dim3(B, slabs), gather_smem_bytes(ix->Dp, R, cap), c->cur, gp);
+  ix->prof_end(c, KK_SCAN);
+  MergeParams mp{};
+  mp.ws = gp.ws;
+  mp.ws_cnt = gp.ws_cnt;
+  mp.qt = 1;
+  mp.slabs = slabs;
+  mp.cap = cap;
+  mp.k = k_eff;
+  mp.sort_n = std::max<uint32_t>(512, next_pow2(2 * k_eff));
+  mp.out_dist = c->out_dist.as<float>();
+  mp.out_labels = c->out_labels.as<uint64_t>();
+  mp.out_slots = c->out_slots.as<uint32_t>();
+  mp.out_n = c->out_n.as<uint32_t>();
+  ix->prof_begin(c, KK_MERGE);
+  launch_topk_merge(B, c->cur, mp);
+  ix->prof_end(c, KK_MERGE);
+  ix->kernels += 2;
+  ix->last_qt = 1;
+  ix->last_passes = B;
+}
+
 void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff,
                               const uint32_t *d_row_ids, const uint64_t *d_list_off, bool per_query_lists,
                               uint64_t n_rows) {
   VK_REQUIRE(k_eff >= 1 && k_eff <= kMaxFusedK, VKGPU_ERR_UNSUPPORTED,
              "k > 1024 is not implemented on the fused top-k path yet");
-  int qt = per_query_lists ? 1 : (B == 1 ? 1 : B == 2 ? 2 : B <= 4 ? 4 : 8);
+  if (per_query_lists) {
+    gather_search_device(ix, c, B, k_eff, d_row_ids, d_list_off, n_rows);
+    return;
+  }
+  int qt = (B == 1 ? 1 : B == 2 ? 2 : B <= 4 ? 4 : 8);
   const uint32_t qtiles = (B + qt - 1) / qt;
   const uint32_t cap = std::max<uint32_t>(256, next_pow2(k_eff + kScanTileRows));
   const uint64_t max_rows = n_rows;  // for per-query lists this is the longest list
@@ -541,6 +603,7 @@ int vkgpu_index_create(const vkgpu_config *cfg, vkgpu_index **out) {
     ix->metric_l2 = cfg->metric == VKGPU_L2;
     VK_CUDA(cudaStreamCreateWithFlags(&ix->mut_stream, cudaStreamNonBlocking));
     flat_scan_set_smem_attr(ix->smem_max);
+    gather_scan_set_smem_attr(ix->smem_max);
     ix->capacity = cfg->initial_cap;
     if (cfg->algo == VKGPU_HNSW) hnsw_create(ix);
     if (cfg->initial_cap) {
