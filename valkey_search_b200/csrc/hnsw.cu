@@ -566,9 +566,8 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
 // markDelete hnswalg.h:1173-1209: tombstone; the node keeps routing
 void hnsw_remove(vkgpu_index_impl *ix, uint64_t label) {
   Hnsw *g = G(ix);
-  auto it = ix->slot_of.find(label);
-  VK_REQUIRE(it != ix->slot_of.end(), VKGPU_ERR_INTERNAL, "Label not found");
-  const uint32_t id = it->second;
+  uint32_t id;
+  VK_REQUIRE(ix->slot_of.get(label, &id), VKGPU_ERR_INTERNAL, "Label not found");
   VK_REQUIRE(!g->h_deleted[id], VKGPU_ERR_INTERNAL, "The requested to delete element is already deleted");
   g->h_deleted[id] = 1;
   g->num_deleted++;
@@ -636,7 +635,7 @@ void hnsw_import(vkgpu_index_impl *ix, uint64_t n, const int32_t *levels, const 
   g->enterpoint = enterpoint;
   ix->h_labels.assign(labels, labels + n);
   ix->slot_of.clear();
-  for (uint64_t i = 0; i < n; i++) ix->slot_of[labels[i]] = (uint32_t)i;  // hnswalg.h:1040-1056: last slot wins
+  for (uint64_t i = 0; i < n; i++) ix->slot_of.set(labels[i], (uint32_t)i);  // hnswalg.h:1040-1056: last slot wins
   ix->n = n;
 }
 

@@ -392,8 +392,8 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
       size_t start = slots.size();
       if (f.labels) {
         for (uint64_t i = 0; i < f.n_labels; i++) {
-          auto it = ix->slot_of.find(f.labels[i]);
-          if (it != ix->slot_of.end()) slots.push_back(it->second);
+          uint32_t sl;
+          if (ix->slot_of.get(f.labels[i], &sl)) slots.push_back(sl);
         }
       } else if (f.label_bitmap) {
         for (uint64_t s = 0; s < ix->n; s++) {
@@ -403,7 +403,7 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
       } else {
         for (uint64_t s = 0; s < ix->n; s++) slots.push_back((uint32_t)s);
       }
-      std::sort(slots.begin() + start, slots.end());
+      if (!std::is_sorted(slots.begin() + start, slots.end())) std::sort(slots.begin() + start, slots.end());
       slots.erase(std::unique(slots.begin() + start, slots.end()), slots.end());
       off[b + 1] = slots.size();
       longest = std::max<uint64_t>(longest, slots.size() - start);
@@ -480,7 +480,7 @@ static void flat_add_rows(vkgpu_index_impl *ix, const uint64_t *labels, const fl
   // fast path: all labels new (bulk backfill); otherwise fall back to per-row upsert
   bool all_new = true;
   if (labels) {
-    for (uint64_t i = 0; i < n && all_new; i++) all_new = ix->slot_of.find(labels[i]) == ix->slot_of.end();
+    for (uint64_t i = 0; i < n && all_new; i++) all_new = !ix->slot_of.has(labels[i]);
     if (all_new && n > 1) {
       std::vector<uint64_t> tmp(labels, labels + n);
       std::sort(tmp.begin(), tmp.end());
@@ -496,16 +496,16 @@ static void flat_add_rows(vkgpu_index_impl *ix, const uint64_t *labels, const fl
     if (labels) {
       for (uint64_t i = 0; i < n; i++) {
         ix->h_labels[first + i] = labels[i];
-        ix->slot_of.emplace(labels[i], (uint32_t)(first + i));
+        ix->slot_of.set(labels[i], (uint32_t)(first + i));
       }
       VK_CUDA(cudaMemcpyAsync(ix->dLabels.as<uint64_t>() + first, labels, n * 8, cudaMemcpyHostToDevice,
                               ix->mut_stream));
     } else {
       // labels = first..first+n-1 (VectorBase::TrackKey hands out inc_id_++, vector_base.cc:340-358)
       for (uint64_t i = 0; i < n; i++) {
-        VK_REQUIRE(ix->slot_of.find(first + i) == ix->slot_of.end(), VKGPU_ERR_EXISTS, "implicit label in use");
+        VK_REQUIRE(!ix->slot_of.has(first + i), VKGPU_ERR_EXISTS, "implicit label in use");
         ix->h_labels[first + i] = first + i;
-        ix->slot_of.emplace(first + i, (uint32_t)(first + i));
+        ix->slot_of.set(first + i, (uint32_t)(first + i));
       }
       launch_iota_labels(ix->dLabels.as<uint64_t>() + first, first, n, ix->mut_stream);
       ix->kernels++;
@@ -514,10 +514,10 @@ static void flat_add_rows(vkgpu_index_impl *ix, const uint64_t *labels, const fl
   } else {
     VK_REQUIRE(labels != nullptr, VKGPU_ERR_INVALID, "labels required");
     for (uint64_t i = 0; i < n; i++) {
-      auto it = ix->slot_of.find(labels[i]);
-      if (it != ix->slot_of.end()) {
+      uint32_t known;
+      if (ix->slot_of.get(labels[i], &known)) {
         // bruteforce.h:66-82: addPoint on a known label rewrites that slot in place
-        upload_rows(ix, it->second, vecs + i * ix->dim, 1, on_device);
+        upload_rows(ix, known, vecs + i * ix->dim, 1, on_device);
       } else {
         flat_add_rows(ix, labels + i, vecs + i * ix->dim, 1, on_device);
       }
@@ -528,14 +528,13 @@ static void flat_add_rows(vkgpu_index_impl *ix, const uint64_t *labels, const fl
 
 // removePoint bruteforce.h:92-113: last slot moves into the hole
 static void flat_remove(vkgpu_index_impl *ix, uint64_t label) {
-  auto it = ix->slot_of.find(label);
-  if (it == ix->slot_of.end()) return;  // the reference returns silently
-  const uint32_t cur = it->second;
-  ix->slot_of.erase(it);
+  uint32_t cur;
+  if (!ix->slot_of.get(label, &cur)) return;  // the reference returns silently
+  ix->slot_of.erase(label);
   const uint64_t last = ix->n - 1;
   if (cur != last) {
     const uint64_t moved = ix->h_labels[last];
-    ix->slot_of[moved] = cur;
+    ix->slot_of.set(moved, cur);
     ix->h_labels[cur] = moved;
     VK_CUDA(cudaMemcpyAsync(ix->dX.as<float>() + (size_t)cur * ix->Dp, ix->dX.as<float>() + last * ix->Dp,
                             (size_t)ix->Dp * 4, cudaMemcpyDeviceToDevice, ix->mut_stream));
@@ -684,7 +683,7 @@ int vkgpu_modify(vkgpu_index *ix, uint64_t label, const float *vec) {
     std::unique_lock<std::shared_mutex> lk(ix->rw);
     VK_CUDA(cudaSetDevice(ix->device));
     // vector_flat.cc:181-198 / vector_hnsw.cc:201-236: unknown id => InternalError "Couldn't find internal id"
-    VK_REQUIRE(ix->slot_of.count(label), VKGPU_ERR_NOT_FOUND, "Couldn't find internal id: " + std::to_string(label));
+    VK_REQUIRE(ix->slot_of.has(label), VKGPU_ERR_NOT_FOUND, "Couldn't find internal id: " + std::to_string(label));
     if (ix->cfg.algo == VKGPU_FLAT)
       flat_add_rows(ix, &label, vec, 1, false);
     else
@@ -709,9 +708,9 @@ int vkgpu_get(vkgpu_index *ix, uint64_t label, float *out_vec) {
     VK_REQUIRE(ix && out_vec, VKGPU_ERR_INVALID, "null argument");
     std::shared_lock<std::shared_mutex> lk(ix->rw);
     VK_CUDA(cudaSetDevice(ix->device));
-    auto it = ix->slot_of.find(label);
-    VK_REQUIRE(it != ix->slot_of.end(), VKGPU_ERR_NOT_FOUND, "unknown label");
-    VK_CUDA(cudaMemcpy(out_vec, ix->dX.as<float>() + (size_t)it->second * ix->Dp, (size_t)ix->dim * 4,
+    uint32_t sl;
+    VK_REQUIRE(ix->slot_of.get(label, &sl), VKGPU_ERR_NOT_FOUND, "unknown label");
+    VK_CUDA(cudaMemcpy(out_vec, ix->dX.as<float>() + (size_t)sl * ix->Dp, (size_t)ix->dim * 4,
                        cudaMemcpyDeviceToHost));
   });
 }
@@ -766,8 +765,8 @@ int vkgpu_distances(vkgpu_index *ix, const float *q, const uint64_t *labels, uin
     c->h_misc.reserve(n * 4);
     uint32_t *hs = c->h_misc.as<uint32_t>();
     for (uint64_t i = 0; i < n; i++) {
-      auto it = ix->slot_of.find(labels[i]);
-      hs[i] = it == ix->slot_of.end() ? 0xffffffffu : it->second;
+      uint32_t sl;
+      hs[i] = ix->slot_of.get(labels[i], &sl) ? sl : 0xffffffffu;
     }
     c->lists.reserve(n * 4);
     c->out_dist.reserve(n * 4);

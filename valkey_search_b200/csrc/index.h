@@ -1,5 +1,6 @@
 // Host-side state behind a vkgpu_index handle (internal to libvkgpu).
 #pragma once
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <memory>
@@ -43,6 +44,51 @@ struct PinnedBuf {
   }
 };
 
+// label -> slot.  The module hands out labels as a dense increasing sequence (vector_base.cc:347), so labels
+// below a bound live in a flat array (one load per lookup — the pre-filter path maps millions of labels per
+// query batch); anything else falls back to a hash map.
+class LabelMap {
+ public:
+  bool get(uint64_t label, uint32_t *slot) const {
+    if (label < dense_.size()) {
+      const uint32_t v = dense_[label];
+      if (v != 0) {
+        if (slot) *slot = v - 1;
+        return true;
+      }
+      if (sparse_.empty()) return false;
+    }
+    auto it = sparse_.find(label);
+    if (it == sparse_.end()) return false;
+    if (slot) *slot = it->second;
+    return true;
+  }
+  bool has(uint64_t label) const { return get(label, nullptr); }
+  void set(uint64_t label, uint32_t slot) {
+    // dense while the array stays reasonably full (labels are handed out densely by the module)
+    if (label < kDenseLimit && (label < dense_.size() || label < 4 * (uint64_t)dense_.size() + (16u << 20))) {
+      if (label >= dense_.size()) dense_.resize(std::max<size_t>(label + 1, dense_.size() + dense_.size() / 2 + 1024), 0);
+      dense_[label] = slot + 1;
+      if (!sparse_.empty()) sparse_.erase(label);
+    } else {
+      sparse_[label] = slot;
+    }
+  }
+  void erase(uint64_t label) {
+    if (label < dense_.size()) dense_[label] = 0;
+    if (!sparse_.empty()) sparse_.erase(label);
+  }
+  void clear() {
+    dense_.clear();
+    sparse_.clear();
+  }
+
+ private:
+  static constexpr uint64_t kDenseLimit = 1ull << 31;
+  std::vector<uint32_t> dense_;
+  std::unordered_map<uint64_t, uint32_t> sparse_;
+};
+
 enum KernelKind { KK_SCAN = 0, KK_MERGE = 1, KK_TENSOR = 2, KK_RERANK = 3, KK_HNSW = 4, kNumKernelKinds = 5 };
 
 // Everything one in-flight search needs; searches on different contexts run concurrently.
@@ -81,7 +127,7 @@ struct vkgpu_index_impl {
   uint64_t capacity = 0;   // logical capacity as the reference reports it (initial_cap + j*block)
   uint64_t phys_cap = 0;   // rows physically allocated
   std::vector<uint64_t> h_labels;                   // slot -> label
-  std::unordered_map<uint64_t, uint32_t> slot_of;   // label -> slot
+  LabelMap slot_of;                                 // label -> slot
 
   // ---- tensor path side data (bf16 mirror + row norms), maintained on ingest
   DevBuf dXh;      // [phys_cap][Dp] bf16

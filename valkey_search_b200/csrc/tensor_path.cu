@@ -311,9 +311,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     };
 
     // Gate + append for 32 columns.  Fast path is branch-free: 32 scores against 32 thresholds -> a per-lane bit
-    // mask, ONE warp vote per 32 columns.  Only when some lane passes does the warp walk the set columns and
-    // append (one shared-memory atomic per warp and column; passing lanes take consecutive slots).
-    auto gate_chunk = [&](const uint32_t (&r)[32], uint32_t c0, float xn, bool valid, uint64_t slot) {
+    // mask, ONE warp vote per 32 columns.  Only when some lane passes does the warp walk the set columns; the
+    // slow path re-reads the one column it needs from TMEM (tcgen05.ld .x1) instead of indexing the register
+    // tile dynamically, which keeps the whole epilogue loop small enough for the instruction cache.
+    auto gate_chunk = [&](const uint32_t (&r)[32], uint32_t taddr, uint32_t c0, float xn, bool valid, uint64_t slot) {
       uint32_t m = 0;
       const float4 *th4 = reinterpret_cast<const float4 *>(thrf + c0);
 #pragma unroll
@@ -330,11 +331,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         m |= (s3 <= th.w ? 1u : 0u) << (4 * j4 + 3);
       }
       if (!valid) m = 0;
-      const uint32_t any = __reduce_or_sync(0xffffffffu, m);
-      if (any == 0) return;
-#pragma unroll
-      for (int j = 0; j < 32; j++) {
-        if (!((any >> j) & 1u)) continue;  // warp-uniform
+      uint32_t any = __reduce_or_sync(0xffffffffu, m);
+#pragma unroll 1
+      while (any) {  // warp-uniform
+        const uint32_t j = __ffs(any) - 1;
+        any &= any - 1;
+        uint32_t v;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr + j) : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const bool pass = (m >> j) & 1u;
         const uint32_t bal = __ballot_sync(0xffffffffu, pass);
         const uint32_t c = c0 + j;
@@ -346,7 +350,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         }
         base = __shfl_sync(0xffffffffu, base, 0);
         if (pass) {
-          const float dot = __uint_as_float(r[j]);
+          const float dot = __uint_as_float(v);
           const float sc = p.metric_l2 ? __fmaf_rn(-2.0f, dot, xn) : -dot;
           Cand cd;
           cd.ord = f32_to_ord(sc);
@@ -380,17 +384,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       mbar_wait(&tfull[a], (t >> 1) & 1);
       tc_fence_after();
       const uint32_t tbase = tmem_base + (lane_base << 16) + a * BN;
-      uint32_t ra[32], rb[32];
-      tmem_ld32_async(tbase, ra);
-      tmem_wait();
+      uint32_t ra[32];
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < BN; c0 += 64) {
-        tmem_ld32_async(tbase + c0 + 32, rb);   // in flight while ra is gated
-        gate_chunk(ra, c0, xn, valid, slot);
+      for (uint32_t c0 = 0; c0 < BN; c0 += 32) {
+        tmem_ld32_async(tbase + c0, ra);
         tmem_wait();
-        if (c0 + 64 < BN) tmem_ld32_async(tbase + c0 + 64, ra);
-        gate_chunk(rb, c0 + 32, xn, valid, slot);
-        tmem_wait();
+        gate_chunk(ra, tbase + c0, c0, xn, valid, slot);
       }
       tc_fence_before();
       mbar_arrive(&tempty[a]);  // accumulator may be overwritten
