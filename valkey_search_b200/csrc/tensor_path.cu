@@ -367,10 +367,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       // Query c belongs to epilogue warp c & 3 for refresh and shrink alike, so thrf[c]/cnt[c] have one writer.
       if ((t & 7) == 0 || ((t - 1) & t) == 0) {
         for (uint32_t c = (warp & 3) + 4 * lane; c < BN; c += 128) {
-          uint32_t go = *reinterpret_cast<volatile uint32_t *>(&p.gthr[qtile * BN + c]);
-          const volatile uint32_t *gs = p.gsl + ((size_t)qtile * BN + c) * p.slabs;
-          uint32_t mx = 0;
-          for (uint32_t sidx = 0; sidx < p.slabs; sidx++) mx = max(mx, gs[sidx]);
+          uint32_t go = __ldcg(&p.gthr[qtile * BN + c]);
+          const uint32_t *gs = p.gsl + ((size_t)qtile * BN + c) * p.slabs;
+          uint32_t mx = 0, sidx = 0;
+          for (; sidx + 4 <= p.slabs; sidx += 4) {  // L2 loads (other CTAs write these), 4 in flight
+            const uint32_t a0 = __ldcg(gs + sidx), a1 = __ldcg(gs + sidx + 1), a2 = __ldcg(gs + sidx + 2),
+                           a3 = __ldcg(gs + sidx + 3);
+            mx = max(max(mx, a0), max(max(a1, a2), a3));
+          }
+          for (; sidx < p.slabs; sidx++) mx = max(mx, __ldcg(gs + sidx));
           go = min(go, mx);
           if (go != kOrdInf) thrf[c] = fminf(thrf[c], ord_to_f32(go));
         }
@@ -726,7 +731,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
     rerank_kernel<false><<<B, 128, rsmem, s>>>(rp);
   VK_CUDA(cudaGetLastError());
   ix->prof_end(c, KK_RERANK);
-  ix->kernels += 4;
+  ix->kernels += 4;  // query conversion, candidate pass, merge, re-rank
   ix->last_qt = BN;
   ix->last_passes = nq_tiles;
 
