@@ -584,6 +584,15 @@ def main():
                         "peak_source": f"{peaks['source']} copy bandwidth", "Qt": qt, "passes": passes,
                         "bytes_per_launch": bytes_algo, "single_pass_floor_bytes": n_local * D * 4,
                         "fma_tflops": (3.0 * B * n_local * D) / avg_s / 1e12}
+        try:  # measured DRAM traffic of this exact configuration, if an ncu capture of it is committed
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            kname = "flat_tensor_kernel" if dom == "tensor" else "flat_scan_kernel"
+            ent = tj.get(f"{kname}:rows={n_local}:dim={D}:batch={B}:k={k}")
+            if ent and world == 1:
+                roofline["traffic"] = ent["bytes"]
+                roofline["traffic_source"] = ent["capture"]
+        except Exception:
+            pass
         roofline["kernel_ms_avg"] = dms / dn
         roofline["share_of_step"] = (dms / K) / ms_step
         roofline["kernels_ms_per_step"] = {n: v[0] / K for n, v in per_kind.items()}

@@ -515,12 +515,18 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   hp.row_stride_bytes = ix->Dp * 4 + 64;
   hp.cand_cap = std::max<uint32_t>(1024, 8 * ef);
   hp.stats = g->d_stats.as<unsigned long long>();
-  // rows staged per round: as many as fit while leaving room for 2 CTAs per SM (down to 1 if rows are big)
+  // rows staged per round vs CTAs per SM: prefer enough resident CTAs to hold the whole batch in ONE wave (a hop
+  // stages ~8 unvisited rows on average, so 12-16 staged rows rarely need a second round), down to 1 CTA/SM for
+  // very wide rows.  Shared memory per SM = opt-in max + 1 KB; each CTA reserves 1 KB.
   const SmemLayout fixed = hnsw_smem_layout(ix->Dp, 0, hp.row_stride_bytes, ef, hp.cand_cap, g->maxM0);
-  const size_t two_cta_budget = (ix->smem_max + 1024) / 2 - 1024;
+  const size_t sm_total = ix->smem_max + 1024;
+  uint32_t want = std::min<uint32_t>(4, std::max<uint32_t>(1, (B + ix->num_sms - 1) / ix->num_sms));
   uint32_t rows = 0;
-  if (fixed.total < two_cta_budget) rows = (uint32_t)((two_cta_budget - fixed.total) / hp.row_stride_bytes);
-  if (rows < 8) rows = fixed.total < ix->smem_max ? (uint32_t)((ix->smem_max - fixed.total) / hp.row_stride_bytes) : 0;
+  for (uint32_t t = want; t >= 1; t--) {
+    const size_t budget = sm_total / t - 1024;
+    rows = fixed.total < budget ? (uint32_t)((budget - fixed.total) / hp.row_stride_bytes) : 0;
+    if (rows >= (t > 1 ? 12u : 1u)) break;
+  }
   rows = std::min<uint32_t>(rows, 32);
   VK_REQUIRE(rows >= 1, VKGPU_ERR_UNSUPPORTED, "vector too large for the HNSW staging buffer");
   hp.rows_per_batch = rows;
