@@ -50,8 +50,8 @@ constexpr int UMMA_K = 16;
 constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
-constexpr int TC_THREADS = 256;
-constexpr int EPI_THREADS = 128;
+constexpr int TC_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
+constexpr int EPI_THREADS = 256;
 constexpr uint32_t TMEM_COLS = 512;
 
 struct TensorParams {
@@ -215,8 +215,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------ epilogue warps (TMEM lanes 32*(warp%4)..)
-    const uint32_t et = tid - 128;                 // 0..127 = row inside the tile = TMEM lane
+    // Two epilogue warps per TMEM lane quadrant: warps 4-7 gate columns 0..127, warps 8-11 columns 128..255.
+    // Threshold refresh, trims and publishes stay with warps 4-7 (query c belongs to warp 4 + (c & 3)).
     const uint32_t lane_base = (warp & 3) * 32;
+    const uint32_t et = lane_base + lane;          // row inside the tile = TMEM lane
+    const uint32_t col_lo = ((warp - 4) >> 2) * (BN / 2);
+    const bool owner_warp = warp < 8;
     Cand *my_ws = p.ws + ((size_t)qtile * p.slabs + slab) * BN * p.cap;
     // One warp trims query c's candidate list to the K' best: radix-select the K'-th smallest score with the
     // list's keys held 32 per lane in registers (32 bit-rounds of count + shuffle-reduce), then compact the
@@ -363,9 +367,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     uint32_t t = 0;
     for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
-      // every 8th tile: refresh the gate thresholds from the running global ones (other slabs tighten them too).
+      // every 8th tile early on, every 32nd later (and right after each publish round): refresh the gate thresholds from the running global ones (other slabs tighten them too).
       // Query c belongs to epilogue warp c & 3 for refresh and shrink alike, so thrf[c]/cnt[c] have one writer.
-      if ((t & 7) == 0 || ((t - 1) & t) == 0) {
+      if (owner_warp && ((t < 64 && (t & 7) == 0) || (t & 31) == 0 || ((t - 1) & t) == 0)) {
         for (uint32_t c = (warp & 3) + 4 * lane; c < BN; c += 128) {
           uint32_t go = __ldcg(&p.gthr[qtile * BN + c]);
           const uint32_t *gs = p.gsl + ((size_t)qtile * BN + c) * p.slabs;
@@ -391,7 +395,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t tbase = tmem_base + (lane_base << 16) + a * BN;
       uint32_t ra[32];
 #pragma unroll 1
-      for (uint32_t c0 = 0; c0 < BN; c0 += 32) {
+      for (uint32_t c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32) {
         tmem_ld32_async(tbase + c0, ra);
         tmem_wait();
         gate_chunk(ra, tbase + c0, c0, xn, valid, slot);
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       // ---- keep room for one more tile (<= BM appends per query per tile): the warp that owns a query trims
       //      it when an append pushed it past cap - BM (flagged in `need` by the appender)
       named_bar_sync(2, EPI_THREADS);
-      {
+      if (owner_warp) {
         const uint32_t w = warp & 3;
 #pragma unroll
         for (int h = 0; h < 2; h++) {
@@ -424,10 +428,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     // final trim so the merge kernel reads at most K' entries per list
     named_bar_sync(2, EPI_THREADS);
-    for (uint32_t c = warp & 3; c < BN; c += 4)
-      if (cnt[c] > p.kprime) warp_shrink(c);
+    if (owner_warp)
+      for (uint32_t c = warp & 3; c < BN; c += 4)
+        if (cnt[c] > p.kprime) warp_shrink(c);
     named_bar_sync(2, EPI_THREADS);
-    for (uint32_t c = et; c < BN; c += EPI_THREADS)
+    for (uint32_t c = tid - 128; c < BN; c += EPI_THREADS)
       p.ws_cnt[((size_t)qtile * p.slabs + slab) * BN + c] = cnt[c];
   }
 
