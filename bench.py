@@ -270,6 +270,63 @@ def hnsw_workload(args):
     return 0
 
 
+def serve_workload(args):
+    """The module's real call shape: ONE query per call, many concurrent callers (reader pool) — here `batch`
+    native threads each calling vkgpu_search, with the library's dynamic batcher (cfg.batch_window_us) turning
+    them into GPU batches.  Same corpus/k as the headline; QPS is wall-clock over all callers."""
+    import numpy as np
+    import torch
+    import valkey_search_b200 as V
+    from valkey_search_b200 import _lib as L
+
+    N, D, k, T = args.rows, args.dim, args.k, args.batch
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(dev)
+    lib = L.lib()
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N, max_batch=T, batch_window_us=args.window_us)
+    BLK = 1_000_000
+    for blk in range((N + BLK - 1) // BLK):
+        rows = min(BLK, N - blk * BLK)
+        Xb = gen_block(torch, dev, blk, rows, D)
+        torch.cuda.synchronize()
+        L.check(lib.vkgpu_add_batch_device(ix.handle(), None, Xb.data_ptr(), rows))
+        del Xb
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321)
+    hQ = torch.randn((T, D), generator=g, device=dev).cpu().numpy()
+    drv = C.CDLL(os.path.join(ROOT, "tests", "native", "libvkdriver.so"))
+    drv.vkdrv_run.restype = C.c_double
+    od, ol, on = np.zeros((T, k), np.float32), np.zeros((T, k), np.uint64), np.zeros(T, np.uint32)
+    ne = C.c_uint64()
+    fn = C.cast(lib.vkgpu_search, C.c_void_p)
+
+    def run(rounds):
+        return drv.vkdrv_run(fn, ix.handle(), hQ.ctypes.data_as(C.c_void_p), T, D, k, 0, T, rounds,
+                             od.ctypes.data_as(C.c_void_p), ol.ctypes.data_as(C.c_void_p),
+                             on.ctypes.data_as(C.c_void_p), C.byref(ne))
+
+    W, K = max(args.warmup, 3), args.steps
+    run(W)
+    st0 = ix.stats()
+    sampler = ClockSampler(0)
+    sampler.start()
+    secs = run(K)
+    clocks = sampler.stop()
+    st1 = ix.stats()
+    nb = st1.batches - st0.batches
+    line = {"metric": f"kNN QPS, one query per call from {T} concurrent callers (FLAT {N}x{D} fp32, k={k})",
+            "value": T * K / secs, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": 1e3 * secs / K,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic N(0,1) fp32", "config": {"workload": f"serve: {T} threads x vkgpu_search, batch window "
+                                                        f"{args.window_us} us", "rows": N, "dim": D, "k": k},
+            "e2e": {"value": T * K / secs, "unit": UNIT, "h2d_bytes_per_step": T * D * 4,
+                    "d2h_bytes_per_step": T * k * 12 + T * 4},
+            "gpu_launches": int(st1.kernels_launched - st0.kernels_launched), "errors": int(ne.value),
+            "batches": int(nb), "mean_batch": (T * K) / max(nb, 1), "clocks": clocks}
+    emit(line)
+    return 0
+
+
 def prefilter_workload(args):
     """BASELINE configs[4] shape on ONE shard: TAG pre-filter at 1 % selectivity + exact kNN over the qualified
     rows (VectorBase::AddPrefilteredKey path), 1536-d fp32.  Tag of row r = r % 100; query b filters tag b % 100.
@@ -376,14 +433,17 @@ def main():
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--cpu-queries", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="flat", choices=["flat", "hnsw", "prefilter"],
+    ap.add_argument("--workload", default="flat", choices=["flat", "hnsw", "prefilter", "serve"],
                     help="flat = BASELINE configs[1] (the driver's default); hnsw = configs[2] at --rows")
     ap.add_argument("--ef", type=int, default=128)
+    ap.add_argument("--window-us", type=int, default=300)
     args = ap.parse_args()
     if args.workload == "hnsw":
         return hnsw_workload(args)
     if args.workload == "prefilter":
         return prefilter_workload(args)
+    if args.workload == "serve":
+        return serve_workload(args)
 
     import numpy as np
     import torch

@@ -70,7 +70,8 @@ typedef struct vkgpu_config {
   int32_t allow_replace_deleted; /* search.hnsw-allow-replace-deleted                               */
   int32_t device;           /* CUDA device ordinal holding this index (shard)                        */
   uint32_t max_batch;       /* largest B the caller will pass to *_batch (0 = 1024)                  */
-  uint32_t reserved;
+  uint32_t batch_window_us; /* 0 = off; else concurrent vkgpu_search calls are coalesced into batches: a call waits at
+                               most this long for company (new config search.gpu-batch-window-us)             */
 } vkgpu_config;
 
 typedef struct vkgpu_index vkgpu_index; /* opaque; owns its HBM */
@@ -99,6 +100,8 @@ typedef struct vkgpu_stats {
   int32_t dim;
   uint32_t last_qt;          /* FLAT: query-tile width of the last exact pass                          */
   uint32_t last_passes;      /* FLAT: corpus passes of the last search                                 */
+  uint64_t batches;          /* dynamic batcher: launches issued                                       */
+  uint64_t batched_requests; /* dynamic batcher: single-query calls answered through those launches    */
 } vkgpu_stats;
 
 /* ---- lifecycle ------------------------------------------------------------------------------------- */

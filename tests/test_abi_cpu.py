@@ -25,7 +25,7 @@ def test_struct_layout_matches_header(built):
     from valkey_search_b200 import _lib as L
     assert C.sizeof(L.Config) == 56
     assert C.sizeof(L.Filter) == 32
-    assert C.sizeof(L.Stats) == 88
+    assert C.sizeof(L.Stats) == 104
 
 
 def test_no_cpu_fallback(built):

@@ -83,3 +83,56 @@ def test_concurrent_searches_from_many_threads(built):
     for t in ts:
         t.join()
     assert not errs, errs[:4]
+
+
+def test_dynamic_batcher_coalesces_concurrent_single_queries(built):
+    """search.gpu-batch-window-us analog: concurrent one-query calls are answered through shared launches and
+    every caller still gets exactly the reference's answer (FLAT and HNSW)."""
+    import os
+    import threading
+
+    import oracle_lib as O
+    import valkey_search_b200 as V
+    from valkey_search_b200 import _lib as L
+    rng = np.random.default_rng(12)
+    N, D, k = 30000, 64, 10
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((256, D)).astype(np.float32)
+    orc = O.PortFlat(D, O.L2)
+    orc.add_many(X)
+    want = [orc.search(q, k) for q in Q]
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N, batch_window_us=3000, max_batch=256)
+    ix.AddRecordsBulk(range(N), X)
+    # Python threads (ctypes releases the GIL inside the call)
+    errs = []
+
+    def worker(t):
+        for i in range(t, 256, 32):
+            res = ix.Search(Q[i], k)
+            if [r.external_id for r in res] != want[i][1].tolist():
+                errs.append(i)
+
+    ts = [threading.Thread(target=worker, args=(t,)) for t in range(32)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs
+    st = ix.stats()
+    assert st.batched_requests == 256 and st.batches < 256, (st.batches, st.batched_requests)
+    # native load generator: 128 threads, one query per call
+    drv = C.CDLL(os.path.join(os.path.dirname(os.path.abspath(__file__)), "native", "libvkdriver.so"))
+    drv.vkdrv_run.restype = C.c_double
+    od = np.zeros((256, k), np.float32)
+    ol = np.zeros((256, k), np.uint64)
+    on = np.zeros(256, np.uint32)
+    ne = C.c_uint64()
+    fn = C.cast(L.lib().vkgpu_search, C.c_void_p)
+    secs = drv.vkdrv_run(fn, ix.handle(), Q.ctypes.data_as(C.c_void_p), 256, D, k, 0, 128, 2,
+                         od.ctypes.data_as(C.c_void_p), ol.ctypes.data_as(C.c_void_p), on.ctypes.data_as(C.c_void_p),
+                         C.byref(ne))
+    assert ne.value == 0 and secs > 0
+    for i in range(256):
+        assert np.array_equal(ol[i], want[i][1]) and np.array_equal(od[i].view(np.uint32), want[i][0].view(np.uint32))
+    st2 = ix.stats()
+    assert st2.batched_requests == 256 + 512 and (st2.batches - st.batches) <= 64

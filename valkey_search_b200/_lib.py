@@ -30,7 +30,7 @@ class Config(C.Structure):
         ("allow_replace_deleted", C.c_int32),
         ("device", C.c_int32),
         ("max_batch", C.c_uint32),
-        ("reserved", C.c_uint32),
+        ("batch_window_us", C.c_uint32),
     ]
 
 
@@ -58,6 +58,8 @@ class Stats(C.Structure):
         ("dim", C.c_int32),
         ("last_qt", C.c_uint32),
         ("last_passes", C.c_uint32),
+        ("batches", C.c_uint64),
+        ("batched_requests", C.c_uint64),
     ]
 
 

@@ -8,6 +8,7 @@
 #include <cmath>
 #include <cstring>
 
+#include "batcher.h"
 #include "hnsw.h"
 #include "tensor_path.h"
 
@@ -259,7 +260,8 @@ void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, ui
   const uint32_t total_tiles = (uint32_t)std::max<uint64_t>(1, (max_rows + kScanTileRows - 1) / kScanTileRows);
   uint32_t slabs;
   if (qtiles == 1)
-    slabs = ix->num_sms;
+    slabs = std::min<uint32_t>(ix->num_sms, std::max<uint32_t>(1, total_tiles / 4));  // >= 4 tiles per CTA: small
+                                                                                    // indexes stay latency-lean
   else
     slabs = (4 * ix->num_sms + qtiles - 1) / qtiles;
   slabs = std::max<uint32_t>(1, std::min<uint32_t>(slabs, total_tiles));
@@ -615,6 +617,7 @@ int vkgpu_index_create(const vkgpu_config *cfg, vkgpu_index **out) {
       ix->capacity = want;
       if (ix->hnsw) hnsw_reserve(ix, want);
     }
+    if (cfg->batch_window_us) ix->batcher = new Batcher(ix, ix->dim, ix->cfg.max_batch, cfg->batch_window_us);
     *out = ix;
   });
   if (rc != VKGPU_OK && ix) {
@@ -626,6 +629,10 @@ int vkgpu_index_create(const vkgpu_config *cfg, vkgpu_index **out) {
 
 void vkgpu_index_destroy(vkgpu_index *ix) {
   if (!ix) return;
+  if (ix->batcher) {
+    delete static_cast<Batcher *>(ix->batcher);  // drains and joins the dispatcher thread
+    ix->batcher = nullptr;
+  }
   cudaSetDevice(ix->device);
   cudaDeviceSynchronize();
   if (ix->hnsw) hnsw_destroy(ix);
@@ -736,6 +743,20 @@ int vkgpu_search_batch(vkgpu_index *ix, const float *Q, uint32_t B, uint32_t k, 
 
 int vkgpu_search(vkgpu_index *ix, const float *q, uint32_t k, uint32_t ef, const vkgpu_filter *filter,
                  uint64_t deadline_ns, float *out_dist, uint64_t *out_labels, uint32_t *out_n) {
+  if (ix && ix->batcher && !filter && q && out_dist && out_labels && out_n && k >= 1) {
+    // dynamic batching: this call joins whatever other reader threads are asking right now
+    BatchRequest r;
+    r.q = q;
+    r.k = k;
+    r.ef = ef;
+    r.deadline_ns = deadline_ns;
+    r.out_dist = out_dist;
+    r.out_labels = out_labels;
+    r.out_n = out_n;
+    const int rc = static_cast<Batcher *>(ix->batcher)->submit(&r);
+    if (rc != VKGPU_OK) set_last_error(r.err);
+    return rc;
+  }
   return vkgpu_search_batch(ix, q, 1, k, ef, filter, deadline_ns, out_dist, out_labels, out_n);
 }
 
@@ -829,6 +850,10 @@ int vkgpu_get_stats(vkgpu_index *ix, vkgpu_stats *out) {
     out->dim = (int32_t)ix->dim;
     out->last_qt = ix->last_qt;
     out->last_passes = ix->last_passes;
+    if (ix->batcher) {
+      out->batches = static_cast<Batcher *>(ix->batcher)->batches();
+      out->batched_requests = static_cast<Batcher *>(ix->batcher)->requests();
+    }
   });
 }
 

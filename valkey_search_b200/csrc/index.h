@@ -134,6 +134,7 @@ struct vkgpu_index_impl {
   DevBuf dNorm;    // [phys_cap] fp32 squared norms (of the bf16-rounded rows)
   bool tensor_ready = false;
   void *tensor_state = nullptr;  // tensor_path.cu private state
+  void *batcher = nullptr;       // Batcher* when cfg.batch_window_us != 0
   std::mutex tensor_mu;
 
   // ---- HNSW graph (device) + host mirror of the small per-node state

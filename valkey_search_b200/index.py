@@ -85,7 +85,7 @@ class VectorBase:
     _ALGO = None
 
     def __init__(self, dimensions, distance_metric, initial_cap, *, block_size=0, m=0, ef_construction=0,
-                 ef_runtime=0, allow_replace_deleted=False, device=0, max_batch=1024):
+                 ef_runtime=0, allow_replace_deleted=False, device=0, max_batch=1024, batch_window_us=0):
         self.dimensions_ = int(dimensions)
         self.distance_metric_ = DistanceMetric(distance_metric)
         self.normalize_ = self.distance_metric_ == DistanceMetric.COSINE  # vector_base.cc:146-149
@@ -103,6 +103,7 @@ class VectorBase:
         cfg.allow_replace_deleted = int(bool(allow_replace_deleted))
         cfg.device = int(device)
         cfg.max_batch = int(max_batch)
+        cfg.batch_window_us = int(batch_window_us)
         self._h = C.c_void_p()
         L.check(self._lib.vkgpu_index_create(C.byref(cfg), C.byref(self._h)))
         self._mu = threading.Lock()           # key_to_metadata_mutex_
@@ -309,8 +310,13 @@ class VectorBase:
                     arr[b].label_bitmap = a.ctypes.data
                     arr[b].bitmap_bits = a.size * 8
             fptr = arr
-        rc = self._lib.vkgpu_search_batch(self._h, self._ptr(Q), B, int(k), int(ef), fptr, int(deadline_ns),
-                                          self._ptr(dist), self._ptr(labels), self._ptr(n))
+        if B == 1 and fptr is None:
+            # one query per call, the module's shape: goes through vkgpu_search (and the dynamic batcher if on)
+            rc = self._lib.vkgpu_search(self._h, self._ptr(Q), int(k), int(ef), None, int(deadline_ns),
+                                        self._ptr(dist), self._ptr(labels), self._ptr(n))
+        else:
+            rc = self._lib.vkgpu_search_batch(self._h, self._ptr(Q), B, int(k), int(ef), fptr, int(deadline_ns),
+                                              self._ptr(dist), self._ptr(labels), self._ptr(n))
         if rc == L.ERR_CANCELLED:
             raise StatusError("CANCELLED", "Search operation cancelled due to timeout")
         if rc != L.OK:
