@@ -359,9 +359,22 @@ def prefilter_workload(args):
     lists = [np.arange(b % 100, N, 100, dtype=np.uint64) for b in range(B)]
     sel = sum(len(x) for x in lists)
     filt = (L.Filter * B)()
+    tag_sets = {}
     for b in range(B):
-        filt[b].labels = lists[b].ctypes.data
-        filt[b].n_labels = lists[b].size
+        if args.host_lists:  # candidate label lists shipped from the host on every call
+            filt[b].labels = lists[b].ctypes.data
+            filt[b].n_labels = lists[b].size
+            continue
+        t = b % 100          # default: the tag's posting list lives on the device as a label bitmap (N1)
+        if t not in tag_sets:
+            bm = np.zeros((N + 7) // 8, np.uint8)
+            ids = lists[b]
+            np.bitwise_or.at(bm, (ids >> np.uint64(3)).astype(np.int64),
+                             (1 << (ids & np.uint64(7)).astype(np.uint8)).astype(np.uint8))
+            sid = C.c_uint64()
+            L.check(lib.vkgpu_set_create(ix.handle(), bm.ctypes.data, N, C.byref(sid)))
+            tag_sets[t] = sid.value
+        filt[b].device_set = tag_sets[t]
     od, ol, on = np.empty((B, k), np.float32), np.empty((B, k), np.uint64), np.empty(B, np.uint32)
 
     def step():
@@ -407,7 +420,7 @@ def prefilter_workload(args):
             "data": "synthetic N(0,1) fp32; tag = row % 100",
             "config": {"workload": f"pre-filter 1% + exact kNN, one shard of BASELINE configs[4]: {N}x{D}, batch={B}",
                        "rows": N, "selected_rows_per_query": sel // B},
-            "e2e": {"value": B * K / secs, "unit": UNIT, "h2d_bytes_per_step": B * D * 4 + sel * 4,
+            "e2e": {"value": B * K / secs, "unit": UNIT, "h2d_bytes_per_step": B * D * 4 + (sel * 4 if args.host_lists else B * 16),
                     "d2h_bytes_per_step": B * k * 12 + B * 4},
             "gpu_launches": int(ix.stats().kernels_launched - k0),
             "roofline": {"bound": "hbm", "kernel": "gather_scan_kernel<L2> (TMA row gather)", "achieved": ach,
@@ -437,6 +450,7 @@ def main():
                     help="flat = BASELINE configs[1] (the driver's default); hnsw = configs[2] at --rows")
     ap.add_argument("--ef", type=int, default=128)
     ap.add_argument("--window-us", type=int, default=300)
+    ap.add_argument("--host-lists", action="store_true", help="prefilter: ship label lists per call")
     args = ap.parse_args()
     if args.workload == "hnsw":
         return hnsw_workload(args)

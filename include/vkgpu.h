@@ -83,7 +83,14 @@ typedef struct vkgpu_filter {
   uint64_t n_labels;
   const uint8_t *label_bitmap; /* bit i set => label i allowed (inline filter, hnswalg.h:515-518), or NULL */
   uint64_t bitmap_bits;
+  uint64_t device_set;      /* id from vkgpu_set_create (a label bitmap already resident in HBM), or 0      */
 } vkgpu_filter;
+
+/* Device-resident candidate sets — the GPU-side mirror of a TAG / NUMERIC posting list
+ * (src/indexes/tag.h:44-178).  The bitmap over labels is uploaded once; searches refer to it by
+ * id, so a filtered query moves no candidate list across PCIe and does no host-side label lookups. */
+int vkgpu_set_create(vkgpu_index *h, const uint8_t *label_bitmap, uint64_t bits, uint64_t *out_set_id);
+int vkgpu_set_destroy(vkgpu_index *h, uint64_t set_id);
 
 typedef struct vkgpu_stats {
   uint64_t count;            /* live vectors          (GetTrackedKeyCount, vector_base.cc:385-409)     */

@@ -24,7 +24,7 @@ def test_header_symbols_are_exported(built):
 def test_struct_layout_matches_header(built):
     from valkey_search_b200 import _lib as L
     assert C.sizeof(L.Config) == 56
-    assert C.sizeof(L.Filter) == 32
+    assert C.sizeof(L.Filter) == 40
     assert C.sizeof(L.Stats) == 104
 
 

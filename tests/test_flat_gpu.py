@@ -186,3 +186,36 @@ def test_flat_large_property_checks(built):
         for s in sample:
             ds = p.vko_l2sq(Q[b], X[s], D)
             assert (ds, int(s)) > kth or int(s) in got
+
+
+def test_device_resident_filter_sets(built):
+    """a TAG posting list mirrored on the device as a label bitmap (vkgpu_set_create) drives the
+    pre-filtered exact search without host-side label lists; results equal the oracle's subset search, also
+    after the index mutates (cached slot lists are rebuilt)."""
+    rng = np.random.default_rng(17)
+    N, D, k = 6000, 80, 10
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    ix = _mk(D, "L2", cap=N)
+    ix.AddRecordsBulk([f"k{i}" for i in range(N)], X)
+    orc = O.PortFlat(D, O.L2)
+    orc.add_many(X)
+    tags = {t: [i for i in range(N) if i % 7 == t] for t in range(3)}
+    sets = {t: ix.CreateFilterSet([f"k{i}" for i in tags[t]]) for t in tags}
+    Q = rng.standard_normal((6, D)).astype(np.float32)
+    for rnd in range(2):
+        for t in tags:
+            res = ix.SearchWithSet(Q, k, sets[t])
+            for b in range(Q.shape[0]):
+                d, l = orc.search_subset(Q[b], k, np.array(tags[t], np.uint64))
+                assert [r.external_id for r in res[b]] == [f"k{int(i)}" for i in l]
+                assert np.array_equal(_bits([r.distance for r in res[b]]), _bits(d))
+        # mutate: swap-deletes move rows between slots; the sets must follow the labels
+        for i in (0, 7, 14, 5999):
+            ix.RemoveRecord(f"k{i}")
+            orc.remove(i)
+            for t in tags:
+                if i in tags[t]:
+                    tags[t].remove(i)
+    ix.DestroyFilterSet(sets[0])
+    with pytest.raises(Exception):
+        ix.SearchWithSet(Q, k, sets[0])

@@ -97,6 +97,11 @@ def test_hnsw_tombstones_and_inline_filter(built):
     for b in range(16):
         d, l = orc.search(Q[b], 10, 50, allow=bm)
         assert np.array_equal(labels[b, : n[b]], l) and np.array_equal(_bits(dist[b, : n[b]]), _bits(d))
+    sid = ix.CreateFilterSet([int(i) for i in allowed])  # same bitmap, resident on the device
+    res = ix.SearchWithSet(Q, 10, sid, ef_runtime=50)
+    for b in range(16):
+        d, l = orc.search(Q[b], 10, 50, allow=bm)
+        assert [r.external_id for r in res[b]] == [int(x) for x in l]
     st = ix.stats()
     assert st.deleted == 400 and st.count == N - 400 and st.distance_evals > 0 and st.hops > 0
 

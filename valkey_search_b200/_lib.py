@@ -40,6 +40,7 @@ class Filter(C.Structure):
         ("n_labels", C.c_uint64),
         ("label_bitmap", C.c_void_p),
         ("bitmap_bits", C.c_uint64),
+        ("device_set", C.c_uint64),
     ]
 
 
@@ -91,6 +92,8 @@ SYMBOLS = {
     "vkgpu_merge_topk_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
     "vkgpu_hnsw_import": (C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_uint32, _P]),
     "vkgpu_hnsw_export": (C.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "vkgpu_set_create": (C.c_int, [_P, _P, C.c_uint64, C.POINTER(C.c_uint64)]),
+    "vkgpu_set_destroy": (C.c_int, [_P, C.c_uint64]),
     "vkgpu_get_stats": (C.c_int, [_P, C.POINTER(Stats)]),
     "vkgpu_set_flat_path": (C.c_int, [_P, C.c_int]),
     "vkgpu_set_profiling": (C.c_int, [_P, C.c_int]),

@@ -369,8 +369,8 @@ __global__ void __launch_bounds__(GT) gather_scan_kernel(const GatherParams p) {
   uint32_t *sh = reinterpret_cast<uint32_t *>(full + 2);            // [0]=thr [1]=cnt
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gi = tid >> 2, u = tid & 3;
   const uint32_t b = blockIdx.x, slab = blockIdx.y, slabs = gridDim.y;
-  const uint64_t base = p.list_off[b];
-  const uint64_t n = p.list_off[b + 1] - base;
+  const uint32_t *ids = p.list_ptr[b];
+  const uint64_t n = p.list_len[b];
   const uint32_t tiles = (uint32_t)((n + R - 1) / R);
   Cand *my = p.ws + ((size_t)b * slabs + slab) * p.cap;
 
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(GT) gather_scan_kernel(const GatherParams p) {
     if (lane == 0) mbar_arrive_expect_tx(&full[st], m * row_bytes);
     __syncwarp();
     for (uint32_t r = lane; r < m; r += 32)
-      bulk_g2s(stage0 + ((size_t)st * R + r) * stride, p.X + (size_t)p.row_ids[base + r0 + r] * p.Dp, row_bytes, &full[st]);
+      bulk_g2s(stage0 + ((size_t)st * R + r) * stride, p.X + (size_t)ids[r0 + r] * p.Dp, row_bytes, &full[st]);
   };
 
   uint32_t it = 0;
@@ -411,7 +411,7 @@ __global__ void __launch_bounds__(GT) gather_scan_kernel(const GatherParams p) {
         const uint32_t o = f32_to_ord(d);
         if (o <= sh[0]) {
           const uint32_t pos = atomicAdd(&sh[1], 1u);
-          const uint32_t slot = p.row_ids[base + r0 + r];
+          const uint32_t slot = ids[r0 + r];
           Cand cd;
           cd.ord = o;
           cd.slot = slot;

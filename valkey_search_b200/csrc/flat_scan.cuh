@@ -50,8 +50,8 @@ void flat_scan_set_smem_attr(size_t max_smem);
 struct GatherParams {
   const float *X;
   const uint64_t *labels;
-  const uint32_t *row_ids;   // concatenated slot lists
-  const uint64_t *list_off;  // [B+1]
+  const uint32_t *const *list_ptr;  // [B] device pointers: the slot list of each query
+  const uint64_t *list_len;         // [B]
   const float *Q;            // zero-padded queries [B][Dp]
   uint32_t Dp, k, cap, rows_per_stage;
   Cand *ws;                  // [B][slabs][cap]

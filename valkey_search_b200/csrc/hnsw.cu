@@ -488,6 +488,13 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
       const bool none = !f.label_bitmap && !f.labels;
       hptr[b] = none ? 0 : (uint64_t)(uintptr_t)(c->scratch1.as<uint8_t>() + offs[b]);
       hptr[B + b] = bits;
+      if (f.device_set) {  // label bitmap already resident in HBM (vkgpu_set_create)
+        std::lock_guard<std::mutex> sl(ix->sets_mu);
+        auto it = ix->sets.find(f.device_set);
+        VK_REQUIRE(it != ix->sets.end(), VKGPU_ERR_NOT_FOUND, "unknown device set id");
+        hptr[b] = (uint64_t)(uintptr_t)it->second->bitmap.p;
+        hptr[B + b] = it->second->bits;
+      }
     }
     if (total) VK_CUDA(cudaMemcpyAsync(c->scratch1.p, hb, total, cudaMemcpyHostToDevice, s));
     VK_CUDA(cudaMemcpyAsync(c->scratch2.p, hptr, hdr_bytes, cudaMemcpyHostToDevice, s));

@@ -188,7 +188,9 @@ static constexpr uint32_t kMaxFusedK = 1024;
 
 // pre-filter exact search: one slot list per query (longest list = n_rows)
 static void gather_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff,
-                                 const uint32_t *d_row_ids, const uint64_t *d_list_off, uint64_t n_rows) {
+                                 const uint32_t *const *d_list_ptr, const uint64_t *d_list_len, uint64_t n_rows) {
+  VK_REQUIRE(k_eff >= 1 && k_eff <= kMaxFusedK, VKGPU_ERR_UNSUPPORTED,
+             "k > 1024 is not implemented on the fused top-k path yet");
   // rows per stage: as many as fit twice while leaving room for 2 CTAs per SM
   const uint32_t stride = ix->Dp * 4 + 64;
   const size_t budget = (ix->smem_max + 1024) / 2 - 1024;
@@ -212,8 +214,8 @@ static void gather_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B,
   GatherParams gp{};
   gp.X = ix->dX.as<float>();
   gp.labels = ix->dLabels.as<uint64_t>();
-  gp.row_ids = d_row_ids;
-  gp.list_off = d_list_off;
+  gp.list_ptr = d_list_ptr;
+  gp.list_len = d_list_len;
   gp.Q = c->q_pad.as<float>();
   gp.Dp = ix->Dp;
   gp.k = k_eff;
@@ -244,15 +246,12 @@ static void gather_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B,
   ix->last_passes = B;
 }
 
-void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff,
-                              const uint32_t *d_row_ids, const uint64_t *d_list_off, bool per_query_lists,
-                              uint64_t n_rows) {
+void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff) {
   VK_REQUIRE(k_eff >= 1 && k_eff <= kMaxFusedK, VKGPU_ERR_UNSUPPORTED,
              "k > 1024 is not implemented on the fused top-k path yet");
-  if (per_query_lists) {
-    gather_search_device(ix, c, B, k_eff, d_row_ids, d_list_off, n_rows);
-    return;
-  }
+  const uint32_t *d_row_ids = nullptr;
+  const uint64_t *d_list_off = nullptr;
+  const uint64_t n_rows = ix->n;
   int qt = (B == 1 ? 1 : B == 2 ? 2 : B <= 4 ? 4 : 8);
   const uint32_t qtiles = (B + qt - 1) / qt;
   const uint32_t cap = std::max<uint32_t>(256, next_pow2(k_eff + kScanTileRows));
@@ -364,6 +363,31 @@ static void fetch_results(SearchCtx *c, uint32_t B, uint32_t k_dev, uint32_t k_u
   }
 }
 
+// Slot list of a device-resident label set, (re)built on the device when the index has mutated since.
+DeviceSet *device_set_slots(vkgpu_index_impl *ix, SearchCtx *c, uint64_t set_id) {
+  std::lock_guard<std::mutex> lk(ix->sets_mu);
+  auto it = ix->sets.find(set_id);
+  VK_REQUIRE(it != ix->sets.end(), VKGPU_ERR_NOT_FOUND, "unknown device set id");
+  DeviceSet *ds = it->second.get();
+  if (ds->built_epoch != ix->mutation_epoch) {
+    ix->set_scratch.reserve(std::max<uint64_t>(ix->n, 1) * 4);
+    ix->set_count.reserve(8);
+    VK_CUDA(cudaMemsetAsync(ix->set_count.p, 0, 8, c->cur));
+    launch_bitmap_to_slots(ix->dLabels.as<uint64_t>(), ix->n, ds->bitmap.as<uint8_t>(), ds->bits,
+                           ix->set_scratch.as<uint32_t>(), ix->set_count.as<unsigned long long>(), c->cur);
+    unsigned long long cnt = 0;
+    VK_CUDA(cudaMemcpyAsync(&cnt, ix->set_count.p, 8, cudaMemcpyDeviceToHost, c->cur));
+    VK_CUDA(cudaStreamSynchronize(c->cur));
+    ds->slots.reserve(std::max<uint64_t>(cnt, 1) * 4);
+    if (cnt) VK_CUDA(cudaMemcpyAsync(ds->slots.p, ix->set_scratch.p, cnt * 4, cudaMemcpyDeviceToDevice, c->cur));
+    VK_CUDA(cudaStreamSynchronize(c->cur));
+    ds->nslots = cnt;
+    ds->built_epoch = ix->mutation_epoch;
+    ix->kernels++;
+  }
+  return ds;
+}
+
 // FLAT search over the whole shard (vector_flat.cc:224-254: k = min(k,count); empty index => empty reply)
 static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_t B, uint32_t k,
                         const vkgpu_filter *filters, float *out_dist, uint64_t *out_labels, uint32_t *out_n,
@@ -383,14 +407,24 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
 
   uint32_t k_eff;
   if (filters) {
-    // pre-filter path (VectorBase::AddPrefilteredKey, vector_base.cc:509-530): labels -> slots on the host
-    // (unknown labels skipped, vector_base.cc:513-516; duplicates collapse), one gather list per query.
+    // pre-filter path (VectorBase::AddPrefilteredKey, vector_base.cc:509-530): one slot list per query.
+    //  * device_set : a label bitmap already resident in HBM; its slot list is built on the device and cached
+    //  * labels     : labels -> slots on the host (unknown labels skipped, vector_base.cc:513-516; duplicates
+    //                 collapse), uploaded
+    //  * bitmap     : host bitmap -> slots on the host
     VK_REQUIRE(!out_on_device, VKGPU_ERR_UNSUPPORTED, "filtered search needs host outputs");
     std::vector<uint32_t> slots;
-    std::vector<uint64_t> off(B + 1, 0);
+    std::vector<uint64_t> ptrs(B, 0), lens(B, 0), host_off(B, ~0ull);
     uint64_t longest = 0;
     for (uint32_t b = 0; b < B; b++) {
       const vkgpu_filter &f = filters[b];
+      if (f.device_set) {
+        DeviceSet *ds = device_set_slots(ix, c, f.device_set);
+        ptrs[b] = (uint64_t)(uintptr_t)ds->slots.p;
+        lens[b] = ds->nslots;
+        longest = std::max<uint64_t>(longest, ds->nslots);
+        continue;
+      }
       size_t start = slots.size();
       if (f.labels) {
         for (uint64_t i = 0; i < f.n_labels; i++) {
@@ -407,21 +441,26 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
       }
       if (!std::is_sorted(slots.begin() + start, slots.end())) std::sort(slots.begin() + start, slots.end());
       slots.erase(std::unique(slots.begin() + start, slots.end()), slots.end());
-      off[b + 1] = slots.size();
-      longest = std::max<uint64_t>(longest, slots.size() - start);
+      host_off[b] = start;
+      lens[b] = slots.size() - start;
+      longest = std::max<uint64_t>(longest, lens[b]);
     }
     k_eff = (uint32_t)std::min<uint64_t>(k, std::max<uint64_t>(longest, 1));
     const size_t slots_bytes = (slots.size() * 4 + 7) & ~size_t(7);
     c->lists.reserve(std::max<size_t>(slots_bytes, 8));
-    c->list_off.reserve(off.size() * 8);
-    c->h_misc.reserve(slots_bytes + off.size() * 8);
-    uint8_t *off_host = c->h_misc.as<uint8_t>() + slots_bytes;
+    for (uint32_t b = 0; b < B; b++)
+      if (host_off[b] != ~0ull) ptrs[b] = (uint64_t)(uintptr_t)(c->lists.as<uint32_t>() + host_off[b]);
+    c->list_off.reserve((size_t)B * 16);
+    c->h_misc.reserve(slots_bytes + (size_t)B * 16);
+    uint8_t *meta_host = c->h_misc.as<uint8_t>() + slots_bytes;
     std::memcpy(c->h_misc.p, slots.data(), slots.size() * 4);
-    std::memcpy(off_host, off.data(), off.size() * 8);
+    std::memcpy(meta_host, ptrs.data(), (size_t)B * 8);
+    std::memcpy(meta_host + (size_t)B * 8, lens.data(), (size_t)B * 8);
     if (!slots.empty())
       VK_CUDA(cudaMemcpyAsync(c->lists.p, c->h_misc.p, slots.size() * 4, cudaMemcpyHostToDevice, c->cur));
-    VK_CUDA(cudaMemcpyAsync(c->list_off.p, off_host, off.size() * 8, cudaMemcpyHostToDevice, c->cur));
-    flat_exact_search_device(ix, c, B, k_eff, c->lists.as<uint32_t>(), c->list_off.as<uint64_t>(), true, longest);
+    VK_CUDA(cudaMemcpyAsync(c->list_off.p, meta_host, (size_t)B * 16, cudaMemcpyHostToDevice, c->cur));
+    gather_search_device(ix, c, B, k_eff, c->list_off.as<const uint32_t *>(),
+                         reinterpret_cast<const uint64_t *>(c->list_off.as<uint8_t>() + (size_t)B * 8), longest);
   } else {
     k_eff = (uint32_t)std::min<uint64_t>(k, ix->n);
     bool use_tensor = false;
@@ -436,7 +475,7 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     if (use_tensor && tensor_path_supported(ix, B, k_eff))
       tensor_search_device(ix, c, B, k_eff);
     else
-      flat_exact_search_device(ix, c, B, k_eff, nullptr, nullptr, false, ix->n);
+      flat_exact_search_device(ix, c, B, k_eff);
   }
 
   if (out_on_device) {
@@ -649,6 +688,12 @@ void vkgpu_index_destroy(vkgpu_index *ix) {
       b->release();
     for (PinnedBuf *b : {&c->h_q, &c->h_dist, &c->h_labels, &c->h_n, &c->h_misc}) b->release();
   }
+  for (auto &kv : ix->sets) {
+    kv.second->bitmap.release();
+    kv.second->slots.release();
+  }
+  ix->set_scratch.release();
+  ix->set_count.release();
   ix->dX.release();
   ix->dLabels.release();
   ix->h_stage.release();
@@ -662,6 +707,7 @@ int vkgpu_add_batch(vkgpu_index *ix, const uint64_t *labels, const float *vecs, 
     if (n == 0) return;
     std::unique_lock<std::shared_mutex> lk(ix->rw);
     VK_CUDA(cudaSetDevice(ix->device));
+    ix->mutation_epoch++;
     if (ix->cfg.algo == VKGPU_FLAT)
       flat_add_rows(ix, labels, vecs, n, false);
     else
@@ -675,6 +721,7 @@ int vkgpu_add_batch_device(vkgpu_index *ix, const uint64_t *labels, const float 
     if (n == 0) return;
     std::unique_lock<std::shared_mutex> lk(ix->rw);
     VK_CUDA(cudaSetDevice(ix->device));
+    ix->mutation_epoch++;
     if (ix->cfg.algo == VKGPU_FLAT)
       flat_add_rows(ix, labels, d_vecs, n, true);
     else
@@ -689,6 +736,7 @@ int vkgpu_modify(vkgpu_index *ix, uint64_t label, const float *vec) {
     VK_REQUIRE(ix && vec, VKGPU_ERR_INVALID, "null argument");
     std::unique_lock<std::shared_mutex> lk(ix->rw);
     VK_CUDA(cudaSetDevice(ix->device));
+    ix->mutation_epoch++;
     // vector_flat.cc:181-198 / vector_hnsw.cc:201-236: unknown id => InternalError "Couldn't find internal id"
     VK_REQUIRE(ix->slot_of.has(label), VKGPU_ERR_NOT_FOUND, "Couldn't find internal id: " + std::to_string(label));
     if (ix->cfg.algo == VKGPU_FLAT)
@@ -703,6 +751,7 @@ int vkgpu_remove(vkgpu_index *ix, uint64_t label) {
     VK_REQUIRE(ix, VKGPU_ERR_INVALID, "null argument");
     std::unique_lock<std::shared_mutex> lk(ix->rw);
     VK_CUDA(cudaSetDevice(ix->device));
+    ix->mutation_epoch++;
     if (ix->cfg.algo == VKGPU_FLAT)
       flat_remove(ix, label);
     else
@@ -868,6 +917,35 @@ int vkgpu_set_flat_path(vkgpu_index *ix, int path) {
       tensor_prepare(ix);
     }
     ix->flat_path = path;
+  });
+}
+
+int vkgpu_set_create(vkgpu_index *ix, const uint8_t *label_bitmap, uint64_t bits, uint64_t *out_set_id) {
+  return guarded([&] {
+    VK_REQUIRE(ix && label_bitmap && out_set_id && bits, VKGPU_ERR_INVALID, "null argument");
+    VK_CUDA(cudaSetDevice(ix->device));
+    auto ds = std::make_unique<DeviceSet>();
+    ds->bits = bits;
+    ds->bitmap.reserve((bits + 7) / 8);
+    VK_CUDA(cudaMemcpy(ds->bitmap.p, label_bitmap, (bits + 7) / 8, cudaMemcpyHostToDevice));
+    std::lock_guard<std::mutex> lk(ix->sets_mu);
+    const uint64_t id = ix->next_set_id++;
+    ix->sets.emplace(id, std::move(ds));
+    *out_set_id = id;
+  });
+}
+
+int vkgpu_set_destroy(vkgpu_index *ix, uint64_t set_id) {
+  return guarded([&] {
+    VK_REQUIRE(ix, VKGPU_ERR_INVALID, "null argument");
+    VK_CUDA(cudaSetDevice(ix->device));
+    std::unique_lock<std::shared_mutex> lk(ix->rw);  // no search may be using the set
+    std::lock_guard<std::mutex> sl(ix->sets_mu);
+    auto it = ix->sets.find(set_id);
+    VK_REQUIRE(it != ix->sets.end(), VKGPU_ERR_NOT_FOUND, "unknown device set id");
+    it->second->bitmap.release();
+    it->second->slots.release();
+    ix->sets.erase(it);
   });
 }
 

@@ -111,6 +111,16 @@ struct SearchCtx {
   bool ev_pending[kNumKernelKinds] = {};
 };
 
+// Device-resident candidate set ("next" row N1): the GPU mirror of a TAG/NUMERIC posting list — a label bitmap
+// uploaded once; its slot list is materialised on the device on first use and cached until the index mutates.
+struct DeviceSet {
+  DevBuf bitmap;
+  uint64_t bits = 0;
+  DevBuf slots;
+  uint64_t nslots = 0;
+  uint64_t built_epoch = ~0ull;
+};
+
 struct vkgpu_index_impl {
   vkgpu_config cfg{};
   int device = 0;
@@ -135,6 +145,11 @@ struct vkgpu_index_impl {
   bool tensor_ready = false;
   void *tensor_state = nullptr;  // tensor_path.cu private state
   void *batcher = nullptr;       // Batcher* when cfg.batch_window_us != 0
+  std::mutex sets_mu;
+  std::unordered_map<uint64_t, std::unique_ptr<DeviceSet>> sets;
+  uint64_t next_set_id = 1;
+  uint64_t mutation_epoch = 0;   // bumped by every add/modify/remove: cached slot lists are rebuilt lazily
+  DevBuf set_scratch, set_count;
   std::mutex tensor_mu;
 
   // ---- HNSW graph (device) + host mirror of the small per-node state
@@ -173,15 +188,15 @@ struct CtxLease {
 
 // ---- FLAT search drivers (flat_host.cu)
 // Runs the exact scan + merge for B padded queries already in c->q_pad; leaves results in c->out_*.
-void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff,
-                              const uint32_t *d_row_ids, const uint64_t *d_list_off, bool per_query_lists,
-                              uint64_t n_rows);
+void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff);
 
 // ---- small kernels (misc_kernels.cu)
 void launch_exact_distances(const float *X, uint32_t Dp, bool l2, const float *q_pad, const uint32_t *slots,
                             uint64_t n, float *out, cudaStream_t s);
 void launch_pad_rows(const float *src, uint32_t dim, float *dst, uint32_t Dp, uint64_t n, cudaStream_t s);
 void launch_iota_labels(uint64_t *dst, uint64_t start, uint64_t n, cudaStream_t s);
+void launch_bitmap_to_slots(const uint64_t *labels, uint64_t n, const uint8_t *bm, uint64_t bits, uint32_t *out,
+                            unsigned long long *count, cudaStream_t s);
 void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n, uint32_t G,
                                uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt, cudaStream_t s);
 

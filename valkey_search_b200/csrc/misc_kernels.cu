@@ -57,7 +57,36 @@ __global__ void pack_shard_results_kernel(const float *d_dist, const uint64_t *d
   }
 }
 
+// slots whose label is in the bitmap -> out[] (unordered, warp-aggregated append); *count receives the total
+__global__ void bitmap_to_slots_kernel(const uint64_t *__restrict__ labels, uint64_t n, const uint8_t *__restrict__ bm,
+                                       uint64_t bits, uint32_t *__restrict__ out, unsigned long long *count) {
+  const uint32_t lane = threadIdx.x & 31;
+  for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n;
+       i0 += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = i0 + lane;
+    bool in = false;
+    if (i < n) {
+      const uint64_t lab = labels[i];
+      in = lab < bits && ((bm[lab >> 3] >> (lab & 7)) & 1);
+    }
+    const uint32_t bal = __ballot_sync(0xffffffffu, in);
+    if (bal) {
+      unsigned long long base = 0;
+      if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(bal));
+      base = __shfl_sync(0xffffffffu, base, 0);
+      if (in) out[base + __popc(bal & ((1u << lane) - 1))] = (uint32_t)i;
+    }
+  }
+}
+
 }  // namespace
+
+void launch_bitmap_to_slots(const uint64_t *labels, uint64_t n, const uint8_t *bm, uint64_t bits, uint32_t *out,
+                            unsigned long long *count, cudaStream_t s) {
+  if (n == 0) return;
+  bitmap_to_slots_kernel<<<592, 256, 0, s>>>(labels, n, bm, bits, out, count);
+  VK_CUDA(cudaGetLastError());
+}
 
 void launch_exact_distances(const float *X, uint32_t Dp, bool l2, const float *q_pad, const uint32_t *slots,
                             uint64_t n, float *out, cudaStream_t s) {

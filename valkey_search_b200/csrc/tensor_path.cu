@@ -759,7 +759,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
     for (uint32_t i = 0; i < R; i++)
       VK_CUDA(cudaMemcpyAsync(c2->q_pad.as<float>() + (size_t)i * ix->Dp, c->q_pad.as<float>() + (size_t)redo[i] * ix->Dp,
                               (size_t)ix->Dp * 4, cudaMemcpyDeviceToDevice, s));
-    flat_exact_search_device(ix, c2, R, k_eff, nullptr, nullptr, false, ix->n);
+    flat_exact_search_device(ix, c2, R, k_eff);
     for (uint32_t i = 0; i < R; i++) {
       VK_CUDA(cudaMemcpyAsync(c->out_dist.as<float>() + (size_t)redo[i] * k_eff, c2->out_dist.as<float>() + (size_t)i * k_eff,
                               (size_t)k_eff * 4, cudaMemcpyDeviceToDevice, s));

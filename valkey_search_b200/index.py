@@ -304,6 +304,8 @@ class VectorBase:
                     keep.append(a)
                     arr[b].labels = a.ctypes.data
                     arr[b].n_labels = a.size
+                if "set" in f:
+                    arr[b].device_set = int(f["set"])
                 if "bitmap" in f:
                     a = np.ascontiguousarray(f["bitmap"], np.uint8)
                     keep.append(a)
@@ -342,6 +344,30 @@ class VectorBase:
         Q = self._prepare_queries(query)
         dist, labels, n = self._search_raw(Q, count, 0, [{"labels": np.array(ids, np.uint64)}], 0)
         return self._create_reply(dist[0], labels[0], int(n[0]))
+
+    # ------------------------------------------------------------------ device-resident candidate sets
+    def CreateFilterSet(self, keys):
+        """Mirror a TAG/NUMERIC posting list (the keys a filter matches, src/indexes/tag.h:44-178) on the device
+        as a label bitmap; returns an id usable as `filter_set=` in Search.  SURVEY §8f N1."""
+        with self._mu:
+            ids = [self.tracked_metadata_by_key_[k][0] for k in keys if k in self.tracked_metadata_by_key_]
+        nbits = (max(ids) + 1) if ids else 1
+        bm = np.zeros((nbits + 7) // 8, np.uint8)
+        if ids:
+            a = np.asarray(ids, np.uint64)
+            np.bitwise_or.at(bm, (a >> np.uint64(3)).astype(np.int64), (1 << (a & np.uint64(7)).astype(np.uint8)).astype(np.uint8))
+        sid = C.c_uint64()
+        L.check(self._lib.vkgpu_set_create(self._h, self._ptr(bm), nbits, C.byref(sid)))
+        return sid.value
+
+    def DestroyFilterSet(self, set_id):
+        L.check(self._lib.vkgpu_set_destroy(self._h, int(set_id)))
+
+    def SearchWithSet(self, query, count, set_id, ef_runtime=0):
+        """Exact (FLAT) / inline-filtered (HNSW) kNN restricted to a device-resident set."""
+        Q = self._prepare_queries(query)
+        dist, labels, n = self._search_raw(Q, count, ef_runtime, [{"set": set_id}] * Q.shape[0], 0)
+        return [self._create_reply(dist[b], labels[b], int(n[b])) for b in range(Q.shape[0])]
 
     # ------------------------------------------------------------------ info
     def stats(self):
