@@ -21,8 +21,12 @@ def test_unsupported_and_invalid_requests(built):
     l = np.empty(2000, np.uint64)
     n = np.zeros(1, np.uint32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    # k beyond the fused top-k limit: explicit UNSUPPORTED, not a silent fallback
-    rc = lib.vkgpu_search_batch(ix.handle(), p(q), 1, 2000, 0, None, 0, p(d), p(l), p(n))
+    # large k on a pre-filtered search is not implemented: explicit UNSUPPORTED, not a silent fallback
+    lab = np.arange(3000, dtype=np.uint64)
+    f = (L.Filter * 1)()
+    f[0].labels = lab.ctypes.data
+    f[0].n_labels = lab.size
+    rc = lib.vkgpu_search_batch(ix.handle(), p(q), 1, 2000, 0, f, 0, p(d), p(l), p(n))
     assert rc == L.ERR_UNSUPPORTED and b"1024" in lib.vkgpu_last_error()
     # expired deadline => CANCELLED (vector_hnsw.cc:327-329 / cancel::Token)
     rc = lib.vkgpu_search_batch(ix.handle(), p(q), 1, 10, 0, None, 1, p(d), p(l), p(n))

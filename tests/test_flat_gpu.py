@@ -219,3 +219,21 @@ def test_device_resident_filter_sets(built):
     ix.DestroyFilterSet(sets[0])
     with pytest.raises(Exception):
         ix.SearchWithSet(Q, k, sets[0])
+
+
+@pytest.mark.parametrize("metric", ["L2", "IP"])
+def test_flat_large_k_select_path(built, metric):
+    """k above the fused top-k limit (max-vector-knn allows 10 000+, ft_search_parser.cc:34-45): all distances +
+    radix select on (distance,label); ties at the k-th distance must resolve by label exactly."""
+    rng = np.random.default_rng(23)
+    N, D = 7000, 40
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    X[2000:4500] = X[2000]  # 2500 identical rows: the k-th boundary falls inside a tie for the queries below
+    ix = _mk(D, metric, cap=N)
+    ix.AddRecordsBulk([f"k{i}" for i in range(N)], X)
+    orc = O.PortFlat(D, METRICS[metric])
+    orc.add_many(X)
+    Q = rng.standard_normal((3, D)).astype(np.float32)
+    Q[0] = X[2000]
+    for k in (1025, 1500, 5000, 7000, 9000):
+        _check_batch(ix, orc, Q, k)

@@ -238,3 +238,28 @@ def test_hnsw_modify_and_readd(built):
     assert all(r.external_id != "k7" for r in ix.Search(target, 5, ef_runtime=64))
     assert ix.AddRecord("k7", target).name == "kAdded"  # new internal id
     assert ix.Search(target, 1, ef_runtime=64)[0].external_id == "k7"
+
+
+def test_hnsw_allow_replace_deleted_reuses_slots(built):
+    """search.hnsw-allow-replace-deleted (hnswalg.h:1297-1339): a new key takes over a tombstoned slot, the
+    graph does not grow, and the new vector is findable while the old key is gone."""
+    import valkey_search_b200 as V
+    rng = np.random.default_rng(41)
+    N, D = 2000, 32
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    ix = V.VectorHNSW(D, V.DistanceMetric.L2, initial_cap=N, m=16, ef_construction=100, ef_runtime=64,
+                      allow_replace_deleted=True)
+    ix.AddRecordsBulk([f"k{i}" for i in range(N)], X)
+    for i in range(10):
+        assert ix.RemoveRecord(f"k{i}") is True
+    assert ix.stats().deleted == 10
+    fresh = rng.standard_normal((6, D)).astype(np.float32) + 4.0
+    for j in range(6):
+        assert ix.AddRecord(f"new{j}", fresh[j]).name == "kAdded"
+    st = ix.stats()
+    assert st.deleted == 4 and st.count == N - 10 + 6  # six tombstones revived under new keys, four left
+    for j in range(6):
+        res = ix.Search(fresh[j], 1, ef_runtime=64)
+        assert res[0].external_id == f"new{j}" and res[0].distance == 0.0
+    got = {r.external_id for q in X[:10] for r in ix.Search(q, 5, ef_runtime=64)}
+    assert not any(k in got for k in (f"k{i}" for i in range(10)))

@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 
   const uint32_t tid = threadIdx.x;
   const uint32_t warp = tid >> 5, lane = tid & 31;
-  const uint32_t qtile = blockIdx.x, slab = blockIdx.y, slabs = gridDim.y;
+  const uint32_t qtile = blockIdx.x + p.qtile_base, slab = blockIdx.y, slabs = gridDim.y;
 
   // rows this CTA scans
   uint64_t list_base = 0, n_rows = p.n_rows;
@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kScanThreads, 1)
   }
   __syncthreads();
 
-  Cand *my_ws = p.ws + ((size_t)qtile * slabs + slab) * QT * p.cap;
+  Cand *my_ws = p.ws + ((size_t)blockIdx.x * slabs + slab) * QT * p.cap;
 
   if (warp == NCOMPUTE / 32) {
     // ------------------------------------------------------------------ copy-issuing warp
@@ -244,7 +244,9 @@ __global__ void __launch_bounds__(kScanThreads, 1)
         const float sum = __fadd_rn(__fadd_rn(v.x, v.z), __fadd_rn(v.y, v.w));
         // hnswlib/simsimd.h:16-34: L2 returns the sum; IP returns (float)(1.0 - (double)dot)
         const float dist = L2 ? sum : (float)(1.0 - (double)sum);
-        if ((q & 3) == (int)u && r < n_rows) {
+        if (p.all_dist) {
+          if ((q & 3) == (int)u && r < n_rows) p.all_dist[(size_t)q * n_rows + r] = dist;
+        } else if ((q & 3) == (int)u && r < n_rows) {
           const uint32_t o = f32_to_ord(dist);
           if (o <= thr[q]) {
             const uint32_t pos = atomicAdd(&cnt[q], 1u);
@@ -299,7 +301,7 @@ __global__ void __launch_bounds__(kScanThreads, 1)
   }
 
   named_bar_sync(1, NCOMPUTE);
-  if (tid < QT) p.ws_cnt[((size_t)qtile * slabs + slab) * QT + tid] = cnt[tid];
+  if (tid < QT) p.ws_cnt[((size_t)blockIdx.x * slabs + slab) * QT + tid] = cnt[tid];
 }
 
 template <int QT, bool L2>

@@ -26,6 +26,8 @@ struct ScanParams {
   uint32_t stages;           // pipeline depth
   Cand *ws;                  // [qtiles][slabs][QT][cap]
   uint32_t *ws_cnt;          // [qtiles][slabs][QT]
+  float *all_dist;           // optional [QT][n_rows]: write every distance instead of gating (large-k path)
+  uint32_t qtile_base;       // first query tile of this launch inside Q
 };
 
 // bytes per pipeline stage / of dynamic shared memory the scan kernel needs

@@ -37,6 +37,7 @@ struct Hnsw {
   uint64_t rows_reserved = 0;
   std::vector<int32_t> h_level;
   std::vector<uint8_t> h_deleted;
+  std::vector<uint32_t> free_ids;  // tombstoned slots available for reuse (hnsw-allow-replace-deleted)
   std::vector<uint64_t> h_up_off;
   uint64_t num_deleted = 0;
   uint32_t rng = 100;  // std::default_random_engine(100), hnswalg.h:149
@@ -584,6 +585,7 @@ void hnsw_remove(vkgpu_index_impl *ix, uint64_t label) {
   VK_REQUIRE(!g->h_deleted[id], VKGPU_ERR_INTERNAL, "The requested to delete element is already deleted");
   g->h_deleted[id] = 1;
   g->num_deleted++;
+  if (ix->cfg.allow_replace_deleted) g->free_ids.push_back(id);  // deleted_elements, hnswalg.h:1203-1206
   hnsw_mark_deleted_kernel<<<1, 1, 0, ix->mut_stream>>>(g->hdr0.as<uint32_t>(), id, 1);
   VK_CUDA(cudaGetLastError());
   VK_CUDA(cudaStreamSynchronize(ix->mut_stream));

@@ -190,7 +190,7 @@ static constexpr uint32_t kMaxFusedK = 1024;
 static void gather_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff,
                                  const uint32_t *const *d_list_ptr, const uint64_t *d_list_len, uint64_t n_rows) {
   VK_REQUIRE(k_eff >= 1 && k_eff <= kMaxFusedK, VKGPU_ERR_UNSUPPORTED,
-             "k > 1024 is not implemented on the fused top-k path yet");
+             "k > 1024 is not implemented for pre-filtered searches yet");
   // rows per stage: as many as fit twice while leaving room for 2 CTAs per SM
   const uint32_t stride = ix->Dp * 4 + 64;
   const size_t budget = (ix->smem_max + 1024) / 2 - 1024;
@@ -246,9 +246,45 @@ static void gather_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B,
   ix->last_passes = B;
 }
 
+void flat_all_distances_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t b0, uint32_t nb, float *dist_out) {
+  (void)nb;
+  const int qt = kScanMaxQt;
+  const uint32_t cap = 256;
+  const uint32_t total_tiles = (uint32_t)std::max<uint64_t>(1, (ix->n + kScanTileRows - 1) / kScanTileRows);
+  const uint32_t slabs = std::min<uint32_t>(ix->num_sms, total_tiles);
+  const size_t stage_bytes = scan_stage_bytes(qt, true);
+  const uint32_t stages =
+      (uint32_t)std::min<size_t>(16, (ix->smem_max - 1024 - (size_t)cap * sizeof(Cand) - 512) / stage_bytes);
+  c->ws.reserve((size_t)slabs * qt * cap * sizeof(Cand));
+  c->ws_cnt.reserve((size_t)slabs * qt * 4);
+  ScanParams sp{};
+  sp.X = ix->dX.as<float>();
+  sp.labels = ix->dLabels.as<uint64_t>();
+  sp.n_rows = ix->n;
+  sp.Q = c->q_pad.as<float>();
+  sp.Dp = ix->Dp;
+  sp.k = 1;
+  sp.cap = cap;
+  sp.stages = stages;
+  sp.ws = c->ws.as<Cand>();
+  sp.ws_cnt = c->ws_cnt.as<uint32_t>();
+  sp.all_dist = dist_out;
+  sp.qtile_base = b0 / qt;
+  CUtensorMap tmX, tmQ;
+  const uint32_t q_rows = (b0 / qt + 1) * qt;
+  make_tensor_map_2d_f32(&tmX, ix->dX.p, ix->Dp, ix->n, (uint64_t)ix->Dp * 4, 32, kScanTileRows, true);
+  make_tensor_map_2d_f32(&tmQ, c->q_pad.p, ix->Dp, q_rows, (uint64_t)ix->Dp * 4, 32, qt, true);
+  ix->prof_begin(c, KK_SCAN);
+  launch_flat_scan(qt, ix->metric_l2, dim3(1, slabs), scan_smem_bytes(qt, cap, stages, true), c->cur, sp, &tmX, &tmQ);
+  ix->prof_end(c, KK_SCAN);
+  ix->kernels++;
+}
+
 void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff) {
-  VK_REQUIRE(k_eff >= 1 && k_eff <= kMaxFusedK, VKGPU_ERR_UNSUPPORTED,
-             "k > 1024 is not implemented on the fused top-k path yet");
+  if (k_eff > kMaxFusedK) {  // large k: all distances + radix select (flat_select.cu)
+    flat_select_search_device(ix, c, B, k_eff);
+    return;
+  }
   const uint32_t *d_row_ids = nullptr;
   const uint64_t *d_list_off = nullptr;
   const uint64_t n_rows = ix->n;
@@ -372,9 +408,11 @@ DeviceSet *device_set_slots(vkgpu_index_impl *ix, SearchCtx *c, uint64_t set_id)
   if (ds->built_epoch != ix->mutation_epoch) {
     ix->set_scratch.reserve(std::max<uint64_t>(ix->n, 1) * 4);
     ix->set_count.reserve(8);
+    ix->set_blocks.reserve(((ix->n + 255) / 256 + 1) * 4);
     VK_CUDA(cudaMemsetAsync(ix->set_count.p, 0, 8, c->cur));
     launch_bitmap_to_slots(ix->dLabels.as<uint64_t>(), ix->n, ds->bitmap.as<uint8_t>(), ds->bits,
-                           ix->set_scratch.as<uint32_t>(), ix->set_count.as<unsigned long long>(), c->cur);
+                           ix->set_scratch.as<uint32_t>(), ix->set_blocks.as<uint32_t>(),
+                           ix->set_count.as<unsigned long long>(), c->cur);
     unsigned long long cnt = 0;
     VK_CUDA(cudaMemcpyAsync(&cnt, ix->set_count.p, 8, cudaMemcpyDeviceToHost, c->cur));
     VK_CUDA(cudaStreamSynchronize(c->cur));
@@ -383,7 +421,7 @@ DeviceSet *device_set_slots(vkgpu_index_impl *ix, SearchCtx *c, uint64_t set_id)
     VK_CUDA(cudaStreamSynchronize(c->cur));
     ds->nslots = cnt;
     ds->built_epoch = ix->mutation_epoch;
-    ix->kernels++;
+    ix->kernels += 3;
   }
   return ds;
 }
@@ -694,6 +732,7 @@ void vkgpu_index_destroy(vkgpu_index *ix) {
   }
   ix->set_scratch.release();
   ix->set_count.release();
+  ix->set_blocks.release();
   ix->dX.release();
   ix->dLabels.release();
   ix->h_stage.release();

@@ -149,7 +149,7 @@ struct vkgpu_index_impl {
   std::unordered_map<uint64_t, std::unique_ptr<DeviceSet>> sets;
   uint64_t next_set_id = 1;
   uint64_t mutation_epoch = 0;   // bumped by every add/modify/remove: cached slot lists are rebuilt lazily
-  DevBuf set_scratch, set_count;
+  DevBuf set_scratch, set_count, set_blocks;
   std::mutex tensor_mu;
 
   // ---- HNSW graph (device) + host mirror of the small per-node state
@@ -189,14 +189,19 @@ struct CtxLease {
 // ---- FLAT search drivers (flat_host.cu)
 // Runs the exact scan + merge for B padded queries already in c->q_pad; leaves results in c->out_*.
 void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff);
+// every exact distance of queries [b0, b0+nb) (nb <= 8, b0 % 8 == 0) -> dist_out[nb][n]
+void flat_all_distances_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t b0, uint32_t nb, float *dist_out);
+// any-k exact search (flat_select.cu)
+void flat_select_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff);
 
 // ---- small kernels (misc_kernels.cu)
 void launch_exact_distances(const float *X, uint32_t Dp, bool l2, const float *q_pad, const uint32_t *slots,
                             uint64_t n, float *out, cudaStream_t s);
 void launch_pad_rows(const float *src, uint32_t dim, float *dst, uint32_t Dp, uint64_t n, cudaStream_t s);
 void launch_iota_labels(uint64_t *dst, uint64_t start, uint64_t n, cudaStream_t s);
+// ordered compaction; counts = scratch of ceil(n/256) u32
 void launch_bitmap_to_slots(const uint64_t *labels, uint64_t n, const uint8_t *bm, uint64_t bits, uint32_t *out,
-                            unsigned long long *count, cudaStream_t s);
+                            uint32_t *counts, unsigned long long *count, cudaStream_t s);
 void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n, uint32_t G,
                                uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt, cudaStream_t s);
 

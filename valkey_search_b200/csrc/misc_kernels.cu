@@ -57,34 +57,69 @@ __global__ void pack_shard_results_kernel(const float *d_dist, const uint64_t *d
   }
 }
 
-// slots whose label is in the bitmap -> out[] (unordered, warp-aggregated append); *count receives the total
-__global__ void bitmap_to_slots_kernel(const uint64_t *__restrict__ labels, uint64_t n, const uint8_t *__restrict__ bm,
-                                       uint64_t bits, uint32_t *__restrict__ out, unsigned long long *count) {
-  const uint32_t lane = threadIdx.x & 31;
-  for (uint64_t i0 = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < n;
-       i0 += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t i = i0 + lane;
-    bool in = false;
-    if (i < n) {
-      const uint64_t lab = labels[i];
-      in = lab < bits && ((bm[lab >> 3] >> (lab & 7)) & 1);
-    }
-    const uint32_t bal = __ballot_sync(0xffffffffu, in);
-    if (bal) {
-      unsigned long long base = 0;
-      if (lane == 0) base = atomicAdd(count, (unsigned long long)__popc(bal));
-      base = __shfl_sync(0xffffffffu, base, 0);
-      if (in) out[base + __popc(bal & ((1u << lane) - 1))] = (uint32_t)i;
-    }
+// Ordered stream compaction: slots whose label is in the bitmap -> out[] in increasing slot order (so the
+// gather scan walks HBM monotonically).  Three small kernels: per-256-slot counts, exclusive scan, fill.
+__device__ __forceinline__ bool slot_in_set(const uint64_t *labels, uint64_t n, const uint8_t *bm, uint64_t bits,
+                                            uint64_t i) {
+  if (i >= n) return false;
+  const uint64_t lab = labels[i];
+  return lab < bits && ((bm[lab >> 3] >> (lab & 7)) & 1);
+}
+__global__ void __launch_bounds__(256) set_count_kernel(const uint64_t *__restrict__ labels, uint64_t n,
+                                                        const uint8_t *__restrict__ bm, uint64_t bits,
+                                                        uint32_t *__restrict__ counts) {
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const int c = __syncthreads_count(slot_in_set(labels, n, bm, bits, i));
+  if (threadIdx.x == 0) counts[blockIdx.x] = (uint32_t)c;
+}
+// in-place exclusive scan of counts[nb] by ONE block of 1024 threads; total -> *total
+__global__ void __launch_bounds__(1024) set_scan_kernel(uint32_t *counts, uint32_t nb, unsigned long long *total) {
+  __shared__ unsigned long long part[1024];
+  const uint32_t t = threadIdx.x;
+  const uint32_t per = (nb + 1023) / 1024;
+  const uint32_t lo = min(nb, t * per), hi = min(nb, lo + per);
+  unsigned long long s = 0;
+  for (uint32_t i = lo; i < hi; i++) s += counts[i];
+  part[t] = s;
+  __syncthreads();
+  for (uint32_t off = 1; off < 1024; off <<= 1) {  // inclusive Hillis-Steele
+    const unsigned long long v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
   }
+  unsigned long long run = t ? part[t - 1] : 0;
+  for (uint32_t i = lo; i < hi; i++) {
+    const uint32_t c = counts[i];
+    counts[i] = (uint32_t)run;  // sets hold < 2^32 slots
+    run += c;
+  }
+  if (t == 1023) *total = part[1023];
+}
+__global__ void __launch_bounds__(256) set_fill_kernel(const uint64_t *__restrict__ labels, uint64_t n,
+                                                       const uint8_t *__restrict__ bm, uint64_t bits,
+                                                       const uint32_t *__restrict__ offsets, uint32_t *__restrict__ out) {
+  __shared__ uint32_t warp_base[8];
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool in = slot_in_set(labels, n, bm, bits, i);
+  const uint32_t bal = __ballot_sync(0xffffffffu, in);
+  if (lane == 0) warp_base[w] = __popc(bal);
+  __syncthreads();
+  uint32_t base = offsets[blockIdx.x];
+  for (uint32_t j = 0; j < w; j++) base += warp_base[j];
+  if (in) out[base + __popc(bal & ((1u << lane) - 1))] = (uint32_t)i;
 }
 
 }  // namespace
 
 void launch_bitmap_to_slots(const uint64_t *labels, uint64_t n, const uint8_t *bm, uint64_t bits, uint32_t *out,
-                            unsigned long long *count, cudaStream_t s) {
+                            uint32_t *counts, unsigned long long *count, cudaStream_t s) {
   if (n == 0) return;
-  bitmap_to_slots_kernel<<<592, 256, 0, s>>>(labels, n, bm, bits, out, count);
+  const uint32_t nb = (uint32_t)((n + 255) / 256);
+  set_count_kernel<<<nb, 256, 0, s>>>(labels, n, bm, bits, counts);
+  set_scan_kernel<<<1, 1024, 0, s>>>(counts, nb, count);
+  set_fill_kernel<<<nb, 256, 0, s>>>(labels, n, bm, bits, counts, out);
   VK_CUDA(cudaGetLastError());
 }
 
