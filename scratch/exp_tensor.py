@@ -1,0 +1,38 @@
+"""Throwaway: time the tensor candidate kernel under experiment flags (results are wrong under flags)."""
+import ctypes as C, os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import valkey_search_b200 as V
+from valkey_search_b200 import _lib as L
+N = int(os.environ.get("EXP_ROWS", 10_000_000)); D = 768; B = 1024; k = 100
+dev = torch.device("cuda", 0); torch.cuda.set_device(dev)
+lib = L.lib()
+ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+BLK = 1_000_000
+for blk in range((N + BLK - 1) // BLK):
+    rows = min(BLK, N - blk * BLK)
+    g = torch.Generator(device=dev); g.manual_seed(1234 + blk)
+    Xb = torch.randn((rows, D), generator=g, device=dev, dtype=torch.float32)
+    torch.cuda.synchronize()
+    L.check(lib.vkgpu_add_batch_device(ix.handle(), None, Xb.data_ptr(), rows))
+    del Xb
+g = torch.Generator(device=dev); g.manual_seed(4321)
+dQ = torch.randn((B, D), generator=g, device=dev)
+od = torch.empty((B, k), dtype=torch.float32, device=dev); ol = torch.empty((B, k), dtype=torch.int64, device=dev)
+on = torch.empty((B,), dtype=torch.int32, device=dev)
+def run(tag, env):
+    for kk, v in env.items(): os.environ[kk] = v
+    for _ in range(2):
+        L.check(lib.vkgpu_search_batch_device(ix.handle(), dQ.data_ptr(), B, k, 0, od.data_ptr(), ol.data_ptr(), on.data_ptr(), None))
+    torch.cuda.synchronize()
+    L.check(lib.vkgpu_set_profiling(ix.handle(), 1))
+    for _ in range(4):
+        L.check(lib.vkgpu_search_batch_device(ix.handle(), dQ.data_ptr(), B, k, 0, od.data_ptr(), ol.data_ptr(), on.data_ptr(), None))
+    torch.cuda.synchronize()
+    tm = L.Timings(); L.check(lib.vkgpu_get_timings(ix.handle(), C.byref(tm)))
+    L.check(lib.vkgpu_set_profiling(ix.handle(), 0))
+    print(tag, env, "ms per kind:", [round(tm.ms[i] / max(int(tm.launches[i]), 1), 3) for i in range(8)], flush=True)
+for spec in sys.argv[1:]:
+    pair, dbg = spec.split(":")
+    run(spec, {"VKGPU_TENSOR_PAIR": pair, "VKGPU_TENSOR_DEBUG": dbg})

@@ -97,3 +97,46 @@ def test_tensor_path_after_mutations(built):
     ix.SetSearchPath(V.PATH_EXACT_FMA)
     d0, l0, _ = ix.SearchBatchRaw(Q, k)
     assert np.array_equal(l0, l1) and np.array_equal(_bits(d0), _bits(d1))
+
+
+@pytest.mark.parametrize("pair", ["0", "1"])
+def test_tensor_path_adversarial_order_trims_lists(built, pair, monkeypatch):
+    """Rows arrive in DECREASING distance from every query, so each new row beats all earlier ones, passes every
+    running threshold and the per-(CTA, query) candidate lists overflow again and again: exercises the trim
+    rendezvous of the epilogue (no per-tile barrier) on both the single-CTA and the opt-in CTA-pair
+    (tcgen05 cta_group::2) kernel."""
+    import valkey_search_b200 as V
+    monkeypatch.setenv("VKGPU_TENSOR_PAIR", pair)
+    rng = np.random.default_rng(21)
+    N, D, B, k = 400_000, 64, 96, 100
+    centre = rng.standard_normal(D).astype(np.float32)
+    u = rng.standard_normal((N, D)).astype(np.float32)
+    u /= np.linalg.norm(u, axis=1, keepdims=True)
+    radius = np.linspace(40.0, 2.0, N, dtype=np.float32)[:, None]
+    X = (centre + radius * u).astype(np.float32)
+    Q = (centre + 0.05 * rng.standard_normal((B, D))).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    ix.SetSearchPath(V.PATH_EXACT_FMA)
+    d0, l0, _ = ix.SearchBatchRaw(Q, k)
+    ix.SetSearchPath(V.PATH_TENSOR)
+    d1, l1, _ = ix.SearchBatchRaw(Q, k)
+    assert np.array_equal(l0, l1), np.argwhere(l0 != l1)[:5]
+    assert np.array_equal(_bits(d0), _bits(d1))
+
+
+@pytest.mark.parametrize("metric,N,D,B,k", [("L2", 200_000, 768, 300, 100), ("IP", 90_000, 128, 1024, 10)])
+def test_tensor_pair_kernel_equals_exact_path(built, metric, N, D, B, k, monkeypatch):
+    """The opt-in tcgen05 cta_group::2 variant (two CTAs share one 256-row MMA) returns the same bits."""
+    import valkey_search_b200 as V
+    monkeypatch.setenv("VKGPU_TENSOR_PAIR", "1")
+    rng = np.random.default_rng(N + B)
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric[metric], initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    ix.SetSearchPath(V.PATH_EXACT_FMA)
+    d0, l0, _ = ix.SearchBatchRaw(Q, k)
+    ix.SetSearchPath(V.PATH_TENSOR)
+    d1, l1, _ = ix.SearchBatchRaw(Q, k)
+    assert np.array_equal(l0, l1) and np.array_equal(_bits(d0), _bits(d1))

@@ -90,6 +90,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {
   }
 }
+// Same, with a suspend-time hint (ns): the waiting thread is parked by the hardware for up to that long instead
+// of re-polling every ~100 cycles, so it stops competing for issue slots with the warps that still have work.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity, uint32_t hint_ns = 20000) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
+        : "memory");
+  } while (!ok);
+}
 // 1-D bulk copy global -> shared (TMA engine, no tensor map): `bytes` and both addresses 16-B aligned.
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes, uint64_t *bar) {
   asm volatile(

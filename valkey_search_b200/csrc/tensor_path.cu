@@ -15,11 +15,13 @@
 //      (flat_scan.cu) — still on the GPU, never on the CPU.
 // Output is therefore bit-identical to the exact path / the CPU oracle.
 //
-// Kernel anatomy (flat_tensor_kernel): 256 threads; warp 0 = TMA producer (cp.async.bulk.tensor, 128B
-// swizzle), warp 1 = single-thread tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-7 = epilogue
-// (tcgen05.ld 32x32b -> score -> threshold gate -> append).  Tile = 128 corpus rows (M) x 256 queries (N),
-// K streamed in 64-element (128 B) stages through a 4-deep smem ring; two 256-column TMEM accumulators
-// double-buffer MMA against the epilogue.  CTAs are persistent: (query tile, corpus slab) pairs.
+// Kernel anatomy (flat_tensor_kernel): 384 threads; warp 0 = TMA producer (cp.async.bulk.tensor, 128B
+// swizzle), warp 1 = single-thread tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-11 = epilogue
+// (tcgen05.ld 32x32b -> score -> threshold gate -> lane-parallel append).  Tile = 128 corpus rows (M) x 256
+// queries (N), K streamed in 64-element (128 B) stages through a 4-deep smem ring; two 256-column TMEM
+// accumulators double-buffer MMA against the epilogue.  CTAs are persistent: (query tile, corpus slab) pairs.
+// The epilogue warps run the tile loop WITHOUT per-tile barriers; they meet only for list trims and for the
+// publish rounds (half-octave spacing) that share per-slab bounds of the running K'-th best across CTAs.
 #include "tensor_path.h"
 
 #include <cuda_bf16.h>
@@ -47,9 +49,17 @@ constexpr int BM = 128;        // corpus rows per tile  (UMMA M)
 constexpr int BN = 256;        // queries per tile      (UMMA N)
 constexpr int BK = 64;         // bf16 elements per stage = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int STAGES = 4;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-constexpr int B_STAGE_BYTES = BN * BK * 2;  // 32 KB
+// Per-CTA ring geometry.  PAIR = the two CTAs of a cluster drive ONE tcgen05.mma.cta_group::2 (UMMA M = 256:
+// each CTA supplies its own 128 corpus rows and HALF of the 256-query operand), which cuts the L2->SM operand
+// stream per FLOP by a third: 32 KB instead of 48 KB per 64-wide K step and 128x256 accumulator.
+template <bool PAIR>
+struct Ring {
+  static constexpr int kBRows = PAIR ? BN / 2 : BN;          // query rows this CTA stages per K step
+  static constexpr int kBStage = kBRows * BK * 2;            // 16 KB / 32 KB
+  static constexpr int kStages = PAIR ? 6 : 4;               // 192 KB either way
+  static constexpr int kBytes = kStages * (A_STAGE_BYTES + kBStage);
+};
 constexpr int TC_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 constexpr int EPI_THREADS = 256;
 constexpr uint32_t TMEM_COLS = 512;
@@ -62,9 +72,11 @@ struct TensorParams {
   uint32_t kprime;           // K' kept per (CTA, query) after a shrink
   uint32_t cap;              // candidate buffer capacity per (CTA, query): pow2 >= K' + 128
   Cand *ws;                  // [nq_tiles][slabs][BN][cap]
+  uint32_t *ws_ord;          // same shape, scores only: what the publish rounds scan (coalesced 16-byte loads)
   uint32_t *ws_cnt;          // [nq_tiles][slabs][BN]
   uint32_t *gthr;            // [nq_tiles*BN] shared running thresholds (ord), initialised to 0xffffffff
-  uint32_t *gsl;             // [nq_tiles*BN][slabs] per-slab upper bounds of the local j-th best score (ord)
+  uint32_t *gsl;             // [nq_tiles*BN][gsl_stride] per-slab upper bounds of the local j-th best score (ord)
+  uint32_t gsl_stride;       // row stride of gsl: slabs rounded up to 4 (16-byte loads)
   uint32_t jrank;            // j = ceil(K'/slabs): slabs*j >= K' rows are <= max_s gsl[q][s]
   int metric_l2;
 };
@@ -78,11 +90,60 @@ __device__ __forceinline__ void tma_load_2d_bf16(void *smem_dst, const CUtensorM
       "l"(tm), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
       : "memory");
 }
+// cta_group::2 form: issued by BOTH CTAs of the pair for their own smem; the mbarrier address has the peer bit
+// (24) cleared so the transaction bytes land on the leader CTA's barrier (cute SM100_TMA_2SM_LOAD_2D).
+__device__ __forceinline__ void tma_load_2d_bf16_pair(void *smem_dst, const CUtensorMap *tm, int32_t c0, int32_t c1,
+                                                      uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], "
+      "[%2];" ::"r"(smem_u32(smem_dst)),
+      "l"(tm), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t *bar, uint32_t rank) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(rank)
+      : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_commit(uint64_t *bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+// commit of cta_group::2 MMAs: one arrive on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void tc_commit_pair(uint64_t *bar, uint16_t mask) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"(mask)
+      : "memory");
+}
+// pair form: M = 256 (128 rows from each CTA's A tile), N = 256 (128 query rows from each CTA's B tile); each CTA
+// receives its own 128 x 256 accumulator at the same TMEM address.  Issued by the leader CTA only.
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 inputs, fp32 accumulate, M=128 N=256 K=16
 __device__ __forceinline__ void tc_mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
@@ -103,7 +164,9 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
          (2ull << 61);
 }
 // cute::UMMA::InstrDescriptor: c=F32 (1<<4), a=BF16 (1<<7), b=BF16 (1<<10), K-major both, N>>3 @17, M>>4 @24
-constexpr uint32_t kIdescBf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t idesc_bf16(uint32_t m, uint32_t n) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((m >> 4) << 24);
+}
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -119,12 +182,35 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// Per-tile timeline of one CTA (build with -DVKGPU_TENSOR_TRACE, run with VKGPU_TENSOR_TRACE=1): globaltimer
+// stamps of the MMA issuer and of epilogue warp 4, appends per tile.  This is how the epilogue was tuned: the
+// rounds of L2 round trips, not the gate arithmetic, were what stalled the accumulator hand-off.
+#ifdef VKGPU_TENSOR_TRACE
+__device__ unsigned long long g_trace[6][4096];
+__device__ unsigned int g_apt[4096];
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define VK_TRACE(row, t, on) \
+  do {                       \
+    if ((on) && blockIdx.x == 5 && (t) < 4096) g_trace[row][t] = gtime(); \
+  } while (0)
+#else
+#define VK_TRACE(row, t, on) \
+  do {                       \
+  } while (0)
+#endif
 // ---------------------------------------------------------------- the candidate kernel
+template <bool PAIR>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     flat_tensor_kernel(const TensorParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
+  constexpr int STAGES = Ring<PAIR>::kStages;
+  constexpr int B_STAGE_BYTES = Ring<PAIR>::kBStage;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *sA = smem;                                   // [STAGES][16 KB]
-  uint8_t *sB = smem + STAGES * A_STAGE_BYTES;          // [STAGES][32 KB]
+  uint8_t *sB = smem + STAGES * A_STAGE_BYTES;          // [STAGES][32 KB | 16 KB]
   uint8_t *tail = sB + STAGES * B_STAGE_BYTES;
   Cand *scratch = reinterpret_cast<Cand *>(tail);       // [4 warps][kprime]  shrink compaction buffers
   uint8_t *ctl = tail + (size_t)4 * p.kprime * sizeof(Cand);
@@ -136,10 +222,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   float *thrf = reinterpret_cast<float *>(tmem_slot + 4);          // [BN] float thresholds (gate)
   uint32_t *cnt = reinterpret_cast<uint32_t *>(thrf + BN);         // [BN]
   uint32_t *need = cnt + BN;                                       // [8] per-owner-warp shrink flags
+  uint32_t *sync_tile = need + 8;                                  // tile index of the next trim rendezvous
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const uint32_t qtile = blockIdx.x % p.nq_tiles, slab = blockIdx.x / p.nq_tiles;
-  const uint32_t total_tiles = (uint32_t)((p.n_rows + BM - 1) / BM);
+  // PAIR: cluster = (query tile, pair slab); CTA `rank` of the pair owns corpus tiles 2T + rank, i.e. it is
+  // CTA-level slab 2*pslab + rank of p.slabs = 2*pslabs, and both CTAs walk the same number of super-tiles T.
+  const uint32_t rank = PAIR ? cluster_ctarank() : 0;
+  const uint32_t unit = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+  const uint32_t qtile = unit % p.nq_tiles;
+  const uint32_t slab = PAIR ? 2 * (unit / p.nq_tiles) + rank : unit / p.nq_tiles;
+  const uint32_t total_tiles = PAIR ? ((uint32_t)((p.n_rows + BM - 1) / BM) + 1) & ~1u : (uint32_t)((p.n_rows + BM - 1) / BM);
+  constexpr uint32_t kTemptyArrivals = (PAIR ? 2 : 1) * (EPI_THREADS / 32);  // one arrive per epilogue warp
 
   if (tid == 0) {
     for (int s = 0; s < STAGES; s++) {
@@ -148,7 +241,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(&tfull[a], 1);
-      mbar_init(&tempty[a], EPI_THREADS);
+      mbar_init(&tempty[a], kTemptyArrivals);
     }
     fence_mbar_init();
   }
@@ -157,14 +250,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     cnt[i] = 0;
   }
   if (tid < 8) need[tid] = 0;
+  if (tid == 8) *sync_tile = 0xffffffffu;
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {  // warp 2 of BOTH CTAs, same smem slot (cute::TMEM::Allocator2Sm)
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                   "r"(TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -174,10 +276,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       uint32_t stage = 0, phase = 0;
       for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs) {
         for (uint32_t kb = 0; kb < p.kchunks; kb++) {
-          mbar_wait(&empty[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
-          tma_load_2d_bf16(sA + stage * A_STAGE_BYTES, &tmA, (int32_t)(kb * BK), (int32_t)(tile * BM), &full[stage]);
-          tma_load_2d_bf16(sB + stage * B_STAGE_BYTES, &tmB, (int32_t)(kb * BK), (int32_t)(qtile * BN), &full[stage]);
+          mbar_wait_parked(&empty[stage], phase ^ 1);
+          if constexpr (PAIR) {
+            // the leader's barrier collects the bytes of both CTAs (A 16 KB + B 16 KB each)
+            if (rank == 0) mbar_arrive_expect_tx(&full[stage], 2 * (A_STAGE_BYTES + B_STAGE_BYTES));
+            tma_load_2d_bf16_pair(sA + stage * A_STAGE_BYTES, &tmA, (int32_t)(kb * BK), (int32_t)(tile * BM), &full[stage]);
+            tma_load_2d_bf16_pair(sB + stage * B_STAGE_BYTES, &tmB, (int32_t)(kb * BK),
+                                  (int32_t)(qtile * BN + rank * (BN / 2)), &full[stage]);
+          } else {
+            mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
+            tma_load_2d_bf16(sA + stage * A_STAGE_BYTES, &tmA, (int32_t)(kb * BK), (int32_t)(tile * BM), &full[stage]);
+            tma_load_2d_bf16(sB + stage * B_STAGE_BYTES, &tmB, (int32_t)(kb * BK), (int32_t)(qtile * BN), &full[stage]);
+          }
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
@@ -187,30 +297,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
+    if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0, t = 0;
       for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
         const uint32_t a = t & 1;
-        mbar_wait(&tempty[a], ((t >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
+        VK_TRACE(4, t, true);
+        mbar_wait_parked(&tempty[a], ((t >> 1) & 1) ^ 1);  // epilogue (of both CTAs) has drained this accumulator
         tc_fence_after();
+        VK_TRACE(0, t, true);
         const uint32_t tmem_d = tmem_base + a * BN;
         for (uint32_t kb = 0; kb < p.kchunks; kb++) {
-          mbar_wait(&full[stage], phase);
+          mbar_wait_parked(&full[stage], phase);
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; k++) {
-            tc_mma_bf16(tmem_d, make_sw128_desc(a_addr + k * UMMA_K * 2), make_sw128_desc(b_addr + k * UMMA_K * 2),
-                        kIdescBf16, (kb | (uint32_t)k) != 0 ? 1u : 0u);
+            if constexpr (PAIR)
+              tc_mma_bf16_pair(tmem_d, make_sw128_desc(a_addr + k * UMMA_K * 2), make_sw128_desc(b_addr + k * UMMA_K * 2),
+                               idesc_bf16(2 * BM, BN), (kb | (uint32_t)k) != 0 ? 1u : 0u);
+            else
+              tc_mma_bf16(tmem_d, make_sw128_desc(a_addr + k * UMMA_K * 2), make_sw128_desc(b_addr + k * UMMA_K * 2),
+                          idesc_bf16(BM, BN), (kb | (uint32_t)k) != 0 ? 1u : 0u);
           }
-          tc_commit(&empty[stage]);  // smem slot reusable once these MMAs have read it
+          // smem slot reusable (in both CTAs) once these MMAs have read it
+          if constexpr (PAIR) tc_commit_pair(&empty[stage], 3); else tc_commit(&empty[stage]);
           if (++stage == STAGES) {
             stage = 0;
             phase ^= 1;
           }
         }
-        tc_commit(&tfull[a]);  // accumulator complete
+        if constexpr (PAIR) tc_commit_pair(&tfull[a], 3); else tc_commit(&tfull[a]);  // accumulator complete
+        VK_TRACE(1, t, true);
       }
     }
   } else if (warp >= 4) {
@@ -222,9 +340,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     const uint32_t col_lo = ((warp - 4) >> 2) * (BN / 2);
     const bool owner_warp = warp < 8;
     Cand *my_ws = p.ws + ((size_t)qtile * p.slabs + slab) * BN * p.cap;
+    uint32_t *my_ord = p.ws_ord + ((size_t)qtile * p.slabs + slab) * BN * p.cap;
     // One warp trims query c's candidate list to the K' best: radix-select the K'-th smallest score with the
     // list's keys held 32 per lane in registers (32 bit-rounds of count + shuffle-reduce), then compact the
     // survivors through a per-warp shared-memory buffer.
+    uint32_t t = 0;  // tiles this CTA has processed (captured by the lambdas below)
     auto warp_shrink = [&](uint32_t c) {
       const uint32_t n = cnt[c];
       Cand *wscr = scratch + (size_t)(warp & 3) * p.kprime;
@@ -262,7 +382,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         base += __popc(kb);
       }
       __syncwarp();
-      for (uint32_t i = lane; i < p.kprime; i += 32) buf[i] = wscr[i];
+      for (uint32_t i = lane; i < p.kprime; i += 32) {
+        buf[i] = wscr[i];
+        my_ord[(size_t)c * p.cap + i] = wscr[i].ord;
+      }
       if (lane == 0) {
         cnt[c] = p.kprime;
         thrf[c] = fminf(thrf[c], ord_to_f32(T));
@@ -285,33 +408,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     };
     auto tmem_wait = [] { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); };
 
-    // Cheap upper bound of the j-th smallest score in query c's list: every lane takes the minimum of its
-    // strided share, the j-th smallest of the 32 lane minima bounds the j-th smallest overall from above.
-    // Published per slab; max over slabs bounds the GLOBAL K'-th best (slabs * j >= K'), so all CTAs gate on a
-    // threshold that tightens with the whole corpus seen so far, not just their own slab.
-    auto warp_publish = [&](uint32_t c) {
+    // Cheap upper bound of the j-th smallest score in a query's list: take the list's most recent <= 64 entries
+    // (later entries passed tighter gates, so the slab's best rows are almost always among them; any subset still
+    // gives a valid bound), pair them up, and take the j-th smallest of the 32 pair minima: it bounds the j-th
+    // smallest of the whole list from above.  Published per slab; max over slabs bounds the GLOBAL K'-th best
+    // (slabs * j >= K'), so all CTAs gate on a threshold that tightens with the whole corpus seen so far.
+    // One THREAD per query (query c = warp-4 + 8*lane): sixteen independent 16-byte loads per lane, i.e. ONE L2
+    // round trip per round for the whole warp, then a register bitonic network.  L2 latency under the operand
+    // stream is ~2-4 us, which is why the earlier warp-per-query scans cost 35-110 us per round.
+    auto warp_publish_all = [&]() {
+      if (p.jrank > 32) return;
+      const uint32_t c = (warp - 4) + 8 * lane;
       const uint32_t n = min(cnt[c], p.cap);
-      if (n < p.jrank || p.jrank > 32) return;  // warp-uniform
-      const Cand *buf = my_ws + (size_t)c * p.cap;
-      uint32_t m = kOrdInf;
-      uint32_t idx = lane;
-      for (; idx + 96 < n; idx += 128) {  // 4 independent loads in flight
-        const uint32_t a0 = buf[idx].ord, a1 = buf[idx + 32].ord, a2 = buf[idx + 64].ord, a3 = buf[idx + 96].ord;
-        m = min(min(m, a0), min(min(a1, a2), a3));
-      }
-      for (; idx < n; idx += 32) m = min(m, buf[idx].ord);
-      uint32_t rank = 0;
+      const uint32_t first = n > 64 ? (n - 61) & ~3u : 0u;  // 16-byte aligned window of <= 64 entries ending at n
+      const uint32_t *src = my_ord + (size_t)c * p.cap + first;
+      uint32_t g[32];
 #pragma unroll
-      for (int l = 0; l < 32; l++) {
-        const uint32_t ml = __shfl_sync(0xffffffffu, m, l);
-        rank += (ml < m || (ml == m && (uint32_t)l < lane)) ? 1u : 0u;
+      for (int i = 0; i < 16; i++) {
+        const uint32_t idx = first + 4 * i;
+        uint4 v = make_uint4(kOrdInf, kOrdInf, kOrdInf, kOrdInf);
+        if (idx < n) v = __ldcg(reinterpret_cast<const uint4 *>(src + 4 * i));
+        g[2 * i] = min(idx < n ? v.x : kOrdInf, idx + 1 < n ? v.y : kOrdInf);
+        g[2 * i + 1] = min(idx + 2 < n ? v.z : kOrdInf, idx + 3 < n ? v.w : kOrdInf);
       }
-      const uint32_t who = __ballot_sync(0xffffffffu, rank == p.jrank - 1);
-      const uint32_t est = __shfl_sync(0xffffffffu, m, __ffs(who) - 1);
-      if (lane == 0 && est != kOrdInf) {
-        uint32_t *dst = &p.gsl[((size_t)qtile * BN + c) * p.slabs + slab];
-        if (est < *dst) *reinterpret_cast<volatile uint32_t *>(dst) = est;
+      // bitonic sorting network, ascending (240 compare-exchanges on registers)
+#pragma unroll
+      for (int ks = 1; ks <= 5; ks++) {
+#pragma unroll
+        for (int js = 4; js >= 0; js--) {
+          if (js >= ks) continue;
+          const int k = 1 << ks, j = 1 << js;
+#pragma unroll
+          for (int i = 0; i < 32; i++) {
+            const int l = i ^ j;
+            if (l > i) {
+              const uint32_t lo = min(g[i], g[l]), hi = max(g[i], g[l]);
+              const bool up = (i & k) == 0;
+              g[i] = up ? lo : hi;
+              g[l] = up ? hi : lo;
+            }
+          }
+        }
       }
+      uint32_t est = g[0];
+#pragma unroll
+      for (int i = 1; i < 32; i++) est = (uint32_t)i == p.jrank - 1 ? g[i] : est;
+      // fire-and-forget reduction (RED.MIN): a read-compare-write would cost another L2 round trip
+      if (n >= p.jrank && est != kOrdInf) atomicMin(&p.gsl[((size_t)qtile * BN + c) * p.gsl_stride + slab], est);
     };
 
     // Gate + append for 32 columns.  Fast path is branch-free: 32 scores against 32 thresholds -> a per-lane bit
@@ -335,63 +478,121 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         m |= (s3 <= th.w ? 1u : 0u) << (4 * j4 + 3);
       }
       if (!valid) m = 0;
-      uint32_t any = __reduce_or_sync(0xffffffffu, m);
-#pragma unroll 1
-      while (any) {  // warp-uniform
-        const uint32_t j = __ffs(any) - 1;
-        any &= any - 1;
-        uint32_t v;
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(v) : "r"(taddr + j) : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        const bool pass = (m >> j) & 1u;
-        const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+      if (!__any_sync(0xffffffffu, m != 0)) return;  // warp-uniform; the common case once thresholds are tight
+#ifdef VKGPU_TENSOR_TRACE
+      if (blockIdx.x == 5 && t < 4096 && m) atomicAdd(&g_apt[t], __popc(m));
+#endif
+      // Slow path, lane-parallel: every lane walks ITS OWN passing columns (usually one), picks the score out of
+      // the register tile with a 5-level select tree (no dynamic register indexing, no TMEM re-read), reserves a
+      // list position with one shared-memory atomic and stores the candidate.  Order inside a list is irrelevant.
+      while (m) {
+        const uint32_t j = __ffs(m) - 1;
+        m &= m - 1;
+        uint32_t s16[16], s8[8], s4[4];
+#pragma unroll
+        for (int i = 0; i < 16; i++) s16[i] = (j & 1u) ? r[2 * i + 1] : r[2 * i];
+#pragma unroll
+        for (int i = 0; i < 8; i++) s8[i] = (j & 2u) ? s16[2 * i + 1] : s16[2 * i];
+#pragma unroll
+        for (int i = 0; i < 4; i++) s4[i] = (j & 4u) ? s8[2 * i + 1] : s8[2 * i];
+        const uint32_t s2a = (j & 8u) ? s4[1] : s4[0], s2b = (j & 8u) ? s4[3] : s4[2];
+        const float dot = __uint_as_float((j & 16u) ? s2b : s2a);
         const uint32_t c = c0 + j;
-        const uint32_t npass = __popc(bal);
-        uint32_t base = 0;
-        if (lane == 0) {
-          base = atomicAdd(&cnt[c], npass);
-          if (base + npass + BM > p.cap) atomicOr(&need[(c & 3) * 2 + (c >> 7)], 1u << ((c >> 2) & 31));
+        const uint32_t base = atomicAdd(&cnt[c], 1u);
+        if (base + 1 + 2 * BM > p.cap) {  // ask for a trim at the rendezvous of tile t+2
+          atomicOr(&need[(c & 3) * 2 + (c >> 7)], 1u << ((c >> 2) & 31));
+          atomicMin(sync_tile, t + 2);
         }
-        base = __shfl_sync(0xffffffffu, base, 0);
-        if (pass) {
-          const float dot = __uint_as_float(v);
-          const float sc = p.metric_l2 ? __fmaf_rn(-2.0f, dot, xn) : -dot;
-          Cand cd;
-          cd.ord = f32_to_ord(sc);
-          cd.slot = (uint32_t)slot;
-          cd.label = slot;
-          my_ws[(size_t)c * p.cap + base + __popc(bal & ((1u << lane) - 1))] = cd;  // < cap by the shrink rule
-        }
+        const float sc = p.metric_l2 ? __fmaf_rn(-2.0f, dot, xn) : -dot;
+        Cand cd;
+        cd.ord = f32_to_ord(sc);
+        cd.slot = (uint32_t)slot;
+        cd.label = slot;
+        my_ws[(size_t)c * p.cap + base] = cd;  // base < cap: see the trim rendezvous in the tile loop
+        my_ord[(size_t)c * p.cap + base] = cd.ord;
       }
     };
 
-    uint32_t t = 0;
     for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
-      // every 8th tile early on, every 32nd later (and right after each publish round): refresh the gate thresholds from the running global ones (other slabs tighten them too).
-      // Query c belongs to epilogue warp c & 3 for refresh and shrink alike, so thrf[c]/cnt[c] have one writer.
-      if (owner_warp && ((t < 64 && (t & 7) == 0) || (t & 31) == 0 || ((t - 1) & t) == 0)) {
-        for (uint32_t c = (warp & 3) + 4 * lane; c < BN; c += 128) {
-          uint32_t go = __ldcg(&p.gthr[qtile * BN + c]);
-          const uint32_t *gs = p.gsl + ((size_t)qtile * BN + c) * p.slabs;
-          uint32_t mx = 0, sidx = 0;
-          for (; sidx + 4 <= p.slabs; sidx += 4) {  // L2 loads (other CTAs write these), 4 in flight
-            const uint32_t a0 = __ldcg(gs + sidx), a1 = __ldcg(gs + sidx + 1), a2 = __ldcg(gs + sidx + 2),
-                           a3 = __ldcg(gs + sidx + 3);
-            mx = max(max(mx, a0), max(max(a1, a2), a3));
+      // every 8th tile early on, every 32nd later (and right after each publish round): refresh the gate
+      // thresholds from the running global ones (other slabs tighten them too).  No barrier: thresholds only
+      // ever tighten, so a warp that still gates on the previous value merely keeps a few more candidates.
+      // thrf[c] is written here by warp 4 + (c & 7) and, inside a rendezvous, by the trimming owner 4 + (c & 3).
+      const uint32_t tp1 = t - 1, tp3 = tp1 / 3;  // a publish round ran before tile t-1: every slab has published by now
+      const bool after_pub = t > 1 && ((tp1 & (tp1 - 1)) == 0 || (tp3 * 3 == tp1 && (tp3 & (tp3 - 1)) == 0));
+      if ((after_pub || (t < 64 && (t & 7) == 0) || (t & 31) == 0)) {
+        // one thread per query (c = warp-4 + 8*lane): the per-slab bounds of a query are contiguous, the lane
+        // reads them with 16-byte loads, eight in flight, so a refresh is one or two L2 round trips per warp
+        const uint32_t my_c = (warp - 4) + 8 * lane;
+        const uint4 *gs = reinterpret_cast<const uint4 *>(p.gsl + ((size_t)qtile * BN + my_c) * p.gsl_stride);
+        uint32_t go = __ldcg(&p.gthr[qtile * BN + my_c]);
+        uint32_t mx = 0;
+        for (uint32_t s0 = 0; s0 < p.slabs; s0 += 32) {
+          uint4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            v[i] = make_uint4(0, 0, 0, 0);
+            if (s0 + 4 * i < p.slabs) v[i] = __ldcg(gs + (s0 >> 2) + i);
           }
-          for (; sidx < p.slabs; sidx++) mx = max(mx, __ldcg(gs + sidx));
-          go = min(go, mx);
-          if (go != kOrdInf) thrf[c] = fminf(thrf[c], ord_to_f32(go));
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const uint32_t sb = s0 + 4 * i;  // entries past p.slabs are padding
+            mx = max(mx, max(max(sb < p.slabs ? v[i].x : 0u, sb + 1 < p.slabs ? v[i].y : 0u),
+                             max(sb + 2 < p.slabs ? v[i].z : 0u, sb + 3 < p.slabs ? v[i].w : 0u)));
+          }
         }
+        go = min(go, mx);
+        if (go != kOrdInf) thrf[my_c] = fminf(thrf[my_c], ord_to_f32(go));
       }
-      named_bar_sync(2, EPI_THREADS);  // thresholds + previous tile's shrinks visible before any append
 
       const uint32_t a = t & 1;
       const uint64_t slot = (uint64_t)tile * BM + et;
       const bool valid = slot < p.n_rows;
       const float xn = (valid && p.metric_l2) ? p.xnorm[slot] : 0.0f;
-      mbar_wait(&tfull[a], (t >> 1) & 1);
+      mbar_wait_parked(&tfull[a], (t >> 1) & 1);
       tc_fence_after();
+      VK_TRACE(2, t, tid == 128);
+
+      // ---- rendezvous of the eight epilogue warps, only when needed.  The warps run the tile loop without
+      // per-tile barriers; the accumulator hand-off bounds their drift: tfull(t) fires only after EVERY warp has
+      // released tile t-2, so whatever was written to shared memory while gating tile t-2 is visible here to
+      // all of them and the decision below is uniform.
+      //  * trim: an append that left fewer than 2*BM free entries in a list (while gating tile t-2) set
+      //    *sync_tile = t; the list can have grown by at most the rest of tile t-2 plus tile t-1 since (<= 2*BM).
+      //  * publish rounds before tiles t = 2^i and 3*2^(i-1) (half-octave spacing): the global K'-th best moves
+      //    like 1/t, so denser rounds late in the scan cost more list scans than the appends they save.
+      {
+        const bool do_trim = *reinterpret_cast<volatile uint32_t *>(sync_tile) <= t;
+        const uint32_t t3 = t / 3;
+        const bool do_pub = t > 0 && ((t & (t - 1)) == 0 || (t3 * 3 == t && (t3 & (t3 - 1)) == 0));
+        if (do_trim || do_pub) {
+          named_bar_sync(2, EPI_THREADS);  // every warp has finished tile t-1: no append is in flight
+          if (do_trim) {
+            if (owner_warp) {
+              const uint32_t w = warp & 3;
+#pragma unroll
+              for (int h = 0; h < 2; h++) {
+                uint32_t bits = need[w * 2 + h];
+                if (bits == 0) continue;
+                if (lane == 0) need[w * 2 + h] = 0;
+                __syncwarp();
+                while (bits) {
+                  const uint32_t i = __ffs(bits) - 1;
+                  bits &= bits - 1;
+                  const uint32_t c = ((h * 32 + i) << 2) | w;
+                  if (cnt[c] + 2 * BM > p.cap) warp_shrink(c);
+                }
+              }
+            }
+            if (tid == 128) *sync_tile = 0xffffffffu;
+            named_bar_sync(2, EPI_THREADS);  // trimmed lists before anyone publishes from them
+          }
+          if (do_pub) warp_publish_all();
+          named_bar_sync(2, EPI_THREADS);
+        }
+      }
+
+      VK_TRACE(5, t, tid == 128);
       const uint32_t tbase = tmem_base + (lane_base << 16) + a * BN;
       uint32_t ra[32];
 #pragma unroll 1
@@ -401,30 +602,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         gate_chunk(ra, tbase + c0, c0, xn, valid, slot);
       }
       tc_fence_before();
-      mbar_arrive(&tempty[a]);  // accumulator may be overwritten
-
-      // ---- keep room for one more tile (<= BM appends per query per tile): the warp that owns a query trims
-      //      it when an append pushed it past cap - BM (flagged in `need` by the appender)
-      named_bar_sync(2, EPI_THREADS);
-      if (owner_warp) {
-        const uint32_t w = warp & 3;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          uint32_t bits = need[w * 2 + h];
-          if (bits == 0) continue;
-          if (lane == 0) need[w * 2 + h] = 0;
-          __syncwarp();
-          while (bits) {
-            const uint32_t i = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const uint32_t c = ((h * 32 + i) << 2) | w;
-            if (cnt[c] + BM > p.cap) warp_shrink(c);
-          }
-        }
-        // publish rounds at tiles 1,2,4,8,... and every 128th: bounds tighten while lists are still short
-        if (((t + 1) & t) == 0 || (t & 127) == 127)
-          for (uint32_t c = w; c < BN; c += 4) warp_publish(c);
+      __syncwarp();
+      if (lane == 0) {  // accumulator may be overwritten: the issuer lives in the leader CTA
+        if constexpr (PAIR) mbar_arrive_cluster(&tempty[a], 0); else mbar_arrive(&tempty[a]);
       }
+      VK_TRACE(3, t, tid == 128);
     }
     // final trim so the merge kernel reads at most K' entries per list
     named_bar_sync(2, EPI_THREADS);
@@ -438,9 +620,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's smem and write its TMEM
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(TMEM_COLS) : "memory");
   }
 }
 
@@ -599,7 +785,8 @@ void tensor_prepare(vkgpu_index_impl *ix) {
   ix->dNorm.reserve(rows * 4);
   tensor_refresh_rows(ix, 0, ix->n);
   VK_CUDA(cudaStreamSynchronize(ix->mut_stream));
-  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
   VK_CUDA(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   VK_CUDA(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   ix->tensor_ready = true;
@@ -632,8 +819,23 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   const uint32_t kprime = (3 * k_eff + 64 + 127) / 128 * 128;  // survivors per query (k + margin)
   const uint32_t cap = 1024;  // 32 keys per lane in the warp-level shrink
   const uint32_t total_tiles = (uint32_t)((ix->n + BM - 1) / BM);
-  uint32_t slabs = std::max<uint32_t>(1, ix->num_sms / nq_tiles);
-  slabs = std::min(slabs, total_tiles);
+  // CTA pairs (tcgen05 cta_group::2) only with VKGPU_TENSOR_PAIR=1: measured on B200 (10M x 768, batch 1024) the
+  // pair kernel is 5-8 % SLOWER than the single-CTA one (144 instead of 148 CTAs at four query tiles, and the
+  // epilogue's TMEM reads take longer), and the operand stream it saves is not what bounds this kernel — the
+  // MMA issue loop with NO operand loads at all already needs 9.5 ms of the 13.4 ms.
+  const bool pair_env = [] {
+    const char *e = getenv("VKGPU_TENSOR_PAIR");
+    return e && e[0] == '1';
+  }();
+  const bool pair = pair_env && total_tiles >= 2 && ix->num_sms / 2 >= nq_tiles;
+  uint32_t slabs;  // CTA-level corpus slabs per query tile
+  if (pair) {
+    const uint32_t pslabs = std::min<uint32_t>(std::max<uint32_t>(1, (ix->num_sms / 2) / nq_tiles), (total_tiles + 1) / 2);
+    slabs = 2 * pslabs;
+  } else {
+    slabs = std::max<uint32_t>(1, ix->num_sms / nq_tiles);
+    slabs = std::min(slabs, total_tiles);
+  }
 
   // bf16 queries [Bpad][Dh] + squared norms
   c->scratch0.reserve((size_t)Bpad * Dh * 2);
@@ -645,18 +847,19 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   VK_CUDA(cudaGetLastError());
 
   const size_t nlists = (size_t)nq_tiles * slabs * BN;
-  c->ws.reserve(nlists * cap * sizeof(Cand));
+  c->ws.reserve(nlists * cap * (sizeof(Cand) + 4));
   c->ws_cnt.reserve(nlists * 4);
-  c->scratch2.reserve((size_t)Bpad * 4 + (size_t)B * 4 + (size_t)Bpad * slabs * 4);  // gthr [Bpad] + flags [B] + gsl
+  const uint32_t gsl_stride = (slabs + 3) & ~3u, flags_pad = (B + 3) & ~3u;
+  c->scratch2.reserve(((size_t)Bpad + flags_pad + (size_t)Bpad * gsl_stride) * 4);  // gthr [Bpad] + flags [B] + gsl
   VK_CUDA(cudaMemsetAsync(c->scratch2.p, 0xff, (size_t)Bpad * 4, s));
-  uint32_t *d_gsl = c->scratch2.as<uint32_t>() + Bpad + B;
-  VK_CUDA(cudaMemsetAsync(d_gsl, 0xff, (size_t)Bpad * slabs * 4, s));
+  uint32_t *d_gsl = c->scratch2.as<uint32_t>() + Bpad + flags_pad;
+  VK_CUDA(cudaMemsetAsync(d_gsl, 0xff, (size_t)Bpad * gsl_stride * 4, s));
 
   CUtensorMap tmA, tmB;
   make_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ix->dXh.p, Dh, ix->n, (uint64_t)Dh * 2, BK, BM,
                      CU_TENSOR_MAP_SWIZZLE_128B);
-  make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->scratch0.p, Dh, Bpad, (uint64_t)Dh * 2, BK, BN,
-                     CU_TENSOR_MAP_SWIZZLE_128B);
+  make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->scratch0.p, Dh, Bpad, (uint64_t)Dh * 2, BK,
+                     pair ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B);
 
   TensorParams tp{};
   tp.xnorm = ix->dNorm.as<float>();
@@ -667,17 +870,65 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   tp.kprime = kprime;
   tp.cap = cap;
   tp.ws = c->ws.as<Cand>();
+  tp.ws_ord = reinterpret_cast<uint32_t *>(c->ws.as<Cand>() + nlists * cap);
   tp.ws_cnt = c->ws_cnt.as<uint32_t>();
   tp.gthr = c->scratch2.as<uint32_t>();
   tp.gsl = d_gsl;
+  tp.gsl_stride = gsl_stride;
   tp.jrank = (kprime + slabs - 1) / slabs;
   tp.metric_l2 = ix->metric_l2 ? 1 : 0;
-  const size_t smem = (size_t)STAGES * (A_STAGE_BYTES + B_STAGE_BYTES) + (size_t)4 * kprime * sizeof(Cand) + 256 + BN * 8 + 64;
+  static_assert(Ring<true>::kBytes == Ring<false>::kBytes, "both ring geometries use the same shared memory");
+  const size_t smem = (size_t)Ring<true>::kBytes + (size_t)4 * kprime * sizeof(Cand) + 256 + BN * 8 + 64;
   VK_REQUIRE(smem <= ix->smem_max, VKGPU_ERR_INTERNAL, "tensor kernel shared memory budget exceeded");
   ix->prof_begin(c, KK_TENSOR);
-  flat_tensor_kernel<<<nq_tiles * slabs, TC_THREADS, smem, s>>>(tp, tmA, tmB);
+  if (pair) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(nq_tiles * slabs);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    VK_CUDA(cudaLaunchKernelEx(&cfg, flat_tensor_kernel<true>, tp, tmA, tmB));
+  } else {
+    flat_tensor_kernel<false><<<nq_tiles * slabs, TC_THREADS, smem, s>>>(tp, tmA, tmB);
+  }
   VK_CUDA(cudaGetLastError());
   ix->prof_end(c, KK_TENSOR);
+#ifdef VKGPU_TENSOR_TRACE
+  if (getenv("VKGPU_TENSOR_TRACE")) {
+    static unsigned long long h[6][4096];
+    VK_CUDA(cudaStreamSynchronize(s));
+    VK_CUDA(cudaMemcpyFromSymbol(h, g_trace, sizeof(h)));
+    const uint32_t T = std::min<uint32_t>(4096, (total_tiles + slabs - 1) / slabs) - 1;
+    double mma_issue = 0, mma_wait = 0, epi_wait = 0, epi_rdv = 0, epi_gate = 0, lag = 0;
+    for (uint32_t t = 2; t < T; t++) {
+      mma_issue += (double)(h[1][t] - h[0][t]);
+      mma_wait += (double)(h[0][t] - h[4][t]);
+      epi_wait += (double)(h[2][t] - h[3][t - 1]);
+      epi_rdv += (double)(h[5][t] - h[2][t]);
+      epi_gate += (double)(h[3][t] - h[5][t]);
+      lag += (double)(h[2][t] - h[1][t]);
+    }
+    const double n = T - 2;
+    fprintf(stderr, "[trace] tiles=%u total=%.1f us | per tile ns: mma_issue=%.0f mma_wait_tempty=%.0f | epi wait_tfull=%.0f rendezvous=%.0f gate=%.0f | tfull-after-last-commit=%.0f\n",
+            T, (h[3][T - 1] - h[4][0]) / 1e3, mma_issue / n, mma_wait / n, epi_wait / n, epi_rdv / n, epi_gate / n, lag / n);
+    static unsigned int apt[4096];
+    VK_CUDA(cudaMemcpyFromSymbol(apt, g_apt, sizeof(apt)));
+    for (uint32_t t : {0u, 1u, 2u, 3u, 4u, 5u, 6u, 7u, 8u, 9u, 12u, 16u, 17u, 24u, 32u, 33u, 64u, 100u, 500u, 1000u, 1024u, 1025u, 2000u})
+      if (t < T)
+        fprintf(stderr, "  t=%u mma[start-wait %lld, issue %lld] epi[tfull@%lld rdv %lld gate %lld] appends=%u\n", t,
+                (long long)(h[0][t] - h[4][t]), (long long)(h[1][t] - h[0][t]), (long long)(h[2][t] - h[4][0]),
+                (long long)(h[5][t] - h[2][t]), (long long)(h[3][t] - h[5][t]), apt[t]);
+    memset(apt, 0, sizeof(apt));
+    VK_CUDA(cudaMemcpyToSymbol(g_apt, apt, sizeof(apt)));
+  }
+#endif
 
   // per-query top-K' by approximate score
   c->scratch3.reserve((size_t)B * kprime * (4 + 8 + 4) + (size_t)B * 4);
