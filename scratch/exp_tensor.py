@@ -1,11 +1,11 @@
-"""Throwaway: time the tensor candidate kernel under experiment flags (results are wrong under flags)."""
+"""Throwaway: time the tensor candidate kernel (env toggles per run)."""
 import ctypes as C, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
 import valkey_search_b200 as V
 from valkey_search_b200 import _lib as L
-N = int(os.environ.get("EXP_ROWS", 10_000_000)); D = 768; B = 1024; k = 100
+N = int(os.environ.get("EXP_ROWS", 10_000_000)); D = 768; B = int(os.environ.get("EXP_B", 1024)); k = 100
 dev = torch.device("cuda", 0); torch.cuda.set_device(dev)
 lib = L.lib()
 ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
@@ -32,7 +32,6 @@ def run(tag, env):
     torch.cuda.synchronize()
     tm = L.Timings(); L.check(lib.vkgpu_get_timings(ix.handle(), C.byref(tm)))
     L.check(lib.vkgpu_set_profiling(ix.handle(), 0))
-    print(tag, env, "ms per kind:", [round(tm.ms[i] / max(int(tm.launches[i]), 1), 3) for i in range(8)], flush=True)
+    print(tag, "ms per kind:", [round(tm.ms[i] / max(int(tm.launches[i]), 1), 3) for i in range(5)], flush=True)
 for spec in sys.argv[1:]:
-    pair, dbg = spec.split(":")
-    run(spec, {"VKGPU_TENSOR_PAIR": pair, "VKGPU_TENSOR_DEBUG": dbg})
+    run(spec, {"VKGPU_TENSOR_PAIR": spec})

@@ -408,10 +408,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     };
     auto tmem_wait = [] { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); };
 
-    // Cheap upper bound of the j-th smallest score in a query's list: take the list's most recent <= 64 entries
+    // Cheap upper bound of the j-th smallest score in a query's list: take the list's most recent entries
     // (later entries passed tighter gates, so the slab's best rows are almost always among them; any subset still
-    // gives a valid bound), pair them up, and take the j-th smallest of the 32 pair minima: it bounds the j-th
-    // smallest of the whole list from above.  Published per slab; max over slabs bounds the GLOBAL K'-th best
+    // gives a valid bound), deal them into 32 groups, and take the j-th smallest of the 32 group minima: it
+    // bounds the j-th smallest of the whole list from above.  Published per slab; max over slabs bounds the GLOBAL K'-th best
     // (slabs * j >= K'), so all CTAs gate on a threshold that tightens with the whole corpus seen so far.
     // One THREAD per query (query c = warp-4 + 8*lane): sixteen independent 16-byte loads per lane, i.e. ONE L2
     // round trip per round for the whole warp, then a register bitonic network.  L2 latency under the operand
@@ -420,16 +420,23 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       if (p.jrank > 32) return;
       const uint32_t c = (warp - 4) + 8 * lane;
       const uint32_t n = min(cnt[c], p.cap);
-      const uint32_t first = n > 64 ? (n - 61) & ~3u : 0u;  // 16-byte aligned window of <= 64 entries ending at n
-      const uint32_t *src = my_ord + (size_t)c * p.cap + first;
+      // window: the last <= 64 entries; during the first tiles (gates still open, lists mostly unfiltered rows)
+      // the last <= 256 in four passes, so that the very first bounds already sit near the slab's true j-th best
+      const uint32_t win = t <= 16 ? 256u : 64u;
+      const uint32_t first = n > win ? (n - win + 3) & ~3u : 0u;  // 16-byte aligned
+      const uint32_t *src = my_ord + (size_t)c * p.cap;
       uint32_t g[32];
 #pragma unroll
-      for (int i = 0; i < 16; i++) {
-        const uint32_t idx = first + 4 * i;
-        uint4 v = make_uint4(kOrdInf, kOrdInf, kOrdInf, kOrdInf);
-        if (idx < n) v = __ldcg(reinterpret_cast<const uint4 *>(src + 4 * i));
-        g[2 * i] = min(idx < n ? v.x : kOrdInf, idx + 1 < n ? v.y : kOrdInf);
-        g[2 * i + 1] = min(idx + 2 < n ? v.z : kOrdInf, idx + 3 < n ? v.w : kOrdInf);
+      for (int i = 0; i < 32; i++) g[i] = kOrdInf;
+      for (uint32_t w0 = first; w0 < n; w0 += 64) {
+#pragma unroll
+        for (int i = 0; i < 16; i++) {
+          const uint32_t idx = w0 + 4 * i;
+          uint4 v = make_uint4(kOrdInf, kOrdInf, kOrdInf, kOrdInf);
+          if (idx < n) v = __ldcg(reinterpret_cast<const uint4 *>(src + idx));
+          g[2 * i] = min(g[2 * i], min(idx < n ? v.x : kOrdInf, idx + 1 < n ? v.y : kOrdInf));
+          g[2 * i + 1] = min(g[2 * i + 1], min(idx + 2 < n ? v.z : kOrdInf, idx + 3 < n ? v.w : kOrdInf));
+        }
       }
       // bitonic sorting network, ascending (240 compare-exchanges on registers)
 #pragma unroll
@@ -608,14 +615,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       VK_TRACE(3, t, tid == 128);
     }
-    // final trim so the merge kernel reads at most K' entries per list
-    named_bar_sync(2, EPI_THREADS);
-    if (owner_warp)
-      for (uint32_t c = warp & 3; c < BN; c += 4)
-        if (cnt[c] > p.kprime) warp_shrink(c);
+    // No final trim: the merge is selection based (topk_select_merge_kernel) and takes lists of any length up to
+    // cap; trimming ~450-entry lists to K' here used to cost 0.7 ms per launch for nothing.
     named_bar_sync(2, EPI_THREADS);
     for (uint32_t c = tid - 128; c < BN; c += EPI_THREADS)
-      p.ws_cnt[((size_t)qtile * p.slabs + slab) * BN + c] = cnt[c];
+      p.ws_cnt[((size_t)qtile * p.slabs + slab) * BN + c] = min(cnt[c], p.cap);
   }
 
   tc_fence_before();
