@@ -160,7 +160,7 @@ def hnsw_workload(args):
     from valkey_search_b200 import _lib as L
     import oracle_lib as O
 
-    N = args.rows if args.rows != 10_000_000 else 1_000_000
+    N = args.rows if args.rows is not None else 1_000_000
     D, k, ef, M, efc = args.dim, (10 if args.k == 100 else args.k), args.ef, 16, 200
     B = 512 if args.batch == 1024 else args.batch
     dev = torch.device("cuda", 0)
@@ -170,18 +170,32 @@ def hnsw_workload(args):
     g = torch.Generator(device=dev)
     g.manual_seed(777)
     centres = torch.randn((1024, D), generator=g, device=dev) * 1.0
-    assign = torch.randint(0, 1024, (N,), generator=g, device=dev)
-    X = centres[assign] + 0.3 * torch.randn((N, D), generator=g, device=dev)
     qa = torch.randint(0, 1024, (B,), generator=g, device=dev)
     dQ = (centres[qa] + 0.3 * torch.randn((B, D), generator=g, device=dev)).contiguous()
-    torch.cuda.synchronize()
+
+    def gen_rows(blk, rows):  # 1M-row blocks, seed 777 + 1 + block: the 10M corpus never exists twice in HBM
+        gb = torch.Generator(device=dev)
+        gb.manual_seed(778 + blk)
+        assign = torch.randint(0, 1024, (rows,), generator=gb, device=dev)
+        return (centres[assign] + 0.3 * torch.randn((rows, D), generator=gb, device=dev)).contiguous()
+
+    BLK = 1_000_000
+    nblk = (N + BLK - 1) // BLK
     ix = V.VectorHNSW(D, V.DistanceMetric.L2, initial_cap=N, m=M, ef_construction=efc, ef_runtime=ef, max_batch=B)
-    t0 = time.perf_counter()
-    L.check(lib.vkgpu_add_batch_device(ix.handle(), None, X.data_ptr(), N))
-    build_s = time.perf_counter() - t0
-    log(f"[hnsw] GPU build of {N} x {D}: {build_s:.1f}s ({N / build_s:.0f} inserts/s)")
     flat = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
-    L.check(lib.vkgpu_add_batch_device(flat.handle(), None, X.data_ptr(), N))
+    build_s = 0.0
+    X = None
+    for blk in range(nblk):
+        Xb = gen_rows(blk, min(BLK, N - blk * BLK))
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        L.check(lib.vkgpu_add_batch_device(ix.handle(), None, Xb.data_ptr(), Xb.shape[0]))
+        build_s += time.perf_counter() - t0
+        L.check(lib.vkgpu_add_batch_device(flat.handle(), None, Xb.data_ptr(), Xb.shape[0]))
+        if nblk == 1:
+            X = Xb
+        del Xb
+    log(f"[hnsw] GPU build of {N} x {D}: {build_s:.1f}s ({N / build_s:.0f} inserts/s)")
     mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
     od, ol, on = mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32)
     td, tl, tn = mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32)
@@ -230,7 +244,7 @@ def hnsw_workload(args):
                 "distance_evals_per_query": evals, "hops_per_query": st1.hops / max(B, 1),
                 "kernel_ms_avg": hnsw_ms / max(hnsw_n, 1)}
     cpu_base = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and X is not None:  # the CPU arm needs the corpus on the host: single-block runs only
         sys.path.insert(0, os.path.join(ROOT, "tests"))
         from test_hnsw_gpu import export_graph
         ix._m = M
@@ -337,7 +351,7 @@ def prefilter_workload(args):
     import valkey_search_b200 as V
     from valkey_search_b200 import _lib as L
 
-    N = args.rows if args.rows != 10_000_000 else 2_000_000
+    N = args.rows if args.rows is not None else 2_000_000
     D = 1536 if args.dim == 768 else args.dim
     k = 10 if args.k == 100 else args.k
     B = 64 if args.batch == 1024 else args.batch
@@ -438,7 +452,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--rows", type=int, default=None,
+                    help="default: 10M (flat, serve), 1M (hnsw), 2M (prefilter)")
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--batch", type=int, default=1024)
@@ -454,6 +469,8 @@ def main():
     args = ap.parse_args()
     if args.workload == "hnsw":
         return hnsw_workload(args)
+    if args.rows is None and args.workload in ("flat", "serve"):
+        args.rows = 10_000_000
     if args.workload == "prefilter":
         return prefilter_workload(args)
     if args.workload == "serve":

@@ -1,0 +1,363 @@
+// Parity tests for the C++ host mirror (valkey_search_b200/host/vector_index.h), written to read like the
+// reference's own testing/vector_test.cc: same fixtures (DeterministicallyGenerateVectors, testing/common.cc:42-53;
+// kDimensions/kInitialCap/kBlockSize/kM/kEFConstruction/kEFRuntime, vector_test.cc:54-59; IndexToKey :126-128),
+// same cases (TestIndex :238-291 through BasicHNSW/BasicFlat :353-375, EfRuntimeRecall :439-500) plus the
+// integration test's cosine goldens (testing/integration/vector_search_integration_test.py:19-23,144-166) and the
+// pre-filter path.  Needs a B200: there is no CPU path behind the ABI.  `--host-only` runs the host-side cases.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../valkey_search_b200/host/vector_index.h"
+
+using namespace valkey_search::indexes;
+
+static int g_failures = 0, g_checks = 0;
+#define EXPECT_TRUE(c)                                                              \
+  do {                                                                              \
+    g_checks++;                                                                     \
+    if (!(c)) {                                                                     \
+      g_failures++;                                                                 \
+      std::fprintf(stderr, "  FAILED %s:%d: %s\n", __FILE__, __LINE__, #c);         \
+    }                                                                               \
+  } while (0)
+#define EXPECT_FALSE(c) EXPECT_TRUE(!(c))
+#define EXPECT_EQ(a, b) EXPECT_TRUE((a) == (b))
+#define EXPECT_OK(s) EXPECT_TRUE((s).ok())
+
+constexpr int kDimensions = 100;
+constexpr int kInitialCap = 15000;
+constexpr uint32_t kBlockSize = 250;
+constexpr int kM = 16;
+constexpr int kEFConstruction = 20;
+constexpr int kEFRuntime = 20;
+
+static std::vector<std::vector<float>> DeterministicallyGenerateVectors(int size, int dimensions, float max_value) {
+  std::vector<std::vector<float>> result(size, std::vector<float>(dimensions));
+  for (int i = 0; i < size; ++i)
+    for (int j = 0; j < dimensions; ++j)
+      result[i][j] = max_value * (static_cast<float>(i + j) / static_cast<float>(size + dimensions));
+  return result;
+}
+static std::string IndexToKey(int i) { return std::to_string(i) + "_key"; }
+static std::string_view VectorToStr(const std::vector<float> &v) {
+  return std::string_view(reinterpret_cast<const char *>(v.data()), v.size() * sizeof(float));
+}
+static VectorIndexProto CreateHNSWVectorIndexProto(int dim, DistanceMetric metric, int initial_cap, int m, int efc, int ef) {
+  VectorIndexProto p;
+  p.dimension_count = dim;
+  p.distance_metric = metric;
+  p.initial_cap = initial_cap;
+  p.hnsw_algorithm.m = m;
+  p.hnsw_algorithm.ef_construction = efc;
+  p.hnsw_algorithm.ef_runtime = ef;
+  return p;
+}
+static VectorIndexProto CreateFlatVectorIndexProto(int dim, DistanceMetric metric, int initial_cap, uint32_t block_size) {
+  VectorIndexProto p;
+  p.dimension_count = dim;
+  p.distance_metric = metric;
+  p.initial_cap = initial_cap;
+  p.flat_algorithm.block_size = block_size;
+  return p;
+}
+
+enum class ExpectedResults { kSuccess, kMissing, kInvalidData, kError };
+
+static void VerifyResult(const vks::StatusOr<RecordResult> &res, ExpectedResults expected) {
+  if (expected == ExpectedResults::kSuccess) {
+    EXPECT_OK(res);
+    if (res.ok()) EXPECT_EQ(res.value(), RecordResult::kAdded);
+  } else if (expected == ExpectedResults::kMissing) {
+    EXPECT_OK(res);
+    if (res.ok()) EXPECT_EQ(res.value(), RecordResult::kMissing);
+  } else if (expected == ExpectedResults::kInvalidData) {
+    EXPECT_OK(res);
+    if (res.ok()) EXPECT_EQ(res.value(), RecordResult::kInvalidData);
+  } else {
+    EXPECT_FALSE(res.status().ok());
+  }
+}
+static void VerifyAdd(VectorBase *index, const std::vector<std::vector<float>> &vectors, int i, ExpectedResults expected) {
+  const auto id = IndexToKey(i);
+  const bool already = index->IsTracked(id);
+  auto res = index->AddRecord(id, VectorToStr(vectors[i]));
+  if (res.ok() && res.value() == RecordResult::kAdded) {
+    EXPECT_TRUE(index->IsTracked(id));
+  } else if (!already) {
+    EXPECT_FALSE(index->IsTracked(id));
+  }
+  VerifyResult(res, expected);
+}
+static void VerifyModify(VectorBase *index, const std::vector<float> &vector, int i, ExpectedResults expected,
+                         bool expected_tracked) {
+  const auto id = IndexToKey(i);
+  auto res = index->ModifyRecord(id, VectorToStr(vector));
+  EXPECT_EQ(index->IsTracked(id), expected_tracked);
+  VerifyResult(res, expected);
+}
+
+// testing/vector_test.cc:238-291
+template <typename T>
+static void TestIndex(T *index, int dimensions, int vector_size) {
+  auto vectors = DeterministicallyGenerateVectors(vector_size, dimensions, 10.0);
+  for (size_t i = 0; i < vectors.size(); ++i) VerifyAdd(index, vectors, i, ExpectedResults::kSuccess);
+  VerifyAdd(index, vectors, 0, ExpectedResults::kError);  // "Embedding id already exists"
+  auto vectors_small_dim = DeterministicallyGenerateVectors(vectors.size(), dimensions - 1, 1.0);
+  VerifyAdd(index, vectors_small_dim, 0, ExpectedResults::kInvalidData);
+  VerifyModify(index, vectors_small_dim[0], 0, ExpectedResults::kInvalidData, false);  // and the key is removed
+  VerifyModify(index, vectors[0], 0, ExpectedResults::kError, false);
+  VerifyModify(index, vectors[0], vectors.size(), ExpectedResults::kError, false);
+  VerifyModify(index, vectors[vectors.size() - 2], vectors.size() - 1, ExpectedResults::kSuccess, true);
+  // (ours) an unchanged vector is a no-op reported as kMissing (vector_base.cc:239-243)
+  VerifyModify(index, vectors[vectors.size() - 2], vectors.size() - 1, ExpectedResults::kMissing, true);
+
+  for (size_t i = 1; i < vectors.size() - 1; ++i) {
+    auto res = index->Search(VectorToStr(vectors[i]), 10, CancelNever());
+    EXPECT_OK(res);
+    if (res.ok()) {
+      EXPECT_FALSE(res->empty());
+      bool found = false;
+      for (const auto &neighbor : res.value()) {
+        if (neighbor.external_id == IndexToKey(i)) {
+          EXPECT_TRUE(neighbor.distance - res.value()[0].distance < 0.0001);
+          found = true;
+          break;
+        }
+      }
+      EXPECT_TRUE(found);
+    }
+  }
+  EXPECT_OK(index->RemoveRecord(IndexToKey(vectors.size()), DeletionType::kNone));
+  EXPECT_FALSE(index->RemoveRecord(IndexToKey(vectors.size()), DeletionType::kNone).value());
+  for (size_t i = 0; i < vectors.size(); ++i) {
+    EXPECT_OK(index->RemoveRecord(IndexToKey(i), DeletionType::kNone));
+    EXPECT_FALSE(index->IsTracked(IndexToKey(i)));
+  }
+  for (size_t i = 0; i < vectors.size(); ++i) VerifyAdd(index, vectors, i, ExpectedResults::kSuccess);
+}
+
+static void BasicHNSW() {
+  for (auto metric : {DistanceMetric::kCosine, DistanceMetric::kL2}) {
+    auto index = VectorHNSW<float>::Create(
+        CreateHNSWVectorIndexProto(kDimensions, metric, kInitialCap, kM, kEFConstruction, kEFRuntime));
+    EXPECT_OK(index);
+    if (index.ok()) TestIndex<VectorHNSW<float>>(index->get(), kDimensions, 100);
+  }
+}
+static void BasicFlat() {
+  for (auto metric : {DistanceMetric::kCosine, DistanceMetric::kL2}) {
+    auto index = VectorFlat<float>::Create(CreateFlatVectorIndexProto(kDimensions, metric, kInitialCap, kBlockSize));
+    EXPECT_OK(index);
+    if (index.ok()) TestIndex<VectorFlat<float>>(index->get(), kDimensions, 100);
+  }
+}
+
+// testing/vector_test.cc:418-437
+static float CalcRecall(VectorFlat<float> *flat_index, VectorHNSW<float> *hnsw_index, uint64_t k, int dimensions,
+                        std::optional<size_t> ef_runtime) {
+  auto search_vectors = DeterministicallyGenerateVectors(50, dimensions, 1.5);
+  int cnt = 0;
+  for (const auto &search_vector : search_vectors) {
+    auto res_hnsw = hnsw_index->Search(VectorToStr(search_vector), k, CancelNever(), nullptr, ef_runtime);
+    auto res_flat = flat_index->Search(VectorToStr(search_vector), k, CancelNever());
+    EXPECT_OK(res_hnsw);
+    EXPECT_OK(res_flat);
+    if (!res_hnsw.ok() || !res_flat.ok()) return 0.f;
+    for (auto &label : *res_hnsw)
+      for (auto &real_label : *res_flat)
+        if (label.external_id == real_label.external_id) {
+          ++cnt;
+          break;
+        }
+  }
+  return ((float)cnt) / ((float)(k * search_vectors.size()));
+}
+// testing/vector_test.cc:439-500
+static void EfRuntimeRecall() {
+  const int initial_cap = 31000;
+  auto index_hnsw = VectorHNSW<float>::Create(
+      CreateHNSWVectorIndexProto(kDimensions, DistanceMetric::kL2, initial_cap, kM, kEFConstruction, kEFRuntime));
+  auto index_flat = VectorFlat<float>::Create(CreateFlatVectorIndexProto(kDimensions, DistanceMetric::kL2, initial_cap, kBlockSize));
+  EXPECT_OK(index_hnsw);
+  EXPECT_OK(index_flat);
+  if (!index_hnsw.ok() || !index_flat.ok()) return;
+  auto vectors = DeterministicallyGenerateVectors(1000, kDimensions, 2.2);
+  for (size_t i = 0; i < vectors.size(); ++i) VerifyAdd(index_hnsw->get(), vectors, i, ExpectedResults::kSuccess);
+  for (size_t i = 0; i < vectors.size(); ++i) VerifyAdd(index_flat->get(), vectors, i, ExpectedResults::kSuccess);
+  const uint64_t k = 10;
+  auto no_ef = CalcRecall(index_flat->get(), index_hnsw->get(), k, kDimensions, std::nullopt);
+  auto default_ef = CalcRecall(index_flat->get(), index_hnsw->get(), k, kDimensions, kEFRuntime);
+  auto ef8 = CalcRecall(index_flat->get(), index_hnsw->get(), k, kDimensions, kEFRuntime * 8);
+  std::fprintf(stderr, "  recall@10: ef=default %.3f, ef=%d %.3f, ef=%d %.3f\n", no_ef, kEFRuntime, default_ef,
+               kEFRuntime * 8, ef8);
+  EXPECT_TRUE(ef8 >= 0.96f);
+  EXPECT_EQ(default_ef, no_ef);
+}
+
+// testing/integration/vector_search_integration_test.py:19-23,144-166: vectors [1, data, 0...] D=100 COSINE,
+// query [1,0,...], k=3 => keys 0,1,2 with scores "0", "0.292893230915", "0.552786409855" (%.12g of the float,
+// src/commands/ft_search.cc:69).
+static void IntegrationCosineGoldens() {
+  for (int algo = 0; algo < 2; algo++) {
+    std::shared_ptr<VectorBase> index;
+    if (algo == 0) {
+      auto r = VectorFlat<float>::Create(CreateFlatVectorIndexProto(100, DistanceMetric::kCosine, 1000, 1024));
+      EXPECT_OK(r);
+      if (!r.ok()) continue;
+      index = *r;
+    } else {
+      auto r = VectorHNSW<float>::Create(CreateHNSWVectorIndexProto(100, DistanceMetric::kCosine, 1000, 16, 200, 10));
+      EXPECT_OK(r);
+      if (!r.ok()) continue;
+      index = *r;
+    }
+    for (int i = 0; i < 10; i++) {
+      std::vector<float> v(100, 0.0f);
+      v[0] = 1.0f;
+      v[1] = (float)i;
+      EXPECT_OK(index->AddRecord(std::to_string(i), VectorToStr(v)));
+    }
+    std::vector<float> q(100, 0.0f);
+    q[0] = 1.0f;
+    vks::StatusOr<std::vector<Neighbor>> res = algo == 0
+        ? static_cast<VectorFlat<float> *>(index.get())->Search(VectorToStr(q), 3, CancelNever())
+        : static_cast<VectorHNSW<float> *>(index.get())->Search(VectorToStr(q), 3, CancelNever());
+    EXPECT_OK(res);
+    if (!res.ok()) continue;
+    EXPECT_EQ(res->size(), (size_t)3);
+    const char *want[3] = {"0", "0.292893230915", "0.552786409855"};
+    for (size_t j = 0; j < res->size() && j < 3; j++) {
+      char buf[64];
+      std::snprintf(buf, sizeof(buf), "%.12g", (*res)[j].distance);
+      EXPECT_EQ((*res)[j].external_id, std::to_string(j));
+      EXPECT_TRUE(std::strcmp(buf, want[j]) == 0);
+      if (std::strcmp(buf, want[j]) != 0) std::fprintf(stderr, "  score[%zu] = %s, want %s\n", j, buf, want[j]);
+    }
+    // GetValue de-normalises with the stored magnitude (vector_base.cc:279-297)
+    auto val = index->GetValue("3");
+    EXPECT_OK(val);
+    if (val.ok()) {
+      const float *f = reinterpret_cast<const float *>(val->data());
+      EXPECT_TRUE(std::fabs(f[0] - 1.0f) < 1e-5f && std::fabs(f[1] - 3.0f) < 1e-5f);
+    }
+  }
+}
+
+// AddPrefilteredKey loop (src/query/search.cc:457-481) vs the one-call SearchPrefiltered vs Search with a filter
+static void Prefilter() {
+  auto r = VectorFlat<float>::Create(CreateFlatVectorIndexProto(kDimensions, DistanceMetric::kL2, kInitialCap, kBlockSize));
+  EXPECT_OK(r);
+  if (!r.ok()) return;
+  auto index = *r;
+  auto vectors = DeterministicallyGenerateVectors(500, kDimensions, 10.0);
+  for (size_t i = 0; i < vectors.size(); ++i) VerifyAdd(index.get(), vectors, i, ExpectedResults::kSuccess);
+  std::vector<std::string> keys;
+  for (int i = 0; i < 500; i += 7) keys.push_back(IndexToKey(i));
+  keys.push_back("not_indexed_key");  // skipped, vector_base.cc:513-516
+  auto query = VectorToStr(vectors[250]);
+  std::priority_queue<std::pair<float, uint64_t>> results;
+  std::unordered_set<std::string> top_keys;
+  for (const auto &key : keys)
+    if (index->AddPrefilteredKey(query, 5, key, results, top_keys)) top_keys.insert(key);
+  auto loop = index->CreateReply(results);
+  auto one = index->SearchPrefiltered(query, 5, keys);
+  KeyFilter filter = [](const std::string &key) { return std::stoi(key) % 7 == 0; };
+  auto via_filter = index->Search(query, 5, CancelNever(), &filter);
+  EXPECT_OK(loop);
+  EXPECT_OK(one);
+  EXPECT_OK(via_filter);
+  if (!loop.ok() || !one.ok() || !via_filter.ok()) return;
+  EXPECT_EQ(loop->size(), (size_t)5);
+  EXPECT_EQ(one->size(), loop->size());
+  EXPECT_EQ(via_filter->size(), loop->size());
+  for (size_t j = 0; j < loop->size() && j < one->size() && j < via_filter->size(); j++) {
+    EXPECT_EQ((*loop)[j].external_id, (*one)[j].external_id);
+    EXPECT_TRUE(std::memcmp(&(*loop)[j].distance, &(*one)[j].distance, 4) == 0);
+    EXPECT_EQ((*via_filter)[j].external_id, (*one)[j].external_id);
+  }
+  EXPECT_EQ(top_keys.size(), (size_t)5);
+}
+
+// HNSW inline filter (hnswalg.h:515-524) and the batched entry
+static void InlineFilterAndBatch() {
+  auto rh = VectorHNSW<float>::Create(CreateHNSWVectorIndexProto(kDimensions, DistanceMetric::kL2, kInitialCap, kM, 100, 64));
+  auto rf = VectorFlat<float>::Create(CreateFlatVectorIndexProto(kDimensions, DistanceMetric::kL2, kInitialCap, kBlockSize));
+  EXPECT_OK(rh);
+  EXPECT_OK(rf);
+  if (!rh.ok() || !rf.ok()) return;
+  auto vectors = DeterministicallyGenerateVectors(800, kDimensions, 10.0);
+  for (size_t i = 0; i < vectors.size(); ++i) {
+    VerifyAdd(rh->get(), vectors, i, ExpectedResults::kSuccess);
+    VerifyAdd(rf->get(), vectors, i, ExpectedResults::kSuccess);
+  }
+  KeyFilter even = [](const std::string &key) { return std::stoi(key) % 2 == 0; };
+  auto res = (*rh)->Search(VectorToStr(vectors[401]), 10, CancelNever(), &even, 200);
+  EXPECT_OK(res);
+  if (res.ok()) {
+    EXPECT_EQ(res->size(), (size_t)10);
+    for (const auto &n : *res) EXPECT_TRUE(std::stoi(n.external_id) % 2 == 0);
+  }
+  // 64 queries in one launch == 64 single searches
+  std::vector<float> flatq;
+  for (int b = 0; b < 64; b++) flatq.insert(flatq.end(), vectors[b * 3].begin(), vectors[b * 3].end());
+  auto batch = (*rf)->SearchBatch(std::string_view(reinterpret_cast<const char *>(flatq.data()), flatq.size() * 4), 64, 10);
+  EXPECT_OK(batch);
+  if (batch.ok())
+    for (int b = 0; b < 64; b += 9) {
+      auto single = (*rf)->Search(VectorToStr(vectors[b * 3]), 10, CancelNever());
+      EXPECT_OK(single);
+      if (!single.ok()) continue;
+      EXPECT_EQ(single->size(), (*batch)[b].size());
+      for (size_t j = 0; j < single->size() && j < (*batch)[b].size(); j++) {
+        EXPECT_EQ((*single)[j].external_id, (*batch)[b][j].external_id);
+        EXPECT_TRUE(std::memcmp(&(*single)[j].distance, &(*batch)[b][j].distance, 4) == 0);
+      }
+    }
+}
+
+// host-only: normalisation arithmetic (vector_base.cc:112-138) and the no-CPU-fallback contract
+static void HostOnly(bool have_gpu) {
+  std::vector<float> v = {3.0f, 4.0f, 0.0f};
+  float mag = 0;
+  auto n = NormalizeEmbedding(VectorToStr(v), sizeof(float), &mag);
+  const float *f = reinterpret_cast<const float *>(n.data());
+  EXPECT_TRUE(mag == 5.0f);
+  EXPECT_TRUE(f[0] == 0.2f * 3.0f && f[1] == 0.2f * 4.0f && f[2] == 0.0f);
+  std::vector<float> z(8, 0.0f);
+  auto nz = NormalizeEmbedding(VectorToStr(z), sizeof(float), &mag);
+  EXPECT_TRUE(mag == 0.0f && reinterpret_cast<const float *>(nz.data())[3] == 0.0f);  // zero vector stays zero
+  if (!have_gpu) {
+    auto r = VectorFlat<float>::Create(CreateFlatVectorIndexProto(16, DistanceMetric::kL2, 100, 10));
+    EXPECT_FALSE(r.ok());  // no device => error status, never a CPU index
+    if (!r.ok()) std::fprintf(stderr, "  Create without a GPU: %s\n", r.status().message().c_str());
+  }
+}
+
+int main(int argc, char **argv) {
+  const bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";
+  struct Case {
+    const char *name;
+    void (*fn)();
+  } cases[] = {{"BasicFlat", BasicFlat},
+               {"BasicHNSW", BasicHNSW},
+               {"EfRuntimeRecall", EfRuntimeRecall},
+               {"IntegrationCosineGoldens", IntegrationCosineGoldens},
+               {"Prefilter", Prefilter},
+               {"InlineFilterAndBatch", InlineFilterAndBatch}};
+  {
+    const int before = g_failures;
+    HostOnly(vkgpu_device_count() > 0);
+    std::printf("[%s] HostOnly\n", g_failures == before ? "  OK  " : "FAILED");
+  }
+  if (!host_only)
+    for (const auto &c : cases) {
+      const int before = g_failures;
+      c.fn();
+      std::printf("[%s] %s\n", g_failures == before ? "  OK  " : "FAILED", c.name);
+    }
+  std::printf("%d checks, %d failures\n", g_checks, g_failures);
+  return g_failures ? 1 : 0;
+}

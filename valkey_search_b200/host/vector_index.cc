@@ -1,0 +1,387 @@
+// Host mirror of valkey_search::indexes::VectorBase / VectorFlat / VectorHNSW over libvkgpu (see vector_index.h).
+// Compile with -ffp-contract=off: the reference builds with it (cmake/Modules/valkey_search.cmake:121), and the
+// normalisation below must round `src[i] * src[i]` before the add exactly like vector_base.cc:112-124 does.
+#include "vector_index.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace valkey_search::indexes {
+
+// ------------------------------------------------------------------------------------------ normalisation
+// vector_base.cc:112-124
+static float CopyAndNormalizeEmbedding(float *dst, const float *src, size_t size) {
+  float magnitude = 0.0f;
+  for (size_t i = 0; i < size; i++) magnitude += src[i] * src[i];
+  magnitude = std::sqrt(magnitude);
+  const float norm = (magnitude == 0.0f) ? 1.0f : (1.0f / magnitude);
+  for (size_t i = 0; i < size; i++) dst[i] = norm * src[i];
+  return magnitude;
+}
+
+std::vector<char> NormalizeEmbedding(std::string_view record, size_t type_size, float *magnitude) {
+  std::vector<char> ret(record.size());
+  if (type_size != sizeof(float)) return {};  // the reference CHECK-fails on any other type size
+  std::vector<float> src(record.size() / sizeof(float));
+  std::memcpy(src.data(), record.data(), src.size() * sizeof(float));  // records need not be aligned
+  std::vector<float> dst(src.size());
+  const float result = CopyAndNormalizeEmbedding(dst.data(), src.data(), src.size());
+  std::memcpy(ret.data(), dst.data(), dst.size() * sizeof(float));
+  if (magnitude) *magnitude = result;
+  return ret;
+}
+
+// ------------------------------------------------------------------------------------------ VectorBase
+VectorBase::VectorBase(int dimensions, DistanceMetric metric)
+    : dimensions_(dimensions), distance_metric_(metric), normalize_(metric == DistanceMetric::kCosine) {}
+
+VectorBase::~VectorBase() {
+  if (gpu_) vkgpu_index_destroy(gpu_);
+}
+
+Status VectorBase::FromRc(int rc) const {  // vkgpu_status -> absl::Status
+  switch (rc) {
+    case VKGPU_OK:
+      return vks::OkStatus();
+    case VKGPU_ERR_CANCELLED:
+      return vks::CancelledError("Search operation cancelled due to timeout");  // query::kTimeoutMsg
+    case VKGPU_ERR_NOT_FOUND:
+      return vks::NotFoundError(vkgpu_last_error());
+    case VKGPU_ERR_INVALID:
+      return vks::InvalidArgumentError(vkgpu_last_error());
+    case VKGPU_ERR_EXISTS:
+      return vks::AlreadyExistsError(vkgpu_last_error());
+    case VKGPU_ERR_OOM:
+      return vks::ResourceExhaustedError(vkgpu_last_error());
+    case VKGPU_ERR_UNSUPPORTED:
+      return vks::UnimplementedError(vkgpu_last_error());
+    default:
+      return vks::InternalError(vkgpu_last_error());
+  }
+}
+
+Status VectorBase::CreateCore(const vkgpu_config &cfg) { return FromRc(vkgpu_index_create(&cfg, &gpu_)); }
+
+std::optional<std::vector<char>> VectorBase::InternVector(std::string_view record, float &magnitude) const {
+  if (!IsValidSizeVector(record)) return std::nullopt;
+  magnitude = kDefaultMagnitude;
+  if (normalize_) return NormalizeEmbedding(record, GetDataTypeSize(), &magnitude);
+  return std::vector<char>(record.begin(), record.end());
+}
+
+StatusOr<uint64_t> VectorBase::TrackKey(const std::string &key, float magnitude) {
+  if (key.empty()) return vks::InvalidArgumentError("key can't be empty");
+  std::unique_lock lock(key_to_metadata_mutex_);
+  const uint64_t id = inc_id_++;  // consumed even when the insert fails, as in the reference
+  auto [it, succ] = tracked_metadata_by_key_.insert({key, TrackedKeyMetadata{id, magnitude}});
+  if (!succ) return vks::InvalidArgumentError("Embedding id already exists: " + key);
+  key_by_internal_id_.insert({id, key});
+  return id;
+}
+
+StatusOr<std::optional<uint64_t>> VectorBase::UnTrackKey(const std::string &key) {
+  if (key.empty()) return std::optional<uint64_t>();
+  std::unique_lock lock(key_to_metadata_mutex_);
+  auto it = tracked_metadata_by_key_.find(key);
+  if (it == tracked_metadata_by_key_.end()) return std::optional<uint64_t>();
+  const uint64_t id = it->second.internal_id;
+  tracked_metadata_by_key_.erase(it);
+  auto kit = key_by_internal_id_.find(id);
+  if (kit == key_by_internal_id_.end())
+    return vks::InvalidArgumentError(
+        "Error while untracking key - key was not found in key_by_internal_id_ but in internal_by_key_");
+  key_by_internal_id_.erase(kit);
+  return std::optional<uint64_t>(id);
+}
+
+StatusOr<uint64_t> VectorBase::GetInternalId(const std::string &key) const {
+  std::shared_lock lock(key_to_metadata_mutex_);
+  auto it = tracked_metadata_by_key_.find(key);
+  if (it == tracked_metadata_by_key_.end()) return vks::InvalidArgumentError("Record was not found");
+  return it->second.internal_id;
+}
+
+StatusOr<RecordResult> VectorBase::AddRecord(const std::string &key, std::string_view record) {
+  float magnitude;
+  auto interned = InternVector(record, magnitude);
+  if (!interned) return RecordResult::kInvalidData;  // wrong byte length
+  auto id = TrackKey(key, magnitude);
+  if (!id.ok()) return id.status();
+  const Status add = FromRc(vkgpu_add(gpu_, *id, reinterpret_cast<const float *>(interned->data())));
+  if (!add.ok()) {
+    (void)UnTrackKey(key);
+    return add;
+  }
+  return RecordResult::kAdded;
+}
+
+StatusOr<RecordResult> VectorBase::ModifyRecord(const std::string &key, std::string_view record) {
+  float magnitude;
+  auto interned = InternVector(record, magnitude);
+  if (!interned) {
+    (void)RemoveRecord(key, DeletionType::kRecord);
+    return RecordResult::kInvalidData;
+  }
+  auto id = GetInternalId(key);
+  if (!id.ok()) return id.status();
+  {  // UpdateMetadata (vector_base.cc:360-384)
+    if (key.empty()) return vks::InvalidArgumentError("key can't be empty");
+    std::unique_lock lock(key_to_metadata_mutex_);
+    auto it = tracked_metadata_by_key_.find(key);
+    if (it == tracked_metadata_by_key_.end()) return vks::InvalidArgumentError("Embedding id not found: " + key);
+    it->second.magnitude = magnitude;
+  }
+  // IsVectorMatch: the new vector is identical to the stored one => nothing to re-index (kMissing)
+  std::vector<float> cur(dimensions_);
+  VKS_RETURN_IF_ERROR(FromRc(vkgpu_get(gpu_, *id, cur.data())));
+  if (std::memcmp(cur.data(), interned->data(), interned->size()) == 0) return RecordResult::kMissing;
+  const Status mod = FromRc(vkgpu_modify(gpu_, *id, reinterpret_cast<const float *>(interned->data())));
+  if (!mod.ok()) {
+    (void)UnTrackKey(key);
+    return mod;
+  }
+  return RecordResult::kAdded;
+}
+
+StatusOr<bool> VectorBase::RemoveRecord(const std::string &key, DeletionType) {
+  auto res = UnTrackKey(key);
+  if (!res.ok()) return res.status();
+  if (!res->has_value()) return false;
+  VKS_RETURN_IF_ERROR(FromRc(vkgpu_remove(gpu_, res->value())));
+  return true;
+}
+
+size_t VectorBase::GetCapacity() const { return Stats().capacity; }
+
+vkgpu_stats VectorBase::Stats() const {
+  vkgpu_stats s{};
+  vkgpu_get_stats(gpu_, &s);
+  return s;
+}
+
+size_t VectorBase::GetTrackedKeyCount() const {
+  std::shared_lock lock(key_to_metadata_mutex_);
+  return tracked_metadata_by_key_.size();
+}
+
+bool VectorBase::IsTracked(const std::string &key) const {
+  std::shared_lock lock(key_to_metadata_mutex_);
+  return tracked_metadata_by_key_.count(key) != 0;
+}
+
+Status VectorBase::ForEachTrackedKey(const std::function<Status(const std::string &)> &fn) const {
+  std::shared_lock lock(key_to_metadata_mutex_);
+  for (const auto &[key, _] : tracked_metadata_by_key_) VKS_RETURN_IF_ERROR(fn(key));
+  return vks::OkStatus();
+}
+
+StatusOr<std::string> VectorBase::GetKeyDuringSearch(uint64_t internal_id) const {
+  auto it = key_by_internal_id_.find(internal_id);  // no lock: searches never overlap mutations (MRMW lock)
+  if (it == key_by_internal_id_.end()) return vks::InvalidArgumentError("Record was not found");
+  return it->second;
+}
+
+StatusOr<std::vector<char>> VectorBase::GetValue(const std::string &key) const {
+  auto it = tracked_metadata_by_key_.find(key);
+  if (it == tracked_metadata_by_key_.end()) return vks::NotFoundError("Record was not found");
+  std::vector<float> row(dimensions_);
+  VKS_RETURN_IF_ERROR(FromRc(vkgpu_get(gpu_, it->second.internal_id, row.data())));
+  if (normalize_) {
+    if (it->second.magnitude < 0) return vks::InternalError("Magnitude is not initialized");
+    for (float &x : row) x = x * it->second.magnitude;  // CopyAndDenormalizeEmbedding (src/vector_externalizer.cc:30-40)
+  }
+  std::vector<char> result(GetVectorDataSize());
+  std::memcpy(result.data(), row.data(), result.size());
+  return result;
+}
+
+StatusOr<std::vector<Neighbor>> VectorBase::CreateReply(std::priority_queue<std::pair<float, uint64_t>> &knn_res) const {
+  std::vector<Neighbor> ret;
+  ret.reserve(knn_res.size());
+  while (!knn_res.empty()) {
+    const auto &ele = knn_res.top();
+    auto key = GetKeyDuringSearch(ele.second);
+    if (key.ok()) ret.emplace_back(*key, ele.first);  // descending while popping
+    knn_res.pop();
+  }
+  std::reverse(ret.begin(), ret.end());  // closest first
+  return ret;
+}
+
+bool VectorBase::AddPrefilteredKey(std::string_view query, uint64_t count, const std::string &key,
+                                   std::priority_queue<std::pair<float, uint64_t>> &results,
+                                   std::unordered_set<std::string> &top_keys) const {
+  auto it = tracked_metadata_by_key_.find(key);  // GetInternalIdDuringSearch
+  if (it == tracked_metadata_by_key_.end()) return false;
+  const uint64_t id = it->second.internal_id;
+  float d;
+  if (vkgpu_distances(gpu_, reinterpret_cast<const float *>(query.data()), &id, 1, &d) != VKGPU_OK) return false;
+  const std::pair<float, uint64_t> cand{d, id};
+  if (results.size() < count) {
+    results.emplace(cand);
+    return true;
+  }
+  if (cand.first < results.top().first) {
+    auto top_key = GetKeyDuringSearch(results.top().second);
+    if (top_key.ok()) top_keys.erase(*top_key);
+    results.pop();
+    results.emplace(cand);
+    return true;
+  }
+  return false;
+}
+
+std::vector<uint64_t> VectorBase::IdsMatching(const KeyFilter &filter) const {
+  std::vector<uint64_t> ids;
+  std::shared_lock lock(key_to_metadata_mutex_);
+  for (const auto &[key, meta] : tracked_metadata_by_key_)
+    if (filter(key)) ids.push_back(meta.internal_id);
+  return ids;
+}
+
+StatusOr<std::vector<Neighbor>> VectorBase::SearchOne(std::string_view query, uint64_t count, uint32_t ef,
+                                                      const vkgpu_filter *filter, CancelToken token) const {
+  if (!IsValidSizeVector(query)) return vks::InvalidArgumentError("query vector has the wrong byte length");
+  std::vector<char> norm;
+  if (normalize_) {  // vector_flat.cc:244-249, vector_hnsw.cc:337-343
+    norm = NormalizeEmbedding(query, GetDataTypeSize());
+    query = std::string_view(norm.data(), norm.size());
+  }
+  std::vector<float> q(dimensions_);
+  std::memcpy(q.data(), query.data(), query.size());
+  const uint32_t k = (uint32_t)std::max<uint64_t>(count, 1);
+  std::vector<float> dist(k);
+  std::vector<uint64_t> labels(k);
+  uint32_t n = 0;
+  VKS_RETURN_IF_ERROR(FromRc(vkgpu_search(gpu_, q.data(), (uint32_t)count, ef, filter, token, dist.data(), labels.data(), &n)));
+  std::priority_queue<std::pair<float, uint64_t>> pq;  // CreateReply wants the heap it always got
+  for (uint32_t i = 0; i < n; i++) pq.emplace(dist[i], labels[i]);
+  return CreateReply(pq);
+}
+
+StatusOr<std::vector<Neighbor>> VectorBase::SearchPrefiltered(std::string_view query, uint64_t count,
+                                                              const std::vector<std::string> &keys) const {
+  std::vector<uint64_t> ids;
+  ids.reserve(keys.size());
+  for (const auto &key : keys) {
+    auto it = tracked_metadata_by_key_.find(key);
+    if (it != tracked_metadata_by_key_.end()) ids.push_back(it->second.internal_id);
+  }
+  vkgpu_filter f{};
+  f.labels = ids.data();
+  f.n_labels = ids.size();
+  return SearchOne(query, count, 0, &f, CancelNever());
+}
+
+StatusOr<std::vector<std::vector<Neighbor>>> VectorBase::SearchBatch(std::string_view queries, uint32_t batch,
+                                                                     uint64_t count,
+                                                                     std::optional<size_t> ef_runtime) const {
+  const size_t row = (size_t)dimensions_ * sizeof(float);
+  if (queries.size() != row * batch) return vks::InvalidArgumentError("query batch has the wrong byte length");
+  std::vector<float> q((size_t)batch * dimensions_);
+  for (uint32_t b = 0; b < batch; b++) {
+    std::string_view one = queries.substr(b * row, row);
+    if (normalize_) {
+      auto norm = NormalizeEmbedding(one, GetDataTypeSize());
+      std::memcpy(q.data() + (size_t)b * dimensions_, norm.data(), row);
+    } else {
+      std::memcpy(q.data() + (size_t)b * dimensions_, one.data(), row);
+    }
+  }
+  const uint32_t k = (uint32_t)std::max<uint64_t>(count, 1);
+  std::vector<float> dist((size_t)batch * k);
+  std::vector<uint64_t> labels((size_t)batch * k);
+  std::vector<uint32_t> n(batch);
+  VKS_RETURN_IF_ERROR(FromRc(vkgpu_search_batch(gpu_, q.data(), batch, (uint32_t)count, (uint32_t)ef_runtime.value_or(0),
+                                                nullptr, 0, dist.data(), labels.data(), n.data())));
+  std::vector<std::vector<Neighbor>> out(batch);
+  for (uint32_t b = 0; b < batch; b++) {
+    std::priority_queue<std::pair<float, uint64_t>> pq;
+    for (uint32_t i = 0; i < n[b]; i++) pq.emplace(dist[(size_t)b * k + i], labels[(size_t)b * k + i]);
+    auto r = CreateReply(pq);
+    if (!r.ok()) return r.status();
+    out[b] = std::move(*r);
+  }
+  return out;
+}
+
+// ------------------------------------------------------------------------------------------ VectorFlat
+static vkgpu_config BaseConfig(const VectorIndexProto &p, vkgpu_algo algo) {
+  vkgpu_config cfg{};
+  cfg.struct_size = sizeof(cfg);
+  cfg.algo = algo;
+  cfg.metric = (int32_t)p.distance_metric;
+  cfg.dim = p.dimension_count;
+  cfg.initial_cap = p.initial_cap;
+  cfg.device = p.gpu_device;
+  cfg.max_batch = p.gpu_max_batch;
+  cfg.batch_window_us = p.gpu_batch_window_us;
+  return cfg;
+}
+
+template <typename T>
+StatusOr<std::shared_ptr<VectorFlat<T>>> VectorFlat<T>::Create(const VectorIndexProto &p) {
+  auto index = std::shared_ptr<VectorFlat<T>>(
+      new VectorFlat<T>((int)p.dimension_count, p.distance_metric, p.flat_algorithm.block_size));
+  vkgpu_config cfg = BaseConfig(p, VKGPU_FLAT);
+  cfg.block_size = p.flat_algorithm.block_size;
+  const Status s = index->CreateCore(cfg);  // the reference wraps hnswlib's constructor in try/catch: vector_flat.cc:68-72
+  if (!s.ok()) return s;
+  return index;
+}
+
+template <typename T>
+StatusOr<std::vector<Neighbor>> VectorFlat<T>::Search(std::string_view query, uint64_t count, CancelToken token,
+                                                      const KeyFilter *filter) const {
+  if (filter) {
+    std::vector<std::string> keys;
+    (void)ForEachTrackedKey([&](const std::string &key) {
+      if ((*filter)(key)) keys.push_back(key);
+      return vks::OkStatus();
+    });
+    return SearchPrefiltered(query, count, keys);
+  }
+  return SearchOne(query, count, 0, nullptr, token);
+}
+
+// ------------------------------------------------------------------------------------------ VectorHNSW
+template <typename T>
+StatusOr<std::shared_ptr<VectorHNSW<T>>> VectorHNSW<T>::Create(const VectorIndexProto &p) {
+  auto index = std::shared_ptr<VectorHNSW<T>>(new VectorHNSW<T>((int)p.dimension_count, p.distance_metric));
+  index->m_ = p.hnsw_algorithm.m;
+  index->ef_construction_ = p.hnsw_algorithm.ef_construction;
+  index->ef_runtime_ = p.hnsw_algorithm.ef_runtime;
+  vkgpu_config cfg = BaseConfig(p, VKGPU_HNSW);
+  cfg.m = p.hnsw_algorithm.m;
+  cfg.ef_construction = p.hnsw_algorithm.ef_construction;
+  cfg.ef_runtime = p.hnsw_algorithm.ef_runtime;
+  cfg.allow_replace_deleted = p.hnsw_allow_replace_deleted ? 1 : 0;
+  const Status s = index->CreateCore(cfg);
+  if (!s.ok()) return s;
+  return index;
+}
+
+template <typename T>
+StatusOr<std::vector<Neighbor>> VectorHNSW<T>::Search(std::string_view query, uint64_t count, CancelToken token,
+                                                      const KeyFilter *filter, std::optional<size_t> ef_runtime,
+                                                      bool enable_partial_results) const {
+  (void)enable_partial_results;  // the core answers within the deadline or reports CANCELLED; no partial heaps
+  const uint32_t ef = (uint32_t)ef_runtime.value_or(0);
+  if (!filter) return SearchOne(query, count, ef, nullptr, token);
+  // inline filter: the set of internal ids whose key satisfies the predicate, as a label bitmap
+  uint64_t max_id = 0;
+  const std::vector<uint64_t> ids = IdsMatching(*filter);
+  for (uint64_t id : ids) max_id = std::max(max_id, id);
+  std::vector<uint8_t> bitmap((max_id + 8) / 8, 0);
+  for (uint64_t id : ids) bitmap[id >> 3] |= (uint8_t)(1u << (id & 7));
+  vkgpu_filter f{};
+  f.label_bitmap = bitmap.data();
+  f.bitmap_bits = bitmap.size() * 8;
+  return SearchOne(query, count, ef, &f, token);
+}
+
+template class VectorFlat<float>;
+template class VectorHNSW<float>;
+
+}  // namespace valkey_search::indexes
