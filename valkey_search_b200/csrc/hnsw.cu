@@ -57,6 +57,7 @@ struct HnswSearchParams {
   uint64_t *out_labels;  // [B][k]
   uint32_t *out_n;       // [B]
   uint32_t rows_per_batch, row_stride_bytes, cand_cap;
+  uint32_t need_flags;  // some node is tombstoned or a filter is present: resolve live/allowed per neighbour
   unsigned long long *stats;
 };
 
@@ -237,23 +238,29 @@ __global__ void __launch_bounds__(HT) hnsw_search_kernel(const HnswSearchParams 
     if (ctl[0]) break;
     const uint32_t cur = ctl[1];
     n_hops++;
-    // phase 1: visited filter, list order preserved
+    // phase 1: visited filter, list order preserved.  The hop is a chain of dependent HBM round trips, so
+    // everything whose address is already known is issued together: the neighbour row is read in full while the
+    // count is still in flight (the row is maxM0 words whatever the count), and the live/deleted word of each
+    // neighbour is requested alongside its visited-bitmap atomic instead of after it.
     if (warp == 0) {
-      const uint32_t cnt = g.hdr0[cur] & kHdrCountMask;
       const uint32_t *nb = g.link0 + (size_t)cur * g.maxM0;
+      const uint32_t first = lane < g.maxM0 ? nb[lane] : 0u;
+      const uint32_t cnt = g.hdr0[cur] & kHdrCountMask;
       uint32_t nuv = 0;
       for (uint32_t base = 0; base < cnt; base += 32) {
         const uint32_t j = base + lane;
         uint32_t id = 0, flag = 0;
         bool unv = false;
         if (j < cnt) {
-          id = nb[j];
+          id = base == 0 ? first : nb[j];
           const uint32_t bit = 1u << (id & 31);
+          const uint32_t hdr = p.need_flags ? g.hdr0[id] : 0u;
           const uint32_t old = atomicOr(&vis[id >> 5], bit);
           unv = !(old & bit);
-          if (unv) {
+          flag = 1u;
+          if (unv && p.need_flags) {
             // live + allowed? (resolved here, in parallel, so the sequential heap replay never waits on HBM)
-            bool ok = !(g.hdr0[id] & kHdrDeleted);
+            bool ok = !(hdr & kHdrDeleted);
             if (ok && allow) {
               const uint64_t lab = g.labels[id];
               ok = lab < allow_bits && ((allow[lab >> 3] >> (lab & 7)) & 1);
@@ -274,6 +281,14 @@ __global__ void __launch_bounds__(HT) hnsw_search_kernel(const HnswSearchParams 
     __syncthreads();
     const uint32_t nuv = ctl[2];
     // phases 2+3a: rows -> shared memory, all distances at once
+    // every evaluated neighbour may become a candidate: pull its link row and header towards L2 now, so that the
+    // pop that selects it later finds them there (the reference prefetches the next candidate's list the same
+    // way, hnswalg.h:426-492)
+    if (tid < nuv) {
+      const uint32_t id = uvi[tid];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(g.link0 + (size_t)id * g.maxM0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(g.hdr0 + id));
+    }
     stage_and_dist(nuv);
     n_dist += nuv;
     // phase 3b: the reference's sequential heap updates (hnswalg.h:497-545)
@@ -522,6 +537,7 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   hp.out_n = c->out_n.as<uint32_t>();
   hp.row_stride_bytes = ix->Dp * 4 + 64;
   hp.cand_cap = std::max<uint32_t>(1024, 8 * ef);
+  hp.need_flags = (g->num_deleted != 0 || filters != nullptr) ? 1u : 0u;
   hp.stats = g->d_stats.as<unsigned long long>();
   // rows staged per round vs CTAs per SM: prefer enough resident CTAs to hold the whole batch in ONE wave (a hop
   // stages ~8 unvisited rows on average, so 12-16 staged rows rarely need a second round), down to 1 CTA/SM for
