@@ -1,4 +1,5 @@
-"""Throwaway: time the tensor candidate kernel (env toggles per run)."""
+"""Times the tensor candidate kernel alone at EXP_ROWS x 768, batch EXP_B (args: VKGPU_TENSOR_PAIR values, one run each).
+With a -DVKGPU_TENSOR_TRACE build (make EXTRA=-DVKGPU_TENSOR_TRACE) and VKGPU_TENSOR_TRACE=1 it prints the per-tile timeline."""
 import ctypes as C, os, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
