@@ -18,6 +18,8 @@ for blk in range((N + BLK - 1) // BLK):
     torch.cuda.synchronize()
     L.check(lib.vkgpu_add_batch_device(ix.handle(), None, Xb.data_ptr(), rows))
     del Xb
+if os.environ.get("EXP_PATH"):
+    ix.SetSearchPath({"exact": V.PATH_EXACT_FMA, "tensor": V.PATH_TENSOR}[os.environ["EXP_PATH"]])
 g = torch.Generator(device=dev); g.manual_seed(4321)
 dQ = torch.randn((B, D), generator=g, device=dev)
 od = torch.empty((B, k), dtype=torch.float32, device=dev); ol = torch.empty((B, k), dtype=torch.int64, device=dev)
@@ -33,6 +35,11 @@ def run(tag, env):
     torch.cuda.synchronize()
     tm = L.Timings(); L.check(lib.vkgpu_get_timings(ix.handle(), C.byref(tm)))
     L.check(lib.vkgpu_set_profiling(ix.handle(), 0))
-    print(tag, "ms per kind:", [round(tm.ms[i] / max(int(tm.launches[i]), 1), 3) for i in range(5)], flush=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(4):
+        L.check(lib.vkgpu_search_batch_device(ix.handle(), dQ.data_ptr(), B, k, 0, od.data_ptr(), ol.data_ptr(), on.data_ptr(), None))
+    e1.record(); torch.cuda.synchronize()
+    print(tag, f"B={B} step ms={e0.elapsed_time(e1) / 4:.3f}", "ms per kind:", [round(tm.ms[i] / max(int(tm.launches[i]), 1), 3) for i in range(5)], flush=True)
 for spec in sys.argv[1:]:
     run(spec, {"VKGPU_TENSOR_PAIR": spec})

@@ -553,14 +553,23 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
     n = min(p.ws_cnt[li], p.cap);
     return p.ws + li * p.cap;
   };
-  if (tid == 0) {
+  // score of entry i of a list: from the compact score-only copy when the producer keeps one (4-byte stride
+  // instead of 16: the three histogram passes and the keep decision read nothing else)
+  auto ord_of = [&](const Cand *src, uint32_t i) -> uint32_t {
+    return p.ws_ord ? p.ws_ord[(size_t)(src - p.ws) + i] : src[i].ord;
+  };
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  {
     uint32_t tot = 0;
-    for (uint32_t s = 0; s < p.slabs; s++) {
+    for (uint32_t s = tid; s < p.slabs; s += MERGE_THREADS) {
       uint32_t n;
       list_of(s, n);
       tot += n;
     }
-    s_total = tot;
+    if (tot) atomicAdd(&s_total, tot);
+  }
+  if (tid == 0) {
     s_prefix = 0;
     s_rank = K;
     s_pos = 0;
@@ -586,7 +595,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
         uint32_t n;
         const Cand *src = list_of(s, n);
         for (uint32_t i = tid; i < n; i += MERGE_THREADS) {
-          const uint32_t o = src[i].ord;
+          const uint32_t o = ord_of(src, i);
           if ((o & hi_mask) == prefix) atomicAdd(&hist[(o >> shifts[pass]) & ((1u << widths[pass]) - 1u)], 1u);
         }
       }
@@ -618,11 +627,11 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
     uint32_t n;
     const Cand *src = list_of(s, n);
     for (uint32_t i = tid; i < n; i += MERGE_THREADS) {
-      const Cand c = src[i];
-      bool keep = c.ord < T;
-      if (!keep && c.ord == T && total > K) keep = atomicAdd(&s_tie, 1u) < quota;
+      const uint32_t o = ord_of(src, i);
+      bool keep = o < T;
+      if (!keep && o == T && total > K) keep = atomicAdd(&s_tie, 1u) < quota;
       if (total <= K) keep = true;
-      if (keep) buf[atomicAdd(&s_pos, 1u)] = c;
+      if (keep) buf[atomicAdd(&s_pos, 1u)] = src[i];
     }
   }
   __syncthreads();

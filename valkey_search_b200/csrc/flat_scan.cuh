@@ -77,6 +77,7 @@ struct MergeParams {
   uint32_t *out_slots;     // optional [B][k]
   uint32_t *out_n;         // [B]
   const uint32_t *k_limit; // optional per-query cap on results (nullptr => k)
+  const uint32_t *ws_ord;  // optional: the lists' scores alone, same [list][cap] shape (selection merge scans these)
 };
 void launch_topk_merge(uint32_t B, cudaStream_t stream, const MergeParams &p);
 // same contract, for approximate scores: ties at the K-th score are broken arbitrarily; sort_n = pow2 >= k

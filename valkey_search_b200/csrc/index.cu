@@ -503,7 +503,7 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     k_eff = (uint32_t)std::min<uint64_t>(k, ix->n);
     bool use_tensor = false;
     if (ix->flat_path == VKGPU_PATH_TENSOR) use_tensor = true;
-    if (ix->flat_path == VKGPU_PATH_AUTO && B >= 64 && k_eff <= 128 && ix->n >= 100000) {
+    if (ix->flat_path == VKGPU_PATH_AUTO && k_eff <= 128 && tensor_path_cheaper(ix, B)) {
       // first large batch: build the bf16 mirror (searches only read the fp32 rows, so this is safe under
       // the shared lock; tensor_mu makes it happen once)
       std::lock_guard<std::mutex> tl(ix->tensor_mu);

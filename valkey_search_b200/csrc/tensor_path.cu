@@ -744,9 +744,17 @@ bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
   (void)B;
   return ix->tensor_ready && k <= 128 && ix->n >= 4096;  // K' = 3k+64 rounded to 128 <= 512
 }
-bool tensor_path_profitable(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
-  // one tensor pass costs about the same for 1..256 queries; the exact scan wins below ~64 queries
-  return ix->tensor_ready && B >= 64 && k <= 128 && ix->n >= 100000;
+// AUTO policy: a two-line cost model fitted to B200 measurements at 768 dims (both paths scale with rows x dims).
+// The exact scan streams the fp32 corpus once per 8 queries: 4.4 ms per 10M rows for one query, 8 ms per pass at
+// 8 queries per pass.  One tensor pass over the bf16 mirror costs the same for 1..256 queries: 3.2-4.4 ms per 10M
+// rows plus ~0.5 ms of start-up, merge and re-rank.  Measured at 10M x 768: batch 8 -> 8.6 ms exact vs 5.1 ms
+// tensor; batch 32 -> 31.8 vs 5.1; batch 1 is a tie, and small corpora stay on the exact scan.
+bool tensor_path_cheaper(const vkgpu_index_impl *ix, uint32_t B) {
+  if (B < 2 || ix->n < 100000) return false;
+  const double unit = (double)ix->n * ix->Dp / (1e7 * 768.0);
+  const double exact_ms = B >= 8 ? std::ceil(B / 8.0) * 8.0 * unit : (4.4 + 0.5 * (B - 1)) * unit;
+  const double tensor_ms = 0.5 + std::ceil(B / 256.0) * 4.0 * unit;
+  return tensor_ms < exact_ms;
 }
 
 static uint32_t dh_of(uint32_t Dp) { return (Dp + 63) / 64 * 64; }
@@ -953,6 +961,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   mp.out_slots = ap_slot;
   mp.out_n = ap_n;
   mp.k_limit = nullptr;
+  mp.ws_ord = tp.ws_ord;
   ix->prof_begin(c, KK_MERGE);
   launch_topk_select_merge(B, s, mp);
   ix->prof_end(c, KK_MERGE);

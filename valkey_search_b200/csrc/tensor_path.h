@@ -5,7 +5,7 @@
 
 namespace vkgpu {
 
-bool tensor_path_profitable(const vkgpu_index_impl *ix, uint32_t B, uint32_t k);
+bool tensor_path_cheaper(const vkgpu_index_impl *ix, uint32_t B);  // AUTO policy (cost model)
 bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k);
 void tensor_prepare(vkgpu_index_impl *ix);                       // build the bf16 mirror + norms
 void tensor_reserve(vkgpu_index_impl *ix, uint64_t rows);        // grow mirror with the corpus
