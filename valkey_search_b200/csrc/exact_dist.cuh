@@ -62,4 +62,54 @@ __device__ __forceinline__ float exact_dist_group(const float *__restrict__ row,
   return L2 ? sum : (float)(1.0 - (double)sum);
 }
 
+// Same arithmetic with SIXTEEN threads per (row, query) pair — thread j IS the reference's SIMD lane j: it folds
+// elements j, j+16, ... in increasing order with one fma each, then the lanes combine at strides 8, 4, 2, 1.
+// For rows staged in shared memory when only a handful of rows are in flight (an HNSW hop evaluates ~8
+// neighbours, a pre-filter stage holds 8 rows of 1536 dims): the 4-thread form leaves 3/4 of a 128-thread CTA
+// idle there and makes each busy thread walk the whole row.  Consecutive threads read consecutive words (no bank
+// conflict; the query read is a broadcast between the two half-warps).  `j` = lane & 15; both half-warps of a warp
+// must call (inactive ones take part in the shuffles).  Returns the distance in all 16 lanes.
+template <bool L2>
+__device__ __forceinline__ float exact_dist_lane16(const float *__restrict__ row, const float *__restrict__ q,
+                                                   uint32_t Dp, uint32_t j, bool active) {
+  float acc = 0.f;
+  if (active) {
+    const float *r = row + j;
+    const float *y = q + j;
+    const uint32_t steps = Dp >> 4;
+    uint32_t s = 0;
+    for (; s + 8 <= steps; s += 8) {  // 8 independent loads in flight per operand before the dependent fma chain
+      float x[8], z[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        x[i] = r[(s + i) * 16];
+        z[i] = y[(s + i) * 16];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        if (L2) {
+          const float d = __fsub_rn(z[i], x[i]);
+          acc = __fmaf_rn(d, d, acc);
+        } else {
+          acc = __fmaf_rn(z[i], x[i], acc);
+        }
+      }
+    }
+    for (; s < steps; s++) {
+      const float x = r[s * 16], z = y[s * 16];
+      if (L2) {
+        const float d = __fsub_rn(z, x);
+        acc = __fmaf_rn(d, d, acc);
+      } else {
+        acc = __fmaf_rn(z, x, acc);
+      }
+    }
+  }
+  acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 8));
+  acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+  acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+  acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+  return L2 ? acc : (float)(1.0 - (double)acc);
+}
+
 }  // namespace vkgpu

@@ -353,9 +353,11 @@ void launch_flat_scan(int qt, bool l2, dim3 grid, size_t smem, cudaStream_t stre
 // K4: gather scan — exact kNN over an explicit list of rows per query (the pre-filter path,
 // VectorBase::AddPrefilteredKey src/indexes/vector_base.cc:509-530 driven by CalcBestMatchingPrefilteredKeys
 // src/query/search.cc:457-481).  grid = (query, slab); 128 threads.  Listed rows are pulled WHOLE into shared
-// memory, one cp.async.bulk (TMA engine) per row, double-buffered R rows at a time; 32 groups of 4 threads
-// compute the exact-order distances (exact_dist.cuh); top-k as in the tile kernel (threshold-gated append,
-// bitonic trim, topk_merge_kernel).  Rows padded to Dp*4+64 B so a quarter-warp's LDS.128 is conflict free.
+// memory, one cp.async.bulk (TMA engine) per row, through a ring of S stages of R = 8 rows: a stage is refilled
+// the moment it has been consumed, so S-1 stages (not half of a double buffer) are in flight — a random-row gather
+// is bound by bytes in flight per SM / HBM latency.  8 groups of 16 threads compute the exact-order distances
+// (exact_dist_lane16); top-k as in the tile kernel (threshold-gated append, bitonic trim, topk_merge_kernel).
+// Rows padded to Dp*4+64 B so that the two half-warps of a warp read disjoint bank halves.
 // ------------------------------------------------------------------------------------------------
 namespace {
 constexpr int GT = 128;
@@ -366,10 +368,11 @@ __global__ void __launch_bounds__(GT) gather_scan_kernel(const GatherParams p) {
   const uint32_t R = p.rows_per_stage, stride = p.Dp * 4 + 64, row_bytes = p.Dp * 4;
   float *q = reinterpret_cast<float *>(gsm);
   uint8_t *stage0 = gsm + ((p.Dp * 4 + 127) & ~127u);
-  Cand *scratch = reinterpret_cast<Cand *>(stage0 + (size_t)2 * R * stride);
-  uint64_t *full = reinterpret_cast<uint64_t *>(scratch + p.cap);  // [2]
-  uint32_t *sh = reinterpret_cast<uint32_t *>(full + 2);            // [0]=thr [1]=cnt
-  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, gi = tid >> 2, u = tid & 3;
+  const uint32_t S = p.stages;
+  Cand *scratch = reinterpret_cast<Cand *>(stage0 + (size_t)S * R * stride);
+  uint64_t *full = reinterpret_cast<uint64_t *>(scratch + p.cap);  // [S]
+  uint32_t *sh = reinterpret_cast<uint32_t *>(full + S);            // [0]=thr [1]=cnt
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t b = blockIdx.x, slab = blockIdx.y, slabs = gridDim.y;
   const uint32_t *ids = p.list_ptr[b];
   const uint64_t n = p.list_len[b];
@@ -377,8 +380,7 @@ __global__ void __launch_bounds__(GT) gather_scan_kernel(const GatherParams p) {
   Cand *my = p.ws + ((size_t)b * slabs + slab) * p.cap;
 
   if (tid == 0) {
-    mbar_init(&full[0], 1);
-    mbar_init(&full[1], 1);
+    for (uint32_t i = 0; i < S; i++) mbar_init(&full[i], 1);
     fence_mbar_init();
     sh[0] = kOrdInf;
     sh[1] = 0;
@@ -387,29 +389,36 @@ __global__ void __launch_bounds__(GT) gather_scan_kernel(const GatherParams p) {
     reinterpret_cast<float4 *>(q)[i] = reinterpret_cast<const float4 *>(p.Q + (size_t)b * p.Dp)[i];
   __syncthreads();
 
-  auto issue = [&](uint32_t tile, uint32_t st) {  // warp 0: one bulk copy per listed row of the tile
+  // warp 0: one bulk copy per listed row of the tile (R <= 32 rows: lane r copies row r).  The row id is loaded
+  // by `peek` one stage ahead of `issue`, so that its HBM round trip is not paid between the two barriers.
+  auto peek = [&](uint32_t tile) -> uint32_t {
+    const uint64_t r0 = (uint64_t)tile * R;
+    return (tile < tiles && r0 + lane < n && lane < R) ? ids[r0 + lane] : 0u;
+  };
+  auto issue = [&](uint32_t tile, uint32_t st, uint32_t row_id) {
     const uint64_t r0 = (uint64_t)tile * R;
     const uint32_t m = (uint32_t)min((uint64_t)R, n - r0);
     if (lane == 0) mbar_arrive_expect_tx(&full[st], m * row_bytes);
     __syncwarp();
-    for (uint32_t r = lane; r < m; r += 32)
-      bulk_g2s(stage0 + ((size_t)st * R + r) * stride, p.X + (size_t)ids[r0 + r] * p.Dp, row_bytes, &full[st]);
+    if (lane < m) bulk_g2s(stage0 + ((size_t)st * R + lane) * stride, p.X + (size_t)row_id * p.Dp, row_bytes, &full[st]);
   };
 
   uint32_t it = 0;
-  if (slab < tiles && warp == 0) issue(slab, 0);
+  if (warp == 0)
+    for (uint32_t i = 0; i < S; i++)
+      if (slab + i * slabs < tiles) issue(slab + i * slabs, i, peek(slab + i * slabs));
   for (uint32_t tile = slab; tile < tiles; tile += slabs, it++) {
-    const uint32_t st = it & 1;
-    if (warp == 0 && tile + slabs < tiles) issue(tile + slabs, st ^ 1);  // other buffer was released by the sync below
-    mbar_wait(&full[st], (it >> 1) & 1);
+    const uint32_t st = it % S;
+    const uint32_t refill_id = warp == 0 ? peek(tile + S * slabs) : 0u;
+    mbar_wait(&full[st], (it / S) & 1);
     const uint64_t r0 = (uint64_t)tile * R;
     const uint32_t m = (uint32_t)min((uint64_t)R, n - r0);
-    for (uint32_t rr = 0; rr < m; rr += GT / 4) {
-      const uint32_t r = rr + gi;
+    for (uint32_t rr = 0; rr < m; rr += GT / 16) {  // sixteen threads per row: see exact_dist_lane16
+      const uint32_t r = rr + (tid >> 4);
       const bool act = r < m;
-      const float d = exact_dist_group<L2, false>(
-          reinterpret_cast<const float *>(stage0 + ((size_t)st * R + (act ? r : 0)) * stride), q, p.Dp, u, act);
-      if (act && u == 0) {
+      const float d = exact_dist_lane16<L2>(
+          reinterpret_cast<const float *>(stage0 + ((size_t)st * R + (act ? r : 0)) * stride), q, p.Dp, tid & 15, act);
+      if (act && (tid & 15) == 0) {
         const uint32_t o = f32_to_ord(d);
         if (o <= sh[0]) {
           const uint32_t pos = atomicAdd(&sh[1], 1u);
@@ -424,6 +433,7 @@ __global__ void __launch_bounds__(GT) gather_scan_kernel(const GatherParams p) {
     }
     __syncthreads();  // tile consumed (buffer reusable), appends visible
     const uint32_t cntv = sh[1];
+    if (warp == 0 && tile + S * slabs < tiles) issue(tile + S * slabs, st, refill_id);  // refill the stage just consumed
     __syncthreads();  // everyone has read the count before anyone appends again
     if (cntv + R > p.cap) {  // uniform
       for (uint32_t i = tid; i < p.cap; i += GT) {
@@ -453,13 +463,109 @@ __global__ void __launch_bounds__(GT) gather_scan_kernel(const GatherParams p) {
 }
 }  // namespace
 
+// Variant without shared-memory staging: 64 groups of 4 threads per CTA, each group streams ITS row straight
+// from HBM with 16-byte loads (4 in flight per thread, exact_dist_group<.., ROW_GLOBAL>), many CTAs per SM.
+// One cp.async.bulk per 6 KB row keeps a single SM's copy engine at ~13-16 B/clk (the ring kernel above sits at
+// 0.59 of the HBM peak whatever its depth); two thousand threads with four loads each do not have that limit.
+namespace {
+constexpr int GLT = 256;
+template <bool L2>
+__global__ void __launch_bounds__(GLT) gather_scan_ldg_kernel(const GatherParams p) {
+  extern __shared__ __align__(128) uint8_t gsm[];
+  float *q = reinterpret_cast<float *>(gsm);
+  Cand *scratch = reinterpret_cast<Cand *>(gsm + ((p.Dp * 4 + 127) & ~127u));
+  uint32_t *sh = reinterpret_cast<uint32_t *>(scratch + p.cap);  // [0]=thr [1]=cnt
+  const uint32_t tid = threadIdx.x, gi = tid >> 2, u = tid & 3;
+  const uint32_t b = blockIdx.x, slab = blockIdx.y, slabs = gridDim.y;
+  const uint32_t *ids = p.list_ptr[b];
+  const uint64_t n = p.list_len[b];
+  constexpr uint32_t R = GLT / 4;
+  const uint32_t tiles = (uint32_t)((n + R - 1) / R);
+  Cand *my = p.ws + ((size_t)b * slabs + slab) * p.cap;
+  if (tid == 0) {
+    sh[0] = kOrdInf;
+    sh[1] = 0;
+  }
+  for (uint32_t i = tid; i < p.Dp / 4; i += GLT)
+    reinterpret_cast<float4 *>(q)[i] = reinterpret_cast<const float4 *>(p.Q + (size_t)b * p.Dp)[i];
+  __syncthreads();
+  uint32_t next_id = 0;
+  {
+    const uint64_t r = (uint64_t)slab * R + gi;
+    if (slab < tiles && r < n) next_id = ids[r];
+  }
+  for (uint32_t tile = slab; tile < tiles; tile += slabs) {
+    const uint64_t r = (uint64_t)tile * R + gi;
+    const bool act = r < n;
+    const uint32_t slot = next_id;
+    {  // the next tile's row id travels while this row is being read
+      const uint64_t rn = (uint64_t)(tile + slabs) * R + gi;
+      next_id = (tile + slabs < tiles && rn < n) ? ids[rn] : 0u;
+    }
+    const float d = exact_dist_group<L2, true>(p.X + (size_t)(act ? slot : 0) * p.Dp, q, p.Dp, u, act);
+    if (act && u == 0) {
+      const uint32_t o = f32_to_ord(d);
+      if (o <= sh[0]) {
+        const uint32_t pos = atomicAdd(&sh[1], 1u);
+        Cand cd;
+        cd.ord = o;
+        cd.slot = slot;
+        cd.label = p.labels[slot];
+        my[pos] = cd;  // pos < cap by the trim rule below
+      }
+    }
+    __syncthreads();
+    const uint32_t cntv = sh[1];
+    __syncthreads();
+    if (cntv + R > p.cap) {  // uniform
+      for (uint32_t i = tid; i < p.cap; i += GLT) {
+        Cand cd;
+        if (i < cntv) {
+          cd = my[i];
+        } else {
+          cd.ord = kOrdInf;
+          cd.slot = 0xffffffffu;
+          cd.label = ~0ull;
+        }
+        scratch[i] = cd;
+      }
+      __syncthreads();
+      bitonic_sort_cands(scratch, p.cap, tid, GLT, [] { __syncthreads(); });
+      const uint32_t keep = min(cntv, p.k);
+      for (uint32_t i = tid; i < keep; i += GLT) my[i] = scratch[i];
+      if (tid == 0) {
+        sh[1] = keep;
+        if (keep == p.k) sh[0] = scratch[p.k - 1].ord;
+      }
+      __syncthreads();
+    }
+  }
+  __syncthreads();
+  if (tid == 0) p.ws_cnt[(size_t)b * slabs + slab] = sh[1];
+}
+}  // namespace
+
+size_t gather_ldg_smem_bytes(uint32_t Dp, uint32_t cap) {
+  return ((size_t)(Dp * 4 + 127) & ~size_t(127)) + (size_t)cap * sizeof(Cand) + 64;
+}
+void launch_gather_scan_ldg(bool l2, dim3 grid, size_t smem, cudaStream_t stream, const GatherParams &p) {
+  if (l2)
+    gather_scan_ldg_kernel<true><<<grid, GLT, smem, stream>>>(p);
+  else
+    gather_scan_ldg_kernel<false><<<grid, GLT, smem, stream>>>(p);
+  VK_CUDA(cudaGetLastError());
+}
+
 void gather_scan_set_smem_attr(size_t max_smem) {
+  VK_CUDA(cudaFuncSetAttribute(gather_scan_ldg_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
+  VK_CUDA(cudaFuncSetAttribute(gather_scan_ldg_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
   VK_CUDA(cudaFuncSetAttribute(gather_scan_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
   VK_CUDA(cudaFuncSetAttribute(gather_scan_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)max_smem));
 }
 
-size_t gather_smem_bytes(uint32_t Dp, uint32_t rows_per_stage, uint32_t cap) {
-  return ((size_t)(Dp * 4 + 127) & ~size_t(127)) + (size_t)2 * rows_per_stage * (Dp * 4 + 64) + (size_t)cap * sizeof(Cand) + 64;
+size_t gather_smem_bytes(uint32_t Dp, uint32_t rows_per_stage, uint32_t stages, uint32_t cap) {
+  return ((size_t)(Dp * 4 + 127) & ~size_t(127)) + (size_t)stages * rows_per_stage * (Dp * 4 + 64) +
+         (size_t)cap * sizeof(Cand) + (size_t)stages * 8 + 64;
 }
 
 void launch_gather_scan(bool l2, dim3 grid, size_t smem, cudaStream_t stream, const GatherParams &p) {

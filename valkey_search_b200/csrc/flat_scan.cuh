@@ -55,13 +55,16 @@ struct GatherParams {
   const uint32_t *const *list_ptr;  // [B] device pointers: the slot list of each query
   const uint64_t *list_len;         // [B]
   const float *Q;            // zero-padded queries [B][Dp]
-  uint32_t Dp, k, cap, rows_per_stage;
+  uint32_t Dp, k, cap, rows_per_stage, stages;  // ring of `stages` buffers of rows_per_stage rows each
   Cand *ws;                  // [B][slabs][cap]
   uint32_t *ws_cnt;          // [B][slabs]
 };
 void gather_scan_set_smem_attr(size_t max_smem);
-size_t gather_smem_bytes(uint32_t Dp, uint32_t rows_per_stage, uint32_t cap);
+size_t gather_smem_bytes(uint32_t Dp, uint32_t rows_per_stage, uint32_t stages, uint32_t cap);
 void launch_gather_scan(bool metric_l2, dim3 grid, size_t smem, cudaStream_t stream, const GatherParams &p);
+// same contract, rows read straight from HBM by 4-thread groups (no staging); tile = 64 rows, cap >= k + 64
+size_t gather_ldg_smem_bytes(uint32_t Dp, uint32_t cap);
+void launch_gather_scan_ldg(bool metric_l2, dim3 grid, size_t smem, cudaStream_t stream, const GatherParams &p);
 
 // Per-query merge of `nlists` unsorted candidate lists into the ascending top-k.
 struct MergeParams {

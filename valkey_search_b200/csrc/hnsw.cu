@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(HT) hnsw_search_kernel(const HnswSearchParams 
   // ctl[0]=stop/changed  ctl[1]=current node  ctl[2]=count of ids in uvi
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t gi = tid >> 2, u = tid & 3;
   const uint32_t b = blockIdx.x;
   uint32_t *vis = p.visited + (size_t)b * p.vis_words;
   const uint8_t *allow = p.allow_ptr ? p.allow_ptr[b] : nullptr;
@@ -140,12 +139,14 @@ __global__ void __launch_bounds__(HT) hnsw_search_kernel(const HnswSearchParams 
       }
       mbar_wait(bar, parity);
       parity ^= 1;
-      for (uint32_t r0 = 0; r0 < m; r0 += HT / 4) {
-        const uint32_t r = r0 + gi;
+      // sixteen threads per row (thread = SIMD lane of the reference): a hop evaluates ~8 rows, so this keeps
+      // all 128 threads busy where four threads per row would leave three quarters of the CTA idle
+      for (uint32_t r0 = 0; r0 < m; r0 += HT / 16) {
+        const uint32_t r = r0 + (tid >> 4);
         const bool act = r < m;
-        const float d = exact_dist_group<L2, false>(reinterpret_cast<const float *>(stage + (act ? r : 0) * p.row_stride_bytes),
-                                                    q, g.Dp, u, act);
-        if (act && u == 0) uvd[base + r] = d;
+        const float d = exact_dist_lane16<L2>(reinterpret_cast<const float *>(stage + (act ? r : 0) * p.row_stride_bytes),
+                                              q, g.Dp, tid & 15, act);
+        if (act && (tid & 15) == 0) uvd[base + r] = d;
       }
       __syncthreads();
     }

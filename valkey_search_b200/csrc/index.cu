@@ -191,19 +191,32 @@ static void gather_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B,
                                  const uint32_t *const *d_list_ptr, const uint64_t *d_list_len, uint64_t n_rows) {
   VK_REQUIRE(k_eff >= 1 && k_eff <= kMaxFusedK, VKGPU_ERR_UNSUPPORTED,
              "k > 1024 is not implemented for pre-filtered searches yet");
-  // rows per stage: as many as fit twice while leaving room for 2 CTAs per SM
+  // ring geometry: stages of 8 rows (one pass of the 16-threads-per-row distance code), as many stages as fit —
+  // with 2 CTAs per SM when that still leaves each of them >= 4 stages, else 1 CTA per SM (wide rows)
   const uint32_t stride = ix->Dp * 4 + 64;
-  const size_t budget = (ix->smem_max + 1024) / 2 - 1024;
   uint32_t cap = 256;
   while (cap < k_eff + 32) cap <<= 1;
-  const size_t fixed = gather_smem_bytes(ix->Dp, 0, cap);
-  uint32_t R = fixed < budget ? (uint32_t)((budget - fixed) / (2 * (size_t)stride)) : 0;
-  if (R < 4) R = fixed < ix->smem_max ? (uint32_t)((ix->smem_max - fixed) / (2 * (size_t)stride)) : 0;
+  uint32_t R = 8;
+  const size_t fixed = gather_smem_bytes(ix->Dp, 0, 16, cap);
+  const size_t half = (ix->smem_max + 1024) / 2 - 1024;
+  uint32_t S = fixed < half ? (uint32_t)((half - fixed) / ((size_t)R * stride)) : 0;
+  if (S < 4) S = fixed < ix->smem_max ? (uint32_t)((ix->smem_max - fixed) / ((size_t)R * stride)) : 0;
+  while (S < 2 && R > 1) {  // very wide rows: fewer rows per stage
+    R >>= 1;
+    S = fixed < ix->smem_max ? (uint32_t)((ix->smem_max - fixed) / ((size_t)R * stride)) : 0;
+  }
+  S = std::min<uint32_t>(S, 16);
   R = std::min<uint32_t>(R, 32);
-  VK_REQUIRE(R >= 1, VKGPU_ERR_UNSUPPORTED, "vector too large for the gather staging buffer");
+  VK_REQUIRE(S >= 2, VKGPU_ERR_UNSUPPORTED, "vector too large for the gather staging buffer");
+  // Default: rows read straight from HBM by 4-thread groups (measured 0.89 of the HBM copy peak on 6 KB rows);
+  // VKGPU_GATHER_TMA=1 selects the bulk-copy ring kernel (0.59: one SM's copy engine moves ~14 B/clk on 1-D
+  // copies whatever the ring depth), kept to reproduce that measurement.
+  const bool use_ldg = getenv("VKGPU_GATHER_TMA") == nullptr;
+  if (use_ldg) R = 64;
   while (cap < k_eff + R) cap <<= 1;
   const uint32_t tiles = (uint32_t)std::max<uint64_t>(1, (n_rows + R - 1) / R);
-  uint32_t slabs = std::max<uint32_t>(1, std::min<uint32_t>(tiles, (4 * ix->num_sms + B - 1) / B));
+  // one wave of CTAs: 6 per SM for the load kernel (40 registers x 256 threads), 2-4 for the ring kernel
+  uint32_t slabs = std::max<uint32_t>(1, std::min<uint32_t>(tiles, ((use_ldg ? 6 : 4) * ix->num_sms + B - 1) / B));
   const size_t nlists = (size_t)B * slabs;
   c->ws.reserve(nlists * cap * sizeof(Cand));
   c->ws_cnt.reserve(nlists * sizeof(uint32_t));
@@ -221,10 +234,14 @@ static void gather_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B,
   gp.k = k_eff;
   gp.cap = cap;
   gp.rows_per_stage = R;
+  gp.stages = S;
   gp.ws = c->ws.as<Cand>();
   gp.ws_cnt = c->ws_cnt.as<uint32_t>();
   ix->prof_begin(c, KK_SCAN);
-  launch_gather_scan(ix->metric_l2, dim3(B, slabs), gather_smem_bytes(ix->Dp, R, cap), c->cur, gp);
+  if (use_ldg)
+    launch_gather_scan_ldg(ix->metric_l2, dim3(B, slabs), gather_ldg_smem_bytes(ix->Dp, cap), c->cur, gp);
+  else
+    launch_gather_scan(ix->metric_l2, dim3(B, slabs), gather_smem_bytes(ix->Dp, R, S, cap), c->cur, gp);
   ix->prof_end(c, KK_SCAN);
   MergeParams mp{};
   mp.ws = gp.ws;
