@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t n = min(cnt[c], p.cap);
       // window: the last <= 64 entries; during the first tiles (gates still open, lists mostly unfiltered rows)
       // the last <= 256 in four passes, so that the very first bounds already sit near the slab's true j-th best
-      const uint32_t win = t <= 16 ? 256u : 64u;
+      const uint32_t win = t <= 2 ? 256u : (t <= 16 ? 128u : 64u);
       const uint32_t first = n > win ? (n - win + 3) & ~3u : 0u;  // 16-byte aligned
       const uint32_t *src = my_ord + (size_t)c * p.cap;
       uint32_t g[32];
@@ -489,12 +489,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #ifdef VKGPU_TENSOR_TRACE
       if (blockIdx.x == 5 && t < 4096 && m) atomicAdd(&g_apt[t], __popc(m));
 #endif
-      // Slow path, lane-parallel: every lane walks ITS OWN passing columns (usually one), picks the score out of
-      // the register tile with a 5-level select tree (no dynamic register indexing, no TMEM re-read), reserves a
-      // list position with one shared-memory atomic and stores the candidate.  Order inside a list is irrelevant.
-      while (m) {
-        const uint32_t j = __ffs(m) - 1;
-        m &= m - 1;
+      // score of column j out of the register tile: a 5-level select tree (no dynamic register indexing, no
+      // TMEM re-read)
+      auto pick = [&](uint32_t j) -> float {
         uint32_t s16[16], s8[8], s4[4];
 #pragma unroll
         for (int i = 0; i < 16; i++) s16[i] = (j & 1u) ? r[2 * i + 1] : r[2 * i];
@@ -503,20 +500,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
         for (int i = 0; i < 4; i++) s4[i] = (j & 4u) ? s8[2 * i + 1] : s8[2 * i];
         const uint32_t s2a = (j & 8u) ? s4[1] : s4[0], s2b = (j & 8u) ? s4[3] : s4[2];
-        const float dot = __uint_as_float((j & 16u) ? s2b : s2a);
-        const uint32_t c = c0 + j;
-        const uint32_t base = atomicAdd(&cnt[c], 1u);
-        if (base + 1 + 2 * BM > p.cap) {  // ask for a trim at the rendezvous of tile t+2
-          atomicOr(&need[(c & 3) * 2 + (c >> 7)], 1u << ((c >> 2) & 31));
-          atomicMin(sync_tile, t + 2);
-        }
+        return __uint_as_float((j & 16u) ? s2b : s2a);
+      };
+      auto put = [&](uint32_t c, uint32_t pos, float dot) {
         const float sc = p.metric_l2 ? __fmaf_rn(-2.0f, dot, xn) : -dot;
         Cand cd;
         cd.ord = f32_to_ord(sc);
         cd.slot = (uint32_t)slot;
         cd.label = slot;
-        my_ws[(size_t)c * p.cap + base] = cd;  // base < cap: see the trim rendezvous in the tile loop
-        my_ord[(size_t)c * p.cap + base] = cd.ord;
+        my_ws[(size_t)c * p.cap + pos] = cd;  // pos < cap: see the trim rendezvous in the tile loop
+        my_ord[(size_t)c * p.cap + pos] = cd.ord;
+      };
+      auto ask_trim = [&](uint32_t c) {  // at the rendezvous of tile t+2
+        atomicOr(&need[(c & 3) * 2 + (c >> 7)], 1u << ((c >> 2) & 31));
+        atomicMin(sync_tile, t + 2);
+      };
+      if (__reduce_max_sync(0xffffffffu, __popc(m)) >= 24) {
+        // Dense chunk (the first tiles, while the gates are still open: every row passes every query): walk the
+        // COLUMNS, one warp-aggregated reservation per column.  The lane-parallel walk below would have all 32
+        // lanes hit the same counter in every iteration — 32-way serialised shared-memory atomics, 35 us per tile.
+        uint32_t any = __reduce_or_sync(0xffffffffu, m);
+#pragma unroll 1
+        while (any) {
+          const uint32_t j = __ffs(any) - 1;
+          any &= any - 1;
+          const bool pass = (m >> j) & 1u;
+          const uint32_t bal = __ballot_sync(0xffffffffu, pass);
+          const uint32_t npass = __popc(bal), c = c0 + j;
+          uint32_t base = 0;
+          if (lane == 0) {
+            base = atomicAdd(&cnt[c], npass);
+            if (base + npass + 2 * BM > p.cap) ask_trim(c);
+          }
+          base = __shfl_sync(0xffffffffu, base, 0);
+          const float dot = pick(j);
+          if (pass) put(c, base + __popc(bal & ((1u << lane) - 1)), dot);
+        }
+        return;
+      }
+      // Sparse chunk, lane-parallel: every lane walks ITS OWN passing columns (usually one), reserves a list
+      // position with one shared-memory atomic and stores the candidate.  Order inside a list is irrelevant.
+      while (m) {
+        const uint32_t j = __ffs(m) - 1;
+        m &= m - 1;
+        const float dot = pick(j);
+        const uint32_t c = c0 + j;
+        const uint32_t base = atomicAdd(&cnt[c], 1u);
+        if (base + 1 + 2 * BM > p.cap) ask_trim(c);
+        put(c, base, dot);
       }
     };
 
@@ -526,7 +557,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       // ever tighten, so a warp that still gates on the previous value merely keeps a few more candidates.
       // thrf[c] is written here by warp 4 + (c & 7) and, inside a rendezvous, by the trimming owner 4 + (c & 3).
       const uint32_t tp1 = t - 1, tp3 = tp1 / 3;  // a publish round ran before tile t-1: every slab has published by now
-      const bool after_pub = t > 1 && ((tp1 & (tp1 - 1)) == 0 || (tp3 * 3 == tp1 && (tp3 & (tp3 - 1)) == 0));
+      const bool after_pub = t > 1 && ((tp1 & (tp1 - 1)) == 0 || (tp1 >= 24 && tp3 * 3 == tp1 && (tp3 & (tp3 - 1)) == 0));
       if ((after_pub || (t < 64 && (t & 7) == 0) || (t & 31) == 0)) {
         // one thread per query (c = warp-4 + 8*lane): the per-slab bounds of a query are contiguous, the lane
         // reads them with 16-byte loads, eight in flight, so a refresh is one or two L2 round trips per warp
@@ -571,7 +602,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       {
         const bool do_trim = *reinterpret_cast<volatile uint32_t *>(sync_tile) <= t;
         const uint32_t t3 = t / 3;
-        const bool do_pub = t > 0 && ((t & (t - 1)) == 0 || (t3 * 3 == t && (t3 & (t3 - 1)) == 0));
+        const bool do_pub = t > 0 && ((t & (t - 1)) == 0 || (t >= 24 && t3 * 3 == t && (t3 & (t3 - 1)) == 0));
         if (do_trim || do_pub) {
           named_bar_sync(2, EPI_THREADS);  // every warp has finished tile t-1: no append is in flight
           if (do_trim) {
