@@ -13,7 +13,8 @@ def _bits(a):
 
 
 @pytest.mark.parametrize("metric,N,D,B,k", [("L2", 200_000, 768, 300, 100), ("IP", 150_000, 128, 70, 10),
-                                             ("L2", 50_000, 100, 257, 37), ("COSINE", 60_000, 256, 64, 100)])
+                                             ("L2", 50_000, 100, 257, 37), ("COSINE", 60_000, 256, 64, 100),
+                                             ("L2", 120_000, 768, 17, 100), ("IP", 300_000, 64, 2, 10)])
 def test_tensor_path_equals_exact_path(built, metric, N, D, B, k):
     import valkey_search_b200 as V
     rng = np.random.default_rng(N + D + B)

@@ -649,37 +649,29 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
   extern __shared__ __align__(16) uint8_t msm[];
   Cand *buf = reinterpret_cast<Cand *>(msm);                                   // [sort_n]
   uint32_t *hist = reinterpret_cast<uint32_t *>(msm + (size_t)p.sort_n * sizeof(Cand));  // [2048]
+  uint32_t *s_cnt = hist + 2048;                                               // [slabs]
   __shared__ uint32_t part[MERGE_THREADS];
   __shared__ uint32_t s_prefix, s_rank, s_pos, s_tie, s_total;
-  const uint32_t b = blockIdx.x, tid = threadIdx.x;
+  const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t qtile = b / p.qt, qi = b % p.qt;
   const uint32_t K = p.k;
-  auto list_of = [&](uint32_t s, uint32_t &n) -> const Cand * {
-    const size_t li = ((size_t)qtile * p.slabs + s) * p.qt + qi;
-    n = min(p.ws_cnt[li], p.cap);
-    return p.ws + li * p.cap;
-  };
-  // score of entry i of a list: from the compact score-only copy when the producer keeps one (4-byte stride
-  // instead of 16: the three histogram passes and the keep decision read nothing else)
-  auto ord_of = [&](const Cand *src, uint32_t i) -> uint32_t {
-    return p.ws_ord ? p.ws_ord[(size_t)(src - p.ws) + i] : src[i].ord;
-  };
-  if (tid == 0) s_total = 0;
-  __syncthreads();
-  {
-    uint32_t tot = 0;
-    for (uint32_t s = tid; s < p.slabs; s += MERGE_THREADS) {
-      uint32_t n;
-      list_of(s, n);
-      tot += n;
-    }
-    if (tot) atomicAdd(&s_total, tot);
-  }
+  auto list_index = [&](uint32_t s) -> size_t { return ((size_t)qtile * p.slabs + s) * p.qt + qi; };
   if (tid == 0) {
+    s_total = 0;
     s_prefix = 0;
     s_rank = K;
     s_pos = 0;
     s_tie = 0;
+  }
+  __syncthreads();
+  {  // list lengths -> shared memory (all loads in flight at once), total
+    uint32_t tot = 0;
+    for (uint32_t s = tid; s < p.slabs; s += MERGE_THREADS) {
+      const uint32_t n = min(p.ws_cnt[list_index(s)], p.cap);
+      s_cnt[s] = n;
+      tot += n;
+    }
+    if (tot) atomicAdd(&s_total, tot);
   }
   for (uint32_t i = tid; i < p.sort_n; i += MERGE_THREADS) {
     buf[i].ord = kOrdInf;
@@ -688,6 +680,29 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
   }
   __syncthreads();
   const uint32_t total = s_total;
+  // Visit every entry of every list of this query: one WARP per list, four independent loads in flight per lane.
+  // (With one query per CTA and up to 148 lists, walking the lists one after the other with the whole CTA made
+  // the merge a chain of dependent round trips: 0.45 ms for a 2-query batch.)  Scores come from the compact
+  // score-only copy when the producer keeps one (4-byte stride instead of 16).
+  auto for_each_score = [&](auto fn) {
+    for (uint32_t s = warp; s < p.slabs; s += MERGE_THREADS / 32) {
+      const uint32_t n = s_cnt[s];
+      const size_t base = list_index(s) * p.cap;
+      for (uint32_t i0 = lane; i0 < n; i0 += 128) {
+        uint32_t o[4];
+#pragma unroll
+        for (int u2 = 0; u2 < 4; u2++) {
+          const uint32_t i = i0 + 32 * u2;
+          o[u2] = i < n ? (p.ws_ord ? p.ws_ord[base + i] : p.ws[base + i].ord) : 0u;
+        }
+#pragma unroll
+        for (int u2 = 0; u2 < 4; u2++) {
+          const uint32_t i = i0 + 32 * u2;
+          if (i < n) fn(base + i, o[u2]);
+        }
+      }
+    }
+  };
   uint32_t T = kOrdInf, quota = 0;
   if (total > K) {
     const int shifts[3] = {21, 10, 0};
@@ -697,14 +712,11 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
       __syncthreads();
       const uint32_t prefix = s_prefix;
       const uint32_t hi_mask = pass == 0 ? 0u : ~((1u << (shifts[pass] + widths[pass])) - 1u);
-      for (uint32_t s = 0; s < p.slabs; s++) {
-        uint32_t n;
-        const Cand *src = list_of(s, n);
-        for (uint32_t i = tid; i < n; i += MERGE_THREADS) {
-          const uint32_t o = ord_of(src, i);
-          if ((o & hi_mask) == prefix) atomicAdd(&hist[(o >> shifts[pass]) & ((1u << widths[pass]) - 1u)], 1u);
-        }
-      }
+      const int sh = shifts[pass];
+      const uint32_t wmask = (1u << widths[pass]) - 1u;
+      for_each_score([&](size_t, uint32_t o) {
+        if ((o & hi_mask) == prefix) atomicAdd(&hist[(o >> sh) & wmask], 1u);
+      });
       __syncthreads();
       uint32_t sum = 0;
       for (uint32_t i = 0; i < 8; i++) sum += hist[tid * 8 + i];
@@ -729,17 +741,12 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
     T = s_prefix;
     quota = s_rank;  // entries equal to T still needed
   }
-  for (uint32_t s = 0; s < p.slabs; s++) {
-    uint32_t n;
-    const Cand *src = list_of(s, n);
-    for (uint32_t i = tid; i < n; i += MERGE_THREADS) {
-      const uint32_t o = ord_of(src, i);
-      bool keep = o < T;
-      if (!keep && o == T && total > K) keep = atomicAdd(&s_tie, 1u) < quota;
-      if (total <= K) keep = true;
-      if (keep) buf[atomicAdd(&s_pos, 1u)] = src[i];
-    }
-  }
+  for_each_score([&](size_t at, uint32_t o) {
+    bool keep = o < T;
+    if (!keep && o == T && total > K) keep = atomicAdd(&s_tie, 1u) < quota;
+    if (total <= K) keep = true;
+    if (keep) buf[atomicAdd(&s_pos, 1u)] = p.ws[at];
+  });
   __syncthreads();
   const uint32_t have = min(s_pos, K);
   bitonic_sort_cands(buf, p.sort_n, tid, MERGE_THREADS, [] { __syncthreads(); });
@@ -754,7 +761,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
 }  // namespace
 
 void launch_topk_select_merge(uint32_t B, cudaStream_t stream, const MergeParams &p) {
-  const size_t smem = (size_t)p.sort_n * sizeof(Cand) + 2048 * 4;
+  const size_t smem = (size_t)p.sort_n * sizeof(Cand) + 2048 * 4 + (size_t)p.slabs * 4;
   topk_select_merge_kernel<<<B, MERGE_THREADS, smem, stream>>>(p);
   VK_CUDA(cudaGetLastError());
 }

@@ -46,18 +46,19 @@ void make_tensor_map_2d(CUtensorMap *out, CUtensorMapDataType dt, uint32_t elem_
 namespace {
 
 constexpr int BM = 128;        // corpus rows per tile  (UMMA M)
-constexpr int BN = 256;        // queries per tile      (UMMA N)
+constexpr int BN = 256;        // queries per tile      (UMMA N); the kernel also exists with 64 for small batches
+constexpr int BN_SMALL = 64;   // a tile of 64 queries makes the pass HBM-bound on the bf16 mirror instead of MMA-bound
 constexpr int BK = 64;         // bf16 elements per stage = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
 constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 // Per-CTA ring geometry.  PAIR = the two CTAs of a cluster drive ONE tcgen05.mma.cta_group::2 (UMMA M = 256:
 // each CTA supplies its own 128 corpus rows and HALF of the 256-query operand), which cuts the L2->SM operand
 // stream per FLOP by a third: 32 KB instead of 48 KB per 64-wide K step and 128x256 accumulator.
-template <bool PAIR>
+template <bool PAIR, int BN_ = BN>
 struct Ring {
-  static constexpr int kBRows = PAIR ? BN / 2 : BN;          // query rows this CTA stages per K step
-  static constexpr int kBStage = kBRows * BK * 2;            // 16 KB / 32 KB
-  static constexpr int kStages = PAIR ? 6 : 4;               // 192 KB either way
+  static constexpr int kBRows = PAIR ? BN_ / 2 : BN_;        // query rows this CTA stages per K step
+  static constexpr int kBStage = kBRows * BK * 2;            // 16 KB / 32 KB (8 KB for 64-query tiles)
+  static constexpr int kStages = 192 * 1024 / (A_STAGE_BYTES + kBStage);  // 4, 6 or 8 stages: 192 KB either way
   static constexpr int kBytes = kStages * (A_STAGE_BYTES + kBStage);
 };
 constexpr int TC_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
@@ -203,11 +204,13 @@ __device__ __forceinline__ unsigned long long gtime() {
   } while (0)
 #endif
 // ---------------------------------------------------------------- the candidate kernel
-template <bool PAIR>
+template <bool PAIR, int BN_>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     flat_tensor_kernel(const TensorParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
-  constexpr int STAGES = Ring<PAIR>::kStages;
-  constexpr int B_STAGE_BYTES = Ring<PAIR>::kBStage;
+  constexpr int BN = BN_;  // shadows the namespace-level default: everything below is per instantiation
+  static_assert(BN % 64 == 0 && BN <= 256, "two column halves of whole 32-column chunks");
+  constexpr int STAGES = Ring<PAIR, BN_>::kStages;
+  constexpr int B_STAGE_BYTES = Ring<PAIR, BN_>::kBStage;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t *sA = smem;                                   // [STAGES][16 KB]
   uint8_t *sB = smem + STAGES * A_STAGE_BYTES;          // [STAGES][32 KB | 16 KB]
@@ -419,6 +422,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     auto warp_publish_all = [&]() {
       if (p.jrank > 32) return;
       const uint32_t c = (warp - 4) + 8 * lane;
+      if (c >= (uint32_t)BN) return;  // 64-query tiles: eight lanes per warp have a query
       const uint32_t n = min(cnt[c], p.cap);
       // window: the last <= 64 entries; during the first tiles (gates still open, lists mostly unfiltered rows)
       // the last <= 256 in four passes, so that the very first bounds already sit near the slab's true j-th best
@@ -559,28 +563,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t tp1 = t - 1, tp3 = tp1 / 3;  // a publish round ran before tile t-1: every slab has published by now
       const bool after_pub = t > 1 && ((tp1 & (tp1 - 1)) == 0 || (tp1 >= 24 && tp3 * 3 == tp1 && (tp3 & (tp3 - 1)) == 0));
       if ((after_pub || (t < 64 && (t & 7) == 0) || (t & 31) == 0)) {
-        // one thread per query (c = warp-4 + 8*lane): the per-slab bounds of a query are contiguous, the lane
-        // reads them with 16-byte loads, eight in flight, so a refresh is one or two L2 round trips per warp
-        const uint32_t my_c = (warp - 4) + 8 * lane;
+        // 256/BN threads per query (consecutive lanes): the per-slab bounds of a query are contiguous, each thread
+        // reads its share with 16-byte loads, eight in flight, so a refresh is one or two L2 round trips
+        constexpr uint32_t T = EPI_THREADS / BN;  // 1 (256-query tiles) or 4 (64-query tiles, up to 148 slabs)
+        const uint32_t e = tid - 128, my_c = e / T, part = e % T;
         const uint4 *gs = reinterpret_cast<const uint4 *>(p.gsl + ((size_t)qtile * BN + my_c) * p.gsl_stride);
         uint32_t go = __ldcg(&p.gthr[qtile * BN + my_c]);
         uint32_t mx = 0;
-        for (uint32_t s0 = 0; s0 < p.slabs; s0 += 32) {
+        for (uint32_t s0 = 4 * part; s0 < p.slabs; s0 += 32 * T) {
           uint4 v[8];
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             v[i] = make_uint4(0, 0, 0, 0);
-            if (s0 + 4 * i < p.slabs) v[i] = __ldcg(gs + (s0 >> 2) + i);
+            if (s0 + 4 * T * i < p.slabs) v[i] = __ldcg(gs + (s0 >> 2) + T * i);
           }
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            const uint32_t sb = s0 + 4 * i;  // entries past p.slabs are padding
+            const uint32_t sb = s0 + 4 * T * i;  // entries past p.slabs are padding
             mx = max(mx, max(max(sb < p.slabs ? v[i].x : 0u, sb + 1 < p.slabs ? v[i].y : 0u),
                              max(sb + 2 < p.slabs ? v[i].z : 0u, sb + 3 < p.slabs ? v[i].w : 0u)));
           }
         }
+        if (T > 1) {
+          mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+          mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        }
         go = min(go, mx);
-        if (go != kOrdInf) thrf[my_c] = fminf(thrf[my_c], ord_to_f32(go));
+        if (part == 0 && go != kOrdInf) thrf[my_c] = fminf(thrf[my_c], ord_to_f32(go));
       }
 
       const uint32_t a = t & 1;
@@ -777,14 +786,15 @@ bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
 }
 // AUTO policy: a two-line cost model fitted to B200 measurements at 768 dims (both paths scale with rows x dims).
 // The exact scan streams the fp32 corpus once per 8 queries: 4.4 ms per 10M rows for one query, 8 ms per pass at
-// 8 queries per pass.  One tensor pass over the bf16 mirror costs the same for 1..256 queries: 3.2-4.4 ms per 10M
-// rows plus ~0.5 ms of start-up, merge and re-rank.  Measured at 10M x 768: batch 8 -> 8.6 ms exact vs 5.1 ms
-// tensor; batch 32 -> 31.8 vs 5.1; batch 1 is a tie, and small corpora stay on the exact scan.
+// 8 queries per pass.  One tensor pass over the bf16 mirror costs 2.4 ms per 10M rows for up to 64 queries (the
+// 64-query tile runs at the HBM rate of the mirror, which is half the bytes of the fp32 corpus) and 3.2-4.4 ms per
+// 256 queries beyond that, plus ~0.7 ms of start-up, merge and re-rank.  Measured at 10M x 768: one query 5.1 ms
+// exact vs 3.1 ms tensor; batch 32 -> 31.8 vs 3.1; small corpora stay on the exact scan.
 bool tensor_path_cheaper(const vkgpu_index_impl *ix, uint32_t B) {
-  if (B < 2 || ix->n < 100000) return false;
+  if (ix->n < 100000) return false;
   const double unit = (double)ix->n * ix->Dp / (1e7 * 768.0);
-  const double exact_ms = B >= 8 ? std::ceil(B / 8.0) * 8.0 * unit : (4.4 + 0.5 * (B - 1)) * unit;
-  const double tensor_ms = 0.5 + std::ceil(B / 256.0) * 4.0 * unit;
+  const double exact_ms = 0.3 + (B >= 8 ? std::ceil(B / 8.0) * 8.0 : 4.4 + 0.5 * (B - 1)) * unit;
+  const double tensor_ms = 0.7 + (B <= (uint32_t)BN_SMALL ? 2.4 : std::ceil(B / 256.0) * 3.4) * unit;
   return tensor_ms < exact_ms;
 }
 
@@ -828,8 +838,9 @@ void tensor_prepare(vkgpu_index_impl *ix) {
   ix->dNorm.reserve(rows * 4);
   tensor_refresh_rows(ix, 0, ix->n);
   VK_CUDA(cudaStreamSynchronize(ix->mut_stream));
-  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<true, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
   VK_CUDA(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   VK_CUDA(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
   ix->tensor_ready = true;
@@ -857,8 +868,11 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   TensorState *t = ts(ix);
   cudaStream_t s = c->cur;
   const uint32_t Dh = t->Dh;
-  const uint32_t nq_tiles = (B + BN - 1) / BN;
-  const uint32_t Bpad = nq_tiles * BN;
+  // 64-query tiles for small batches: a quarter of the MMA work per corpus tile, so the pass runs at the HBM
+  // rate of the bf16 mirror instead of the tensor rate (the module's reader pool forms batches of this size)
+  const uint32_t bn = B <= (uint32_t)BN_SMALL ? BN_SMALL : BN;
+  const uint32_t nq_tiles = (B + bn - 1) / bn;
+  const uint32_t Bpad = nq_tiles * bn;
   const uint32_t kprime = (3 * k_eff + 64 + 127) / 128 * 128;  // survivors per query (k + margin)
   const uint32_t cap = 1024;  // 32 keys per lane in the warp-level shrink
   const uint32_t total_tiles = (uint32_t)((ix->n + BM - 1) / BM);
@@ -870,7 +884,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
     const char *e = getenv("VKGPU_TENSOR_PAIR");
     return e && e[0] == '1';
   }();
-  const bool pair = pair_env && total_tiles >= 2 && ix->num_sms / 2 >= nq_tiles;
+  const bool pair = pair_env && bn == (uint32_t)BN && total_tiles >= 2 && ix->num_sms / 2 >= nq_tiles;
   uint32_t slabs;  // CTA-level corpus slabs per query tile
   if (pair) {
     const uint32_t pslabs = std::min<uint32_t>(std::max<uint32_t>(1, (ix->num_sms / 2) / nq_tiles), (total_tiles + 1) / 2);
@@ -889,7 +903,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
                                                                         c->scratch1.as<float>(), 0, B, nullptr);
   VK_CUDA(cudaGetLastError());
 
-  const size_t nlists = (size_t)nq_tiles * slabs * BN;
+  const size_t nlists = (size_t)nq_tiles * slabs * bn;
   c->ws.reserve(nlists * cap * (sizeof(Cand) + 4));
   c->ws_cnt.reserve(nlists * 4);
   const uint32_t gsl_stride = (slabs + 3) & ~3u, flags_pad = (B + 3) & ~3u;
@@ -902,7 +916,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   make_tensor_map_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, ix->dXh.p, Dh, ix->n, (uint64_t)Dh * 2, BK, BM,
                      CU_TENSOR_MAP_SWIZZLE_128B);
   make_tensor_map_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, c->scratch0.p, Dh, Bpad, (uint64_t)Dh * 2, BK,
-                     pair ? BN / 2 : BN, CU_TENSOR_MAP_SWIZZLE_128B);
+                     pair ? BN / 2 : bn, CU_TENSOR_MAP_SWIZZLE_128B);
 
   TensorParams tp{};
   tp.xnorm = ix->dNorm.as<float>();
@@ -920,7 +934,8 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   tp.gsl_stride = gsl_stride;
   tp.jrank = (kprime + slabs - 1) / slabs;
   tp.metric_l2 = ix->metric_l2 ? 1 : 0;
-  static_assert(Ring<true>::kBytes == Ring<false>::kBytes, "both ring geometries use the same shared memory");
+  static_assert(Ring<true>::kBytes == Ring<false>::kBytes && Ring<false, BN_SMALL>::kBytes == Ring<false>::kBytes,
+                "all ring geometries use the same shared memory");
   const size_t smem = (size_t)Ring<true>::kBytes + (size_t)4 * kprime * sizeof(Cand) + 256 + BN * 8 + 64;
   VK_REQUIRE(smem <= ix->smem_max, VKGPU_ERR_INTERNAL, "tensor kernel shared memory budget exceeded");
   ix->prof_begin(c, KK_TENSOR);
@@ -937,9 +952,11 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    VK_CUDA(cudaLaunchKernelEx(&cfg, flat_tensor_kernel<true>, tp, tmA, tmB));
+    VK_CUDA(cudaLaunchKernelEx(&cfg, flat_tensor_kernel<true, BN>, tp, tmA, tmB));
+  } else if (bn == (uint32_t)BN) {
+    flat_tensor_kernel<false, BN><<<nq_tiles * slabs, TC_THREADS, smem, s>>>(tp, tmA, tmB);
   } else {
-    flat_tensor_kernel<false><<<nq_tiles * slabs, TC_THREADS, smem, s>>>(tp, tmA, tmB);
+    flat_tensor_kernel<false, BN_SMALL><<<nq_tiles * slabs, TC_THREADS, smem, s>>>(tp, tmA, tmB);
   }
   VK_CUDA(cudaGetLastError());
   ix->prof_end(c, KK_TENSOR);
@@ -982,7 +999,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   MergeParams mp{};
   mp.ws = tp.ws;
   mp.ws_cnt = tp.ws_cnt;
-  mp.qt = BN;
+  mp.qt = bn;
   mp.slabs = slabs;
   mp.cap = cap;
   mp.k = kprime;
@@ -1032,7 +1049,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   VK_CUDA(cudaGetLastError());
   ix->prof_end(c, KK_RERANK);
   ix->kernels += 4;  // query conversion, candidate pass, merge, re-rank
-  ix->last_qt = BN;
+  ix->last_qt = bn;
   ix->last_passes = nq_tiles;
 
   // queries whose margin was too thin are re-run on the exact scan (GPU), results patched in place
