@@ -16,7 +16,7 @@ __device__ __forceinline__ float4 ldrow(const float4 *p) {
 // `u` = lane & 3 inside the group (all 4 lanes of the group must call, with `active` uniform in the
 // group; inactive groups still take part in the shuffles).  q may be global or shared; Dp % 16 == 0 and
 // both pointers are 16-B aligned.  Returns the distance in all 4 lanes.
-template <bool L2, bool ROW_GLOBAL = true>
+template <bool L2, bool ROW_GLOBAL = true, int UNR = 4>
 __device__ __forceinline__ float exact_dist_group(const float *__restrict__ row, const float *__restrict__ q,
                                                   uint32_t Dp, uint32_t u, bool active) {
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -25,11 +25,6 @@ __device__ __forceinline__ float exact_dist_group(const float *__restrict__ row,
     const float4 *q4 = reinterpret_cast<const float4 *>(q) + u;
     const uint32_t steps = Dp >> 4;
     uint32_t s = 0;
-    // 4 independent 16-B loads in flight per thread before the dependent fma chain consumes them
-    for (; s + 4 <= steps; s += 4) {
-      float4 x0 = ldrow<ROW_GLOBAL>(r4 + (s + 0) * 4), x1 = ldrow<ROW_GLOBAL>(r4 + (s + 1) * 4);
-      float4 x2 = ldrow<ROW_GLOBAL>(r4 + (s + 2) * 4), x3 = ldrow<ROW_GLOBAL>(r4 + (s + 3) * 4);
-      float4 y0 = q4[(s + 0) * 4], y1 = q4[(s + 1) * 4], y2 = q4[(s + 2) * 4], y3 = q4[(s + 3) * 4];
 #define VK_STEP(X, Y)                                                                 \
   if (L2) {                                                                           \
     float d;                                                                          \
@@ -41,7 +36,17 @@ __device__ __forceinline__ float exact_dist_group(const float *__restrict__ row,
     acc.x = __fmaf_rn(Y.x, X.x, acc.x); acc.y = __fmaf_rn(Y.y, X.y, acc.y);           \
     acc.z = __fmaf_rn(Y.z, X.z, acc.z); acc.w = __fmaf_rn(Y.w, X.w, acc.w);           \
   }
-      VK_STEP(x0, y0) VK_STEP(x1, y1) VK_STEP(x2, y2) VK_STEP(x3, y3)
+    // UNR independent 16-B row loads in flight per thread before the dependent fma chain consumes them (a row
+    // streamed from HBM is a chain of round trips otherwise: UNR = 8 where the caller has few threads per row set)
+    for (; s + UNR <= steps; s += UNR) {
+      float4 x[UNR];
+#pragma unroll
+      for (int i = 0; i < UNR; i++) x[i] = ldrow<ROW_GLOBAL>(r4 + (s + i) * 4);
+#pragma unroll
+      for (int i = 0; i < UNR; i++) {
+        const float4 y = q4[(s + i) * 4];
+        VK_STEP(x[i], y)
+      }
     }
     for (; s < steps; s++) {
       float4 x0 = ldrow<ROW_GLOBAL>(r4 + s * 4);

@@ -721,26 +721,27 @@ struct RerankParams {
   uint32_t *flags;           // [B]: 1 => margin too thin, re-run on the exact scan
 };
 
+constexpr int RR_THREADS = 256;  // 64 groups of 4 threads: 64 candidate rows in flight per query
 template <bool L2>
-__global__ void __launch_bounds__(128) rerank_kernel(const RerankParams p) {
+__global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankParams p) {
   extern __shared__ __align__(16) uint8_t rsm[];
   Cand *buf = reinterpret_cast<Cand *>(rsm);                       // [sort_n]
   float *q = reinterpret_cast<float *>(rsm + (size_t)p.sort_n * sizeof(Cand));  // [Dp]
   const uint32_t b = blockIdx.x, tid = threadIdx.x, gi = tid >> 2, u = tid & 3;
   const uint32_t n = min(p.napprox[b], p.kprime);
-  for (uint32_t i = tid; i < p.Dp / 4; i += 128)
+  for (uint32_t i = tid; i < p.Dp / 4; i += RR_THREADS)
     reinterpret_cast<float4 *>(q)[i] = reinterpret_cast<const float4 *>(p.Q + (size_t)b * p.Dp)[i];
-  for (uint32_t i = tid; i < p.sort_n; i += 128) {
+  for (uint32_t i = tid; i < p.sort_n; i += RR_THREADS) {
     buf[i].ord = kOrdInf;
     buf[i].slot = 0xffffffffu;
     buf[i].label = ~0ull;
   }
   __syncthreads();
-  for (uint32_t j0 = 0; j0 < n; j0 += 32) {
+  for (uint32_t j0 = 0; j0 < n; j0 += RR_THREADS / 4) {
     const uint32_t j = j0 + gi;
     const bool act = j < n;
     const uint32_t slot = act ? p.slots[(size_t)b * p.kprime + j] : 0;
-    const float d = exact_dist_group<L2, true>(p.X + (size_t)slot * p.Dp, q, p.Dp, u, act);
+    const float d = exact_dist_group<L2, true, 8>(p.X + (size_t)slot * p.Dp, q, p.Dp, u, act);
     if (act && u == 0) {
       buf[j].ord = f32_to_ord(d);
       buf[j].slot = slot;
@@ -748,9 +749,9 @@ __global__ void __launch_bounds__(128) rerank_kernel(const RerankParams p) {
     }
   }
   __syncthreads();
-  bitonic_sort_cands(buf, p.sort_n, tid, 128, [] { __syncthreads(); });
+  bitonic_sort_cands(buf, p.sort_n, tid, RR_THREADS, [] { __syncthreads(); });
   const uint32_t nout = min(n, p.k);
-  for (uint32_t i = tid; i < p.k; i += 128) {
+  for (uint32_t i = tid; i < p.k; i += RR_THREADS) {
     const bool ok = i < nout;
     p.out_dist[(size_t)b * p.k + i] = ok ? ord_to_f32(buf[i].ord) : __int_as_float(0x7f800000);
     p.out_labels[(size_t)b * p.k + i] = ok ? buf[i].label : ~0ull;
@@ -1043,9 +1044,9 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   const size_t rsmem = (size_t)rp.sort_n * sizeof(Cand) + (size_t)ix->Dp * 4;
   ix->prof_begin(c, KK_RERANK);
   if (ix->metric_l2)
-    rerank_kernel<true><<<B, 128, rsmem, s>>>(rp);
+    rerank_kernel<true><<<B, RR_THREADS, rsmem, s>>>(rp);
   else
-    rerank_kernel<false><<<B, 128, rsmem, s>>>(rp);
+    rerank_kernel<false><<<B, RR_THREADS, rsmem, s>>>(rp);
   VK_CUDA(cudaGetLastError());
   ix->prof_end(c, KK_RERANK);
   ix->kernels += 4;  // query conversion, candidate pass, merge, re-rank
