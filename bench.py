@@ -620,17 +620,21 @@ def main():
     def e2e_step():
         L.check(lib.vkgpu_search_batch(ix.handle(), hQ.ctypes.data, B, k, 0, None, 0, out_d.ctypes.data,
                                        out_l.ctypes.data, out_n.ctypes.data))
-        if world > 1:
-            td = torch.from_numpy(out_d).to(dev)
-            tl = torch.from_numpy(out_l.view(np.int64)).to(dev)
-            tn = torch.from_numpy(out_n.view(np.int32)).to(dev)
-            dist.all_gather_into_tensor(out[3].view(world * B, k), td)
-            dist.all_gather_into_tensor(out[4].view(world * B, k), tl)
-            dist.all_gather_into_tensor(out[5].view(world * B), tn)
-            L.check(lib.vkgpu_merge_topk_device(dev.index, out[3].data_ptr(), out[4].data_ptr(), out[5].data_ptr(),
-                                                world, B, k, out[6].data_ptr(), out[7].data_ptr(), out[8].data_ptr(),
-                                                sptr))
+        if world > 1:  # one packed block per rank (labels | distances | counts): ONE H2D, ONE all-gather
+            pk_l[:] = torch.from_numpy(out_l.view(np.int64))
+            pk_d[:] = torch.from_numpy(out_d)
+            pk_n[:] = torch.from_numpy(out_n.view(np.int32))
+            out[9].copy_(h_packed, non_blocking=True)
+            dist.all_gather_into_tensor(out[10], out[9])
+            L.check(lib.vkgpu_merge_topk_packed_device(dev.index, out[10].data_ptr(), world, B, k, out[6].data_ptr(),
+                                                       out[7].data_ptr(), out[8].data_ptr(), sptr))
             out[6].cpu(), out[7].cpu(), out[8].cpu()
+
+    if world > 1:
+        h_packed = torch.zeros((out[9].numel(),), dtype=torch.uint8).pin_memory()
+        pk_l = h_packed[: B * k * 8].view(torch.int64).view(B, k)
+        pk_d = h_packed[B * k * 8: B * k * 12].view(torch.float32).view(B, k)
+        pk_n = h_packed[B * k * 12: B * k * 12 + B * 4].view(torch.int32)
 
     e2e_step()
     barrier()

@@ -160,6 +160,15 @@ int vkgpu_merge_topk_device(int device, const float *d_dist, const uint64_t *d_l
                             uint32_t G, uint32_t B, uint32_t k, float *d_out_dist, uint64_t *d_out_labels,
                             uint32_t *d_out_n, void *cuda_stream);
 
+/* Same merge over ONE packed all-gather buffer, so that the exchange step of the path is a single collective:
+ * each rank contributes a block of vkgpu_packed_result_bytes(B,k) bytes laid out
+ *   labels u64 [B][k] | dist f32 [B][k] | n u32 [B] | padding to 256 bytes
+ * (point the three outputs of vkgpu_search_batch_device at those offsets of the local block), and d_packed holds
+ * the G blocks in rank order. */
+uint64_t vkgpu_packed_result_bytes(uint32_t B, uint32_t k);
+int vkgpu_merge_topk_packed_device(int device, const void *d_packed, uint32_t G, uint32_t B, uint32_t k,
+                                   float *d_out_dist, uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream);
+
 /* ---- HNSW graph interchange (hnswlib in-memory layout, hnswalg.h:152-176; "next" row N3) ----------- */
 /* Import a complete graph: n nodes, per-node level, label, deleted flag, level-0 lists [n][2M] + counts,
  * upper lists concatenated per node (levels[i] blocks of M ids + counts), then vectors [n,dim]. */

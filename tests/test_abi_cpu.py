@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_header_symbols_are_exported(built):
     from valkey_search_b200 import _lib as L
     header = open(os.path.join(ROOT, "include", "vkgpu.h")).read()
-    declared = set(re.findall(r"^(?:int|void|const char \*)\s*(vkgpu_[a-z0-9_]+)\(", header, re.M))
+    declared = set(re.findall(r"^(?:int|void|uint64_t|const char \*)\s*(vkgpu_[a-z0-9_]+)\(", header, re.M))
     assert declared, "no declarations parsed"
     lib = C.CDLL(L.LIB_PATH)
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]
@@ -48,3 +48,12 @@ def test_product_does_not_import_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="replace").read()
                 assert "vk_oracle" not in text and "libvkoracle" not in text and "libvkref" not in text, f
+
+
+def test_packed_result_layout_size(built):
+    """vkgpu_packed_result_bytes: labels u64 [B][k] | dist f32 [B][k] | n u32 [B], padded to 256 bytes (pure host)."""
+    from valkey_search_b200 import _lib as L
+    lib = L.lib()
+    for B, k in ((1, 1), (33, 25), (1024, 100), (512, 10)):
+        n = int(lib.vkgpu_packed_result_bytes(B, k))
+        assert n % 256 == 0 and 0 <= n - (B * k * 12 + B * 4) < 256

@@ -905,9 +905,32 @@ int vkgpu_distances(vkgpu_index *ix, const float *q, const uint64_t *labels, uin
   });
 }
 
+static int merge_topk_impl(int device, const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
+                           uint64_t rank_stride, uint32_t G, uint32_t B, uint32_t k, float *d_out_dist,
+                           uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream);
+
 int vkgpu_merge_topk_device(int device, const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
                             uint32_t G, uint32_t B, uint32_t k, float *d_out_dist, uint64_t *d_out_labels,
                             uint32_t *d_out_n, void *cuda_stream) {
+  return merge_topk_impl(device, d_dist, d_labels, d_n, 0, G, B, k, d_out_dist, d_out_labels, d_out_n, cuda_stream);
+}
+
+uint64_t vkgpu_packed_result_bytes(uint32_t B, uint32_t k) {
+  return (((uint64_t)B * k * 12 + (uint64_t)B * 4) + 255) & ~uint64_t(255);
+}
+
+int vkgpu_merge_topk_packed_device(int device, const void *d_packed, uint32_t G, uint32_t B, uint32_t k,
+                                   float *d_out_dist, uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream) {
+  const char *base = static_cast<const char *>(d_packed);
+  return merge_topk_impl(device, reinterpret_cast<const float *>(base + (uint64_t)B * k * 8),
+                         reinterpret_cast<const uint64_t *>(base),
+                         reinterpret_cast<const uint32_t *>(base + (uint64_t)B * k * 12), vkgpu_packed_result_bytes(B, k),
+                         G, B, k, d_out_dist, d_out_labels, d_out_n, cuda_stream);
+}
+
+static int merge_topk_impl(int device, const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
+                           uint64_t rank_stride, uint32_t G, uint32_t B, uint32_t k, float *d_out_dist,
+                           uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream) {
   return guarded([&] {
     VK_REQUIRE(d_dist && d_labels && d_n && d_out_dist && d_out_labels && d_out_n, VKGPU_ERR_INVALID, "null argument");
     VK_REQUIRE(G >= 1 && B >= 1 && k >= 1 && k <= kMaxFusedK, VKGPU_ERR_INVALID, "bad merge shape");
@@ -919,7 +942,7 @@ int vkgpu_merge_topk_device(int device, const float *d_dist, const uint64_t *d_l
     std::lock_guard<std::mutex> lk(mu);
     ws.reserve((size_t)G * B * k * sizeof(Cand));
     ws_cnt.reserve((size_t)G * B * 4);
-    launch_pack_shard_results(d_dist, d_labels, d_n, G, B, k, ws.as<Cand>(), ws_cnt.as<uint32_t>(), s);
+    launch_pack_shard_results(d_dist, d_labels, d_n, rank_stride, G, B, k, ws.as<Cand>(), ws_cnt.as<uint32_t>(), s);
     MergeParams mp{};
     mp.ws = ws.as<Cand>();
     mp.ws_cnt = ws_cnt.as<uint32_t>();

@@ -202,8 +202,9 @@ void launch_iota_labels(uint64_t *dst, uint64_t start, uint64_t n, cudaStream_t 
 // ordered compaction; counts = scratch of ceil(n/256) u32
 void launch_bitmap_to_slots(const uint64_t *labels, uint64_t n, const uint8_t *bm, uint64_t bits, uint32_t *out,
                             uint32_t *counts, unsigned long long *count, cudaStream_t s);
-void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n, uint32_t G,
-                               uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt, cudaStream_t s);
+void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
+                               uint64_t rank_stride, uint32_t G, uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt,
+                               cudaStream_t s);
 
 }  // namespace vkgpu
 

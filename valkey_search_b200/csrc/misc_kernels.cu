@@ -40,20 +40,29 @@ __global__ void iota_kernel(uint64_t *dst, uint64_t start, uint64_t n) {
 }
 
 // [G][B][k] (dist,label) + [G][B] counts  ->  candidate lists ws[b][g][k] / ws_cnt[b][g]   (qt = 1 layout)
+// rank_stride = 0: the three arrays are contiguous over ranks; else rank g's [B][k] / [B] block starts
+// g * rank_stride BYTES after the given pointer (one packed all-gather buffer per rank)
 __global__ void pack_shard_results_kernel(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
-                                          uint32_t G, uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt) {
+                                          uint64_t rank_stride, uint32_t G, uint32_t B, uint32_t k, Cand *ws,
+                                          uint32_t *ws_cnt) {
   const uint64_t total = (uint64_t)G * B * k;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (uint64_t)gridDim.x * blockDim.x) {
     const uint32_t j = (uint32_t)(i % k);
     const uint64_t gb = i / k;
     const uint32_t b = (uint32_t)(gb % B), g = (uint32_t)(gb / B);
+    const uint64_t in_rank = (uint64_t)b * k + j;
+    const float *dd = rank_stride ? reinterpret_cast<const float *>(reinterpret_cast<const char *>(d_dist) + g * rank_stride) + in_rank : d_dist + i;
+    const uint64_t *dl = rank_stride ? reinterpret_cast<const uint64_t *>(reinterpret_cast<const char *>(d_labels) + g * rank_stride) + in_rank : d_labels + i;
     Cand c;
-    c.ord = f32_to_ord(d_dist[i]);
+    c.ord = f32_to_ord(*dd);
     c.slot = g;
-    c.label = d_labels[i];
+    c.label = *dl;
     ws[((size_t)b * G + g) * k + j] = c;
-    if (j == 0) ws_cnt[(size_t)b * G + g] = min(d_n[gb], k);
+    if (j == 0) {
+      const uint32_t *dn = rank_stride ? reinterpret_cast<const uint32_t *>(reinterpret_cast<const char *>(d_n) + g * rank_stride) + b : d_n + gb;
+      ws_cnt[(size_t)b * G + g] = min(*dn, k);
+    }
   }
 }
 
@@ -147,9 +156,10 @@ void launch_iota_labels(uint64_t *dst, uint64_t start, uint64_t n, cudaStream_t 
   VK_CUDA(cudaGetLastError());
 }
 
-void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n, uint32_t G,
-                               uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt, cudaStream_t s) {
-  pack_shard_results_kernel<<<296, 256, 0, s>>>(d_dist, d_labels, d_n, G, B, k, ws, ws_cnt);
+void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
+                               uint64_t rank_stride, uint32_t G, uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt,
+                               cudaStream_t s) {
+  pack_shard_results_kernel<<<296, 256, 0, s>>>(d_dist, d_labels, d_n, rank_stride, G, B, k, ws, ws_cnt);
   VK_CUDA(cudaGetLastError());
 }
 

@@ -63,19 +63,18 @@ class ShardedFlat:
         dev = d_Q.device
         if out is None:
             out = self.alloc_out(B, k, dev)
-        loc_d, loc_l, loc_n, all_d, all_l, all_n, mer_d, mer_l, mer_n = out
+        loc_d, loc_l, loc_n, all_d, all_l, all_n, mer_d, mer_l, mer_n = out[:9]
         L.check(self._lib.vkgpu_search_batch_device(self.local.handle(), d_Q.data_ptr(), B, k, 0, loc_d.data_ptr(),
                                                     loc_l.data_ptr(), loc_n.data_ptr(), stream_ptr))
         if self.world == 1:
             return loc_d, loc_l, loc_n
-        # the single exchange step of the path: B*k*12 bytes per rank
-        G = self.world
-        self.dist.all_gather_into_tensor(all_d.view(G * B, k), loc_d)
-        self.dist.all_gather_into_tensor(all_l.view(G * B, k), loc_l)
-        self.dist.all_gather_into_tensor(all_n.view(G * B), loc_n)
-        L.check(self._lib.vkgpu_merge_topk_device(dev.index, all_d.data_ptr(), all_l.data_ptr(), all_n.data_ptr(),
-                                                  self.world, B, k, mer_d.data_ptr(), mer_l.data_ptr(),
-                                                  mer_n.data_ptr(), stream_ptr))
+        # the single exchange step of the path: ONE all-gather of the rank's packed block
+        # (labels | distances | counts = B*k*12 + B*4 bytes, vkgpu_packed_result_bytes), then the k-way merge
+        loc_packed, all_packed = out[9], out[10]
+        self.dist.all_gather_into_tensor(all_packed, loc_packed)
+        L.check(self._lib.vkgpu_merge_topk_packed_device(dev.index, all_packed.data_ptr(), self.world, B, k,
+                                                         mer_d.data_ptr(), mer_l.data_ptr(), mer_n.data_ptr(),
+                                                         stream_ptr))
         return mer_d, mer_l, mer_n
 
     def alloc_out(self, B, k, dev):
@@ -83,6 +82,14 @@ class ShardedFlat:
 
         G = self.world
         mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
-        return (mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32),
+        # the local result lives inside one packed block (labels | distances | counts) so that the exchange is a
+        # single collective; loc_* are views into it
+        nbytes = int(self._lib.vkgpu_packed_result_bytes(B, k))
+        loc_packed = torch.zeros((nbytes,), dtype=torch.uint8, device=dev)
+        all_packed = torch.empty((G * nbytes,), dtype=torch.uint8, device=dev)
+        loc_l = loc_packed[: B * k * 8].view(torch.int64).view(B, k)
+        loc_d = loc_packed[B * k * 8: B * k * 12].view(torch.float32).view(B, k)
+        loc_n = loc_packed[B * k * 12: B * k * 12 + B * 4].view(torch.int32)
+        return (loc_d, loc_l, loc_n,
                 mk((G, B, k), torch.float32), mk((G, B, k), torch.int64), mk((G, B), torch.int32),
-                mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32))
+                mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32), loc_packed, all_packed)
