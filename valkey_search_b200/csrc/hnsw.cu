@@ -344,6 +344,352 @@ __global__ void __launch_bounds__(HT) hnsw_search_kernel(const HnswSearchParams 
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Same search with SORTED ARRAYS in place of the two binary heaps (default when 2M <= 32).
+//
+// ncu on the heap kernel above: 52 % of warp samples wait at __syncthreads while thread 0 replays the heap
+// updates, and the hottest line is the LDS of its sift loops — ~3000 cycles of dependent shared-memory round
+// trips per hop (one pop of `candidate_set`, 3-4 pushes into each heap, 3-4 pops of `top_candidates`), more than
+// the HBM part of the hop.  Here the <= 32 neighbours of a hop are sorted once by a warp (shuffle bitonic network)
+// and MERGED into the sorted result list (<= ef) and the sorted candidate list by all 128 threads at once: every
+// element computes its final position (own index + rank in the other list) and writes itself into the second
+// buffer.  Popping the closest candidate is reading the head.
+// Semantics relative to searchBaseLayerST (hnswalg.h:351-551): the result list is the ef best evaluated live
+// nodes, exactly as the heap leaves it; a neighbour enters the candidate list iff the result list is not full or
+// it is no farther than the ef-th best AFTER the whole hop (the reference tests against the bound as it stands
+// neighbour by neighbour — the extra candidates it keeps are farther than the final bound and can only end the
+// search when popped, which their absence does as well).  The one observable difference is the order in which
+// EQUAL distances leave the lists (std::priority_queue's sift order vs stable order here): with exact distance
+// ties the two kernels may return different ids of equal distance.  VKGPU_HNSW_HEAPS=1 selects the heap kernel.
+template <bool L2>
+__global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearchParams p, uint32_t ccap) {
+  extern __shared__ __align__(128) uint8_t sm[];
+  const GraphView &g = p.g;
+  // layout: q | stage | top[2][ef+32] | cand[2][ccap+32] | uvi uvd uvf sd sidx sld slid [32 each] | ctl
+  uint32_t o = 0;
+  float *q = reinterpret_cast<float *>(sm + o);
+  o += g.Dp * 4;
+  o = (o + 127) & ~127u;
+  uint8_t *stage = sm + o;
+  o += p.rows_per_batch * p.row_stride_bytes;
+  HEnt *topb[2], *candb[2];
+  topb[0] = reinterpret_cast<HEnt *>(sm + o);
+  o += (p.ef + 32) * 8;
+  topb[1] = reinterpret_cast<HEnt *>(sm + o);
+  o += (p.ef + 32) * 8;
+  candb[0] = reinterpret_cast<HEnt *>(sm + o);
+  o += (ccap + 32) * 8;
+  candb[1] = reinterpret_cast<HEnt *>(sm + o);
+  o += (ccap + 32) * 8;
+  uint32_t *uvi = reinterpret_cast<uint32_t *>(sm + o);
+  float *uvd = reinterpret_cast<float *>(uvi + 32);
+  uint32_t *uvf = reinterpret_cast<uint32_t *>(uvd + 32);
+  float *sd = reinterpret_cast<float *>(uvf + 32);      // all neighbours of the hop, ascending by (d, list order)
+  uint32_t *sid = reinterpret_cast<uint32_t *>(sd + 32);
+  float *sld = reinterpret_cast<float *>(sid + 32);     // the live ones among them, same order
+  uint32_t *slid = reinterpret_cast<uint32_t *>(sld + 32);
+  o += 7 * 32 * 4;
+  o = (o + 15) & ~15u;
+  uint64_t *bar = reinterpret_cast<uint64_t *>(sm + o);
+  volatile uint32_t *ctl = reinterpret_cast<volatile uint32_t *>(sm + o + 8);
+
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t b = blockIdx.x;
+  uint32_t *vis = p.visited + (size_t)b * p.vis_words;
+  const uint8_t *allow = p.allow_ptr ? p.allow_ptr[b] : nullptr;
+  const uint64_t allow_bits = p.allow_ptr ? p.allow_bits[b] : 0;
+  const uint32_t RB = p.rows_per_batch;
+  const uint32_t row_bytes = g.Dp * 4;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    fence_mbar_init();
+  }
+  for (uint32_t i = tid; i < g.Dp / 4; i += HT)
+    reinterpret_cast<float4 *>(q)[i] = reinterpret_cast<const float4 *>(p.Q + (size_t)b * g.Dp)[i];
+  __syncthreads();
+
+  uint32_t parity = 0;
+  auto stage_and_dist = [&](uint32_t n) {  // distances from q to uvi[0..n) -> uvd[0..n)
+    for (uint32_t base = 0; base < n; base += RB) {
+      const uint32_t m = min(RB, n - base);
+      if (warp == 0) {
+        if (lane == 0) mbar_arrive_expect_tx(bar, m * row_bytes);
+        __syncwarp();
+        for (uint32_t r = lane; r < m; r += 32)
+          bulk_g2s(stage + r * p.row_stride_bytes, g.X + (size_t)uvi[base + r] * g.Dp, row_bytes, bar);
+      }
+      mbar_wait(bar, parity);
+      parity ^= 1;
+      for (uint32_t r0 = 0; r0 < m; r0 += HT / 16) {
+        const uint32_t r = r0 + (tid >> 4);
+        const bool act = r < m;
+        const float d = exact_dist_lane16<L2>(reinterpret_cast<const float *>(stage + (act ? r : 0) * p.row_stride_bytes),
+                                              q, g.Dp, tid & 15, act);
+        if (act && (tid & 15) == 0) uvd[base + r] = d;
+      }
+      __syncthreads();
+    }
+  };
+
+  // ---- entry point + greedy descent through the upper levels (hnswalg.h:1667-1697)
+  uint32_t curr = g.enterpoint;
+  if (tid == 0) uvi[0] = curr;
+  __syncthreads();
+  stage_and_dist(1);
+  float curdist = uvd[0];
+  unsigned long long n_hops = 0, n_dist = 1;
+  for (int level = g.maxlevel; level > 0; level--) {
+    for (;;) {
+      const uint32_t *blk = g.up + (g.up_off[curr] + (uint32_t)(level - 1)) * (size_t)(1 + g.maxM);
+      const uint32_t cnt = blk[0] & kHdrCountMask;
+      __syncthreads();
+      for (uint32_t i = tid; i < cnt; i += HT) uvi[i] = blk[1 + i];
+      __syncthreads();
+      stage_and_dist(cnt);
+      n_hops++;
+      n_dist += cnt;
+      if (tid == 0) {
+        uint32_t changed = 0, c = curr;
+        float cd = curdist;
+        for (uint32_t i = 0; i < cnt; i++) {
+          const float d = uvd[i];
+          if (d < cd) {
+            cd = d;
+            c = uvi[i];
+            changed = 1;
+          }
+        }
+        ctl[0] = changed;
+        ctl[1] = c;
+        ctl[3] = __float_as_uint(cd);
+      }
+      __syncthreads();
+      const uint32_t changed = ctl[0];
+      curr = ctl[1];
+      curdist = __uint_as_float(ctl[3]);
+      if (!changed) break;
+    }
+  }
+  __syncthreads();
+
+  // ---- level 0.  All counters below are computed identically by every thread (no broadcast needed).
+  const uint32_t ef = p.ef;
+  uint32_t ct = 0, cc = 0;              // live buffer of each list
+  uint32_t top_n = 0, cand_h = 0, cand_n = 0;
+  float lower = FLT_MAX;
+  {
+    const uint32_t ep = curr;
+    bool ok = !(g.hdr0[ep] & kHdrDeleted);
+    if (ok && allow) {
+      const uint64_t lab = g.labels[ep];
+      ok = lab < allow_bits && ((allow[lab >> 3] >> (lab & 7)) & 1);
+    }
+    if (tid == 0) {
+      if (ok) {
+        topb[0][0].d = curdist;
+        topb[0][0].id = ep;
+      }
+      candb[0][0].d = ok ? curdist : FLT_MAX;
+      candb[0][0].id = ep;
+      atomicOr(&vis[ep >> 5], 1u << (ep & 31));
+    }
+    top_n = ok ? 1 : 0;
+    lower = ok ? curdist : FLT_MAX;
+    cand_n = 1;
+  }
+  __syncthreads();
+  for (;;) {
+    if (cand_h == cand_n) break;
+    const HEnt c = candb[cc][cand_h];
+    if (c.d > lower && top_n == ef) break;  // hnswalg.h:407-409
+    cand_h++;
+    const uint32_t cur = c.id;
+    n_hops++;
+    // phase 1: visited filter, list order preserved (as in the heap kernel)
+    if (warp == 0) {
+      const uint32_t *nb = g.link0 + (size_t)cur * g.maxM0;
+      const uint32_t first = lane < g.maxM0 ? nb[lane] : 0u;
+      const uint32_t cnt = g.hdr0[cur] & kHdrCountMask;
+      uint32_t id = 0, flag = 0;
+      bool unv = false;
+      if (lane < cnt) {
+        id = first;
+        const uint32_t bit = 1u << (id & 31);
+        const uint32_t hdr = p.need_flags ? g.hdr0[id] : 0u;
+        const uint32_t old = atomicOr(&vis[id >> 5], bit);
+        unv = !(old & bit);
+        flag = 1u;
+        if (unv && p.need_flags) {
+          bool ok = !(hdr & kHdrDeleted);
+          if (ok && allow) {
+            const uint64_t lab = g.labels[id];
+            ok = lab < allow_bits && ((allow[lab >> 3] >> (lab & 7)) & 1);
+          }
+          flag = ok ? 1u : 0u;
+        }
+      }
+      const uint32_t bal = __ballot_sync(0xffffffffu, unv);
+      if (unv) {
+        const uint32_t pos = __popc(bal & ((1u << lane) - 1));
+        uvi[pos] = id;
+        uvf[pos] = flag;
+      }
+      if (lane == 0) ctl[2] = __popc(bal);
+    }
+    __syncthreads();
+    const uint32_t nuv = ctl[2];
+    if (nuv == 0) {  // uniform
+      __syncthreads();  // everyone has read ctl[2] before warp 0 writes the next hop's count
+      continue;
+    }
+    if (tid < nuv) {
+      const uint32_t id = uvi[tid];
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(g.link0 + (size_t)id * g.maxM0));
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(g.hdr0 + id));
+    }
+    stage_and_dist(nuv);  // ends with a block barrier
+    n_dist += nuv;
+
+    // ---- warp 0 sorts the hop's neighbours by (distance, list order): 32-element bitonic network on shuffles
+    if (warp == 0) {
+      float d = lane < nuv ? uvd[lane] : FLT_MAX;
+      uint32_t ix2 = lane;  // position in uvi; lanes >= nuv sort to the end (FLT_MAX, larger index)
+#pragma unroll
+      for (int k2 = 2; k2 <= 32; k2 <<= 1) {
+#pragma unroll
+        for (int j2 = k2 >> 1; j2 > 0; j2 >>= 1) {
+          const float od = __shfl_xor_sync(0xffffffffu, d, j2);
+          const uint32_t oi = __shfl_xor_sync(0xffffffffu, ix2, j2);
+          const bool up = ((lane & k2) == 0);
+          const bool lower_half = (lane & j2) == 0;
+          const bool other_less = od < d || (od == d && oi < ix2);
+          // the lower lane of a pair keeps the smaller key when sorting up, the larger when sorting down
+          const bool take = (lower_half == up) ? other_less : !other_less;
+          if (take) {
+            d = od;
+            ix2 = oi;
+          }
+        }
+      }
+      const bool in = ix2 < nuv;
+      const uint32_t id = in ? uvi[ix2] : 0u;
+      const bool live = in && uvf[ix2] != 0;
+      __syncwarp();
+      sd[lane] = d;
+      sid[lane] = id;
+      const uint32_t lb = __ballot_sync(0xffffffffu, live);
+      if (live) {
+        const uint32_t r = __popc(lb & ((1u << lane) - 1));
+        sld[r] = d;
+        slid[r] = id;
+      }
+      if (lane == 0) ctl[4] = __popc(lb);
+    }
+    __syncthreads();
+    const uint32_t n_live = ctl[4];
+
+    // ---- merge the live neighbours into the result list (keep the ef best)
+    {
+      const HEnt *A = topb[ct];
+      HEnt *Bf = topb[ct ^ 1];
+      for (uint32_t i = tid; i < top_n; i += HT) {
+        const HEnt a = A[i];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < n_live; j++) r += sld[j] < a.d ? 1u : 0u;  // newcomers go after equal distances
+        if (i + r < ef) Bf[i + r] = a;
+      }
+      for (uint32_t j = tid; j < n_live; j += HT) {
+        const float d = sld[j];
+        uint32_t lo = 0, hi = top_n;  // upper bound: first element with distance > d
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (A[mid].d <= d) lo = mid + 1; else hi = mid;
+        }
+        if (j + lo < ef) {
+          Bf[j + lo].d = d;
+          Bf[j + lo].id = slid[j];
+        }
+      }
+    }
+    __syncthreads();
+    top_n = min(top_n + n_live, ef);
+    ct ^= 1;
+    if (top_n) lower = topb[ct][top_n - 1].d;
+    const bool full = top_n == ef;
+
+    // ---- merge the neighbours that can still matter into the candidate list
+    {
+      uint32_t n_push = nuv;
+      if (full) {  // ascending: the qualifying ones are a prefix.  "<=": a neighbour that IS the new ef-th best
+        n_push = 0;  // was pushed by the reference when its turn came (the bound was still looser then)
+        for (uint32_t j = 0; j < nuv; j++) n_push += sd[j] <= lower ? 1u : 0u;
+      }
+      const HEnt *Cw = candb[cc] + cand_h;
+      HEnt *Cn = candb[cc ^ 1];
+      const uint32_t len = cand_n - cand_h;
+      for (uint32_t i = tid; i < len; i += HT) {
+        const HEnt a = Cw[i];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < n_push; j++) r += sd[j] < a.d ? 1u : 0u;
+        if (i + r < ccap) Cn[i + r] = a;
+      }
+      for (uint32_t j = tid; j < n_push; j += HT) {
+        const float d = sd[j];
+        uint32_t lo = 0, hi = len;
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (Cw[mid].d <= d) lo = mid + 1; else hi = mid;
+        }
+        if (j + lo < ccap) {
+          Cn[j + lo].d = d;
+          Cn[j + lo].id = sid[j];
+        }
+      }
+      __syncthreads();
+      cand_n = min(len + n_push, ccap);
+      cand_h = 0;
+      cc ^= 1;
+    }
+  }
+
+  // ---- trim to k (the list is ascending: the k best are its head), translate to labels, reply ascending by
+  //      (distance,label) (hnswalg.h:1715-1723, vector_base.cc:259-277)
+  __syncthreads();
+  const uint32_t nres = min(top_n, p.k);
+  const HEnt *top = topb[ct];
+  uint64_t *labs = reinterpret_cast<uint64_t *>(candb[cc ^ 1]);  // dead buffer as label scratch
+  for (uint32_t i = tid; i < nres; i += HT) labs[i] = g.labels[top[i].id];
+  __syncthreads();
+  if (tid == 0) {
+    float *od = p.out_dist + (size_t)b * p.k;
+    uint64_t *ol = p.out_labels + (size_t)b * p.k;
+    for (uint32_t i = 0; i < nres; i++) {  // insertion sort (equal distances: by label)
+      const float d = top[i].d;
+      const uint64_t lab = labs[i];
+      uint32_t j = i;
+      while (j > 0 && (d < od[j - 1] || (d == od[j - 1] && lab < ol[j - 1]))) {
+        od[j] = od[j - 1];
+        ol[j] = ol[j - 1];
+        j--;
+      }
+      od[j] = d;
+      ol[j] = lab;
+    }
+    p.out_n[b] = nres;
+    atomicAdd(&p.stats[0], n_hops);
+    atomicAdd(&p.stats[1], n_dist);
+  }
+}
+
+static size_t hnsw_sorted_smem_bytes(uint32_t Dp, uint32_t rows, uint32_t row_stride, uint32_t ef, uint32_t ccap) {
+  size_t o = ((size_t)Dp * 4 + 127) & ~size_t(127);
+  o += (size_t)rows * row_stride;
+  o += (size_t)2 * (ef + 32) * 8 + (size_t)2 * (ccap + 32) * 8 + 7 * 32 * 4;
+  o = (o + 15) & ~size_t(15);
+  return o + 64;
+}
+
 __global__ void hnsw_mark_deleted_kernel(uint32_t *hdr0, uint32_t id, uint32_t set) {
   if (set)
     atomicOr(&hdr0[id], kHdrDeleted);
@@ -375,6 +721,8 @@ void hnsw_create(vkgpu_index_impl *ix) {
   VK_CUDA(cudaMemset(g->d_stats.p, 0, 4 * sizeof(unsigned long long)));
   VK_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
   VK_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
 }
 
 void hnsw_destroy(vkgpu_index_impl *ix) {
@@ -543,25 +891,36 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   // rows staged per round vs CTAs per SM: prefer enough resident CTAs to hold the whole batch in ONE wave (a hop
   // stages ~8 unvisited rows on average, so 12-16 staged rows rarely need a second round), down to 1 CTA/SM for
   // very wide rows.  Shared memory per SM = opt-in max + 1 KB; each CTA reserves 1 KB.
-  const SmemLayout fixed = hnsw_smem_layout(ix->Dp, 0, hp.row_stride_bytes, ef, hp.cand_cap, g->maxM0);
+  // sorted-array kernel (default) needs the whole neighbour list of a hop in one warp pass: 2M <= 32
+  const bool sorted = g->maxM0 <= 32 && getenv("VKGPU_HNSW_HEAPS") == nullptr;
+  const uint32_t ccap = std::max<uint32_t>(256, 2 * ef);
+  const size_t fixed_total = sorted ? hnsw_sorted_smem_bytes(ix->Dp, 0, hp.row_stride_bytes, ef, ccap)
+                                    : hnsw_smem_layout(ix->Dp, 0, hp.row_stride_bytes, ef, hp.cand_cap, g->maxM0).total;
   const size_t sm_total = ix->smem_max + 1024;
   uint32_t want = std::min<uint32_t>(4, std::max<uint32_t>(1, (B + ix->num_sms - 1) / ix->num_sms));
   uint32_t rows = 0;
   for (uint32_t t = want; t >= 1; t--) {
     const size_t budget = sm_total / t - 1024;
-    rows = fixed.total < budget ? (uint32_t)((budget - fixed.total) / hp.row_stride_bytes) : 0;
+    rows = fixed_total < budget ? (uint32_t)((budget - fixed_total) / hp.row_stride_bytes) : 0;
     if (rows >= (t > 1 ? 12u : 1u)) break;
   }
   rows = std::min<uint32_t>(rows, 32);
   VK_REQUIRE(rows >= 1, VKGPU_ERR_UNSUPPORTED, "vector too large for the HNSW staging buffer");
   hp.rows_per_batch = rows;
-  const SmemLayout lay = hnsw_smem_layout(ix->Dp, rows, hp.row_stride_bytes, ef, hp.cand_cap, g->maxM0);
+  const size_t smem_bytes = sorted ? hnsw_sorted_smem_bytes(ix->Dp, rows, hp.row_stride_bytes, ef, ccap)
+                                   : hnsw_smem_layout(ix->Dp, rows, hp.row_stride_bytes, ef, hp.cand_cap, g->maxM0).total;
 
   ix->prof_begin(c, KK_HNSW);
-  if (ix->metric_l2)
-    hnsw_search_kernel<true><<<B, HT, lay.total, s>>>(hp);
-  else
-    hnsw_search_kernel<false><<<B, HT, lay.total, s>>>(hp);
+  if (sorted) {
+    if (ix->metric_l2)
+      hnsw_search_sorted_kernel<true><<<B, HT, smem_bytes, s>>>(hp, ccap);
+    else
+      hnsw_search_sorted_kernel<false><<<B, HT, smem_bytes, s>>>(hp, ccap);
+  } else if (ix->metric_l2) {
+    hnsw_search_kernel<true><<<B, HT, smem_bytes, s>>>(hp);
+  } else {
+    hnsw_search_kernel<false><<<B, HT, smem_bytes, s>>>(hp);
+  }
   VK_CUDA(cudaGetLastError());
   ix->prof_end(c, KK_HNSW);
   ix->kernels++;
