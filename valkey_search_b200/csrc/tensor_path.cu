@@ -785,17 +785,19 @@ bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
   (void)B;
   return ix->tensor_ready && k <= 128 && ix->n >= 4096;  // K' = 3k+64 rounded to 128 <= 512
 }
-// AUTO policy: a two-line cost model fitted to B200 measurements at 768 dims (both paths scale with rows x dims).
-// The exact scan streams the fp32 corpus once per 8 queries: 4.4 ms per 10M rows for one query, 8 ms per pass at
-// 8 queries per pass.  One tensor pass over the bf16 mirror costs 2.4 ms per 10M rows for up to 64 queries (the
-// 64-query tile runs at the HBM rate of the mirror, which is half the bytes of the fp32 corpus) and 3.2-4.4 ms per
-// 256 queries beyond that, plus ~0.7 ms of start-up, merge and re-rank.  Measured at 10M x 768: one query 5.1 ms
-// exact vs 3.1 ms tensor; batch 32 -> 31.8 vs 3.1; small corpora stay on the exact scan.
+// AUTO policy: a two-line cost model fitted to B200 measurements at 768 dims (both paths scale with rows x dims;
+// profiles/tensor_kernel_timing.py with EXP_PATH=exact|tensor).  The exact scan streams the fp32 corpus once per 8
+// queries (4.4 ms per 10M rows for one query, 8 ms per pass at 8 queries per pass) and its sort-based merge costs a
+// flat 0.65 ms.  One tensor pass over the bf16 mirror costs 2.4 ms per 10M rows for up to 64 queries (the 64-query
+// tile runs at the HBM rate of the mirror, half the bytes of the fp32 corpus) and ~3.2 ms per 256 queries beyond
+// that, plus 0.33 ms of start-up, merge and re-rank.  Measured, one query: 0.83 vs 0.45 ms at 300K rows, 1.16 vs
+// 0.66 at 1M, 2.07 vs 1.15 at 3M, 5.10 vs 2.73 at 10M; batch 32 at 10M: 31.8 vs 3.1 ms.  Below 100K rows the exact
+// scan (few slabs, cheap merge, no mirror to keep) stays.
 bool tensor_path_cheaper(const vkgpu_index_impl *ix, uint32_t B) {
   if (ix->n < 100000) return false;
   const double unit = (double)ix->n * ix->Dp / (1e7 * 768.0);
-  const double exact_ms = 0.3 + (B >= 8 ? std::ceil(B / 8.0) * 8.0 : 4.4 + 0.5 * (B - 1)) * unit;
-  const double tensor_ms = 0.7 + (B <= (uint32_t)BN_SMALL ? 2.4 : std::ceil(B / 256.0) * 3.4) * unit;
+  const double exact_ms = 0.65 + (B >= 8 ? std::ceil(B / 8.0) * 8.0 : 4.4 + 0.5 * (B - 1)) * unit;
+  const double tensor_ms = 0.33 + (B <= (uint32_t)BN_SMALL ? 2.4 : std::ceil(B / 256.0) * 3.2) * unit;
   return tensor_ms < exact_ms;
 }
 
