@@ -237,3 +237,28 @@ def test_flat_large_k_select_path(built, metric):
     Q[0] = X[2000]
     for k in (1025, 1500, 5000, 7000, 9000):
         _check_batch(ix, orc, Q, k)
+
+
+@pytest.mark.parametrize("dups,k", [(1500, 20), (40, 25), (700, 600)])
+def test_flat_many_equal_distances_pick_smallest_labels(built, dups, k):
+    """`dups` identical rows are all at the same distance from every query: the reference's (distance,label) order
+    (bruteforce.h:118, std::pair comparison) keeps the smallest labels among them.  With more ties than the merge
+    kernel's sort buffer holds, its in-kernel fallback (repeated sorting) has to produce the same answer."""
+    import valkey_search_b200 as V
+    rng = np.random.default_rng(dups + k)
+    N, D = 6000, 32
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    pos = rng.permutation(N)[:dups]          # the duplicates are scattered over the slabs
+    X[pos] = X[pos[0]]
+    Q = np.stack([X[pos[0]], X[pos[0]] + 0.01, rng.standard_normal(D).astype(np.float32)]).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    dist, labels, n = ix.SearchBatchRaw(Q, k)
+    orc = O.PortFlat(D, O.L2)
+    orc.add_many(X)
+    for b in range(Q.shape[0]):
+        d, l = orc.search(Q[b], k)
+        assert n[b] == len(l)
+        assert np.array_equal(labels[b, : n[b]], l), (b, labels[b, :8], l[:8])
+        assert np.array_equal(dist[b, : n[b]].view(np.uint32), d.view(np.uint32))
+    assert sorted(labels[0, : min(k, dups)].tolist()) == sorted(np.sort(pos)[: min(k, dups)].tolist())

@@ -584,16 +584,15 @@ void launch_gather_scan(bool l2, dim3 grid, size_t smem, cudaStream_t stream, co
 namespace {
 constexpr int MERGE_THREADS = 256;
 
-__global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const MergeParams p) {
-  extern __shared__ __align__(16) uint8_t msm[];
-  Cand *buf = reinterpret_cast<Cand *>(msm);  // [sort_n]
-  __shared__ uint32_t fill;
+// Merge by repeated sorting: lists are appended to a sort_n-entry buffer, which is sorted and cut to K whenever it
+// fills.  Exact for any input (all ties ordered by label); used directly for huge k and as the in-kernel fallback
+// of the selection merge when more equal-distance entries than the buffer holds straddle the K-th place.
+__device__ void merge_by_sorting(const MergeParams &p, Cand *buf) {
   const uint32_t b = blockIdx.x, tid = threadIdx.x;
   const uint32_t qtile = b / p.qt, qi = b % p.qt;
   const uint32_t N = p.sort_n, K = p.k;
   auto sync = [] { __syncthreads(); };
 
-  if (tid == 0) fill = 0;
   for (uint32_t i = tid; i < N; i += MERGE_THREADS) {
     buf[i].ord = kOrdInf;
     buf[i].slot = 0xffffffffu;
@@ -638,13 +637,22 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const MergePa
   }
   if (tid == 0) p.out_n[b] = nout;
 }
+
+__global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const MergeParams p) {
+  extern __shared__ __align__(16) uint8_t msm[];
+  merge_by_sorting(p, reinterpret_cast<Cand *>(msm));
+}
 }  // namespace
 
-// Selection-based merge for APPROXIMATE scores (tensor path): the K best of all lists without sorting them —
-// a 3-pass (11/11/10-bit) radix select finds the K-th smallest score, entries below it (and just enough ties,
-// any of them) are gathered into shared memory and only those K are sorted.  Which of several equal-score rows
-// survives is immaterial there: the re-rank kernel's proof depends on score VALUES only.
+// Selection-based merge: the K best of all lists without sorting them — a 3-pass (11/11/10-bit) radix select
+// finds the K-th smallest distance T, entries below it are gathered into shared memory and only those are sorted.
+//  EXACT = false (tensor path, approximate scores): just enough entries equal to T, any of them — which of
+//   several equal-score rows survives is immaterial there, the re-rank proof depends on score VALUES only.
+//  EXACT = true (exact scan, pre-filter, shard merge): ALL entries equal to T are gathered and the sort by
+//   (distance,label) decides, i.e. the reference's std::pair order (bruteforce.h:118).  If more ties than the
+//   buffer holds straddle the K-th place (hundreds of identical vectors) the CTA falls back to merge_by_sorting.
 namespace {
+template <bool EXACT>
 __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const MergeParams p) {
   extern __shared__ __align__(16) uint8_t msm[];
   Cand *buf = reinterpret_cast<Cand *>(msm);                                   // [sort_n]
@@ -743,12 +751,26 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
   }
   for_each_score([&](size_t at, uint32_t o) {
     bool keep = o < T;
-    if (!keep && o == T && total > K) keep = atomicAdd(&s_tie, 1u) < quota;
+    if (EXACT) {
+      if (o == T) keep = true;  // every tie: the (distance,label) sort below picks among them
+    } else {
+      if (!keep && o == T && total > K) keep = atomicAdd(&s_tie, 1u) < quota;
+    }
     if (total <= K) keep = true;
-    if (keep) buf[atomicAdd(&s_pos, 1u)] = p.ws[at];
+    if (keep) {
+      const uint32_t pos = atomicAdd(&s_pos, 1u);
+      if (pos < p.sort_n) buf[pos] = p.ws[at];
+    }
   });
   __syncthreads();
-  const uint32_t have = min(s_pos, K);
+  if (EXACT && s_pos > p.sort_n) {  // uniform; too many ties for the buffer
+    __syncthreads();
+    merge_by_sorting(p, buf);
+    return;
+  }
+  (void)quota;
+  uint32_t have = min(s_pos, K);
+  if (p.k_limit) have = min(have, p.k_limit[b]);
   bitonic_sort_cands(buf, p.sort_n, tid, MERGE_THREADS, [] { __syncthreads(); });
   for (uint32_t i = tid; i < K; i += MERGE_THREADS) {
     const bool ok = i < have;
@@ -762,18 +784,25 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
 
 void launch_topk_select_merge(uint32_t B, cudaStream_t stream, const MergeParams &p) {
   const size_t smem = (size_t)p.sort_n * sizeof(Cand) + 2048 * 4 + (size_t)p.slabs * 4;
-  topk_select_merge_kernel<<<B, MERGE_THREADS, smem, stream>>>(p);
+  topk_select_merge_kernel<false><<<B, MERGE_THREADS, smem, stream>>>(p);
   VK_CUDA(cudaGetLastError());
 }
 
+// exact (distance,label) merge: selection kernel with all ties kept; plain repeated sorting when the lists are so
+// many that their lengths do not fit beside the sort buffer
 void launch_topk_merge(uint32_t B, cudaStream_t stream, const MergeParams &p) {
-  size_t smem = (size_t)p.sort_n * sizeof(Cand);
   static bool attr_set = false;
   if (!attr_set) {
     VK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    VK_CUDA(cudaFuncSetAttribute(topk_select_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     attr_set = true;
   }
-  topk_merge_kernel<<<B, MERGE_THREADS, smem, stream>>>(p);
+  const size_t smem_sel = (size_t)p.sort_n * sizeof(Cand) + 2048 * 4 + (size_t)p.slabs * 4;
+  if (smem_sel <= 200 * 1024) {
+    topk_select_merge_kernel<true><<<B, MERGE_THREADS, smem_sel, stream>>>(p);
+  } else {
+    topk_merge_kernel<<<B, MERGE_THREADS, (size_t)p.sort_n * sizeof(Cand), stream>>>(p);
+  }
   VK_CUDA(cudaGetLastError());
 }
 

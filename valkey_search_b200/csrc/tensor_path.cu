@@ -785,19 +785,20 @@ bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
   (void)B;
   return ix->tensor_ready && k <= 128 && ix->n >= 4096;  // K' = 3k+64 rounded to 128 <= 512
 }
-// AUTO policy: a two-line cost model fitted to B200 measurements at 768 dims (both paths scale with rows x dims;
-// profiles/tensor_kernel_timing.py with EXP_PATH=exact|tensor).  The exact scan streams the fp32 corpus once per 8
-// queries (4.4 ms per 10M rows for one query, 8 ms per pass at 8 queries per pass) and its sort-based merge costs a
-// flat 0.65 ms.  One tensor pass over the bf16 mirror costs 2.4 ms per 10M rows for up to 64 queries (the 64-query
-// tile runs at the HBM rate of the mirror, half the bytes of the fp32 corpus) and ~3.2 ms per 256 queries beyond
-// that, plus 0.33 ms of start-up, merge and re-rank.  Measured, one query: 0.83 vs 0.45 ms at 300K rows, 1.16 vs
-// 0.66 at 1M, 2.07 vs 1.15 at 3M, 5.10 vs 2.73 at 10M; batch 32 at 10M: 31.8 vs 3.1 ms.  Below 100K rows the exact
-// scan (few slabs, cheap merge, no mirror to keep) stays.
+// AUTO policy: a cost model fitted to B200 measurements at 768 dims (both paths scale with rows x dims;
+// profiles/tensor_kernel_timing.py with EXP_PATH=exact|tensor, u = rows x dims / (10M x 768)):
+//   exact scan, one query        0.13 + 4.35 u ms   (0.26 at 300K rows, 0.54 at 1M, 1.44 at 3M, 4.4 at 10M)
+//   exact scan, 8 queries/pass   0.08 + passes x (0.5 + 7.5 u)
+//   tensor path, <= 64 queries   0.38 + 2.35 u      (0.45 at 300K, 0.66 at 1M, 1.15 at 3M, 2.73 at 10M: the 64-query
+//                                                    tile runs at the HBM rate of the bf16 mirror, half the bytes)
+//   tensor path, beyond          0.38 + 3.2 u per 256 queries
+// One query crosses over at ~1.25M x 768; eight queries already at ~150K rows.  Below 100K rows the exact scan stays
+// (no mirror to keep).
 bool tensor_path_cheaper(const vkgpu_index_impl *ix, uint32_t B) {
   if (ix->n < 100000) return false;
-  const double unit = (double)ix->n * ix->Dp / (1e7 * 768.0);
-  const double exact_ms = 0.65 + (B >= 8 ? std::ceil(B / 8.0) * 8.0 : 4.4 + 0.5 * (B - 1)) * unit;
-  const double tensor_ms = 0.33 + (B <= (uint32_t)BN_SMALL ? 2.4 : std::ceil(B / 256.0) * 3.2) * unit;
+  const double u = (double)ix->n * ix->Dp / (1e7 * 768.0);
+  const double exact_ms = B >= 8 ? 0.08 + std::ceil(B / 8.0) * (0.5 + 7.5 * u) : 0.13 + (4.35 + 0.5 * (B - 1)) * u;
+  const double tensor_ms = 0.38 + (B <= (uint32_t)BN_SMALL ? 2.35 : std::ceil(B / 256.0) * 3.2) * u;
   return tensor_ms < exact_ms;
 }
 
