@@ -262,3 +262,22 @@ def test_flat_many_equal_distances_pick_smallest_labels(built, dups, k):
         assert np.array_equal(labels[b, : n[b]], l), (b, labels[b, :8], l[:8])
         assert np.array_equal(dist[b, : n[b]].view(np.uint32), d.view(np.uint32))
     assert sorted(labels[0, : min(k, dups)].tolist()) == sorted(np.sort(pos)[: min(k, dups)].tolist())
+
+
+def test_prefilter_ring_kernel_matches_default(built, monkeypatch):
+    """The bulk-copy ring variant of the gather kernel (VKGPU_GATHER_TMA=1, kept to reproduce its measurement)
+    returns what the default load-based kernel returns."""
+    import valkey_search_b200 as V
+    rng = np.random.default_rng(12)
+    N, D, k = 20_000, 200, 15
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric.IP, initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    keys = [int(x) for x in rng.permutation(N)[:3000]]
+    q = rng.standard_normal(D).astype(np.float32)
+    monkeypatch.delenv("VKGPU_GATHER_TMA", raising=False)
+    a = ix.SearchPrefiltered(q, k, keys)
+    monkeypatch.setenv("VKGPU_GATHER_TMA", "1")
+    b = ix.SearchPrefiltered(q, k, keys)
+    assert [(n.external_id, np.float32(n.distance).tobytes()) for n in a] == \
+           [(n.external_id, np.float32(n.distance).tobytes()) for n in b]

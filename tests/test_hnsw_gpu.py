@@ -49,7 +49,8 @@ def import_graph(ix, orc, X):
 
 
 @pytest.mark.parametrize("metric,N,D,M,efc", [("L2", 3000, 64, 16, 100), ("IP", 2000, 100, 8, 60),
-                                               ("L2", 1500, 768, 16, 200)])
+                                               ("L2", 1500, 768, 16, 200),
+                                               ("L2", 1200, 48, 32, 80)])  # 2M = 64 > 32: the heap kernel
 def test_hnsw_search_bit_exact_on_imported_graph(built, metric, N, D, M, efc):
     import valkey_search_b200 as V
     rng = np.random.default_rng(N + D)
@@ -59,7 +60,7 @@ def test_hnsw_search_bit_exact_on_imported_graph(built, metric, N, D, M, efc):
     ix = V.VectorHNSW(D, V.DistanceMetric[metric], initial_cap=N, m=M, ef_construction=efc, ef_runtime=10)
     import_graph(ix, orc, X)
     Q = rng.standard_normal((24, D)).astype(np.float32)
-    for k, ef in ((10, 0), (10, 64), (5, 128), (100, 100), (1, 1)):
+    for k, ef in ((10, 0), (10, 64), (5, 128), (100, 100), (1, 1), (10, 300), (200, 1000)):
         dist, labels, n = ix.SearchBatchRaw(Q, k, ef_runtime=ef)
         for b in range(Q.shape[0]):
             d, l = orc.search(Q[b], k, ef)
@@ -263,3 +264,27 @@ def test_hnsw_allow_replace_deleted_reuses_slots(built):
         assert res[0].external_id == f"new{j}" and res[0].distance == 0.0
     got = {r.external_id for q in X[:10] for r in ix.Search(q, 5, ef_runtime=64)}
     assert not any(k in got for k in (f"k{i}" for i in range(10)))
+
+
+def test_hnsw_heap_and_sorted_kernels_agree(built, monkeypatch):
+    """The default sorted-list kernel and the heap kernel (VKGPU_HNSW_HEAPS=1, libstdc++ sift order) return the
+    same neighbours and distance bits on data without exact distance ties, tombstones included."""
+    import valkey_search_b200 as V
+    rng = np.random.default_rng(77)
+    N, D = 5000, 96
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    ix = _mk_hnsw(D, "L2", 16, 100, 10, cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    for key in range(0, N, 7):
+        assert ix.RemoveRecord(key)
+    Q = rng.standard_normal((40, D)).astype(np.float32)
+    out = {}
+    for mode in ("sorted", "heaps"):
+        if mode == "heaps":
+            monkeypatch.setenv("VKGPU_HNSW_HEAPS", "1")
+        else:
+            monkeypatch.delenv("VKGPU_HNSW_HEAPS", raising=False)
+        out[mode] = [ix.SearchBatchRaw(Q, k, ef_runtime=ef) for k, ef in ((10, 50), (3, 3), (50, 400))]
+    for a, b in zip(out["sorted"], out["heaps"]):
+        assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1])
+        assert np.array_equal(_bits(a[0]), _bits(b[0]))
