@@ -622,29 +622,25 @@ def main():
     ms_step = ms_total / K
     value = B * K / (ms_total / 1e3)
 
-    # ---- end to end through the host-buffer C-ABI (every rank answers on its shard; merge on the host)
+    # ---- end to end with HOST buffers: one GPU = the C-ABI call a module adapter makes (vkgpu_search_batch);
+    #      several GPUs = ShardedFlat.search_host (H2D of the queries, device search/exchange/merge, D2H of the result)
     out_d = np.empty((B, k), np.float32)
     out_l = np.empty((B, k), np.uint64)
     out_n = np.empty(B, np.uint32)
 
-    def e2e_step():
-        L.check(lib.vkgpu_search_batch(ix.handle(), hQ.ctypes.data, B, k, 0, None, 0, out_d.ctypes.data,
-                                       out_l.ctypes.data, out_n.ctypes.data))
-        if world > 1:  # one packed block per rank (labels | distances | counts): ONE H2D, ONE all-gather
-            pk_l[:] = torch.from_numpy(out_l.view(np.int64))
-            pk_d[:] = torch.from_numpy(out_d)
-            pk_n[:] = torch.from_numpy(out_n.view(np.int32))
-            out[9].copy_(h_packed, non_blocking=True)
-            dist.all_gather_into_tensor(out[10], out[9])
-            L.check(lib.vkgpu_merge_topk_packed_device(dev.index, out[10].data_ptr(), world, B, k, out[6].data_ptr(),
-                                                       out[7].data_ptr(), out[8].data_ptr(), sptr))
-            out[6].cpu(), out[7].cpu(), out[8].cpu()
-
     if world > 1:
-        h_packed = torch.zeros((out[9].numel(),), dtype=torch.uint8).pin_memory()
-        pk_l = h_packed[: B * k * 8].view(torch.int64).view(B, k)
-        pk_d = h_packed[B * k * 8: B * k * 12].view(torch.float32).view(B, k)
-        pk_n = h_packed[B * k * 12: B * k * 12 + B * 4].view(torch.int32)
+        # sharded: pinned host queries -> device, local search + ONE packed all-gather + merge on the device,
+        # merged [B,k] -> pinned host buffers (ShardedFlat.search_host, the call a multi-GPU user makes)
+        pin_q = torch.from_numpy(hQ).pin_memory()
+        pinned = (torch.empty((B, k), dtype=torch.float32).pin_memory(), torch.empty((B, k), dtype=torch.int64).pin_memory(),
+                  torch.empty((B,), dtype=torch.int32).pin_memory())
+
+    def e2e_step():
+        if world > 1:
+            sh.search_host(pin_q, k, sptr, out, pinned)
+        else:
+            L.check(lib.vkgpu_search_batch(ix.handle(), hQ.ctypes.data, B, k, 0, None, 0, out_d.ctypes.data,
+                                           out_l.ctypes.data, out_n.ctypes.data))
 
     e2e_step()
     barrier()

@@ -80,3 +80,29 @@ def test_merge_kernels_equal_single_index(built):
     hd, hl, hn = merge_topk_host(all_d.cpu().numpy(), all_l.cpu().numpy().astype(np.uint64),
                                  all_n.cpu().numpy().astype(np.uint32), k)
     assert np.array_equal(hl, l0) and np.array_equal(hd.view(np.uint32), d0.view(np.uint32))
+
+
+def test_sharded_flat_search_host_single_rank(built):
+    """ShardedFlat with one rank (no process group): the host-buffer entry (pinned queries in, pinned merged result
+    out) returns the local index's answer."""
+    import torch
+    import valkey_search_b200 as V
+    from valkey_search_b200.sharded import ShardedFlat
+
+    rng = np.random.default_rng(9)
+    N, D, B, k = 9000, 40, 17, 12
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    d0, l0, n0 = ix.SearchBatchRaw(Q, k)
+    dev = torch.device("cuda", 0)
+    sh = ShardedFlat(ix, None, dev)
+    out = sh.alloc_out(B, k, dev)
+    pinned = (torch.empty((B, k), dtype=torch.float32).pin_memory(), torch.empty((B, k), dtype=torch.int64).pin_memory(),
+              torch.empty((B,), dtype=torch.int32).pin_memory())
+    hq = torch.from_numpy(Q).pin_memory()
+    d, l, n = sh.search_host(hq, k, torch.cuda.current_stream().cuda_stream, out, pinned)
+    assert np.array_equal(n.numpy().astype(np.uint32), n0)
+    assert np.array_equal(l.numpy().astype(np.uint64), l0)
+    assert np.array_equal(d.numpy().view(np.uint32), d0.view(np.uint32))

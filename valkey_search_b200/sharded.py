@@ -77,6 +77,21 @@ class ShardedFlat:
                                                          stream_ptr))
         return mer_d, mer_l, mer_n
 
+    def search_host(self, h_Q, k, stream_ptr, out, pinned):
+        """End-to-end form of search_device for HOST buffers: `h_Q` is a pinned [B,dim] fp32 torch tensor,
+        `pinned` = (dist [B,k] f32, labels [B,k] i64, n [B] i32) pinned host tensors that receive the merged
+        result.  One H2D copy of the queries, the sharded search + exchange + merge on the device, one D2H copy
+        of the final [B,k] — the per-shard partial results never visit the host."""
+        import torch
+
+        d_Q = out[11]
+        d_Q.copy_(h_Q, non_blocking=True)
+        res = self.search_device(d_Q, k, stream_ptr, out)
+        for dst, src in zip(pinned, res):
+            dst.copy_(src, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return pinned
+
     def alloc_out(self, B, k, dev):
         import torch
 
@@ -92,4 +107,5 @@ class ShardedFlat:
         loc_n = loc_packed[B * k * 12: B * k * 12 + B * 4].view(torch.int32)
         return (loc_d, loc_l, loc_n,
                 mk((G, B, k), torch.float32), mk((G, B, k), torch.int64), mk((G, B), torch.int32),
-                mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32), loc_packed, all_packed)
+                mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32), loc_packed, all_packed,
+                mk((B, self.local.dimensions_), torch.float32))
