@@ -575,6 +575,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
         }
         go = min(go, mx);
+        // (deliberately unsynchronised with the gates of the other warps: racecheck flags this write against their
+        //  reads; a 4-byte threshold is read whole and only ever tightens, so a stale read keeps a candidate too many)
         if (part == 0 && go != kOrdInf) thrf[my_c] = fminf(thrf[my_c], ord_to_f32(go));
       }
 
@@ -606,7 +608,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 #pragma unroll
               for (int h = 0; h < 2; h++) {
                 uint32_t bits = need[w * 2 + h];
-                if (bits == 0) continue;
+                if (bits == 0) continue;  // warp-uniform
+                __syncwarp();             // every lane has read the flags before lane 0 clears them
                 if (lane == 0) need[w * 2 + h] = 0;
                 __syncwarp();
                 while (bits) {
