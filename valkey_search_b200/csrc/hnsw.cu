@@ -361,6 +361,30 @@ __global__ void __launch_bounds__(HT) hnsw_search_kernel(const HnswSearchParams 
 // search when popped, which their absence does as well).  The one observable difference is the order in which
 // EQUAL distances leave the lists (std::priority_queue's sift order vs stable order here): with exact distance
 // ties the two kernels may return different ids of equal distance.  VKGPU_HNSW_HEAPS=1 selects the heap kernel.
+// Per-phase time of the hop loop, summed over the hops of query 0 (build with -DVKGPU_HNSW_TRACE; the host prints
+// the averages after the launch): [0] link row + count arrive, [1] visited atomics + compaction, [2] block barrier,
+// [3] rows -> shared memory + distances, [4] sort, [5] result-list merge, [6] candidate-list merge, [7] hops.
+#ifdef VKGPU_HNSW_TRACE
+__device__ unsigned long long g_hop_ns[8];
+__device__ __forceinline__ unsigned long long hop_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define HOP_T(var) const unsigned long long var = hop_now()
+#define HOP_ADD(i, a, b) \
+  do {                   \
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_hop_ns[i] += (b) - (a); \
+  } while (0)
+#else
+#define HOP_T(var) \
+  do {             \
+  } while (0)
+#define HOP_ADD(i, a, b) \
+  do {                   \
+  } while (0)
+#endif
+
 template <bool L2>
 __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearchParams p, uint32_t ccap) {
   extern __shared__ __align__(128) uint8_t sm[];
@@ -506,17 +530,25 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
     cand_h++;
     const uint32_t cur = c.id;
     n_hops++;
+    HOP_T(h0);
     // phase 1: visited filter, list order preserved (as in the heap kernel)
     if (warp == 0) {
       const uint32_t *nb = g.link0 + (size_t)cur * g.maxM0;
       const uint32_t first = lane < g.maxM0 ? nb[lane] : 0u;
       const uint32_t cnt = g.hdr0[cur] & kHdrCountMask;
+#ifdef VKGPU_HNSW_TRACE
+      if (first + cnt == 0xffffffffu) ctl[6] = 1;  // consume the loads before the stamp
+      HOP_T(h1);
+      HOP_ADD(0, h0, h1);
+#endif
       uint32_t id = 0, flag = 0;
       bool unv = false;
       if (lane < cnt) {
         id = first;
         const uint32_t bit = 1u << (id & 31);
         const uint32_t hdr = p.need_flags ? g.hdr0[id] : 0u;
+        // (tried: a plain L2 load + fire-and-forget RED.OR instead of the returning atomic, the bitmap being
+        //  private to the CTA - 253.9 K vs 251.8 K QPS, within noise; the returning atomic stays)
         const uint32_t old = atomicOr(&vis[id >> 5], bit);
         unv = !(old & bit);
         flag = 1u;
@@ -536,8 +568,15 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
         uvf[pos] = flag;
       }
       if (lane == 0) ctl[2] = __popc(bal);
+#ifdef VKGPU_HNSW_TRACE
+      HOP_T(h2);
+      HOP_ADD(1, h0, h2);  // includes [0]
+#endif
     }
+    HOP_T(h3);
     __syncthreads();
+    HOP_T(h4);
+    HOP_ADD(2, h3, h4);
     const uint32_t nuv = ctl[2];
     if (nuv == 0) {  // uniform
       __syncthreads();  // everyone has read ctl[2] before warp 0 writes the next hop's count
@@ -550,6 +589,8 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
     }
     stage_and_dist(nuv);  // ends with a block barrier
     n_dist += nuv;
+    HOP_T(h5);
+    HOP_ADD(3, h4, h5);
 
     // ---- warp 0 sorts the hop's neighbours by (distance, list order): 32-element bitonic network on shuffles
     if (warp == 0) {
@@ -587,6 +628,8 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
       if (lane == 0) ctl[4] = __popc(lb);
     }
     __syncthreads();
+    HOP_T(h6);
+    HOP_ADD(4, h5, h6);
     const uint32_t n_live = ctl[4];
 
     // ---- merge the live neighbours into the result list (keep the ef best)
@@ -613,6 +656,8 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
       }
     }
     __syncthreads();
+    HOP_T(h7);
+    HOP_ADD(5, h6, h7);
     top_n = min(top_n + n_live, ef);
     ct ^= 1;
     if (top_n) lower = topb[ct][top_n - 1].d;
@@ -651,6 +696,9 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
       cand_h = 0;
       cc ^= 1;
     }
+    HOP_T(h8);
+    HOP_ADD(6, h7, h8);
+    HOP_ADD(7, 0ull, 1ull);
   }
 
   // ---- trim to k (the list is ascending: the k best are its head), translate to labels, reply ascending by
@@ -924,6 +972,19 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   VK_CUDA(cudaGetLastError());
   ix->prof_end(c, KK_HNSW);
   ix->kernels++;
+#ifdef VKGPU_HNSW_TRACE
+  if (sorted) {
+    unsigned long long h[8];
+    VK_CUDA(cudaStreamSynchronize(s));
+    VK_CUDA(cudaMemcpyFromSymbol(h, g_hop_ns, sizeof(h)));
+    const double n = h[7] ? (double)h[7] : 1.0;
+    fprintf(stderr, "[hnsw trace] query 0: %llu hops with neighbours to evaluate; ns per hop: link row %.0f, + visited atomics %.0f, "
+            "barrier %.0f, rows+distances %.0f, sort %.0f, result merge %.0f, candidate merge %.0f\n",
+            h[7], h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n);
+    memset(h, 0, sizeof(h));
+    VK_CUDA(cudaMemcpyToSymbol(g_hop_ns, h, sizeof(h)));
+  }
+#endif
 
   if (out_on_device) {
     VK_CUDA(cudaMemcpyAsync(out_dist, c->out_dist.p, (size_t)B * k * 4, cudaMemcpyDeviceToDevice, s));
