@@ -73,6 +73,14 @@ def _worker(rank, world, port, q):
     dist.all_gather_into_tensor(all_l.view(world * B, k), torch.from_numpy(loc_l))
     dist.all_gather_into_tensor(all_n.view(world * B), torch.from_numpy(loc_n))
     md, ml, mn = merge_topk_host(all_d.numpy(), all_l.numpy().astype(np.uint64), all_n.numpy().astype(np.uint32), k)
+    # the exchange as the GPU path does it: ONE all-gather of each rank's packed block
+    from valkey_search_b200.sharded import pack_result_host, packed_result_bytes, unpack_results_host
+    blk = torch.from_numpy(pack_result_host(loc_d, loc_l.astype(np.uint64), loc_n.astype(np.uint32)))
+    all_blk = torch.empty((world * packed_result_bytes(B, k),), dtype=torch.uint8)
+    dist.all_gather_into_tensor(all_blk, blk)
+    pd, pl, pn = unpack_results_host(all_blk.numpy(), world, B, k)
+    md2, ml2, mn2 = merge_topk_host(pd, pl, pn, k)
+    packed_ok = bool(np.array_equal(mn2, mn) and np.array_equal(ml2, ml) and np.array_equal(md2.view(np.uint32), md.view(np.uint32)))
     # single-index truth
     g = O.PortFlat(D, O.L2)
     g.add_many(X)
@@ -80,7 +88,7 @@ def _worker(rank, world, port, q):
     for b in range(B):
         d, l = g.search(Q[b], k)
         ok &= bool(np.array_equal(ml[b, : mn[b]], l) and np.array_equal(md[b, : mn[b]].view(np.uint32), d.view(np.uint32)))
-    q.put((rank, ok))
+    q.put((rank, ok and packed_ok))
     dist.destroy_process_group()
 
 
@@ -100,3 +108,17 @@ def test_two_rank_gloo_sharded_search_equals_single_index(built):
     for p in procs:
         p.join(timeout=60)
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def test_packed_layout_helpers_round_trip_and_match_the_abi(built):
+    from valkey_search_b200 import _lib as L
+    from valkey_search_b200.sharded import pack_result_host, packed_result_bytes, unpack_results_host
+    rng = np.random.default_rng(1)
+    for B, k, G in ((1, 1, 1), (33, 25, 3), (7, 100, 2)):
+        assert packed_result_bytes(B, k) == int(L.lib().vkgpu_packed_result_bytes(B, k))
+        d = rng.standard_normal((G, B, k)).astype(np.float32)
+        l = rng.integers(0, 2**63, (G, B, k)).astype(np.uint64)
+        n = rng.integers(0, k + 1, (G, B)).astype(np.uint32)
+        blocks = np.concatenate([pack_result_host(d[g], l[g], n[g]) for g in range(G)])
+        d2, l2, n2 = unpack_results_host(blocks, G, B, k)
+        assert np.array_equal(d2.view(np.uint32), d.view(np.uint32)) and np.array_equal(l2, l) and np.array_equal(n2, n)

@@ -42,6 +42,32 @@ def merge_topk_host(dist, labels, counts, k):
     return out_d, out_l, out_n
 
 
+def packed_result_bytes(B, k):
+    """Size of one rank's packed result block: labels u64 [B][k] | dist f32 [B][k] | n u32 [B], padded to 256 bytes
+    (the host-side statement of vkgpu_packed_result_bytes, include/vkgpu.h)."""
+    return (B * k * 12 + B * 4 + 255) & ~255
+
+
+def pack_result_host(dist, labels, counts):
+    """numpy [B,k] f32, [B,k] u64, [B] u32 -> one uint8 block in the packed layout."""
+    B, k = dist.shape
+    blk = np.zeros(packed_result_bytes(B, k), np.uint8)
+    blk[: B * k * 8] = np.ascontiguousarray(labels, np.uint64).view(np.uint8).reshape(-1)
+    blk[B * k * 8: B * k * 12] = np.ascontiguousarray(dist, np.float32).view(np.uint8).reshape(-1)
+    blk[B * k * 12: B * k * 12 + B * 4] = np.ascontiguousarray(counts, np.uint32).view(np.uint8).reshape(-1)
+    return blk
+
+
+def unpack_results_host(all_blocks, G, B, k):
+    """The G gathered blocks (uint8, rank order) -> ([G,B,k] dist, [G,B,k] labels, [G,B] counts)."""
+    n = packed_result_bytes(B, k)
+    blocks = np.asarray(all_blocks, np.uint8).reshape(G, n)
+    labels = np.stack([blocks[g, : B * k * 8].copy().view(np.uint64).reshape(B, k) for g in range(G)])
+    dist = np.stack([blocks[g, B * k * 8: B * k * 12].copy().view(np.float32).reshape(B, k) for g in range(G)])
+    counts = np.stack([blocks[g, B * k * 12: B * k * 12 + B * 4].copy().view(np.uint32) for g in range(G)])
+    return dist, labels, counts
+
+
 class ShardedFlat:
     """One rank's view of a row-sharded FLAT index.  `local` is a VectorFlat holding this rank's rows with
     GLOBAL labels.  search_device() runs local search -> all_gather -> merge entirely on the device."""
