@@ -1,5 +1,5 @@
 """The C++ host mirror of the reference's vector-index interface (valkey_search_b200/host/vector_index.{h,cc}):
-tests/native/vector_test.cc is a transcription of the reference's own testing/vector_test.cc cases (BasicFlat,
+tests/native/host_mirror_test.cc re-states the cases of the reference's own testing/vector_test.cc (BasicFlat,
 BasicHNSW via TestIndex, EfRuntimeRecall) plus the integration goldens, run here as a subprocess.  Without a GPU
 only the host-side cases run (normalisation arithmetic, and Create() failing loudly: no CPU fallback)."""
 import os
@@ -8,11 +8,11 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-BIN = os.path.join(ROOT, "tests", "native", "vector_test")
+BIN = os.path.join(ROOT, "tests", "native", "host_mirror_test")
 
 
 def _run(args):
-    assert os.path.exists(BIN), "tests/native/vector_test missing: run __graft_entry__.build()"
+    assert os.path.exists(BIN), "tests/native/host_mirror_test missing: run __graft_entry__.build()"
     p = subprocess.run([BIN] + args, capture_output=True, text=True, timeout=600)
     print(p.stdout)
     print(p.stderr)

@@ -4,7 +4,7 @@
 // concrete classes VectorFlat<T> (src/indexes/vector_flat.{h,cc}) and VectorHNSW<T>
 // (src/indexes/vector_hnsw.{h,cc}): same class and method names, same argument meaning, same result / error
 // behaviour (RecordResult vs Status channel, "Embedding id already exists", unchanged vector => kMissing,
-// wrong byte length => kInvalidData and, on modify, removal of the key ...), so that tests/native/vector_test.cc
+// wrong byte length => kInvalidData and, on modify, removal of the key ...), so that tests/native/host_mirror_test.cc
 // reads like testing/vector_test.cc.  What stays on the host, as in the reference: key <-> internal-id maps, id
 // allocation, cosine normalisation + magnitude bookkeeping, reply construction.  Behind the ABI (GPU): the
 // vectors, the graph, every distance and every top-k.
