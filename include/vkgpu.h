@@ -169,6 +169,13 @@ uint64_t vkgpu_packed_result_bytes(uint32_t B, uint32_t k);
 int vkgpu_merge_topk_packed_device(int device, const void *d_packed, uint32_t G, uint32_t B, uint32_t k,
                                    float *d_out_dist, uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream);
 
+/* ---- FLAT interchange ("next" row N3) ------------------------------------------------------------------ */
+/* Rows [first_slot, first_slot+n) in SLOT order with their labels: what BruteforceSearch::SaveIndex walks
+ * (third_party/hnswlib/bruteforce.h:147-171 — one chunk of vector bytes + label per element, slot by slot).  Slots
+ * follow the reference exactly (insertion position, swap-delete), so the exported sequence is the one the CPU module
+ * would write; loading is vkgpu_add_batch in the saved order (bruteforce.h:173-207). */
+int vkgpu_flat_export(vkgpu_index *h, uint64_t first_slot, uint64_t n, float *out_vecs, uint64_t *out_labels);
+
 /* ---- HNSW graph interchange (hnswlib in-memory layout, hnswalg.h:152-176; "next" row N3) ----------- */
 /* Import a complete graph: n nodes, per-node level, label, deleted flag, level-0 lists [n][2M] + counts,
  * upper lists concatenated per node (levels[i] blocks of M ids + counts), then vectors [n,dim]. */

@@ -318,6 +318,133 @@ static void InlineFilterAndBatch() {
     }
 }
 
+// In-memory chunk streams (the module's are RDBChunkOutputStream / RDBChunkInputStream)
+struct MemoryStream : public OutputStream, public InputStream {
+  std::vector<std::string> chunks;
+  size_t next = 0;
+  vks::Status SaveChunk(const char *data, size_t len) override {
+    chunks.emplace_back(data, len);
+    return vks::OkStatus();
+  }
+  vks::StatusOr<std::unique_ptr<std::string>> LoadChunk() override {
+    if (next >= chunks.size()) return vks::NotFoundError("no more chunks");
+    return std::make_unique<std::string>(chunks[next++]);
+  }
+  bool HasNext() const override { return next < chunks.size(); }
+};
+
+// SaveAndLoadFlat (testing/vector_test.cc:620-694): 50 queries answer the same (key and float distance) after a
+// save + load; here additionally after swap-deletes, for COSINE (stored normalised, magnitudes in the key metadata)
+// and with the byte layout of the element chunks checked.
+static void SaveAndLoadFlat() {
+  for (auto metric : {DistanceMetric::kL2, DistanceMetric::kCosine}) {
+    auto r = VectorFlat<float>::Create(CreateFlatVectorIndexProto(kDimensions, metric, kInitialCap, kBlockSize));
+    EXPECT_OK(r);
+    if (!r.ok()) return;
+    auto index = *r;
+    auto vectors = DeterministicallyGenerateVectors(1000, kDimensions, 10.0);
+    for (size_t i = 0; i < vectors.size(); ++i) VerifyAdd(index.get(), vectors, i, ExpectedResults::kSuccess);
+    for (int i = 3; i < 1000; i += 17) EXPECT_OK(index->RemoveRecord(IndexToKey(i)));  // swap-deletes reorder the slots
+    MemoryStream data, keys;
+    EXPECT_OK(index->SaveIndex(data));
+    EXPECT_OK(index->SaveTrackedKeys(keys));
+    const size_t live = index->GetTrackedKeyCount();
+    EXPECT_EQ(data.chunks.size(), live + 1);
+    EXPECT_EQ(keys.chunks.size(), live);
+    BruteForceIndexHeader header;
+    EXPECT_TRUE(header.ParseFromString(data.chunks[0]));
+    EXPECT_EQ(header.curr_element_count, (uint64_t)live);
+    EXPECT_EQ(header.size_per_element, (uint64_t)(kDimensions * 4 + 8));
+    EXPECT_EQ(header.max_elements, (uint64_t)index->GetCapacity());
+    for (size_t i = 1; i < data.chunks.size(); i++) EXPECT_EQ(data.chunks[i].size(), (size_t)(kDimensions * 4 + 8));
+    // element chunk = the stored row + its label: slot 0 still holds key 0 (never moved)
+    {
+      uint64_t label0;
+      std::memcpy(&label0, data.chunks[1].data() + kDimensions * 4, 8);
+      auto key0 = index->GetKeyDuringSearch(label0);
+      EXPECT_OK(key0);
+      if (key0.ok()) EXPECT_EQ(*key0, IndexToKey(0));
+    }
+    auto loaded = VectorFlat<float>::LoadFromStream(CreateFlatVectorIndexProto(kDimensions, metric, kInitialCap, kBlockSize), data);
+    EXPECT_OK(loaded);
+    if (!loaded.ok()) continue;
+    EXPECT_OK((*loaded)->LoadTrackedKeys(keys));
+    EXPECT_EQ((*loaded)->GetTrackedKeyCount(), live);
+    auto search_vectors = DeterministicallyGenerateVectors(50, kDimensions, 1.5);
+    for (const auto &q : search_vectors) {
+      auto a = index->Search(VectorToStr(q), 10, CancelNever());
+      auto b = (*loaded)->Search(VectorToStr(q), 10, CancelNever());
+      EXPECT_OK(a);
+      EXPECT_OK(b);
+      if (!a.ok() || !b.ok()) continue;
+      EXPECT_EQ(a->size(), b->size());
+      for (size_t j = 0; j < a->size() && j < b->size(); j++) {
+        EXPECT_EQ((*a)[j].external_id, (*b)[j].external_id);
+        EXPECT_TRUE(std::memcmp(&(*a)[j].distance, &(*b)[j].distance, 4) == 0);
+      }
+    }
+    // a second save of the loaded index is byte-identical (slot order and rows survived)
+    MemoryStream again;
+    EXPECT_OK((*loaded)->SaveIndex(again));
+    EXPECT_EQ(again.chunks.size(), data.chunks.size());
+    for (size_t i = 1; i < again.chunks.size() && i < data.chunks.size(); i++) EXPECT_TRUE(again.chunks[i] == data.chunks[i]);
+    // new keys continue after the largest loaded id (vector_base.cc:480-481)
+    auto extra = DeterministicallyGenerateVectors(1, kDimensions, 3.0);
+    EXPECT_OK((*loaded)->AddRecord("fresh_key", VectorToStr(extra[0])));
+    // wrong dimension in the persisted header is rejected (bruteforce.h:190-193)
+    MemoryStream bad = data;
+    bad.next = 0;
+    auto rejected = VectorFlat<float>::LoadFromStream(CreateFlatVectorIndexProto(kDimensions + 1, metric, kInitialCap, kBlockSize), bad);
+    EXPECT_FALSE(rejected.ok());
+  }
+}
+
+static std::string Hex(const std::string &s) {
+  static const char *d = "0123456789abcdef";
+  std::string out;
+  for (unsigned char c : s) {
+    out.push_back(d[c >> 4]);
+    out.push_back(d[c & 15]);
+  }
+  return out;
+}
+// `--wire`: prints the hand-encoded protobuf messages for a fixed list of cases; tests/test_host_cpp.py compares
+// them with what the protobuf runtime produces for the reference's message definitions.
+static int PrintWire() {
+  const uint64_t hdr[][3] = {{15000, 408, 100}, {0, 0, 0}, {10240, 3080, 0}, {1ull << 40, 12, 300}, {1, 1, 1}};
+  for (const auto &h : hdr) {
+    BruteForceIndexHeader m;
+    m.max_elements = h[0];
+    m.size_per_element = h[1];
+    m.curr_element_count = h[2];
+    BruteForceIndexHeader back;
+    if (!back.ParseFromString(m.SerializeAsString()) || back.max_elements != h[0] || back.size_per_element != h[1] ||
+        back.curr_element_count != h[2])
+      return 2;
+    std::printf("header %llu %llu %llu %s\n", (unsigned long long)h[0], (unsigned long long)h[1], (unsigned long long)h[2],
+                Hex(m.SerializeAsString()).c_str());
+  }
+  struct {
+    const char *key;
+    uint64_t id;
+    float mag;
+  } keys[] = {{"0_key", 5, -1.0f}, {"", 0, 0.0f}, {"doc:1", 0, 1.5f}, {"k", 1ull << 33, 0.0f}, {"x", 7, -0.0f}};
+  for (const auto &k : keys) {
+    TrackedKeyMetadataPb m;
+    m.key = k.key;
+    m.internal_id = k.id;
+    m.magnitude = k.mag;
+    TrackedKeyMetadataPb back;
+    if (!back.ParseFromString(m.SerializeAsString()) || back.key != k.key || back.internal_id != k.id ||
+        std::memcmp(&back.magnitude, &k.mag, 4) != 0)
+      return 2;
+    uint32_t bits;
+    std::memcpy(&bits, &k.mag, 4);
+    std::printf("key %s|%llu|%08x %s\n", k.key, (unsigned long long)k.id, bits, Hex(m.SerializeAsString()).c_str());
+  }
+  return 0;
+}
+
 // host-only: normalisation arithmetic (vector_base.cc:112-138) and the no-CPU-fallback contract
 static void HostOnly(bool have_gpu) {
   std::vector<float> v = {3.0f, 4.0f, 0.0f};
@@ -337,6 +464,7 @@ static void HostOnly(bool have_gpu) {
 }
 
 int main(int argc, char **argv) {
+  if (argc > 1 && std::string(argv[1]) == "--wire") return PrintWire();
   const bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";
   struct Case {
     const char *name;
@@ -346,6 +474,7 @@ int main(int argc, char **argv) {
                {"EfRuntimeRecall", EfRuntimeRecall},
                {"IntegrationCosineGoldens", IntegrationCosineGoldens},
                {"Prefilter", Prefilter},
+               {"SaveAndLoadFlat", SaveAndLoadFlat},
                {"InlineFilterAndBatch", InlineFilterAndBatch}};
   {
     const int before = g_failures;

@@ -29,6 +29,63 @@ def test_cpp_host_mirror_host_only(built):
 def test_cpp_host_mirror_reads_like_reference_vector_test(built):
     p = _run([])
     assert p.returncode == 0, p.stdout + p.stderr
-    for case in ("BasicFlat", "BasicHNSW", "EfRuntimeRecall", "IntegrationCosineGoldens", "Prefilter",
+    for case in ("BasicFlat", "BasicHNSW", "EfRuntimeRecall", "IntegrationCosineGoldens", "Prefilter", "SaveAndLoadFlat",
                  "InlineFilterAndBatch"):
         assert f"[  OK  ] {case}" in p.stdout, p.stdout + p.stderr
+
+
+def _reference_messages():
+    """data_model::BruteForceIndexHeader (third_party/hnswlib/index.proto:6-10) and data_model::TrackedKeyMetadata
+    (src/index_schema.proto:81-85) as protobuf message classes, built from descriptors stated here (no protoc in the
+    image); the protobuf RUNTIME does the encoding the C++ host mirror restates by hand."""
+    from google.protobuf import descriptor_pb2, descriptor_pool, message_factory
+
+    fd = descriptor_pb2.FileDescriptorProto()
+    fd.name = "vks_golden.proto"
+    fd.package = "valkey_search.data_model"
+    fd.syntax = "proto3"
+    T = descriptor_pb2.FieldDescriptorProto
+    m = fd.message_type.add()
+    m.name = "BruteForceIndexHeader"
+    for i, name in enumerate(("max_elements", "size_per_element", "curr_element_count"), 1):
+        f = m.field.add()
+        f.name, f.number, f.type, f.label = name, i, T.TYPE_UINT64, T.LABEL_OPTIONAL
+    m = fd.message_type.add()
+    m.name = "TrackedKeyMetadata"
+    for i, (name, typ) in enumerate((("key", T.TYPE_STRING), ("internal_id", T.TYPE_UINT64), ("magnitude", T.TYPE_FLOAT)), 1):
+        f = m.field.add()
+        f.name, f.number, f.type, f.label = name, i, typ, T.LABEL_OPTIONAL
+    pool = descriptor_pool.DescriptorPool()
+    pool.Add(fd)
+    get = getattr(message_factory, "GetMessageClass", None)
+    if get is None:  # older protobuf
+        factory = message_factory.MessageFactory(pool)
+        get = factory.GetPrototype
+    return (get(pool.FindMessageTypeByName("valkey_search.data_model.BruteForceIndexHeader")),
+            get(pool.FindMessageTypeByName("valkey_search.data_model.TrackedKeyMetadata")))
+
+
+def test_cpp_host_mirror_wire_format_matches_protobuf(built):
+    """The save/load path writes two protobuf messages; the host mirror encodes them by hand.  Every case the binary
+    prints must be byte-identical to the protobuf runtime's serialisation of the same message."""
+    import struct
+    Header, Key = _reference_messages()
+    p = _run(["--wire"])
+    assert p.returncode == 0, p.stdout + p.stderr
+    seen = 0
+    for line in p.stdout.splitlines():
+        parts = line.split(" ")
+        if parts[0] == "header":
+            a, b, c = (int(x) for x in parts[1:4])
+            want = Header(max_elements=a, size_per_element=b, curr_element_count=c).SerializeToString()
+            got = bytes.fromhex(parts[4]) if len(parts) > 4 else b""
+        elif parts[0] == "key":
+            key, iid, bits = parts[1].split("|")
+            mag = struct.unpack("<f", struct.pack("<I", int(bits, 16)))[0]
+            want = Key(key=key, internal_id=int(iid), magnitude=mag).SerializeToString()
+            got = bytes.fromhex(parts[2]) if len(parts) > 2 else b""
+        else:
+            continue
+        assert got == want, (line, want.hex())
+        seen += 1
+    assert seen == 10

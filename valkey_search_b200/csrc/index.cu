@@ -827,6 +827,21 @@ int vkgpu_get(vkgpu_index *ix, uint64_t label, float *out_vec) {
   });
 }
 
+int vkgpu_flat_export(vkgpu_index *ix, uint64_t first_slot, uint64_t n, float *out_vecs, uint64_t *out_labels) {
+  return guarded([&] {
+    VK_REQUIRE(ix && (n == 0 || (out_vecs && out_labels)), VKGPU_ERR_INVALID, "null argument");
+    VK_REQUIRE(ix->cfg.algo == VKGPU_FLAT, VKGPU_ERR_INVALID, "slot-order export is FLAT only");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_REQUIRE(first_slot + n <= ix->n, VKGPU_ERR_INVALID, "slot range beyond the element count");
+    if (n == 0) return;
+    VK_CUDA(cudaSetDevice(ix->device));
+    // rows are stored padded to Dp floats: strip the padding on the way out
+    VK_CUDA(cudaMemcpy2D(out_vecs, (size_t)ix->dim * 4, ix->dX.as<float>() + first_slot * ix->Dp, (size_t)ix->Dp * 4,
+                         (size_t)ix->dim * 4, n, cudaMemcpyDeviceToHost));
+    VK_CUDA(cudaMemcpy(out_labels, ix->dLabels.as<uint64_t>() + first_slot, n * 8, cudaMemcpyDeviceToHost));
+  });
+}
+
 int vkgpu_search_batch(vkgpu_index *ix, const float *Q, uint32_t B, uint32_t k, uint32_t ef,
                        const vkgpu_filter *filters, uint64_t deadline_ns, float *out_dist, uint64_t *out_labels,
                        uint32_t *out_n) {

@@ -306,6 +306,202 @@ StatusOr<std::vector<std::vector<Neighbor>>> VectorBase::SearchBatch(std::string
   return out;
 }
 
+// ------------------------------------------------------------------------------------------ wire format
+namespace {
+void PutVarint(std::string &out, uint64_t v) {
+  while (v >= 0x80) {
+    out.push_back((char)((v & 0x7f) | 0x80));
+    v >>= 7;
+  }
+  out.push_back((char)v);
+}
+bool GetVarint(std::string_view s, size_t &pos, uint64_t &v) {
+  v = 0;
+  for (int shift = 0; shift < 64 && pos < s.size(); shift += 7) {
+    const uint8_t b = (uint8_t)s[pos++];
+    v |= (uint64_t)(b & 0x7f) << shift;
+    if (!(b & 0x80)) return true;
+  }
+  return false;
+}
+// skips one field of wire type `wt` (unknown fields are ignored, as protobuf does)
+bool SkipField(std::string_view s, size_t &pos, uint32_t wt) {
+  uint64_t v;
+  switch (wt) {
+    case 0: return GetVarint(s, pos, v);
+    case 1: pos += 8; return pos <= s.size();
+    case 2: if (!GetVarint(s, pos, v)) return false; pos += v; return pos <= s.size();
+    case 5: pos += 4; return pos <= s.size();
+    default: return false;
+  }
+}
+}  // namespace
+
+std::string BruteForceIndexHeader::SerializeAsString() const {
+  std::string out;
+  const uint64_t f[3] = {max_elements, size_per_element, curr_element_count};
+  for (int i = 0; i < 3; i++)
+    if (f[i]) {  // proto3: default values are not written
+      out.push_back((char)(((i + 1) << 3) | 0));
+      PutVarint(out, f[i]);
+    }
+  return out;
+}
+bool BruteForceIndexHeader::ParseFromString(std::string_view s) {
+  *this = BruteForceIndexHeader();
+  size_t pos = 0;
+  while (pos < s.size()) {
+    uint64_t tag, v;
+    if (!GetVarint(s, pos, tag)) return false;
+    const uint32_t field = (uint32_t)(tag >> 3), wt = (uint32_t)(tag & 7);
+    if (wt == 0 && field >= 1 && field <= 3) {
+      if (!GetVarint(s, pos, v)) return false;
+      (field == 1 ? max_elements : field == 2 ? size_per_element : curr_element_count) = v;
+    } else if (!SkipField(s, pos, wt)) {
+      return false;
+    }
+  }
+  return true;
+}
+
+std::string TrackedKeyMetadataPb::SerializeAsString() const {
+  std::string out;
+  if (!key.empty()) {
+    out.push_back((char)((1 << 3) | 2));
+    PutVarint(out, key.size());
+    out += key;
+  }
+  if (internal_id) {
+    out.push_back((char)((2 << 3) | 0));
+    PutVarint(out, internal_id);
+  }
+  uint32_t bits;
+  std::memcpy(&bits, &magnitude, 4);
+  if (bits) {  // protobuf omits +0.0f only (a negative zero is written)
+    out.push_back((char)((3 << 3) | 5));
+    out.append(reinterpret_cast<const char *>(&bits), 4);  // little endian, as on every host this runs on
+  }
+  return out;
+}
+bool TrackedKeyMetadataPb::ParseFromString(std::string_view s) {
+  *this = TrackedKeyMetadataPb();
+  size_t pos = 0;
+  while (pos < s.size()) {
+    uint64_t tag, v;
+    if (!GetVarint(s, pos, tag)) return false;
+    const uint32_t field = (uint32_t)(tag >> 3), wt = (uint32_t)(tag & 7);
+    if (field == 1 && wt == 2) {
+      if (!GetVarint(s, pos, v) || pos + v > s.size()) return false;
+      key.assign(s.substr(pos, v));
+      pos += v;
+    } else if (field == 2 && wt == 0) {
+      if (!GetVarint(s, pos, internal_id)) return false;
+    } else if (field == 3 && wt == 5) {
+      if (pos + 4 > s.size()) return false;
+      std::memcpy(&magnitude, s.data() + pos, 4);
+      pos += 4;
+    } else if (!SkipField(s, pos, wt)) {
+      return false;
+    }
+  }
+  return true;
+}
+
+// ------------------------------------------------------------------------------------------ save / load
+Status VectorBase::SaveTrackedKeys(OutputStream &chunked_out) const {
+  std::shared_lock lock(key_to_metadata_mutex_);
+  for (const auto &[key, metadata] : tracked_metadata_by_key_) {
+    TrackedKeyMetadataPb pb;
+    pb.key = key;
+    pb.internal_id = metadata.internal_id;
+    pb.magnitude = metadata.magnitude;
+    const std::string bytes = pb.SerializeAsString();
+    VKS_RETURN_IF_ERROR(chunked_out.SaveChunk(bytes.data(), bytes.size()));
+  }
+  return vks::OkStatus();
+}
+
+Status VectorBase::LoadTrackedKeys(InputStream &iter) {
+  std::unique_lock lock(key_to_metadata_mutex_);
+  uint64_t max_id = 0;
+  bool any = false;
+  while (iter.HasNext()) {
+    auto chunk = iter.LoadChunk();
+    if (!chunk.ok()) return chunk.status();
+    TrackedKeyMetadataPb pb;
+    if (!pb.ParseFromString(**chunk)) return vks::InvalidArgumentError("Error parsing metadata from proto");
+    tracked_metadata_by_key_.insert({pb.key, TrackedKeyMetadata{pb.internal_id, pb.magnitude}});
+    key_by_internal_id_.insert({pb.internal_id, pb.key});
+    max_id = std::max(max_id, pb.internal_id);
+    any = true;
+  }
+  inc_id_ = any ? max_id + 1 : inc_id_;  // vector_base.cc:480-481: max label + 1
+  return vks::OkStatus();
+}
+
+template <typename T>
+Status VectorFlat<T>::SaveIndex(OutputStream &chunked_out) const {
+  const vkgpu_stats st = Stats();
+  const size_t vector_size = (size_t)dimensions_ * sizeof(T);
+  BruteForceIndexHeader header;
+  header.max_elements = st.capacity;
+  header.size_per_element = vector_size + sizeof(uint64_t);
+  header.curr_element_count = st.count;
+  const std::string serialized = header.SerializeAsString();
+  VKS_RETURN_IF_ERROR(chunked_out.SaveChunk(serialized.data(), serialized.size()));
+  constexpr uint64_t kBlock = 4096;  // rows fetched from HBM per call; the chunks stay one element each
+  std::vector<float> rows(kBlock * dimensions_);
+  std::vector<uint64_t> labels(kBlock);
+  std::vector<char> buf(header.size_per_element);
+  for (uint64_t first = 0; first < st.count; first += kBlock) {
+    const uint64_t n = std::min<uint64_t>(kBlock, st.count - first);
+    VKS_RETURN_IF_ERROR(FromRc(vkgpu_flat_export(gpu_, first, n, rows.data(), labels.data())));
+    for (uint64_t i = 0; i < n; i++) {
+      std::memcpy(buf.data(), rows.data() + i * dimensions_, vector_size);
+      std::memcpy(buf.data() + vector_size, &labels[i], sizeof(uint64_t));
+      VKS_RETURN_IF_ERROR(chunked_out.SaveChunk(buf.data(), buf.size()));
+    }
+  }
+  return vks::OkStatus();
+}
+
+template <typename T>
+StatusOr<std::shared_ptr<VectorFlat<T>>> VectorFlat<T>::LoadFromStream(const VectorIndexProto &p, InputStream &input) {
+  auto serialized_header = input.LoadChunk();
+  if (!serialized_header.ok()) return serialized_header.status();
+  BruteForceIndexHeader header;
+  if (!header.ParseFromString(**serialized_header)) return vks::InternalError("Could not deserialize bruteforce header");
+  const size_t vector_size = (size_t)p.dimension_count * sizeof(T);
+  if (header.size_per_element != vector_size + sizeof(uint64_t))
+    return vks::InternalError("Persisted size_per_element does not match expectation.");  // bruteforce.h:190-193
+  VectorIndexProto q = p;
+  q.initial_cap = std::max<uint64_t>(header.max_elements, header.curr_element_count);
+  auto created = Create(q);
+  if (!created.ok()) return created.status();
+  auto index = *created;
+  constexpr uint64_t kBlock = 4096;
+  std::vector<float> rows;
+  std::vector<uint64_t> labels;
+  for (uint64_t i = 0; i < header.curr_element_count; i++) {
+    auto chunk = input.LoadChunk();
+    if (!chunk.ok()) return chunk.status();
+    if ((*chunk)->size() != header.size_per_element) return vks::InternalError("bruteforce element chunk has the wrong size");
+    const size_t at = rows.size();
+    rows.resize(at + p.dimension_count);
+    std::memcpy(rows.data() + at, (*chunk)->data(), vector_size);
+    uint64_t id;
+    std::memcpy(&id, (*chunk)->data() + vector_size, sizeof(id));
+    labels.push_back(id);
+    if (labels.size() == kBlock || i + 1 == header.curr_element_count) {  // slot i = i-th saved element
+      const Status s = index->FromRc(vkgpu_add_batch(index->gpu_, labels.data(), rows.data(), labels.size()));
+      if (!s.ok()) return s;
+      rows.clear();
+      labels.clear();
+    }
+  }
+  return index;
+}
+
 // ------------------------------------------------------------------------------------------ VectorFlat
 static vkgpu_config BaseConfig(const VectorIndexProto &p, vkgpu_algo algo) {
   vkgpu_config cfg{};

@@ -70,6 +70,36 @@ struct VectorIndexProto {  // data_model::VectorIndex, src/index_schema.proto:87
   bool hnsw_allow_replace_deleted{false};
 };
 
+// Chunk streams of the save/load path (third_party/hnswlib/iostream.h:27-42; the module's implementations are
+// RDBChunkOutputStream / RDBChunkInputStream, src/rdb_serialization.h).
+class OutputStream {
+ public:
+  virtual ~OutputStream() = default;
+  virtual Status SaveChunk(const char *data, size_t len) = 0;
+};
+class InputStream {
+ public:
+  virtual ~InputStream() = default;
+  virtual StatusOr<std::unique_ptr<std::string>> LoadChunk() = 0;
+  virtual bool HasNext() const = 0;  // SupplementalContentChunkIter::HasNext
+};
+
+// The two protobuf messages of this path, hand-encoded in proto3 wire format (no protobuf in the image):
+// data_model::BruteForceIndexHeader (third_party/hnswlib/index.proto:6-10) and data_model::TrackedKeyMetadata
+// (src/index_schema.proto:81-85).  Zero-valued fields are omitted, as protobuf does.
+struct BruteForceIndexHeader {
+  uint64_t max_elements{0}, size_per_element{0}, curr_element_count{0};
+  std::string SerializeAsString() const;
+  bool ParseFromString(std::string_view s);
+};
+struct TrackedKeyMetadataPb {
+  std::string key;
+  uint64_t internal_id{0};
+  float magnitude{0.0f};
+  std::string SerializeAsString() const;
+  bool ParseFromString(std::string_view s);
+};
+
 using CancelToken = uint64_t;                     // deadline in CLOCK_MONOTONIC ns; 0 = CancelNever()
 inline CancelToken CancelNever() { return 0; }
 using KeyFilter = std::function<bool(const std::string &key)>;
@@ -117,6 +147,11 @@ class VectorBase {
   StatusOr<std::vector<std::vector<Neighbor>>> SearchBatch(std::string_view queries, uint32_t batch, uint64_t count,
                                                            std::optional<size_t> ef_runtime = std::nullopt) const;
 
+  // SaveTrackedKeys / LoadTrackedKeys (vector_base.cc:416-432, 460-483): one TrackedKeyMetadata chunk per key;
+  // after loading, the next internal id is max + 1.
+  Status SaveTrackedKeys(OutputStream &chunked_out) const;
+  Status LoadTrackedKeys(InputStream &iter);
+
   vkgpu_index *handle() const { return gpu_; }
   vkgpu_stats Stats() const;
 
@@ -159,6 +194,14 @@ class VectorFlat : public VectorBase {
  public:
   static StatusOr<std::shared_ptr<VectorFlat<T>>> Create(const VectorIndexProto &vector_index_proto);  // vector_flat.cc:53-73
   int GetBlockSize() const { return (int)block_size_; }
+  // SaveIndexImpl -> BruteforceSearch::SaveIndex (vector_flat.cc:96-104, bruteforce.h:147-171): a header chunk, then
+  // one chunk per element in slot order = vector bytes (normalised for COSINE, as stored) + 8-byte label.
+  // Byte-compatible with what the CPU module writes for the same sequence of mutations.
+  Status SaveIndex(OutputStream &chunked_out) const;
+  // LoadFromRDB -> BruteforceSearch::LoadIndex (vector_flat.cc:75-94, bruteforce.h:173-207); the tracked keys are
+  // loaded separately with LoadTrackedKeys, as in the module.
+  static StatusOr<std::shared_ptr<VectorFlat<T>>> LoadFromStream(const VectorIndexProto &vector_index_proto,
+                                                                 InputStream &input);
   // vector_flat.cc:224-254.  FLAT + filter always pre-filters in the module (planner.cc:23-28): a filter here is
   // applied by evaluating it over the tracked keys and running the exact scan over the qualifying ones.
   StatusOr<std::vector<Neighbor>> Search(std::string_view query, uint64_t count, CancelToken cancellation_token,
