@@ -173,7 +173,9 @@ int vkgpu_merge_topk_packed_device(int device, const void *d_packed, uint32_t G,
 /* Rows [first_slot, first_slot+n) in SLOT order with their labels: what BruteforceSearch::SaveIndex walks
  * (third_party/hnswlib/bruteforce.h:147-171 — one chunk of vector bytes + label per element, slot by slot).  Slots
  * follow the reference exactly (insertion position, swap-delete), so the exported sequence is the one the CPU module
- * would write; loading is vkgpu_add_batch in the saved order (bruteforce.h:173-207). */
+ * would write; loading is vkgpu_add_batch in the saved order (bruteforce.h:173-207).  On an HNSW index the slot is
+ * the internal id, i.e. the element order of HierarchicalNSW::SaveIndex (hnswalg.h:841-850): the vectors that go
+ * with vkgpu_hnsw_export. */
 int vkgpu_flat_export(vkgpu_index *h, uint64_t first_slot, uint64_t n, float *out_vecs, uint64_t *out_labels);
 
 /* ---- HNSW graph interchange (hnswlib in-memory layout, hnswalg.h:152-176; "next" row N3) ----------- */

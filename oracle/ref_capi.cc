@@ -65,6 +65,7 @@ struct Flat {
 };
 
 struct Hnsw {
+  virtual ~Hnsw() = default;  // vkref_hnsw_load hands out a derived object
   std::unique_ptr<hnswlib::SpaceInterface<float>> space;
   std::unique_ptr<hnswlib::HierarchicalNSW<float>> algo;
   VecStore store;
@@ -273,6 +274,116 @@ uint32_t vkref_hnsw_links(void *h, uint32_t id, int level, uint32_t *out) {
 }
 const float *vkref_hnsw_vector(void *h, uint32_t id) {
   return reinterpret_cast<const float *>(static_cast<Hnsw *>(h)->algo->getDataByInternalId(id));
+}
+
+// ---------------------------------------------------------------- HNSW save / load (hnswalg.h:808-1139)
+// The reference's own SaveIndex / LoadIndex over an in-memory chunk stream.  The stream crosses this API as one flat
+// buffer: u64 chunk count, then per chunk u64 length + bytes.
+namespace {
+struct ChunkBuf : public hnswlib::OutputStream, public hnswlib::InputStream {
+  std::vector<std::string> chunks;
+  size_t next = 0;
+  absl::Status SaveChunk(const char *data, size_t len) override {
+    chunks.emplace_back(data, len);
+    return absl::OkStatus();
+  }
+  absl::StatusOr<std::unique_ptr<std::string>> LoadChunk() override {
+    if (next >= chunks.size()) return absl::NotFoundError("no more chunks");
+    return std::make_unique<std::string>(chunks[next++]);
+  }
+};
+struct StoreTracker : public hnswlib::VectorTracker {
+  VecStore *store;
+  // LoadIndex hands over the vector bytes of one element; the adapter layer owns them (vector_hnsw.cc:108-113).
+  // Keyed by slot order, not label, so that duplicate labels of old files keep their own bytes.
+  std::vector<std::unique_ptr<char[]>> owned;
+  char *TrackVector(uint64_t, char *vector, size_t len) override {
+    owned.emplace_back(new char[len]);
+    std::memcpy(owned.back().get(), vector, len);
+    return owned.back().get();
+  }
+};
+struct LoadedHnsw : public Hnsw {
+  StoreTracker tracker;
+};
+}  // namespace
+
+// forced level (> 0) as in the reference's golden builder (testing/vector_test.cc:866-893); level <= 0 => seeded RNG
+int vkref_hnsw_add_level(void *h, const float *v, uint64_t label, int level) {
+  auto *g = static_cast<Hnsw *>(h);
+  const float *p = g->store.Put(label, v);
+  try {
+    g->algo->addPoint(p, label, level);
+  } catch (...) {
+    return -1;
+  }
+  return 0;
+}
+
+// returns the number of bytes the flat buffer needs; fills `out` when cap is large enough
+uint64_t vkref_hnsw_save(void *h, uint8_t *out, uint64_t cap) {
+  auto *g = static_cast<Hnsw *>(h);
+  ChunkBuf buf;
+  if (!g->algo->SaveIndex(buf).ok()) return 0;
+  uint64_t need = 8;
+  for (auto &c : buf.chunks) need += 8 + c.size();
+  if (out && cap >= need) {
+    uint64_t n = buf.chunks.size();
+    std::memcpy(out, &n, 8);
+    uint8_t *p = out + 8;
+    for (auto &c : buf.chunks) {
+      uint64_t len = c.size();
+      std::memcpy(p, &len, 8);
+      std::memcpy(p + 8, c.data(), len);
+      p += 8 + len;
+    }
+  }
+  return need;
+}
+
+// VectorHNSW::LoadFromRDB (vector_hnsw.cc:133-170): empty HierarchicalNSW + LoadIndex; exceptions => error text.
+// Returns a handle usable with every vkref_hnsw_* call, or NULL with the message in err.
+void *vkref_hnsw_load(const uint8_t *buf, uint64_t len, size_t dim, int metric, size_t initial_cap, size_t expected_m,
+                      int validate, size_t ef_runtime, char *err, size_t errcap) {
+  auto fail = [&](const std::string &m) -> void * {
+    if (err && errcap) {
+      std::strncpy(err, m.c_str(), errcap - 1);
+      err[errcap - 1] = 0;
+    }
+    return nullptr;
+  };
+  ChunkBuf in;
+  {
+    if (len < 8) return fail("short buffer");
+    uint64_t n;
+    std::memcpy(&n, buf, 8);
+    uint64_t pos = 8;
+    for (uint64_t i = 0; i < n; i++) {
+      if (pos + 8 > len) return fail("short buffer");
+      uint64_t l;
+      std::memcpy(&l, buf + pos, 8);
+      pos += 8;
+      if (pos + l > len) return fail("short buffer");
+      in.chunks.emplace_back(reinterpret_cast<const char *>(buf + pos), l);
+      pos += l;
+    }
+  }
+  auto g = std::make_unique<LoadedHnsw>();
+  g->space = MakeSpace(dim, metric);
+  g->store.dim = dim;
+  g->block_size = 10240;
+  g->allow_replace_deleted = false;
+  g->tracker.store = &g->store;
+  try {
+    g->algo = std::make_unique<hnswlib::HierarchicalNSW<float>>(g->space.get());
+    g->algo->allow_replace_deleted_ = false;
+    auto st = g->algo->LoadIndex(in, g->space.get(), initial_cap, &g->tracker, expected_m, validate != 0);
+    if (!st.ok()) return fail(std::string(st.message()));
+    g->algo->setEf(ef_runtime);
+  } catch (const std::exception &e) {
+    return fail(std::string("HNSWLib error while loading an index: ") + e.what());
+  }
+  return static_cast<Hnsw *>(g.release());
 }
 
 }  // extern "C"

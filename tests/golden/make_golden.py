@@ -115,6 +115,23 @@ def ref_golden():
     print("ref_golden keys:", len(out), "skylake:", ref.vkref_uses_skylake())
 
 
+def hnsw_multilayer_golden():
+    """The reference test's MultiLayerGolden (testing/vector_test.cc:866-893, 963-968): 8 elements, D=100, M=16,
+    ef_construction=20, element 0 forced to level 2, element 1 to level 1, saved by the reference's own SaveIndex
+    (hnswalg.h:808-862).  Stored as the flat chunk container of oracle/ref_capi.cc."""
+    D, M, EFC, CAP = 100, 16, 20, 32
+    h = O.RefHnsw(D, O.L2, M=M, efc=EFC, ef=10, initial_cap=CAP)
+    for i, lv in enumerate([2, 1, 0, 0, 0, 0, 0, 0]):
+        v = np.full(D, 0.1, np.float32)
+        v[i % D] = float(i + 1)
+        O.ref_hnsw_add_level(h, v, i, lv)
+    chunks = O.ref_hnsw_save(h)
+    with open(os.path.join(HERE, "hnsw_multilayer_golden.bin"), "wb") as f:
+        f.write(O.pack_chunks(chunks))
+    print("hnsw_multilayer_golden.bin:", len(chunks), "chunks")
+
+
 if __name__ == "__main__":
     redisearch()
     ref_golden()
+    hnsw_multilayer_golden()

@@ -10,6 +10,7 @@
 #include <string>
 #include <vector>
 
+#include "../../valkey_search_b200/host/hnsw_serialization.h"
 #include "../../valkey_search_b200/host/vector_index.h"
 
 using namespace valkey_search::indexes;
@@ -399,6 +400,169 @@ static void SaveAndLoadFlat() {
   }
 }
 
+// SaveAndLoadHnsw (testing/vector_test.cc:502-580): save an EMPTY index, load it, populate it, recall >= 0.96, save,
+// load again, recall >= 0.96.  Here additionally: the reloaded index answers every query exactly like the one that
+// was saved (same graph on the same kernels), tombstones survive, and saving the reloaded index reproduces the
+// stream byte for byte.
+static void SaveAndLoadHnsw() {
+  for (auto metric : {DistanceMetric::kCosine, DistanceMetric::kL2}) {
+    const int initial_cap = 1000;
+    const uint64_t k = 10;
+    auto vectors = DeterministicallyGenerateVectors(1000, kDimensions, 2.2);
+    auto index_flat = VectorFlat<float>::Create(CreateFlatVectorIndexProto(kDimensions, metric, initial_cap, kBlockSize));
+    EXPECT_OK(index_flat);
+    if (!index_flat.ok()) return;
+    for (size_t i = 0; i < vectors.size(); ++i) VerifyAdd(index_flat->get(), vectors, i, ExpectedResults::kSuccess);
+    const VectorIndexProto hnsw_proto =
+        CreateHNSWVectorIndexProto(kDimensions, metric, initial_cap, kM, kEFConstruction, kEFRuntime);
+    MemoryStream empty_data, empty_keys;
+    {
+      auto index_hnsw = VectorHNSW<float>::Create(hnsw_proto);
+      EXPECT_OK(index_hnsw);
+      if (!index_hnsw.ok()) return;
+      if (metric == DistanceMetric::kCosine) EXPECT_TRUE((*index_hnsw)->GetNormalize());
+      EXPECT_OK((*index_hnsw)->SaveIndex(empty_data));
+      EXPECT_OK((*index_hnsw)->SaveTrackedKeys(empty_keys));
+      EXPECT_EQ(empty_data.chunks.size(), (size_t)1);  // header only (hnswalg.h:831-833)
+      HNSWIndexHeader h;
+      EXPECT_TRUE(h.ParseFromString(empty_data.chunks[0]));
+      EXPECT_EQ(h.max_level, -1);
+      EXPECT_EQ(h.enterpoint_node, 0xffffffffu);
+      EXPECT_EQ(h.m, (uint64_t)kM);
+      EXPECT_EQ(h.serialize_size_data_per_element, (uint64_t)(2 * kM * 4 + 4 + kDimensions * 4 + 8));
+    }
+    MemoryStream data, keys;
+    std::vector<std::vector<Neighbor>> before;
+    auto search_vectors = DeterministicallyGenerateVectors(50, kDimensions, 1.5);
+    {
+      auto loaded = VectorHNSW<float>::LoadFromStream(hnsw_proto, empty_data);
+      EXPECT_OK(loaded);
+      if (!loaded.ok()) return;
+      EXPECT_OK((*loaded)->LoadTrackedKeys(empty_keys));
+      for (size_t i = 0; i < vectors.size(); ++i) VerifyAdd(loaded->get(), vectors, i, ExpectedResults::kSuccess);
+      for (int i = 5; i < 1000; i += 23) {  // tombstones in the graph, swap-deletes in the exact index
+        EXPECT_OK((*loaded)->RemoveRecord(IndexToKey(i)));
+        EXPECT_OK((*index_flat)->RemoveRecord(IndexToKey(i)));
+      }
+      EXPECT_TRUE(CalcRecall(index_flat->get(), loaded->get(), k, kDimensions, kEFRuntime) >= 0.96f);
+      for (const auto &q : search_vectors) {
+        auto r = (*loaded)->Search(VectorToStr(q), k, CancelNever());
+        EXPECT_OK(r);
+        before.push_back(r.ok() ? *r : std::vector<Neighbor>());
+      }
+      EXPECT_OK((*loaded)->SaveIndex(data));
+      EXPECT_OK((*loaded)->SaveTrackedKeys(keys));
+    }
+    auto reloaded = VectorHNSW<float>::LoadFromStream(hnsw_proto, data);
+    EXPECT_OK(reloaded);
+    if (!reloaded.ok()) {
+      std::fprintf(stderr, "  load: %s\n", reloaded.status().message().c_str());
+      continue;
+    }
+    EXPECT_OK((*reloaded)->LoadTrackedKeys(keys));
+    EXPECT_TRUE(CalcRecall(index_flat->get(), reloaded->get(), k, kDimensions, kEFRuntime) >= 0.96f);
+    for (size_t qi = 0; qi < search_vectors.size(); qi++) {
+      auto r = (*reloaded)->Search(VectorToStr(search_vectors[qi]), k, CancelNever());
+      EXPECT_OK(r);
+      if (!r.ok()) continue;
+      EXPECT_EQ(r->size(), before[qi].size());
+      for (size_t j = 0; j < r->size() && j < before[qi].size(); j++) {
+        EXPECT_EQ((*r)[j].external_id, before[qi][j].external_id);
+        EXPECT_TRUE(std::memcmp(&(*r)[j].distance, &before[qi][j].distance, 4) == 0);
+      }
+      for (const auto &nb : *r) {  // a tombstoned key is never returned
+        const int id = std::atoi(nb.external_id.c_str());
+        EXPECT_TRUE(!(id >= 5 && (id - 5) % 23 == 0));
+      }
+    }
+    MemoryStream again;
+    EXPECT_OK((*reloaded)->SaveIndex(again));
+    EXPECT_EQ(again.chunks.size(), data.chunks.size());
+    size_t differing = 0;
+    for (size_t i = 1; i < again.chunks.size() && i < data.chunks.size(); i++) differing += again.chunks[i] != data.chunks[i];
+    EXPECT_EQ(differing, (size_t)0);
+    // the index stays usable after a load: new keys continue after the largest loaded id and are found
+    // (alternating signs: no stored vector points the same way, so the COSINE answer is unique too)
+    std::vector<std::vector<float>> extra(1, std::vector<float>(kDimensions));
+    for (int j = 0; j < kDimensions; j++) extra[0][j] = (j % 2 ? -1.0f : 1.0f) * (float)(j + 1);
+    EXPECT_OK((*reloaded)->AddRecord("fresh_key", VectorToStr(extra[0])));
+    auto r = (*reloaded)->Search(VectorToStr(extra[0]), 1, CancelNever());
+    EXPECT_OK(r);
+    if (r.ok() && !r->empty()) EXPECT_EQ((*r)[0].external_id, std::string("fresh_key"));
+    // a corrupted stream is rejected with the reference's message (hnswalg.h:1000)
+    MemoryStream bad = data;
+    bad.next = 0;
+    uint16_t too_many = 2 * kM + 1;
+    std::memcpy(bad.chunks[1].data(), &too_many, 2);
+    auto rejected = VectorHNSW<float>::LoadFromStream(hnsw_proto, bad);
+    EXPECT_FALSE(rejected.ok());
+    EXPECT_TRUE(rejected.status().message().find("level-0 neighbor count exceeds 2*M") != std::string::npos);
+  }
+}
+
+// ---- host-only modes for tests/test_hnsw_serialization.py: chunk streams cross the process boundary as one file,
+// u64 chunk count, then per chunk u64 length + bytes (the same container oracle/ref_capi.cc uses).
+static bool ReadStreamFile(const char *path, MemoryStream &out) {
+  FILE *f = std::fopen(path, "rb");
+  if (!f) return false;
+  uint64_t n = 0;
+  bool ok = std::fread(&n, 8, 1, f) == 1;
+  for (uint64_t i = 0; ok && i < n; i++) {
+    uint64_t len = 0;
+    ok = std::fread(&len, 8, 1, f) == 1 && len < (1ull << 32);
+    if (!ok) break;
+    std::string c(len, '\0');
+    ok = len == 0 || std::fread(c.data(), 1, len, f) == len;
+    out.chunks.push_back(std::move(c));
+  }
+  std::fclose(f);
+  return ok;
+}
+static bool WriteStreamFile(const char *path, const MemoryStream &s) {
+  FILE *f = std::fopen(path, "wb");
+  if (!f) return false;
+  const uint64_t n = s.chunks.size();
+  std::fwrite(&n, 8, 1, f);
+  for (const auto &c : s.chunks) {
+    const uint64_t len = c.size();
+    std::fwrite(&len, 8, 1, f);
+    std::fwrite(c.data(), 1, len, f);
+  }
+  return std::fclose(f) == 0;
+}
+// --hnsw-load IN DIM CAP M VALIDATE [OUT]: LoadHnswImage on the stream; prints "OK n max_level enterpoint
+// max_elements duplicates deleted" or "ERR message"; with OUT, SaveHnswImage of what was loaded goes there.
+static int HnswLoadMode(int argc, char **argv) {
+  if (argc < 7) return 2;
+  MemoryStream in;
+  if (!ReadStreamFile(argv[2], in)) return 2;
+  const size_t dim = std::strtoull(argv[3], nullptr, 10), cap = std::strtoull(argv[4], nullptr, 10);
+  const size_t m = std::strtoull(argv[5], nullptr, 10);
+  const bool validate = std::atoi(argv[6]) != 0;
+  auto loaded = LoadHnswImage(in, dim, cap, m, validate);
+  if (!loaded.ok()) {
+    std::printf("ERR %s\n", loaded.status().message().c_str());
+    return 0;
+  }
+  const HnswGraphImage &g = loaded->image;
+  uint64_t deleted = 0;
+  for (uint8_t d : g.deleted) deleted += d;
+  std::printf("OK %llu %d %u %llu %llu %llu\n", (unsigned long long)g.n, g.max_level, g.enterpoint,
+              (unsigned long long)loaded->max_elements, (unsigned long long)loaded->duplicate_labels,
+              (unsigned long long)deleted);
+  if (argc > 7) {
+    MemoryStream out;
+    const HnswRowFetcher rows = [&](uint64_t first, uint64_t count, float *dst) {
+      std::memcpy(dst, g.vecs.data() + first * dim, count * dim * sizeof(float));
+      return vks::OkStatus();
+    };
+    // max_elements as the header recorded it: the reference re-saves max_elements_ = the resolved capacity
+    const vks::Status s = SaveHnswImage(g, dim, loaded->max_elements, loaded->ef_construction, rows, out);
+    if (!s.ok() || !WriteStreamFile(argv[7], out)) return 3;
+  }
+  return 0;
+}
+
 static std::string Hex(const std::string &s) {
   static const char *d = "0123456789abcdef";
   std::string out;
@@ -423,6 +587,44 @@ static int PrintWire() {
       return 2;
     std::printf("header %llu %llu %llu %s\n", (unsigned long long)h[0], (unsigned long long)h[1], (unsigned long long)h[2],
                 Hex(m.SerializeAsString()).c_str());
+  }
+  {
+    struct {
+      uint64_t cap, count;
+      int32_t max_level;
+      uint32_t ep;
+      uint64_t m;
+      double mult;
+      uint64_t efc;
+    } cases[] = {{1000, 0, -1, 0xffffffffu, 16, 1 / std::log(16.0), 20},
+                 {32, 8, 2, 0, 16, 1 / std::log(16.0), 200},
+                 {10240000, 10000000, 5, 123456, 32, 1 / std::log(32.0), 400},
+                 {0, 0, 0, 0, 0, 0.0, 0},
+                 {5, 5, 0, 4, 2, -0.0, 1}};
+    for (const auto &c : cases) {
+      HNSWIndexHeader m;
+      m.max_elements = c.cap;
+      m.curr_element_count = c.count;
+      m.serialize_size_data_per_element = c.m * 8 + 4 + 400 + 8;
+      m.label_offset = ((c.m * 8 + 4 + 7) & ~7ull) + 8;
+      m.offset_data = c.m * 8 + 4;
+      m.max_level = c.max_level;
+      m.enterpoint_node = c.ep;
+      m.max_m = c.m;
+      m.max_m_0 = 2 * c.m;
+      m.m = c.m;
+      m.mult = c.mult;
+      m.ef_construction = c.efc;
+      HNSWIndexHeader back;
+      if (!back.ParseFromString(m.SerializeAsString()) || back.max_level != c.max_level || back.enterpoint_node != c.ep ||
+          std::memcmp(&back.mult, &c.mult, 8) != 0 || back.ef_construction != c.efc || back.max_m_0 != 2 * c.m)
+        return 2;
+      uint64_t bits;
+      std::memcpy(&bits, &c.mult, 8);
+      std::printf("hnsw %llu %llu %d %u %llu %016llx %llu %s\n", (unsigned long long)c.cap, (unsigned long long)c.count,
+                  c.max_level, c.ep, (unsigned long long)c.m, (unsigned long long)bits, (unsigned long long)c.efc,
+                  Hex(m.SerializeAsString()).c_str());
+    }
   }
   struct {
     const char *key;
@@ -465,6 +667,7 @@ static void HostOnly(bool have_gpu) {
 
 int main(int argc, char **argv) {
   if (argc > 1 && std::string(argv[1]) == "--wire") return PrintWire();
+  if (argc > 1 && std::string(argv[1]) == "--hnsw-load") return HnswLoadMode(argc, argv);
   const bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";
   struct Case {
     const char *name;
@@ -475,6 +678,7 @@ int main(int argc, char **argv) {
                {"IntegrationCosineGoldens", IntegrationCosineGoldens},
                {"Prefilter", Prefilter},
                {"SaveAndLoadFlat", SaveAndLoadFlat},
+               {"SaveAndLoadHnsw", SaveAndLoadHnsw},
                {"InlineFilterAndBatch", InlineFilterAndBatch}};
   {
     const int before = g_failures;

@@ -118,6 +118,10 @@ def ref():
         _sig(lib, "vkref_hnsw_deleted", C.c_int, [C.c_void_p, C.c_uint32])
         _sig(lib, "vkref_hnsw_links", C.c_uint32, [C.c_void_p, C.c_uint32, C.c_int, _u32p])
         _sig(lib, "vkref_hnsw_vector", C.POINTER(C.c_float), [C.c_void_p, C.c_uint32])
+        _sig(lib, "vkref_hnsw_add_level", C.c_int, [C.c_void_p, _f32p, C.c_uint64, C.c_int])
+        _sig(lib, "vkref_hnsw_save", C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64])
+        _sig(lib, "vkref_hnsw_load", C.c_void_p,
+             [C.c_char_p, C.c_uint64, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t])
         _ref = lib
     return _ref
 
@@ -365,6 +369,56 @@ class RefHnsw(_HnswCommon):
 
     def _links(self, i, lv, buf):
         return self.lib.vkref_hnsw_links(self.h, i, lv, buf)
+
+
+def pack_chunks(chunks):
+    """Chunk stream -> the flat container of oracle/ref_capi.cc (u64 count, then u64 length + bytes per chunk)."""
+    import struct
+    out = [struct.pack("<Q", len(chunks))]
+    for c in chunks:
+        out.append(struct.pack("<Q", len(c)))
+        out.append(bytes(c))
+    return b"".join(out)
+
+
+def unpack_chunks(buf):
+    import struct
+    (n,) = struct.unpack_from("<Q", buf, 0)
+    pos, chunks = 8, []
+    for _ in range(n):
+        (ln,) = struct.unpack_from("<Q", buf, pos)
+        chunks.append(bytes(buf[pos + 8: pos + 8 + ln]))
+        pos += 8 + ln
+    return chunks
+
+
+def ref_hnsw_add_level(h, v, label, level):
+    """HierarchicalNSW::addPoint(data, label, level): a forced level (> 0), as the reference's golden builder does."""
+    rc = h.lib.vkref_hnsw_add_level(h.h, np.ascontiguousarray(v, np.float32), int(label), int(level))
+    assert rc == 0
+
+
+def ref_hnsw_save(h):
+    """The reference's HierarchicalNSW::SaveIndex (hnswalg.h:808-862) -> list of chunks."""
+    need = h.lib.vkref_hnsw_save(h.h, None, 0)
+    assert need >= 8
+    buf = C.create_string_buffer(need)
+    assert h.lib.vkref_hnsw_save(h.h, buf, need) == need
+    return unpack_chunks(buf.raw)
+
+
+def ref_hnsw_load(chunks, dim, metric, initial_cap, expected_m, validate=True, ef=10):
+    """The reference's LoadFromRDB path (vector_hnsw.cc:133-170 -> hnswalg.h:886-1139).  Returns (RefHnsw, None) or
+    (None, error message)."""
+    lib = ref()
+    data = pack_chunks(chunks)
+    err = C.create_string_buffer(512)
+    hnd = lib.vkref_hnsw_load(data, len(data), dim, metric, initial_cap, expected_m, 1 if validate else 0, ef, err, 512)
+    if not hnd:
+        return None, err.value.decode()
+    obj = RefHnsw.__new__(RefHnsw)
+    obj.lib, obj.dim, obj.h = lib, dim, hnd
+    return obj, None
 
 
 def deterministic_vectors(size, dim, max_value):

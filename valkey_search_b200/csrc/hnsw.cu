@@ -1076,7 +1076,8 @@ void hnsw_import(vkgpu_index_impl *ix, uint64_t n, const int32_t *levels, const 
       const uint64_t src = upper_offset[i] + lv, dst = g->h_up_off[i] + lv;
       VK_REQUIRE(upper_cnt[src] <= g->maxM, VKGPU_ERR_INVALID, "upper list longer than M");
       up[dst * (1 + g->maxM)] = upper_cnt[src];
-      std::memcpy(&up[dst * (1 + g->maxM) + 1], upper_links + src * g->maxM, upper_cnt[src] * 4);
+      // the whole block, stale tail included: a saved file re-exports byte for byte (hnswalg.h:855-858)
+      std::memcpy(&up[dst * (1 + g->maxM) + 1], upper_links + src * g->maxM, (size_t)g->maxM * 4);
     }
   }
   g->up.reserve(up.size() * 4 + (size_t)(1 + g->maxM) * 4 * 1024);

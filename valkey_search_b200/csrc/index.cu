@@ -830,7 +830,6 @@ int vkgpu_get(vkgpu_index *ix, uint64_t label, float *out_vec) {
 int vkgpu_flat_export(vkgpu_index *ix, uint64_t first_slot, uint64_t n, float *out_vecs, uint64_t *out_labels) {
   return guarded([&] {
     VK_REQUIRE(ix && (n == 0 || (out_vecs && out_labels)), VKGPU_ERR_INVALID, "null argument");
-    VK_REQUIRE(ix->cfg.algo == VKGPU_FLAT, VKGPU_ERR_INVALID, "slot-order export is FLAT only");
     std::shared_lock<std::shared_mutex> lk(ix->rw);
     VK_REQUIRE(first_slot + n <= ix->n, VKGPU_ERR_INVALID, "slot range beyond the element count");
     if (n == 0) return;

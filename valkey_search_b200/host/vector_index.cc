@@ -3,6 +3,8 @@
 // normalisation below must round `src[i] * src[i]` before the add exactly like vector_base.cc:112-124 does.
 #include "vector_index.h"
 
+#include "hnsw_serialization.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -575,6 +577,63 @@ StatusOr<std::vector<Neighbor>> VectorHNSW<T>::Search(std::string_view query, ui
   f.label_bitmap = bitmap.data();
   f.bitmap_bits = bitmap.size() * 8;
   return SearchOne(query, count, ef, &f, token);
+}
+
+template <typename T>
+Status VectorHNSW<T>::SaveIndex(OutputStream &chunked_out) const {
+  HnswGraphImage g;
+  g.M = m_;
+  uint64_t n = 0, blocks = 0;
+  VKS_RETURN_IF_ERROR(FromRc(vkgpu_hnsw_export(gpu_, &n, &blocks, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                               nullptr, nullptr, &g.max_level, &g.enterpoint)));
+  g.n = n;
+  g.levels.resize(n);
+  g.labels.resize(n);
+  g.deleted.resize(n);
+  g.links0.resize(n * 2 * (size_t)m_);
+  g.cnt0.resize(n);
+  g.upper_links.resize(std::max<uint64_t>(blocks, 1) * m_);
+  g.upper_cnt.resize(std::max<uint64_t>(blocks, 1));
+  g.upper_offset.resize(n);
+  if (n)
+    VKS_RETURN_IF_ERROR(FromRc(vkgpu_hnsw_export(gpu_, &n, &blocks, g.levels.data(), g.labels.data(), g.deleted.data(),
+                                                 g.links0.data(), g.cnt0.data(), g.upper_links.data(),
+                                                 g.upper_cnt.data(), g.upper_offset.data(), &g.max_level,
+                                                 &g.enterpoint)));
+  if (n == 0) {  // hnswalg.h:168-169: an empty graph has no entry point
+    g.max_level = -1;
+    g.enterpoint = 0xffffffffu;
+  }
+  std::vector<uint64_t> row_labels;
+  const HnswRowFetcher rows = [&](uint64_t first, uint64_t count, float *out) {
+    row_labels.resize(count);
+    return FromRc(vkgpu_flat_export(gpu_, first, count, out, row_labels.data()));
+  };
+  // ef_construction_ = max(ef_construction, M) in the reference's constructor (hnswalg.h:146)
+  return SaveHnswImage(g, (size_t)dimensions_, Stats().capacity, std::max<uint64_t>(ef_construction_, m_), rows,
+                       chunked_out);
+}
+
+template <typename T>
+StatusOr<std::shared_ptr<VectorHNSW<T>>> VectorHNSW<T>::LoadFromStream(const VectorIndexProto &p, InputStream &input,
+                                                                       bool validate) {
+  auto loaded = LoadHnswImage(input, p.dimension_count, p.initial_cap, p.hnsw_algorithm.m, validate);
+  if (!loaded.ok()) return loaded.status();
+  const HnswGraphImage &g = loaded->image;
+  VectorIndexProto q = p;
+  q.initial_cap = loaded->max_elements;
+  q.hnsw_algorithm.m = g.M;  // equals p's M unless validation is off (the header's geometry rules, hnswalg.h:905-907)
+  if (loaded->ef_construction) q.hnsw_algorithm.ef_construction = (uint32_t)loaded->ef_construction;
+  auto created = Create(q);
+  if (!created.ok()) return created.status();
+  auto index = *created;
+  if (g.n) {
+    const Status s = index->FromRc(vkgpu_hnsw_import(
+        index->gpu_, g.n, g.levels.data(), g.labels.data(), g.deleted.data(), g.links0.data(), g.cnt0.data(),
+        g.upper_links.data(), g.upper_cnt.data(), g.upper_offset.data(), g.max_level, g.enterpoint, g.vecs.data()));
+    if (!s.ok()) return s;
+  }
+  return index;
 }
 
 template class VectorFlat<float>;

@@ -31,6 +31,7 @@
 #include <vector>
 
 #include "../../include/vkgpu.h"
+#include "chunk_stream.h"
 #include "status.h"
 
 namespace valkey_search::indexes {
@@ -68,20 +69,6 @@ struct VectorIndexProto {  // data_model::VectorIndex, src/index_schema.proto:87
   uint32_t gpu_max_batch{1024};
   uint32_t gpu_batch_window_us{0};
   bool hnsw_allow_replace_deleted{false};
-};
-
-// Chunk streams of the save/load path (third_party/hnswlib/iostream.h:27-42; the module's implementations are
-// RDBChunkOutputStream / RDBChunkInputStream, src/rdb_serialization.h).
-class OutputStream {
- public:
-  virtual ~OutputStream() = default;
-  virtual Status SaveChunk(const char *data, size_t len) = 0;
-};
-class InputStream {
- public:
-  virtual ~InputStream() = default;
-  virtual StatusOr<std::unique_ptr<std::string>> LoadChunk() = 0;
-  virtual bool HasNext() const = 0;  // SupplementalContentChunkIter::HasNext
 };
 
 // The two protobuf messages of this path, hand-encoded in proto3 wire format (no protobuf in the image):
@@ -228,6 +215,15 @@ class VectorHNSW : public VectorBase {
                                          const KeyFilter *filter = nullptr,
                                          std::optional<size_t> ef_runtime = std::nullopt,
                                          bool enable_partial_results = false) const;
+  // SaveIndexImpl -> HierarchicalNSW::SaveIndex (vector_hnsw.cc, hnswalg.h:808-862): header chunk, one level-0
+  // record + vector + label chunk per element, then the upper lists — hnswlib's format, so the file loads in the
+  // CPU module and a CPU-written file loads here (host/hnsw_serialization.h).
+  Status SaveIndex(OutputStream &chunked_out) const;
+  // LoadFromRDB -> HierarchicalNSW::LoadIndex (vector_hnsw.cc:133-160, hnswalg.h:886-1139) with the reference's
+  // load-time validation (`validate` = the hnsw-validation-enable config); ef_runtime comes from the proto, it is
+  // not persisted.  Tracked keys are loaded separately with LoadTrackedKeys, as in the module.
+  static StatusOr<std::shared_ptr<VectorHNSW<T>>> LoadFromStream(const VectorIndexProto &vector_index_proto,
+                                                                 InputStream &input, bool validate = true);
 
  private:
   VectorHNSW(int dimensions, DistanceMetric metric) : VectorBase(dimensions, metric) {}
