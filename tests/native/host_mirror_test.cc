@@ -563,6 +563,106 @@ static int HnswLoadMode(int argc, char **argv) {
   return 0;
 }
 
+// ---- GPU modes for tests/test_hnsw_interchange_gpu.py (files cross between the reference and the GPU index)
+static bool ReadFloats(const char *path, std::vector<float> &out) {
+  FILE *f = std::fopen(path, "rb");
+  if (!f) return false;
+  std::fseek(f, 0, SEEK_END);
+  const long bytes = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  out.resize((size_t)bytes / 4);
+  const bool ok = std::fread(out.data(), 4, out.size(), f) == out.size();
+  std::fclose(f);
+  return ok;
+}
+// keys of a loaded stream: one TrackedKeyMetadata chunk per level-0 record, key = decimal label
+static MemoryStream KeysOf(const MemoryStream &data, size_t dim, size_t m) {
+  MemoryStream keys;
+  HNSWIndexHeader h;
+  if (!h.ParseFromString(data.chunks[0])) return keys;
+  const size_t label_off = 2 * m * 4 + 4 + dim * 4;
+  for (uint64_t i = 0; i < h.curr_element_count; i++) {
+    uint64_t label;
+    std::memcpy(&label, data.chunks[1 + i].data() + label_off, 8);
+    uint32_t word;
+    std::memcpy(&word, data.chunks[1 + i].data(), 4);
+    if (word & (1u << 16)) continue;  // tombstoned elements have no key any more
+    TrackedKeyMetadataPb pb;
+    pb.key = std::to_string(label);
+    pb.internal_id = label;
+    pb.magnitude = kDefaultMagnitude;
+    const std::string b = pb.SerializeAsString();
+    keys.chunks.emplace_back(b);
+  }
+  return keys;
+}
+// --hnsw-gpu-load IN DIM CAP M QUERIES K EF RESULTS RESAVED: a stream written by the CPU module -> LoadFromStream ->
+// search every query on the GPU (results: per query u32 n, then n x {u64 label, f32 distance}) -> SaveIndex again.
+static int HnswGpuLoadMode(int argc, char **argv) {
+  if (argc < 11) return 2;
+  MemoryStream in;
+  if (!ReadStreamFile(argv[2], in)) return 2;
+  const int dim = std::atoi(argv[3]), cap = std::atoi(argv[4]), m = std::atoi(argv[5]);
+  std::vector<float> Q;
+  if (!ReadFloats(argv[6], Q)) return 2;
+  const uint64_t k = std::strtoull(argv[7], nullptr, 10);
+  const size_t ef = std::strtoull(argv[8], nullptr, 10);
+  auto loaded = VectorHNSW<float>::LoadFromStream(CreateHNSWVectorIndexProto(dim, DistanceMetric::kL2, cap, m, 200, 10), in);
+  if (!loaded.ok()) {
+    std::printf("ERR %s\n", loaded.status().message().c_str());
+    return 1;
+  }
+  MemoryStream keys = KeysOf(in, dim, m);
+  if (!(*loaded)->LoadTrackedKeys(keys).ok()) return 3;
+  FILE *f = std::fopen(argv[9], "wb");
+  if (!f) return 3;
+  for (size_t q = 0; q + dim <= Q.size(); q += dim) {
+    auto r = (*loaded)->Search(std::string_view(reinterpret_cast<const char *>(&Q[q]), (size_t)dim * 4), k, CancelNever(),
+                               nullptr, ef);
+    if (!r.ok()) {
+      std::printf("ERR %s\n", r.status().message().c_str());
+      return 1;
+    }
+    const uint32_t n = (uint32_t)r->size();
+    std::fwrite(&n, 4, 1, f);
+    for (const auto &nb : *r) {
+      const uint64_t label = std::strtoull(nb.external_id.c_str(), nullptr, 10);
+      std::fwrite(&label, 8, 1, f);
+      std::fwrite(&nb.distance, 4, 1, f);
+    }
+  }
+  std::fclose(f);
+  MemoryStream out;
+  if (!(*loaded)->SaveIndex(out).ok() || !WriteStreamFile(argv[10], out)) return 3;
+  std::printf("OK %zu\n", (*loaded)->GetTrackedKeyCount());
+  return 0;
+}
+// --hnsw-gpu-build VECTORS DIM M EFC DELETE_EVERY OUT: build on the GPU through AddRecord (keys = decimal row index),
+// tombstone every DELETE_EVERY-th key, SaveIndex -> OUT (for the CPU module to load).
+static int HnswGpuBuildMode(int argc, char **argv) {
+  if (argc < 8) return 2;
+  std::vector<float> X;
+  if (!ReadFloats(argv[2], X)) return 2;
+  const int dim = std::atoi(argv[3]), m = std::atoi(argv[4]), efc = std::atoi(argv[5]), every = std::atoi(argv[6]);
+  const size_t n = X.size() / dim;
+  auto index = VectorHNSW<float>::Create(CreateHNSWVectorIndexProto(dim, DistanceMetric::kL2, (int)n, m, efc, 10));
+  if (!index.ok()) {
+    std::printf("ERR %s\n", index.status().message().c_str());
+    return 1;
+  }
+  for (size_t i = 0; i < n; i++) {
+    auto r = (*index)->AddRecord(std::to_string(i), std::string_view(reinterpret_cast<const char *>(&X[i * dim]), (size_t)dim * 4));
+    if (!r.ok() || *r != RecordResult::kAdded) return 3;
+  }
+  if (every > 0)
+    for (size_t i = 1; i < n; i += every)
+      if (!(*index)->RemoveRecord(std::to_string(i)).ok()) return 3;
+  MemoryStream out;
+  if (!(*index)->SaveIndex(out).ok() || !WriteStreamFile(argv[7], out)) return 3;
+  std::printf("OK %zu\n", (*index)->GetTrackedKeyCount());
+  return 0;
+}
+
 static std::string Hex(const std::string &s) {
   static const char *d = "0123456789abcdef";
   std::string out;
@@ -668,6 +768,8 @@ static void HostOnly(bool have_gpu) {
 int main(int argc, char **argv) {
   if (argc > 1 && std::string(argv[1]) == "--wire") return PrintWire();
   if (argc > 1 && std::string(argv[1]) == "--hnsw-load") return HnswLoadMode(argc, argv);
+  if (argc > 1 && std::string(argv[1]) == "--hnsw-gpu-load") return HnswGpuLoadMode(argc, argv);
+  if (argc > 1 && std::string(argv[1]) == "--hnsw-gpu-build") return HnswGpuBuildMode(argc, argv);
   const bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";
   struct Case {
     const char *name;
