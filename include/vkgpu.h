@@ -99,8 +99,9 @@ typedef struct vkgpu_stats {
   uint64_t hbm_bytes;        /* device memory owned by the index                                       */
   uint64_t searches;         /* queries answered                                                       */
   uint64_t kernels_launched; /* CUDA kernels launched by this handle (bench.py "gpu_launches")         */
-  uint64_t distance_evals;   /* HNSW: metric_distance_computations analog (hnswalg.h:98-99)            */
-  uint64_t hops;             /* HNSW: metric_hops analog                                               */
+  uint64_t distance_evals;   /* HNSW: metric_distance_computations analog (hnswalg.h:98-99), summed over the
+                                queries of the MOST RECENT search call on this index                    */
+  uint64_t hops;             /* HNSW: metric_hops analog, same scope                                   */
   uint64_t tensor_fallbacks; /* TENSOR-path queries whose candidate margin was too thin and that were
                                 re-run on the exact FMA path (still on the GPU)                        */
   int32_t max_level;         /* HNSW maxlevel_                                                         */

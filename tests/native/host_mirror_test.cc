@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <ctime>
 #include <string>
 #include <vector>
 
@@ -500,6 +501,42 @@ static void SaveAndLoadHnsw() {
   }
 }
 
+// vkgpu_stats.hops / distance_evals describe the MOST RECENT search call (bench.py divides them by that call's
+// batch to state algorithmic bytes): repeating a call repeats the numbers, a batch is the sum of its queries.
+static void HnswCountersPerCall() {
+  auto index = VectorHNSW<float>::Create(CreateHNSWVectorIndexProto(kDimensions, DistanceMetric::kL2, 2000, kM, 100, 64));
+  EXPECT_OK(index);
+  if (!index.ok()) return;
+  auto vectors = DeterministicallyGenerateVectors(2000, kDimensions, 3.0);
+  for (size_t i = 0; i < vectors.size(); ++i) VerifyAdd(index->get(), vectors, i, ExpectedResults::kSuccess);
+  auto queries = DeterministicallyGenerateVectors(8, kDimensions, 1.7);
+  uint64_t hops[8], evals[8], sum_h = 0, sum_e = 0;
+  for (int rep = 0; rep < 2; rep++)
+    for (int i = 0; i < 8; i++) {
+      EXPECT_OK((*index)->Search(VectorToStr(queries[i]), 10, CancelNever()));
+      const vkgpu_stats st = (*index)->Stats();
+      EXPECT_TRUE(st.hops > 0 && st.distance_evals >= st.hops);
+      EXPECT_TRUE(st.distance_evals < 2000 + 512);  // level 0 evaluates a node at most once; the descent adds a few
+      if (rep == 0) {
+        hops[i] = st.hops;
+        evals[i] = st.distance_evals;
+        sum_h += st.hops;
+        sum_e += st.distance_evals;
+      } else {
+        EXPECT_EQ(st.hops, hops[i]);
+        EXPECT_EQ(st.distance_evals, evals[i]);
+      }
+    }
+  std::string flat;
+  for (const auto &q : queries) flat.append(reinterpret_cast<const char *>(q.data()), q.size() * 4);
+  for (int rep = 0; rep < 2; rep++) {
+    EXPECT_OK((*index)->SearchBatch(flat, 8, 10));
+    const vkgpu_stats st = (*index)->Stats();
+    EXPECT_EQ(st.hops, sum_h);
+    EXPECT_EQ(st.distance_evals, sum_e);
+  }
+}
+
 // ---- host-only modes for tests/test_hnsw_serialization.py: chunk streams cross the process boundary as one file,
 // u64 chunk count, then per chunk u64 length + bytes (the same container oracle/ref_capi.cc uses).
 static bool ReadStreamFile(const char *path, MemoryStream &out) {
@@ -663,6 +700,74 @@ static int HnswGpuBuildMode(int argc, char **argv) {
   return 0;
 }
 
+// --hnsw-perf N DIM BATCH K EF REPS: clustered corpus built on the GPU with one vkgpu_add_batch, then the same batch
+// searched REPS times per setting of the environment variable named in VAR (unset / set), wall-clock per batch.
+// A quick A/B of a kernel switch inside one process; the numbers that count are bench.py's.
+static int HnswPerfMode(int argc, char **argv) {
+  if (argc < 9) return 2;
+  const size_t n = std::strtoull(argv[2], nullptr, 10);
+  const int dim = std::atoi(argv[3]), batch = std::atoi(argv[4]), k = std::atoi(argv[5]), ef = std::atoi(argv[6]);
+  const int reps = std::atoi(argv[7]);
+  const char *var = argv[8];
+  uint64_t rng = 88172645463325252ull;
+  auto uni = [&]() {
+    rng ^= rng << 13;
+    rng ^= rng >> 7;
+    rng ^= rng << 17;
+    return (float)((rng >> 11) * (1.0 / 9007199254740992.0));
+  };
+  auto gauss = [&]() {  // Irwin-Hall, good enough for a timing corpus
+    float s = 0;
+    for (int i = 0; i < 12; i++) s += uni();
+    return s - 6.0f;
+  };
+  const size_t ncent = std::max<size_t>(n / 1000, 8);
+  std::vector<float> cent(ncent * dim), X(n * dim), Q((size_t)batch * dim);
+  for (auto &v : cent) v = gauss();
+  for (size_t i = 0; i < n; i++) {
+    const size_t c = (size_t)(uni() * ncent) % ncent;
+    for (int j = 0; j < dim; j++) X[i * dim + j] = cent[c * dim + j] + 0.3f * gauss();
+  }
+  for (int i = 0; i < batch; i++) {
+    const size_t c = (size_t)(uni() * ncent) % ncent;
+    for (int j = 0; j < dim; j++) Q[(size_t)i * dim + j] = cent[c * dim + j] + 0.3f * gauss();
+  }
+  auto index = VectorHNSW<float>::Create(CreateHNSWVectorIndexProto(dim, DistanceMetric::kL2, (int)n, 16, 200, ef));
+  if (!index.ok()) {
+    std::printf("ERR %s\n", index.status().message().c_str());
+    return 1;
+  }
+  std::vector<uint64_t> labels(n);
+  for (size_t i = 0; i < n; i++) labels[i] = i;
+  timespec t0, t1;
+  clock_gettime(CLOCK_MONOTONIC, &t0);
+  if (vkgpu_add_batch((*index)->handle(), labels.data(), X.data(), n) != 0) return 3;
+  clock_gettime(CLOCK_MONOTONIC, &t1);
+  std::printf("build %zu x %d: %.2f s\n", n, dim, (t1.tv_sec - t0.tv_sec) + (t1.tv_nsec - t0.tv_nsec) * 1e-9);
+  std::vector<float> od((size_t)batch * k), od2((size_t)batch * k);
+  std::vector<uint64_t> ol((size_t)batch * k), ol2((size_t)batch * k);
+  std::vector<uint32_t> on(batch);
+  for (int setting = 0; setting < 4; setting++) {
+    const bool set = setting & 1;
+    if (set) setenv(var, "1", 1); else unsetenv(var);
+    auto &d = set ? od2 : od;
+    auto &l = set ? ol2 : ol;
+    for (int w = 0; w < 3; w++)
+      if (vkgpu_search_batch((*index)->handle(), Q.data(), batch, k, ef, nullptr, 0, d.data(), l.data(), on.data()) != 0) return 3;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    for (int r = 0; r < reps; r++)
+      if (vkgpu_search_batch((*index)->handle(), Q.data(), batch, k, ef, nullptr, 0, d.data(), l.data(), on.data()) != 0) return 3;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double ms = ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6) / reps;
+    const vkgpu_stats st = (*index)->Stats();
+    std::printf("%s=%s: %.3f ms per batch of %d (host buffers), %.0f QPS; hops/query %.1f, evaluations/query %.1f\n", var,
+                set ? "1" : "unset", ms, batch, batch / ms * 1e3, (double)st.hops / batch, (double)st.distance_evals / batch);
+  }
+  std::printf("results identical across settings: %s\n",
+              (od == od2 && ol == ol2) ? "yes" : "NO");
+  return (od == od2 && ol == ol2) ? 0 : 1;
+}
+
 static std::string Hex(const std::string &s) {
   static const char *d = "0123456789abcdef";
   std::string out;
@@ -770,6 +875,7 @@ int main(int argc, char **argv) {
   if (argc > 1 && std::string(argv[1]) == "--hnsw-load") return HnswLoadMode(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--hnsw-gpu-load") return HnswGpuLoadMode(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--hnsw-gpu-build") return HnswGpuBuildMode(argc, argv);
+  if (argc > 1 && std::string(argv[1]) == "--hnsw-perf") return HnswPerfMode(argc, argv);
   const bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";
   struct Case {
     const char *name;
@@ -781,6 +887,7 @@ int main(int argc, char **argv) {
                {"Prefilter", Prefilter},
                {"SaveAndLoadFlat", SaveAndLoadFlat},
                {"SaveAndLoadHnsw", SaveAndLoadHnsw},
+               {"HnswCountersPerCall", HnswCountersPerCall},
                {"InlineFilterAndBatch", InlineFilterAndBatch}};
   {
     const int before = g_failures;

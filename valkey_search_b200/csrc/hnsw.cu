@@ -41,7 +41,6 @@ struct Hnsw {
   std::vector<uint64_t> h_up_off;
   uint64_t num_deleted = 0;
   uint32_t rng = 100;  // std::default_random_engine(100), hnswalg.h:149
-  DevBuf d_stats;      // [4] u64: hops, distance evals, candidate-heap overflows, spare
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -58,6 +57,7 @@ struct HnswSearchParams {
   uint32_t *out_n;       // [B]
   uint32_t rows_per_batch, row_stride_bytes, cand_cap;
   uint32_t need_flags;  // some node is tombstoned or a filter is present: resolve live/allowed per neighbour
+  uint32_t merge_skip;  // sorted kernel: leave a list alone when the hop cannot change it (VKGPU_HNSW_NO_MERGE_SKIP=1: off)
   unsigned long long *stats;
 };
 
@@ -632,7 +632,12 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
     HOP_ADD(4, h5, h6);
     const uint32_t n_live = ctl[4];
 
-    // ---- merge the live neighbours into the result list (keep the ef best)
+    // ---- merge the live neighbours into the result list (keep the ef best).  Once the list is full most hops
+    //      bring nothing closer than its last entry (a newcomer AT that distance goes after it, i.e. out): the list,
+    //      its length and the bound stay as they are and the copy + barrier are skipped.  Uniform: every thread
+    //      evaluates the same shared values.
+    const bool top_same = p.merge_skip && (n_live == 0 || (top_n == ef && sld[0] >= lower));
+    if (!top_same) {
     {
       const HEnt *A = topb[ct];
       HEnt *Bf = topb[ct ^ 1];
@@ -656,11 +661,12 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
       }
     }
     __syncthreads();
-    HOP_T(h7);
-    HOP_ADD(5, h6, h7);
     top_n = min(top_n + n_live, ef);
     ct ^= 1;
     if (top_n) lower = topb[ct][top_n - 1].d;
+    }  // !top_same
+    HOP_T(h7);
+    HOP_ADD(5, h6, h7);
     const bool full = top_n == ef;
 
     // ---- merge the neighbours that can still matter into the candidate list
@@ -670,6 +676,8 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
         n_push = 0;  // was pushed by the reference when its turn came (the bound was still looser then)
         for (uint32_t j = 0; j < nuv; j++) n_push += sd[j] <= lower ? 1u : 0u;
       }
+      // nothing to push (every neighbour is farther than the ef-th best): the list stays where it is, head included
+      if (!(p.merge_skip && n_push == 0)) {
       const HEnt *Cw = candb[cc] + cand_h;
       HEnt *Cn = candb[cc ^ 1];
       const uint32_t len = cand_n - cand_h;
@@ -695,6 +703,7 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
       cand_n = min(len + n_push, ccap);
       cand_h = 0;
       cc ^= 1;
+      }
     }
     HOP_T(h8);
     HOP_ADD(6, h7, h8);
@@ -765,8 +774,6 @@ void hnsw_create(vkgpu_index_impl *ix) {
     ix->hnsw = nullptr;
     throw StatusError{VKGPU_ERR_UNSUPPORTED, "HNSW M > 256 is not supported by the GPU core"};
   }
-  g->d_stats.reserve(4 * sizeof(unsigned long long));
-  VK_CUDA(cudaMemset(g->d_stats.p, 0, 4 * sizeof(unsigned long long)));
   VK_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
   VK_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
   VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
@@ -776,7 +783,7 @@ void hnsw_create(vkgpu_index_impl *ix) {
 void hnsw_destroy(vkgpu_index_impl *ix) {
   Hnsw *g = G(ix);
   if (!g) return;
-  for (DevBuf *b : {&g->hdr0, &g->link0, &g->level, &g->up_off, &g->up, &g->locks, &g->d_stats}) b->release();
+  for (DevBuf *b : {&g->hdr0, &g->link0, &g->level, &g->up_off, &g->up, &g->locks}) b->release();
   delete g;
   ix->hnsw = nullptr;
 }
@@ -935,7 +942,12 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   hp.row_stride_bytes = ix->Dp * 4 + 64;
   hp.cand_cap = std::max<uint32_t>(1024, 8 * ef);
   hp.need_flags = (g->num_deleted != 0 || filters != nullptr) ? 1u : 0u;
-  hp.stats = g->d_stats.as<unsigned long long>();
+  hp.merge_skip = getenv("VKGPU_HNSW_NO_MERGE_SKIP") == nullptr ? 1u : 0u;
+  // per-call counters in this context's scratch (concurrent searches do not mix, and vkgpu_stats reports the most
+  // recent call: bench.py divides them by that call's batch)
+  c->scratch3.reserve(4 * sizeof(unsigned long long));
+  VK_CUDA(cudaMemsetAsync(c->scratch3.p, 0, 4 * sizeof(unsigned long long), s));
+  hp.stats = c->scratch3.as<unsigned long long>();
   // rows staged per round vs CTAs per SM: prefer enough resident CTAs to hold the whole batch in ONE wave (a hop
   // stages ~8 unvisited rows on average, so 12-16 staged rows rarely need a second round), down to 1 CTA/SM for
   // very wide rows.  Shared memory per SM = opt-in max + 1 KB; each CTA reserves 1 KB.
@@ -1008,7 +1020,8 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
     }
   }
   unsigned long long hs[4];
-  VK_CUDA(cudaMemcpy(hs, g->d_stats.p, sizeof(hs), cudaMemcpyDeviceToHost));
+  VK_CUDA(cudaMemcpyAsync(hs, c->scratch3.p, sizeof(hs), cudaMemcpyDeviceToHost, s));
+  VK_CUDA(cudaStreamSynchronize(s));
   ix->hops = hs[0];
   ix->dist_evals = hs[1];
   ix->searches += B;
