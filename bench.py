@@ -247,9 +247,9 @@ def hnsw_workload(args):
         pass
     roofline = {"bound": "hbm", "kernel": "hnsw_search_sorted_kernel<L2> (one CTA per query, TMA-staged rows, sorted lists)",
                 "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": traffic,
-                "note": "algorithmic row bytes / time; queries of one cluster re-read the same rows from L2, so this can "
-                        "exceed what DRAM delivers (ncu at 1M rows: 1.83 GB of DRAM reads for 15.3 GB algorithmic) - "
-                        "the kernel is bound by the latency of the hop chain, not by HBM bandwidth",
+                "note": "algorithmic row bytes of ONE launch / its time (ncu at 1M rows: 1.85 GB of DRAM reads for 1.91 GB "
+                        "algorithmic, L2 hit rate 10 %) - the kernel is bound by the latency of the dependent hop chain, "
+                        "not by HBM bandwidth",
                 "peak_source": f"{peaks['source']} copy bandwidth", "bytes_per_launch": bytes_algo,
                 "distance_evals_per_query": evals, "hops_per_query": st1.hops / max(B, 1),
                 "kernel_ms_avg": hnsw_ms / max(hnsw_n, 1)}
