@@ -91,6 +91,25 @@ typedef struct vkgpu_filter {
  * id, so a filtered query moves no candidate list across PCIe and does no host-side label lookups. */
 int vkgpu_set_create(vkgpu_index *h, const uint8_t *label_bitmap, uint64_t bits, uint64_t *out_set_id);
 int vkgpu_set_destroy(vkgpu_index *h, uint64_t set_id);
+/* Incremental maintenance, what Tag::AddRecord / ModifyRecord / RemoveRecord do to one posting list
+ * (src/indexes/tag.cc:107-262): present[i] != 0 adds labels[i] to the set (growing it), 0 removes it. */
+int vkgpu_set_update(vkgpu_index *h, uint64_t set_id, const uint64_t *labels, const uint8_t *present, uint64_t n);
+/* The predicate tree of a hybrid query evaluated as set algebra on the device instead of once per key on the host
+ * (ComposedPredicate / NegatePredicate, src/query/predicate.cc:36-39,429-520): a new set = a AND b, a OR b, or
+ * a AND NOT b (negation: a = the set of all labels of the index, see the host mirror's DeviceFilterIndex). */
+typedef enum vkgpu_set_op { VKGPU_SET_AND = 0, VKGPU_SET_OR = 1, VKGPU_SET_ANDNOT = 2 } vkgpu_set_op;
+int vkgpu_set_combine(vkgpu_index *h, int op, uint64_t set_a, uint64_t set_b, uint64_t *out_set_id);
+int vkgpu_set_cardinality(vkgpu_index *h, uint64_t set_id, uint64_t *out_count);   /* EntriesFetcher::Size analog */
+int vkgpu_set_read(vkgpu_index *h, uint64_t set_id, uint8_t *out_bitmap, uint64_t bits);
+/* NUMERIC attribute resident in HBM (src/indexes/numeric.h): one double per label; a range predicate
+ * (NumericPredicate::Evaluate, src/query/predicate.cc:332-341: ((v > start || (incl_start && v == start)) && v < end)
+ * || (incl_end && v == end)) becomes a set without the values leaving the device. */
+int vkgpu_values_create(vkgpu_index *h, uint64_t *out_values_id);
+int vkgpu_values_destroy(vkgpu_index *h, uint64_t values_id);
+int vkgpu_values_update(vkgpu_index *h, uint64_t values_id, const uint64_t *labels, const double *values,
+                        const uint8_t *present, uint64_t n);
+int vkgpu_set_from_range(vkgpu_index *h, uint64_t values_id, double start, int inclusive_start, double end,
+                         int inclusive_end, uint64_t *out_set_id);
 
 typedef struct vkgpu_stats {
   uint64_t count;            /* live vectors          (GetTrackedKeyCount, vector_base.cc:385-409)     */

@@ -1,0 +1,450 @@
+// Tests of the TAG / NUMERIC candidate-set bridge (valkey_search_b200/host/filter_index.h).
+//   host cases  = the reference's testing/tag_index_test.cc and testing/numeric_index_test.cc re-stated (same inputs,
+//                 same expectations) + the predicate tree's Evaluate();  run everywhere (`--host-only`)
+//   device case = on a B200: for a corpus with tags and prices attached in every order, mutated, for a list of
+//                 predicate trees — the label set computed ON THE DEVICE (posting bitmaps, range kernel, set
+//                 algebra) equals the set the reference's per-key evaluation gives, and the filtered kNN through it
+//                 returns exactly what the already-verified key-list pre-filter path returns
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <set>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../../valkey_search_b200/host/filter_index.h"
+
+using namespace valkey_search::indexes;
+
+static int g_failures = 0, g_checks = 0;
+#define EXPECT_TRUE(c)                                                      \
+  do {                                                                      \
+    g_checks++;                                                             \
+    if (!(c)) {                                                             \
+      g_failures++;                                                         \
+      std::fprintf(stderr, "  FAILED %s:%d: %s\n", __FILE__, __LINE__, #c); \
+    }                                                                       \
+  } while (0)
+#define EXPECT_FALSE(c) EXPECT_TRUE(!(c))
+#define EXPECT_EQ(a, b) EXPECT_TRUE((a) == (b))
+#define EXPECT_OK(s) EXPECT_TRUE((s).ok())
+
+using Keys = std::multiset<std::string>;
+static Keys AsSet(const std::vector<std::string> &v) { return Keys(v.begin(), v.end()); }
+static std::set<std::string> Unescaped(const std::string &raw, char sep) {  // ParseAndUnescapeTags, tag_index_test.cc:268-278
+  auto parsed = Tag::ParseSearchTags(raw, sep);
+  std::set<std::string> out;
+  if (!parsed.ok()) return out;
+  for (const auto &t : *parsed) out.insert(Tag::UnescapeTag(t));
+  return out;
+}
+static TagPredicate QueryTags(Tag *index, const std::string &filter) {  // FilterParser::ParseQueryTags: '|' separates
+  return TagPredicate(index, *Tag::ParseSearchTags(filter, '|'));
+}
+
+// ------------------------------------------------------------------------------------------ tag_index_test.cc
+static void TagIndexCases() {
+  {  // AddRecordAndSearchTest :52-69
+    Tag index(',', false);
+    EXPECT_EQ(*index.AddRecord("key1", "    "), RecordResult::kMissing);
+    EXPECT_EQ(*index.AddRecord("key1", "tag1"), RecordResult::kAdded);
+    EXPECT_EQ(*index.AddRecord("key2", "tag2"), RecordResult::kAdded);
+    EXPECT_EQ(index.AddRecord("key2", "tag2").status().code(), vks::StatusCode::kAlreadyExists);
+    EXPECT_EQ(AsSet(index.Search(QueryTags(&index, "tag1"), false)), Keys({"key1"}));
+  }
+  {  // RemoveRecordAndSearchTest :71-85
+    Tag index(',', false);
+    EXPECT_OK(index.AddRecord("key1", "tag1"));
+    EXPECT_OK(index.AddRecord("key2", "tag2"));
+    EXPECT_TRUE(*index.RemoveRecord("key1"));
+    EXPECT_EQ(index.Search(QueryTags(&index, "tag1"), false).size(), (size_t)0);
+  }
+  {  // ModifyRecordAndSearchTest :87-103
+    Tag index(',', false);
+    EXPECT_OK(index.AddRecord("key1", "tag2"));
+    EXPECT_EQ(*index.ModifyRecord("key1", "tag2.1,tag2.2"), RecordResult::kAdded);
+    EXPECT_EQ(AsSet(index.Search(QueryTags(&index, "tag2.1"), false)), Keys({"key1"}));
+    EXPECT_EQ(index.Search(QueryTags(&index, "tag2"), false).size(), (size_t)0);
+    EXPECT_EQ(index.ModifyRecord("key5", "tag5").status().code(), vks::StatusCode::kNotFound);
+  }
+  {  // ModifyRecordWithEmptyString :105-119
+    Tag index(',', false);
+    EXPECT_OK(index.AddRecord("key1", "tag2"));
+    EXPECT_EQ(*index.ModifyRecord("key1", ""), RecordResult::kMissing);
+    EXPECT_EQ(index.Search(QueryTags(&index, "tag2"), false).size(), (size_t)0);
+    EXPECT_EQ(index.GetTrackedKeyCount(), (size_t)0);
+  }
+  {  // KeyTrackingTest :121-135
+    Tag index(',', false);
+    EXPECT_OK(index.AddRecord("key1", "tag1"));
+    EXPECT_OK(index.AddRecord("key2", "tag2"));
+    EXPECT_FALSE(index.IsTracked("key3"));
+    EXPECT_OK(index.AddRecord("key3", "tag3"));
+    EXPECT_TRUE(index.IsTracked("key3"));
+    EXPECT_TRUE(*index.RemoveRecord("key3"));
+    EXPECT_FALSE(index.IsTracked("key3"));
+    auto res = index.RemoveRecord("key3");
+    EXPECT_TRUE(res.ok() && !*res);
+    EXPECT_EQ(*index.AddRecord("key5", "  "), RecordResult::kMissing);
+    EXPECT_EQ(*index.ModifyRecord("key5", " "), RecordResult::kMissing);
+    EXPECT_EQ(*index.AddRecord("key6", " tag6 , tag7 "), RecordResult::kAdded);
+    EXPECT_EQ(*index.GetValue("key6"), std::set<std::string>({"tag6", "tag7"}));
+  }
+  for (const char *filter : {"dis*", "dIs*"}) {  // PrefixSearchHappyTest / CaseInsensitive :137-175
+    Tag index(',', false);
+    EXPECT_OK(index.AddRecord("doc1", "disagree"));
+    EXPECT_OK(index.AddRecord("doc2", "disappear"));
+    EXPECT_OK(index.AddRecord("doc3", "dislike"));
+    EXPECT_OK(index.AddRecord("doc4", "disadvantage"));
+    EXPECT_OK(index.AddRecord("doc5", "preschool"));
+    auto parsed = Tag::ParseSearchTags(filter, '|');
+    EXPECT_OK(parsed);
+    EXPECT_EQ(*parsed, std::set<std::string>({filter}));
+    EXPECT_EQ(AsSet(index.Search(TagPredicate(&index, *parsed), false)), Keys({"doc1", "doc2", "doc3", "doc4"}));
+  }
+  // PrefixSearchInvalidTagTest / MinLength :177-207
+  EXPECT_EQ(Tag::ParseSearchTags("dis**", ',').status().code(), vks::StatusCode::kInvalidArgument);
+  EXPECT_EQ(Tag::ParseSearchTags("d*", '|').status().code(), vks::StatusCode::kInvalidArgument);
+  EXPECT_EQ(Tag::ParseSearchTags("dis*", '|')->size(), (size_t)1);
+  {  // NegativeSearchTest :209-235
+    Tag index(',', false);
+    EXPECT_OK(index.AddRecord("doc1", "disagree"));
+    EXPECT_OK(index.AddRecord("doc2", "distance"));
+    EXPECT_TRUE(*index.RemoveRecord("doc1"));  // now untracked
+    EXPECT_TRUE(*index.RemoveRecord("doc2"));
+    EXPECT_OK(index.AddRecord("doc3", "decorum"));
+    EXPECT_OK(index.AddRecord("doc4", "dismiss"));
+    EXPECT_FALSE(*index.RemoveRecord("doc5"));  // removed, never added
+    EXPECT_OK(index.AddRecord("doc6", "demand"));
+    EXPECT_TRUE(*index.RemoveRecord("doc6"));
+    EXPECT_OK(index.AddRecord("doc6", "demand2"));  // removed then added
+    EXPECT_EQ(AsSet(index.Search(QueryTags(&index, "dis*"), true)), Keys({"doc1", "doc2", "doc3", "doc5", "doc6"}));
+  }
+  {  // DeletedKeysNegativeSearchTest :237-266
+    Tag index(',', false);
+    EXPECT_OK(index.AddRecord("doc0", "ambiance"));
+    EXPECT_OK(index.AddRecord("doc1", "demand"));
+    EXPECT_TRUE(*index.RemoveRecord("doc1", DeletionType::kNone));  // the field went away
+    EXPECT_EQ(AsSet(index.Search(QueryTags(&index, "dis*"), true)), Keys({"doc0", "doc1"}));
+    EXPECT_FALSE(*index.RemoveRecord("doc1", DeletionType::kRecord));  // the key went away
+    EXPECT_EQ(AsSet(index.Search(QueryTags(&index, "dis*"), true)), Keys({"doc0"}));
+  }
+  // escapes :281-337
+  EXPECT_EQ(Unescaped(R"(foo\|bar)", '|'), std::set<std::string>({"foo|bar"}));
+  EXPECT_EQ(Unescaped(R"(a\|b|c)", '|'), std::set<std::string>({"a|b", "c"}));
+  EXPECT_EQ(Unescaped(R"(foo\\|bar)", '|'), std::set<std::string>({R"(foo\)", "bar"}));
+  EXPECT_EQ(Unescaped(R"(foo\\\|bar)", '|'), std::set<std::string>({R"(foo\|bar)"}));
+  EXPECT_EQ(Unescaped(R"(a\|b\|c|d\|e)", '|'), std::set<std::string>({"a|b|c", "d|e"}));
+  EXPECT_EQ(Unescaped(R"(foo\\)", '|'), std::set<std::string>({R"(foo\)"}));
+  EXPECT_EQ(Unescaped(R"(foo\|)", '|'), std::set<std::string>({"foo|"}));
+  // UnescapeTag :339-378
+  EXPECT_EQ(Tag::UnescapeTag(""), std::string(""));
+  EXPECT_EQ(Tag::UnescapeTag("hello world"), std::string("hello world"));
+  EXPECT_EQ(Tag::UnescapeTag(R"(a\|b)"), std::string("a|b"));
+  EXPECT_EQ(Tag::UnescapeTag(R"(a\\b)"), std::string(R"(a\b)"));
+  EXPECT_EQ(Tag::UnescapeTag(R"(abc\)"), std::string(R"(abc\)"));
+  EXPECT_EQ(Tag::UnescapeTag(R"(\)"), std::string(R"(\)"));
+  EXPECT_EQ(Tag::UnescapeTag(R"(a\|b\\c)"), std::string(R"(a|b\c)"));
+  EXPECT_EQ(Tag::UnescapeTag(R"(\\\\)"), std::string(R"(\\)"));
+  EXPECT_EQ(Tag::UnescapeTag(R"(test\value)"), std::string("testvalue"));
+  // edge cases :384-435
+  EXPECT_EQ(Unescaped("a||b", '|'), std::set<std::string>({"a", "b"}));
+  EXPECT_EQ(Unescaped("a|   |b", '|'), std::set<std::string>({"a", "b"}));
+  EXPECT_EQ(Tag::ParseSearchTags("b*", '|').status().code(), vks::StatusCode::kInvalidArgument);
+  EXPECT_EQ(Tag::ParseSearchTags("*", '|').status().code(), vks::StatusCode::kInvalidArgument);
+  EXPECT_EQ(*Tag::ParseSearchTags(R"(tag\)", '|'), std::set<std::string>({R"(tag\)"}));
+  EXPECT_EQ(*Tag::ParseSearchTags(R"(\)", '|'), std::set<std::string>({R"(\)"}));
+  EXPECT_EQ(Unescaped("日本語|中文", '|'), std::set<std::string>({"日本語", "中文"}));
+  EXPECT_TRUE(Tag::ParseSearchTags("", '|')->empty());
+  EXPECT_TRUE(Tag::ParseSearchTags("   ", '|')->empty());
+  {  // a case-sensitive index keeps spellings apart (tag.cc:81-90)
+    Tag index(',', true);
+    EXPECT_OK(index.AddRecord("k1", "Red"));
+    EXPECT_OK(index.AddRecord("k2", "red"));
+    EXPECT_EQ(AsSet(index.Search(QueryTags(&index, "red"), false)), Keys({"k2"}));
+    EXPECT_TRUE(QueryTags(&index, "Red").Evaluate("k1"));
+    EXPECT_FALSE(QueryTags(&index, "Red").Evaluate("k2"));
+  }
+}
+
+// ------------------------------------------------------------------------------------------ numeric_index_test.cc
+static void NumericIndexCases() {
+  {  // SimpleAddModifyRemove :43-83
+    Numeric index;
+    EXPECT_EQ(*index.AddRecord("key1", "1.5"), RecordResult::kAdded);
+    EXPECT_EQ(*index.AddRecord("key2", "2.0"), RecordResult::kAdded);
+    EXPECT_EQ(AsSet(index.Search(NumericPredicate(&index, 1.0, true, 2.0, true), false)), Keys({"key1", "key2"}));
+    EXPECT_EQ(index.AddRecord("key2", "2.0").status().code(), vks::StatusCode::kAlreadyExists);
+    EXPECT_EQ(*index.ModifyRecord("key2", "2.1"), RecordResult::kAdded);
+    EXPECT_EQ(AsSet(index.Search(NumericPredicate(&index, 2.05, true, 2.2, true), false)), Keys({"key2"}));
+    EXPECT_EQ(index.ModifyRecord("key5", "2.1").status().code(), vks::StatusCode::kNotFound);
+    EXPECT_FALSE(index.IsTracked("key3"));
+    EXPECT_OK(index.AddRecord("key3", "3.0"));
+    EXPECT_TRUE(index.IsTracked("key3"));
+    EXPECT_TRUE(*index.RemoveRecord("key3"));
+    EXPECT_TRUE(index.Search(NumericPredicate(&index, 2.5, true, 3.5, true), false).empty());
+    EXPECT_FALSE(index.IsTracked("key3"));
+    auto res = index.RemoveRecord("key3");
+    EXPECT_TRUE(res.ok() && !*res);
+    EXPECT_EQ(*index.AddRecord("key5", "aaa"), RecordResult::kInvalidData);
+    EXPECT_EQ(*index.ModifyRecord("key5", "aaa"), RecordResult::kInvalidData);
+  }
+  {  // DetectsInvalidData :87-108
+    Numeric index;
+    EXPECT_EQ(*index.AddRecord("key1", "not_a_number"), RecordResult::kInvalidData);
+    EXPECT_FALSE(index.IsTracked("key1"));
+    EXPECT_EQ(*index.AddRecord("key2", "nan"), RecordResult::kInvalidData);
+    EXPECT_EQ(*index.AddRecord("key3", ""), RecordResult::kInvalidData);
+    EXPECT_EQ(*index.AddRecord("key4", "42"), RecordResult::kAdded);
+    EXPECT_TRUE(index.IsTracked("key4"));
+    EXPECT_EQ(*index.ModifyRecord("key4", "still_not_a_number"), RecordResult::kInvalidData);
+    EXPECT_FALSE(index.IsTracked("key4"));
+  }
+  {  // RangeSearchInclusiveExclusive :147-191
+    Numeric index;
+    const char *v[] = {"1.0", "2.0", "2.2", "3.2", "2.0", "2.1"};
+    for (int i = 0; i < 6; i++) EXPECT_OK(index.AddRecord("key" + std::to_string(i + 1), v[i]));
+    EXPECT_EQ(AsSet(index.Search(NumericPredicate(&index, 1.0, true, 2.1, true), false)), Keys({"key1", "key2", "key5", "key6"}));
+    EXPECT_EQ(AsSet(index.Search(NumericPredicate(&index, 1.0, false, 2.1, true), false)), Keys({"key2", "key5", "key6"}));
+    EXPECT_EQ(AsSet(index.Search(NumericPredicate(&index, 1.0, false, 2.1, false), false)), Keys({"key2", "key5"}));
+    EXPECT_EQ(AsSet(index.Search(NumericPredicate(&index, 1.0, false, 3.5, false), false)),
+              Keys({"key2", "key3", "key4", "key5", "key6"}));
+    EXPECT_EQ(AsSet(index.Search(NumericPredicate(&index, 0.0, false, 2.1, false), false)), Keys({"key1", "key2", "key5"}));
+    // negate: everything outside the range plus the keys without the field
+    EXPECT_EQ(*index.AddRecord("key7", "abc"), RecordResult::kInvalidData);
+    EXPECT_EQ(AsSet(index.Search(NumericPredicate(&index, 1.0, false, 2.1, false), true)),
+              Keys({"key1", "key3", "key4", "key6", "key7"}));
+  }
+  EXPECT_TRUE(Numeric::ParseNumber(" 1e3 ").value_or(0) == 1000.0);
+  EXPECT_TRUE(Numeric::ParseNumber("-inf").value_or(0) < -1e300);
+  EXPECT_FALSE(Numeric::ParseNumber("0x10").has_value());
+  EXPECT_FALSE(Numeric::ParseNumber("1.5abc").has_value());
+}
+
+static void PredicateCases() {  // predicate.cc:36-39, 332-341, 362-393, 429-520
+  Tag tags(',', false);
+  Numeric price;
+  EXPECT_OK(tags.AddRecord("a", "red,Dark Blue"));
+  EXPECT_OK(tags.AddRecord("b", "green"));
+  EXPECT_OK(tags.AddRecord("c", "RED"));
+  EXPECT_OK(price.AddRecord("a", "10"));
+  EXPECT_OK(price.AddRecord("b", "20"));
+  EXPECT_OK(price.AddRecord("d", "30"));
+  auto red = [&] { return std::make_unique<TagPredicate>(&tags, *Tag::ParseSearchTags("red", '|')); };
+  auto cheap = [&] { return std::make_unique<NumericPredicate>(&price, 0.0, true, 15.0, false); };
+  EXPECT_TRUE(red()->Evaluate("a") && red()->Evaluate("c") && !red()->Evaluate("b") && !red()->Evaluate("zzz"));
+  EXPECT_TRUE(TagPredicate(&tags, *Tag::ParseSearchTags("dark*", '|')).Evaluate("a"));
+  EXPECT_TRUE(cheap()->Evaluate("a") && !cheap()->Evaluate("b") && !cheap()->Evaluate("c"));
+  ComposedPredicate both(PredicateType::kComposedAnd);
+  both.AddChild(red());
+  both.AddChild(cheap());
+  EXPECT_TRUE(both.Evaluate("a") && !both.Evaluate("c") && !both.Evaluate("b"));
+  ComposedPredicate either(PredicateType::kComposedOr);
+  either.AddChild(red());
+  either.AddChild(cheap());
+  EXPECT_TRUE(either.Evaluate("a") && either.Evaluate("c") && !either.Evaluate("b") && !either.Evaluate("d"));
+  NegatePredicate not_red(red());
+  EXPECT_TRUE(!not_red.Evaluate("a") && not_red.Evaluate("b") && not_red.Evaluate("d") && not_red.Evaluate("nokey"));
+  // the end point matches even when the interval is empty otherwise (the formula's second clause)
+  EXPECT_TRUE(NumericPredicate(&price, 50.0, true, 20.0, true).Evaluate("b"));
+}
+
+// ------------------------------------------------------------------------------------------ device case (B200)
+static uint64_t g_rng = 0x9E3779B97F4A7C15ull;
+static uint64_t Next() {
+  g_rng ^= g_rng << 13;
+  g_rng ^= g_rng >> 7;
+  g_rng ^= g_rng << 17;
+  return g_rng;
+}
+static float Unit() { return (float)((Next() >> 11) * (1.0 / 9007199254740992.0)); }
+
+struct Doc {
+  std::vector<float> vec;
+  std::string tags;   // "" = no TAG field
+  std::string price;  // "" = no NUMERIC field
+};
+
+static std::string_view Bytes(const std::vector<float> &v) {
+  return std::string_view(reinterpret_cast<const char *>(v.data()), v.size() * sizeof(float));
+}
+
+template <typename Index>
+static void DeviceBridgeOn(Index *vectors, int dim, int n, bool hnsw) {
+  const char *palette[] = {"red", "green", "blue", "Dark Blue", "darkness", "disagree", "dislike", "RED", "a|b"};
+  std::vector<Doc> docs(n);
+  for (auto &d : docs) {
+    d.vec.resize(dim);
+    for (auto &x : d.vec) x = Unit() * 2.0f - 1.0f;
+    const int nt = (int)(Next() % 4);  // 0..3 tags
+    for (int t = 0; t < nt; t++) d.tags += (t ? " , " : "") + std::string(palette[Next() % 9]);
+    if (Next() % 5) d.price = std::to_string((int)(Next() % 1000) / 10.0);
+  }
+  Tag tags(',', false, vectors);
+  Numeric price(vectors);
+  DeviceFilterEvaluator evaluator(vectors);
+  auto key = [](int i) { return "doc:" + std::to_string(i); };
+  // attach the three attributes of a key in every order
+  for (int i = 0; i < n; i++) {
+    const int order = i % 3;
+    if (order == 0) EXPECT_OK(vectors->AddRecord(key(i), Bytes(docs[i].vec)));
+    EXPECT_OK(tags.AddRecord(key(i), docs[i].tags));
+    if (order == 1) EXPECT_OK(vectors->AddRecord(key(i), Bytes(docs[i].vec)));
+    EXPECT_OK(price.AddRecord(key(i), docs[i].price));
+    if (order == 2) EXPECT_OK(vectors->AddRecord(key(i), Bytes(docs[i].vec)));
+  }
+  auto tag_leaf = [&](const char *q) { return std::make_unique<TagPredicate>(&tags, *Tag::ParseSearchTags(q, '|')); };
+  auto range = [&](double a, bool ia, double b, bool ib) { return std::make_unique<NumericPredicate>(&price, a, ia, b, ib); };
+  auto build_roots = [&]() {
+    std::vector<std::unique_ptr<Predicate>> roots;
+    roots.push_back(tag_leaf("red"));
+    roots.push_back(tag_leaf("dark*"));
+    roots.push_back(tag_leaf("green|blue|dis*"));
+    roots.push_back(tag_leaf(R"(a\|b)"));
+    roots.push_back(tag_leaf("no-such-tag"));
+    roots.push_back(range(10.0, true, 20.0, false));
+    roots.push_back(range(0.0, false, 99.9, true));
+    roots.push_back(range(50.0, true, 50.0, true));
+    {
+      auto p = std::make_unique<ComposedPredicate>(PredicateType::kComposedAnd);
+      p->AddChild(tag_leaf("red"));
+      p->AddChild(range(0.0, true, 50.0, true));
+      roots.push_back(std::move(p));
+    }
+    {
+      auto p = std::make_unique<ComposedPredicate>(PredicateType::kComposedOr);
+      p->AddChild(tag_leaf("green"));
+      p->AddChild(range(90.0, true, 100.0, true));
+      roots.push_back(std::move(p));
+    }
+    roots.push_back(std::make_unique<NegatePredicate>(tag_leaf("red|green")));
+    {
+      auto p = std::make_unique<ComposedPredicate>(PredicateType::kComposedAnd);
+      p->AddChild(std::make_unique<NegatePredicate>(tag_leaf("blue")));
+      p->AddChild(range(25.0, false, 75.0, false));
+      p->AddChild(tag_leaf("dis*|dark*"));
+      roots.push_back(std::move(p));
+    }
+    {
+      auto inner = std::make_unique<ComposedPredicate>(PredicateType::kComposedAnd);
+      inner->AddChild(tag_leaf("red"));
+      inner->AddChild(std::make_unique<NegatePredicate>(range(0.0, true, 30.0, true)));
+      auto p = std::make_unique<ComposedPredicate>(PredicateType::kComposedOr);
+      p->AddChild(std::move(inner));
+      p->AddChild(std::make_unique<NegatePredicate>(std::make_unique<NegatePredicate>(tag_leaf("darkness"))));
+      roots.push_back(std::move(p));
+    }
+    return roots;
+  };
+  std::vector<float> q(dim);
+  auto check_all = [&](const char *phase) {
+    auto roots = build_roots();
+    for (size_t r = 0; r < roots.size(); r++) {
+      const Predicate &root = *roots[r];
+      std::vector<std::string> want = evaluator.EvaluateOnHost(root);
+      auto set = evaluator.Evaluate(root);
+      EXPECT_OK(set);
+      if (!set.ok()) {
+        std::fprintf(stderr, "  %s predicate %zu: %s\n", phase, r, set.status().message().c_str());
+        continue;
+      }
+      const uint64_t bits = (uint64_t)n * 4 + 64;  // every label ever handed out is below this
+      std::vector<uint8_t> bitmap((bits + 7) / 8);
+      EXPECT_EQ(vkgpu_set_read(vectors->handle(), set->id(), bitmap.data(), bits), 0);
+      std::set<std::string> got;
+      bool unknown_label = false;
+      for (uint64_t l = 0; l < bits; l++)
+        if ((bitmap[l >> 3] >> (l & 7)) & 1) {
+          auto k = vectors->GetKeyDuringSearch(l);
+          if (k.ok()) got.insert(*k); else unknown_label = true;
+        }
+      EXPECT_FALSE(unknown_label);  // no bit for a label that left the vector index
+      EXPECT_EQ(got, std::set<std::string>(want.begin(), want.end()));
+      uint64_t card = 0;
+      EXPECT_EQ(vkgpu_set_cardinality(vectors->handle(), set->id(), &card), 0);
+      EXPECT_EQ(card, (uint64_t)want.size());
+      if (got != std::set<std::string>(want.begin(), want.end()))
+        std::fprintf(stderr, "  %s predicate %zu: device %zu keys, host %zu keys\n", phase, r, got.size(), want.size());
+      // filtered kNN through the device set == the key-list pre-filter over the host-evaluated keys
+      for (auto &x : q) x = Unit() * 2.0f - 1.0f;
+      auto a = evaluator.Search(Bytes(q), 10, root, hnsw ? std::optional<size_t>(400) : std::nullopt);
+      EXPECT_OK(a);
+      if (want.empty() && a.ok()) EXPECT_TRUE(a->empty());
+      StatusOr<std::vector<Neighbor>> b = std::vector<Neighbor>();
+      if constexpr (std::is_same_v<Index, VectorHNSW<float>>) {
+        const KeyFilter f = [&](const std::string &k) { return root.Evaluate(k); };
+        b = vectors->Search(Bytes(q), 10, CancelNever(), &f, 400);
+      } else {
+        b = vectors->SearchPrefiltered(Bytes(q), 10, want);
+      }
+      EXPECT_OK(b);
+      if (!a.ok() || !b.ok()) continue;
+      EXPECT_EQ(a->size(), b->size());
+      if (!hnsw) EXPECT_EQ(a->size(), std::min<size_t>(10, want.size()));
+      for (size_t j = 0; j < a->size() && j < b->size(); j++) {
+        EXPECT_EQ((*a)[j].external_id, (*b)[j].external_id);
+        EXPECT_TRUE(std::memcmp(&(*a)[j].distance, &(*b)[j].distance, 4) == 0);
+      }
+    }
+  };
+  check_all("after ingest");
+  // mutations: vectors leave and come back under new labels, tags and prices change, fields disappear
+  for (int i = 0; i < n; i += 7) EXPECT_OK(vectors->RemoveRecord(key(i)));
+  for (int i = 0; i < n; i += 14) EXPECT_OK(vectors->AddRecord(key(i), Bytes(docs[i].vec)));
+  for (int i = 3; i < n; i += 11) (void)tags.ModifyRecord(key(i), "red, disagree");  // NotFound when the key had no tags
+  for (int i = 5; i < n; i += 13) (void)tags.RemoveRecord(key(i));
+  for (int i = 1; i < n; i += 9) (void)price.ModifyRecord(key(i), "15.5");
+  for (int i = 2; i < n; i += 17) (void)price.RemoveRecord(key(i));
+  for (int i = 4; i < n; i += 19) (void)price.ModifyRecord(key(i), "oops");  // invalid: the field is dropped
+  check_all("after mutations");
+}
+
+static void DeviceBridgeFlat() {
+  {
+    VectorIndexProto p;
+    p.dimension_count = 32;
+    p.distance_metric = DistanceMetric::kL2;
+    p.initial_cap = 4096;
+    p.flat_algorithm.block_size = 1024;
+    auto flat = VectorFlat<float>::Create(p);
+    EXPECT_OK(flat);
+    if (flat.ok()) DeviceBridgeOn(flat->get(), 32, 3000, false);
+  }
+}
+static void DeviceBridgeHnsw() {
+  {
+    VectorIndexProto p;
+    p.dimension_count = 32;
+    p.distance_metric = DistanceMetric::kCosine;
+    p.initial_cap = 2048;
+    p.hnsw_algorithm.m = 16;
+    p.hnsw_algorithm.ef_construction = 100;
+    p.hnsw_algorithm.ef_runtime = 50;
+    auto hnsw = VectorHNSW<float>::Create(p);
+    EXPECT_OK(hnsw);
+    if (hnsw.ok()) DeviceBridgeOn(hnsw->get(), 32, 1200, true);
+  }
+}
+
+int main(int argc, char **argv) {
+  const bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";
+  struct Case {
+    const char *name;
+    void (*fn)();
+    bool needs_gpu;
+  } cases[] = {{"TagIndex", TagIndexCases, false},
+               {"NumericIndex", NumericIndexCases, false},
+               {"Predicates", PredicateCases, false},
+               {"DeviceBridgeFlat", DeviceBridgeFlat, true},
+               {"DeviceBridgeHnsw", DeviceBridgeHnsw, true}};
+  setvbuf(stdout, nullptr, _IOLBF, 0);
+  for (const auto &c : cases) {
+    if (c.needs_gpu && host_only) continue;
+    const int before = g_failures;
+    c.fn();
+    std::printf("[%s] %s\n", g_failures == before ? "  OK  " : "FAILED", c.name);
+  }
+  std::printf("%d checks, %d failures\n", g_checks, g_failures);
+  return g_failures ? 1 : 0;
+}

@@ -91,6 +91,14 @@ SYMBOLS = {
     "vkgpu_distances": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     "vkgpu_merge_topk_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
     "vkgpu_flat_export": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, _P]),
+    "vkgpu_set_update": (C.c_int, [_P, C.c_uint64, _P, _P, C.c_uint64]),
+    "vkgpu_set_combine": (C.c_int, [_P, C.c_int, C.c_uint64, C.c_uint64, _P]),
+    "vkgpu_set_cardinality": (C.c_int, [_P, C.c_uint64, _P]),
+    "vkgpu_set_read": (C.c_int, [_P, C.c_uint64, _P, C.c_uint64]),
+    "vkgpu_values_create": (C.c_int, [_P, _P]),
+    "vkgpu_values_destroy": (C.c_int, [_P, C.c_uint64]),
+    "vkgpu_values_update": (C.c_int, [_P, C.c_uint64, _P, _P, _P, C.c_uint64]),
+    "vkgpu_set_from_range": (C.c_int, [_P, C.c_uint64, C.c_double, C.c_int, C.c_double, C.c_int, _P]),
     "vkgpu_packed_result_bytes": (C.c_uint64, [C.c_uint32, C.c_uint32]),
     "vkgpu_merge_topk_packed_device": (C.c_int, [C.c_int, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
     "vkgpu_hnsw_import": (C.c_int, [_P, C.c_uint64, _P, _P, _P, _P, _P, _P, _P, _P, C.c_int32, C.c_uint32, _P]),

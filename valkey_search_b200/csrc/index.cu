@@ -500,6 +500,11 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
       lens[b] = slots.size() - start;
       longest = std::max<uint64_t>(longest, lens[b]);
     }
+    if (longest == 0) {  // no key qualifies for any query of the batch: empty replies (search.cc:457-481 with no keys)
+      for (uint32_t b = 0; b < B; b++) out_n[b] = 0;
+      ix->searches += B;
+      return;
+    }
     k_eff = (uint32_t)std::min<uint64_t>(k, std::max<uint64_t>(longest, 1));
     const size_t slots_bytes = (slots.size() * 4 + 7) & ~size_t(7);
     c->lists.reserve(std::max<size_t>(slots_bytes, 8));
@@ -746,6 +751,10 @@ void vkgpu_index_destroy(vkgpu_index *ix) {
   for (auto &kv : ix->sets) {
     kv.second->bitmap.release();
     kv.second->slots.release();
+  }
+  for (auto &kv : ix->values) {
+    kv.second->vals.release();
+    kv.second->has.release();
   }
   ix->set_scratch.release();
   ix->set_count.release();
@@ -1013,18 +1022,269 @@ int vkgpu_set_flat_path(vkgpu_index *ix, int path) {
   });
 }
 
+// Every DeviceSet keeps: allocation a whole number of 32-bit words, all bits at or beyond `bits` zero.
+static std::unique_ptr<DeviceSet> new_device_set(uint64_t bits) {
+  auto ds = std::make_unique<DeviceSet>();
+  ds->bits = bits;
+  ds->bitmap.reserve(std::max<uint64_t>((bits + 31) / 32, 1) * 4);
+  VK_CUDA(cudaMemset(ds->bitmap.p, 0, ds->bitmap.bytes));
+  VK_CUDA(cudaStreamSynchronize(nullptr));  // the fill is complete before any other stream writes the set
+  return ds;
+}
+static uint64_t publish_set(vkgpu_index_impl *ix, std::unique_ptr<DeviceSet> ds) {
+  std::lock_guard<std::mutex> lk(ix->sets_mu);
+  const uint64_t id = ix->next_set_id++;
+  ix->sets.emplace(id, std::move(ds));
+  return id;
+}
+static DeviceSet *find_set(vkgpu_index_impl *ix, uint64_t id) {
+  std::lock_guard<std::mutex> lk(ix->sets_mu);
+  auto it = ix->sets.find(id);
+  VK_REQUIRE(it != ix->sets.end(), VKGPU_ERR_NOT_FOUND, "unknown device set id");
+  return it->second.get();
+}
+
 int vkgpu_set_create(vkgpu_index *ix, const uint8_t *label_bitmap, uint64_t bits, uint64_t *out_set_id) {
   return guarded([&] {
-    VK_REQUIRE(ix && label_bitmap && out_set_id && bits, VKGPU_ERR_INVALID, "null argument");
+    VK_REQUIRE(ix && out_set_id && (label_bitmap || bits == 0), VKGPU_ERR_INVALID, "null argument");
     VK_CUDA(cudaSetDevice(ix->device));
-    auto ds = std::make_unique<DeviceSet>();
-    ds->bits = bits;
-    ds->bitmap.reserve((bits + 7) / 8);
-    VK_CUDA(cudaMemcpy(ds->bitmap.p, label_bitmap, (bits + 7) / 8, cudaMemcpyHostToDevice));
+    auto ds = new_device_set(bits);
+    if (bits) {
+      std::vector<uint8_t> host(label_bitmap, label_bitmap + (bits + 7) / 8);
+      if (bits & 7) host.back() &= (uint8_t)((1u << (bits & 7)) - 1u);  // nothing at or beyond `bits`
+      VK_CUDA(cudaMemcpy(ds->bitmap.p, host.data(), host.size(), cudaMemcpyHostToDevice));
+    }
+    *out_set_id = publish_set(ix, std::move(ds));
+  });
+}
+
+int vkgpu_set_combine(vkgpu_index *ix, int op, uint64_t set_a, uint64_t set_b, uint64_t *out_set_id) {
+  return guarded([&] {
+    VK_REQUIRE(ix && out_set_id, VKGPU_ERR_INVALID, "null argument");
+    VK_REQUIRE(op >= VKGPU_SET_AND && op <= VKGPU_SET_ANDNOT, VKGPU_ERR_INVALID, "unknown set operation");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);  // operands must not be updated or destroyed meanwhile
+    VK_CUDA(cudaSetDevice(ix->device));
+    DeviceSet *a = find_set(ix, set_a), *b = find_set(ix, set_b);
+    // AND cannot exceed the shorter operand, AND-NOT the first one, OR needs the longer one
+    const uint64_t bits = op == VKGPU_SET_AND ? std::min(a->bits, b->bits) : op == VKGPU_SET_OR ? std::max(a->bits, b->bits) : a->bits;
+    auto ds = new_device_set(bits);
+    cudaStream_t s = nullptr;
+    VK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    try {
+      launch_set_combine(op, a->bitmap.as<uint32_t>(), (a->bits + 31) / 32, b->bitmap.as<uint32_t>(), (b->bits + 31) / 32,
+                         ds->bitmap.as<uint32_t>(), bits, s);
+      VK_CUDA(cudaStreamSynchronize(s));
+    } catch (...) {
+      cudaStreamDestroy(s);
+      ds->bitmap.release();
+      throw;
+    }
+    cudaStreamDestroy(s);
+    ix->kernels++;
+    *out_set_id = publish_set(ix, std::move(ds));
+  });
+}
+
+// grows a bitmap to hold `bits` labels, keeping its content and zeroing the new part
+static void grow_words(DevBuf &buf, uint64_t old_bits, uint64_t bits, cudaStream_t s) {
+  const size_t old_bytes = buf.bytes;
+  buf.reserve(std::max<uint64_t>((bits + 31) / 32, 1) * 4, true, s);
+  if (buf.bytes > old_bytes)
+    VK_CUDA(cudaMemsetAsync(static_cast<char *>(buf.p) + old_bytes, 0, buf.bytes - old_bytes, s));
+  (void)old_bits;
+}
+
+int vkgpu_set_update(vkgpu_index *ix, uint64_t set_id, const uint64_t *labels, const uint8_t *present, uint64_t n) {
+  return guarded([&] {
+    VK_REQUIRE(ix && (n == 0 || (labels && present)), VKGPU_ERR_INVALID, "null argument");
+    if (n == 0) return;
+    std::unique_lock<std::shared_mutex> lk(ix->rw);  // like every mutation: never concurrent with a search
+    VK_CUDA(cudaSetDevice(ix->device));
+    DeviceSet *ds = find_set(ix, set_id);
+    cudaStream_t s = ix->mut_stream;
+    uint64_t need = ds->bits;
+    for (uint64_t i = 0; i < n; i++)
+      if (present[i]) need = std::max(need, labels[i] + 1);
+    // a label being cleared beyond the set is already absent: drop it on the host
+    std::vector<uint64_t> lab;
+    std::vector<uint8_t> pre;
+    lab.reserve(n);
+    pre.reserve(n);
+    for (uint64_t i = 0; i < n; i++)
+      if (labels[i] < need) {
+        lab.push_back(labels[i]);
+        pre.push_back(present[i] ? 1 : 0);
+      }
+    if (need > ds->bits) {
+      grow_words(ds->bitmap, ds->bits, need, s);
+      ds->bits = need;
+    }
+    if (!lab.empty()) {
+      DevBuf dl, dp;
+      dl.reserve(lab.size() * 8);
+      dp.reserve(pre.size());
+      try {
+        VK_CUDA(cudaMemcpyAsync(dl.p, lab.data(), lab.size() * 8, cudaMemcpyHostToDevice, s));
+        VK_CUDA(cudaMemcpyAsync(dp.p, pre.data(), pre.size(), cudaMemcpyHostToDevice, s));
+        launch_set_update(ds->bitmap.as<uint32_t>(), dl.as<uint64_t>(), dp.as<uint8_t>(), lab.size(), s);
+        VK_CUDA(cudaStreamSynchronize(s));
+      } catch (...) {
+        dl.release();
+        dp.release();
+        throw;
+      }
+      dl.release();
+      dp.release();
+      ix->kernels++;
+    }
+    ds->built_epoch = ~0ull;  // cached slot list is stale
+  });
+}
+
+int vkgpu_set_cardinality(vkgpu_index *ix, uint64_t set_id, uint64_t *out_count) {
+  return guarded([&] {
+    VK_REQUIRE(ix && out_count, VKGPU_ERR_INVALID, "null argument");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    DeviceSet *ds = find_set(ix, set_id);
+    DevBuf total;
+    total.reserve(8);
+    unsigned long long h = 0;
+    try {
+      VK_CUDA(cudaMemset(total.p, 0, 8));
+      launch_set_popcount(ds->bitmap.as<uint32_t>(), (ds->bits + 31) / 32, total.as<unsigned long long>(), nullptr);
+      VK_CUDA(cudaMemcpy(&h, total.p, 8, cudaMemcpyDeviceToHost));
+    } catch (...) {
+      total.release();
+      throw;
+    }
+    total.release();
+    ix->kernels++;
+    *out_count = h;
+  });
+}
+
+int vkgpu_set_read(vkgpu_index *ix, uint64_t set_id, uint8_t *out_bitmap, uint64_t bits) {
+  return guarded([&] {
+    VK_REQUIRE(ix && (out_bitmap || bits == 0), VKGPU_ERR_INVALID, "null argument");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    DeviceSet *ds = find_set(ix, set_id);
+    const uint64_t out_bytes = (bits + 7) / 8, have = std::min<uint64_t>(out_bytes, ((ds->bits + 31) / 32) * 4);
+    std::memset(out_bitmap, 0, out_bytes);
+    if (have) VK_CUDA(cudaMemcpy(out_bitmap, ds->bitmap.p, have, cudaMemcpyDeviceToHost));
+    if (bits & 7) out_bitmap[out_bytes - 1] &= (uint8_t)((1u << (bits & 7)) - 1u);
+  });
+}
+
+int vkgpu_values_create(vkgpu_index *ix, uint64_t *out_values_id) {
+  return guarded([&] {
+    VK_REQUIRE(ix && out_values_id, VKGPU_ERR_INVALID, "null argument");
     std::lock_guard<std::mutex> lk(ix->sets_mu);
     const uint64_t id = ix->next_set_id++;
-    ix->sets.emplace(id, std::move(ds));
-    *out_set_id = id;
+    ix->values.emplace(id, std::make_unique<DeviceValues>());
+    *out_values_id = id;
+  });
+}
+
+int vkgpu_values_destroy(vkgpu_index *ix, uint64_t values_id) {
+  return guarded([&] {
+    VK_REQUIRE(ix, VKGPU_ERR_INVALID, "null argument");
+    VK_CUDA(cudaSetDevice(ix->device));
+    std::unique_lock<std::shared_mutex> lk(ix->rw);
+    std::lock_guard<std::mutex> sl(ix->sets_mu);
+    auto it = ix->values.find(values_id);
+    VK_REQUIRE(it != ix->values.end(), VKGPU_ERR_NOT_FOUND, "unknown device values id");
+    it->second->vals.release();
+    it->second->has.release();
+    ix->values.erase(it);
+  });
+}
+
+static DeviceValues *find_values(vkgpu_index_impl *ix, uint64_t id) {
+  std::lock_guard<std::mutex> lk(ix->sets_mu);
+  auto it = ix->values.find(id);
+  VK_REQUIRE(it != ix->values.end(), VKGPU_ERR_NOT_FOUND, "unknown device values id");
+  return it->second.get();
+}
+
+int vkgpu_values_update(vkgpu_index *ix, uint64_t values_id, const uint64_t *labels, const double *values,
+                        const uint8_t *present, uint64_t n) {
+  return guarded([&] {
+    VK_REQUIRE(ix && (n == 0 || (labels && values && present)), VKGPU_ERR_INVALID, "null argument");
+    if (n == 0) return;
+    std::unique_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    DeviceValues *dv = find_values(ix, values_id);
+    cudaStream_t s = ix->mut_stream;
+    uint64_t need = dv->bits;
+    for (uint64_t i = 0; i < n; i++)
+      if (present[i]) need = std::max(need, labels[i] + 1);
+    std::vector<uint64_t> lab;
+    std::vector<double> val;
+    std::vector<uint8_t> pre;
+    for (uint64_t i = 0; i < n; i++)
+      if (labels[i] < need) {
+        lab.push_back(labels[i]);
+        val.push_back(values[i]);
+        pre.push_back(present[i] ? 1 : 0);
+      }
+    if (need > dv->cap) {
+      const uint64_t cap = std::max<uint64_t>(need, dv->cap + dv->cap / 2 + 1024);
+      dv->vals.reserve(cap * 8, true, s);
+      grow_words(dv->has, dv->cap, cap, s);
+      dv->cap = cap;
+    }
+    dv->bits = need;
+    if (lab.empty()) return;
+    DevBuf dl, dvv, dp;
+    dl.reserve(lab.size() * 8);
+    dvv.reserve(val.size() * 8);
+    dp.reserve(pre.size());
+    try {
+      VK_CUDA(cudaMemcpyAsync(dl.p, lab.data(), lab.size() * 8, cudaMemcpyHostToDevice, s));
+      VK_CUDA(cudaMemcpyAsync(dvv.p, val.data(), val.size() * 8, cudaMemcpyHostToDevice, s));
+      VK_CUDA(cudaMemcpyAsync(dp.p, pre.data(), pre.size(), cudaMemcpyHostToDevice, s));
+      launch_values_update(dv->vals.as<double>(), dv->has.as<uint32_t>(), dl.as<uint64_t>(), dvv.as<double>(),
+                           dp.as<uint8_t>(), lab.size(), s);
+      VK_CUDA(cudaStreamSynchronize(s));
+    } catch (...) {
+      dl.release();
+      dvv.release();
+      dp.release();
+      throw;
+    }
+    dl.release();
+    dvv.release();
+    dp.release();
+    ix->kernels++;
+  });
+}
+
+int vkgpu_set_from_range(vkgpu_index *ix, uint64_t values_id, double start, int inclusive_start, double end,
+                         int inclusive_end, uint64_t *out_set_id) {
+  return guarded([&] {
+    VK_REQUIRE(ix && out_set_id, VKGPU_ERR_INVALID, "null argument");
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    DeviceValues *dv = find_values(ix, values_id);
+    auto ds = new_device_set(dv->bits);
+    if (dv->bits) {
+      cudaStream_t s = nullptr;
+      VK_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+      try {
+        launch_values_range(dv->vals.as<double>(), dv->has.as<uint32_t>(), dv->bits, start, inclusive_start, end,
+                            inclusive_end, ds->bitmap.as<uint32_t>(), s);
+        VK_CUDA(cudaStreamSynchronize(s));
+      } catch (...) {
+        cudaStreamDestroy(s);
+        ds->bitmap.release();
+        throw;
+      }
+      cudaStreamDestroy(s);
+      ix->kernels++;
+    }
+    *out_set_id = publish_set(ix, std::move(ds));
   });
 }
 

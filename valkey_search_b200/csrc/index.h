@@ -121,6 +121,15 @@ struct DeviceSet {
   uint64_t built_epoch = ~0ull;
 };
 
+// Device-resident NUMERIC attribute (N1): value per label + presence bitmap; vkgpu_set_from_range turns a range
+// predicate into a DeviceSet without the values leaving HBM.
+struct DeviceValues {
+  DevBuf vals;  // double[cap]
+  DevBuf has;   // u32[(cap + 31) / 32]
+  uint64_t cap = 0;   // labels < cap are addressable
+  uint64_t bits = 0;  // 1 + largest label ever set
+};
+
 struct vkgpu_index_impl {
   vkgpu_config cfg{};
   int device = 0;
@@ -148,6 +157,7 @@ struct vkgpu_index_impl {
   std::mutex sets_mu;
   std::unordered_map<uint64_t, std::unique_ptr<DeviceSet>> sets;
   uint64_t next_set_id = 1;
+  std::unordered_map<uint64_t, std::unique_ptr<DeviceValues>> values;
   uint64_t mutation_epoch = 0;   // bumped by every add/modify/remove: cached slot lists are rebuilt lazily
   DevBuf set_scratch, set_count, set_blocks;
   std::mutex tensor_mu;
@@ -202,6 +212,15 @@ void launch_iota_labels(uint64_t *dst, uint64_t start, uint64_t n, cudaStream_t 
 // ordered compaction; counts = scratch of ceil(n/256) u32
 void launch_bitmap_to_slots(const uint64_t *labels, uint64_t n, const uint8_t *bm, uint64_t bits, uint32_t *out,
                             uint32_t *counts, unsigned long long *count, cudaStream_t s);
+// set algebra / NUMERIC ranges over label bitmaps (N1); op: 0 AND, 1 OR, 2 AND-NOT
+void launch_set_combine(int op, const uint32_t *a, uint64_t a_words, const uint32_t *b, uint64_t b_words, uint32_t *out,
+                        uint64_t out_bits, cudaStream_t s);
+void launch_set_update(uint32_t *words, const uint64_t *labels, const uint8_t *present, uint64_t n, cudaStream_t s);
+void launch_set_popcount(const uint32_t *words, uint64_t n_words, unsigned long long *total, cudaStream_t s);
+void launch_values_update(double *vals, uint32_t *has, const uint64_t *labels, const double *values,
+                          const uint8_t *present, uint64_t n, cudaStream_t s);
+void launch_values_range(const double *vals, const uint32_t *has, uint64_t bits, double start, int incl_start,
+                         double end, int incl_end, uint32_t *out, cudaStream_t s);
 void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
                                uint64_t rank_stride, uint32_t G, uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt,
                                cudaStream_t s);

@@ -1,4 +1,6 @@
 // Small support kernels: exact per-row distances, row padding on ingest, label iota, shard-result packing.
+#include <algorithm>
+
 #include "exact_dist.cuh"
 #include "index.h"
 
@@ -120,7 +122,110 @@ __global__ void __launch_bounds__(256) set_fill_kernel(const uint64_t *__restric
   if (in) out[base + __popc(bal & ((1u << lane) - 1))] = (uint32_t)i;
 }
 
+// ---- set algebra over label bitmaps ("next" row N1): AND / OR / AND-NOT of two resident bitmaps, word by word.
+// A shorter operand reads as zeros past its end; bits past `out_bits` are cleared so that every set keeps the
+// invariant "no bit at or beyond its own bit count".  HBM-bound, 12 bytes per output word.
+__global__ void __launch_bounds__(256) set_combine_kernel(int op, const uint32_t *__restrict__ a, uint64_t a_words,
+                                                          const uint32_t *__restrict__ b, uint64_t b_words,
+                                                          uint32_t *__restrict__ out, uint64_t out_words,
+                                                          uint64_t out_bits) {
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < out_words;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t x = i < a_words ? a[i] : 0u;
+    const uint32_t y = i < b_words ? b[i] : 0u;
+    uint32_t r = op == 0 ? (x & y) : op == 1 ? (x | y) : (x & ~y);
+    if (i == out_words - 1 && (out_bits & 31)) r &= (1u << (out_bits & 31)) - 1u;
+    out[i] = r;
+  }
+}
+// incremental posting-list maintenance: set / clear single labels (labels < bits, checked on the host)
+__global__ void __launch_bounds__(256) set_update_kernel(uint32_t *__restrict__ words,
+                                                         const uint64_t *__restrict__ labels,
+                                                         const uint8_t *__restrict__ present, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t lab = labels[i];
+  const uint32_t bit = 1u << (lab & 31);
+  if (present[i])
+    atomicOr(&words[lab >> 5], bit);
+  else
+    atomicAnd(&words[lab >> 5], ~bit);
+}
+__global__ void __launch_bounds__(256) set_popcount_kernel(const uint32_t *__restrict__ words, uint64_t n_words,
+                                                           unsigned long long *__restrict__ total) {
+  unsigned long long c = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_words;
+       i += (uint64_t)gridDim.x * blockDim.x)
+    c += __popc(words[i]);
+  for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+  if ((threadIdx.x & 31) == 0 && c) atomicAdd(total, c);
+}
+// NUMERIC attribute: per-label value + presence word; the range test is NumericPredicate::Evaluate
+// (src/query/predicate.cc:332-341) verbatim, one label per thread, one ballot per output word.
+__global__ void __launch_bounds__(256) values_update_kernel(double *__restrict__ vals, uint32_t *__restrict__ has,
+                                                            const uint64_t *__restrict__ labels,
+                                                            const double *__restrict__ values,
+                                                            const uint8_t *__restrict__ present, uint64_t n) {
+  const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint64_t lab = labels[i];
+  const uint32_t bit = 1u << (lab & 31);
+  if (present[i]) {
+    vals[lab] = values[i];
+    atomicOr(&has[lab >> 5], bit);
+  } else {
+    atomicAnd(&has[lab >> 5], ~bit);
+  }
+}
+__global__ void __launch_bounds__(256) values_range_kernel(const double *__restrict__ vals,
+                                                           const uint32_t *__restrict__ has, uint64_t bits,
+                                                           double start, int incl_start, double end, int incl_end,
+                                                           uint32_t *__restrict__ out) {
+  const uint64_t lab = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // grid covers ceil(bits/32)*32 labels
+  bool m = false;
+  if (lab < bits && ((has[lab >> 5] >> (lab & 31)) & 1u)) {
+    const double v = vals[lab];
+    m = ((v > start || (incl_start && v == start)) && v < end) || (incl_end && v == end);
+  }
+  const uint32_t bal = __ballot_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0 && (lab >> 5) < ((bits + 31) >> 5)) out[lab >> 5] = bal;
+}
+
 }  // namespace
+
+void launch_set_combine(int op, const uint32_t *a, uint64_t a_words, const uint32_t *b, uint64_t b_words, uint32_t *out,
+                        uint64_t out_bits, cudaStream_t s) {
+  const uint64_t out_words = (out_bits + 31) / 32;
+  if (out_words == 0) return;
+  const uint32_t blocks = (uint32_t)std::min<uint64_t>((out_words + 255) / 256, 148 * 8);
+  set_combine_kernel<<<blocks, 256, 0, s>>>(op, a, a_words, b, b_words, out, out_words, out_bits);
+  VK_CUDA(cudaGetLastError());
+}
+void launch_set_update(uint32_t *words, const uint64_t *labels, const uint8_t *present, uint64_t n, cudaStream_t s) {
+  if (n == 0) return;
+  set_update_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(words, labels, present, n);
+  VK_CUDA(cudaGetLastError());
+}
+void launch_set_popcount(const uint32_t *words, uint64_t n_words, unsigned long long *total, cudaStream_t s) {
+  if (n_words == 0) return;
+  const uint32_t blocks = (uint32_t)std::min<uint64_t>((n_words + 255) / 256, 148 * 8);
+  set_popcount_kernel<<<blocks, 256, 0, s>>>(words, n_words, total);
+  VK_CUDA(cudaGetLastError());
+}
+void launch_values_update(double *vals, uint32_t *has, const uint64_t *labels, const double *values,
+                          const uint8_t *present, uint64_t n, cudaStream_t s) {
+  if (n == 0) return;
+  values_update_kernel<<<(uint32_t)((n + 255) / 256), 256, 0, s>>>(vals, has, labels, values, present, n);
+  VK_CUDA(cudaGetLastError());
+}
+void launch_values_range(const double *vals, const uint32_t *has, uint64_t bits, double start, int incl_start,
+                         double end, int incl_end, uint32_t *out, cudaStream_t s) {
+  if (bits == 0) return;
+  const uint64_t threads = ((bits + 31) / 32) * 32;
+  values_range_kernel<<<(uint32_t)((threads + 255) / 256), 256, 0, s>>>(vals, has, bits, start, incl_start, end,
+                                                                          incl_end, out);
+  VK_CUDA(cudaGetLastError());
+}
 
 void launch_bitmap_to_slots(const uint64_t *labels, uint64_t n, const uint8_t *bm, uint64_t bits, uint32_t *out,
                             uint32_t *counts, unsigned long long *count, cudaStream_t s) {

@@ -79,7 +79,40 @@ StatusOr<uint64_t> VectorBase::TrackKey(const std::string &key, float magnitude)
   auto [it, succ] = tracked_metadata_by_key_.insert({key, TrackedKeyMetadata{id, magnitude}});
   if (!succ) return vks::InvalidArgumentError("Embedding id already exists: " + key);
   key_by_internal_id_.insert({id, key});
+  lock.unlock();
+  NotifyLabel(key, id, true);
   return id;
+}
+
+void VectorBase::AddLabelListener(LabelListener *listener) {
+  std::lock_guard<std::mutex> lock(listeners_mutex_);
+  listeners_.push_back(listener);
+}
+void VectorBase::RemoveLabelListener(LabelListener *listener) {
+  std::lock_guard<std::mutex> lock(listeners_mutex_);
+  listeners_.erase(std::remove(listeners_.begin(), listeners_.end(), listener), listeners_.end());
+}
+void VectorBase::NotifyLabel(const std::string &key, uint64_t label, bool assigned) const {
+  std::vector<LabelListener *> copy;
+  {
+    std::lock_guard<std::mutex> lock(listeners_mutex_);
+    copy = listeners_;
+  }
+  for (LabelListener *l : copy) assigned ? l->OnLabelAssigned(key, label) : l->OnLabelReleased(key, label);
+}
+std::optional<uint64_t> VectorBase::GetLabel(const std::string &key) const {
+  std::shared_lock lock(key_to_metadata_mutex_);
+  auto it = tracked_metadata_by_key_.find(key);
+  if (it == tracked_metadata_by_key_.end()) return std::nullopt;
+  return it->second.internal_id;
+}
+
+StatusOr<std::vector<Neighbor>> VectorBase::SearchWithDeviceSet(std::string_view query, uint64_t count,
+                                                                uint64_t device_set,
+                                                                std::optional<size_t> ef_runtime) const {
+  vkgpu_filter f{};
+  f.device_set = device_set;
+  return SearchOne(query, count, (uint32_t)ef_runtime.value_or(0), &f, CancelNever());
 }
 
 StatusOr<std::optional<uint64_t>> VectorBase::UnTrackKey(const std::string &key) {
@@ -94,6 +127,8 @@ StatusOr<std::optional<uint64_t>> VectorBase::UnTrackKey(const std::string &key)
     return vks::InvalidArgumentError(
         "Error while untracking key - key was not found in key_by_internal_id_ but in internal_by_key_");
   key_by_internal_id_.erase(kit);
+  lock.unlock();
+  NotifyLabel(key, id, false);
   return std::optional<uint64_t>(id);
 }
 
@@ -270,6 +305,7 @@ StatusOr<std::vector<Neighbor>> VectorBase::SearchPrefiltered(std::string_view q
     auto it = tracked_metadata_by_key_.find(key);
     if (it != tracked_metadata_by_key_.end()) ids.push_back(it->second.internal_id);
   }
+  if (ids.empty()) return std::vector<Neighbor>();  // no qualifying key: nothing to rank (a NULL list means "no filter")
   vkgpu_filter f{};
   f.labels = ids.data();
   f.n_labels = ids.size();
@@ -427,6 +463,7 @@ Status VectorBase::LoadTrackedKeys(InputStream &iter) {
   std::unique_lock lock(key_to_metadata_mutex_);
   uint64_t max_id = 0;
   bool any = false;
+  std::vector<std::pair<std::string, uint64_t>> loaded;
   while (iter.HasNext()) {
     auto chunk = iter.LoadChunk();
     if (!chunk.ok()) return chunk.status();
@@ -436,8 +473,11 @@ Status VectorBase::LoadTrackedKeys(InputStream &iter) {
     key_by_internal_id_.insert({pb.internal_id, pb.key});
     max_id = std::max(max_id, pb.internal_id);
     any = true;
+    loaded.emplace_back(pb.key, pb.internal_id);
   }
   inc_id_ = any ? max_id + 1 : inc_id_;  // vector_base.cc:480-481: max label + 1
+  lock.unlock();
+  for (const auto &[key, id] : loaded) NotifyLabel(key, id, true);
   return vks::OkStatus();
 }
 

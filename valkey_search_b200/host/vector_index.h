@@ -95,6 +95,15 @@ using KeyFilter = std::function<bool(const std::string &key)>;
 // sqrt, scale by 1/magnitude; the zero vector keeps scale 1.
 std::vector<char> NormalizeEmbedding(std::string_view record, size_t type_size, float *magnitude = nullptr);
 
+// Told when a key gains or loses its internal id (= label on the device): TrackKey / UnTrackKey / LoadTrackedKeys.
+// The TAG / NUMERIC bridge (host/filter_index.h) keeps its device bitmaps over labels in step through this.
+class LabelListener {
+ public:
+  virtual ~LabelListener() = default;
+  virtual void OnLabelAssigned(const std::string &key, uint64_t label) = 0;
+  virtual void OnLabelReleased(const std::string &key, uint64_t label) = 0;
+};
+
 class VectorBase {
  public:
   virtual ~VectorBase();
@@ -142,6 +151,15 @@ class VectorBase {
   vkgpu_index *handle() const { return gpu_; }
   vkgpu_stats Stats() const;
 
+  // ---- hooks of the TAG / NUMERIC bridge (host/filter_index.h)
+  void AddLabelListener(LabelListener *listener);
+  void RemoveLabelListener(LabelListener *listener);
+  std::optional<uint64_t> GetLabel(const std::string &key) const;
+  // kNN restricted to a device-resident label set (vkgpu_set_*): FLAT = exact scan over the set's rows (the
+  // pre-filter path, vector_base.cc:509-530), HNSW = inline filter (hnswalg.h:515-524)
+  StatusOr<std::vector<Neighbor>> SearchWithDeviceSet(std::string_view query, uint64_t count, uint64_t device_set,
+                                                      std::optional<size_t> ef_runtime = std::nullopt) const;
+
  protected:
   VectorBase(int dimensions, DistanceMetric metric);
   Status CreateCore(const vkgpu_config &cfg);
@@ -172,6 +190,9 @@ class VectorBase {
   std::unordered_map<std::string, TrackedKeyMetadata> tracked_metadata_by_key_;
   std::unordered_map<uint64_t, std::string> key_by_internal_id_;
   uint64_t inc_id_{0};
+  mutable std::mutex listeners_mutex_;
+  std::vector<LabelListener *> listeners_;
+  void NotifyLabel(const std::string &key, uint64_t label, bool assigned) const;
 };
 
 template <typename T>
