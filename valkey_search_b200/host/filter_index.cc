@@ -186,6 +186,7 @@ void Tag::DeindexTagForKey(const std::string &tag, const std::string &key) {
 // A key gained or lost its label: move its bit in every posting it belongs to.  Two spellings of one tag in a
 // record ("A,a" on a case-insensitive index) share a posting; a set of labels does not mind being told twice.
 void Tag::ApplyLabel(const std::string &key, uint64_t label, bool present) {
+  std::lock_guard<std::mutex> lock(index_mutex_);
   auto it = tracked_tags_by_keys_.find(key);
   if (it == tracked_tags_by_keys_.end()) return;
   for (const auto &tag : ParseRecordTags(it->second, separator_)) {
@@ -198,6 +199,7 @@ void Tag::ApplyLabel(const std::string &key, uint64_t label, bool present) {
 
 StatusOr<RecordResult> Tag::AddRecord(const std::string &key, std::string_view data) {
   auto parsed_tags = ParseRecordTags(data, separator_);
+  std::lock_guard<std::mutex> lock(index_mutex_);
   if (parsed_tags.empty()) {  // an empty tag set is a missing value
     untracked_keys_.insert(key);
     return RecordResult::kMissing;
@@ -215,6 +217,7 @@ StatusOr<RecordResult> Tag::ModifyRecord(const std::string &key, std::string_vie
     (void)RemoveRecord(key, DeletionType::kIdentifier);
     return RecordResult::kMissing;
   }
+  std::lock_guard<std::mutex> lock(index_mutex_);
   auto it = tracked_tags_by_keys_.find(key);
   if (it == tracked_tags_by_keys_.end()) return vks::NotFoundError("Key `" + key + "` not found");
   auto old_parsed_tags = ParseRecordTags(it->second, separator_);
@@ -231,6 +234,7 @@ StatusOr<RecordResult> Tag::ModifyRecord(const std::string &key, std::string_vie
 }
 
 StatusOr<bool> Tag::RemoveRecord(const std::string &key, DeletionType deletion_type) {
+  std::lock_guard<std::mutex> lock(index_mutex_);
   if (deletion_type == DeletionType::kRecord)
     untracked_keys_.erase(key);  // the key is gone
   else
@@ -243,6 +247,7 @@ StatusOr<bool> Tag::RemoveRecord(const std::string &key, DeletionType deletion_t
 }
 
 std::optional<std::set<std::string>> Tag::GetValue(const std::string &key) const {
+  std::lock_guard<std::mutex> lock(index_mutex_);
   auto it = tracked_tags_by_keys_.find(key);
   if (it == tracked_tags_by_keys_.end()) return std::nullopt;
   return ParseRecordTags(it->second, separator_);
@@ -262,6 +267,7 @@ void ForEachMatchingPosting(Tree &tree, const std::string &norm, bool is_prefix,
 }  // namespace
 
 std::vector<std::string> Tag::Search(const TagPredicate &predicate, bool negate) const {
+  std::lock_guard<std::mutex> lock(index_mutex_);
   std::set<const Posting *> seen;
   std::vector<const Posting *> matched;
   for (const auto &tag : predicate.GetTags()) {
@@ -284,6 +290,7 @@ std::vector<std::string> Tag::Search(const TagPredicate &predicate, bool negate)
 
 StatusOr<DeviceSetRef> Tag::SearchDevice(const TagPredicate &predicate) {
   if (!gpu()) return vks::InternalError("no vector index attached: device sets are unavailable");
+  std::lock_guard<std::mutex> lock(index_mutex_);  // flushing a posting's queue mutates it
   std::set<Posting *> seen;
   std::vector<Posting *> matched;
   for (const auto &tag : predicate.GetTags()) {
@@ -327,12 +334,15 @@ std::optional<double> Numeric::ParseNumber(std::string_view data) {
   return v;
 }
 
-const double *Numeric::GetValue(const std::string &key) const {
+std::optional<double> Numeric::GetValue(const std::string &key) const {
+  std::lock_guard<std::mutex> lock(index_mutex_);
   auto it = tracked_keys_.find(key);
-  return it == tracked_keys_.end() ? nullptr : &it->second;
+  if (it == tracked_keys_.end()) return std::nullopt;
+  return it->second;
 }
 
 void Numeric::ApplyLabel(const std::string &key, uint64_t label, bool present) {
+  std::lock_guard<std::mutex> lock(index_mutex_);
   auto it = tracked_keys_.find(key);
   if (it == tracked_keys_.end()) return;
   pending_[label] = PendingValue{it->second, (uint8_t)(present ? 1 : 0)};
@@ -340,6 +350,7 @@ void Numeric::ApplyLabel(const std::string &key, uint64_t label, bool present) {
 
 StatusOr<RecordResult> Numeric::AddRecord(const std::string &key, std::string_view data) {
   auto value = ParseNumber(data);
+  std::lock_guard<std::mutex> lock(index_mutex_);
   if (!value) {  // does not parse: invalid data, tracked as a key without the field
     untracked_keys_.insert(key);
     return RecordResult::kInvalidData;
@@ -357,6 +368,7 @@ StatusOr<RecordResult> Numeric::ModifyRecord(const std::string &key, std::string
     (void)RemoveRecord(key, DeletionType::kIdentifier);
     return RecordResult::kInvalidData;
   }
+  std::lock_guard<std::mutex> lock(index_mutex_);
   auto it = tracked_keys_.find(key);
   if (it == tracked_keys_.end()) return vks::NotFoundError("Key `" + key + "` not found");
   it->second = *value;
@@ -365,6 +377,7 @@ StatusOr<RecordResult> Numeric::ModifyRecord(const std::string &key, std::string
 }
 
 StatusOr<bool> Numeric::RemoveRecord(const std::string &key, DeletionType deletion_type) {
+  std::lock_guard<std::mutex> lock(index_mutex_);
   if (deletion_type == DeletionType::kRecord)
     untracked_keys_.erase(key);
   else
@@ -377,6 +390,7 @@ StatusOr<bool> Numeric::RemoveRecord(const std::string &key, DeletionType deleti
 }
 
 std::vector<std::string> Numeric::Search(const NumericPredicate &predicate, bool negate) const {
+  std::lock_guard<std::mutex> lock(index_mutex_);
   std::vector<std::string> out;
   for (const auto &[key, value] : tracked_keys_)
     if (predicate.Evaluate(&value) != negate) out.push_back(key);
@@ -403,6 +417,7 @@ Status Numeric::Flush() {
 }
 
 StatusOr<DeviceSetRef> Numeric::SearchDevice(const NumericPredicate &predicate) {
+  std::lock_guard<std::mutex> lock(index_mutex_);
   VKS_RETURN_IF_ERROR(Flush());
   uint64_t id = 0;
   VKS_RETURN_IF_ERROR(RcToStatus(gpu(), vkgpu_set_from_range(gpu(), values_id_, predicate.GetStart(),
@@ -446,7 +461,10 @@ NumericPredicate::NumericPredicate(Numeric *index, double start, bool is_inclusi
       is_inclusive_start_(is_inclusive_start),
       is_inclusive_end_(is_inclusive_end) {}
 
-bool NumericPredicate::Evaluate(const std::string &key) const { return Evaluate(index_->GetValue(key)); }
+bool NumericPredicate::Evaluate(const std::string &key) const {
+  const std::optional<double> value = index_->GetValue(key);
+  return Evaluate(value ? &*value : nullptr);
+}
 
 bool NumericPredicate::Evaluate(const double *value) const {
   if (!value) return false;
@@ -477,8 +495,18 @@ DeviceFilterEvaluator::DeviceFilterEvaluator(VectorBase *vectors) : vectors_(vec
   vectors_->AddLabelListener(this);
 }
 DeviceFilterEvaluator::~DeviceFilterEvaluator() { vectors_->RemoveLabelListener(this); }
-void DeviceFilterEvaluator::OnLabelAssigned(const std::string &, uint64_t label) { universe_.Set(label, true); }
-void DeviceFilterEvaluator::OnLabelReleased(const std::string &, uint64_t label) { universe_.Set(label, false); }
+void DeviceFilterEvaluator::OnLabelAssigned(const std::string &, uint64_t label) {
+  std::lock_guard<std::mutex> lock(mutex_);
+  universe_.Set(label, true);
+}
+void DeviceFilterEvaluator::OnLabelReleased(const std::string &, uint64_t label) {
+  std::lock_guard<std::mutex> lock(mutex_);
+  universe_.Set(label, false);
+}
+StatusOr<uint64_t> DeviceFilterEvaluator::UniverseId() {
+  std::lock_guard<std::mutex> lock(mutex_);
+  return universe_.Id();
+}
 
 StatusOr<DeviceSetRef> DeviceFilterEvaluator::Evaluate(const Predicate &root) {
   vkgpu_index *gpu = vectors_->handle();
@@ -494,7 +522,7 @@ StatusOr<DeviceSetRef> DeviceFilterEvaluator::Evaluate(const Predicate &root) {
     case PredicateType::kNegate: {
       auto child = Evaluate(*static_cast<const NegatePredicate &>(root).GetPredicate());
       if (!child.ok()) return child.status();
-      auto all = universe_.Id();
+      auto all = UniverseId();
       if (!all.ok()) return all.status();
       return Combine(gpu, VKGPU_SET_ANDNOT, DeviceSetRef(gpu, *all, false), *child);
     }
@@ -504,7 +532,7 @@ StatusOr<DeviceSetRef> DeviceFilterEvaluator::Evaluate(const Predicate &root) {
       const bool is_and = root.GetType() == PredicateType::kComposedAnd;
       if (p.GetChildren().empty()) {  // AND of nothing is everything, OR of nothing is nothing
         if (!is_and) return EmptySet(gpu);
-        auto all = universe_.Id();
+        auto all = UniverseId();
         if (!all.ok()) return all.status();
         return DeviceSetRef(gpu, *all, false);
       }

@@ -3,7 +3,7 @@
 // query's filter is evaluated as set algebra on the device and handed to the kNN kernels by id — no per-key
 // predicate evaluation, no key -> id -> slot hash lookups and no candidate list crossing PCIe.
 //
-// What is mirrored (same names, argument meaning and error behaviour; tests/native/host_mirror_test.cc re-states
+// What is mirrored (same names, argument meaning and error behaviour; tests/native/filter_index_test.cc re-states
 // testing/tag_index_test.cc and testing/numeric_index_test.cc):
 //   indexes::Tag      src/indexes/tag.{h,cc}      AddRecord / ModifyRecord / RemoveRecord, untracked keys,
 //                                                  ParseSearchTags / ParseRecordTags / UnescapeTag, Search (+negate)
@@ -18,6 +18,7 @@
 #pragma once
 #include <map>
 #include <memory>
+#include <mutex>
 #include <optional>
 #include <set>
 #include <string>
@@ -93,10 +94,22 @@ class Tag : public FilterIndexBase {
   StatusOr<RecordResult> AddRecord(const std::string &key, std::string_view data);     // tag.cc:107-129
   StatusOr<bool> RemoveRecord(const std::string &key, DeletionType deletion_type = DeletionType::kNone);  // :244-265
   StatusOr<RecordResult> ModifyRecord(const std::string &key, std::string_view data);  // tag.cc:208-242
-  size_t GetTrackedKeyCount() const { return tracked_tags_by_keys_.size(); }
-  size_t GetUnTrackedKeyCount() const { return untracked_keys_.size(); }
-  bool IsTracked(const std::string &key) const { return tracked_tags_by_keys_.count(key) != 0; }
-  bool IsUnTracked(const std::string &key) const { return untracked_keys_.count(key) != 0; }
+  size_t GetTrackedKeyCount() const {
+    std::lock_guard<std::mutex> lock(index_mutex_);
+    return tracked_tags_by_keys_.size();
+  }
+  size_t GetUnTrackedKeyCount() const {
+    std::lock_guard<std::mutex> lock(index_mutex_);
+    return untracked_keys_.size();
+  }
+  bool IsTracked(const std::string &key) const {
+    std::lock_guard<std::mutex> lock(index_mutex_);
+    return tracked_tags_by_keys_.count(key) != 0;
+  }
+  bool IsUnTracked(const std::string &key) const {
+    std::lock_guard<std::mutex> lock(index_mutex_);
+    return untracked_keys_.count(key) != 0;
+  }
   char GetSeparator() const { return separator_; }
   bool IsCaseSensitive() const { return case_sensitive_; }
   // the parsed tag set of a key (tag.cc:306-315), nullopt when the key is not tracked
@@ -131,6 +144,8 @@ class Tag : public FilterIndexBase {
   std::unordered_map<std::string, std::string> tracked_tags_by_keys_;  // key -> raw tag string
   std::unordered_set<std::string> untracked_keys_;
   std::map<std::string, Posting> tree_;  // normalised tag -> posting; ordered, so a prefix is a range (the rax)
+  mutable std::mutex index_mutex_;       // as Tag::index_mutex_ (tag.h).  Taken before VectorBase's key lock, never after:
+                                         // VectorBase notifies its listeners with no lock of its own held
 };
 
 class Numeric : public FilterIndexBase {
@@ -140,10 +155,20 @@ class Numeric : public FilterIndexBase {
   StatusOr<RecordResult> AddRecord(const std::string &key, std::string_view data);     // numeric.cc:44-63
   StatusOr<bool> RemoveRecord(const std::string &key, DeletionType deletion_type = DeletionType::kNone);
   StatusOr<RecordResult> ModifyRecord(const std::string &key, std::string_view data);  // numeric.cc:65-86
-  size_t GetTrackedKeyCount() const { return tracked_keys_.size(); }
-  size_t GetUnTrackedKeyCount() const { return untracked_keys_.size(); }
-  bool IsTracked(const std::string &key) const { return tracked_keys_.count(key) != 0; }
-  const double *GetValue(const std::string &key) const;
+  size_t GetTrackedKeyCount() const {
+    std::lock_guard<std::mutex> lock(index_mutex_);
+    return tracked_keys_.size();
+  }
+  size_t GetUnTrackedKeyCount() const {
+    std::lock_guard<std::mutex> lock(index_mutex_);
+    return untracked_keys_.size();
+  }
+  bool IsTracked(const std::string &key) const {
+    std::lock_guard<std::mutex> lock(index_mutex_);
+    return tracked_keys_.count(key) != 0;
+  }
+  // the value of a key, or nullopt when it has none (read during searches, when the index is not mutated)
+  std::optional<double> GetValue(const std::string &key) const;
   static std::optional<double> ParseNumber(std::string_view data);  // numeric.cc:30-36
   std::vector<std::string> Search(const NumericPredicate &predicate, bool negate) const;
   StatusOr<DeviceSetRef> SearchDevice(const NumericPredicate &predicate);
@@ -161,6 +186,7 @@ class Numeric : public FilterIndexBase {
     uint8_t present;
   };
   std::unordered_map<uint64_t, PendingValue> pending_;  // label -> last write
+  mutable std::mutex index_mutex_;
 };
 
 // ---- predicates (src/query/predicate.h)
@@ -251,8 +277,10 @@ class DeviceFilterEvaluator : public LabelListener {
   std::vector<std::string> EvaluateOnHost(const Predicate &root) const;
 
  private:
+  StatusOr<uint64_t> UniverseId();
   VectorBase *vectors_;
   DevicePosting universe_;
+  std::mutex mutex_;  // guards universe_
 };
 
 }  // namespace valkey_search::indexes
