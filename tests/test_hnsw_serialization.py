@@ -240,6 +240,22 @@ def test_large_graph_round_trip_and_cross_load(built, tmp_path):
     assert fields[3] == n
 
 
+def test_old_snapshot_header_with_unpadded_offsets_loads(built, tmp_path):
+    """LoadRecomputesAlignedOffsetForOldSnapshot (vector_test.cc:764-801): older files recorded the unpadded offset_data
+    (132) and label_offset (140); the geometry is recomputed from M, the header's copies are not trusted."""
+    unpadded = 2 * M * 4 + 4
+    hdr = encode_header({1: 0, 2: 16, 3: 0, 4: unpadded + D * 4 + 8, 5: unpadded + 8, 6: unpadded, 7: -1, 8: 0, 9: M,
+                         10: 2 * M, 11: M, 12: 1.0 / np.log(float(M)), 13: EFC})
+    fields, err, again = ours_load([hdr], tmp_path, cap=16, resave=True)
+    assert err is None and fields[0] == 0 and fields[3] == 16
+    # what we write back carries the current (padded) label offset, like a file the reference writes today
+    h = parse_header(again[0])
+    assert h[5] == ((unpadded + 7) & ~7) + 8 and h[6] == unpadded and h[7] == -1
+    if O.ref() is not None:
+        assert O.ref_hnsw_load([hdr], D, O.L2, 16, M)[1] is None
+        assert O.ref_hnsw_load(again, D, O.L2, 16, M)[1] is None
+
+
 # ---------------------------------------------------------------------------------------------- header corruption
 def test_reject_header_m_mismatch(built, tmp_path):
     expect_reject(with_header(multilayer_golden(), m=M + 1), "header M does not match", tmp_path)
