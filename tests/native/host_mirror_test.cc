@@ -854,6 +854,29 @@ static int PrintWire() {
 
 // host-only: normalisation arithmetic (vector_base.cc:112-138) and the no-CPU-fallback contract
 static void HostOnly(bool have_gpu) {
+  {  // NormalizeStringRecordTests (testing/vector_test.cc:303-351)
+    struct {
+      const char *record;
+      bool success;
+      std::vector<float> expected;
+    } cases[] = {{"[ 0.1]", true, {0.1f}},
+                 {"[,0.1]", true, {0.1f}},
+                 {"[ 0.1, ,0.2,0.3,]", true, {0.1f, 0.2f, 0.3f}},
+                 {"[ 0.1, ,0.2,a,]", false, {}},
+                 {"1.5, -2e3", true, {1.5f, -2000.0f}},  // brackets are optional
+                 {"", true, {}}};
+    for (const auto &c : cases) {
+      auto r = VectorBase::NormalizeStringRecord(c.record);
+      EXPECT_EQ(r.has_value(), c.success);
+      if (!r || !c.success) continue;
+      EXPECT_EQ(r->size(), c.expected.size() * sizeof(float));
+      for (size_t i = 0; i < c.expected.size() && (i + 1) * 4 <= r->size(); i++) {
+        float value;
+        std::memcpy(&value, r->data() + i * 4, 4);
+        EXPECT_TRUE(value == c.expected[i]);
+      }
+    }
+  }
   std::vector<float> v = {3.0f, 4.0f, 0.0f};
   float mag = 0;
   auto n = NormalizeEmbedding(VectorToStr(v), sizeof(float), &mag);

@@ -6,6 +6,7 @@
 #include "hnsw_serialization.h"
 
 #include <algorithm>
+#include <cctype>
 #include <cmath>
 #include <cstring>
 
@@ -187,6 +188,32 @@ StatusOr<bool> VectorBase::RemoveRecord(const std::string &key, DeletionType) {
   if (!res->has_value()) return false;
   VKS_RETURN_IF_ERROR(FromRc(vkgpu_remove(gpu_, res->value())));
   return true;
+}
+
+std::optional<std::string> VectorBase::NormalizeStringRecord(std::string_view record) {
+  if (!record.empty() && record.front() == '[') {  // ConsumePrefix("["), then ConsumeSuffix("]")
+    record.remove_prefix(1);
+    if (!record.empty() && record.back() == ']') record.remove_suffix(1);
+  }
+  std::string binary_string;
+  size_t start = 0;
+  for (size_t i = 0; i <= record.size(); ++i) {
+    if (i != record.size() && record[i] != ',') continue;
+    std::string_view item = record.substr(start, i - start);
+    start = i + 1;
+    while (!item.empty() && std::isspace((unsigned char)item.front())) item.remove_prefix(1);
+    while (!item.empty() && std::isspace((unsigned char)item.back())) item.remove_suffix(1);
+    if (item.empty()) continue;  // absl::SkipWhitespace
+    // absl::SimpleAtof: decimal / scientific notation, inf and nan spellings, no hexadecimal
+    const std::string text(item);
+    for (char c : text)
+      if (c == 'x' || c == 'X') return std::nullopt;
+    char *end = nullptr;
+    const float value = std::strtof(text.c_str(), &end);
+    if (end != text.c_str() + text.size()) return std::nullopt;
+    binary_string.append(reinterpret_cast<const char *>(&value), sizeof(float));
+  }
+  return binary_string;
 }
 
 size_t VectorBase::GetCapacity() const { return Stats().capacity; }

@@ -115,6 +115,10 @@ class VectorBase {
   StatusOr<bool> RemoveRecord(const std::string &key, DeletionType deletion_type = DeletionType::kNone);
   StatusOr<RecordResult> ModifyRecord(const std::string &key, std::string_view record);
 
+  // NormalizeStringRecord (vector_base.cc:532-551): the textual vector of a JSON attribute ("[0.1, 0.2]", brackets
+  // optional, empty or blank items skipped) -> packed fp32 bytes; nullopt when an item is not a number.  What the
+  // ingest path runs before AddRecord for JSON-typed indexes.
+  static std::optional<std::string> NormalizeStringRecord(std::string_view record);  // a const member in the reference
   size_t GetCapacity() const;
   bool GetNormalize() const { return normalize_; }
   int GetDimensions() const { return dimensions_; }
