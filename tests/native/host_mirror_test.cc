@@ -4,6 +4,7 @@
 // same cases (TestIndex :238-291 through BasicHNSW/BasicFlat :353-375, EfRuntimeRecall :439-500) plus the
 // integration test's cosine goldens (testing/integration/vector_search_integration_test.py:19-23,144-166) and the
 // pre-filter path.  Needs a B200: there is no CPU path behind the ABI.  `--host-only` runs the host-side cases.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -11,6 +12,7 @@
 #include <string>
 #include <vector>
 
+#include "../../valkey_search_b200/host/fanout_merge.h"
 #include "../../valkey_search_b200/host/hnsw_serialization.h"
 #include "../../valkey_search_b200/host/vector_index.h"
 
@@ -853,7 +855,51 @@ static int PrintWire() {
 }
 
 // host-only: normalisation arithmetic (vector_base.cc:112-138) and the no-CPU-fallback contract
+// Cross-shard aggregation (src/query/fanout.cc:50-64, 153-212)
+static void FanoutMerge() {
+  using valkey_search::query::fanout::SearchPartitionResultsTracker;
+  auto keys_of = [](const std::vector<Neighbor> &v) {
+    std::string s;
+    for (const auto &n : v) s += n.external_id + " ";
+    return s;
+  };
+  {  // distinct distances: the merge of the shards' top-k is the global top-k, ascending, whatever the arrival order
+    std::vector<Neighbor> all;
+    for (int i = 0; i < 40; i++) all.emplace_back("k" + std::to_string(i), (float)((i * 37) % 41));
+    std::vector<Neighbor> sorted = all;
+    std::sort(sorted.begin(), sorted.end(), [](const Neighbor &a, const Neighbor &b) { return a.distance < b.distance; });
+    for (int order = 0; order < 2; order++) {
+      SearchPartitionResultsTracker tracker(7);
+      for (int shard = 0; shard < 4; shard++) {
+        const int sh = order ? 3 - shard : shard;
+        std::vector<Neighbor> local;
+        for (int i = sh; i < 40; i += 4) local.push_back(all[i]);
+        std::sort(local.begin(), local.end(), [](const Neighbor &a, const Neighbor &b) { return a.distance < b.distance; });
+        local.resize(7);  // each shard answers its own top-k
+        tracker.AddResults(local);
+      }
+      auto merged = tracker.TakeNeighbors();
+      EXPECT_EQ(merged.size(), (size_t)7);
+      for (size_t i = 0; i < merged.size(); i++) EXPECT_EQ(merged[i].external_id, sorted[i].external_id);
+    }
+  }
+  {  // equal distances: descending key order inside the tie; once full, an equal distance is NOT admitted
+    SearchPartitionResultsTracker tracker(3);
+    std::vector<Neighbor> a = {{"b", 1.0f}, {"d", 1.0f}}, b = {{"a", 1.0f}, {"c", 1.0f}, {"e", 0.5f}};
+    tracker.AddResults(a);
+    tracker.AddResults(b);  // "a" fills the heap, "c" ties with the worst and stays out, "e" evicts the smallest key
+    EXPECT_EQ(keys_of(tracker.TakeNeighbors()), std::string("e d b "));
+    SearchPartitionResultsTracker other(3);
+    a = {{"b", 1.0f}, {"d", 1.0f}};  // AddResults moves the neighbours out, as the reference does
+    b = {{"a", 1.0f}, {"c", 1.0f}, {"e", 0.5f}};
+    other.AddResults(b);
+    other.AddResults(a);  // the other arrival order keeps a different tie: documented, not hidden
+    EXPECT_EQ(keys_of(other.TakeNeighbors()), std::string("e c a "));
+  }
+}
+
 static void HostOnly(bool have_gpu) {
+  FanoutMerge();
   {  // NormalizeStringRecordTests (testing/vector_test.cc:303-351)
     struct {
       const char *record;
