@@ -74,6 +74,46 @@ __device__ __forceinline__ float exact_dist_group(const float *__restrict__ row,
 // idle there and makes each busy thread walk the whole row.  Consecutive threads read consecutive words (no bank
 // conflict; the query read is a broadcast between the two half-warps).  `j` = lane & 15; both half-warps of a warp
 // must call (inactive ones take part in the shuffles).  Returns the distance in all 16 lanes.
+// The same arithmetic with the row read straight from GLOBAL memory: up to 48 steps (768 floats) of one lane's loads
+// are issued before the first fma, so a row costs one memory round trip instead of one per group of eight loads.
+// `q` is the query in shared memory.  Used by the opt-in DIRECT variant of the HNSW search kernel.
+template <bool L2>
+__device__ __forceinline__ float exact_dist_lane16_direct(const float *__restrict__ row, const float *__restrict__ q,
+                                                          uint32_t Dp, uint32_t j, bool active) {
+  float acc = 0.f;
+  if (active) {
+    const float *r = row + j;
+    const float *y = q + j;
+    const uint32_t steps = Dp >> 4;
+    uint32_t s = 0;
+    // unpredicated blocks (a predicate per load would cap the loads in flight at the seven predicate registers)
+#define VK_DIRECT_BLOCK(N)                                              \
+  for (; s + (N) <= steps; s += (N)) {                                  \
+    float x[N];                                                         \
+    _Pragma("unroll") for (int i = 0; i < (N); i++) x[i] = __ldg(r + (size_t)(s + i) * 16); \
+    _Pragma("unroll") for (int i = 0; i < (N); i++) {                   \
+      const float z = y[(s + i) * 16];                                  \
+      if (L2) {                                                         \
+        const float d = __fsub_rn(z, x[i]);                             \
+        acc = __fmaf_rn(d, d, acc);                                     \
+      } else {                                                          \
+        acc = __fmaf_rn(z, x[i], acc);                                  \
+      }                                                                 \
+    }                                                                   \
+  }
+    VK_DIRECT_BLOCK(48)
+    VK_DIRECT_BLOCK(16)
+    VK_DIRECT_BLOCK(4)
+    VK_DIRECT_BLOCK(1)
+#undef VK_DIRECT_BLOCK
+  }
+  acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 8));
+  acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 4));
+  acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 2));
+  acc = __fadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, 1));
+  return L2 ? acc : (float)(1.0 - (double)acc);
+}
+
 template <bool L2>
 __device__ __forceinline__ float exact_dist_lane16(const float *__restrict__ row, const float *__restrict__ q,
                                                    uint32_t Dp, uint32_t j, bool active) {
