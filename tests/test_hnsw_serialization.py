@@ -419,6 +419,16 @@ def test_validation_disabled_still_rejects_what_the_gpu_arrays_cannot_hold(built
     assert fields is None and "level-0 neighbor count exceeds 2*M" in err
 
 
+def test_absurd_element_count_fails_the_load_not_the_process(built, tmp_path):
+    """A header claiming 2^40 elements: the stream ends long before memory does."""
+    g = with_header(multilayer_golden(), curr_element_count=1 << 40, max_elements=1 << 40)
+    fields, err, _ = ours_load(g, tmp_path)
+    assert fields is None and err
+    g = with_header(multilayer_golden(), curr_element_count=(1 << 32) - 2, max_elements=1 << 33)
+    fields, err, _ = ours_load(g, tmp_path)
+    assert fields is None and err
+
+
 def test_truncated_stream_is_an_error_not_a_crash(built, tmp_path):
     g = multilayer_golden()
     for cut in (1, 5, 9, 10, len(g) - 1):

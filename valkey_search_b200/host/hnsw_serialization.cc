@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstring>
+#include <stdexcept>
 #include <unordered_map>
 
 namespace valkey_search::indexes {
@@ -235,13 +236,16 @@ StatusOr<HnswLoadResult> LoadHnswImage(InputStream &input, size_t dim, size_t ma
     g.n = cur;
     g.max_level = cur ? header.max_level : -1;
     g.enterpoint = cur ? header.enterpoint_node : 0xffffffffu;
-    g.levels.assign(cur, 0);
-    g.labels.resize(cur);
-    g.deleted.assign(cur, 0);
-    g.links0.resize(cur * maxM0);
-    g.cnt0.resize(cur);
-    g.upper_offset.assign(cur, 0);
-    g.vecs.resize(cur * dim);
+    // The arrays grow with the chunks that actually arrive: an absurd element count in a corrupt header runs out of
+    // stream long before it runs out of memory.
+    const uint64_t reserve = std::min<uint64_t>(cur, 1u << 20);
+    g.levels.reserve(reserve);
+    g.labels.reserve(reserve);
+    g.deleted.reserve(reserve);
+    g.cnt0.reserve(reserve);
+    g.upper_offset.reserve(reserve);
+    g.links0.reserve(reserve * maxM0);
+    g.vecs.reserve(reserve * dim);
 
     // level-0 records (hnswalg.h:986-1015)
     for (uint64_t i = 0; i < cur; i++) {
@@ -249,6 +253,13 @@ StatusOr<HnswLoadResult> LoadHnswImage(InputStream &input, size_t dim, size_t ma
       if (!chunk.ok()) return chunk.status();
       const std::string &c = **chunk;
       hard(c.size() == size_links_level0 + vector_size + kLabelBytes, "level-0 element chunk has the wrong size");
+      g.levels.push_back(0);
+      g.labels.push_back(0);
+      g.deleted.push_back(0);
+      g.cnt0.push_back(0);
+      g.upper_offset.push_back(0);
+      g.links0.resize((i + 1) * maxM0);
+      g.vecs.resize((i + 1) * dim);
       uint32_t word;
       std::memcpy(&word, c.data(), kU32);
       std::memcpy(&g.links0[i * maxM0], c.data() + kU32, maxM0 * kU32);
@@ -267,7 +278,7 @@ StatusOr<HnswLoadResult> LoadHnswImage(InputStream &input, size_t dim, size_t ma
 
     // label lookup + upper lists (hnswalg.h:1028-1099)
     std::unordered_map<uint64_t, uint64_t> label_lookup;
-    label_lookup.reserve(cur);
+    label_lookup.reserve(g.labels.size());
     uint64_t blocks = 0;
     for (uint64_t i = 0; i < cur; i++) {
       auto it = label_lookup.find(g.labels[i]);
@@ -324,6 +335,8 @@ StatusOr<HnswLoadResult> LoadHnswImage(InputStream &input, size_t dim, size_t ma
     return out;
   } catch (const LoadFailure &f) {
     return vks::InternalError(f.msg);
+  } catch (const std::exception &e) {  // vector_hnsw.cc:166-170: any exception fails the load, never the process
+    return vks::InternalError(std::string("HNSWLib error while loading an index: ") + e.what());
   }
 }
 
