@@ -6,6 +6,8 @@
 //                 algebra) equals the set the reference's per-key evaluation gives, and the filtered kNN through it
 //                 returns exactly what the already-verified key-list pre-filter path returns
 #include <algorithm>
+#include <cmath>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <set>
@@ -389,6 +391,41 @@ static void DeviceBridgeOn(Index *vectors, int dim, int n, bool hnsw) {
     }
   };
   check_all("after ingest");
+  if constexpr (std::is_same_v<Index, VectorHNSW<float>>) {
+    // the planner's other branch (UsePreFiltering, planner.cc:21-46): with the threshold at 1.0 every filtered query on
+    // the graph index is answered by exact distances over the qualifying keys — the k nearest of them by brute
+    // force in double precision on the host (COSINE index: rank by 1 - cos)
+    EXPECT_TRUE(valkey_search::query::UsePreFiltering(1, vectors));
+    EXPECT_FALSE(valkey_search::query::UsePreFiltering((size_t)n, vectors));
+    evaluator.SetPrefilteringThresholdRatio(1.0);
+    auto roots = build_roots();
+    for (size_t r = 0; r < roots.size(); r++) {
+      std::vector<std::string> want = evaluator.EvaluateOnHost(*roots[r]);
+      for (auto &x : q) x = Unit() * 2.0f - 1.0f;
+      auto got = evaluator.Search(Bytes(q), 10, *roots[r]);
+      EXPECT_OK(got);
+      if (!got.ok()) continue;
+      std::vector<std::pair<double, std::string>> ranked;
+      for (const auto &k : want) {
+        const int i = std::atoi(k.c_str() + 4);  // "doc:<i>"
+        double dot = 0, nq = 0, nv = 0;
+        for (int j = 0; j < dim; j++) {
+          dot += (double)q[j] * docs[i].vec[j];
+          nq += (double)q[j] * q[j];
+          nv += (double)docs[i].vec[j] * docs[i].vec[j];
+        }
+        ranked.emplace_back(1.0 - dot / std::sqrt(nq * nv), k);
+      }
+      std::sort(ranked.begin(), ranked.end());
+      EXPECT_EQ(got->size(), std::min<size_t>(10, ranked.size()));
+      std::set<std::string> a, b;
+      for (const auto &nb : *got) a.insert(nb.external_id);
+      for (size_t j = 0; j < ranked.size() && j < 10; j++) b.insert(ranked[j].second);
+      EXPECT_EQ(a, b);
+      for (size_t j = 1; j < got->size(); j++) EXPECT_TRUE((*got)[j - 1].distance <= (*got)[j].distance);
+    }
+    evaluator.SetPrefilteringThresholdRatio(0.0);  // the checks below compare against the inline filter
+  }
   // mutations: vectors leave and come back under new labels, tags and prices change, fields disappear
   for (int i = 0; i < n; i += 7) EXPECT_OK(vectors->RemoveRecord(key(i)));
   for (int i = 0; i < n; i += 14) EXPECT_OK(vectors->AddRecord(key(i), Bytes(docs[i].vec)));

@@ -555,6 +555,24 @@ StatusOr<std::vector<Neighbor>> DeviceFilterEvaluator::Search(std::string_view q
                                                               const Predicate &root, std::optional<size_t> ef_runtime) {
   auto set = Evaluate(root);
   if (!set.ok()) return set.status();
+  if (vectors_->GetIndexerType() == IndexerType::kHNSW) {
+    // the planner's choice (src/query/planner.cc:21-46, search.cc:136-170): few qualifying keys => exact distances over
+    // exactly those keys; many => the graph search with the set as its inline filter
+    vkgpu_index *gpu = vectors_->handle();
+    uint64_t qualified = 0;
+    VKS_RETURN_IF_ERROR(RcToStatus(gpu, vkgpu_set_cardinality(gpu, set->id(), &qualified)));
+    if (query::UsePreFiltering(qualified, vectors_, prefiltering_threshold_ratio_)) {
+      const uint64_t bits = vectors_->GetLabelBound();
+      std::vector<uint8_t> bitmap((bits + 7) / 8);
+      if (bits) VKS_RETURN_IF_ERROR(RcToStatus(gpu, vkgpu_set_read(gpu, set->id(), bitmap.data(), bits)));
+      std::vector<uint64_t> ids;
+      ids.reserve(qualified);
+      for (uint64_t w = 0; w < bitmap.size(); w++)
+        for (uint8_t b = bitmap[w]; b; b &= (uint8_t)(b - 1)) ids.push_back(w * 8 + (uint64_t)__builtin_ctz(b));
+      if (ids.empty()) return std::vector<Neighbor>();
+      return vectors_->ExactOverLabels(query, count, ids);
+    }
+  }
   return vectors_->SearchWithDeviceSet(query, count, set->id(), ef_runtime);
 }
 

@@ -269,18 +269,22 @@ class DeviceFilterEvaluator : public LabelListener {
 
   // the root predicate as one device set (labels of the vector index whose key satisfies it)
   StatusOr<DeviceSetRef> Evaluate(const Predicate &root);
-  // EvaluatePrefilteredKeys + CalcBestMatchingPrefilteredKeys (search.cc:401-481) in one call: exact kNN (FLAT) or
-  // inline-filtered graph search (HNSW) restricted to the keys satisfying `root`
+  // EvaluatePrefilteredKeys + CalcBestMatchingPrefilteredKeys (search.cc:401-481) in one call.  FLAT: exact kNN over
+  // the set's rows.  HNSW: the planner decides (UsePreFiltering) between exact distances over the few qualifying keys
+  // and the graph search with the set as its inline filter
   StatusOr<std::vector<Neighbor>> Search(std::string_view query, uint64_t count, const Predicate &root,
                                          std::optional<size_t> ef_runtime = std::nullopt);
   // the same set the reference's way: every tracked key of the vector index for which root.Evaluate(key) is true
   std::vector<std::string> EvaluateOnHost(const Predicate &root) const;
+  // the prefiltering-threshold-ratio config (valkey_search_options.cc:363-371); HNSW only
+  void SetPrefilteringThresholdRatio(double ratio) { prefiltering_threshold_ratio_ = ratio; }
 
  private:
   StatusOr<uint64_t> UniverseId();
   VectorBase *vectors_;
   DevicePosting universe_;
   std::mutex mutex_;  // guards universe_
+  double prefiltering_threshold_ratio_{query::kDefaultPrefilteringThresholdRatio};
 };
 
 }  // namespace valkey_search::indexes

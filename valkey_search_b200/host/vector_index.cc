@@ -101,6 +101,10 @@ void VectorBase::NotifyLabel(const std::string &key, uint64_t label, bool assign
   }
   for (LabelListener *l : copy) assigned ? l->OnLabelAssigned(key, label) : l->OnLabelReleased(key, label);
 }
+uint64_t VectorBase::GetLabelBound() const {
+  std::shared_lock lock(key_to_metadata_mutex_);
+  return inc_id_;
+}
 std::optional<uint64_t> VectorBase::GetLabel(const std::string &key) const {
   std::shared_lock lock(key_to_metadata_mutex_);
   auto it = tracked_metadata_by_key_.find(key);
@@ -333,10 +337,40 @@ StatusOr<std::vector<Neighbor>> VectorBase::SearchPrefiltered(std::string_view q
     if (it != tracked_metadata_by_key_.end()) ids.push_back(it->second.internal_id);
   }
   if (ids.empty()) return std::vector<Neighbor>();  // no qualifying key: nothing to rank (a NULL list means "no filter")
+  if (indexer_type_ == IndexerType::kHNSW) return ExactOverLabels(query, count, ids);
   vkgpu_filter f{};
   f.labels = ids.data();
   f.n_labels = ids.size();
   return SearchOne(query, count, 0, &f, CancelNever());
+}
+
+// Pre-filtering on a graph index is NOT a graph search: the reference computes one exact distance per qualifying key
+// (ComputeDistanceFromRecordImpl, vector_hnsw.cc:370-383) and keeps the `count` closest in a heap
+// (AddPrefilteredKey, vector_base.cc:509-530: admitted while the heap is short, afterwards only when strictly closer
+// than its worst).  Here: all distances in ONE vkgpu_distances call, the same heap rule on the host.
+StatusOr<std::vector<Neighbor>> VectorBase::ExactOverLabels(std::string_view query, uint64_t count,
+                                                            const std::vector<uint64_t> &ids) const {
+  if (!IsValidSizeVector(query)) return vks::InvalidArgumentError("query vector has the wrong byte length");
+  std::vector<char> norm;
+  if (normalize_) {  // search.cc:465-469
+    norm = NormalizeEmbedding(query, GetDataTypeSize());
+    query = std::string_view(norm.data(), norm.size());
+  }
+  std::vector<float> q(dimensions_);
+  std::memcpy(q.data(), query.data(), query.size());
+  std::vector<float> dist(ids.size());
+  VKS_RETURN_IF_ERROR(FromRc(vkgpu_distances(gpu_, q.data(), ids.data(), ids.size(), dist.data())));
+  std::priority_queue<std::pair<float, uint64_t>> results;
+  for (size_t i = 0; i < ids.size(); i++) {
+    if (dist[i] != dist[i]) continue;  // NaN: the label is not in the index (ComputeDistanceFromRecord failed)
+    if (results.size() < count) {
+      results.emplace(dist[i], ids[i]);
+    } else if (dist[i] < results.top().first) {
+      results.pop();
+      results.emplace(dist[i], ids[i]);
+    }
+  }
+  return CreateReply(results);
 }
 
 StatusOr<std::vector<std::vector<Neighbor>>> VectorBase::SearchBatch(std::string_view queries, uint32_t batch,
@@ -707,3 +741,12 @@ template class VectorFlat<float>;
 template class VectorHNSW<float>;
 
 }  // namespace valkey_search::indexes
+
+namespace valkey_search::query {
+bool UsePreFiltering(size_t estimated_num_of_keys, const indexes::VectorBase *vector_index,
+                     double prefiltering_threshold_ratio) {
+  if (vector_index->GetIndexerType() == indexes::IndexerType::kFlat) return true;
+  const size_t N = vector_index->GetTrackedKeyCount();
+  return (double)estimated_num_of_keys <= prefiltering_threshold_ratio * (double)N;
+}
+}  // namespace valkey_search::query

@@ -39,6 +39,7 @@ namespace valkey_search::indexes {
 using vks::Status;
 using vks::StatusOr;
 
+enum class IndexerType { kHNSW, kFlat, kNumeric, kTag, kVector, kNone, kText };  // src/indexes/index_base.h:28
 enum class DeletionType { kRecord, kIdentifier, kNone };       // src/indexes/index_base.h:37-41
 enum class RecordResult { kAdded, kMissing, kInvalidData };    // src/indexes/index_base.h:46-56
 enum class DistanceMetric { kL2 = VKGPU_L2, kIP = VKGPU_IP, kCosine = VKGPU_COSINE };  // data_model::DistanceMetric
@@ -120,6 +121,7 @@ class VectorBase {
   // ingest path runs before AddRecord for JSON-typed indexes.
   static std::optional<std::string> NormalizeStringRecord(std::string_view record);  // a const member in the reference
   size_t GetCapacity() const;
+  IndexerType GetIndexerType() const { return indexer_type_; }
   bool GetNormalize() const { return normalize_; }
   int GetDimensions() const { return dimensions_; }
   size_t GetTrackedKeyCount() const;
@@ -159,6 +161,7 @@ class VectorBase {
   void AddLabelListener(LabelListener *listener);
   void RemoveLabelListener(LabelListener *listener);
   std::optional<uint64_t> GetLabel(const std::string &key) const;
+  uint64_t GetLabelBound() const;  // every internal id handed out so far is below this (inc_id_)
   // kNN restricted to a device-resident label set (vkgpu_set_*): FLAT = exact scan over the set's rows (the
   // pre-filter path, vector_base.cc:509-530), HNSW = inline filter (hnswalg.h:515-524)
   StatusOr<std::vector<Neighbor>> SearchWithDeviceSet(std::string_view query, uint64_t count, uint64_t device_set,
@@ -174,11 +177,17 @@ class VectorBase {
   std::optional<std::vector<char>> InternVector(std::string_view record, float &magnitude) const;
   StatusOr<std::vector<Neighbor>> SearchOne(std::string_view query, uint64_t count, uint32_t ef,
                                             const vkgpu_filter *filter, CancelToken token) const;
+ public:
+  // exact kNN over an explicit list of internal ids, whatever the index type (the pre-filter of a graph index)
+  StatusOr<std::vector<Neighbor>> ExactOverLabels(std::string_view query, uint64_t count,
+                                                  const std::vector<uint64_t> &ids) const;
+ protected:
   Status FromRc(int rc) const;
   std::vector<uint64_t> IdsMatching(const KeyFilter &filter) const;  // internal ids of the keys a predicate accepts
 
   int dimensions_;
   DistanceMetric distance_metric_;
+  IndexerType indexer_type_{IndexerType::kFlat};
   bool normalize_{false};
   vkgpu_index *gpu_{nullptr};
 
@@ -251,7 +260,7 @@ class VectorHNSW : public VectorBase {
                                                                  InputStream &input, bool validate = true);
 
  private:
-  VectorHNSW(int dimensions, DistanceMetric metric) : VectorBase(dimensions, metric) {}
+  VectorHNSW(int dimensions, DistanceMetric metric) : VectorBase(dimensions, metric) { indexer_type_ = IndexerType::kHNSW; }
   uint32_t m_{16}, ef_construction_{200};
   size_t ef_runtime_{10};
 };
@@ -260,3 +269,12 @@ extern template class VectorFlat<float>;
 extern template class VectorHNSW<float>;
 
 }  // namespace valkey_search::indexes
+
+namespace valkey_search::query {
+// UsePreFiltering (src/query/planner.cc:21-46): FLAT always pre-filters (the scan shrinks with the candidate set); HNSW
+// pre-filters when the filter qualifies at most prefiltering-threshold-ratio (default 0.001,
+// src/valkey_search_options.cc:363-371) of the tracked vectors, else filters inline during the graph search.
+constexpr double kDefaultPrefilteringThresholdRatio = 0.001;
+bool UsePreFiltering(size_t estimated_num_of_keys, const indexes::VectorBase *vector_index,
+                     double prefiltering_threshold_ratio = kDefaultPrefilteringThresholdRatio);
+}  // namespace valkey_search::query
