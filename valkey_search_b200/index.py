@@ -341,7 +341,27 @@ class VectorBase:
         filter-qualified keys; keys not in the index are skipped (vector_base.cc:513-516)."""
         with self._mu:
             ids = [self.tracked_metadata_by_key_[k][0] for k in keys if k in self.tracked_metadata_by_key_]
+        if not ids:
+            return []
         Q = self._prepare_queries(query)
+        if self._ALGO == L.HNSW:
+            # pre-filtering on a graph index is one exact distance per qualifying key (vector_hnsw.cc:370-383) and
+            # AddPrefilteredKey's heap rule (vector_base.cc:509-530), not a filtered graph search
+            import heapq
+            lab = np.array(ids, np.uint64)
+            out = np.zeros(lab.size, np.float32)
+            L.check(self._lib.vkgpu_distances(self._h, self._ptr(Q[0]), self._ptr(lab), lab.size, self._ptr(out)))
+            heap = []  # max-heap on distance through negation
+            for d, i in zip(out.tolist(), ids):
+                if d != d:
+                    continue
+                if len(heap) < count:
+                    heapq.heappush(heap, (-d, i))
+                elif d < -heap[0][0]:
+                    heapq.heapreplace(heap, (-d, i))
+            best = sorted((-nd, i) for nd, i in heap)
+            return self._create_reply(np.array([b[0] for b in best], np.float32), np.array([b[1] for b in best], np.uint64),
+                                      len(best))
         dist, labels, n = self._search_raw(Q, count, 0, [{"labels": np.array(ids, np.uint64)}], 0)
         return self._create_reply(dist[0], labels[0], int(n[0]))
 
