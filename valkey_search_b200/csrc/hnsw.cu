@@ -461,8 +461,7 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
         if (act && (tid & 15) == 0) uvd[r] = d;
       }
       __syncthreads();
-      return;
-    }
+    } else {
     for (uint32_t base = 0; base < n; base += RB) {
       const uint32_t m = min(RB, n - base);
       if (warp == 0) {
@@ -482,6 +481,7 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
       }
       __syncthreads();
     }
+    }  // !DIRECT
   };
 
   // ---- entry point + greedy descent through the upper levels (hnswalg.h:1667-1697)
