@@ -131,7 +131,36 @@ def hnsw_multilayer_golden():
     print("hnsw_multilayer_golden.bin:", len(chunks), "chunks")
 
 
+def redisearch_tag_special_chars():
+    """RediSearch's recorded answers for the reference's `tag special chars` data set (integration/compatibility/
+    data_sets.py:522-556, HASH keys: a TAG field with separator ',', values holding '}', '|', '\\', quotes, tabs,
+    newlines, accents, CJK, emoji) and the 15 escaped TAG queries of test_tag_escaped_special_chars.  Pins the query-side
+    tag parsing (FilterParser::ParseTagString + Tag::ParseSearchTags + UnescapeTag) and TagPredicate matching of the
+    host mirror (valkey_search_b200/host/filter_index.cc) to a third engine's behaviour."""
+    import types
+    sys.modules.setdefault("valkey", types.ModuleType("valkey"))  # data_sets.py imports the client; nothing here uses it
+    sys.path.insert(0, os.path.join(REF, "integration", "compatibility"))
+    import data_sets
+    docs = data_sets.compute_data_sets()["tag special chars"][data_sets.SETS_KEY("hash")]
+    d = pickle.load(gzip.open(os.path.join(REF, "integration/compatibility/aggregate-answers.pickle.gz"), "rb"))
+    cases = {}
+    for a in d["answers"]:
+        if a["data_set_name"] != "tag special chars" or a["key_type"] != "hash" or a["cmd"][0] != "ft.search":
+            continue
+        assert not a["exception"]
+        res = a["result"]
+        keys = sorted(k.decode() for k in res[1::2])
+        prev = cases.setdefault(a["cmd"][2], {"query": a["cmd"][2], "count": int(res[0]), "keys": keys})
+        assert prev["count"] == int(res[0]) and prev["keys"] == keys  # the four recordings of a query agree
+    out = {"separator": ",", "case_sensitive": False, "docs": [[k, v["tags"]] for k, v in docs],
+           "cases": sorted(cases.values(), key=lambda c: c["query"])}
+    with open(os.path.join(HERE, "redisearch_tag_special_chars.json"), "w") as f:
+        json.dump(out, f, ensure_ascii=True, indent=0)
+    print("redisearch_tag_special_chars.json:", len(out["docs"]), "docs,", len(out["cases"]), "queries")
+
+
 if __name__ == "__main__":
     redisearch()
     ref_golden()
     hnsw_multilayer_golden()
+    redisearch_tag_special_chars()

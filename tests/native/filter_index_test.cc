@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <memory>
 #include <set>
 #include <string>
 #include <type_traits>
@@ -464,7 +465,79 @@ static void DeviceBridgeHnsw() {
   }
 }
 
+// --tag-golden FILE: a TAG index and queries from a text file (every string hex-encoded: "sep XX", "case 0|1",
+// "doc KEY TAGS", "query TEXT" with TEXT = the whole filter expression "@field:{ ... }"); prints per query
+// "N key key ..." (hex keys, sorted) or "ERR message".  Host only.  tests/test_zz_filter_bridge.py feeds it the
+// RediSearch answers recorded by the reference's compatibility suite.
+static std::string FromHex(const std::string &h) {
+  std::string out;
+  for (size_t i = 0; i + 1 < h.size(); i += 2) out.push_back((char)std::stoi(h.substr(i, 2), nullptr, 16));
+  return out;
+}
+static std::string ToHex(const std::string &s) {
+  static const char *d = "0123456789abcdef";
+  std::string out;
+  for (unsigned char c : s) {
+    out.push_back(d[c >> 4]);
+    out.push_back(d[c & 15]);
+  }
+  return out;
+}
+static int TagGoldenMode(const char *path) {
+  FILE *f = std::fopen(path, "r");
+  if (!f) return 2;
+  char sep = ',';
+  bool case_sensitive = false;
+  std::unique_ptr<Tag> index;
+  std::vector<char> line(1 << 16);
+  while (std::fgets(line.data(), (int)line.size(), f)) {
+    std::string l(line.data());
+    while (!l.empty() && (l.back() == '\n' || l.back() == '\r')) l.pop_back();
+    const size_t sp = l.find(' ');
+    const std::string cmd = l.substr(0, sp), rest = sp == std::string::npos ? "" : l.substr(sp + 1);
+    if (cmd == "sep") {
+      sep = FromHex(rest)[0];
+    } else if (cmd == "case") {
+      case_sensitive = rest == "1";
+    } else if (cmd == "doc") {
+      if (!index) index = std::make_unique<Tag>(sep, case_sensitive);
+      const size_t sp2 = rest.find(' ');
+      const std::string key = FromHex(rest.substr(0, sp2)), tags = sp2 == std::string::npos ? "" : FromHex(rest.substr(sp2 + 1));
+      if (!index->AddRecord(key, tags).ok()) return 3;
+    } else if (cmd == "query") {
+      if (!index) index = std::make_unique<Tag>(sep, case_sensitive);
+      const std::string q = FromHex(rest);
+      const size_t brace = q.find('{');
+      if (brace == std::string::npos) {
+        std::printf("ERR no tag clause\n");
+        continue;
+      }
+      auto tag_string = Tag::ParseTagString(std::string_view(q).substr(brace + 1));
+      if (!tag_string.ok()) {
+        std::printf("ERR %s\n", tag_string.status().message().c_str());
+        continue;
+      }
+      auto parsed = Tag::ParseSearchTags(*tag_string, '|');  // FilterParser::ParseQueryTags
+      if (!parsed.ok()) {
+        std::printf("ERR %s\n", parsed.status().message().c_str());
+        continue;
+      }
+      TagPredicate predicate(index.get(), *parsed);
+      // candidates from the index (Tag::Search), each confirmed by the predicate, de-duplicated: the pre-filter loop
+      std::set<std::string> keys;
+      for (const auto &k : index->Search(predicate, false))
+        if (predicate.Evaluate(k)) keys.insert(k);
+      std::printf("%zu", keys.size());
+      for (const auto &k : keys) std::printf(" %s", ToHex(k).c_str());
+      std::printf("\n");
+    }
+  }
+  std::fclose(f);
+  return 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc > 2 && std::string(argv[1]) == "--tag-golden") return TagGoldenMode(argv[2]);
   const bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";
   struct Case {
     const char *name;

@@ -36,3 +36,29 @@ def test_filter_bridge_device_sets_equal_per_key_evaluation(built):
     assert p.returncode == 0, p.stdout + p.stderr
     for case in ("DeviceBridgeFlat", "DeviceBridgeHnsw"):
         assert f"[  OK  ] {case}" in p.stdout, p.stdout + p.stderr
+
+
+def test_tag_queries_match_redisearch_recorded_answers(built, tmp_path):
+    """The reference's compatibility suite records RediSearch's answers for a TAG field full of special characters
+    ('}', '|', backslash, quote, tab, newline, accents, CJK, emoji) and 15 escaped queries (tests/golden/
+    redisearch_tag_special_chars.json, written by tests/golden/make_golden.py from integration/compatibility).  The host
+    mirror's query-side parsing (ParseTagString, ParseSearchTags, UnescapeTag) and TagPredicate must select exactly
+    those keys."""
+    import json
+    g = json.load(open(os.path.join(ROOT, "tests", "golden", "redisearch_tag_special_chars.json")))
+    hx = lambda s: s.encode("utf-8").hex()
+    lines = ["sep " + hx(g["separator"]), "case " + ("1" if g["case_sensitive"] else "0")]
+    lines += [f"doc {hx(k)} {hx(v)}" for k, v in g["docs"]]
+    lines += ["query " + hx(c["query"]) for c in g["cases"]]
+    path = tmp_path / "tag_golden.txt"
+    path.write_text("\n".join(lines) + "\n")
+    p = subprocess.run([FILTER_BIN, "--tag-golden", str(path)], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = p.stdout.strip().splitlines()
+    assert len(out) == len(g["cases"]) == 15
+    for c, line in zip(g["cases"], out):
+        parts = line.split()
+        assert parts[0] != "ERR", (c["query"], line)
+        keys = sorted(bytes.fromhex(h).decode() for h in parts[1:])
+        assert int(parts[0]) == c["count"], (c["query"], keys, c["keys"])
+        assert keys == c["keys"], c["query"]

@@ -125,6 +125,16 @@ std::string Tag::UnescapeTag(std::string_view tag) {  // tag.cc:131-143
   return result;
 }
 
+StatusOr<std::string> Tag::ParseTagString(std::string_view expression) {
+  for (size_t i = 0; i < expression.size(); ++i) {
+    if (expression[i] == '\\' && i + 1 < expression.size())
+      ++i;  // skip the escaped character
+    else if (expression[i] == '}')
+      return std::string(expression.substr(0, i));
+  }
+  return vks::InvalidArgumentError("Missing closing TAG bracket, '}'");
+}
+
 StatusOr<std::set<std::string>> Tag::ParseSearchTags(std::string_view data, char separator, size_t min_prefix_length) {
   std::set<std::string> parsed_tags;
   auto insert_tag = [&](std::string_view raw) -> Status {

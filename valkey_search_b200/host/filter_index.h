@@ -120,6 +120,9 @@ class Tag : public FilterIndexBase {
                                                          size_t min_prefix_length = 2);
   static std::set<std::string> ParseRecordTags(std::string_view data, char separator);
   static std::string UnescapeTag(std::string_view tag);
+  // FilterParser::ParseTagString (src/commands/filter_parser.cc:329-348): the text between "@field:{" and the first
+  // '}' that is not escaped by a backslash; `expression` starts right after the opening brace.
+  static StatusOr<std::string> ParseTagString(std::string_view expression);
 
   // Tag::Search (tag.cc:383-451) as a key list: the postings of the matching tags (exact or prefix); negated: every
   // posting that did not match plus the untracked keys.  A key appears once per matching posting, as in the
