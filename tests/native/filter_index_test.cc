@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <set>
 #include <string>
@@ -536,8 +537,128 @@ static int TagGoldenMode(const char *path) {
   return 0;
 }
 
+// --eval FILE: indexes, records, a universe of keys and predicate trees from a text file; prints, per tree, the keys
+// of the universe the tree accepts (hex, sorted) — Predicate::Evaluate per key, the reference's pre-filter loop.
+// tests/test_filter_oracle.py compares the output with oracle/filter_oracle.py on random inputs.  Host only.
+//   tagindex NAME SEPHEX 0|1      numindex NAME
+//   tadd|tmod NAME KEYHEX DATAHEX   trem NAME KEYHEX none|record     (same with n... for numeric)
+//   universe KEYHEX
+//   pred TOKENS...   prefix notation: AND n | OR n | NOT | TAG NAME TAGSTRINGHEX | NUM NAME start incl end incl
+struct EvalState {
+  std::map<std::string, std::unique_ptr<Tag>> tags;
+  std::map<std::string, std::unique_ptr<Numeric>> nums;
+  std::vector<std::string> universe;
+};
+static std::unique_ptr<Predicate> BuildPredicate(EvalState &st, std::vector<std::string> &tok, size_t &pos, std::string &err) {
+  if (pos >= tok.size()) {
+    err = "truncated predicate";
+    return nullptr;
+  }
+  const std::string t = tok[pos++];
+  if (t == "AND" || t == "OR") {
+    const int n = std::atoi(tok[pos++].c_str());
+    auto p = std::make_unique<ComposedPredicate>(t == "AND" ? PredicateType::kComposedAnd : PredicateType::kComposedOr);
+    for (int i = 0; i < n; i++) {
+      auto c = BuildPredicate(st, tok, pos, err);
+      if (!c) return nullptr;
+      p->AddChild(std::move(c));
+    }
+    return p;
+  }
+  if (t == "NOT") {
+    auto c = BuildPredicate(st, tok, pos, err);
+    if (!c) return nullptr;
+    return std::make_unique<NegatePredicate>(std::move(c));
+  }
+  if (t == "TAG") {
+    Tag *ix = st.tags.at(tok[pos++]).get();
+    auto parsed = Tag::ParseSearchTags(FromHex(tok[pos++]), '|');
+    if (!parsed.ok()) {
+      err = parsed.status().message();
+      return nullptr;
+    }
+    return std::make_unique<TagPredicate>(ix, *parsed);
+  }
+  if (t == "NUM") {
+    Numeric *ix = st.nums.at(tok[pos++]).get();
+    const double a = std::strtod(tok[pos++].c_str(), nullptr);
+    const bool ia = tok[pos++] == "1";
+    const double b = std::strtod(tok[pos++].c_str(), nullptr);
+    const bool ib = tok[pos++] == "1";
+    return std::make_unique<NumericPredicate>(ix, a, ia, b, ib);
+  }
+  err = "unknown token " + t;
+  return nullptr;
+}
+static int EvalMode(const char *path) {
+  FILE *f = std::fopen(path, "r");
+  if (!f) return 2;
+  EvalState st;
+  std::vector<char> line(1 << 20);
+  while (std::fgets(line.data(), (int)line.size(), f)) {
+    std::vector<std::string> tok;
+    {
+      std::string cur;
+      for (const char *p = line.data(); *p; p++) {
+        if (*p == ' ' || *p == '\n' || *p == '\r') {
+          if (!cur.empty()) tok.push_back(cur);
+          cur.clear();
+        } else {
+          cur.push_back(*p);
+        }
+      }
+      if (!cur.empty()) tok.push_back(cur);
+    }
+    if (tok.empty()) continue;
+    const std::string &cmd = tok[0];
+    auto arg = [&](size_t i) { return i < tok.size() ? tok[i] : std::string(); };
+    auto report = [&](const vks::StatusOr<RecordResult> &r) {
+      if (!r.ok()) std::printf("rec ERR %s\n", r.status().message().c_str());
+      else std::printf("rec %s\n", *r == RecordResult::kAdded ? "added" : *r == RecordResult::kMissing ? "missing" : "invalid");
+    };
+    if (cmd == "tagindex") {
+      st.tags[arg(1)] = std::make_unique<Tag>(FromHex(arg(2))[0], arg(3) == "1");
+    } else if (cmd == "numindex") {
+      st.nums[arg(1)] = std::make_unique<Numeric>();
+    } else if (cmd == "tadd") {
+      report(st.tags.at(arg(1))->AddRecord(FromHex(arg(2)), FromHex(arg(3))));
+    } else if (cmd == "tmod") {
+      report(st.tags.at(arg(1))->ModifyRecord(FromHex(arg(2)), FromHex(arg(3))));
+    } else if (cmd == "trem") {
+      auto r = st.tags.at(arg(1))->RemoveRecord(FromHex(arg(2)), arg(3) == "record" ? DeletionType::kRecord : DeletionType::kNone);
+      std::printf("rem %d\n", r.ok() && *r ? 1 : 0);
+    } else if (cmd == "nadd") {
+      report(st.nums.at(arg(1))->AddRecord(FromHex(arg(2)), FromHex(arg(3))));
+    } else if (cmd == "nmod") {
+      report(st.nums.at(arg(1))->ModifyRecord(FromHex(arg(2)), FromHex(arg(3))));
+    } else if (cmd == "nrem") {
+      auto r = st.nums.at(arg(1))->RemoveRecord(FromHex(arg(2)), arg(3) == "record" ? DeletionType::kRecord : DeletionType::kNone);
+      std::printf("rem %d\n", r.ok() && *r ? 1 : 0);
+    } else if (cmd == "universe") {
+      st.universe.push_back(FromHex(arg(1)));
+    } else if (cmd == "pred") {
+      size_t pos = 1;
+      std::string err;
+      auto p = BuildPredicate(st, tok, pos, err);
+      if (!p) {
+        std::printf("pred ERR %s\n", err.c_str());
+        continue;
+      }
+      std::set<std::string> keys;
+      for (const auto &k : st.universe)
+        if (p->Evaluate(k)) keys.insert(k);
+      std::printf("pred %zu", keys.size());
+      for (const auto &k : keys) std::printf(" %s", ToHex(k).c_str());
+      std::printf("\n");
+    }
+  }
+  std::fclose(f);
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc > 2 && std::string(argv[1]) == "--tag-golden") return TagGoldenMode(argv[2]);
+  if (argc > 2 && std::string(argv[1]) == "--eval") return EvalMode(argv[2]);
   const bool host_only = argc > 1 && std::string(argv[1]) == "--host-only";
   struct Case {
     const char *name;
