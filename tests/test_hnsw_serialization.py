@@ -480,3 +480,70 @@ def test_hnsw_header_wire_format_matches_protobuf(built):
         assert got == want, (line, want.hex())
         seen += 1
     assert seen == 5
+
+
+@pytest.mark.parametrize("seed", [2026, 7, 99])
+def test_random_corruptions_get_the_reference_verdict(built, tmp_path, seed):
+    """Differential fuzz of the load validation: 3 x 300 random corruptions of the multi-layer golden (bit flips, byte
+    pokes, truncated or duplicated chunks, header field changes).  Our loader never crashes, and accepts or rejects
+    exactly when the reference's own LoadIndex (validation on) does; when both reject, the reference's reason is the
+    one we give."""
+    if O.ref() is None:
+        pytest.skip("needs oracle/_ref")
+    import random
+    rng = random.Random(seed)
+    base = multilayer_golden()
+    agree_ok = agree_reject = 0
+    for it in range(300):
+        g = list(base)
+        kind = rng.random()
+        if kind < 0.45:  # flip a bit in the graph part of a chunk (links, counts, sizes) or anywhere
+            i = rng.randrange(1, len(g))
+            c = bytearray(g[i])
+            if not c:
+                continue
+            limit = LINKS0 if (i <= 8 and rng.random() < 0.7) else len(c)
+            j = rng.randrange(min(limit, len(c)))
+            c[j] ^= 1 << rng.randrange(8)
+            g[i] = bytes(c)
+        elif kind < 0.6:  # overwrite a 16/32-bit field with a boundary value
+            i = rng.randrange(1, len(g))
+            c = bytearray(g[i])
+            if len(c) < 4:
+                continue
+            off = rng.randrange(0, min(len(c), LINKS0) - 3, 4) if len(c) >= 8 else 0
+            struct.pack_into("<I", c, off, rng.choice([0, 1, 7, 8, 9, 16, 17, 32, 33, 0xFFFF, 0x10000, 0xFFFFFFFF]))
+            g[i] = bytes(c)
+        elif kind < 0.75:  # truncate, extend, drop or duplicate a chunk
+            i = rng.randrange(1, len(g))
+            how = rng.randrange(4)
+            if how == 0:
+                g[i] = g[i][: rng.randrange(len(g[i]) + 1)]
+            elif how == 1:
+                g[i] = g[i] + b"\0" * rng.randrange(1, 9)
+            elif how == 2:
+                del g[i]
+            else:
+                g.insert(i, g[i])
+        else:  # header fields
+            name = rng.choice(["offset_level_0", "max_elements", "curr_element_count", "serialize_size", "max_level",
+                               "enterpoint_node", "max_m", "max_m_0", "m", "mult", "ef_construction"])
+            if name == "mult":
+                value = rng.choice([0.0, 0.5, -1.0, 1 / np.log(M), 1 / np.log(M) * (1 + 1e-5), 1e300])
+            elif name == "max_level":
+                value = rng.choice([-1, 0, 1, 2, 3, 8, 9, 1000])
+            else:
+                value = rng.choice([0, 1, 2, 7, 8, 9, 15, 16, 17, 31, 32, 33, ELEM, ELEM + 1, 1 << 20])
+            g = with_header(g, **{name: value})
+        h, ref_err = O.ref_hnsw_load(g, D, O.L2, CAP, M, validate=True)
+        fields, err, _ = ours_load(g, tmp_path, validate=True)
+        if ref_err is None:
+            assert err is None, (it, kind, err)
+            assert fields[0] == h.count()
+            agree_ok += 1
+        else:
+            assert fields is None and err, (it, kind, ref_err)
+            if "load validation failed" in ref_err:  # same rule, same words
+                assert err == ref_err, (it, err, ref_err)
+            agree_reject += 1
+    assert agree_ok >= 20 and agree_reject >= 60, (agree_ok, agree_reject)
