@@ -300,7 +300,9 @@ StatusOr<HnswLoadResult> LoadHnswImage(InputStream &input, size_t dim, size_t ma
       if (link_list_size == 0) continue;
       hard(link_list_size % stride == 0, "upper-level link-list size is not a multiple of the stride");
       const uint64_t level = link_list_size / stride;
-      hard(level <= (uint64_t)header.max_level, "element level exceeds max_level");
+      // the reference holds the level in an `int` (hnswalg.h:1066): a size with garbage in its upper bytes wraps
+      // here and is caught by the chunk-size check below instead — same verdict, and the same words
+      hard((int)level <= header.max_level, "element level exceeds max_level");
       auto link_list_chunk = input.LoadChunk();
       if (!link_list_chunk.ok()) return link_list_chunk.status();
       const std::string &c = **link_list_chunk;
