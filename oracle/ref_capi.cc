@@ -58,6 +58,7 @@ struct VecStore {
 };
 
 struct Flat {
+  virtual ~Flat() = default;  // vkref_flat_load hands out a derived object
   std::unique_ptr<hnswlib::SpaceInterface<float>> space;
   std::unique_ptr<hnswlib::BruteforceSearch<float>> algo;
   VecStore store;
@@ -307,6 +308,78 @@ struct LoadedHnsw : public Hnsw {
   StoreTracker tracker;
 };
 }  // namespace
+
+// ---------------------------------------------------------------- FLAT save / load (bruteforce.h:147-207)
+static uint64_t PackChunks(const ChunkBuf &buf, uint8_t *out, uint64_t cap) {
+  uint64_t need = 8;
+  for (auto &c : buf.chunks) need += 8 + c.size();
+  if (out && cap >= need) {
+    uint64_t n = buf.chunks.size();
+    std::memcpy(out, &n, 8);
+    uint8_t *p = out + 8;
+    for (auto &c : buf.chunks) {
+      uint64_t len = c.size();
+      std::memcpy(p, &len, 8);
+      std::memcpy(p + 8, c.data(), len);
+      p += 8 + len;
+    }
+  }
+  return need;
+}
+static bool UnpackChunks(const uint8_t *buf, uint64_t len, ChunkBuf *in) {
+  if (len < 8) return false;
+  uint64_t n;
+  std::memcpy(&n, buf, 8);
+  uint64_t pos = 8;
+  for (uint64_t i = 0; i < n; i++) {
+    if (pos + 8 > len) return false;
+    uint64_t l;
+    std::memcpy(&l, buf + pos, 8);
+    pos += 8;
+    if (pos + l > len) return false;
+    in->chunks.emplace_back(reinterpret_cast<const char *>(buf + pos), l);
+    pos += l;
+  }
+  return true;
+}
+namespace {
+struct LoadedFlat : public Flat {
+  StoreTracker tracker;
+};
+}  // namespace
+
+uint64_t vkref_flat_save(void *h, uint8_t *out, uint64_t cap) {
+  ChunkBuf buf;
+  if (!static_cast<Flat *>(h)->algo->SaveIndex(buf).ok()) return 0;
+  return PackChunks(buf, out, cap);
+}
+
+// VectorFlat::LoadFromRDB (vector_flat.cc:99-125): empty BruteforceSearch + LoadIndex; exceptions => error text
+void *vkref_flat_load(const uint8_t *buf, uint64_t len, size_t dim, int metric, char *err, size_t errcap) {
+  auto fail = [&](const std::string &m) -> void * {
+    if (err && errcap) {
+      std::strncpy(err, m.c_str(), errcap - 1);
+      err[errcap - 1] = 0;
+    }
+    return nullptr;
+  };
+  ChunkBuf in;
+  if (!UnpackChunks(buf, len, &in)) return fail("short buffer");
+  auto f = std::make_unique<LoadedFlat>();
+  f->space = MakeSpace(dim, metric);
+  f->store.dim = dim;
+  f->block_size = 1024;
+  f->tracker.store = &f->store;
+  try {
+    f->algo = std::make_unique<hnswlib::BruteforceSearch<float>>(f->space.get());
+    auto st = f->algo->LoadIndex(in, f->space.get(), &f->tracker);
+    if (!st.ok()) return fail(std::string(st.message()));
+  } catch (const std::exception &e) {
+    return fail(std::string("HNSWLib error: ") + e.what());
+  }
+  return static_cast<Flat *>(f.release());
+}
+uint64_t vkref_flat_capacity(void *h) { return static_cast<Flat *>(h)->algo->data_->getCapacity(); }
 
 // forced level (> 0) as in the reference's golden builder (testing/vector_test.cc:866-893); level <= 0 => seeded RNG
 int vkref_hnsw_add_level(void *h, const float *v, uint64_t label, int level) {

@@ -569,6 +569,44 @@ static bool WriteStreamFile(const char *path, const MemoryStream &s) {
   }
   return std::fclose(f) == 0;
 }
+// --flat-resave IN DIM [OUT]: LoadFlatHeader + LoadFlatElements on the stream; prints "OK count capacity" or
+// "ERR message"; with OUT, SaveFlatImage of what was loaded goes there.  Host only.
+static int FlatResaveMode(int argc, char **argv) {
+  if (argc < 4) return 2;
+  MemoryStream in;
+  if (!ReadStreamFile(argv[2], in)) return 2;
+  const size_t dim = std::strtoull(argv[3], nullptr, 10);
+  auto header = LoadFlatHeader(in, dim);
+  if (!header.ok()) {
+    std::printf("ERR %s\n", header.status().message().c_str());
+    return 0;
+  }
+  std::vector<float> rows;
+  std::vector<uint64_t> labels;
+  const vks::Status s = LoadFlatElements(in, *header, dim, [&](const uint64_t *l, const float *r, uint64_t n) {
+    labels.insert(labels.end(), l, l + n);
+    rows.insert(rows.end(), r, r + n * dim);
+    return vks::OkStatus();
+  });
+  if (!s.ok()) {
+    std::printf("ERR %s\n", s.message().c_str());
+    return 0;
+  }
+  std::printf("OK %llu %llu\n", (unsigned long long)labels.size(), (unsigned long long)header->max_elements);
+  if (argc > 4) {
+    MemoryStream out;
+    const vks::Status w = SaveFlatImage(labels.size(), header->max_elements, dim,
+                                        [&](uint64_t first, uint64_t n, float *r, uint64_t *l) {
+                                          std::memcpy(r, rows.data() + first * dim, n * dim * sizeof(float));
+                                          std::memcpy(l, labels.data() + first, n * sizeof(uint64_t));
+                                          return vks::OkStatus();
+                                        },
+                                        out);
+    if (!w.ok() || !WriteStreamFile(argv[4], out)) return 3;
+  }
+  return 0;
+}
+
 // --hnsw-load IN DIM CAP M VALIDATE [OUT]: LoadHnswImage on the stream; prints "OK n max_level enterpoint
 // max_elements duplicates deleted" or "ERR message"; with OUT, SaveHnswImage of what was loaded goes there.
 static int HnswLoadMode(int argc, char **argv) {
@@ -942,6 +980,7 @@ static void HostOnly(bool have_gpu) {
 int main(int argc, char **argv) {
   if (argc > 1 && std::string(argv[1]) == "--wire") return PrintWire();
   if (argc > 1 && std::string(argv[1]) == "--hnsw-load") return HnswLoadMode(argc, argv);
+  if (argc > 1 && std::string(argv[1]) == "--flat-resave") return FlatResaveMode(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--hnsw-gpu-load") return HnswGpuLoadMode(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--hnsw-gpu-build") return HnswGpuBuildMode(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--hnsw-perf") return HnswPerfMode(argc, argv);

@@ -118,6 +118,9 @@ def ref():
         _sig(lib, "vkref_hnsw_deleted", C.c_int, [C.c_void_p, C.c_uint32])
         _sig(lib, "vkref_hnsw_links", C.c_uint32, [C.c_void_p, C.c_uint32, C.c_int, _u32p])
         _sig(lib, "vkref_hnsw_vector", C.POINTER(C.c_float), [C.c_void_p, C.c_uint32])
+        _sig(lib, "vkref_flat_save", C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64])
+        _sig(lib, "vkref_flat_load", C.c_void_p, [C.c_char_p, C.c_uint64, C.c_size_t, C.c_int, C.c_char_p, C.c_size_t])
+        _sig(lib, "vkref_flat_capacity", C.c_uint64, [C.c_void_p])
         _sig(lib, "vkref_hnsw_add_level", C.c_int, [C.c_void_p, _f32p, C.c_uint64, C.c_int])
         _sig(lib, "vkref_hnsw_save", C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64])
         _sig(lib, "vkref_hnsw_load", C.c_void_p,
@@ -390,6 +393,29 @@ def unpack_chunks(buf):
         chunks.append(bytes(buf[pos + 8: pos + 8 + ln]))
         pos += 8 + ln
     return chunks
+
+
+def ref_flat_save(f):
+    """The reference's BruteforceSearch::SaveIndex (bruteforce.h:147-171) -> list of chunks."""
+    need = f.lib.vkref_flat_save(f.h, None, 0)
+    assert need >= 8
+    buf = C.create_string_buffer(need)
+    assert f.lib.vkref_flat_save(f.h, buf, need) == need
+    return unpack_chunks(buf.raw)
+
+
+def ref_flat_load(chunks, dim, metric):
+    """The reference's LoadFromRDB path for FLAT (vector_flat.cc:99-125 -> bruteforce.h:173-207).  Returns
+    (RefFlat, None) or (None, error message)."""
+    lib = ref()
+    data = pack_chunks(chunks)
+    err = C.create_string_buffer(512)
+    hnd = lib.vkref_flat_load(data, len(data), dim, metric, err, 512)
+    if not hnd:
+        return None, err.value.decode()
+    obj = RefFlat.__new__(RefFlat)
+    obj.lib, obj.dim, obj.h = lib, dim, hnd
+    return obj, None
 
 
 def ref_hnsw_add_level(h, v, label, level):

@@ -542,66 +542,88 @@ Status VectorBase::LoadTrackedKeys(InputStream &iter) {
   return vks::OkStatus();
 }
 
-template <typename T>
-Status VectorFlat<T>::SaveIndex(OutputStream &chunked_out) const {
-  const vkgpu_stats st = Stats();
-  const size_t vector_size = (size_t)dimensions_ * sizeof(T);
+Status SaveFlatImage(uint64_t count, uint64_t capacity, size_t dim, const FlatBlockFetcher &fetch, OutputStream &output) {
+  const size_t vector_size = dim * sizeof(float);
   BruteForceIndexHeader header;
-  header.max_elements = st.capacity;
+  header.max_elements = capacity;
   header.size_per_element = vector_size + sizeof(uint64_t);
-  header.curr_element_count = st.count;
+  header.curr_element_count = count;
   const std::string serialized = header.SerializeAsString();
-  VKS_RETURN_IF_ERROR(chunked_out.SaveChunk(serialized.data(), serialized.size()));
-  constexpr uint64_t kBlock = 4096;  // rows fetched from HBM per call; the chunks stay one element each
-  std::vector<float> rows(kBlock * dimensions_);
+  VKS_RETURN_IF_ERROR(output.SaveChunk(serialized.data(), serialized.size()));
+  constexpr uint64_t kBlock = 4096;  // rows fetched per call; the chunks stay one element each
+  std::vector<float> rows(kBlock * dim);
   std::vector<uint64_t> labels(kBlock);
   std::vector<char> buf(header.size_per_element);
-  for (uint64_t first = 0; first < st.count; first += kBlock) {
-    const uint64_t n = std::min<uint64_t>(kBlock, st.count - first);
-    VKS_RETURN_IF_ERROR(FromRc(vkgpu_flat_export(gpu_, first, n, rows.data(), labels.data())));
+  for (uint64_t first = 0; first < count; first += kBlock) {
+    const uint64_t n = std::min<uint64_t>(kBlock, count - first);
+    VKS_RETURN_IF_ERROR(fetch(first, n, rows.data(), labels.data()));
     for (uint64_t i = 0; i < n; i++) {
-      std::memcpy(buf.data(), rows.data() + i * dimensions_, vector_size);
+      std::memcpy(buf.data(), rows.data() + i * dim, vector_size);
       std::memcpy(buf.data() + vector_size, &labels[i], sizeof(uint64_t));
-      VKS_RETURN_IF_ERROR(chunked_out.SaveChunk(buf.data(), buf.size()));
+      VKS_RETURN_IF_ERROR(output.SaveChunk(buf.data(), buf.size()));
     }
   }
   return vks::OkStatus();
 }
 
-template <typename T>
-StatusOr<std::shared_ptr<VectorFlat<T>>> VectorFlat<T>::LoadFromStream(const VectorIndexProto &p, InputStream &input) {
+StatusOr<BruteForceIndexHeader> LoadFlatHeader(InputStream &input, size_t dim) {
   auto serialized_header = input.LoadChunk();
   if (!serialized_header.ok()) return serialized_header.status();
   BruteForceIndexHeader header;
   if (!header.ParseFromString(**serialized_header)) return vks::InternalError("Could not deserialize bruteforce header");
-  const size_t vector_size = (size_t)p.dimension_count * sizeof(T);
-  if (header.size_per_element != vector_size + sizeof(uint64_t))
+  if (header.size_per_element != dim * sizeof(float) + sizeof(uint64_t))
     return vks::InternalError("Persisted size_per_element does not match expectation.");  // bruteforce.h:190-193
-  VectorIndexProto q = p;
-  q.initial_cap = std::max<uint64_t>(header.max_elements, header.curr_element_count);
-  auto created = Create(q);
-  if (!created.ok()) return created.status();
-  auto index = *created;
+  return header;
+}
+
+Status LoadFlatElements(InputStream &input, const BruteForceIndexHeader &header, size_t dim, const FlatBlockSink &sink) {
+  const size_t vector_size = dim * sizeof(float);
   constexpr uint64_t kBlock = 4096;
   std::vector<float> rows;
   std::vector<uint64_t> labels;
   for (uint64_t i = 0; i < header.curr_element_count; i++) {
     auto chunk = input.LoadChunk();
     if (!chunk.ok()) return chunk.status();
+    // the reference reads vector_size + 8 bytes of whatever arrives; a short chunk would be read past its end, so it
+    // is refused here
     if ((*chunk)->size() != header.size_per_element) return vks::InternalError("bruteforce element chunk has the wrong size");
     const size_t at = rows.size();
-    rows.resize(at + p.dimension_count);
+    rows.resize(at + dim);
     std::memcpy(rows.data() + at, (*chunk)->data(), vector_size);
     uint64_t id;
     std::memcpy(&id, (*chunk)->data() + vector_size, sizeof(id));
     labels.push_back(id);
     if (labels.size() == kBlock || i + 1 == header.curr_element_count) {  // slot i = i-th saved element
-      const Status s = index->FromRc(vkgpu_add_batch(index->gpu_, labels.data(), rows.data(), labels.size()));
-      if (!s.ok()) return s;
+      VKS_RETURN_IF_ERROR(sink(labels.data(), rows.data(), labels.size()));
       rows.clear();
       labels.clear();
     }
   }
+  return vks::OkStatus();
+}
+
+template <typename T>
+Status VectorFlat<T>::SaveIndex(OutputStream &chunked_out) const {
+  const vkgpu_stats st = Stats();
+  const FlatBlockFetcher fetch = [&](uint64_t first, uint64_t n, float *rows, uint64_t *labels) {
+    return FromRc(vkgpu_flat_export(gpu_, first, n, rows, labels));
+  };
+  return SaveFlatImage(st.count, st.capacity, (size_t)dimensions_, fetch, chunked_out);
+}
+
+template <typename T>
+StatusOr<std::shared_ptr<VectorFlat<T>>> VectorFlat<T>::LoadFromStream(const VectorIndexProto &p, InputStream &input) {
+  auto header = LoadFlatHeader(input, p.dimension_count);
+  if (!header.ok()) return header.status();
+  VectorIndexProto q = p;
+  q.initial_cap = std::max<uint64_t>(header->max_elements, header->curr_element_count);
+  auto created = Create(q);
+  if (!created.ok()) return created.status();
+  auto index = *created;
+  const FlatBlockSink sink = [&](const uint64_t *labels, const float *rows, uint64_t n) {
+    return index->FromRc(vkgpu_add_batch(index->gpu_, labels, rows, n));
+  };
+  VKS_RETURN_IF_ERROR(LoadFlatElements(input, *header, p.dimension_count, sink));
   return index;
 }
 

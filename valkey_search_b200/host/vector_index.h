@@ -88,6 +88,17 @@ struct TrackedKeyMetadataPb {
   bool ParseFromString(std::string_view s);
 };
 
+// BruteforceSearch::SaveIndex / LoadIndex (third_party/hnswlib/bruteforce.h:147-207) as pure stream <-> rows code, so
+// that the byte format is checked on CPU against the reference's own output (tests/test_flat_serialization.py).
+//   save: header chunk, then one chunk per element in slot order = dim * 4 vector bytes | 8-byte label
+//   load: the header's size_per_element must equal dim * 4 + 8 (else "Persisted size_per_element does not match
+//         expectation."); elements are handed to the sink in blocks, in stream order (= slot order)
+using FlatBlockFetcher = std::function<Status(uint64_t first, uint64_t count, float *rows, uint64_t *labels)>;
+using FlatBlockSink = std::function<Status(const uint64_t *labels, const float *rows, uint64_t count)>;
+Status SaveFlatImage(uint64_t count, uint64_t capacity, size_t dim, const FlatBlockFetcher &fetch, OutputStream &output);
+StatusOr<BruteForceIndexHeader> LoadFlatHeader(InputStream &input, size_t dim);
+Status LoadFlatElements(InputStream &input, const BruteForceIndexHeader &header, size_t dim, const FlatBlockSink &sink);
+
 using CancelToken = uint64_t;                     // deadline in CLOCK_MONOTONIC ns; 0 = CancelNever()
 inline CancelToken CancelNever() { return 0; }
 using KeyFilter = std::function<bool(const std::string &key)>;
