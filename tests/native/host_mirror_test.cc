@@ -569,6 +569,36 @@ static bool WriteStreamFile(const char *path, const MemoryStream &s) {
   }
   return std::fclose(f) == 0;
 }
+static bool ReadFloats(const char *path, std::vector<float> &out) {
+  FILE *f = std::fopen(path, "rb");
+  if (!f) return false;
+  std::fseek(f, 0, SEEK_END);
+  const long bytes = std::ftell(f);
+  std::fseek(f, 0, SEEK_SET);
+  out.resize((size_t)bytes / 4);
+  const bool ok = std::fread(out.data(), 4, out.size(), f) == out.size();
+  std::fclose(f);
+  return ok;
+}
+// --normalize IN DIM OUT: NormalizeEmbedding on every row of a raw float32 file; OUT = the normalised rows followed by
+// one magnitude per row.  Host only (tests/test_host_cpp.py compares the bits with the C oracle and the Python mirror).
+static int NormalizeMode(int argc, char **argv) {
+  if (argc < 5) return 2;
+  std::vector<float> X;
+  if (!ReadFloats(argv[2], X)) return 2;
+  const size_t dim = std::strtoull(argv[3], nullptr, 10), n = X.size() / dim;
+  std::vector<float> out(n * dim), mags(n);
+  for (size_t i = 0; i < n; i++) {
+    auto r = NormalizeEmbedding(std::string_view(reinterpret_cast<const char *>(&X[i * dim]), dim * 4), sizeof(float), &mags[i]);
+    std::memcpy(&out[i * dim], r.data(), dim * 4);
+  }
+  FILE *f = std::fopen(argv[4], "wb");
+  if (!f) return 3;
+  std::fwrite(out.data(), 4, out.size(), f);
+  std::fwrite(mags.data(), 4, mags.size(), f);
+  return std::fclose(f) == 0 ? 0 : 3;
+}
+
 // --flat-resave IN DIM [OUT]: LoadFlatHeader + LoadFlatElements on the stream; prints "OK count capacity" or
 // "ERR message"; with OUT, SaveFlatImage of what was loaded goes there.  Host only.
 static int FlatResaveMode(int argc, char **argv) {
@@ -641,17 +671,6 @@ static int HnswLoadMode(int argc, char **argv) {
 }
 
 // ---- GPU modes for tests/test_hnsw_interchange_gpu.py (files cross between the reference and the GPU index)
-static bool ReadFloats(const char *path, std::vector<float> &out) {
-  FILE *f = std::fopen(path, "rb");
-  if (!f) return false;
-  std::fseek(f, 0, SEEK_END);
-  const long bytes = std::ftell(f);
-  std::fseek(f, 0, SEEK_SET);
-  out.resize((size_t)bytes / 4);
-  const bool ok = std::fread(out.data(), 4, out.size(), f) == out.size();
-  std::fclose(f);
-  return ok;
-}
 // keys of a loaded stream: one TrackedKeyMetadata chunk per level-0 record, key = decimal label
 static MemoryStream KeysOf(const MemoryStream &data, size_t dim, size_t m) {
   MemoryStream keys;
@@ -981,6 +1000,7 @@ int main(int argc, char **argv) {
   if (argc > 1 && std::string(argv[1]) == "--wire") return PrintWire();
   if (argc > 1 && std::string(argv[1]) == "--hnsw-load") return HnswLoadMode(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--flat-resave") return FlatResaveMode(argc, argv);
+  if (argc > 1 && std::string(argv[1]) == "--normalize") return NormalizeMode(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--hnsw-gpu-load") return HnswGpuLoadMode(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--hnsw-gpu-build") return HnswGpuBuildMode(argc, argv);
   if (argc > 1 && std::string(argv[1]) == "--hnsw-perf") return HnswPerfMode(argc, argv);

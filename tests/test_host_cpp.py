@@ -90,3 +90,35 @@ def test_cpp_host_mirror_wire_format_matches_protobuf(built):
         seen += 1
     assert seen == 10
 
+
+
+def test_normalisation_bits_agree_across_cpp_mirror_c_oracle_and_python_mirror(built, tmp_path):
+    """CopyAndNormalizeEmbedding (src/indexes/vector_base.cc:112-138) exists three times here: the C++ host mirror, the
+    C oracle and the Python mirror.  COSINE results depend on its exact fp32 arithmetic (sequential sum of squares,
+    sqrt, one reciprocal, one multiply per element), so the three must agree to the bit on random and awkward rows."""
+    import numpy as np
+    import oracle_lib as O
+    from valkey_search_b200 import index as I
+    rng = np.random.default_rng(17)
+    dim = 37
+    X = rng.standard_normal((300, dim)).astype(np.float32)
+    X[0] = 0.0                       # the zero vector keeps scale 1
+    X[1] = 1e-30                     # squares underflow to denormals / zero
+    X[2] = 3e18                      # squares near the top of the fp32 range
+    X[3, :] = 0.0
+    X[3, 5] = -7.25
+    X[4] *= np.float32(1e-20)
+    (tmp_path / "x.bin").write_bytes(X.tobytes())
+    p = _run(["--normalize", str(tmp_path / "x.bin"), str(dim), str(tmp_path / "y.bin")])
+    assert p.returncode == 0, p.stdout + p.stderr
+    out = np.fromfile(tmp_path / "y.bin", np.float32)
+    Y, mags = out[: X.size].reshape(X.shape), out[X.size:]
+    port = O.port()
+    for i in range(X.shape[0]):
+        want = np.empty(dim, np.float32)
+        m = port.vko_normalize(want, np.ascontiguousarray(X[i]), dim)
+        assert np.array_equal(Y[i].view(np.uint32), want.view(np.uint32)), i
+        assert np.float32(m).view(np.uint32) == mags[i].view(np.uint32), i
+        v, pm = I.normalize_embedding(X[i])
+        assert np.array_equal(np.asarray(v, np.float32).view(np.uint32), want.view(np.uint32)), i
+        assert np.float32(pm).view(np.uint32) == np.float32(m).view(np.uint32), i
