@@ -439,6 +439,106 @@ static void DeviceBridgeOn(Index *vectors, int dim, int n, bool hnsw) {
   check_all("after mutations");
 }
 
+// SearchTest (testing/search_test.cc:751-895; the corpus of CreateIndexSchemaWithMultipleAttributes :466-540): 10 000
+// vectors v[i][j] = 10 (i + j) / 10100 in 100 dimensions (lower index = closer to the zero query), numeric = i, tags
+// "LT10000" (+ ",LT5" for i < 5, + ",LT3" for i < 3); zero query, k = 5, ef = 30; the reference's 15 filters and
+// the key SETS it expects, for both index types.  The filters are built as predicate trees (the filter parser is
+// command surface and stays in the module).
+template <typename Index>
+static void ReferenceSearchTestOn(Index *vectors) {
+  constexpr int kDim = 100, kRecords = 10000;
+  Tag tag(',', false, vectors);
+  Numeric numeric(vectors);
+  DeviceFilterEvaluator evaluator(vectors);
+  std::vector<float> v(kDim);
+  for (int i = 0; i < kRecords; i++) {
+    for (int j = 0; j < kDim; j++) v[j] = 10.0f * ((float)(i + j) / (float)(kRecords + kDim));  // testing/common.cc:42-53
+    const std::string key = std::to_string(i);
+    EXPECT_OK(vectors->AddRecord(key, Bytes(v)));
+    EXPECT_OK(numeric.AddRecord(key, std::to_string(i)));
+    std::string tags = "LT10000";
+    if (i < 5) tags += ",LT5";
+    if (i < 3) tags += ",LT3";
+    EXPECT_OK(tag.AddRecord(key, tags));
+  }
+  auto T = [&](const char *q) { return std::make_unique<TagPredicate>(&tag, *Tag::ParseSearchTags(q, '|')); };
+  auto N = [&](double a, double b) { return std::make_unique<NumericPredicate>(&numeric, a, true, b, true); };
+  auto Not = [](std::unique_ptr<Predicate> p) { return std::make_unique<NegatePredicate>(std::move(p)); };
+  auto Two = [](PredicateType t, std::unique_ptr<Predicate> a, std::unique_ptr<Predicate> b) {
+    auto p = std::make_unique<ComposedPredicate>(t);
+    p->AddChild(std::move(a));
+    p->AddChild(std::move(b));
+    return p;
+  };
+  struct Case {
+    const char *name;
+    std::unique_ptr<Predicate> filter;  // null: no filter
+    std::set<std::string> expected;
+  };
+  std::vector<Case> cases;
+  const std::set<std::string> first5 = {"0", "1", "2", "3", "4"};
+  cases.push_back({"no_filter", nullptr, first5});
+  cases.push_back({"prefix_match_filter", T("lT*"), first5});
+  cases.push_back({"numeric_filter_all_candidates_eligible", N(0, 10000), first5});
+  cases.push_back({"numeric_filter_k_eligible_candidates", N(0, 4), first5});
+  cases.push_back({"numeric_filter_less_than_k_eligible_candidates", N(0, 2), {"0", "1", "2"}});
+  cases.push_back({"numeric_filter_no_eligible_candidates", N(10000, 20000), {}});
+  cases.push_back({"tag_filter_all_candidates_eligible", T("LT10000"), first5});
+  cases.push_back({"tag_filter_k_eligible_candidates", T("LT5"), first5});
+  cases.push_back({"tag_filter_less_than_k_eligible_candidates", T("LT3"), {"0", "1", "2"}});
+  cases.push_back({"tag_filter_no_eligible_candidates", T("random"), {}});
+  cases.push_back({"or_filter", Two(PredicateType::kComposedOr, N(4, 100), T("LT5")), first5});
+  cases.push_back({"and_filter", Two(PredicateType::kComposedAnd, N(4, 100), T("LT5")), {"4"}});
+  cases.push_back({"numeric_negate_filter", Not(N(0, 100)), {"101", "102", "103", "104", "105"}});
+  cases.push_back({"tag_negate_filter", Not(T("LT5")), {"5", "6", "7", "8", "9"}});
+  cases.push_back({"composite_filter_with_negate", Two(PredicateType::kComposedAnd, Not(N(4, 100)), T("LT5")), {"0", "1", "2", "3"}});
+  const std::vector<float> zero(kDim, 0.0f);
+  for (const auto &c : cases) {
+    StatusOr<std::vector<Neighbor>> r = std::vector<Neighbor>();
+    if (c.filter) {
+      r = evaluator.Search(Bytes(zero), 5, *c.filter, 30);
+    } else {
+      if constexpr (std::is_same_v<Index, VectorHNSW<float>>)
+        r = vectors->Search(Bytes(zero), 5, CancelNever(), nullptr, 30);
+      else
+        r = vectors->Search(Bytes(zero), 5, CancelNever());
+    }
+    EXPECT_OK(r);
+    if (!r.ok()) continue;
+    std::set<std::string> got;
+    for (const auto &nb : *r) got.insert(nb.external_id);
+    EXPECT_EQ(r->size(), c.expected.size());
+    EXPECT_EQ(got, c.expected);
+    if (got != c.expected) {
+      std::string s;
+      for (const auto &k : got) s += k + " ";
+      std::fprintf(stderr, "  %s: got { %s}\n", c.name, s.c_str());
+    }
+  }
+}
+static void ReferenceSearchTestFlat() {
+  VectorIndexProto p;
+  p.dimension_count = 100;
+  p.distance_metric = DistanceMetric::kL2;
+  p.initial_cap = 1000;
+  p.flat_algorithm.block_size = 250;
+  auto flat = VectorFlat<float>::Create(p);
+  EXPECT_OK(flat);
+  if (flat.ok()) ReferenceSearchTestOn(flat->get());
+}
+static void ReferenceSearchTestHnsw() {
+  VectorIndexProto p;
+  p.dimension_count = 100;
+  p.distance_metric = DistanceMetric::kL2;
+  p.initial_cap = 1000;
+  p.hnsw_algorithm.m = 10;
+  p.hnsw_algorithm.ef_construction = 300;
+  p.hnsw_algorithm.ef_runtime = 30;
+  auto hnsw = VectorHNSW<float>::Create(p);
+  EXPECT_OK(hnsw);
+  if (hnsw.ok()) ReferenceSearchTestOn(hnsw->get());
+}
+
 static void DeviceBridgeFlat() {
   {
     VectorIndexProto p;
@@ -668,10 +768,14 @@ int main(int argc, char **argv) {
                {"NumericIndex", NumericIndexCases, false},
                {"Predicates", PredicateCases, false},
                {"DeviceBridgeFlat", DeviceBridgeFlat, true},
-               {"DeviceBridgeHnsw", DeviceBridgeHnsw, true}};
+               {"DeviceBridgeHnsw", DeviceBridgeHnsw, true},
+               {"ReferenceSearchTestFlat", ReferenceSearchTestFlat, true},
+               {"ReferenceSearchTestHnsw", ReferenceSearchTestHnsw, true}};
   setvbuf(stdout, nullptr, _IOLBF, 0);
+  const std::string only = argc > 2 && std::string(argv[1]) == "--case" ? argv[2] : "";
   for (const auto &c : cases) {
     if (c.needs_gpu && host_only) continue;
+    if (!only.empty() && only != c.name) continue;
     const int before = g_failures;
     c.fn();
     std::printf("[%s] %s\n", g_failures == before ? "  OK  " : "FAILED", c.name);

@@ -27,15 +27,21 @@ def test_filter_index_host_cases(built):
         assert f"[  OK  ] {case}" in p.stdout, p.stdout + p.stderr
 
 
+# most certain first: `-x` stops the run at the first failure
 @pytest.mark.gpu
-def test_filter_bridge_device_sets_equal_per_key_evaluation(built):
-    """On a B200: for 13 predicate trees (TAG exact / prefix / escaped, NUMERIC ranges, AND, OR, NOT, nested), before and
-    after mutations, the label set computed on the device equals the reference's per-key evaluation, and the kNN
-    through it equals the key-list pre-filter (FLAT) / the host-bitmap inline filter (HNSW) bit for bit."""
-    p = _run_filter([])
+@pytest.mark.parametrize("case", ["DeviceBridgeFlat", "ReferenceSearchTestFlat", "DeviceBridgeHnsw", "ReferenceSearchTestHnsw"])
+def test_filter_bridge_on_device(built, case):
+    """On a B200, tests/native/filter_index_test --case NAME:
+    DeviceBridge*: 13 predicate trees (TAG exact / prefix / escaped, NUMERIC ranges, AND, OR, NOT, nested), before and
+      after mutations — the label set computed on the device equals the reference's per-key evaluation, and the kNN
+      through it equals the key-list pre-filter (FLAT) / the host-bitmap inline filter (HNSW) bit for bit; on HNSW also
+      the planner's pre-filter branch against brute force.
+    ReferenceSearchTest*: the reference's SearchTest (testing/search_test.cc:751-895): 10 000 x 100 L2 vectors, numeric
+      and tag attributes, zero query, k = 5, ef = 30, fifteen filters -> the key sets the reference expects, for FLAT
+      and for HNSW (M = 10, ef_construction = 300), through the device-evaluated filter."""
+    p = _run_filter(["--case", case])
     assert p.returncode == 0, p.stdout + p.stderr
-    for case in ("DeviceBridgeFlat", "DeviceBridgeHnsw"):
-        assert f"[  OK  ] {case}" in p.stdout, p.stdout + p.stderr
+    assert f"[  OK  ] {case}" in p.stdout, p.stdout + p.stderr
 
 
 def test_tag_queries_match_redisearch_recorded_answers(built, tmp_path):
