@@ -516,6 +516,78 @@ static void ReferenceSearchTestOn(Index *vectors) {
     }
   }
 }
+// LocalSearchTest (testing/search_test.cc:542-676): FLAT index, L2 and COSINE, the same corpus, query = (1, ..., 1):
+// how many neighbours each filter yields (vector queries: min(k, qualifying keys); non-vector queries: the qualifying
+// keys themselves, here the cardinality of the device-evaluated set) and, for COSINE, distances within [0, 2].
+static void ReferenceLocalSearchTest() {
+  for (auto metric : {DistanceMetric::kL2, DistanceMetric::kCosine}) {
+    constexpr int kDim = 100, kRecords = 10000;
+    VectorIndexProto p;
+    p.dimension_count = kDim;
+    p.distance_metric = metric;
+    p.initial_cap = 1000;
+    p.flat_algorithm.block_size = 250;
+    auto flat = VectorFlat<float>::Create(p);
+    EXPECT_OK(flat);
+    if (!flat.ok()) return;
+    VectorFlat<float> *vectors = flat->get();
+    Tag tag(',', false, vectors);
+    Numeric numeric(vectors);
+    DeviceFilterEvaluator evaluator(vectors);
+    std::vector<float> v(kDim);
+    for (int i = 0; i < kRecords; i++) {
+      for (int j = 0; j < kDim; j++) v[j] = 10.0f * ((float)(i + j) / (float)(kRecords + kDim));
+      const std::string key = std::to_string(i);
+      EXPECT_OK(vectors->AddRecord(key, Bytes(v)));
+      EXPECT_OK(numeric.AddRecord(key, std::to_string(i)));
+      EXPECT_OK(tag.AddRecord(key, std::string("LT10000") + (i < 5 ? ",LT5" : "") + (i < 3 ? ",LT3" : "")));
+    }
+    auto T = [&](const char *q) { return std::make_unique<TagPredicate>(&tag, *Tag::ParseSearchTags(q, '|')); };
+    auto N = [&](double a, double b) { return std::make_unique<NumericPredicate>(&numeric, a, true, b, true); };
+    auto Two = [](PredicateType t, std::unique_ptr<Predicate> a, std::unique_ptr<Predicate> b) {
+      auto c = std::make_unique<ComposedPredicate>(t);
+      c->AddChild(std::move(a));
+      c->AddChild(std::move(b));
+      return c;
+    };
+    struct Case {
+      std::unique_ptr<Predicate> filter;
+      int k;  // 0: not a vector query
+      size_t expected;
+    };
+    std::vector<Case> cases;
+    cases.push_back({N(10, 20), 10, 10});
+    cases.push_back({N(99, 99), 10, 1});
+    cases.push_back({N(10000, 20000), 10, 0});
+    cases.push_back({T("LT5"), 5, 5});
+    cases.push_back({T("LT3"), 5, 3});
+    cases.push_back({T("Lt*"), 10, 10});
+    cases.push_back({T("random"), 10, 0});
+    cases.push_back({N(1, 10), 0, 10});
+    cases.push_back({Two(PredicateType::kComposedAnd, N(1, 10), T("LT5")), 0, 4});
+    cases.push_back({Two(PredicateType::kComposedOr, N(1, 10), N(21, 25)), 0, 15});
+    const std::vector<float> ones(kDim, 1.0f);
+    for (const auto &c : cases) {
+      if (c.k == 0) {
+        auto set = evaluator.Evaluate(*c.filter);
+        EXPECT_OK(set);
+        if (!set.ok()) continue;
+        uint64_t card = 0;
+        EXPECT_EQ(vkgpu_set_cardinality(vectors->handle(), set->id(), &card), 0);
+        EXPECT_EQ(card, (uint64_t)c.expected);
+        EXPECT_EQ(evaluator.EvaluateOnHost(*c.filter).size(), c.expected);
+        continue;
+      }
+      auto r = evaluator.Search(Bytes(ones), c.k, *c.filter);
+      EXPECT_OK(r);
+      if (!r.ok()) continue;
+      EXPECT_EQ(r->size(), c.expected);
+      if (metric == DistanceMetric::kCosine)
+        for (const auto &nb : *r) EXPECT_TRUE(nb.distance >= 0.0f && nb.distance <= 2.0f);
+    }
+  }
+}
+
 static void ReferenceSearchTestFlat() {
   VectorIndexProto p;
   p.dimension_count = 100;
@@ -770,6 +842,7 @@ int main(int argc, char **argv) {
                {"DeviceBridgeFlat", DeviceBridgeFlat, true},
                {"DeviceBridgeHnsw", DeviceBridgeHnsw, true},
                {"ReferenceSearchTestFlat", ReferenceSearchTestFlat, true},
+               {"ReferenceLocalSearchTest", ReferenceLocalSearchTest, true},
                {"ReferenceSearchTestHnsw", ReferenceSearchTestHnsw, true}};
   setvbuf(stdout, nullptr, _IOLBF, 0);
   const std::string only = argc > 2 && std::string(argv[1]) == "--case" ? argv[2] : "";

@@ -29,7 +29,8 @@ def test_filter_index_host_cases(built):
 
 # most certain first: `-x` stops the run at the first failure
 @pytest.mark.gpu
-@pytest.mark.parametrize("case", ["DeviceBridgeFlat", "ReferenceSearchTestFlat", "DeviceBridgeHnsw", "ReferenceSearchTestHnsw"])
+@pytest.mark.parametrize("case", ["DeviceBridgeFlat", "ReferenceSearchTestFlat", "ReferenceLocalSearchTest", "DeviceBridgeHnsw",
+                                  "ReferenceSearchTestHnsw"])
 def test_filter_bridge_on_device(built, case):
     """On a B200, tests/native/filter_index_test --case NAME:
     DeviceBridge*: 13 predicate trees (TAG exact / prefix / escaped, NUMERIC ranges, AND, OR, NOT, nested), before and
@@ -38,7 +39,9 @@ def test_filter_bridge_on_device(built, case):
       the planner's pre-filter branch against brute force.
     ReferenceSearchTest*: the reference's SearchTest (testing/search_test.cc:751-895): 10 000 x 100 L2 vectors, numeric
       and tag attributes, zero query, k = 5, ef = 30, fifteen filters -> the key sets the reference expects, for FLAT
-      and for HNSW (M = 10, ef_construction = 300), through the device-evaluated filter."""
+      and for HNSW (M = 10, ef_construction = 300), through the device-evaluated filter.
+    ReferenceLocalSearchTest: the reference's LocalSearchTest (search_test.cc:542-676), FLAT x {L2, COSINE}: neighbour
+      counts per filter, cosine distances within [0, 2]."""
     p = _run_filter(["--case", case])
     assert p.returncode == 0, p.stdout + p.stderr
     assert f"[  OK  ] {case}" in p.stdout, p.stdout + p.stderr
