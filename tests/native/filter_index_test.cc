@@ -492,6 +492,34 @@ static void ReferenceSearchTestOn(Index *vectors) {
   cases.push_back({"numeric_negate_filter", Not(N(0, 100)), {"101", "102", "103", "104", "105"}});
   cases.push_back({"tag_negate_filter", Not(T("LT5")), {"5", "6", "7", "8", "9"}});
   cases.push_back({"composite_filter_with_negate", Two(PredicateType::kComposedAnd, Not(N(4, 100)), T("LT5")), {"0", "1", "2", "3"}});
+  {
+    // FetchFilteredKeysTest (search_test.cc:677-749): CalcBestMatchingPrefilteredKeys with k = 100 over fetched key
+    // ranges — every fetched key is re-evaluated against the predicate, a key fetched twice counts once
+    struct Fetch {
+      std::unique_ptr<Predicate> filter;
+      std::vector<std::pair<int, int>> ranges;
+      std::set<std::string> expected;
+    };
+    std::vector<Fetch> fetches;
+    fetches.push_back({N(0, 4), {{0, 4}}, {"0", "1", "2", "3", "4"}});
+    fetches.push_back({Two(PredicateType::kComposedOr, N(0, 4), N(1, 6)), {{0, 4}, {1, 6}}, {"0", "1", "2", "3", "4", "5", "6"}});
+    fetches.push_back({Two(PredicateType::kComposedAnd, N(0, 4), N(1, 6)), {{0, 4}}, {"1", "2", "3", "4"}});
+    fetches.push_back({N(1, 5), {{0, 4}}, {"1", "2", "3", "4"}});
+    for (int j = 0; j < kDim; j++) v[j] = 10.0f * ((float)j / (float)(1 + kDim));  // DeterministicallyGenerateVectors(1, ...)
+    for (const auto &f : fetches) {
+      std::vector<std::string> keys;
+      for (const auto &range : f.ranges)
+        for (int i = range.first; i <= range.second; i++)
+          if (f.filter->Evaluate(std::to_string(i))) keys.push_back(std::to_string(i));
+      auto r = vectors->SearchPrefiltered(Bytes(v), 100, keys);
+      EXPECT_OK(r);
+      if (!r.ok()) continue;
+      std::set<std::string> got;
+      for (const auto &nb : *r) got.insert(nb.external_id);
+      EXPECT_EQ(r->size(), f.expected.size());
+      EXPECT_EQ(got, f.expected);
+    }
+  }
   const std::vector<float> zero(kDim, 0.0f);
   for (const auto &c : cases) {
     StatusOr<std::vector<Neighbor>> r = std::vector<Neighbor>();

@@ -337,7 +337,14 @@ StatusOr<std::vector<Neighbor>> VectorBase::SearchPrefiltered(std::string_view q
     if (it != tracked_metadata_by_key_.end()) ids.push_back(it->second.internal_id);
   }
   if (ids.empty()) return std::vector<Neighbor>();  // no qualifying key: nothing to rank (a NULL list means "no filter")
-  if (indexer_type_ == IndexerType::kHNSW) return ExactOverLabels(query, count, ids);
+  if (indexer_type_ == IndexerType::kHNSW) {
+    // a key fetched twice (OR of two ranges) counts once: EvaluatePrefilteredKeys de-duplicates (search.cc:412-431)
+    std::vector<uint64_t> unique_ids;
+    std::unordered_set<uint64_t> seen;
+    for (uint64_t id : ids)
+      if (seen.insert(id).second) unique_ids.push_back(id);
+    return ExactOverLabels(query, count, unique_ids);
+  }
   vkgpu_filter f{};
   f.labels = ids.data();
   f.n_labels = ids.size();
