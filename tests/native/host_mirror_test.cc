@@ -1022,8 +1022,10 @@ int main(int argc, char **argv) {
     HostOnly(vkgpu_device_count() > 0);
     std::printf("[%s] HostOnly\n", g_failures == before ? "  OK  " : "FAILED");
   }
+  const std::string only = argc > 2 && std::string(argv[1]) == "--case" ? argv[2] : "";
   if (!host_only)
     for (const auto &c : cases) {
+      if (!only.empty() && only != c.name) continue;
       const int before = g_failures;
       c.fn();
       std::printf("[%s] %s\n", g_failures == before ? "  OK  " : "FAILED", c.name);
