@@ -42,3 +42,56 @@ def test_the_double_is_not_reachable_from_the_product():
             if f.endswith((".py", ".cc", ".h", ".cu", ".cuh", ".inc")) or f == "Makefile":
                 text = open(os.path.join(base, f), errors="ignore").read()
                 assert "abi_test_double" not in text and "test_double" not in text, os.path.join(base, f)
+
+
+def test_host_mirror_hnsw_save_equals_the_references_stream_for_the_same_history(built, tmp_path):
+    """VectorHNSW<T> of the host mirror, fed 1500 AddRecord calls and 167 RemoveRecord calls, then SaveIndex — next to the
+    reference's own HierarchicalNSW given the same points, labels and deletions, then ITS SaveIndex.  Over the double
+    the graph is the oracle's (= the reference's, tests/test_oracle_vs_ref.py), so the two streams must agree in
+    everything that carries meaning: header bytes, every count word with its delete mark, every live neighbour id,
+    every vector, every label, every upper list.  They may differ only in the unused tail of a neighbour list, which
+    hnswlib leaves stale and the interchange arrays zero."""
+    import struct
+    import sys
+    import numpy as np
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    if O.ref() is None:
+        pytest.skip("needs oracle/_ref")
+    rng = np.random.default_rng(21)
+    n, d, m, efc = 1500, 24, 8, 60
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    X.tofile(tmp_path / "x.bin")
+    p = subprocess.run([os.path.join(NATIVE, "host_mirror_test_double"), "--hnsw-gpu-build", str(tmp_path / "x.bin"), str(d),
+                        str(m), str(efc), "9", str(tmp_path / "o.bin")], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and p.stdout.startswith("OK"), p.stdout + p.stderr
+    ours = O.unpack_chunks((tmp_path / "o.bin").read_bytes())
+    h = O.RefHnsw(d, O.L2, M=m, efc=efc, ef=10, initial_cap=n)
+    h.add_many(X)
+    for lab in range(1, n, 9):
+        h.mark_delete(lab)
+    ref = O.ref_hnsw_save(h)
+    links0, stride = 2 * m * 4 + 4, m * 4 + 4
+
+    def element(c):
+        (word,) = struct.unpack_from("<I", c, 0)
+        return word, c[4: 4 + 4 * (word & 0xFFFF)], c[links0:]
+
+    def upper(c):
+        out = []
+        for l in range(len(c) // stride):
+            (word,) = struct.unpack_from("<I", c, l * stride)
+            out.append((word, c[l * stride + 4: l * stride + 4 + 4 * (word & 0xFFFF)]))
+        return out
+
+    assert len(ours) == len(ref) and ours[0] == ref[0]
+    for i in range(1, 1 + n):
+        assert element(ours[i]) == element(ref[i]), i
+    i = 1 + n
+    while i < len(ref):
+        assert ours[i] == ref[i] and len(ref[i]) == 8, i
+        (size,) = struct.unpack("<Q", ref[i])
+        i += 1
+        if size:
+            assert upper(ours[i]) == upper(ref[i]), i
+            i += 1
