@@ -444,8 +444,10 @@ static void DeviceBridgeOn(Index *vectors, int dim, int n, bool hnsw) {
 // "LT10000" (+ ",LT5" for i < 5, + ",LT3" for i < 3); zero query, k = 5, ef = 30; the reference's 15 filters and
 // the key SETS it expects, for both index types.  The filters are built as predicate trees (the filter parser is
 // command surface and stays in the module).
+static const char *g_graph_path = nullptr;  // --graph FILE: an HNSW stream written by the reference for this corpus
+
 template <typename Index>
-static void ReferenceSearchTestOn(Index *vectors) {
+static void ReferenceSearchTestOn(Index *vectors, bool vectors_loaded = false) {
   constexpr int kDim = 100, kRecords = 10000;
   Tag tag(',', false, vectors);
   Numeric numeric(vectors);
@@ -454,7 +456,7 @@ static void ReferenceSearchTestOn(Index *vectors) {
   for (int i = 0; i < kRecords; i++) {
     for (int j = 0; j < kDim; j++) v[j] = 10.0f * ((float)(i + j) / (float)(kRecords + kDim));  // testing/common.cc:42-53
     const std::string key = std::to_string(i);
-    EXPECT_OK(vectors->AddRecord(key, Bytes(v)));
+    if (!vectors_loaded) EXPECT_OK(vectors->AddRecord(key, Bytes(v)));
     EXPECT_OK(numeric.AddRecord(key, std::to_string(i)));
     std::string tags = "LT10000";
     if (i < 5) tags += ",LT5";
@@ -626,6 +628,32 @@ static void ReferenceSearchTestFlat() {
   EXPECT_OK(flat);
   if (flat.ok()) ReferenceSearchTestOn(flat->get());
 }
+// One chunk stream in a file: u64 chunk count, then per chunk u64 length + bytes (the container of oracle/ref_capi.cc)
+struct FileStream : public InputStream {
+  std::vector<std::string> chunks;
+  size_t next = 0;
+  bool Read(const char *path) {
+    FILE *f = std::fopen(path, "rb");
+    if (!f) return false;
+    uint64_t n = 0;
+    bool ok = std::fread(&n, 8, 1, f) == 1;
+    for (uint64_t i = 0; ok && i < n; i++) {
+      uint64_t len = 0;
+      ok = std::fread(&len, 8, 1, f) == 1 && len < (1ull << 32);
+      if (!ok) break;
+      std::string c(len, '\0');
+      ok = len == 0 || std::fread(c.data(), 1, len, f) == len;
+      chunks.push_back(std::move(c));
+    }
+    std::fclose(f);
+    return ok;
+  }
+  vks::StatusOr<std::unique_ptr<std::string>> LoadChunk() override {
+    if (next >= chunks.size()) return vks::NotFoundError("no more chunks");
+    return std::make_unique<std::string>(chunks[next++]);
+  }
+  bool HasNext() const override { return next < chunks.size(); }
+};
 static void ReferenceSearchTestHnsw() {
   VectorIndexProto p;
   p.dimension_count = 100;
@@ -634,6 +662,26 @@ static void ReferenceSearchTestHnsw() {
   p.hnsw_algorithm.m = 10;
   p.hnsw_algorithm.ef_construction = 300;
   p.hnsw_algorithm.ef_runtime = 30;
+  if (g_graph_path) {
+    // the reference's OWN graph for this corpus (built and saved by its hnswlib through oracle/_ref), loaded the way
+    // an RDB load would: the searches below then run on exactly the graph the reference's SearchTest runs on
+    FileStream data;
+    EXPECT_TRUE(data.Read(g_graph_path));
+    auto hnsw = VectorHNSW<float>::LoadFromStream(p, data);
+    EXPECT_OK(hnsw);
+    if (!hnsw.ok()) return;
+    FileStream keys;  // TrackedKeyMetadata: key = decimal label, as the corpus assigns them
+    for (int i = 0; i < 10000; i++) {
+      TrackedKeyMetadataPb pb;
+      pb.key = std::to_string(i);
+      pb.internal_id = (uint64_t)i;
+      pb.magnitude = kDefaultMagnitude;
+      keys.chunks.push_back(pb.SerializeAsString());
+    }
+    EXPECT_OK((*hnsw)->LoadTrackedKeys(keys));
+    ReferenceSearchTestOn(hnsw->get(), true);
+    return;
+  }
   auto hnsw = VectorHNSW<float>::Create(p);
   EXPECT_OK(hnsw);
   if (hnsw.ok()) ReferenceSearchTestOn(hnsw->get());
@@ -874,6 +922,7 @@ int main(int argc, char **argv) {
                {"ReferenceSearchTestHnsw", ReferenceSearchTestHnsw, true}};
   setvbuf(stdout, nullptr, _IOLBF, 0);
   const std::string only = argc > 2 && std::string(argv[1]) == "--case" ? argv[2] : "";
+  if (argc > 4 && std::string(argv[3]) == "--graph") g_graph_path = argv[4];
   for (const auto &c : cases) {
     if (c.needs_gpu && host_only) continue;
     if (!only.empty() && only != c.name) continue;

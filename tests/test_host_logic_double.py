@@ -95,3 +95,20 @@ def test_host_mirror_hnsw_save_equals_the_references_stream_for_the_same_history
         if size:
             assert upper(ours[i]) == upper(ref[i]), i
             i += 1
+
+
+def test_reference_search_test_on_the_references_own_graph_over_the_double(built, tmp_path):
+    """What tests/test_zz_filter_bridge.py does on a B200 for ReferenceSearchTestHnsw, over the double: the reference
+    builds and saves the graph, the host mirror loads the stream and answers the fifteen filters."""
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import oracle_lib as O
+    if O.ref() is None:
+        pytest.skip("needs oracle/_ref")
+    h = O.RefHnsw(100, O.L2, M=10, efc=300, ef=30, initial_cap=1000)
+    h.add_many(O.deterministic_vectors(10000, 100, 10.0))
+    path = tmp_path / "reference_graph.bin"
+    path.write_bytes(O.pack_chunks(O.ref_hnsw_save(h)))
+    p = subprocess.run([os.path.join(NATIVE, "filter_index_test_double"), "--case", "ReferenceSearchTestHnsw", "--graph", str(path)],
+                       capture_output=True, text=True, timeout=900)
+    assert p.returncode == 0 and "[  OK  ] ReferenceSearchTestHnsw" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]

@@ -31,7 +31,7 @@ def test_filter_index_host_cases(built):
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["DeviceBridgeFlat", "ReferenceSearchTestFlat", "ReferenceLocalSearchTest", "DeviceBridgeHnsw",
                                   "ReferenceSearchTestHnsw"])
-def test_filter_bridge_on_device(built, case):
+def test_filter_bridge_on_device(built, tmp_path, case):
     """On a B200, tests/native/filter_index_test --case NAME:
     DeviceBridge*: 13 predicate trees (TAG exact / prefix / escaped, NUMERIC ranges, AND, OR, NOT, nested), before and
       after mutations — the label set computed on the device equals the reference's per-key evaluation, and the kNN
@@ -39,10 +39,24 @@ def test_filter_bridge_on_device(built, case):
       the planner's pre-filter branch against brute force.
     ReferenceSearchTest*: the reference's SearchTest (testing/search_test.cc:751-895): 10 000 x 100 L2 vectors, numeric
       and tag attributes, zero query, k = 5, ef = 30, fifteen filters -> the key sets the reference expects, for FLAT
-      and for HNSW (M = 10, ef_construction = 300), through the device-evaluated filter.
+      and for HNSW (M = 10, ef_construction = 300; on the reference's own graph, loaded from its stream), through the
+      device-evaluated filter.
     ReferenceLocalSearchTest: the reference's LocalSearchTest (search_test.cc:542-676), FLAT x {L2, COSINE}: neighbour
       counts per filter, cosine distances within [0, 2]."""
-    p = _run_filter(["--case", case])
+    args = ["--case", case]
+    if case == "ReferenceSearchTestHnsw":
+        # the reference's OWN graph for this corpus (its hnswlib builds and saves it here through oracle/_ref), loaded
+        # through VectorHNSW::LoadFromStream: the searches run on exactly the graph the reference's test runs on
+        import sys
+        sys.path.insert(0, os.path.join(ROOT, "tests"))
+        import oracle_lib as O
+        if O.ref() is not None:
+            h = O.RefHnsw(100, O.L2, M=10, efc=300, ef=30, initial_cap=1000)
+            h.add_many(O.deterministic_vectors(10000, 100, 10.0))
+            path = tmp_path / "reference_graph.bin"
+            path.write_bytes(O.pack_chunks(O.ref_hnsw_save(h)))
+            args += ["--graph", str(path)]
+    p = _run_filter(args)
     assert p.returncode == 0, p.stdout + p.stderr
     assert f"[  OK  ] {case}" in p.stdout, p.stdout + p.stderr
 
