@@ -53,7 +53,7 @@ def parse_search_tags(data, separator, min_prefix_length=2):
         if tag[-1] == "*":
             if not is_valid_prefix(tag):
                 raise FilterError(f"Tag string `{tag}` ends with multiple *.")
-            if len(tag) <= min_prefix_length:
+            if len(tag.encode("utf-8")) <= min_prefix_length:  # the reference measures bytes
                 raise FilterError(f"Tag string `{tag}` is too short for prefix wildcard.")
         out.add(tag)
 
@@ -236,9 +236,24 @@ def evaluate(tree, key, indexes):
     raise ValueError(kind)
 
 
+def validate(tree):
+    """The query is parsed before anything is evaluated (FilterParser::Parse builds every TagPredicate up front,
+    src/commands/filter_parser.cc:359-376), so a malformed tag clause fails the query even where evaluation would
+    have short-circuited past it."""
+    kind = tree[0]
+    if kind == "tag":
+        query_tags(tree[2])
+    elif kind == "not":
+        validate(tree[1])
+    elif kind in ("and", "or"):
+        for c in tree[1]:
+            validate(c)
+
+
 def prefiltered_keys(tree, universe, indexes):
     """EvaluatePrefilteredKeys (src/query/search.cc:401-455) reduced to its result: the keys of the vector index
     (`universe`) for which the root predicate holds."""
+    validate(tree)
     return sorted(k for k in universe if evaluate(tree, k, indexes))
 
 

@@ -84,6 +84,13 @@ NUMBERS = ["0", "-0", "1", "1.5", "-2.25", "1e3", "-1E-2", " 7 ", "inf", "-inf",
            "0x10", "1.5abc", "12 3", "1e999"]
 
 
+CHARSET = ["a", "b", "A", "B", "\\", "|", "*", " ", ",", ";", "}", "\t", "é", "x"]
+
+
+def _random_text(rng, lo=0, hi=7):
+    return "".join(rng.choice(CHARSET) for _ in range(rng.randint(lo, hi)))
+
+
 def _random_tree(rng, depth=0):
     r = rng.random()
     if depth >= 3 or r < 0.35:
@@ -93,6 +100,8 @@ def _random_tree(rng, depth=0):
                 t = rng.choice(["red", "RED", "green", "blu*", "dark*", "dis*", "disagree", "a\\|b", "a\\}b", "a\\\\b", "x\\\\",
                                 "café", "中文", "😀", "padded", "tab\\\there", "q\\*", "nomatch", "  ", "da*"])
                 pieces.append(t)
+            if rng.random() < 0.35:  # arbitrary text: escapes, separators, wildcards and blanks in any position
+                return ("tag", rng.choice(["t1", "t2"]), _random_text(rng, 0, 9))
             return ("tag", rng.choice(["t1", "t2"]), " | ".join(pieces))
         a, b = sorted(rng.choice([-3.0, -0.01, 0.0, 0.5, 1.0, 1.5, 3.0, 7.0, 1000.0, float("-inf"), float("inf")]) for _ in range(2))
         return ("num", rng.choice(["n1", "n2"]), a, rng.random() < 0.5, b, rng.random() < 0.5)
@@ -115,7 +124,7 @@ def _tokens(tree):
     return out
 
 
-@pytest.mark.parametrize("seed", [1, 2, 3, 4])
+@pytest.mark.parametrize("seed", [1, 2, 3, 4, 5, 6, 7, 8])
 def test_cpp_host_mirror_agrees_with_the_oracle_on_random_inputs(built, tmp_path, seed):
     rng = random.Random(seed)
     sep = rng.choice([",", ";", "|"])
@@ -140,6 +149,8 @@ def test_cpp_host_mirror_agrees_with_the_oracle_on_random_inputs(built, tmp_path
         if rng.random() < 0.55:
             name = rng.choice(list(tags))
             data = sep.join(rng.choice(TAG_ALPHABET) for _ in range(rng.randint(0, 3)))
+            if rng.random() < 0.3:
+                data = _random_text(rng, 0, 9)
             if op < 0.5:
                 lines.append(f"tadd {name} {hx(key)} {hx(data)}")
                 record(lambda: tags[name].add(key, data))
