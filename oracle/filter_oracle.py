@@ -160,18 +160,25 @@ class TagIndex:
 
 # ---------------------------------------------------------------------------------------------- NUMERIC
 def parse_number(data):
-    """ParseNumber, src/indexes/numeric.cc:30-36: absl::SimpleAtod (surrounding whitespace allowed, decimal or
-    scientific notation, inf / infinity with a sign, no hexadecimal); any spelling of nan is rejected."""
+    """ParseNumber, src/indexes/numeric.cc:30-36: the exact text "nan" (any case, nothing around it) is refused;
+    everything else goes through absl::SimpleAtod — surrounding whitespace allowed, one leading '+' allowed unless a
+    '-' follows, decimal or scientific notation, inf / infinity / nan spellings, no hexadecimal, no digit separators,
+    the whole text must be consumed, overflow gives +-infinity.  So " nan" or "-nan" is accepted, as a NaN."""
+    import re
+    if data.lower() == "nan":
+        return None
     s = strip_ascii_whitespace(data)
-    if not s:
+    if s.startswith("+"):
+        s = s[1:]
+        if s.startswith("-"):
+            return None
+    if not s or s[0] in ASCII_WS:
         return None
-    low = s.lower()
-    if "nan" in low or "x" in low or "_" in low:
+    if not re.fullmatch(r"-?(\d+\.?\d*([eE][+-]?\d+)?|\.\d+([eE][+-]?\d+)?|inf|infinity|nan(\([A-Za-z0-9_]*\))?)", s, re.I | re.A):
         return None
-    try:
-        return float(s)
-    except ValueError:
-        return None
+    if "nan" in s.lower():
+        return float("nan")
+    return float(s)
 
 
 def numeric_predicate_evaluate(value, start, inclusive_start, end, inclusive_end):

@@ -81,7 +81,8 @@ def test_oracle_numeric_cases_of_the_reference_unit_tests():
 TAG_ALPHABET = ["red", "RED", "Red", "green", "blue", "dark blue", "darkness", "dis", "disagree", "dislike", "a|b", "a}b",
                 "a\\b", "x\\", "café", "中文", "😀", " padded ", "tab\there", "q*", "star*x", ""]
 NUMBERS = ["0", "-0", "1", "1.5", "-2.25", "1e3", "-1E-2", " 7 ", "inf", "-inf", "+3", ".5", "5.", "bad", "nan", "NaN", "",
-           "0x10", "1.5abc", "12 3", "1e999"]
+           "0x10", "1.5abc", "12 3", "1e999", "+-3", "-+3", "+ 3", " nan", "-nan", "Infinity", "-INF", "1e", "e5", ".", "-.5e1",
+           "1_000", "-0x1p3", "1e-999", "00012", "1.e2"]
 
 
 CHARSET = ["a", "b", "A", "B", "\\", "|", "*", " ", ",", ";", "}", "\t", "é", "x"]

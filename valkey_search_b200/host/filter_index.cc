@@ -331,13 +331,24 @@ Numeric::~Numeric() {
 }
 
 std::optional<double> Numeric::ParseNumber(std::string_view data) {
-  // absl::SimpleAtod: optional surrounding whitespace, decimal or scientific notation, "inf" / "infinity" with a
-  // sign, no hexadecimal; "nan" is rejected by the caller (numeric.cc:30-36)
+  // numeric.cc:30-36: the exact text "nan" (any case, nothing around it) is refused; everything else goes through
+  // absl::SimpleAtod — surrounding whitespace allowed, one leading '+' allowed unless a '-' follows, decimal or
+  // scientific notation, inf / infinity / nan(...) spellings, no hexadecimal, the whole text must be consumed,
+  // overflow gives +-infinity.  (So " nan" or "-nan" IS accepted, as a NaN that no range ever matches.)
+  {
+    std::string lower(data);
+    for (auto &c : lower) c = (char)std::tolower((unsigned char)c);
+    if (lower == "nan") return std::nullopt;
+  }
   std::string s(StripAsciiWhitespace(data));
+  if (!s.empty() && s[0] == '+') {
+    s.erase(0, 1);
+    if (!s.empty() && s[0] == '-') return std::nullopt;
+  }
   if (s.empty()) return std::nullopt;
-  std::string lower = s;
-  for (auto &c : lower) c = (char)std::tolower((unsigned char)c);
-  if (lower.find("nan") != std::string::npos || lower.find('x') != std::string::npos) return std::nullopt;
+  for (size_t i = 0; i + 1 < s.size(); i++)  // strtod would take "0x..." as hexadecimal; absl::from_chars does not
+    if (s[i] == '0' && (s[i + 1] == 'x' || s[i + 1] == 'X') && (i == 0 || s[i - 1] == '-')) return std::nullopt;
+  if (std::isspace((unsigned char)s[0])) return std::nullopt;  // strtod skips leading blanks ("+ 3"); from_chars does not
   char *end = nullptr;
   const double v = std::strtod(s.c_str(), &end);
   if (end != s.c_str() + s.size()) return std::nullopt;
