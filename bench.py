@@ -115,38 +115,103 @@ def host_threads():
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
-def cpu_reference_arm(X_sample, Q, k, n_total, threads, nq):
-    """Times the reference's CPU FLAT search (its own hnswlib+simsimd if oracle/_ref was built, else the C
-    port) on `X_sample` with `threads` host threads, one query per thread at a time (the module's model,
-    src/query/search.cc:886-910), and scales QPS linearly to n_total rows."""
-    import numpy as np
-    import oracle_lib as O
+def mem_available_bytes():
+    try:
+        for ln in open("/proc/meminfo"):
+            if ln.startswith("MemAvailable:"):
+                return int(ln.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
 
-    ref = O.ref()
-    kind = "reference" if ref is not None else "port"
-    S, D = X_sample.shape
-    if ref is not None:
-        ix = O.RefFlat(D, O.L2, initial_cap=S)
-        info = f"simsimd skylake={ref.vkref_uses_skylake()} haswell={ref.vkref_uses_haswell()}"
-    else:
-        ix = O.PortFlat(D, O.L2)
-        info = "C port"
-    t0 = time.perf_counter()
-    ix.add_many(X_sample)
-    log(f"[cpu arm] {kind} ({info}): indexed {S} rows in {time.perf_counter() - t0:.1f}s")
-    Qs = np.ascontiguousarray(Q[:nq])
-    secs, d, l, n = ix.search_mt(Qs, k, threads)
-    qps_sample = nq / secs
-    qps_full = qps_sample * (S / float(n_total))
-    sample = (f"{nq} queries x {S} rows x {D} dims, k={k}, {threads} threads, {secs:.2f}s wall; "
-              f"QPS scaled linearly by {S}/{n_total} rows ({info})")
-    return dict(value=qps_full, unit=UNIT, cores=threads, kind=kind, sample=sample), secs, (d, l, n)
+
+def choose_cpu_rows(args, N, D):
+    """Rows the CPU arm searches: the FULL corpus of the stated configuration when the host has the RAM for one
+    fp32 copy of it (10M x 768 = 30.7 GB; the GPU boxes have ~196 GB), else a bounded sample (QPS then scaled
+    linearly by rows and marked `extrapolated`)."""
+    if args.cpu_sample_rows:
+        return min(args.cpu_sample_rows, N)
+    need = N * D * 4 + (16 << 30)
+    return N if mem_available_bytes() >= need else min(1_000_000, N)
 
 
 def gen_block(torch, dev, block, rows, D):
     g = torch.Generator(device=dev)
     g.manual_seed(1234 + block)
     return torch.randn((rows, D), generator=g, device=dev, dtype=torch.float32)
+
+
+def host_corpus(S, N, D, dev=None):
+    """The first S rows of the N-row synthetic corpus on the host, bit-identical to what the GPU arm indexes (same
+    torch CUDA generator, seed 1234 + block, every 1M-row block generated at the size the GPU arm generates it);
+    numpy RNG when there is no CUDA device (CPU-only smoke runs)."""
+    import numpy as np
+    import torch
+
+    Xs = np.empty((S, D), np.float32)
+    if dev is not None:
+        BLK = 1_000_000
+        for blk in range((S + BLK - 1) // BLK):
+            lo, hi = blk * BLK, min((blk + 1) * BLK, S)
+            Xb = gen_block(torch, dev, blk, min(BLK, N - lo), D)[: hi - lo]
+            torch.from_numpy(Xs[lo:hi]).copy_(Xb)
+            del Xb
+    else:
+        Xs[:] = np.random.default_rng(1234).standard_normal((S, D), dtype=np.float32)
+    return Xs
+
+
+def make_cpu_index(Xs, D):
+    """The reference's own BruteforceSearch over the host rows (oracle/_ref when built, else the C port)."""
+    import oracle_lib as O
+
+    ref = O.ref()
+    S = Xs.shape[0]
+    t0 = time.perf_counter()
+    if ref is not None:
+        ix = O.RefFlat(D, O.L2, initial_cap=S)
+        if hasattr(ref, "vkref_flat_add_many_borrowed"):
+            ix.add_many_borrowed(Xs)
+        else:
+            ix.add_many(Xs)
+        kind, info = "reference", f"simsimd skylake={ref.vkref_uses_skylake()} haswell={ref.vkref_uses_haswell()}"
+    else:
+        ix = O.PortFlat(D, O.L2)
+        ix.add_many(Xs)
+        kind, info = "port", "C port"
+    log(f"[cpu arm] {kind} ({info}): indexed {S} rows in {time.perf_counter() - t0:.1f}s")
+    return ix, kind, info
+
+
+def cpu_reference_arm(Xs, Q, k, n_total, threads, nq):
+    """Times the reference's CPU FLAT search on `Xs` with `threads` host threads, one query per thread at a time
+    (the module's model, src/query/search.cc:886-910).  When Xs holds fewer rows than the configuration names, QPS
+    is scaled linearly and the line says so."""
+    import numpy as np
+
+    S, D = Xs.shape
+    ix, kind, info = make_cpu_index(Xs, D)
+    Qs = np.ascontiguousarray(Q[:nq])
+    secs, d, l, n = ix.search_mt(Qs, k, threads)
+    qps = (nq / secs) * (S / float(n_total))
+    scaled = "" if S == n_total else f"; QPS scaled linearly by {S}/{n_total} rows"
+    sample = f"{nq} queries x {S} rows x {D} dims, k={k}, {threads} threads, {secs:.2f}s wall{scaled} ({info})"
+    return dict(value=qps, unit=UNIT, cores=threads, kind=kind, sample=sample, measured_rows=S,
+                extrapolated=S != n_total), secs, (d, l, n)
+
+
+def count_mismatches(np, got, want, nq):
+    """Queries whose (count, ids, distance BITS) differ between two result triples (dist, labels, n)."""
+    gd, gl, gn = got
+    wd, wl, wn = want
+    bad = 0
+    for b in range(nq):
+        c = int(wn[b])
+        ok = int(gn[b]) == c and np.array_equal(np.asarray(gl[b][:c], np.uint64), np.asarray(wl[b][:c], np.uint64)) and \
+            np.array_equal(np.ascontiguousarray(gd[b][:c], np.float32).view(np.uint32),
+                           np.ascontiguousarray(wd[b][:c], np.float32).view(np.uint32))
+        bad += 0 if ok else 1
+    return bad
 
 
 def hnsw_workload(args):
@@ -468,9 +533,12 @@ def main():
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--path", default="auto", choices=["auto", "exact", "tensor"])
-    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
-    ap.add_argument("--cpu-queries", type=int, default=64)
+    ap.add_argument("--cpu-sample-rows", type=int, default=0,
+                    help="rows the CPU arm searches; 0 = the whole corpus when host RAM allows, else 1M")
+    ap.add_argument("--cpu-queries", type=int, default=0, help="queries per CPU step; 0 = one per host thread")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--parity-queries", type=int, default=16,
+                    help="queries of the batch re-answered by the exact fp32-order scan and compared bit for bit")
     ap.add_argument("--workload", default="flat", choices=["flat", "hnsw", "prefilter", "serve"],
                     help="flat = BASELINE configs[1] (the driver's default); hnsw = configs[2] at --rows")
     ap.add_argument("--ef", type=int, default=128)
@@ -504,37 +572,39 @@ def main():
         if rank != 0:
             return 0
         threads = host_threads()
-        S = min(args.cpu_sample_rows, N)
-        if torch.cuda.is_available():
-            dev = torch.device("cuda", local_rank)
-            Xs = gen_block(torch, dev, 0, S, D).cpu().numpy()
+        S = choose_cpu_rows(args, N, D)
+        has_gpu = torch.cuda.is_available()
+        dev = torch.device("cuda", local_rank) if has_gpu else None
+        t0 = time.perf_counter()
+        Xs = host_corpus(S, N, D, dev)
+        if has_gpu:
             g = torch.Generator(device=dev)
             g.manual_seed(4321)
             Q = torch.randn((B, D), generator=g, device=dev, dtype=torch.float32).cpu().numpy()
         else:
-            rng = np.random.default_rng(1234)
-            Xs = rng.standard_normal((S, D), dtype=np.float32)
             Q = np.random.default_rng(4321).standard_normal((B, D), dtype=np.float32)
-        nq = max(threads, min(args.cpu_queries, B))
-        import oracle_lib as O
-        ref = O.ref()
-        ix = O.RefFlat(D, O.L2, initial_cap=S) if ref is not None else O.PortFlat(D, O.L2)
-        kind = "reference" if ref is not None else "port"
-        ix.add_many(Xs)
-        Qs = np.ascontiguousarray(Q[:nq])
+        log(f"[reference arm] {S} x {D} rows on the host after {time.perf_counter() - t0:.1f}s")
+        nq = max(threads, min(args.cpu_queries or threads, B))
+        ix, kind, info = make_cpu_index(Xs, D)
         times = []
         for it in range(W + K):
-            secs, _, _, _ = ix.search_mt(Qs, k, threads)
+            # a different slice of the batch every step (the corpus is far larger than any cache either way)
+            q0 = (it * nq) % max(B - nq + 1, 1)
+            secs, _, _, _ = ix.search_mt(np.ascontiguousarray(Q[q0:q0 + nq]), k, threads)
             if it >= W:
                 times.append(secs)
         total = sum(times)
         qps = (nq * K / total) * (S / float(N))
+        scaled = "" if S == N else f"; QPS scaled linearly by {S}/{N} rows"
         sample = (f"each step = {nq} queries x {S} rows x {D} dims, k={k}, {threads} host threads "
-                  f"(one query per thread at a time); QPS scaled linearly by {S}/{N} rows")
+                  f"(one query per thread at a time, {info}){scaled}")
+        rcfg = cfg if S == N else dict(cfg, cpu_rows=S)  # identical config whenever the CPU ran the whole corpus
         line = {"impl": "reference", "metric": METRIC, "value": qps, "unit": UNIT, "n_gpus": args.gpus, "steps": K,
                 "warmup": W, "ms_per_step": 1000.0 * total / K, "higher_is_better": True, "scaling": "strong",
-                "vs_baseline": None, "dtype": "f32", "data": "synthetic N(0,1)", "config": cfg,
-                "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample},
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic N(0,1)", "config": rcfg,
+                "measured_rows": S, "extrapolated": S != N, "cpu_queries_per_step": nq,
+                "cpu_baseline": {"value": qps, "unit": UNIT, "cores": threads, "kind": kind, "sample": sample,
+                                 "measured_rows": S, "extrapolated": S != N},
                 "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(line)
         return 0
@@ -560,13 +630,9 @@ def main():
     lib = L.lib()
     t0 = time.perf_counter()
     BLK = 1_000_000
-    X_sample = None
-    S = min(args.cpu_sample_rows, N)
     for blk in range(lo // BLK, (hi + BLK - 1) // BLK):
         b_lo, b_hi = blk * BLK, min((blk + 1) * BLK, N)
         Xb = gen_block(torch, dev, blk, b_hi - b_lo, D)
-        if blk == 0 and rank == 0 and not args.no_cpu_baseline:
-            X_sample = Xb[:S].cpu().numpy()
         s_lo, s_hi = max(lo, b_lo), min(hi, b_hi)
         part = Xb[s_lo - b_lo: s_hi - b_lo].contiguous()
         labels = np.arange(s_lo, s_hi, dtype=np.uint64)
@@ -575,8 +641,9 @@ def main():
         del Xb, part
     torch.cuda.synchronize()
     log(f"[rank {rank}] corpus rows [{lo},{hi}) resident in HBM after {time.perf_counter() - t0:.1f}s")
+    path_id = {"auto": V.PATH_AUTO, "exact": V.PATH_EXACT_FMA, "tensor": V.PATH_TENSOR}[args.path]
     if args.path != "auto":
-        ix.SetSearchPath({"exact": V.PATH_EXACT_FMA, "tensor": V.PATH_TENSOR}[args.path])
+        ix.SetSearchPath(path_id)
 
     g = torch.Generator(device=dev)
     g.manual_seed(4321)
@@ -621,6 +688,8 @@ def main():
     ms_total = float(t.item())
     ms_step = ms_total / K
     value = B * K / (ms_total / 1e3)
+    # the answer of the last timed step (merged over all ranks when world > 1), kept for the parity checks below
+    timed_res = tuple(x.cpu().numpy().copy() for x in res)
 
     # ---- end to end with HOST buffers: one GPU = the C-ABI call a module adapter makes (vkgpu_search_batch);
     #      several GPUs = ShardedFlat.search_host (H2D of the queries, device search/exchange/merge, D2H of the result)
@@ -653,6 +722,27 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_qps = B * K / float(te.item())
+
+    # ---- parity (a): the headline path against the exact fp32-order scan (PATH_EXACT_FMA: the reference's own
+    #      summation order, bit-checked against the oracle by the -m gpu tests) on the FULL corpus — every rank
+    #      re-answers the first `pq` queries on its shard with the exact scan, same exchange + merge, and rank 0
+    #      compares ids and distance bits with what the timed steps returned for those queries.
+    parity = {"queries": 0, "mismatches": 0}
+    pq = min(args.parity_queries, B)
+    if pq and args.path != "exact":
+        ix.SetSearchPath(V.PATH_EXACT_FMA)
+        out_x = sh.alloc_out(pq, k, dev)
+        res_x = sh.search_device(dQ[:pq].contiguous(), k, sptr, out_x)
+        barrier()
+        exact_res = tuple(x.cpu().numpy().copy() for x in res_x)
+        ix.SetSearchPath(path_id)
+        if rank == 0:
+            bad = count_mismatches(np, timed_res, exact_res, pq)
+            parity.update(queries=pq, mismatches=bad, headline_vs_exact_scan={"queries": pq, "rows": N, "mismatches": bad})
+            if world == 1:  # the host-buffer C-ABI call answered the same batch: it must agree too
+                bad_h = count_mismatches(np, (out_d, out_l, out_n), exact_res, pq)
+                parity["mismatches"] += bad_h
+                parity["host_call_vs_exact_scan"] = {"queries": pq, "mismatches": bad_h}
 
     if rank != 0:
         if world > 1:
@@ -702,11 +792,33 @@ def main():
         roofline["share_of_step"] = (dms / K) / ms_step
         roofline["kernels_ms_per_step"] = {n: v[0] / K for n, v in per_kind.items()}
 
+    # ---- CPU arm + parity (b): the reference's own hnswlib + simsimd (oracle/_ref) answers `nq` of the batch's
+    #      queries on the host over the SAME rows — the whole corpus of the configuration when host RAM allows — and
+    #      every id, rank and distance bit the GPU returned for them is compared with the CPU's.
     cpu_base = None
-    if not args.no_cpu_baseline and X_sample is not None:
+    if not args.no_cpu_baseline:
         threads = host_threads()
-        nq = max(threads, min(args.cpu_queries, B))
-        cpu_base, secs, (cd, cl, cn) = cpu_reference_arm(X_sample, hQ, k, N, threads, nq)
+        nq = max(1, min(args.cpu_queries or threads, B))
+        S = choose_cpu_rows(args, N, D)
+        t0 = time.perf_counter()
+        X_host = host_corpus(S, N, D, dev)
+        log(f"[cpu arm] {S} x {D} rows copied to the host in {time.perf_counter() - t0:.1f}s")
+        cpu_base, secs, cpu_res = cpu_reference_arm(X_host, hQ, k, N, threads, nq)
+        if S == N:
+            gpu_res = timed_res
+        else:  # the CPU could only hold a sample: the GPU answers the same queries over the same first S rows
+            ix2 = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=S, max_batch=nq, device=local_rank)
+            ix2.AddRecordsBulk(range(S), X_host)
+            if S >= 4096 and args.path != "exact":
+                ix2.SetSearchPath(V.PATH_TENSOR)
+            gpu_res = ix2.SearchBatchRaw(hQ[:nq], k)
+        bad = count_mismatches(np, gpu_res, cpu_res, nq)
+        parity["queries"] += nq
+        parity["mismatches"] += bad
+        parity["gpu_vs_cpu_reference"] = {"queries": nq, "rows": S, "mismatches": bad, "cpu_kind": cpu_base["kind"]}
+        del X_host
+    parity["ok"] = parity["mismatches"] == 0
+    parity["compared"] = "neighbour ids, ranks and fp32 distance bits"
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -714,11 +826,14 @@ def main():
             "e2e": {"value": e2e_qps, "unit": UNIT, "h2d_bytes_per_step": B * D * 4,
                     "d2h_bytes_per_step": B * k * 12 + B * 4},
             "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_base, "clocks": clocks,
-            "path": {0: "auto", 1: "exact", 2: "tensor"}.get(0 if args.path == "auto" else (1 if args.path == "exact" else 2)),
+            "parity": parity, "path": args.path,
             "tensor_fallback_queries": int(st.tensor_fallbacks), "rows_per_gpu": n_local}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+    if not parity["ok"]:
+        log(f"PARITY FAILURE: {parity}")
+        return 1
     return 0
 
 

@@ -141,6 +141,25 @@ int vkref_flat_add(void *h, const float *v, uint64_t label) {
   }
   return -1;
 }
+// Bulk ingest that BORROWS the caller's rows: BruteforceSearch stores a pointer per slot and the adapter layer owns
+// the bytes (interned strings, vector_base.cc:152-166) — here the caller's [n][dim] array plays that role and must
+// outlive the index.  Used by bench.py's CPU arm at the full 10M-row configuration (no second copy of 30 GB).
+int vkref_flat_add_many_borrowed(void *h, const float *X, uint64_t n, uint64_t first_label) {
+  auto *f = static_cast<Flat *>(h);
+  const size_t dim = f->store.dim;
+  for (uint64_t i = 0; i < n; i++) {
+    for (int attempt = 0;; ++attempt) {
+      try {
+        f->algo->addPoint(X + i * dim, first_label + i);
+        break;
+      } catch (const std::runtime_error &e) {
+        if (attempt || std::string(e.what()).find("exceeds the specified limit") == std::string::npos) return -1;
+        f->algo->resizeIndex(f->algo->data_->getCapacity() + f->block_size);
+      }
+    }
+  }
+  return 0;
+}
 int vkref_flat_remove(void *h, uint64_t label) {
   auto *f = static_cast<Flat *>(h);
   try {

@@ -98,6 +98,8 @@ def ref():
         _sig(lib, "vkref_flat_free", None, [C.c_void_p])
         _sig(lib, "vkref_flat_add", C.c_int, [C.c_void_p, _f32p, C.c_uint64])
         _sig(lib, "vkref_flat_remove", C.c_int, [C.c_void_p, C.c_uint64])
+        if hasattr(lib, "vkref_flat_add_many_borrowed"):  # absent from a libvkref.so built before round 2
+            _sig(lib, "vkref_flat_add_many_borrowed", C.c_int, [C.c_void_p, _f32p, C.c_uint64, C.c_uint64])
         _sig(lib, "vkref_flat_count", C.c_size_t, [C.c_void_p])
         _sig(lib, "vkref_flat_search", C.c_size_t, [C.c_void_p, _f32p, C.c_size_t, _f32p, _u64p])
         _sig(lib, "vkref_flat_search_mt", C.c_double,
@@ -197,6 +199,14 @@ class RefFlat(_Base):
         X = np.ascontiguousarray(X, np.float32)
         for i in range(X.shape[0]):
             self.lib.vkref_flat_add(self.h, X[i], int(i if labels is None else labels[i]))
+
+    def add_many_borrowed(self, X, first_label=0):
+        """Bulk ingest without copying: the index keeps pointers into X, which must stay alive (and unchanged)."""
+        assert X.dtype == np.float32 and X.flags["C_CONTIGUOUS"] and X.shape[1] == self.dim
+        self._borrowed = getattr(self, "_borrowed", []) + [X]
+        rc = self.lib.vkref_flat_add_many_borrowed(self.h, X, X.shape[0], int(first_label))
+        assert rc == 0
+        return rc
 
     def remove(self, label):
         return self.lib.vkref_flat_remove(self.h, int(label))

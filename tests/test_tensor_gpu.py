@@ -141,3 +141,48 @@ def test_tensor_pair_kernel_equals_exact_path(built, metric, N, D, B, k, monkeyp
     ix.SetSearchPath(V.PATH_TENSOR)
     d1, l1, _ = ix.SearchBatchRaw(Q, k)
     assert np.array_equal(l0, l1) and np.array_equal(_bits(d0), _bits(d1))
+
+
+def test_headline_shape_2M_rows_batch_1024_k100_vs_exact_scan_and_cpu_reference(built):
+    """The headline configuration's shape (768-d fp32, k=100, batch=1024, L2) at 2M rows — four query tiles x 37
+    slabs of the persistent tcgen05 kernel, thousands of tiles per CTA, publish rounds and trims at scale:
+    64 of the 1024 answers are compared bit for bit with the exact fp32-order scan, and 16 with the reference's own
+    hnswlib + simsimd on the host over the same rows (bruteforce.h:116-145, vector_base.cc:259-277).  bench.py
+    repeats the same two checks at the full 10M rows inside the driver-run line ("parity")."""
+    import torch
+    import valkey_search_b200 as V
+    from valkey_search_b200 import _lib as L
+
+    N, D, B, k = 2_000_000, 768, 1024, 100
+    dev = torch.device("cuda", 0)
+    lib = L.lib()
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N, max_batch=B)
+    X_host = np.empty((N, D), np.float32)
+    for blk in range(N // 500_000):
+        g = torch.Generator(device=dev)
+        g.manual_seed(4242 + blk)
+        Xb = torch.randn((500_000, D), generator=g, device=dev, dtype=torch.float32)
+        torch.cuda.synchronize()
+        L.check(lib.vkgpu_add_batch_device(ix.handle(), None, Xb.data_ptr(), Xb.shape[0]))
+        torch.from_numpy(X_host[blk * 500_000:(blk + 1) * 500_000]).copy_(Xb)
+        del Xb
+    Q = np.random.default_rng(77).standard_normal((B, D)).astype(np.float32)
+    ix.SetSearchPath(V.PATH_TENSOR)
+    d1, l1, n1 = ix.SearchBatchRaw(Q, k)
+    assert ix.stats().tensor_fallbacks == 0
+    assert (n1 == k).all()
+    sel = np.arange(0, B, 16)  # 64 queries spread over all four query tiles
+    ix.SetSearchPath(V.PATH_EXACT_FMA)
+    d0, l0, n0 = ix.SearchBatchRaw(Q[sel], k)
+    assert np.array_equal(l0, l1[sel]), np.argwhere(l0 != l1[sel])[:5]
+    assert np.array_equal(_bits(d0), _bits(d1[sel]))
+    if O.ref() is not None and hasattr(O.ref(), "vkref_flat_add_many_borrowed"):
+        cpu = O.RefFlat(D, O.L2, initial_cap=N)
+        cpu.add_many_borrowed(X_host)
+    else:
+        pytest.skip("needs oracle/_ref with the bulk ingest entry")
+    sel2 = np.arange(5, B, 64)  # 16 queries
+    _, dc, lc, nc = cpu.search_mt(Q[sel2], k, 16)
+    assert (nc == k).all()
+    assert np.array_equal(lc, l1[sel2]), np.argwhere(lc != l1[sel2])[:5]
+    assert np.array_equal(_bits(dc), _bits(d1[sel2]))
