@@ -808,7 +808,11 @@ static int HnswPerfMode(int argc, char **argv) {
   std::vector<uint32_t> on(batch);
   for (int setting = 0; setting < 4; setting++) {
     const bool set = setting & 1;
-    if (set) setenv(var, "1", 1); else unsetenv(var);
+    // VAR or VAR=VALUE: the second setting of each pair exports VALUE (default "1"), the first leaves VAR unset
+    const std::string vs(var);
+    const size_t eq = vs.find('=');
+    const std::string vname = vs.substr(0, eq), vval = eq == std::string::npos ? "1" : vs.substr(eq + 1);
+    if (set) setenv(vname.c_str(), vval.c_str(), 1); else unsetenv(vname.c_str());
     auto &d = set ? od2 : od;
     auto &l = set ? ol2 : ol;
     for (int w = 0; w < 3; w++)

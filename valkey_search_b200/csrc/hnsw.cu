@@ -58,9 +58,15 @@ struct HnswSearchParams {
   uint32_t rows_per_batch, row_stride_bytes, cand_cap;
   uint32_t need_flags;  // some node is tombstoned or a filter is present: resolve live/allowed per neighbour
   uint32_t merge_skip;  // sorted kernel: leave a list alone when the hop cannot change it (VKGPU_HNSW_NO_MERGE_SKIP=1: off)
-  uint32_t vis_tab_cap, vis_tab_shift;  // DIRECT variant: shared-memory visited table (entries, 32 - log2(entries))
+  uint32_t vis_tab_cap, vis_tab_shift;  // warp kernel: shared-memory visited table (entries, 32 - log2(entries))
+  uint32_t *redo;       // [B] warp kernel: 1 => the visited table filled up, the bitmap kernel answers this query
+  uint32_t only_redo;   // sorted kernel launched as that second pass: CTAs of unflagged queries exit at once
   unsigned long long *stats;
 };
+
+}  // namespace vkgpu
+#include "hnsw_warp.cuh"
+namespace vkgpu {
 
 namespace {
 
@@ -386,15 +392,7 @@ __device__ __forceinline__ unsigned long long hop_now() {
   } while (0)
 #endif
 
-// DIRECT (opt-in, VKGPU_HNSW_DIRECT=1; NOT yet measured or parity-run on a GPU — a round-2 candidate, see DESIGN.md
-// section 5 "left on the table"): the two round trips that dominate a hop are taken off the critical path.
-//   * visited test: an exact open-addressing table of node ids in shared memory (CAS insert, linear probing) instead
-//     of a returning atomic on the per-query bitmap in L2; when the table is three quarters full the search switches,
-//     between two hops, to "look up the table, insert into the bitmap" — the set stays exact, only slower.
-//   * distances: each 16-lane group reads its row straight from global memory with every load of a lane in flight at
-//     once (exact_dist_lane16_direct) instead of bulk copy -> mbarrier -> shared memory -> compute.
-// The lists, the order of every decision and therefore the results are those of the default kernel.
-template <bool L2, bool DIRECT>
+template <bool L2>
 __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearchParams p, uint32_t ccap) {
   extern __shared__ __align__(128) uint8_t sm[];
   const GraphView &g = p.g;
@@ -424,9 +422,7 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
   o += 7 * 32 * 4;
   o = (o + 15) & ~15u;
   uint64_t *bar = reinterpret_cast<uint64_t *>(sm + o);
-  volatile uint32_t *ctl = reinterpret_cast<volatile uint32_t *>(sm + o + 8);  // 14 words; [8] table fill, [9] table closed
-  uint32_t *vtab = reinterpret_cast<uint32_t *>(sm + o + 64);                  // DIRECT only
-  constexpr uint32_t kEmpty = 0xffffffffu;  // never a node id (ids < 0xffffffff, hnsw_import / hnsw_add_rows)
+  volatile uint32_t *ctl = reinterpret_cast<volatile uint32_t *>(sm + o + 8);  // 14 words
 
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const uint32_t b = blockIdx.x;
@@ -436,16 +432,13 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
   const uint32_t RB = p.rows_per_batch;
   const uint32_t row_bytes = g.Dp * 4;
 
+  if (p.only_redo) {  // second pass after the warp kernel: only the queries whose visited table filled up
+    if (!p.redo[b]) return;
+    for (uint64_t i = tid; i < p.vis_words; i += HT) vis[i] = 0;  // the bitmaps are not cleared by the host then
+  }
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
-  }
-  if constexpr (DIRECT) {
-    for (uint32_t i = tid; i < p.vis_tab_cap; i += HT) vtab[i] = kEmpty;
-    if (tid == 0) {
-      ctl[8] = 0;
-      ctl[9] = 0;
-    }
   }
   for (uint32_t i = tid; i < g.Dp / 4; i += HT)
     reinterpret_cast<float4 *>(q)[i] = reinterpret_cast<const float4 *>(p.Q + (size_t)b * g.Dp)[i];
@@ -453,15 +446,6 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
 
   uint32_t parity = 0;
   auto stage_and_dist = [&](uint32_t n) {  // distances from q to uvi[0..n) -> uvd[0..n)
-    if constexpr (DIRECT) {
-      for (uint32_t r0 = 0; r0 < n; r0 += HT / 16) {
-        const uint32_t r = r0 + (tid >> 4);
-        const bool act = r < n;
-        const float d = exact_dist_lane16_direct<L2>(g.X + (size_t)uvi[act ? r : 0] * g.Dp, q, g.Dp, tid & 15, act);
-        if (act && (tid & 15) == 0) uvd[r] = d;
-      }
-      __syncthreads();
-    } else {
     for (uint32_t base = 0; base < n; base += RB) {
       const uint32_t m = min(RB, n - base);
       if (warp == 0) {
@@ -481,7 +465,6 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
       }
       __syncthreads();
     }
-    }  // !DIRECT
   };
 
   // ---- entry point + greedy descent through the upper levels (hnswalg.h:1667-1697)
@@ -544,12 +527,7 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
       }
       candb[0][0].d = ok ? curdist : FLT_MAX;
       candb[0][0].id = ep;
-      if constexpr (DIRECT) {
-        vtab[(ep * 2654435761u) >> p.vis_tab_shift] = ep;
-        ctl[8] = 1;
-      } else {
-        atomicOr(&vis[ep >> 5], 1u << (ep & 31));
-      }
+      atomicOr(&vis[ep >> 5], 1u << (ep & 31));
     }
     top_n = ok ? 1 : 0;
     lower = ok ? curdist : FLT_MAX;
@@ -582,26 +560,8 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
         const uint32_t hdr = p.need_flags ? g.hdr0[id] : 0u;
         // (tried: a plain L2 load + fire-and-forget RED.OR instead of the returning atomic, the bitmap being
         //  private to the CTA - 253.9 K vs 251.8 K QPS, within noise; the returning atomic stays)
-        if constexpr (DIRECT) {
-          const bool closed = ctl[9] != 0;  // written by this warp's lane 0 at the end of an earlier hop
-          const uint32_t mask = p.vis_tab_cap - 1;
-          uint32_t h = (id * 2654435761u) >> p.vis_tab_shift;
-          bool found = false;
-          for (;;) {  // the table never fills (closed at 3/4), so a probe always ends at the id or at an empty slot
-            const uint32_t v = closed ? reinterpret_cast<volatile uint32_t *>(vtab)[h] : atomicCAS(&vtab[h], kEmpty, id);
-            if (v == id) {
-              found = true;
-              break;
-            }
-            if (v == kEmpty) break;  // open table: the CAS has just inserted the id
-            h = (h + 1) & mask;
-          }
-          if (closed && !found) found = (atomicOr(&vis[id >> 5], bit) & bit) != 0;
-          unv = !found;
-        } else {
         const uint32_t old = atomicOr(&vis[id >> 5], bit);
         unv = !(old & bit);
-        }
         flag = 1u;
         if (unv && p.need_flags) {
           bool ok = !(hdr & kHdrDeleted);
@@ -619,13 +579,6 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
         uvf[pos] = flag;
       }
       if (lane == 0) ctl[2] = __popc(bal);
-      if constexpr (DIRECT) {
-        if (lane == 0 && ctl[9] == 0) {  // every unvisited neighbour of this hop went into the table
-          const uint32_t fill = ctl[8] + __popc(bal);
-          ctl[8] = fill;
-          if (fill + 32 > p.vis_tab_cap - p.vis_tab_cap / 4) ctl[9] = 1;  // the next hop must still fit: close early
-        }
-      }
 #ifdef VKGPU_HNSW_TRACE
       HOP_T(h2);
       HOP_ADD(1, h0, h2);  // includes [0]
@@ -797,13 +750,12 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
   }
 }
 
-static size_t hnsw_sorted_smem_bytes(uint32_t Dp, uint32_t rows, uint32_t row_stride, uint32_t ef, uint32_t ccap,
-                                     uint32_t vis_tab_cap = 0) {
+static size_t hnsw_sorted_smem_bytes(uint32_t Dp, uint32_t rows, uint32_t row_stride, uint32_t ef, uint32_t ccap) {
   size_t o = ((size_t)Dp * 4 + 127) & ~size_t(127);
   o += (size_t)rows * row_stride;
   o += (size_t)2 * (ef + 32) * 8 + (size_t)2 * (ccap + 32) * 8 + 7 * 32 * 4;
   o = (o + 15) & ~size_t(15);
-  return o + 64 + (size_t)vis_tab_cap * 4;
+  return o + 64;
 }
 
 __global__ void hnsw_mark_deleted_kernel(uint32_t *hdr0, uint32_t id, uint32_t set) {
@@ -835,10 +787,10 @@ void hnsw_create(vkgpu_index_impl *ix) {
   }
   VK_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
   VK_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-  VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-  VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-  VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-  VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(hnsw_search_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+  VK_CUDA(cudaFuncSetAttribute(hnsw_search_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
 }
 
 void hnsw_destroy(vkgpu_index_impl *ix) {
@@ -927,8 +879,7 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
 
   // per-query visited bitmaps
   const uint64_t vis_words = (ix->n + 31) / 32;
-  c->scratch0.reserve((size_t)B * vis_words * 4);
-  VK_CUDA(cudaMemsetAsync(c->scratch0.p, 0, (size_t)B * vis_words * 4, s));
+  c->scratch0.reserve((size_t)B * vis_words * 4);  // cleared below only where the bitmap kernels run first
 
   // optional inline-filter bitmaps (src/query/search.cc:103-134): uploaded per query
   const uint8_t **d_allow_ptr = nullptr;
@@ -1026,30 +977,66 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
     if (rows >= (t > 1 ? 12u : 1u)) break;
   }
   rows = std::min<uint32_t>(rows, 32);
-  // DIRECT variant of the sorted kernel (opt-in, see the kernel's comment): no staging rows; the space goes to the
-  // visited table — the largest power of two (<= 16384 ids) that still lets four CTAs share an SM
-  bool direct = false;
-  if (sorted && getenv("VKGPU_HNSW_DIRECT") != nullptr) {
-    const size_t budget = sm_total / 4 - 1024;
-    uint32_t cap = 16384;
-    while (cap >= 1024 && fixed_total + (size_t)cap * 4 > budget) cap >>= 1;
-    if (cap >= 1024) {
-      direct = true;
-      rows = 0;
+  VK_REQUIRE(rows >= 1, VKGPU_ERR_UNSUPPORTED, "vector too large for the HNSW staging buffer");
+  hp.rows_per_batch = rows;
+  const size_t smem_bytes = sorted ? hnsw_sorted_smem_bytes(ix->Dp, rows, hp.row_stride_bytes, ef, ccap)
+                                   : hnsw_smem_layout(ix->Dp, rows, hp.row_stride_bytes, ef, hp.cand_cap, g->maxM0).total;
+
+  // Default for 2M <= 32: one WARP per query with the visited set in shared memory (hnsw_warp.cuh); the sorted CTA
+  // kernel then runs as a second pass over the queries whose table filled up (none at the usual ef).  The table
+  // holds every evaluated node (about 10 x ef of them): 32 x ef entries rounded up to a power of two, 3/4 usable.
+  // VKGPU_HNSW_WARP=0 sends everything to the CTA kernel (A/B runs and the parity test between the two).
+  bool warp = sorted && [] {
+    const char *e = getenv("VKGPU_HNSW_WARP");
+    return !(e && e[0] == '0');
+  }();
+  uint32_t wrows = 0;
+  size_t wsmem = 0;
+  if (warp) {
+    uint32_t cap = 2048;
+    while (cap < 32 * ef && cap < 32768) cap <<= 1;
+    const size_t wfixed = hnsw_warp_smem_bytes(ix->Dp, 0, ef, ccap, cap);
+    const uint32_t wstride = hnsw_warp_row_stride(ix->Dp);
+    // resident queries per SM: the whole batch in one wave when it fits (up to 8), with at least 8 staged rows (an
+    // average hop's worth); fewer per SM for wide rows
+    uint32_t wwant = std::min<uint32_t>(8, std::max<uint32_t>(1, (B + ix->num_sms - 1) / ix->num_sms));
+    for (uint32_t t = wwant; t >= 1; t--) {
+      const size_t budget = sm_total / t - 1024;
+      wrows = wfixed < budget ? (uint32_t)((budget - wfixed) / wstride) : 0;
+      if (wrows >= (t > 1 ? 8u : 1u)) break;
+    }
+    wrows = std::min<uint32_t>(wrows, 16);
+    if (wrows >= 1) {
       hp.vis_tab_cap = cap;
       hp.vis_tab_shift = 32;
       for (uint32_t c2 = cap; c2 > 1; c2 >>= 1) hp.vis_tab_shift--;
+      wsmem = hnsw_warp_smem_bytes(ix->Dp, wrows, ef, ccap, cap);
+      c->klimit.reserve((size_t)B * 4);
+    } else {
+      warp = false;
     }
   }
-  VK_REQUIRE(direct || rows >= 1, VKGPU_ERR_UNSUPPORTED, "vector too large for the HNSW staging buffer");
-  hp.rows_per_batch = rows;
-  const size_t smem_bytes = sorted ? hnsw_sorted_smem_bytes(ix->Dp, rows, hp.row_stride_bytes, ef, ccap, direct ? hp.vis_tab_cap : 0)
-                                   : hnsw_smem_layout(ix->Dp, rows, hp.row_stride_bytes, ef, hp.cand_cap, g->maxM0).total;
+  if (warp) {
+    hp.redo = c->klimit.as<uint32_t>();
+    VK_CUDA(cudaMemsetAsync(hp.redo, 0, (size_t)B * 4, s));
+  } else {
+    VK_CUDA(cudaMemsetAsync(c->scratch0.p, 0, (size_t)B * vis_words * 4, s));
+  }
 
   ix->prof_begin(c, KK_HNSW);
+  if (warp) {
+    HnswSearchParams wp = hp;
+    wp.rows_per_batch = wrows;
+    if (ix->metric_l2)
+      hnsw_search_warp_kernel<true><<<B, 32, wsmem, s>>>(wp, ccap);
+    else
+      hnsw_search_warp_kernel<false><<<B, 32, wsmem, s>>>(wp, ccap);
+    VK_CUDA(cudaGetLastError());
+    hp.only_redo = 1;
+    ix->kernels++;
+  }
   if (sorted) {
-    auto kern = ix->metric_l2 ? (direct ? hnsw_search_sorted_kernel<true, true> : hnsw_search_sorted_kernel<true, false>)
-                              : (direct ? hnsw_search_sorted_kernel<false, true> : hnsw_search_sorted_kernel<false, false>);
+    auto kern = ix->metric_l2 ? hnsw_search_sorted_kernel<true> : hnsw_search_sorted_kernel<false>;
     kern<<<B, HT, smem_bytes, s>>>(hp, ccap);
   } else if (ix->metric_l2) {
     hnsw_search_kernel<true><<<B, HT, smem_bytes, s>>>(hp);
@@ -1060,7 +1047,20 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   ix->prof_end(c, KK_HNSW);
   ix->kernels++;
 #ifdef VKGPU_HNSW_TRACE
-  if (sorted) {
+  if (warp) {
+    unsigned long long h[10];
+    VK_CUDA(cudaStreamSynchronize(s));
+    VK_CUDA(cudaMemcpyFromSymbol(h, g_whop_ns, sizeof(h)));
+    const double n = h[7] ? (double)h[7] : 1.0;
+    unsigned long long st[4];
+    VK_CUDA(cudaMemcpy(st, c->scratch3.p, sizeof(st), cudaMemcpyDeviceToHost));
+    fprintf(stderr, "[hnsw warp trace] query 0: %llu hops with work, %llu staging rounds (%u rows max); ns per hop: link row + visited %.0f, "
+            "cp.async issue %.0f, row wait %.0f, distances %.0f, sort %.0f, next-row request + result merge %.0f, candidate merge %.0f; "
+            "%llu queries sent to the bitmap kernel\n",
+            h[7], h[8], wrows, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, st[2]);
+    memset(h, 0, sizeof(h));
+    VK_CUDA(cudaMemcpyToSymbol(g_whop_ns, h, sizeof(h)));
+  } else if (sorted) {
     unsigned long long h[8];
     VK_CUDA(cudaStreamSynchronize(s));
     VK_CUDA(cudaMemcpyFromSymbol(h, g_hop_ns, sizeof(h)));

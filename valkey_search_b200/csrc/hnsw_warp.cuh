@@ -44,6 +44,30 @@ __host__ __device__ inline size_t hnsw_warp_smem_bytes(uint32_t Dp, uint32_t row
   return o + (size_t)tab_cap * 4;
 }
 
+// Per-phase time of the hop loop of query 0 (build with -DVKGPU_HNSW_TRACE; the host prints the averages):
+// [0] link row + visited table, [1] cp.async issue, [2] wait for the rows, [3] distances, [4] sort,
+// [5] next-row request + result merge, [6] candidate merge, [7] hops with work, [8] staging rounds.
+#ifdef VKGPU_HNSW_TRACE
+__device__ unsigned long long g_whop_ns[10];
+__device__ __forceinline__ unsigned long long whop_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define WHOP_T(var) const unsigned long long var = whop_now()
+#define WHOP_ADD(i, a, b) \
+  do {                    \
+    if (blockIdx.x == 0 && threadIdx.x == 0) g_whop_ns[i] += (b) - (a); \
+  } while (0)
+#else
+#define WHOP_T(var) \
+  do {              \
+  } while (0)
+#define WHOP_ADD(i, a, b) \
+  do {                    \
+  } while (0)
+#endif
+
 template <bool L2>
 __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchParams p, uint32_t ccap) {
   extern __shared__ __align__(128) uint8_t sm[];
@@ -55,15 +79,14 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
   o += (g.Dp * 4 + 127) & ~127u;
   uint8_t *stage = sm + o;
   o += RB * stride;
-  HEnt *topb[2], *candb[2];
-  topb[0] = reinterpret_cast<HEnt *>(sm + o);
-  o += (ef + 32) * 8;
-  topb[1] = reinterpret_cast<HEnt *>(sm + o);
-  o += (ef + 32) * 8;
-  candb[0] = reinterpret_cast<HEnt *>(sm + o);
-  o += (ccap + 32) * 8;
-  candb[1] = reinterpret_cast<HEnt *>(sm + o);
-  o += (ccap + 32) * 8;
+  // two buffers per list (merged from one into the other); addressed arithmetically: an array of pointers indexed by
+  // a run-time value would live in local memory
+  HEnt *const top0 = reinterpret_cast<HEnt *>(sm + o);
+  o += 2 * (ef + 32) * 8;
+  HEnt *const cand0 = reinterpret_cast<HEnt *>(sm + o);
+  o += 2 * (ccap + 32) * 8;
+  auto topb = [&](uint32_t i) { return top0 + i * (ef + 32); };
+  auto candb = [&](uint32_t i) { return cand0 + i * (ccap + 32); };
   uint32_t *uvi = reinterpret_cast<uint32_t *>(sm + o);  // unvisited neighbours of the hop, list order
   uint32_t *uvf = uvi + 32;                              // live + allowed?
   float *uvd = reinterpret_cast<float *>(uvf + 32);      // their distances
@@ -86,13 +109,19 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
   auto stage_and_dist = [&](uint32_t n) {
     for (uint32_t base = 0; base < n; base += RB) {
       const uint32_t m = min(RB, n - base);
+      WHOP_T(s0);
       for (uint32_t r = 0; r < m; r++) {
         const float *src = g.X + (size_t)uvi[base + r] * g.Dp;
         uint8_t *dst = stage + r * stride;
         for (uint32_t c = lane; c < g.Dp / 4; c += 32) cp_async16(dst + c * 16, src + c * 4);
       }
+      WHOP_T(s1);
       cp_async_wait_all();
       __syncwarp();
+      WHOP_T(s2);
+      WHOP_ADD(1, s0, s1);
+      WHOP_ADD(2, s1, s2);
+      WHOP_ADD(8, 0ull, 1ull);
       for (uint32_t r0 = 0; r0 < m; r0 += 8) {
         const float *rp[4];
         float acc[4];
@@ -151,6 +180,8 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
         }
       }
       __syncwarp();  // distances visible; the staging rows may be overwritten
+      WHOP_T(s3);
+      WHOP_ADD(3, s2, s3);
     }
   };
 
@@ -202,11 +233,11 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
     }
     if (lane == 0) {
       if (ok) {
-        topb[0][0].d = curdist;
-        topb[0][0].id = ep;
+        topb(0)[0].d = curdist;
+        topb(0)[0].id = ep;
       }
-      candb[0][0].d = ok ? curdist : FLT_MAX;
-      candb[0][0].id = ep;
+      candb(0)[0].d = ok ? curdist : FLT_MAX;
+      candb(0)[0].id = ep;
       vtab[(ep * 2654435761u) >> p.vis_tab_shift] = ep;
     }
     top_n = ok ? 1 : 0;
@@ -216,15 +247,19 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
   uint32_t pf_id = kEmpty, pf_nb = 0, pf_hdr = 0;  // link row requested ahead for the node expected next
   for (;;) {
     if (cand_h == cand_n) break;
-    const HEnt c = candb[cc][cand_h];
+    const HEnt c = candb(cc)[cand_h];
     if (c.d > lower && top_n == ef) break;  // hnswalg.h:407-409
     if (fill + 32 > tab_limit) {            // the visited table could overflow in this hop: bitmap kernel answers
-      if (lane == 0) p.redo[b] = 1;
+      if (lane == 0) {
+        p.redo[b] = 1;
+        atomicAdd(&p.stats[2], 1ull);
+      }
       return;
     }
     cand_h++;
     const uint32_t cur = c.id;
     n_hops++;
+    WHOP_T(h0);
     // phase 1: visited filter, list order preserved
     uint32_t id, cnt;
     if (cur == pf_id) {
@@ -269,8 +304,11 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
     }
     fill += nuv;
     __syncwarp();
+    WHOP_T(h1);
+    WHOP_ADD(0, h0, h1);
     stage_and_dist(nuv);
     n_dist += nuv;
+    WHOP_T(h2);
 
     // ---- sort the hop's neighbours by (distance, list order): 32-element bitonic network on shuffles
     float sd = lane < nuv ? uvd[lane] : FLT_MAX;
@@ -297,6 +335,8 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
     const uint32_t lb = __ballot_sync(0xffffffffu, live);
     const uint32_t n_live = __popc(lb);
     const uint32_t lrank = __popc(lb & ((1u << lane) - 1));
+    WHOP_T(h3);
+    WHOP_ADD(4, h2, h3);
 
     // ---- request the link row of the node that will be expanded next (see the file header)
     {
@@ -304,7 +344,7 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
       const uint32_t sid0 = __shfl_sync(0xffffffffu, sid, 0);
       uint32_t nid = sid0;
       if (cand_h < cand_n) {
-        const HEnt hd = candb[cc][cand_h];
+        const HEnt hd = candb(cc)[cand_h];
         if (!(sd0 < hd.d)) nid = hd.id;  // equal distances: the older entry leaves the list first
       }
       pf_id = nid;
@@ -319,8 +359,8 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
       __syncwarp();
       if (live) sld[lrank] = sd;
       __syncwarp();
-      const HEnt *A = topb[ct];
-      HEnt *Bf = topb[ct ^ 1];
+      const HEnt *A = topb(ct);
+      HEnt *Bf = topb(ct ^ 1);
       for (uint32_t i = lane; i < top_n; i += 32) {
         const HEnt a = A[i];
         uint32_t r = 0;
@@ -341,9 +381,11 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
       __syncwarp();
       top_n = min(top_n + n_live, ef);
       ct ^= 1;
-      if (top_n) lower = topb[ct][top_n - 1].d;
+      if (top_n) lower = topb(ct)[top_n - 1].d;
     }
     const bool full = top_n == ef;
+    WHOP_T(h4);
+    WHOP_ADD(5, h3, h4);
 
     // ---- merge the neighbours that can still matter into the candidate list ("<=": a neighbour that IS the new
     //      ef-th best was pushed by the reference when its turn came, the bound being looser then)
@@ -353,8 +395,8 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
         __syncwarp();
         if (lane < n_push) sld[32 + lane] = sd;
         __syncwarp();
-        const HEnt *Cw = candb[cc] + cand_h;
-        HEnt *Cn = candb[cc ^ 1];
+        const HEnt *Cw = candb(cc) + cand_h;
+        HEnt *Cn = candb(cc ^ 1);
         const uint32_t len = cand_n - cand_h;
         for (uint32_t i = lane; i < len; i += 32) {
           const HEnt a = Cw[i];
@@ -379,14 +421,17 @@ __global__ void __launch_bounds__(32) hnsw_search_warp_kernel(const HnswSearchPa
         cc ^= 1;
       }
     }
+    WHOP_T(h5);
+    WHOP_ADD(6, h4, h5);
+    WHOP_ADD(7, 0ull, 1ull);
   }
 
   // ---- the k best are the head of the ascending list; translate to labels and order equal distances by label
   //      (hnswalg.h:1715-1723, vector_base.cc:259-277)
   __syncwarp();
   const uint32_t nres = min(top_n, p.k);
-  const HEnt *top = topb[ct];
-  uint64_t *labs = reinterpret_cast<uint64_t *>(candb[cc ^ 1]);  // dead buffer (nres <= ef <= ccap) as label scratch
+  const HEnt *top = topb(ct);
+  uint64_t *labs = reinterpret_cast<uint64_t *>(candb(cc ^ 1));  // dead buffer (nres <= ef <= ccap) as label scratch
   for (uint32_t i = lane; i < nres; i += 32) labs[i] = g.labels[top[i].id];
   __syncwarp();
   for (uint32_t i = lane; i < nres; i += 32) {
