@@ -214,20 +214,48 @@ def count_mismatches(np, got, want, nq):
     return bad
 
 
-def hnsw_workload(args):
+def export_graph_arrays(ix, M):
+    """vkgpu_hnsw_export -> the flat interchange arrays (no per-node Python work: 10M nodes)."""
+    import numpy as np
+    from valkey_search_b200 import _lib as L
+    lib = L.lib()
+    n, blocks = C.c_uint64(), C.c_uint64()
+    L.check(lib.vkgpu_hnsw_export(ix.handle(), C.byref(n), C.byref(blocks), None, None, None, None, None, None, None,
+                                  None, None, None))
+    N, Bk = n.value, blocks.value
+    a = dict(levels=np.zeros(N, np.int32), labels=np.zeros(N, np.uint64), deleted=np.zeros(N, np.uint8),
+             links0=np.zeros((N, 2 * M), np.uint32), cnt0=np.zeros(N, np.uint32),
+             up_links=np.zeros((max(Bk, 1), M), np.uint32), up_cnt=np.zeros(max(Bk, 1), np.uint32),
+             up_off=np.zeros(N, np.uint64))
+    maxlevel, ep = C.c_int32(), C.c_uint32()
+    p = lambda x: x.ctypes.data_as(C.c_void_p)
+    L.check(lib.vkgpu_hnsw_export(ix.handle(), C.byref(n), C.byref(blocks), p(a["levels"]), p(a["labels"]),
+                                  p(a["deleted"]), p(a["links0"]), p(a["cnt0"]), p(a["up_links"]), p(a["up_cnt"]),
+                                  p(a["up_off"]), C.byref(maxlevel), C.byref(ep)))
+    a["maxlevel"], a["enterpoint"] = maxlevel.value, ep.value
+    return a
+
+
+def hnsw_workload(args, embedded=False):
     """BASELINE configs[2] shape: HNSW M=16 efSearch=128, 768-d fp32, k=10, batch=512 on one B200.  The graph is
     built on the GPU (single-GPU build, as the north star says); recall@10 is measured against exact FLAT ground
-    truth from the GPU FLAT path; the CPU arm searches the SAME graph (exported through vkgpu_hnsw_export and
-    loaded into the oracle) with all host threads, so QPS compares like for like and results must be identical."""
+    truth from the GPU FLAT path.  `--in-flight F` batches of 512 are kept in flight by F host threads, each through
+    its own vkgpu_search_batch_device call (the module's reader threads do the same through the batcher): a batch
+    ends with its slowest hop chain, so a single batch leaves most of the GPU idle for most of its duration;
+    the F=1 figure is reported next to it.  The CPU arm is the REFERENCE's hnswlib searching the SAME graph (exported
+    through vkgpu_hnsw_export and loaded by the reference's LoadIndex, validation on) with all host threads; its
+    results must be identical to the GPU's."""
+    import threading
     import numpy as np
     import torch
     import valkey_search_b200 as V
     from valkey_search_b200 import _lib as L
     import oracle_lib as O
 
-    N = args.rows if args.rows is not None else 1_000_000
+    N = args.hnsw_rows if embedded else (args.rows if args.rows is not None else 10_000_000)
     D, k, ef, M, efc = args.dim, (10 if args.k == 100 else args.k), args.ef, 16, 200
     B = 512 if args.batch == 1024 else args.batch
+    F = max(1, args.in_flight)
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     peaks = load_peaks()
@@ -235,8 +263,11 @@ def hnsw_workload(args):
     g = torch.Generator(device=dev)
     g.manual_seed(777)
     centres = torch.randn((1024, D), generator=g, device=dev) * 1.0
-    qa = torch.randint(0, 1024, (B,), generator=g, device=dev)
-    dQ = (centres[qa] + 0.3 * torch.randn((B, D), generator=g, device=dev)).contiguous()
+    # one batch of queries per slot in flight (different queries, same distribution)
+    dQs = []
+    for _ in range(F):
+        qa = torch.randint(0, 1024, (B,), generator=g, device=dev)
+        dQs.append((centres[qa] + 0.3 * torch.randn((B, D), generator=g, device=dev)).contiguous())
 
     def gen_rows(blk, rows):  # 1M-row blocks, seed 777 + 1 + block: the 10M corpus never exists twice in HBM
         gb = torch.Generator(device=dev)
@@ -249,7 +280,6 @@ def hnsw_workload(args):
     ix = V.VectorHNSW(D, V.DistanceMetric.L2, initial_cap=N, m=M, ef_construction=efc, ef_runtime=ef, max_batch=B)
     flat = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
     build_s = 0.0
-    X = None
     for blk in range(nblk):
         Xb = gen_rows(blk, min(BLK, N - blk * BLK))
         torch.cuda.synchronize()
@@ -257,52 +287,93 @@ def hnsw_workload(args):
         L.check(lib.vkgpu_add_batch_device(ix.handle(), None, Xb.data_ptr(), Xb.shape[0]))
         build_s += time.perf_counter() - t0
         L.check(lib.vkgpu_add_batch_device(flat.handle(), None, Xb.data_ptr(), Xb.shape[0]))
-        if nblk == 1:
-            X = Xb
         del Xb
     log(f"[hnsw] GPU build of {N} x {D}: {build_s:.1f}s ({N / build_s:.0f} inserts/s)")
     mk = lambda shape, dt: torch.empty(shape, dtype=dt, device=dev)
-    od, ol, on = mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32)
-    td, tl, tn = mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32)
-    L.check(lib.vkgpu_search_batch_device(flat.handle(), dQ.data_ptr(), B, k, 0, td.data_ptr(), tl.data_ptr(),
-                                          tn.data_ptr(), None))
-    W, K = max(args.warmup, 3), args.steps
-    for _ in range(W):
-        L.check(lib.vkgpu_search_batch_device(ix.handle(), dQ.data_ptr(), B, k, ef, od.data_ptr(), ol.data_ptr(),
+    outs = [(mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32)) for _ in range(F)]
+    truth = []
+    for f in range(F):
+        td, tl, tn = mk((B, k), torch.float32), mk((B, k), torch.int64), mk((B,), torch.int32)
+        L.check(lib.vkgpu_search_batch_device(flat.handle(), dQs[f].data_ptr(), B, k, 0, td.data_ptr(), tl.data_ptr(),
+                                              tn.data_ptr(), None))
+        truth.append(tl.cpu().numpy())
+    del flat
+
+    def call(f):
+        od, ol, on = outs[f]
+        L.check(lib.vkgpu_search_batch_device(ix.handle(), dQs[f].data_ptr(), B, k, ef, od.data_ptr(), ol.data_ptr(),
                                               on.data_ptr(), None))
-    torch.cuda.synchronize()
+
+    def run(steps, slots):
+        """`steps` batches over `slots` host threads (slot f runs steps f, f+slots, ...); device time of the lot"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        if slots == 1:
+            for _ in range(steps):
+                call(0)
+        else:
+            ts = [threading.Thread(target=lambda f=f: [call(f) for _ in range(f, steps, slots)]) for f in range(slots)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    W, K = max(args.warmup, 3), max(args.steps, 1)
+    # per-slot work counters (the library reports the most recent call's): one untimed pass per slot
+    slot_bytes, slot_hops, slot_evals = [], [], []
+    for f in range(F):
+        call(f)
+        st = ix.stats()
+        slot_hops.append(st.hops)
+        slot_evals.append(st.distance_evals)
+        slot_bytes.append(float(st.distance_evals) * D * 4 + float(st.hops) * 136)
+    for _ in range(W):
+        run(F, F)
+    # ---- single batch in flight: per-launch kernel time and the F=1 figure
     L.check(lib.vkgpu_set_profiling(ix.handle(), 1))
+    st0 = ix.stats()
+    ms_single = run(K, 1)
+    tm = L.Timings()
+    L.check(lib.vkgpu_get_timings(ix.handle(), C.byref(tm)))
+    single_launches = int(ix.stats().kernels_launched - st0.kernels_launched)
+    L.check(lib.vkgpu_set_profiling(ix.handle(), 0))
+    hnsw_ms, hnsw_n = tm.ms[4], int(tm.launches[4])
+    # ---- F batches in flight: the headline of this workload
+    KF = K * F
     st0 = ix.stats()
     sampler = ClockSampler(0)
     sampler.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(K):
-        L.check(lib.vkgpu_search_batch_device(ix.handle(), dQ.data_ptr(), B, k, ef, od.data_ptr(), ol.data_ptr(),
-                                              on.data_ptr(), None))
-    e1.record()
-    torch.cuda.synchronize()
-    ms_total = e0.elapsed_time(e1)
+    ms_total = run(KF, F)
     clocks = sampler.stop()
-    tm = L.Timings()
-    L.check(lib.vkgpu_get_timings(ix.handle(), C.byref(tm)))
     st1 = ix.stats()
-    value = B * K / (ms_total / 1e3)
-    truth = tl.cpu().numpy()
-    got = ol.cpu().numpy()
-    recall = float(np.mean([len(set(got[b].tolist()) & set(truth[b].tolist())) / float(k) for b in range(B)]))
-    # e2e through host buffers
-    hQ = dQ.cpu().numpy()
-    hd, hl, hn = np.empty((B, k), np.float32), np.empty((B, k), np.uint64), np.empty(B, np.uint32)
-    t0 = time.perf_counter()
-    for _ in range(K):
-        L.check(lib.vkgpu_search_batch(ix.handle(), hQ.ctypes.data, B, k, ef, None, 0, hd.ctypes.data, hl.ctypes.data,
+    value = B * KF / (ms_total / 1e3)
+    bytes_total = sum(slot_bytes[s % F] for s in range(KF))
+    ach = bytes_total / (ms_total / 1e3) / 1e9
+    got = [o[1].cpu().numpy() for o in outs]
+    recall = float(np.mean([len(set(got[f][b].tolist()) & set(truth[f][b].tolist())) / float(k)
+                            for f in range(F) for b in range(B)]))
+    # e2e through host buffers, same number of batches in flight
+    hQs = [q.cpu().numpy() for q in dQs]
+    houts = [(np.empty((B, k), np.float32), np.empty((B, k), np.uint64), np.empty(B, np.uint32)) for _ in range(F)]
+
+    def hcall(f):
+        hd, hl, hn = houts[f]
+        L.check(lib.vkgpu_search_batch(ix.handle(), hQs[f].ctypes.data, B, k, ef, None, 0, hd.ctypes.data, hl.ctypes.data,
                                        hn.ctypes.data))
-    e2e = B * K / (time.perf_counter() - t0)
-    hnsw_ms, hnsw_n = tm.ms[4], int(tm.launches[4])
-    evals = (st1.distance_evals) / max(B, 1)   # counters hold the last call's totals
-    bytes_algo = float(st1.distance_evals) * D * 4 + float(st1.hops) * 136
-    ach = bytes_algo / (hnsw_ms / max(hnsw_n, 1) / 1e3) / 1e9
+    for f in range(F):
+        hcall(f)
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=lambda f=f: [hcall(f) for _ in range(f, KF, F)]) for f in range(F)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    e2e = B * KF / (time.perf_counter() - t0)
+    same_paths = all(np.array_equal(houts[f][1].astype(np.int64), got[f]) for f in range(F))
     traffic = None
     try:  # measured DRAM traffic of this exact configuration, if an ncu capture of it is committed
         ent = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(
@@ -310,51 +381,77 @@ def hnsw_workload(args):
         traffic = ent["bytes"] if ent else None
     except Exception:
         pass
+    single_ach = slot_bytes[0] / (hnsw_ms / max(hnsw_n, 1) / 1e3) / 1e9 if hnsw_n else None
     roofline = {"bound": "hbm", "kernel": "hnsw_search_sorted_kernel<L2> (one CTA per query, TMA-staged rows, sorted lists)",
                 "achieved": ach, "peak": peaks["hbm"], "unit": "GB/s", "frac": ach / peaks["hbm"], "traffic": traffic,
-                "note": "algorithmic row bytes of ONE launch / its time (ncu at 1M rows: 1.85 GB of DRAM reads for 1.91 GB "
-                        "algorithmic, L2 hit rate 10 %) - the kernel is bound by the latency of the dependent hop chain, "
-                        "not by HBM bandwidth",
-                "peak_source": f"{peaks['source']} copy bandwidth", "bytes_per_launch": bytes_algo,
-                "distance_evals_per_query": evals, "hops_per_query": st1.hops / max(B, 1),
-                "kernel_ms_avg": hnsw_ms / max(hnsw_n, 1)}
+                "note": f"algorithmic row + link bytes of all {KF} launches / the timed region ({F} launches overlap on "
+                        "the device, so a per-launch duration is not the launch's own cost); a single launch is bound by "
+                        "the latency of its slowest dependent hop chain, not by HBM bandwidth",
+                "peak_source": f"{peaks['source']} copy bandwidth", "bytes_per_launch": slot_bytes[0],
+                "distance_evals_per_query": slot_evals[0] / B, "hops_per_query": slot_hops[0] / B,
+                "single_launch": {"kernel_ms_avg": hnsw_ms / max(hnsw_n, 1), "achieved": single_ach,
+                                  "frac": single_ach / peaks["hbm"] if single_ach else None}}
     cpu_base = None
-    if not args.no_cpu_baseline and X is not None:  # the CPU arm needs the corpus on the host: single-block runs only
-        sys.path.insert(0, os.path.join(ROOT, "tests"))
-        from test_hnsw_gpu import export_graph
-        ix._m = M
-        gexp = export_graph(ix)
-        n = len(gexp["levels"])
-        off = np.zeros(n, np.uint64)
-        blocks = 0
-        for i in range(n):
-            off[i] = blocks
-            blocks += max(int(gexp["levels"][i]), 0)
-        upl = np.zeros((max(blocks, 1), M), np.uint32)
-        upc = np.zeros(max(blocks, 1), np.uint32)
-        for (i, lv), ids in gexp["upper"].items():
-            b = int(off[i]) + lv - 1
-            upc[b] = ids.size
-            upl[b, : ids.size] = ids
-        orc = O.PortHnsw(D, O.L2, M, efc, ef)
-        orc.import_arrays(gexp["levels"], gexp["labels"], gexp["deleted"], gexp["links0"], gexp["cnt0"], upl, upc, off,
-                          gexp["maxlevel"], gexp["enterpoint"], X.cpu().numpy())
-        threads = host_threads()
-        secs, cd, cl, cn = orc.search_mt(hQ, k, ef, threads)
-        same = bool(np.array_equal(cl, hl) and np.array_equal(cd.view(np.uint32), hd.view(np.uint32)))
-        cpu_base = {"value": B / secs, "unit": UNIT, "cores": threads, "kind": "port",
-                    "sample": f"{B} queries, same GPU-built graph loaded into the CPU oracle, {threads} threads, "
-                              f"{secs:.2f}s; results identical to the GPU's: {same}"}
+    if not args.no_cpu_baseline:
+        need = N * D * 4 * 2.2 + N * 400
+        if mem_available_bytes() < need:
+            cpu_base = {"value": None, "unit": UNIT, "kind": "reference",
+                        "sample": f"skipped: the reference's hnswlib needs {need / 2**30:.0f} GiB of host memory for {N} rows"}
+        else:
+            t0 = time.perf_counter()
+            arr = export_graph_arrays(ix, M)
+            hX = np.empty((N, D), np.float32)
+            for blk in range(nblk):
+                lo, hi = blk * BLK, min((blk + 1) * BLK, N)
+                hX[lo:hi] = gen_rows(blk, hi - lo).cpu().numpy()
+            orc, err = O.ref_hnsw_from_arrays(D, O.L2, M, efc, ef, arr, hX)
+            if orc is None:
+                raise SystemExit(f"the reference refused the GPU-built graph: {err}")
+            del hX
+            log(f"[hnsw] reference hnswlib loaded the GPU-built graph (LoadIndex, validation on) in "
+                f"{time.perf_counter() - t0:.1f}s")
+            threads = host_threads()
+            Qall = np.concatenate(hQs, axis=0)
+            orc.search_mt(Qall[: min(Qall.shape[0], 4 * threads)], k, ef, threads)  # warm
+            reps = 0
+            secs = 0.0
+            while secs < 10.0 and reps < 50:
+                s1, cd, cl, cn = orc.search_mt(Qall, k, ef, threads)
+                secs += s1
+                reps += 1
+            gd = np.concatenate([h[0] for h in houts], axis=0)
+            gl = np.concatenate([h[1] for h in houts], axis=0)
+            mism = int(np.sum(np.any(cl != gl, axis=1) | np.any(cd.view(np.uint32) != gd.view(np.uint32), axis=1)))
+            truth_all = np.concatenate(truth, axis=0)
+            cpu_recall = float(np.mean([len(set(cl[b].tolist()) & set(truth_all[b].tolist())) / float(k)
+                                        for b in range(Qall.shape[0])]))
+            cpu_base = {"value": Qall.shape[0] * reps / secs, "unit": UNIT, "cores": threads, "kind": "reference",
+                        "recall_at_k": cpu_recall,
+                        "sample": f"{reps} x {Qall.shape[0]} queries, the reference's hnswlib + simsimd on the same GPU-built "
+                                  f"graph (its own LoadIndex, validation on), {threads} threads (one query per thread at a "
+                                  f"time), {secs:.2f}s; queries whose ids or distance bits differ from the GPU's: {mism}",
+                        "mismatching_queries": mism}
     line = {"metric": f"kNN QPS @ recall (HNSW M=16 ef={ef}, {N}x{D} fp32, k={k}, batch={B})", "value": value,
-            "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": ms_total / K, "higher_is_better": True,
+            "unit": UNIT, "n_gpus": 1, "steps": KF, "warmup": W * F, "ms_per_step": ms_total / KF, "higher_is_better": True,
             "scaling": "replicas only", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic clustered Gaussian (1024 centres, sigma 0.3), torch seed 777",
-            "config": {"workload": f"HNSW M=16 efc=200 ef={ef} {N}x{D} fp32 k={k} batch={B} (BASELINE configs[2] shape at "
-                                   f"{N} rows)", "rows": N},
+            "config": {"workload": f"HNSW M=16 efc=200 ef={ef} {N}x{D} fp32 k={k} batch={B} (BASELINE configs[2]"
+                                   f"{'' if N == 10_000_000 else f' shape at {N} rows'}), {F} batches in flight",
+                       "rows": N, "batches_in_flight": F},
+            "single_batch": {"value": B * K / (ms_single / 1e3), "unit": UNIT, "ms_per_step": ms_single / K,
+                             "gpu_launches": single_launches},
             "recall_at_k": recall, "build_seconds": build_s, "build_inserts_per_s": N / build_s,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 12 + B * 4},
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": B * D * 4, "d2h_bytes_per_step": B * k * 12 + B * 4,
+                    "host_and_device_calls_agree": bool(same_paths)},
             "gpu_launches": int(st1.kernels_launched - st0.kernels_launched), "roofline": roofline,
             "cpu_baseline": cpu_base, "clocks": clocks}
+    if cpu_base and cpu_base.get("value"):
+        line["vs_cpu_reference"] = {"ratio": value / cpu_base["value"], "e2e_ratio": e2e / cpu_base["value"],
+                                    "single_batch_ratio": line["single_batch"]["value"] / cpu_base["value"]}
+    del ix
+    torch.cuda.empty_cache()
+    if embedded:
+        return line
     emit(line)
     return 0
 
@@ -528,7 +625,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=None,
-                    help="default: 10M (flat, serve), 1M (hnsw), 2M (prefilter)")
+                    help="default: 10M (flat, serve, hnsw), 2M (prefilter)")
     ap.add_argument("--dim", type=int, default=768)
     ap.add_argument("--k", type=int, default=100)
     ap.add_argument("--batch", type=int, default=1024)
@@ -542,6 +639,9 @@ def main():
     ap.add_argument("--workload", default="flat", choices=["flat", "hnsw", "prefilter", "serve"],
                     help="flat = BASELINE configs[1] (the driver's default); hnsw = configs[2] at --rows")
     ap.add_argument("--ef", type=int, default=128)
+    ap.add_argument("--in-flight", type=int, default=4, help="hnsw: batches kept in flight (host threads)")
+    ap.add_argument("--hnsw-rows", type=int, default=1_000_000, help="rows of the HNSW measurement embedded in the flat line")
+    ap.add_argument("--no-secondary", action="store_true", help="flat: skip the embedded HNSW / pre-filter measurements")
     ap.add_argument("--window-us", type=int, default=300)
     ap.add_argument("--host-lists", action="store_true", help="prefilter: ship label lists per call")
     args = ap.parse_args()

@@ -479,3 +479,132 @@ void *vkref_hnsw_load(const uint8_t *buf, uint64_t len, size_t dim, int metric, 
 }
 
 }  // extern "C"
+
+// The reference's LoadIndex fed with a graph held in the interchange arrays of include/vkgpu.h (vkgpu_hnsw_export):
+// the chunks of the stream SaveIndex would have written (hnswalg.h:808-862) are produced one at a time, so a 10M-row
+// graph built on the GPU is handed to the reference's own hnswlib without a second copy of the corpus.  This is how
+// bench.py times the reference CPU search on the very graph the GPU searches.
+namespace {
+struct ArrayStream : public hnswlib::InputStream {
+  size_t dim, M;
+  uint64_t n, efc, cap;
+  const int32_t *levels;
+  const uint64_t *labels;
+  const uint8_t *deleted;
+  const uint32_t *links0, *cnt0, *up_links, *up_cnt;
+  const uint64_t *up_off;
+  int32_t maxlevel;
+  uint32_t enterpoint;
+  const float *vecs;
+  uint64_t elem = 0, list = 0;
+  int phase = 0;  // 0 header, 1 level-0 records, 2 list sizes / lists
+  bool size_sent = false;
+  absl::StatusOr<std::unique_ptr<std::string>> LoadChunk() override {
+    const size_t maxM0 = 2 * M, links0_bytes = maxM0 * 4 + 4, vec_bytes = dim * 4, stride = M * 4 + 4;
+    if (phase == 0) {
+      hnswlib::data_model::HNSWIndexHeader h;
+      h.set_offset_level_0(0);
+      h.set_max_elements(std::max<uint64_t>(cap, n));
+      h.set_curr_element_count(n);
+      h.set_serialize_size_data_per_element(links0_bytes + vec_bytes + 8);
+      h.set_label_offset(((links0_bytes + 7) & ~size_t(7)) + sizeof(char *));
+      h.set_offset_data(links0_bytes);
+      h.set_max_level(maxlevel);
+      h.set_enterpoint_node(enterpoint);
+      h.set_max_m(M);
+      h.set_max_m_0(maxM0);
+      h.set_m(M);
+      h.set_mult(1 / std::log(1.0 * M));
+      h.set_ef_construction(efc);
+      auto out = std::make_unique<std::string>();
+      h.SerializeToString(out.get());
+      phase = n ? 1 : 3;
+      return out;
+    }
+    if (phase == 1) {
+      auto out = std::make_unique<std::string>(links0_bytes + vec_bytes + 8, '\0');
+      const uint64_t i = elem++;
+      const uint32_t word = (cnt0[i] & 0xffffu) | (deleted && deleted[i] ? (1u << 16) : 0u);
+      std::memcpy(out->data(), &word, 4);
+      std::memcpy(out->data() + 4, links0 + i * maxM0, maxM0 * 4);
+      std::memcpy(out->data() + links0_bytes, vecs + i * dim, vec_bytes);
+      std::memcpy(out->data() + links0_bytes + vec_bytes, labels + i, 8);
+      if (elem == n) phase = 2;
+      return out;
+    }
+    if (phase == 2) {
+      const uint64_t i = list;
+      const uint64_t level = levels[i] > 0 ? (uint64_t)levels[i] : 0;
+      const uint64_t bytes = level * stride;
+      if (!size_sent) {
+        auto out = std::make_unique<std::string>(reinterpret_cast<const char *>(&bytes), 8);
+        if (bytes) {
+          size_sent = true;
+        } else if (++list == n) {
+          phase = 3;
+        }
+        return out;
+      }
+      auto out = std::make_unique<std::string>(bytes, '\0');
+      for (uint64_t l = 0; l < level; l++) {
+        const uint64_t b = up_off[i] + l;
+        const uint32_t word = up_cnt[b] & 0xffffu;
+        std::memcpy(out->data() + l * stride, &word, 4);
+        std::memcpy(out->data() + l * stride + 4, up_links + b * M, M * 4);
+      }
+      size_sent = false;
+      if (++list == n) phase = 3;
+      return out;
+    }
+    return absl::NotFoundError("no more chunks");
+  }
+};
+}  // namespace
+
+extern "C" void *vkref_hnsw_from_arrays(size_t dim, int metric, size_t M, size_t ef_construction, size_t ef_runtime,
+                                         uint64_t n, const int32_t *levels, const uint64_t *labels,
+                                         const uint8_t *deleted, const uint32_t *links0, const uint32_t *cnt0,
+                                         const uint32_t *up_links, const uint32_t *up_cnt, const uint64_t *up_off,
+                                         int32_t maxlevel, uint32_t enterpoint, const float *vecs, int validate,
+                                         char *err, size_t errcap) {
+  auto fail = [&](const std::string &m) -> void * {
+    if (err && errcap) {
+      std::strncpy(err, m.c_str(), errcap - 1);
+      err[errcap - 1] = 0;
+    }
+    return nullptr;
+  };
+  ArrayStream in;
+  in.dim = dim;
+  in.M = M;
+  in.n = n;
+  in.efc = std::max(ef_construction, M);
+  in.cap = n;
+  in.levels = levels;
+  in.labels = labels;
+  in.deleted = deleted;
+  in.links0 = links0;
+  in.cnt0 = cnt0;
+  in.up_links = up_links;
+  in.up_cnt = up_cnt;
+  in.up_off = up_off;
+  in.maxlevel = n ? maxlevel : -1;
+  in.enterpoint = n ? enterpoint : 0xffffffffu;
+  in.vecs = vecs;
+  auto g = std::make_unique<LoadedHnsw>();
+  g->space = MakeSpace(dim, metric);
+  g->store.dim = dim;
+  g->block_size = 10240;
+  g->allow_replace_deleted = false;
+  g->tracker.store = &g->store;
+  try {
+    g->algo = std::make_unique<hnswlib::HierarchicalNSW<float>>(g->space.get());
+    g->algo->allow_replace_deleted_ = false;
+    auto st = g->algo->LoadIndex(in, g->space.get(), n, &g->tracker, M, validate != 0);
+    if (!st.ok()) return fail(std::string(st.message()));
+    g->algo->setEf(ef_runtime);
+  } catch (const std::exception &e) {
+    return fail(std::string("HNSWLib error while loading an index: ") + e.what());
+  }
+  return static_cast<Hnsw *>(g.release());
+}

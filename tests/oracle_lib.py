@@ -127,6 +127,10 @@ def ref():
         _sig(lib, "vkref_hnsw_save", C.c_uint64, [C.c_void_p, C.c_void_p, C.c_uint64])
         _sig(lib, "vkref_hnsw_load", C.c_void_p,
              [C.c_char_p, C.c_uint64, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_char_p, C.c_size_t])
+        if hasattr(lib, "vkref_hnsw_from_arrays"):  # absent from a libvkref.so built before this round
+            _sig(lib, "vkref_hnsw_from_arrays", C.c_void_p,
+                 [C.c_size_t, C.c_int, C.c_size_t, C.c_size_t, C.c_size_t, C.c_uint64] + [C.c_void_p] * 8 +
+                 [C.c_int32, C.c_uint32, C.c_void_p, C.c_int, C.c_char_p, C.c_size_t])
         _ref = lib
     return _ref
 
@@ -450,6 +454,47 @@ def ref_hnsw_load(chunks, dim, metric, initial_cap, expected_m, validate=True, e
     data = pack_chunks(chunks)
     err = C.create_string_buffer(512)
     hnd = lib.vkref_hnsw_load(data, len(data), dim, metric, initial_cap, expected_m, 1 if validate else 0, ef, err, 512)
+    if not hnd:
+        return None, err.value.decode()
+    obj = RefHnsw.__new__(RefHnsw)
+    obj.lib, obj.dim, obj.h = lib, dim, hnd
+    return obj, None
+
+
+def graph_arrays(g):
+    """graph() dict -> the flat interchange arrays of include/vkgpu.h (upper lists as blocks of M ids)."""
+    n, M = int(g["info"][0]), int(g["info"][3])
+    levels = g["levels"].astype(np.int32)
+    off = np.zeros(n, np.uint64)
+    blocks = 0
+    for i in range(n):
+        off[i] = blocks
+        blocks += max(int(levels[i]), 0)
+    up_links = np.zeros((max(blocks, 1), M), np.uint32)
+    up_cnt = np.zeros(max(blocks, 1), np.uint32)
+    for (i, lv), ids in g["upper"].items():
+        b = int(off[i]) + lv - 1
+        up_cnt[b] = ids.size
+        up_links[b, : ids.size] = ids
+    return dict(levels=levels, labels=g["labels"].astype(np.uint64), deleted=g["deleted"].astype(np.uint8),
+                links0=np.ascontiguousarray(g["links0"], np.uint32), cnt0=g["cnt0"].astype(np.uint32),
+                up_links=up_links, up_cnt=up_cnt, up_off=off, maxlevel=int(g["info"][1]), enterpoint=int(g["info"][2]))
+
+
+def ref_hnsw_from_arrays(dim, metric, M, efc, ef, a, vecs, validate=True):
+    """The reference's LoadIndex (hnswalg.h:886-1139, validation on by default) fed chunk by chunk from interchange
+    arrays `a` (keys of graph_arrays / vkgpu_hnsw_export) — no intermediate copy of the stream.  Returns
+    (RefHnsw, None) or (None, error message)."""
+    lib = ref()
+    if lib is None or not hasattr(lib, "vkref_hnsw_from_arrays"):
+        return None, "oracle/_ref/libvkref.so lacks vkref_hnsw_from_arrays (rebuild it where /root/reference exists)"
+    vecs = np.ascontiguousarray(vecs, np.float32)
+    n = int(a["levels"].shape[0])
+    assert vecs.shape == (n, dim)
+    keep = [np.ascontiguousarray(a[k]) for k in ("levels", "labels", "deleted", "links0", "cnt0", "up_links", "up_cnt", "up_off")]
+    err = C.create_string_buffer(512)
+    hnd = lib.vkref_hnsw_from_arrays(dim, metric, M, efc, ef, n, *[x.ctypes.data for x in keep], int(a["maxlevel"]),
+                                     int(a["enterpoint"]), vecs.ctypes.data, 1 if validate else 0, err, 512)
     if not hnd:
         return None, err.value.decode()
     obj = RefHnsw.__new__(RefHnsw)

@@ -93,3 +93,28 @@ def test_threaded_search_matches_single_thread(ref):
     _, d1, l1, n1 = pf.search_mt(Q, 10, 4)
     _, d2, l2, n2 = rf.search_mt(Q, 10, 4)
     assert np.array_equal(l1, l2) and np.array_equal(_bits(d1), _bits(d2)) and np.array_equal(n1, n2)
+
+
+def test_reference_load_from_interchange_arrays_equals_the_original(ref):
+    """bench.py hands a GPU-built graph to the reference's own hnswlib through vkref_hnsw_from_arrays (the reference's
+    LoadIndex fed chunk by chunk, validation on).  On a graph the reference built itself, the re-loaded index must
+    answer every query exactly like the original, tombstones included."""
+    rng = np.random.default_rng(5)
+    n, d, M, efc, ef, k = 1500, 48, 8, 60, 40, 10
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Q = rng.standard_normal((40, d)).astype(np.float32)
+    h = O.RefHnsw(d, O.L2, M=M, efc=efc, ef=ef, initial_cap=n)
+    h.add_many(X)
+    for lab in range(3, n, 17):
+        h.mark_delete(lab)
+    a = O.graph_arrays(h.graph())
+    h2, err = O.ref_hnsw_from_arrays(d, O.L2, M, efc, ef, a, X)
+    assert err is None, err
+    assert list(h2.info()[:5]) == list(h.info()[:5])
+    for q in Q:
+        d1, l1 = h.search(q, k, ef)
+        d2, l2 = h2.search(q, k, ef)
+        assert np.array_equal(l1, l2) and np.array_equal(d1.view(np.uint32), d2.view(np.uint32))
+    a["links0"][5, 0] = n + 7  # a neighbour id beyond the element count must fail the reference's validation
+    bad, err = O.ref_hnsw_from_arrays(d, O.L2, M, efc, ef, a, X)
+    assert bad is None and "validation failed" in err

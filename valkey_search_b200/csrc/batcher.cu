@@ -93,10 +93,10 @@ void Batcher::run() {
       requests_ += B;
     }
     for (BatchRequest *r : batch) {
-      {
-        std::lock_guard<std::mutex> lk(r->mu);
-        r->done = true;
-      }
+      // notify under the lock: the request lives on the waiter's stack and is gone as soon as the waiter has seen
+      // `done`, which it cannot before this thread lets go of r->mu
+      std::lock_guard<std::mutex> lk(r->mu);
+      r->done = true;
       r->cv.notify_one();
     }
   }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <mutex>
 #include <string>
 
 namespace vkgpu {
@@ -20,6 +21,22 @@ struct CudaFail {
     cudaError_t vk_e_ = (expr);                                         \
     if (vk_e_ != cudaSuccess) throw ::vkgpu::CudaFail{vk_e_, #expr, __FILE__, __LINE__}; \
   } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per device: `first()` is true once per device ordinal (the
+// current one), so that a second index on another GPU of the same process opts its kernels in as well.
+struct PerDeviceOnce {
+  std::mutex mu;
+  uint64_t done = 0;
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return true;
+    std::lock_guard<std::mutex> lk(mu);
+    const uint64_t bit = 1ull << (dev & 63);
+    if (done & bit) return false;
+    done |= bit;
+    return true;
+  }
+};
 
 // ---------------------------------------------------------------- ordered float keys
 // Monotone map float -> u32 such that a < b  <=>  ord(a) < ord(b) for all non-NaN values; the canonical

@@ -791,11 +791,10 @@ void launch_topk_select_merge(uint32_t B, cudaStream_t stream, const MergeParams
 // exact (distance,label) merge: selection kernel with all ties kept; plain repeated sorting when the lists are so
 // many that their lengths do not fit beside the sort buffer
 void launch_topk_merge(uint32_t B, cudaStream_t stream, const MergeParams &p) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr;
+  if (attr.first()) {
     VK_CUDA(cudaFuncSetAttribute(topk_merge_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     VK_CUDA(cudaFuncSetAttribute(topk_select_merge_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
   }
   const size_t smem_sel = (size_t)p.sort_n * sizeof(Cand) + 2048 * 4 + (size_t)p.slabs * 4;
   if (smem_sel <= 200 * 1024) {

@@ -14,6 +14,7 @@
 // bit-identical to the CPU module, not just recall-equivalent.
 #include "hnsw.h"
 
+#include <atomic>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -41,6 +42,7 @@ struct Hnsw {
   std::vector<uint64_t> h_up_off;
   uint64_t num_deleted = 0;
   uint32_t rng = 100;  // std::default_random_engine(100), hnswalg.h:149
+  std::atomic<int> active_searches{0};  // hnsw_search calls in progress (they share the SMs)
 };
 
 // ------------------------------------------------------------------------------------------------ kernel
@@ -58,15 +60,8 @@ struct HnswSearchParams {
   uint32_t rows_per_batch, row_stride_bytes, cand_cap;
   uint32_t need_flags;  // some node is tombstoned or a filter is present: resolve live/allowed per neighbour
   uint32_t merge_skip;  // sorted kernel: leave a list alone when the hop cannot change it (VKGPU_HNSW_NO_MERGE_SKIP=1: off)
-  uint32_t vis_tab_cap, vis_tab_shift;  // warp kernel: shared-memory visited table (entries, 32 - log2(entries))
-  uint32_t *redo;       // [B] warp kernel: 1 => the visited table filled up, the bitmap kernel answers this query
-  uint32_t only_redo;   // sorted kernel launched as that second pass: CTAs of unflagged queries exit at once
   unsigned long long *stats;
 };
-
-}  // namespace vkgpu
-#include "hnsw_warp.cuh"
-namespace vkgpu {
 
 namespace {
 
@@ -432,10 +427,6 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
   const uint32_t RB = p.rows_per_batch;
   const uint32_t row_bytes = g.Dp * 4;
 
-  if (p.only_redo) {  // second pass after the warp kernel: only the queries whose visited table filled up
-    if (!p.redo[b]) return;
-    for (uint64_t i = tid; i < p.vis_words; i += HT) vis[i] = 0;  // the bitmaps are not cleared by the host then
-  }
   if (tid == 0) {
     mbar_init(bar, 1);
     fence_mbar_init();
@@ -789,8 +780,6 @@ void hnsw_create(vkgpu_index_impl *ix) {
   VK_CUDA(cudaFuncSetAttribute(hnsw_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
   VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
   VK_CUDA(cudaFuncSetAttribute(hnsw_search_sorted_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-  VK_CUDA(cudaFuncSetAttribute(hnsw_search_warp_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-  VK_CUDA(cudaFuncSetAttribute(hnsw_search_warp_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
 }
 
 void hnsw_destroy(vkgpu_index_impl *ix) {
@@ -879,7 +868,7 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
 
   // per-query visited bitmaps
   const uint64_t vis_words = (ix->n + 31) / 32;
-  c->scratch0.reserve((size_t)B * vis_words * 4);  // cleared below only where the bitmap kernels run first
+  c->scratch0.reserve((size_t)B * vis_words * 4);
 
   // optional inline-filter bitmaps (src/query/search.cc:103-134): uploaded per query
   const uint8_t **d_allow_ptr = nullptr;
@@ -969,12 +958,27 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   const size_t fixed_total = sorted ? hnsw_sorted_smem_bytes(ix->Dp, 0, hp.row_stride_bytes, ef, ccap)
                                     : hnsw_smem_layout(ix->Dp, 0, hp.row_stride_bytes, ef, hp.cand_cap, g->maxM0).total;
   const size_t sm_total = ix->smem_max + 1024;
-  uint32_t want = std::min<uint32_t>(4, std::max<uint32_t>(1, (B + ix->num_sms - 1) / ix->num_sms));
+  // Queries of the searches running right now share the SMs: a lone batch wants few CTAs per SM with room for a whole
+  // hop's rows (its duration is its slowest hop chain), while several batches in flight want as many resident queries
+  // as shared memory allows (measured at 1M x 768, 8 batches of 512 in flight: 670 K QPS at 4 CTAs/SM with 14 staged
+  // rows, 916 K at 8 with 5 — profiles/r2_hnsw_occupancy_sweep.log).
+  struct ActiveScope {
+    std::atomic<int> &a;
+    int now;
+    explicit ActiveScope(std::atomic<int> &x) : a(x), now(++x) {}
+    ~ActiveScope() { --a; }
+  } active(g->active_searches);
+  const uint64_t in_flight = (uint64_t)B * (uint64_t)std::max(active.now, 1);
+  uint32_t want = (uint32_t)std::min<uint64_t>(8, std::max<uint64_t>(1, (in_flight + ix->num_sms - 1) / ix->num_sms));
   uint32_t rows = 0;
+  int force_rows = 0;
+  if (const char *e = getenv("VKGPU_HNSW_PER_SM")) want = std::max(1, atoi(e));    // experiments only
+  if (const char *e = getenv("VKGPU_HNSW_MIN_ROWS")) force_rows = std::max(1, atoi(e));
   for (uint32_t t = want; t >= 1; t--) {
     const size_t budget = sm_total / t - 1024;
     rows = fixed_total < budget ? (uint32_t)((budget - fixed_total) / hp.row_stride_bytes) : 0;
-    if (rows >= (t > 1 ? 12u : 1u)) break;
+    const uint32_t min_rows = force_rows ? (uint32_t)force_rows : t > 4 ? 4u : t > 1 ? 12u : 1u;
+    if (rows >= (t > 1 ? min_rows : 1u)) break;
   }
   rows = std::min<uint32_t>(rows, 32);
   VK_REQUIRE(rows >= 1, VKGPU_ERR_UNSUPPORTED, "vector too large for the HNSW staging buffer");
@@ -982,59 +986,9 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   const size_t smem_bytes = sorted ? hnsw_sorted_smem_bytes(ix->Dp, rows, hp.row_stride_bytes, ef, ccap)
                                    : hnsw_smem_layout(ix->Dp, rows, hp.row_stride_bytes, ef, hp.cand_cap, g->maxM0).total;
 
-  // Default for 2M <= 32: one WARP per query with the visited set in shared memory (hnsw_warp.cuh); the sorted CTA
-  // kernel then runs as a second pass over the queries whose table filled up (none at the usual ef).  The table
-  // holds every evaluated node (about 10 x ef of them): 32 x ef entries rounded up to a power of two, 3/4 usable.
-  // VKGPU_HNSW_WARP=0 sends everything to the CTA kernel (A/B runs and the parity test between the two).
-  bool warp = sorted && [] {
-    const char *e = getenv("VKGPU_HNSW_WARP");
-    return !(e && e[0] == '0');
-  }();
-  uint32_t wrows = 0;
-  size_t wsmem = 0;
-  if (warp) {
-    uint32_t cap = 2048;
-    while (cap < 32 * ef && cap < 32768) cap <<= 1;
-    const size_t wfixed = hnsw_warp_smem_bytes(ix->Dp, 0, ef, ccap, cap);
-    const uint32_t wstride = hnsw_warp_row_stride(ix->Dp);
-    // resident queries per SM: the whole batch in one wave when it fits (up to 8), with at least 8 staged rows (an
-    // average hop's worth); fewer per SM for wide rows
-    uint32_t wwant = std::min<uint32_t>(8, std::max<uint32_t>(1, (B + ix->num_sms - 1) / ix->num_sms));
-    for (uint32_t t = wwant; t >= 1; t--) {
-      const size_t budget = sm_total / t - 1024;
-      wrows = wfixed < budget ? (uint32_t)((budget - wfixed) / wstride) : 0;
-      if (wrows >= (t > 1 ? 8u : 1u)) break;
-    }
-    wrows = std::min<uint32_t>(wrows, 16);
-    if (wrows >= 1) {
-      hp.vis_tab_cap = cap;
-      hp.vis_tab_shift = 32;
-      for (uint32_t c2 = cap; c2 > 1; c2 >>= 1) hp.vis_tab_shift--;
-      wsmem = hnsw_warp_smem_bytes(ix->Dp, wrows, ef, ccap, cap);
-      c->klimit.reserve((size_t)B * 4);
-    } else {
-      warp = false;
-    }
-  }
-  if (warp) {
-    hp.redo = c->klimit.as<uint32_t>();
-    VK_CUDA(cudaMemsetAsync(hp.redo, 0, (size_t)B * 4, s));
-  } else {
-    VK_CUDA(cudaMemsetAsync(c->scratch0.p, 0, (size_t)B * vis_words * 4, s));
-  }
+  VK_CUDA(cudaMemsetAsync(c->scratch0.p, 0, (size_t)B * vis_words * 4, s));
 
   ix->prof_begin(c, KK_HNSW);
-  if (warp) {
-    HnswSearchParams wp = hp;
-    wp.rows_per_batch = wrows;
-    if (ix->metric_l2)
-      hnsw_search_warp_kernel<true><<<B, 32, wsmem, s>>>(wp, ccap);
-    else
-      hnsw_search_warp_kernel<false><<<B, 32, wsmem, s>>>(wp, ccap);
-    VK_CUDA(cudaGetLastError());
-    hp.only_redo = 1;
-    ix->kernels++;
-  }
   if (sorted) {
     auto kern = ix->metric_l2 ? hnsw_search_sorted_kernel<true> : hnsw_search_sorted_kernel<false>;
     kern<<<B, HT, smem_bytes, s>>>(hp, ccap);
@@ -1047,20 +1001,7 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   ix->prof_end(c, KK_HNSW);
   ix->kernels++;
 #ifdef VKGPU_HNSW_TRACE
-  if (warp) {
-    unsigned long long h[10];
-    VK_CUDA(cudaStreamSynchronize(s));
-    VK_CUDA(cudaMemcpyFromSymbol(h, g_whop_ns, sizeof(h)));
-    const double n = h[7] ? (double)h[7] : 1.0;
-    unsigned long long st[4];
-    VK_CUDA(cudaMemcpy(st, c->scratch3.p, sizeof(st), cudaMemcpyDeviceToHost));
-    fprintf(stderr, "[hnsw warp trace] query 0: %llu hops with work, %llu staging rounds (%u rows max); ns per hop: link row + visited %.0f, "
-            "cp.async issue %.0f, row wait %.0f, distances %.0f, sort %.0f, next-row request + result merge %.0f, candidate merge %.0f; "
-            "%llu queries sent to the bitmap kernel\n",
-            h[7], h[8], wrows, h[0] / n, h[1] / n, h[2] / n, h[3] / n, h[4] / n, h[5] / n, h[6] / n, st[2]);
-    memset(h, 0, sizeof(h));
-    VK_CUDA(cudaMemcpyToSymbol(g_whop_ns, h, sizeof(h)));
-  } else if (sorted) {
+  if (sorted) {
     unsigned long long h[8];
     VK_CUDA(cudaStreamSynchronize(s));
     VK_CUDA(cudaMemcpyFromSymbol(h, g_hop_ns, sizeof(h)));
@@ -1176,7 +1117,12 @@ void hnsw_import(vkgpu_index_impl *ix, uint64_t n, const int32_t *levels, const 
   g->enterpoint = enterpoint;
   ix->h_labels.assign(labels, labels + n);
   ix->slot_of.clear();
-  for (uint64_t i = 0; i < n; i++) ix->slot_of.set(labels[i], (uint32_t)i);  // hnswalg.h:1040-1056: last slot wins
+  // hnswalg.h:1040-1056: a label may sit on several slots in files of older versions — the first slot keeps the
+  // mapping unless a later slot with the same label is LIVE (a tombstoned duplicate never takes it over)
+  for (uint64_t i = 0; i < n; i++) {
+    uint32_t prev;
+    if (!ix->slot_of.get(labels[i], &prev) || !(deleted && deleted[i])) ix->slot_of.set(labels[i], (uint32_t)i);
+  }
   ix->n = n;
 }
 

@@ -525,12 +525,21 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     k_eff = (uint32_t)std::min<uint64_t>(k, ix->n);
     bool use_tensor = false;
     if (ix->flat_path == VKGPU_PATH_TENSOR) use_tensor = true;
-    if (ix->flat_path == VKGPU_PATH_AUTO && k_eff <= 128 && tensor_path_cheaper(ix, B)) {
+    if (ix->flat_path == VKGPU_PATH_AUTO && k_eff <= 128 && !ix->tensor_unavailable && tensor_path_cheaper(ix, B)) {
       // first large batch: build the bf16 mirror (searches only read the fp32 rows, so this is safe under
-      // the shared lock; tensor_mu makes it happen once)
+      // the shared lock; tensor_mu makes it happen once).  No room for the mirror: the exact scan answers, for good.
       std::lock_guard<std::mutex> tl(ix->tensor_mu);
-      if (!ix->tensor_ready) tensor_prepare(ix);
-      use_tensor = true;
+      if (!ix->tensor_ready && !ix->tensor_unavailable) {
+        try {
+          tensor_prepare(ix);
+        } catch (const CudaFail &f) {
+          if (f.err != cudaErrorMemoryAllocation) throw;
+          ix->tensor_unavailable = true;
+        } catch (const std::bad_alloc &) {
+          ix->tensor_unavailable = true;
+        }
+      }
+      use_tensor = ix->tensor_ready;
     }
     if (use_tensor && tensor_path_supported(ix, B, k_eff))
       tensor_search_device(ix, c, B, k_eff);

@@ -152,6 +152,7 @@ struct vkgpu_index_impl {
   DevBuf dXh;      // [phys_cap][Dp] bf16
   DevBuf dNorm;    // [phys_cap] fp32 squared norms (of the bf16-rounded rows)
   bool tensor_ready = false;
+  bool tensor_unavailable = false;  // AUTO: the mirror did not fit in HBM, the exact scan answers from now on
   void *tensor_state = nullptr;  // tensor_path.cu private state
   void *batcher = nullptr;       // Batcher* when cfg.batch_window_us != 0
   std::mutex sets_mu;

@@ -819,23 +819,35 @@ void tensor_move_row(vkgpu_index_impl *ix, uint64_t from, uint64_t to) {
                           ix->mut_stream));
 }
 
+void tensor_release(vkgpu_index_impl *ix);
 void tensor_prepare(vkgpu_index_impl *ix) {
   if (ix->tensor_ready) return;
+  // The mirror costs +50 % of the corpus: if it does not fit, nothing is published, what was allocated is given
+  // back and the caller's error says so; AUTO latches `tensor_unavailable` and keeps answering with the exact scan.
   TensorState *t = new TensorState();
   t->Dh = dh_of(ix->Dp);
   ix->tensor_state = t;
-  t->max_norm.reserve(4);
-  VK_CUDA(cudaMemsetAsync(t->max_norm.p, 0, 4, ix->mut_stream));
-  const uint64_t rows = std::max<uint64_t>(ix->phys_cap, 1);
-  ix->dXh.reserve(rows * (size_t)t->Dh * 2);
-  ix->dNorm.reserve(rows * 4);
-  tensor_refresh_rows(ix, 0, ix->n);
-  VK_CUDA(cudaStreamSynchronize(ix->mut_stream));
-  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<true, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-  VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-  VK_CUDA(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-  VK_CUDA(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+  try {
+    t->max_norm.reserve(4);
+    VK_CUDA(cudaMemsetAsync(t->max_norm.p, 0, 4, ix->mut_stream));
+    const uint64_t rows = std::max<uint64_t>(ix->phys_cap, 1);
+    ix->dXh.reserve(rows * (size_t)t->Dh * 2);
+    ix->dNorm.reserve(rows * 4);
+    tensor_refresh_rows(ix, 0, ix->n);
+    VK_CUDA(cudaStreamSynchronize(ix->mut_stream));
+    static PerDeviceOnce attr;
+    if (attr.first()) {
+      VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+      VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<true, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+      VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+      VK_CUDA(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      VK_CUDA(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    }
+  } catch (...) {
+    (void)cudaGetLastError();  // an allocation failure is sticky only until read
+    tensor_release(ix);
+    throw;
+  }
   ix->tensor_ready = true;
 }
 
