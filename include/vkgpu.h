@@ -169,6 +169,12 @@ int vkgpu_search_batch(vkgpu_index *h, const float *Q, uint32_t B, uint32_t k, u
  * (a cudaStream_t, NULL = the library's stream for this call, synchronised before return). */
 int vkgpu_search_batch_device(vkgpu_index *h, const float *d_Q, uint32_t B, uint32_t k, uint32_t ef,
                               float *d_out_dist, uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream);
+/* Same with a per-query candidate restriction (filters is NULL, or B entries whose pointers are HOST pointers, or
+ * device_set ids) and a deadline: the entry a sharded search calls on each shard, so that the per-shard results of a
+ * hybrid query stay in HBM until they are merged (src/query/search.cc:401-481 behind src/query/fanout.cc:159-220). */
+int vkgpu_search_batch_device_filtered(vkgpu_index *h, const float *d_Q, uint32_t B, uint32_t k, uint32_t ef,
+                                       const vkgpu_filter *filters, uint64_t deadline_ns, float *d_out_dist,
+                                       uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream);
 /* ComputeDistanceFromRecordImpl (vector_base.h:239-241, vector_flat.cc:257-271, vector_hnsw.cc:370-383):
  * distance from q to each listed label; unknown labels yield NaN. */
 int vkgpu_distances(vkgpu_index *h, const float *q, const uint64_t *labels, uint64_t n, float *out_dist);
@@ -188,6 +194,38 @@ int vkgpu_merge_topk_device(int device, const float *d_dist, const uint64_t *d_l
 uint64_t vkgpu_packed_result_bytes(uint32_t B, uint32_t k);
 int vkgpu_merge_topk_packed_device(int device, const void *d_packed, uint32_t G, uint32_t B, uint32_t k,
                                    float *d_out_dist, uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream);
+
+/* ---- multi-GPU in ONE process: a row-sharded index over G devices --------------------------------------------
+ * What the C++ module calls when the box has several GPUs: one handle, rows spread over the devices, every search
+ * fanned out to all shards and merged — the single-process form of src/query/fanout.cc:159-220 (PerformSearchFanoutAsync
+ * + the coordinator's merge), with NVLink peer loads in place of the gRPC hop.  Each shard is a complete vkgpu_index
+ * (vkgpu_sharded_shard hands it out, e.g. to keep per-shard TAG / NUMERIC device sets next to the rows they describe,
+ * as every node of a reference cluster keeps the attribute indexes of its own keys).
+ * cfg->device is ignored; cfg->initial_cap is the capacity of the whole index.  devices: CUDA ordinals, 1..16. */
+typedef struct vkgpu_sharded vkgpu_sharded;
+int vkgpu_sharded_create(const vkgpu_config *cfg, const int32_t *devices, uint32_t n_devices, vkgpu_sharded **out);
+void vkgpu_sharded_destroy(vkgpu_sharded *s);
+uint32_t vkgpu_sharded_shards(const vkgpu_sharded *s);
+vkgpu_index *vkgpu_sharded_shard(vkgpu_sharded *s, uint32_t shard);   /* borrowed: do not destroy */
+int vkgpu_sharded_peer_access(const vkgpu_sharded *s);                /* 1: the merge reads peer HBM directly */
+/* AddRecord / ModifyRecord / RemoveRecord by label (vector_base.cc:310-358 above each shard): a label that exists is
+ * updated on the shard that holds it; new rows go to the least-loaded shards.  labels == NULL: next free labels. */
+int vkgpu_sharded_add_batch(vkgpu_sharded *s, const uint64_t *labels, const float *vecs, uint64_t n);
+/* bulk load of rows already resident on the shard's own device */
+int vkgpu_sharded_add_batch_device(vkgpu_sharded *s, uint32_t shard, const uint64_t *labels, const float *d_vecs,
+                                   uint64_t n);
+int vkgpu_sharded_modify(vkgpu_sharded *s, uint64_t label, const float *vec);
+int vkgpu_sharded_remove(vkgpu_sharded *s, uint64_t label);
+int vkgpu_sharded_get(vkgpu_sharded *s, uint64_t label, float *out_vec);
+int vkgpu_sharded_shard_of(vkgpu_sharded *s, uint64_t label, uint32_t *out_shard);
+uint64_t vkgpu_sharded_count(vkgpu_sharded *s);
+/* vkgpu_search_batch over all shards.  shard_filters: NULL, or one entry per shard, each NULL or B filters for THAT
+ * shard (its own device_set ids / label lists): the pre-filter of a hybrid query is evaluated where the rows live
+ * (src/query/search.cc:401-481 on every node of the fan-out).  Result = the single-index answer: the k best of the
+ * union by (distance, label). */
+int vkgpu_sharded_search_batch(vkgpu_sharded *s, const float *Q, uint32_t B, uint32_t k, uint32_t ef,
+                               const vkgpu_filter *const *shard_filters, uint64_t deadline_ns, float *out_dist,
+                               uint64_t *out_labels, uint32_t *out_n);
 
 /* ---- FLAT interchange ("next" row N3) ------------------------------------------------------------------ */
 /* Rows [first_slot, first_slot+n) in SLOT order with their labels: what BruteforceSearch::SaveIndex walks

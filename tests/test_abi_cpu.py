@@ -12,7 +12,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 def test_header_symbols_are_exported(built):
     from valkey_search_b200 import _lib as L
     header = open(os.path.join(ROOT, "include", "vkgpu.h")).read()
-    declared = set(re.findall(r"^(?:int|void|uint64_t|const char \*)\s*(vkgpu_[a-z0-9_]+)\(", header, re.M))
+    declared = set(re.findall(r"^(?:int|void|uint32_t|uint64_t|const char \*|vkgpu_index \*)\s*(vkgpu_[a-z0-9_]+)\(", header, re.M))
     assert declared, "no declarations parsed"
     lib = C.CDLL(L.LIB_PATH)
     missing = [s for s in sorted(declared) if not hasattr(lib, s)]

@@ -88,6 +88,8 @@ SYMBOLS = {
     "vkgpu_search_batch": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Filter), C.c_uint64,
                                      _P, _P, _P]),
     "vkgpu_search_batch_device": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
+    "vkgpu_search_batch_device_filtered": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Filter),
+                                                     C.c_uint64, _P, _P, _P, _P]),
     "vkgpu_distances": (C.c_int, [_P, _P, _P, C.c_uint64, _P]),
     "vkgpu_merge_topk_device": (C.c_int, [C.c_int, _P, _P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
     "vkgpu_flat_export": (C.c_int, [_P, C.c_uint64, C.c_uint64, _P, _P]),
@@ -110,6 +112,19 @@ SYMBOLS = {
     "vkgpu_set_profiling": (C.c_int, [_P, C.c_int]),
     "vkgpu_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "vkgpu_device_corpus": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    "vkgpu_sharded_create": (C.c_int, [C.POINTER(Config), _P, C.c_uint32, C.POINTER(_P)]),
+    "vkgpu_sharded_destroy": (None, [_P]),
+    "vkgpu_sharded_shards": (C.c_uint32, [_P]),
+    "vkgpu_sharded_shard": (_P, [_P, C.c_uint32]),
+    "vkgpu_sharded_peer_access": (C.c_int, [_P]),
+    "vkgpu_sharded_add_batch": (C.c_int, [_P, _P, _P, C.c_uint64]),
+    "vkgpu_sharded_add_batch_device": (C.c_int, [_P, C.c_uint32, _P, _P, C.c_uint64]),
+    "vkgpu_sharded_modify": (C.c_int, [_P, C.c_uint64, _P]),
+    "vkgpu_sharded_remove": (C.c_int, [_P, C.c_uint64]),
+    "vkgpu_sharded_get": (C.c_int, [_P, C.c_uint64, _P]),
+    "vkgpu_sharded_shard_of": (C.c_int, [_P, C.c_uint64, C.POINTER(C.c_uint32)]),
+    "vkgpu_sharded_count": (C.c_uint64, [_P]),
+    "vkgpu_sharded_search_batch": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, C.c_uint64, _P, _P, _P]),
 }
 
 _lib = None

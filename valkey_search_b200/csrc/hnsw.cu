@@ -874,7 +874,6 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   const uint8_t **d_allow_ptr = nullptr;
   uint64_t *d_allow_bits = nullptr;
   if (filters) {
-    VK_REQUIRE(!out_on_device, VKGPU_ERR_UNSUPPORTED, "filtered search needs host outputs");
     size_t total = 0;
     std::vector<size_t> offs(B);
     for (uint32_t b = 0; b < B; b++) {

@@ -467,7 +467,6 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     //  * labels     : labels -> slots on the host (unknown labels skipped, vector_base.cc:513-516; duplicates
     //                 collapse), uploaded
     //  * bitmap     : host bitmap -> slots on the host
-    VK_REQUIRE(!out_on_device, VKGPU_ERR_UNSUPPORTED, "filtered search needs host outputs");
     std::vector<uint32_t> slots;
     std::vector<uint64_t> ptrs(B, 0), lens(B, 0), host_off(B, ~0ull);
     uint64_t longest = 0;
@@ -501,7 +500,12 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
       longest = std::max<uint64_t>(longest, lens[b]);
     }
     if (longest == 0) {  // no key qualifies for any query of the batch: empty replies (search.cc:457-481 with no keys)
-      for (uint32_t b = 0; b < B; b++) out_n[b] = 0;
+      if (out_on_device) {
+        VK_CUDA(cudaMemsetAsync(out_n, 0, (size_t)B * 4, c->cur));
+        VK_CUDA(cudaStreamSynchronize(c->cur));
+      } else {
+        for (uint32_t b = 0; b < B; b++) out_n[b] = 0;
+      }
       ix->searches += B;
       return;
     }
@@ -899,15 +903,23 @@ int vkgpu_search(vkgpu_index *ix, const float *q, uint32_t k, uint32_t ef, const
 
 int vkgpu_search_batch_device(vkgpu_index *ix, const float *d_Q, uint32_t B, uint32_t k, uint32_t ef,
                               float *d_out_dist, uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream) {
+  return vkgpu_search_batch_device_filtered(ix, d_Q, B, k, ef, nullptr, 0, d_out_dist, d_out_labels, d_out_n, cuda_stream);
+}
+
+int vkgpu_search_batch_device_filtered(vkgpu_index *ix, const float *d_Q, uint32_t B, uint32_t k, uint32_t ef,
+                                       const vkgpu_filter *filters, uint64_t deadline_ns, float *d_out_dist,
+                                       uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream) {
   return guarded([&] {
     VK_REQUIRE(ix && d_Q && d_out_dist && d_out_labels && d_out_n, VKGPU_ERR_INVALID, "null argument");
     VK_REQUIRE(B >= 1, VKGPU_ERR_INVALID, "empty batch");
+    VK_REQUIRE(deadline_ns == 0 || now_ns() < deadline_ns, VKGPU_ERR_CANCELLED, "Search operation cancelled due to timeout");
     std::shared_lock<std::shared_mutex> lk(ix->rw);
     VK_CUDA(cudaSetDevice(ix->device));
     if (ix->cfg.algo == VKGPU_FLAT)
-      flat_search(ix, d_Q, true, B, k, nullptr, d_out_dist, d_out_labels, d_out_n, true, (cudaStream_t)cuda_stream);
+      flat_search(ix, d_Q, true, B, k, filters, d_out_dist, d_out_labels, d_out_n, true, (cudaStream_t)cuda_stream);
     else
-      hnsw_search(ix, d_Q, true, B, k, ef, nullptr, d_out_dist, d_out_labels, d_out_n, true);
+      hnsw_search(ix, d_Q, true, B, k, ef, filters, d_out_dist, d_out_labels, d_out_n, true);
+    VK_REQUIRE(deadline_ns == 0 || now_ns() < deadline_ns, VKGPU_ERR_CANCELLED, "Search operation cancelled due to timeout");
   });
 }
 
