@@ -6,8 +6,9 @@ No GPU: numpy restatements of what the kernels compute.
    values over the slabs is an upper bound of the global K'-th smallest score, so gating on it never drops a row
    of the true top-K'.
 2. The margin proof.  With operands rounded to bf16 and products accumulated in fp32, |approx - exact| <= e with
-   e = err_coef * |q| * max|x| (+ the kernel's absolute slack); hence if approx[K'] > approx[k] + 2e no row outside
-   the K' survivors can belong to the exact top-k."""
+   e = err_coef * |q| * max|x| (+ the kernel's absolute slack); the survivors are re-ranked exactly, and if
+   approx[K'] - e > (exact k-th best among the survivors) no row outside the K' survivors can belong to the exact
+   top-k (rerank_kernel; the fp32 rounding of the reference's own distance is a further (1 - rho) on the left)."""
 import numpy as np
 import pytest
 
@@ -70,14 +71,50 @@ def test_bf16_score_error_is_within_the_kernels_bound(metric, D, scale):
 
 
 def test_margin_rule_keeps_the_exact_topk():
-    """If approx[K'] > approx[k] + 2e (approx ascending), every exact top-k row is among the K' best by approx."""
+    """Acceptance test of rerank_kernel: gK - e > dk, with gK the K'-th smallest approximate score and dk the exact
+    k-th best among the K' survivors.  Whenever it holds, the exact top-k of ALL rows is the exact top-k of the
+    survivors — for random and for adversarial perturbations bounded by e."""
     rng = np.random.default_rng(3)
     N, k, kprime = 20000, 100, 384
-    exact = rng.standard_normal(N)
-    for e in (0.0005, 0.002, 0.01):
-        approx = exact + rng.uniform(-e, e, N)          # any perturbation bounded by e
+    accepted = 0
+    for trial in range(60):
+        exact = rng.standard_normal(N)
+        e = float(rng.choice([0.0005, 0.002, 0.01, 0.03]))
+        if trial % 3 == 0:
+            approx = exact + rng.uniform(-e, e, N)
+        elif trial % 3 == 1:   # adversarial: the best rows look as bad as allowed, the next ones as good as allowed
+            approx = exact.copy()
+            order_x = np.argsort(exact)
+            approx[order_x[:k]] += e
+            approx[order_x[k:]] -= e
+        else:                  # extreme values only
+            approx = exact + e * rng.choice([-1.0, 1.0], N)
         order = np.argsort(approx)
-        a_sorted = approx[order]
-        if a_sorted[kprime - 1] > a_sorted[k - 1] + 2 * e:   # the kernel's acceptance test
-            survivors = set(order[:kprime].tolist())
-            assert set(np.argsort(exact)[:k].tolist()) <= survivors
+        surv = order[:kprime]
+        gK = approx[order[kprime - 1]]
+        dk = np.sort(exact[surv])[k - 1]
+        if gK - e > dk:
+            accepted += 1
+            want = np.argsort(exact)[:k]
+            got = surv[np.argsort(exact[surv])[:k]]
+            assert np.array_equal(np.sort(want), np.sort(got))
+            # strictly: every outsider is beyond dk
+            outsiders = order[kprime:]
+            assert exact[outsiders].min() > dk
+    assert accepted >= 10
+
+
+def test_new_rule_accepts_whatever_the_old_rule_accepted():
+    """gK > gk + 2e (the round-1 test on approximate scores alone) implies gK - e > dk: the re-ranked k-th distance is
+    at most gk + e.  The new rule flags fewer queries for the exact-scan fallback, never more."""
+    rng = np.random.default_rng(9)
+    N, k, kprime = 5000, 50, 214
+    for _ in range(200):
+        exact = rng.standard_normal(N)
+        e = float(rng.choice([0.001, 0.01, 0.05]))
+        approx = exact + rng.uniform(-e, e, N)
+        order = np.argsort(approx)
+        gk, gK = approx[order[k - 1]], approx[order[kprime - 1]]
+        dk = np.sort(exact[order[:kprime]])[k - 1]
+        if gK > gk + 2 * e:
+            assert gK - e > dk

@@ -749,12 +749,28 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankParams p
     p.out_n[b] = nout;
     uint32_t flag = 0;
     if (n >= p.kprime && (uint64_t)p.kprime < p.n_rows) {
-      // survivors = the K' smallest approximate scores; rows outside have approx >= a[K'-1]
+      // Proof that no row OUTSIDE the K' survivors belongs to the reference's top k.  Such a row i has an approximate
+      // score >= gK (the K'-th smallest), hence a true score s_i >= gK - e, where e bounds |approximate - true|:
+      // bf16 rounding of both operands and the tensor core's fp32 accumulation (err_coef |q| max|x|), plus the fp32
+      // rounding of the stored norms and of |q|^2.  The reference itself computes its distance in fp32 (16 lanes of
+      // Dp/16 fused multiply-adds, then 4 adds): relative error rho on a sum of non-negative terms for L2, absolute
+      // error rho |q||x| on the dot product for IP.  The row stays out if that lower bound on ITS reference distance
+      // is strictly above dk, the k-th best reference distance among the survivors (computed just above in the
+      // reference's own order): equal distances would be ordered by label, so equality is not enough.
       const float xmax = sqrtf(__uint_as_float(*p.max_norm_bits));
-      const float e = p.err_coef * sqrtf(p.qnorm[b]) * xmax + 1e-5f * xmax * xmax + 1e-30f;
-      const float gk = p.approx[(size_t)b * p.kprime + (p.k - 1)];
+      const float qn = p.qnorm[b], qlen = sqrtf(qn);
+      const float e = p.err_coef * qlen * xmax + 1e-5f * (xmax * xmax + qn) + 1e-30f;
+      const float rho = 1.5f * ((float)(p.Dp >> 4) + 8.0f) * 5.9604645e-8f;
       const float gK = p.approx[(size_t)b * p.kprime + (p.kprime - 1)];
-      if (!(gK > gk + 2.0f * e)) flag = 1;
+      const float dk = ord_to_f32(buf[p.k - 1].ord);
+      float lower;
+      if (L2) {
+        lower = gK - e + qn;                     // score = |x|^2 - 2 x.q = distance - |q|^2
+        if (lower > 0.f) lower *= 1.0f - rho;
+      } else {
+        lower = 1.0f + gK - e - rho * qlen * xmax - 2e-7f * (1.0f + qlen * xmax);  // score = -x.q = distance - 1
+      }
+      if (!(lower > dk)) flag = 1;
     }
     p.flags[b] = flag;
   }
