@@ -165,6 +165,22 @@ int vkgpu_search(vkgpu_index *h, const float *q, uint32_t k, uint32_t ef, const 
 int vkgpu_search_batch(vkgpu_index *h, const float *Q, uint32_t B, uint32_t k, uint32_t ef,
                        const vkgpu_filter *filters, uint64_t deadline_ns, float *out_dist, uint64_t *out_labels,
                        uint32_t *out_n);
+/* vkgpu_search_batch with the reference's cancellation semantics.  The deadline is polled INSIDE the HNSW hop loop
+ * (device clock against the host deadline; hnswalg.h:400-402 polls the token once per hop): a search that is still
+ * running when it passes stops and its result list as it stands is the answer.  With VKGPU_SEARCH_PARTIAL_RESULTS
+ * (enable_partial_results, vector_hnsw.cc:313-329) that partial answer is returned with VKGPU_OK; without it the call
+ * returns VKGPU_ERR_CANCELLED ("Search operation cancelled due to timeout").  FLAT (bruteforce.h:129,
+ * vector_flat.cc:224-254: the reference returns what its heap holds, never an error): one launch, polled at its
+ * boundaries.  *out_timed_out (may be NULL) = queries whose search was cut short. */
+typedef struct vkgpu_search_opts {
+  uint32_t struct_size;   /* sizeof(vkgpu_search_opts) */
+  uint32_t flags;         /* VKGPU_SEARCH_* */
+  uint64_t deadline_ns;   /* absolute CLOCK_MONOTONIC ns, 0 = none */
+} vkgpu_search_opts;
+#define VKGPU_SEARCH_PARTIAL_RESULTS 1u
+int vkgpu_search_batch_opts(vkgpu_index *h, const float *Q, uint32_t B, uint32_t k, uint32_t ef,
+                            const vkgpu_filter *filters, const vkgpu_search_opts *opts, float *out_dist,
+                            uint64_t *out_labels, uint32_t *out_n, uint32_t *out_timed_out);
 /* Same with Q and all outputs in DEVICE memory (no host copies); asynchronous on `cuda_stream`
  * (a cudaStream_t, NULL = the library's stream for this call, synchronised before return). */
 int vkgpu_search_batch_device(vkgpu_index *h, const float *d_Q, uint32_t B, uint32_t k, uint32_t ef,

@@ -8,6 +8,7 @@
 // CPU path (tests/test_abi_cpu.py::test_no_cpu_fallback) and nothing under valkey_search_b200/ refers to this file.
 // Only the entry points the host code calls are defined; HNSW modify-in-place is not available in the oracle and
 // answers VKGPU_ERR_UNSUPPORTED.
+#include <time.h>
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -239,6 +240,25 @@ int vkgpu_search_batch(vkgpu_index *ix, const float *Q, uint32_t B, uint32_t k, 
   ix->searches += B;
   return VKGPU_OK;
 }
+// the double has no hop loop to poll in: a deadline already passed cancels (or, with partial results, answers empty)
+int vkgpu_search_batch_opts(vkgpu_index *ix, const float *Q, uint32_t B, uint32_t k, uint32_t ef, const vkgpu_filter *filters,
+                            const vkgpu_search_opts *opts, float *out_dist, uint64_t *out_labels, uint32_t *out_n,
+                            uint32_t *out_timed_out) {
+  if (out_timed_out) *out_timed_out = 0;
+  const uint64_t deadline = opts ? opts->deadline_ns : 0;
+  const bool partial = opts && (opts->flags & VKGPU_SEARCH_PARTIAL_RESULTS);
+  if (deadline && partial) {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    if ((uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec >= deadline) {
+      for (uint32_t b = 0; b < B; b++) out_n[b] = 0;
+      if (out_timed_out) *out_timed_out = B;
+      return VKGPU_OK;
+    }
+  }
+  return vkgpu_search_batch(ix, Q, B, k, ef, filters, deadline, out_dist, out_labels, out_n);
+}
+
 int vkgpu_search(vkgpu_index *ix, const float *q, uint32_t k, uint32_t ef, const vkgpu_filter *filter, uint64_t deadline,
                  float *out_dist, uint64_t *out_labels, uint32_t *out_n) {
   return vkgpu_search_batch(ix, q, 1, k, ef, filter, deadline, out_dist, out_labels, out_n);

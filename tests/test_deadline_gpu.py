@@ -1,0 +1,97 @@
+"""Cancellation inside the kernels (vkgpu_search_batch_opts): the reference polls its cancel::Token once per hop
+(third_party/hnswlib/hnswalg.h:400-402) and VectorHNSW::Search returns the partial heap only when
+enable_partial_results is set, else CancelledError("Search operation cancelled due to timeout")
+(src/indexes/vector_hnsw.cc:313-329).  Here the hop loop compares the device clock with the host deadline."""
+import ctypes as C
+import time
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _now_ns():
+    return time.clock_gettime_ns(time.CLOCK_MONOTONIC)
+
+
+def _opts(L, deadline_ns, partial):
+    o = L.SearchOpts()
+    o.struct_size = C.sizeof(L.SearchOpts)
+    o.flags = L.SEARCH_PARTIAL_RESULTS if partial else 0
+    o.deadline_ns = deadline_ns
+    return o
+
+
+def test_hnsw_deadline_inside_the_hop_loop(built):
+    import valkey_search_b200 as V
+    from valkey_search_b200 import _lib as L
+    lib = L.lib()
+    rng = np.random.default_rng(21)
+    N, D, B, k, ef = 120_000, 96, 512, 10, 3000
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    ix = V.VectorHNSW(D, V.DistanceMetric.L2, initial_cap=N, m=16, ef_construction=100, ef_runtime=ef, max_batch=B)
+    ix.AddRecordsBulk(range(N), X)
+    d, l, n = np.zeros((B, k), np.float32), np.zeros((B, k), np.uint64), np.zeros(B, np.uint32)
+    late = C.c_uint32()
+
+    def run(opts):
+        return lib.vkgpu_search_batch_opts(ix.handle(), Q.ctypes.data, B, k, ef, None, opts, d.ctypes.data, l.ctypes.data,
+                                           n.ctypes.data, C.byref(late))
+
+    # no deadline / a generous one: the complete answer, nothing cut short
+    assert run(None) == L.OK and late.value == 0
+    full_l, full_d = l.copy(), d.copy()
+    t0 = time.perf_counter()
+    assert run(C.byref(_opts(L, 0, False))) == L.OK
+    full_ms = (time.perf_counter() - t0) * 1e3
+    assert run(C.byref(_opts(L, _now_ns() + 30_000_000_000, False))) == L.OK and late.value == 0
+    assert np.array_equal(l, full_l) and np.array_equal(d.view(np.uint32), full_d.view(np.uint32))
+    assert full_ms > 3.0, f"the search must be long enough for a 1 ms deadline to land inside it ({full_ms:.2f} ms)"
+
+    # 1 ms deadline, partial results accepted: returns early with what every hop chain held
+    t0 = time.perf_counter()
+    rc = run(C.byref(_opts(L, _now_ns() + 1_000_000, True)))
+    cut_ms = (time.perf_counter() - t0) * 1e3
+    assert rc == L.OK
+    assert late.value > 0, "no query was cut short"
+    assert cut_ms < 0.75 * full_ms, (cut_ms, full_ms)
+    assert np.all(n <= k)
+    for b in range(B):  # what is returned is a valid ascending result list of real labels
+        m = int(n[b])
+        assert np.all(np.diff(d[b, :m]) >= 0) and np.all(l[b, :m] < N)
+        diff = X[l[b, :m].astype(np.int64)] - Q[b]
+        assert np.allclose(np.sum(diff * diff, axis=1), d[b, :m], rtol=1e-4)
+    recall_cut = np.mean([len(set(l[b, : int(n[b])].tolist()) & set(full_l[b].tolist())) / k for b in range(B)])
+    assert recall_cut < 1.0  # it really stopped early somewhere
+
+    # same deadline without partial results: CancelledError with the reference's message
+    rc = run(C.byref(_opts(L, _now_ns() + 1_000_000, False)))
+    assert rc == L.ERR_CANCELLED
+    assert b"Search operation cancelled due to timeout" in lib.vkgpu_last_error()
+    # a deadline already in the past
+    assert run(C.byref(_opts(L, 1, False))) == L.ERR_CANCELLED
+    assert run(C.byref(_opts(L, 1, True))) == L.OK and late.value == B
+
+
+def test_flat_deadline_is_polled_at_the_launch_boundaries(built):
+    import valkey_search_b200 as V
+    from valkey_search_b200 import _lib as L
+    lib = L.lib()
+    rng = np.random.default_rng(22)
+    N, D, B, k = 50_000, 64, 4, 5
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    d, l, n = np.zeros((B, k), np.float32), np.zeros((B, k), np.uint64), np.zeros(B, np.uint32)
+    late = C.c_uint32()
+    # bruteforce.h:129 + vector_flat.cc:224-254: a fired token is not an error for FLAT, the heap so far is the reply
+    rc = lib.vkgpu_search_batch_opts(ix.handle(), Q.ctypes.data, B, k, 0, None, C.byref(_opts(L, 1, False)), d.ctypes.data,
+                                     l.ctypes.data, n.ctypes.data, C.byref(late))
+    assert rc == L.OK and late.value == B and np.all(n == 0)
+    rc = lib.vkgpu_search_batch_opts(ix.handle(), Q.ctypes.data, B, k, 0, None,
+                                     C.byref(_opts(L, _now_ns() + 10_000_000_000, False)), d.ctypes.data, l.ctypes.data,
+                                     n.ctypes.data, C.byref(late))
+    assert rc == L.OK and late.value == 0 and np.all(n == k)

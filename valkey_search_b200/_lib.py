@@ -44,6 +44,13 @@ class Filter(C.Structure):
     ]
 
 
+class SearchOpts(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32), ("deadline_ns", C.c_uint64)]
+
+
+SEARCH_PARTIAL_RESULTS = 1
+
+
 class Stats(C.Structure):
     _fields_ = [
         ("count", C.c_uint64),
@@ -87,6 +94,8 @@ SYMBOLS = {
     "vkgpu_search": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.POINTER(Filter), C.c_uint64, _P, _P, _P]),
     "vkgpu_search_batch": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Filter), C.c_uint64,
                                      _P, _P, _P]),
+    "vkgpu_search_batch_opts": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Filter),
+                                          C.POINTER(SearchOpts), _P, _P, _P, _P]),
     "vkgpu_search_batch_device": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, _P, _P, _P, _P]),
     "vkgpu_search_batch_device_filtered": (C.c_int, [_P, _P, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(Filter),
                                                      C.c_uint64, _P, _P, _P, _P]),

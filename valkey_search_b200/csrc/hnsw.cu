@@ -60,8 +60,16 @@ struct HnswSearchParams {
   uint32_t rows_per_batch, row_stride_bytes, cand_cap;
   uint32_t need_flags;  // some node is tombstoned or a filter is present: resolve live/allowed per neighbour
   uint32_t merge_skip;  // sorted kernel: leave a list alone when the hop cannot change it (VKGPU_HNSW_NO_MERGE_SKIP=1: off)
-  unsigned long long *stats;
+  unsigned long long deadline_gt;  // %globaltimer value after which a hop loop stops where it is (0 = never)
+  unsigned long long *stats;       // [0] hops, [1] distance evaluations, [3] queries cut short by the deadline
 };
+
+__device__ __forceinline__ bool past_deadline(unsigned long long deadline_gt) {
+  if (deadline_gt == 0) return false;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t > deadline_gt;
+}
 
 namespace {
 
@@ -230,6 +238,9 @@ __global__ void __launch_bounds__(HT) hnsw_search_kernel(const HnswSearchParams 
         const float cd = -c.d;
         if (cd > lower && top_n == ef) {
           stop = 1;
+        } else if (past_deadline(p.deadline_gt)) {  // cancel::Token poll, once per hop (hnswalg.h:400-402)
+          stop = 1;
+          atomicAdd(&p.stats[3], 1ull);
         } else {
           heap_pop(cand, cand_n);
           ctl[1] = c.id;
@@ -569,7 +580,10 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
         uvi[pos] = id;
         uvf[pos] = flag;
       }
-      if (lane == 0) ctl[2] = __popc(bal);
+      if (lane == 0) {
+        ctl[2] = __popc(bal);
+        ctl[7] = past_deadline(p.deadline_gt) ? 1u : 0u;  // cancel::Token poll, once per hop (hnswalg.h:400-402)
+      }
 #ifdef VKGPU_HNSW_TRACE
       HOP_T(h2);
       HOP_ADD(1, h0, h2);  // includes [0]
@@ -579,6 +593,10 @@ __global__ void __launch_bounds__(HT) hnsw_search_sorted_kernel(const HnswSearch
     __syncthreads();
     HOP_T(h4);
     HOP_ADD(2, h3, h4);
+    if (ctl[7]) {  // uniform: the result list as it stands is the (partial) answer
+      if (tid == 0) atomicAdd(&p.stats[3], 1ull);
+      break;
+    }
     const uint32_t nuv = ctl[2];
     if (nuv == 0) {  // uniform
       __syncthreads();  // everyone has read ctl[2] before warp 0 writes the next hop's count
@@ -836,8 +854,9 @@ static GraphView graph_view(vkgpu_index_impl *ix) {
 
 void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_t B, uint32_t k, uint32_t ef_req,
                  const vkgpu_filter *filters, float *out_dist, uint64_t *out_labels, uint32_t *out_n,
-                 bool out_on_device) {
+                 bool out_on_device, uint64_t device_deadline, uint32_t *timed_out) {
   Hnsw *g = G(ix);
+  if (timed_out) *timed_out = 0;
   if (ix->n == 0 || k == 0) {  // hnswalg.h:1665
     if (out_on_device)
       VK_CUDA(cudaMemset(out_n, 0, (size_t)B * 4));
@@ -948,6 +967,7 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   c->scratch3.reserve(4 * sizeof(unsigned long long));
   VK_CUDA(cudaMemsetAsync(c->scratch3.p, 0, 4 * sizeof(unsigned long long), s));
   hp.stats = c->scratch3.as<unsigned long long>();
+  hp.deadline_gt = device_deadline;
   // rows staged per round vs CTAs per SM: prefer enough resident CTAs to hold the whole batch in ONE wave (a hop
   // stages ~8 unvisited rows on average, so 12-16 staged rows rarely need a second round), down to 1 CTA/SM for
   // very wide rows.  Shared memory per SM = opt-in max + 1 KB; each CTA reserves 1 KB.
@@ -1040,6 +1060,7 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   ix->hops = hs[0];
   ix->dist_evals = hs[1];
   ix->searches += B;
+  if (timed_out) *timed_out = (uint32_t)hs[3];
 }
 
 // markDelete hnswalg.h:1173-1209: tombstone; the node keeps routing

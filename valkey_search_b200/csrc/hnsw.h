@@ -14,7 +14,7 @@ void hnsw_modify(vkgpu_index_impl *ix, uint64_t label, const float *vec);
 void hnsw_remove(vkgpu_index_impl *ix, uint64_t label);
 void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_t B, uint32_t k, uint32_t ef,
                  const vkgpu_filter *filters, float *out_dist, uint64_t *out_labels, uint32_t *out_n,
-                 bool out_on_device);
+                 bool out_on_device, uint64_t device_deadline = 0, uint32_t *timed_out = nullptr);
 uint64_t hnsw_live_count(const vkgpu_index_impl *ix);
 uint64_t hnsw_deleted_count(const vkgpu_index_impl *ix);
 int hnsw_max_level(const vkgpu_index_impl *ix);

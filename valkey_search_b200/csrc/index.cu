@@ -177,6 +177,42 @@ static uint64_t now_ns() {
   return (uint64_t)ts.tv_sec * 1000000000ull + (uint64_t)ts.tv_nsec;
 }
 
+__global__ void read_globaltimer_kernel(unsigned long long *out) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  *out = t;
+}
+
+// deadline on the device clock; the offset is re-measured when older than 5 s (three launches, the tightest bracket
+// wins: error = half the launch round trip, ~10 us)
+uint64_t vkgpu_index_impl::device_deadline(uint64_t deadline_ns) {
+  if (deadline_ns == 0) return 0;
+  const uint64_t now = now_ns();
+  if (gt_calibrated_ns.load() == 0 || now - gt_calibrated_ns.load() > 5000000000ull) {
+    std::lock_guard<std::mutex> lk(prof_mu);
+    unsigned long long *d = nullptr, h = 0;
+    VK_CUDA(cudaMalloc(&d, 8));
+    uint64_t best = ~0ull;
+    int64_t off = 0;
+    for (int i = 0; i < 3; i++) {
+      const uint64_t t0 = now_ns();
+      read_globaltimer_kernel<<<1, 1, 0, mut_stream>>>(d);
+      VK_CUDA(cudaMemcpyAsync(&h, d, 8, cudaMemcpyDeviceToHost, mut_stream));
+      VK_CUDA(cudaStreamSynchronize(mut_stream));
+      const uint64_t t1 = now_ns();
+      if (t1 - t0 < best) {
+        best = t1 - t0;
+        off = (int64_t)h - (int64_t)(t0 + (t1 - t0) / 2);
+      }
+    }
+    VK_CUDA(cudaFree(d));
+    gt_offset_ns.store(off);
+    gt_calibrated_ns.store(now_ns());
+  }
+  const int64_t v = (int64_t)deadline_ns + gt_offset_ns.load();
+  return v > 1 ? (uint64_t)v : 1;
+}
+
 static uint32_t next_pow2(uint32_t v) {
   uint32_t p = 1;
   while (p < v) p <<= 1;
@@ -879,6 +915,39 @@ int vkgpu_search_batch(vkgpu_index *ix, const float *Q, uint32_t B, uint32_t k, 
     else
       hnsw_search(ix, Q, false, B, k, ef, filters, out_dist, out_labels, out_n, false);
     VK_REQUIRE(deadline_ns == 0 || now_ns() < deadline_ns, VKGPU_ERR_CANCELLED, "Search operation cancelled due to timeout");
+  });
+}
+
+int vkgpu_search_batch_opts(vkgpu_index *ix, const float *Q, uint32_t B, uint32_t k, uint32_t ef,
+                            const vkgpu_filter *filters, const vkgpu_search_opts *opts, float *out_dist,
+                            uint64_t *out_labels, uint32_t *out_n, uint32_t *out_timed_out) {
+  return guarded([&] {
+    VK_REQUIRE(ix && Q && out_dist && out_labels && out_n, VKGPU_ERR_INVALID, "null argument");
+    VK_REQUIRE(B >= 1, VKGPU_ERR_INVALID, "empty batch");
+    VK_REQUIRE(!opts || opts->struct_size >= sizeof(vkgpu_search_opts), VKGPU_ERR_INVALID, "bad options struct");
+    const uint64_t deadline_ns = opts ? opts->deadline_ns : 0;
+    const bool partial = opts && (opts->flags & VKGPU_SEARCH_PARTIAL_RESULTS);
+    if (out_timed_out) *out_timed_out = 0;
+    std::shared_lock<std::shared_mutex> lk(ix->rw);
+    VK_CUDA(cudaSetDevice(ix->device));
+    if (ix->cfg.algo == VKGPU_FLAT) {
+      // bruteforce.h:129 stops the row loop when the token fires and vector_flat.cc:224-254 returns what the heap
+      // holds; the GPU scan is one launch, polled at its boundaries: a deadline that has already passed yields
+      // empty replies, one that passes during the launch is reported through out_timed_out with complete results
+      if (deadline_ns && now_ns() >= deadline_ns) {
+        for (uint32_t b = 0; b < B; b++) out_n[b] = 0;
+        if (out_timed_out) *out_timed_out = B;
+        return;
+      }
+      flat_search(ix, Q, false, B, k, filters, out_dist, out_labels, out_n, false, nullptr);
+      if (deadline_ns && now_ns() >= deadline_ns && out_timed_out) *out_timed_out = B;
+      return;
+    }
+    uint32_t late = 0;
+    hnsw_search(ix, Q, false, B, k, ef, filters, out_dist, out_labels, out_n, false, ix->device_deadline(deadline_ns), &late);
+    if (out_timed_out) *out_timed_out = late;
+    // vector_hnsw.cc:325-329: the partial heap is the answer only when the caller asked for partial results
+    VK_REQUIRE(late == 0 || partial, VKGPU_ERR_CANCELLED, "Search operation cancelled due to timeout");
   });
 }
 

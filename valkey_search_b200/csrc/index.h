@@ -166,6 +166,12 @@ struct vkgpu_index_impl {
   // ---- HNSW graph (device) + host mirror of the small per-node state
   struct Hnsw *hnsw = nullptr;
 
+  // %globaltimer - CLOCK_MONOTONIC (ns), measured at create and refreshed now and then: lets a kernel compare the
+  // device clock with a host deadline (cancel::Token analog inside the hop loop, hnswalg.h:400-402)
+  std::atomic<int64_t> gt_offset_ns{0};
+  std::atomic<uint64_t> gt_calibrated_ns{0};
+  uint64_t device_deadline(uint64_t deadline_ns);  // 0 stays 0
+
   std::shared_mutex rw;  // searches shared, mutations exclusive
   std::mutex ctx_mu;
   std::condition_variable ctx_cv;

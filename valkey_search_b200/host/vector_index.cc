@@ -309,7 +309,8 @@ std::vector<uint64_t> VectorBase::IdsMatching(const KeyFilter &filter) const {
 }
 
 StatusOr<std::vector<Neighbor>> VectorBase::SearchOne(std::string_view query, uint64_t count, uint32_t ef,
-                                                      const vkgpu_filter *filter, CancelToken token) const {
+                                                      const vkgpu_filter *filter, CancelToken token,
+                                                      bool enable_partial_results) const {
   if (!IsValidSizeVector(query)) return vks::InvalidArgumentError("query vector has the wrong byte length");
   std::vector<char> norm;
   if (normalize_) {  // vector_flat.cc:244-249, vector_hnsw.cc:337-343
@@ -322,7 +323,18 @@ StatusOr<std::vector<Neighbor>> VectorBase::SearchOne(std::string_view query, ui
   std::vector<float> dist(k);
   std::vector<uint64_t> labels(k);
   uint32_t n = 0;
-  VKS_RETURN_IF_ERROR(FromRc(vkgpu_search(gpu_, q.data(), (uint32_t)count, ef, filter, token, dist.data(), labels.data(), &n)));
+  if (token != CancelNever() && indexer_type_ == IndexerType::kHNSW) {
+    // a deadline on a graph search is polled inside the hop loop; what the search holds when it fires is the answer
+    // only if the caller accepts partial results (vector_hnsw.cc:325-329), else CancelledError(kTimeoutMsg)
+    vkgpu_search_opts opts{};
+    opts.struct_size = sizeof(opts);
+    opts.flags = enable_partial_results ? VKGPU_SEARCH_PARTIAL_RESULTS : 0u;
+    opts.deadline_ns = token;
+    VKS_RETURN_IF_ERROR(FromRc(vkgpu_search_batch_opts(gpu_, q.data(), 1, (uint32_t)count, ef, filter, &opts, dist.data(),
+                                                       labels.data(), &n, nullptr)));
+  } else {
+    VKS_RETURN_IF_ERROR(FromRc(vkgpu_search(gpu_, q.data(), (uint32_t)count, ef, filter, token, dist.data(), labels.data(), &n)));
+  }
   std::priority_queue<std::pair<float, uint64_t>> pq;  // CreateReply wants the heap it always got
   for (uint32_t i = 0; i < n; i++) pq.emplace(dist[i], labels[i]);
   return CreateReply(pq);
@@ -694,9 +706,8 @@ template <typename T>
 StatusOr<std::vector<Neighbor>> VectorHNSW<T>::Search(std::string_view query, uint64_t count, CancelToken token,
                                                       const KeyFilter *filter, std::optional<size_t> ef_runtime,
                                                       bool enable_partial_results) const {
-  (void)enable_partial_results;  // the core answers within the deadline or reports CANCELLED; no partial heaps
   const uint32_t ef = (uint32_t)ef_runtime.value_or(0);
-  if (!filter) return SearchOne(query, count, ef, nullptr, token);
+  if (!filter) return SearchOne(query, count, ef, nullptr, token, enable_partial_results);
   // inline filter: the set of internal ids whose key satisfies the predicate, as a label bitmap
   uint64_t max_id = 0;
   const std::vector<uint64_t> ids = IdsMatching(*filter);
@@ -706,7 +717,7 @@ StatusOr<std::vector<Neighbor>> VectorHNSW<T>::Search(std::string_view query, ui
   vkgpu_filter f{};
   f.label_bitmap = bitmap.data();
   f.bitmap_bits = bitmap.size() * 8;
-  return SearchOne(query, count, ef, &f, token);
+  return SearchOne(query, count, ef, &f, token, enable_partial_results);
 }
 
 template <typename T>

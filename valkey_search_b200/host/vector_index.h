@@ -187,7 +187,8 @@ class VectorBase {
   // InternVector (vector_base.cc:152-166): empty => wrong size; else the (normalised) bytes + magnitude
   std::optional<std::vector<char>> InternVector(std::string_view record, float &magnitude) const;
   StatusOr<std::vector<Neighbor>> SearchOne(std::string_view query, uint64_t count, uint32_t ef,
-                                            const vkgpu_filter *filter, CancelToken token) const;
+                                            const vkgpu_filter *filter, CancelToken token,
+                                            bool enable_partial_results = false) const;
  public:
   // exact kNN over an explicit list of internal ids, whatever the index type (the pre-filter of a graph index)
   StatusOr<std::vector<Neighbor>> ExactOverLabels(std::string_view query, uint64_t count,
