@@ -628,7 +628,7 @@ def prefilter_sharded(args):
     """BASELINE configs[4]: hybrid pre-filter (TAG, 1 % selectivity) + exact kNN, 50M x 1536 fp32, batch 256, row-sharded
     over `--gpus` devices in one process through vkgpu_sharded_search_batch.  Tag of row r = r % 100; query b asks for
     tag b % 100.  Every shard keeps the TAG postings of ITS rows in its own HBM, built with the calls the host's
-    DevicePosting / DeviceFilterEvaluator issue (valkey_search_b200/host/filter_index.cc: vkgpu_set_create(empty) +
+    DevicePosting / DeviceFilterEvaluator issue (valkey_search_b200/host/device_filter.cc: vkgpu_set_create(empty) +
     vkgpu_set_update per posting; a one-tag predicate evaluates to the posting's set id) — so a query ships no
     candidate list and the filter is applied where the rows live (src/query/search.cc:401-481 on every node of
     src/query/fanout.cc:159-220).  Parity: the queries of tags 0..P-1 are re-answered by ONE unsharded index holding

@@ -2,7 +2,7 @@
 
 CPU restatement, in plain Python, of the reference's hybrid-filter semantics (the "next" row N1 of SURVEY §8f): what
 a TAG / NUMERIC attribute index accepts, how a query's tag clause is split and unescaped, and when a key satisfies a
-predicate tree.  It is the checker for valkey_search_b200/host/filter_index.{h,cc} (tests/test_filter_oracle.py runs
+predicate tree.  It is the checker for tests/native/reference_filter_standins.{h,cc} + valkey_search_b200/host/device_filter.{h,cc} (tests/test_filter_oracle.py runs
 both on random inputs and compares) and is itself pinned to
   * RediSearch's recorded answers for the reference's `tag special chars` compatibility data set
     (tests/golden/redisearch_tag_special_chars.json, written by tests/golden/make_golden.py), and

@@ -136,7 +136,7 @@ def redisearch_tag_special_chars():
     data_sets.py:522-556, HASH keys: a TAG field with separator ',', values holding '}', '|', '\\', quotes, tabs,
     newlines, accents, CJK, emoji) and the 15 escaped TAG queries of test_tag_escaped_special_chars.  Pins the query-side
     tag parsing (FilterParser::ParseTagString + Tag::ParseSearchTags + UnescapeTag) and TagPredicate matching of the
-    host mirror (valkey_search_b200/host/filter_index.cc) to a third engine's behaviour."""
+    host mirror (tests/native/reference_filter_standins.cc) to a third engine's behaviour."""
     import types
     sys.modules.setdefault("valkey", types.ModuleType("valkey"))  # data_sets.py imports the client; nothing here uses it
     sys.path.insert(0, os.path.join(REF, "integration", "compatibility"))

@@ -1,7 +1,7 @@
 // TEST INFRASTRUCTURE — NOT PRODUCT CODE, NEVER SHIPPED, NEVER LOADED BY THE PACKAGE.
 //
 // A test double of the C-ABI in include/vkgpu.h, built on the CPU oracle (oracle/vk_oracle.c), so that the HOST logic
-// above the ABI — valkey_search_b200/host/{vector_index,filter_index,hnsw_serialization}.cc: key tracking, label
+// above the ABI — valkey_search_b200/host/{vector_index,device_filter,hnsw_serialization}.cc: key tracking, label
 // listeners, posting-list bookkeeping, the planner, predicate evaluation, save / load glue — can be exercised by the
 // native test binaries in the CPU-only `-m "not gpu"` suite.  It says nothing about the kernels: those are checked
 // against the oracle on a B200 by the `-m gpu` tests, which link the real libvkgpu.so.  The product library has no

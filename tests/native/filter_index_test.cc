@@ -1,4 +1,4 @@
-// Tests of the TAG / NUMERIC candidate-set bridge (valkey_search_b200/host/filter_index.h).
+// Tests of the TAG / NUMERIC candidate-set bridge (valkey_search_b200/host/device_filter.h driven by tests/native/reference_filter_standins.h).
 //   host cases  = the reference's testing/tag_index_test.cc and testing/numeric_index_test.cc re-stated (same inputs,
 //                 same expectations) + the predicate tree's Evaluate();  run everywhere (`--host-only`)
 //   device case = on a B200: for a corpus with tags and prices attached in every order, mutated, for a list of
@@ -17,7 +17,7 @@
 #include <type_traits>
 #include <vector>
 
-#include "../../valkey_search_b200/host/filter_index.h"
+#include "reference_filter_standins.h"
 
 using namespace valkey_search::indexes;
 

@@ -1,20 +1,15 @@
-// TAG / NUMERIC candidate-set bridge ("next" row N1 of SURVEY §8f): the reference's non-vector indexes and predicate
-// tree, mirrored on the host with their posting lists ALSO resident on the GPU as label bitmaps, so that a hybrid
-// query's filter is evaluated as set algebra on the device and handed to the kNN kernels by id — no per-key
-// predicate evaluation, no key -> id -> slot hash lookups and no candidate list crossing PCIe.
-//
-// What is mirrored (same names, argument meaning and error behaviour; tests/native/filter_index_test.cc re-states
-// testing/tag_index_test.cc and testing/numeric_index_test.cc):
+// TEST INFRASTRUCTURE — stand-ins for the module's own attribute indexes and leaf predicates, restated from the
+// reference so that the product's device filter (valkey_search_b200/host/device_filter.h) can be driven and checked
+// without the module:
 //   indexes::Tag      src/indexes/tag.{h,cc}      AddRecord / ModifyRecord / RemoveRecord, untracked keys,
 //                                                  ParseSearchTags / ParseRecordTags / UnescapeTag, Search (+negate)
 //   indexes::Numeric  src/indexes/numeric.{h,cc}  AddRecord / ModifyRecord / RemoveRecord, Search (+negate)
-//   query::Predicate  src/query/predicate.{h,cc}  TagPredicate / NumericPredicate / ComposedPredicate (AND, OR) /
-//                                                  NegatePredicate with the reference's Evaluate() semantics
-// and the pre-filter driver (src/query/search.cc:401-481): the set of keys of the VECTOR index for which the root
-// predicate evaluates true.  On the host that set is computed the reference's way (Evaluate per key) — the yardstick
-// of the parity tests; on the device it is  Tag -> OR of the matching posting bitmaps,  Numeric -> range kernel over
-// the resident values,  AND / OR -> word-wise combine,  NOT -> universe AND-NOT child  (universe = labels of the
-// vector index).  Labels are the vector index's internal ids; a key's bit moves with its label (LabelListener).
+//   TagPredicate / NumericPredicate               src/query/predicate.{h,cc} Evaluate() semantics
+// They follow the reference function by function (cited); tests/native/filter_index_test.cc re-states
+// testing/tag_index_test.cc and testing/numeric_index_test.cc over them.  In the real module these classes are the
+// reference's own and only gain a DevicePosting per posting / a resident value column.  One deliberate difference from
+// the reference, pinned by the tests: Tag::ModifyRecord with a spelling-only change on a case-insensitive index keeps
+// the key in its posting (the reference's IndexTagForKey / DeindexTagForKey sequence drops it, tag.cc:208-242).
 #pragma once
 #include <map>
 #include <memory>
@@ -27,44 +22,9 @@
 #include <unordered_set>
 #include <vector>
 
-#include "vector_index.h"
+#include "../../valkey_search_b200/host/device_filter.h"
 
 namespace valkey_search::indexes {
-
-// A label bitmap resident in HBM, synchronised lazily: mutations queue (label, present) pairs, the next query
-// flushes them with one vkgpu_set_update (one small kernel), so ingest never waits for the device.
-class DevicePosting {
- public:
-  explicit DevicePosting(vkgpu_index *gpu) : gpu_(gpu) {}
-  ~DevicePosting();
-  DevicePosting(const DevicePosting &) = delete;
-  DevicePosting &operator=(const DevicePosting &) = delete;
-  void Set(uint64_t label, bool present) { pending_[label] = present ? 1 : 0; }
-  StatusOr<uint64_t> Id();  // flushes; 0 is never returned
-
- private:
-  vkgpu_index *gpu_;
-  uint64_t id_{0};
-  std::unordered_map<uint64_t, uint8_t> pending_;  // last write per label wins
-};
-
-// A temporary device set (result of a predicate); destroyed with the object.
-class DeviceSetRef {
- public:
-  DeviceSetRef() = default;
-  DeviceSetRef(vkgpu_index *gpu, uint64_t id, bool owned) : gpu_(gpu), id_(id), owned_(owned) {}
-  ~DeviceSetRef();
-  DeviceSetRef(DeviceSetRef &&o) noexcept : gpu_(o.gpu_), id_(o.id_), owned_(o.owned_) { o.owned_ = false; }
-  DeviceSetRef &operator=(DeviceSetRef &&o) noexcept;
-  DeviceSetRef(const DeviceSetRef &) = delete;
-  DeviceSetRef &operator=(const DeviceSetRef &) = delete;
-  uint64_t id() const { return id_; }
-
- private:
-  vkgpu_index *gpu_{nullptr};
-  uint64_t id_{0};
-  bool owned_{false};
-};
 
 class TagPredicate;
 class NumericPredicate;
@@ -192,21 +152,6 @@ class Numeric : public FilterIndexBase {
   mutable std::mutex index_mutex_;
 };
 
-// ---- predicates (src/query/predicate.h)
-enum class PredicateType { kTag, kNumeric, kComposedAnd, kComposedOr, kNegate };
-
-class DeviceFilterEvaluator;
-
-class Predicate {
- public:
-  virtual ~Predicate() = default;
-  explicit Predicate(PredicateType type) : type_(type) {}
-  PredicateType GetType() const { return type_; }
-  virtual bool Evaluate(const std::string &key) const = 0;  // the reference's per-key evaluation
- private:
-  PredicateType type_;
-};
-
 class TagPredicate : public Predicate {
  public:
   // `tags` as ParseSearchTags returned them; they are unescaped here (predicate.cc:343-356)
@@ -216,6 +161,7 @@ class TagPredicate : public Predicate {
   bool Evaluate(const std::set<std::string> *in_tags, bool case_sensitive) const;
   const std::set<std::string> &GetTags() const { return tags_; }
   Tag *GetIndex() const { return index_; }
+  StatusOr<DeviceSetRef> LeafDeviceSet() const override { return index_->SearchDevice(*this); }
 
  private:
   Tag *index_;
@@ -232,62 +178,12 @@ class NumericPredicate : public Predicate {
   double GetEnd() const { return end_; }
   bool IsEndInclusive() const { return is_inclusive_end_; }
   Numeric *GetIndex() const { return index_; }
+  StatusOr<DeviceSetRef> LeafDeviceSet() const override { return index_->SearchDevice(*this); }
 
  private:
   Numeric *index_;
   double start_, end_;
   bool is_inclusive_start_, is_inclusive_end_;
-};
-
-class ComposedPredicate : public Predicate {
- public:
-  explicit ComposedPredicate(PredicateType and_or_or) : Predicate(and_or_or) {}
-  void AddChild(std::unique_ptr<Predicate> child) { children_.push_back(std::move(child)); }
-  const std::vector<std::unique_ptr<Predicate>> &GetChildren() const { return children_; }
-  bool Evaluate(const std::string &key) const override;  // AND: all children; OR: any child (predicate.cc:429-520)
-
- private:
-  std::vector<std::unique_ptr<Predicate>> children_;
-};
-
-class NegatePredicate : public Predicate {
- public:
-  explicit NegatePredicate(std::unique_ptr<Predicate> predicate)
-      : Predicate(PredicateType::kNegate), predicate_(std::move(predicate)) {}
-  const Predicate *GetPredicate() const { return predicate_.get(); }
-  bool Evaluate(const std::string &key) const override { return !predicate_->Evaluate(key); }  // predicate.cc:36-39
-
- private:
-  std::unique_ptr<Predicate> predicate_;
-};
-
-// The pre-filter of one vector index on the device.  Keeps the universe (labels currently in the vector index) as a
-// DevicePosting fed by the same LabelListener events.
-class DeviceFilterEvaluator : public LabelListener {
- public:
-  explicit DeviceFilterEvaluator(VectorBase *vectors);
-  ~DeviceFilterEvaluator() override;
-  void OnLabelAssigned(const std::string &key, uint64_t label) override;
-  void OnLabelReleased(const std::string &key, uint64_t label) override;
-
-  // the root predicate as one device set (labels of the vector index whose key satisfies it)
-  StatusOr<DeviceSetRef> Evaluate(const Predicate &root);
-  // EvaluatePrefilteredKeys + CalcBestMatchingPrefilteredKeys (search.cc:401-481) in one call.  FLAT: exact kNN over
-  // the set's rows.  HNSW: the planner decides (UsePreFiltering) between exact distances over the few qualifying keys
-  // and the graph search with the set as its inline filter
-  StatusOr<std::vector<Neighbor>> Search(std::string_view query, uint64_t count, const Predicate &root,
-                                         std::optional<size_t> ef_runtime = std::nullopt);
-  // the same set the reference's way: every tracked key of the vector index for which root.Evaluate(key) is true
-  std::vector<std::string> EvaluateOnHost(const Predicate &root) const;
-  // the prefiltering-threshold-ratio config (valkey_search_options.cc:363-371); HNSW only
-  void SetPrefilteringThresholdRatio(double ratio) { prefiltering_threshold_ratio_ = ratio; }
-
- private:
-  StatusOr<uint64_t> UniverseId();
-  VectorBase *vectors_;
-  DevicePosting universe_;
-  std::mutex mutex_;  // guards universe_
-  double prefiltering_threshold_ratio_{query::kDefaultPrefilteringThresholdRatio};
 };
 
 }  // namespace valkey_search::indexes

@@ -1,6 +1,6 @@
 """The hybrid-filter oracle (oracle/filter_oracle.py, a plain-Python restatement of the reference's TAG / NUMERIC /
 predicate semantics) is (1) pinned to RediSearch's recorded answers and to the reference's own unit-test expectations,
-then (2) used as the checker of the C++ host mirror (valkey_search_b200/host/filter_index.cc) on random inputs: the
+then (2) used as the checker of the C++ host mirror (tests/native/reference_filter_standins.cc) on random inputs: the
 same records, mutations and predicate trees go through both, every status and every selected key set must agree."""
 import json
 import os

@@ -1,4 +1,4 @@
-"""TAG / NUMERIC candidate-set bridge (valkey_search_b200/host/filter_index.h): the native test
+"""TAG / NUMERIC candidate-set bridge (valkey_search_b200/host/device_filter.h): the native test
 binary tests/native/filter_index_test run as a subprocess.  Host cases run everywhere; the device cases need a B200.
 (The file sorts last on purpose: its device cases include the newest code of the round.)"""
 import os
@@ -19,7 +19,7 @@ def _run_filter(args):
 
 
 def test_filter_index_host_cases(built):
-    """TAG / NUMERIC indexes and the predicate tree of the candidate-set bridge (host/filter_index.h): the reference's
+    """TAG / NUMERIC indexes and the predicate tree of the candidate-set bridge (host/device_filter.h + the stand-ins of tests/native/): the reference's
     testing/tag_index_test.cc and testing/numeric_index_test.cc cases, on the host."""
     p = _run_filter(["--host-only"])
     assert p.returncode == 0, p.stdout + p.stderr

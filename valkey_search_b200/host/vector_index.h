@@ -108,7 +108,7 @@ using KeyFilter = std::function<bool(const std::string &key)>;
 std::vector<char> NormalizeEmbedding(std::string_view record, size_t type_size, float *magnitude = nullptr);
 
 // Told when a key gains or loses its internal id (= label on the device): TrackKey / UnTrackKey / LoadTrackedKeys.
-// The TAG / NUMERIC bridge (host/filter_index.h) keeps its device bitmaps over labels in step through this.
+// The TAG / NUMERIC bridge (host/device_filter.h) keeps its device bitmaps over labels in step through this.
 class LabelListener {
  public:
   virtual ~LabelListener() = default;
@@ -168,7 +168,7 @@ class VectorBase {
   vkgpu_index *handle() const { return gpu_; }
   vkgpu_stats Stats() const;
 
-  // ---- hooks of the TAG / NUMERIC bridge (host/filter_index.h)
+  // ---- hooks of the TAG / NUMERIC bridge (host/device_filter.h)
   void AddLabelListener(LabelListener *listener);
   void RemoveLabelListener(LabelListener *listener);
   std::optional<uint64_t> GetLabel(const std::string &key) const;
