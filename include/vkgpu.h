@@ -220,6 +220,9 @@ int vkgpu_merge_topk_packed_device(int device, const void *d_packed, uint32_t G,
  * cfg->device is ignored; cfg->initial_cap is the capacity of the whole index.  devices: CUDA ordinals, 1..16. */
 typedef struct vkgpu_sharded vkgpu_sharded;
 int vkgpu_sharded_create(const vkgpu_config *cfg, const int32_t *devices, uint32_t n_devices, vkgpu_sharded **out);
+/* the same fan-out over indexes the caller already owns (one per device, e.g. each inside the host adapter that also
+ * keeps that shard's attribute indexes); rows are added / removed through the shards' own handles */
+int vkgpu_sharded_adopt(vkgpu_index *const *shards, uint32_t n_shards, vkgpu_sharded **out);
 void vkgpu_sharded_destroy(vkgpu_sharded *s);
 uint32_t vkgpu_sharded_shards(const vkgpu_sharded *s);
 vkgpu_index *vkgpu_sharded_shard(vkgpu_sharded *s, uint32_t shard);   /* borrowed: do not destroy */

@@ -443,4 +443,43 @@ int vkgpu_set_from_range(vkgpu_index *ix, uint64_t id, double start, int incl_st
   return VKGPU_OK;
 }
 
+
+// ---- sharded fan-out (vkgpu_sharded_adopt / _search_batch): every shard answers through the double's own search, the
+// partial results are merged on the host by (distance, label) — the specification the GPU merge kernel is held to
+struct vkgpu_sharded {
+  std::vector<vkgpu_index *> shards;
+};
+int vkgpu_sharded_adopt(vkgpu_index *const *shards, uint32_t n_shards, vkgpu_sharded **out) {
+  if (!shards || !out || n_shards == 0) return VKGPU_ERR_INVALID;
+  auto *s = new vkgpu_sharded();
+  s->shards.assign(shards, shards + n_shards);
+  *out = s;
+  return VKGPU_OK;
+}
+void vkgpu_sharded_destroy(vkgpu_sharded *s) { delete s; }
+int vkgpu_sharded_remove(vkgpu_sharded *, uint64_t) { return VKGPU_ERR_UNSUPPORTED; }
+int vkgpu_sharded_search_batch(vkgpu_sharded *s, const float *Q, uint32_t B, uint32_t k, uint32_t ef,
+                               const vkgpu_filter *const *shard_filters, uint64_t deadline_ns, float *out_dist,
+                               uint64_t *out_labels, uint32_t *out_n) {
+  std::vector<std::vector<std::pair<float, uint64_t>>> all(B);
+  std::vector<float> d((size_t)B * k);
+  std::vector<uint64_t> l((size_t)B * k);
+  std::vector<uint32_t> n(B);
+  for (size_t g = 0; g < s->shards.size(); g++) {
+    const int rc = vkgpu_search_batch(s->shards[g], Q, B, k, ef, shard_filters ? shard_filters[g] : nullptr, deadline_ns,
+                                      d.data(), l.data(), n.data());
+    if (rc != VKGPU_OK) return rc;
+    for (uint32_t b = 0; b < B; b++)
+      for (uint32_t i = 0; i < n[b]; i++) all[b].emplace_back(d[(size_t)b * k + i], l[(size_t)b * k + i]);
+  }
+  for (uint32_t b = 0; b < B; b++) {
+    std::sort(all[b].begin(), all[b].end());
+    out_n[b] = (uint32_t)std::min<size_t>(all[b].size(), k);
+    for (uint32_t i = 0; i < out_n[b]; i++) {
+      out_dist[(size_t)b * k + i] = all[b][i].first;
+      out_labels[(size_t)b * k + i] = all[b][i].second;
+    }
+  }
+  return VKGPU_OK;
+}
 }  // extern "C"

@@ -714,6 +714,154 @@ static void DeviceBridgeHnsw() {
   }
 }
 
+// A hybrid query over a SHARDED index, the way the module would run it on a multi-GPU box:
+// every shard is a complete stack — vector index + TAG + NUMERIC + DeviceFilterEvaluator over ITS keys — the root
+// predicate is evaluated on each shard into a device set of that shard, and ONE vkgpu_sharded_search_batch over the
+// adopted shard handles ranks the qualifying rows of all shards (src/query/search.cc:401-481 on every node +
+// src/query/fanout.cc:159-220).  The answer must be the single-stack answer: same keys, same distance bits.
+static void DeviceBridgeSharded() {
+  const int kDim = 24, kN = 2400, kShards = 3, kK = 12;
+  int ndev = vkgpu_device_count();
+  if (ndev < 1) ndev = 1;
+  struct Stack {
+    std::shared_ptr<VectorFlat<float>> vectors;
+    std::unique_ptr<Tag> tags;
+    std::unique_ptr<Numeric> price;
+    std::unique_ptr<DeviceFilterEvaluator> evaluator;
+  };
+  auto make = [&](int device, uint64_t base) {
+    VectorIndexProto p;
+    p.dimension_count = kDim;
+    p.distance_metric = DistanceMetric::kL2;
+    p.initial_cap = kN;
+    p.flat_algorithm.block_size = 512;
+    p.gpu_device = device;
+    p.gpu_label_base = base;
+    Stack s;
+    auto flat = VectorFlat<float>::Create(p);
+    EXPECT_OK(flat);
+    if (!flat.ok()) return s;
+    s.vectors = *flat;
+    s.tags = std::make_unique<Tag>(',', false, s.vectors.get());
+    s.price = std::make_unique<Numeric>(s.vectors.get());
+    s.evaluator = std::make_unique<DeviceFilterEvaluator>(s.vectors.get());
+    return s;
+  };
+  Stack one = make(0, 0);
+  std::vector<Stack> shards;
+  for (int g = 0; g < kShards; g++) shards.push_back(make(g % ndev, (uint64_t)g * 100000));
+  if (!one.vectors) return;
+  const char *palette[] = {"red", "green", "blue", "dark blue"};
+  auto key = [](int i) { return "doc:" + std::to_string(i); };
+  std::vector<std::vector<float>> vecs(kN, std::vector<float>(kDim));
+  for (int i = 0; i < kN; i++) {
+    for (auto &x : vecs[i]) x = Unit() * 2.0f - 1.0f;
+    if (i % 97 == 5) vecs[i] = vecs[5];  // equal distances across shards: (distance, id) order, ids name the shard
+    const std::string tags = std::string(palette[Next() % 4]) + (i % 3 == 0 ? ",sale" : "");
+    const std::string price = std::to_string((int)(Next() % 1000) / 10.0);
+    for (Stack *s : {&one, &shards[(size_t)(i % kShards)]}) {
+      if (!s->vectors) return;
+      EXPECT_OK(s->vectors->AddRecord(key(i), Bytes(vecs[i])));
+      EXPECT_OK(s->tags->AddRecord(key(i), tags));
+      EXPECT_OK(s->price->AddRecord(key(i), price));
+    }
+  }
+  std::vector<vkgpu_index *> handles;
+  for (auto &s : shards) handles.push_back(s.vectors->handle());
+  vkgpu_sharded *sharded = nullptr;
+  EXPECT_EQ(vkgpu_sharded_adopt(handles.data(), (uint32_t)handles.size(), &sharded), 0);
+  if (!sharded) return;
+  // the same predicate tree built over each stack's own attribute indexes
+  auto build = [&](Stack &s, int which) -> std::unique_ptr<Predicate> {
+    auto tag_leaf = [&](const char *q) { return std::make_unique<TagPredicate>(s.tags.get(), *Tag::ParseSearchTags(q, '|')); };
+    auto range = [&](double a, double b) { return std::make_unique<NumericPredicate>(s.price.get(), a, true, b, false); };
+    if (which == 0) return tag_leaf("red");
+    if (which == 1) return range(10.0, 30.0);
+    if (which == 2) {
+      auto p = std::make_unique<ComposedPredicate>(PredicateType::kComposedAnd);
+      p->AddChild(tag_leaf("sale"));
+      p->AddChild(std::make_unique<NegatePredicate>(tag_leaf("dark*")));
+      return p;
+    }
+    if (which == 3) {
+      auto p = std::make_unique<ComposedPredicate>(PredicateType::kComposedOr);
+      p->AddChild(tag_leaf("green"));
+      p->AddChild(range(95.0, 100.0));
+      return p;
+    }
+    return tag_leaf("no-such-tag");
+  };
+  const int kQueries = 6;
+  std::vector<float> Q((size_t)kQueries * kDim);
+  for (auto &x : Q) x = Unit() * 2.0f - 1.0f;
+  std::memcpy(Q.data(), vecs[5].data(), (size_t)kDim * 4);  // query 0 sits on the duplicated rows
+  for (int which = 0; which < 5; which++) {
+    // per shard: predicate -> device set of that shard -> B filters naming it
+    std::vector<DeviceSetRef> sets;
+    std::vector<std::vector<vkgpu_filter>> filters((size_t)kShards, std::vector<vkgpu_filter>((size_t)kQueries));
+    std::vector<const vkgpu_filter *> per_shard;
+    bool ok = true;
+    for (int g = 0; g < kShards; g++) {
+      auto root = build(shards[(size_t)g], which);
+      auto set = shards[(size_t)g].evaluator->Evaluate(*root);
+      EXPECT_OK(set);
+      if (!set.ok()) {
+        ok = false;
+        break;
+      }
+      for (auto &f : filters[(size_t)g]) f.device_set = set->id();
+      sets.push_back(std::move(*set));
+      per_shard.push_back(filters[(size_t)g].data());
+    }
+    if (!ok) continue;
+    std::vector<float> dist((size_t)kQueries * kK);
+    std::vector<uint64_t> labels((size_t)kQueries * kK);
+    std::vector<uint32_t> n((size_t)kQueries);
+    EXPECT_EQ(vkgpu_sharded_search_batch(sharded, Q.data(), kQueries, kK, 0, per_shard.data(), 0, dist.data(), labels.data(),
+                                         n.data()), 0);
+    auto root1 = build(one, which);
+    for (int q = 0; q < kQueries; q++) {
+      auto want = one.evaluator->Search(std::string_view(reinterpret_cast<const char *>(&Q[(size_t)q * kDim]), (size_t)kDim * 4),
+                                        kK, *root1);
+      EXPECT_OK(want);
+      if (!want.ok()) continue;
+      EXPECT_EQ((size_t)n[(size_t)q], want->size());
+      if ((size_t)n[(size_t)q] != want->size()) continue;
+      // the merged ids name their shard (disjoint id ranges): translate back to keys through that shard's tracker.
+      // Keys at exactly equal distances may come in a different order (ids are assigned per shard): compare as
+      // (distance bits, key) multisets, which pins every rank outside a tie and the membership inside one.
+      std::multiset<std::pair<uint32_t, std::string>> got, exp;
+      for (uint32_t i = 0; i < n[(size_t)q]; i++) {
+        const uint64_t id = labels[(size_t)q * kK + i];
+        const size_t g = (size_t)(id / 100000);
+        EXPECT_TRUE(g < (size_t)kShards);
+        if (g >= (size_t)kShards) continue;
+        auto k2 = shards[g].vectors->GetKeyDuringSearch(id);
+        EXPECT_OK(k2);
+        uint32_t bits;
+        std::memcpy(&bits, &dist[(size_t)q * kK + i], 4);
+        if (k2.ok()) got.emplace(bits, *k2);
+        if (i) EXPECT_TRUE(dist[(size_t)q * kK + i] >= dist[(size_t)q * kK + i - 1]);
+      }
+      for (const auto &nb : *want) {
+        uint32_t bits;
+        std::memcpy(&bits, &nb.distance, 4);
+        exp.emplace(bits, nb.external_id);
+      }
+      // a tie at the k-th place may legitimately keep different keys: drop the last distance class before comparing
+      if (!exp.empty() && exp.size() == (size_t)kK) {
+        const uint32_t last = std::prev(exp.end())->first;
+        for (auto it = exp.begin(); it != exp.end();) it = it->first == last ? exp.erase(it) : std::next(it);
+        for (auto it = got.begin(); it != got.end();) it = it->first == last ? got.erase(it) : std::next(it);
+      }
+      EXPECT_TRUE(got == exp);
+    }
+  }
+  // rows are added through the shards' own handles, not through an adopted handle
+  EXPECT_EQ(vkgpu_sharded_remove(sharded, 1), (int)VKGPU_ERR_UNSUPPORTED);
+  vkgpu_sharded_destroy(sharded);
+}
+
 // --tag-golden FILE: a TAG index and queries from a text file (every string hex-encoded: "sep XX", "case 0|1",
 // "doc KEY TAGS", "query TEXT" with TEXT = the whole filter expression "@field:{ ... }"); prints per query
 // "N key key ..." (hex keys, sorted) or "ERR message".  Host only.  tests/test_zz_filter_bridge.py feeds it the
@@ -917,6 +1065,7 @@ int main(int argc, char **argv) {
                {"Predicates", PredicateCases, false},
                {"DeviceBridgeFlat", DeviceBridgeFlat, true},
                {"DeviceBridgeHnsw", DeviceBridgeHnsw, true},
+               {"DeviceBridgeSharded", DeviceBridgeSharded, true},
                {"ReferenceSearchTestFlat", ReferenceSearchTestFlat, true},
                {"ReferenceLocalSearchTest", ReferenceLocalSearchTest, true},
                {"ReferenceSearchTestHnsw", ReferenceSearchTestHnsw, true}};

@@ -28,7 +28,7 @@ def test_host_mirror_cases_over_the_abi_double(built, case):
 
 
 @pytest.mark.parametrize("case", ["DeviceBridgeFlat", "ReferenceSearchTestFlat", "ReferenceLocalSearchTest", "DeviceBridgeHnsw",
-                                  "ReferenceSearchTestHnsw"])
+                                  "ReferenceSearchTestHnsw", "DeviceBridgeSharded"])
 def test_filter_bridge_cases_over_the_abi_double(built, case):
     """Includes the reference's SearchTest / LocalSearchTest / FetchFilteredKeysTest expectations
     (testing/search_test.cc:542-895) on a graph the oracle builds exactly like hnswlib."""

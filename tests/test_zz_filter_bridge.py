@@ -30,9 +30,12 @@ def test_filter_index_host_cases(built):
 # most certain first: `-x` stops the run at the first failure
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", ["DeviceBridgeFlat", "ReferenceSearchTestFlat", "ReferenceLocalSearchTest", "DeviceBridgeHnsw",
-                                  "ReferenceSearchTestHnsw"])
+                                  "ReferenceSearchTestHnsw", "DeviceBridgeSharded"])
 def test_filter_bridge_on_device(built, tmp_path, case):
     """On a B200, tests/native/filter_index_test --case NAME:
+    DeviceBridgeSharded: three complete shard stacks (vector index + TAG + NUMERIC + DeviceFilterEvaluator over their own
+      keys, disjoint id ranges), five predicate trees evaluated on every shard into that shard's device set, ONE
+      vkgpu_sharded_search_batch over the adopted handles — same keys and distance bits as the single-stack answer.
     DeviceBridge*: 13 predicate trees (TAG exact / prefix / escaped, NUMERIC ranges, AND, OR, NOT, nested), before and
       after mutations — the label set computed on the device equals the reference's per-key evaluation, and the kNN
       through it equals the key-list pre-filter (FLAT) / the host-bitmap inline filter (HNSW) bit for bit; on HNSW also

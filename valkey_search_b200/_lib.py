@@ -122,6 +122,7 @@ SYMBOLS = {
     "vkgpu_get_timings": (C.c_int, [_P, C.POINTER(Timings)]),
     "vkgpu_device_corpus": (C.c_int, [_P, C.POINTER(_P), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     "vkgpu_sharded_create": (C.c_int, [C.POINTER(Config), _P, C.c_uint32, C.POINTER(_P)]),
+    "vkgpu_sharded_adopt": (C.c_int, [_P, C.c_uint32, C.POINTER(_P)]),
     "vkgpu_sharded_destroy": (None, [_P]),
     "vkgpu_sharded_shards": (C.c_uint32, [_P]),
     "vkgpu_sharded_shard": (_P, [_P, C.c_uint32]),

@@ -157,6 +157,7 @@ struct Shard {
   DevBuf dQ, packed, staged;  // queries, this shard's packed result block, peers' blocks when P2P is unavailable
   DevBuf m_dist, m_labels, m_n;  // merged [B][k] / [B] (only this shard's query slice is filled)
   uint64_t count = 0;
+  bool owned = true;  // false: adopted (vkgpu_sharded_adopt), the caller keeps and destroys the index
   Worker worker;
   int rc = 0;
   std::string err;
@@ -171,6 +172,7 @@ struct vkgpu_sharded {
   vkgpu_config cfg{};
   std::vector<std::unique_ptr<Shard>> shards;
   bool p2p = true;
+  bool adopted = false;
   std::mutex search_mu;  // one sharded search at a time (its G device searches run concurrently)
   std::mutex route_mu;
   std::vector<uint8_t> shard_of_dense;  // label -> shard + 1 (0 = unknown), for labels below 2^32
@@ -259,6 +261,34 @@ void on_all(vkgpu_sharded *s, const std::function<void(uint32_t)> &fn) {
     if (s->shards[g]->rc != VKGPU_OK) throw ShError{s->shards[g]->rc, s->shards[g]->err};
 }
 
+// peer access between every pair: the merge kernel of device a loads the result block of device b directly
+void enable_peer_access(vkgpu_sharded *s) {
+  const uint32_t n = s->G();
+  for (uint32_t a = 0; a < n && s->p2p; a++) {
+    for (uint32_t b = 0; b < n; b++) {
+      const int da = s->shards[a]->device, db = s->shards[b]->device;
+      if (a == b || da == db) continue;
+      int can = 0;
+      VK_CUDA(cudaDeviceCanAccessPeer(&can, da, db));
+      if (!can) {
+        s->p2p = false;
+        break;
+      }
+      VK_CUDA(cudaSetDevice(da));
+      cudaError_t e = cudaDeviceEnablePeerAccess(db, 0);
+      if (e == cudaErrorPeerAccessAlreadyEnabled) {
+        cudaGetLastError();
+      } else if (e != cudaSuccess) {
+        cudaGetLastError();
+        s->p2p = false;
+        break;
+      }
+    }
+  }
+  if (const char *e = getenv("VKGPU_SHARDED_NO_P2P"))
+    if (e[0] == '1') s->p2p = false;  // tests: exercise the copy path on a box that has peer access
+}
+
 void check_rc(int rc) {
   if (rc != VKGPU_OK) throw ShError{rc, vkgpu_last_error()};
 }
@@ -290,29 +320,36 @@ int vkgpu_sharded_create(const vkgpu_config *cfg, const int32_t *devices, uint32
       sh->worker.start();
       s->shards.push_back(std::move(sh));
     }
-    // peer access between every pair: the merge kernel of device a loads the result block of device b directly
-    for (uint32_t a = 0; a < n_devices && s->p2p; a++) {
-      for (uint32_t b = 0; b < n_devices; b++) {
-        if (a == b || devices[a] == devices[b]) continue;
-        int can = 0;
-        VK_CUDA(cudaDeviceCanAccessPeer(&can, devices[a], devices[b]));
-        if (!can) {
-          s->p2p = false;
-          break;
-        }
-        VK_CUDA(cudaSetDevice(devices[a]));
-        cudaError_t e = cudaDeviceEnablePeerAccess(devices[b], 0);
-        if (e == cudaErrorPeerAccessAlreadyEnabled) {
-          cudaGetLastError();
-        } else if (e != cudaSuccess) {
-          cudaGetLastError();
-          s->p2p = false;
-          break;
-        }
-      }
+    enable_peer_access(s.get());
+    *out = s.release();
+  });
+}
+
+// A sharded handle over indexes the caller already has (one per device, e.g. each owned by the host adapter that
+// also keeps that shard's attribute indexes): searches fan out and merge as above; rows are added and removed through
+// the shards' own handles.
+int vkgpu_sharded_adopt(vkgpu_index *const *shards, uint32_t n_shards, vkgpu_sharded **out) {
+  return sh_guarded([&] {
+    SH_REQUIRE(shards && out, VKGPU_ERR_INVALID, "null argument");
+    SH_REQUIRE(n_shards >= 1 && n_shards <= 16, VKGPU_ERR_INVALID, "1 to 16 shards");
+    auto s = std::make_unique<vkgpu_sharded>();
+    s->adopted = true;
+    for (uint32_t g = 0; g < n_shards; g++) {
+      SH_REQUIRE(shards[g], VKGPU_ERR_INVALID, "null shard");
+      SH_REQUIRE(shards[g]->cfg.dim == shards[0]->cfg.dim && shards[g]->cfg.metric == shards[0]->cfg.metric &&
+                     shards[g]->cfg.algo == shards[0]->cfg.algo,
+                 VKGPU_ERR_INVALID, "shards of one index share dimension, metric and algorithm");
+      auto sh = std::make_unique<Shard>();
+      sh->ix = shards[g];
+      sh->owned = false;
+      sh->device = shards[g]->device;
+      VK_CUDA(cudaSetDevice(sh->device));
+      VK_CUDA(cudaStreamCreateWithFlags(&sh->stream, cudaStreamNonBlocking));
+      sh->worker.start();
+      s->shards.push_back(std::move(sh));
     }
-    if (const char *e = getenv("VKGPU_SHARDED_NO_P2P"))
-      if (e[0] == '1') s->p2p = false;  // tests: exercise the copy path on a box that has peer access
+    s->cfg = shards[0]->cfg;
+    enable_peer_access(s.get());
     *out = s.release();
   });
 }
@@ -329,7 +366,7 @@ void vkgpu_sharded_destroy(vkgpu_sharded *s) {
     sh->m_dist.release();
     sh->m_labels.release();
     sh->m_n.release();
-    vkgpu_index_destroy(sh->ix);
+    if (sh->owned) vkgpu_index_destroy(sh->ix);
   }
   s->h_q.release();
   s->h_dist.release();
@@ -355,6 +392,7 @@ int vkgpu_sharded_shard_of(vkgpu_sharded *s, uint64_t label, uint32_t *out_shard
 int vkgpu_sharded_add_batch(vkgpu_sharded *s, const uint64_t *labels, const float *vecs, uint64_t n) {
   return sh_guarded([&] {
     SH_REQUIRE(s && vecs, VKGPU_ERR_INVALID, "null argument");
+    SH_REQUIRE(!s->adopted, VKGPU_ERR_UNSUPPORTED, "adopted shards are mutated through their own handles");
     if (n == 0) return;
     const uint32_t G = s->G(), dim = (uint32_t)s->cfg.dim;
     std::vector<uint64_t> gen;
@@ -418,6 +456,7 @@ int vkgpu_sharded_add_batch_device(vkgpu_sharded *s, uint32_t shard, const uint6
                                    uint64_t n) {
   return sh_guarded([&] {
     SH_REQUIRE(s && d_vecs && labels, VKGPU_ERR_INVALID, "null argument");
+    SH_REQUIRE(!s->adopted, VKGPU_ERR_UNSUPPORTED, "adopted shards are mutated through their own handles");
     SH_REQUIRE(shard < s->G(), VKGPU_ERR_INVALID, "no such shard");
     if (n == 0) return;
     std::lock_guard<std::mutex> lk(s->route_mu);
@@ -439,6 +478,7 @@ int vkgpu_sharded_add_batch_device(vkgpu_sharded *s, uint32_t shard, const uint6
 int vkgpu_sharded_modify(vkgpu_sharded *s, uint64_t label, const float *vec) {
   return sh_guarded([&] {
     SH_REQUIRE(s && vec, VKGPU_ERR_INVALID, "null argument");
+    SH_REQUIRE(!s->adopted, VKGPU_ERR_UNSUPPORTED, "adopted shards are mutated through their own handles");
     uint32_t g;
     {
       std::lock_guard<std::mutex> lk(s->route_mu);
@@ -451,6 +491,7 @@ int vkgpu_sharded_modify(vkgpu_sharded *s, uint64_t label, const float *vec) {
 int vkgpu_sharded_remove(vkgpu_sharded *s, uint64_t label) {
   return sh_guarded([&] {
     SH_REQUIRE(s, VKGPU_ERR_INVALID, "null argument");
+    SH_REQUIRE(!s->adopted, VKGPU_ERR_UNSUPPORTED, "adopted shards are mutated through their own handles");
     std::lock_guard<std::mutex> lk(s->route_mu);
     uint32_t g;
     SH_REQUIRE(s->route_get(label, &g), VKGPU_ERR_INTERNAL, "Label not found");

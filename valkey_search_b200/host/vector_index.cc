@@ -668,6 +668,7 @@ StatusOr<std::shared_ptr<VectorFlat<T>>> VectorFlat<T>::Create(const VectorIndex
   cfg.block_size = p.flat_algorithm.block_size;
   const Status s = index->CreateCore(cfg);  // the reference wraps hnswlib's constructor in try/catch: vector_flat.cc:68-72
   if (!s.ok()) return s;
+  index->SetFirstInternalId(p.gpu_label_base);
   return index;
 }
 
@@ -699,6 +700,7 @@ StatusOr<std::shared_ptr<VectorHNSW<T>>> VectorHNSW<T>::Create(const VectorIndex
   cfg.allow_replace_deleted = p.hnsw_allow_replace_deleted ? 1 : 0;
   const Status s = index->CreateCore(cfg);
   if (!s.ok()) return s;
+  index->SetFirstInternalId(p.gpu_label_base);
   return index;
 }
 

@@ -70,6 +70,9 @@ struct VectorIndexProto {  // data_model::VectorIndex, src/index_schema.proto:87
   uint32_t gpu_max_batch{1024};
   uint32_t gpu_batch_window_us{0};
   bool hnsw_allow_replace_deleted{false};
+  // first internal id this index hands out: the shards of one sharded index get disjoint id ranges, so that a merged
+  // reply names its shard (vkgpu_sharded_adopt; every node of a reference cluster answers with keys instead)
+  uint64_t gpu_label_base{0};
 };
 
 // The two protobuf messages of this path, hand-encoded in proto3 wire format (no protobuf in the image):
@@ -172,6 +175,7 @@ class VectorBase {
   void AddLabelListener(LabelListener *listener);
   void RemoveLabelListener(LabelListener *listener);
   std::optional<uint64_t> GetLabel(const std::string &key) const;
+  void SetFirstInternalId(uint64_t id) { inc_id_ = id; }  // before the first AddRecord (VectorIndexProto::gpu_label_base)
   uint64_t GetLabelBound() const;  // every internal id handed out so far is below this (inc_id_)
   // kNN restricted to a device-resident label set (vkgpu_set_*): FLAT = exact scan over the set's rows (the
   // pre-filter path, vector_base.cc:509-530), HNSW = inline filter (hnswalg.h:515-524)
