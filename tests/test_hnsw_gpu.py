@@ -288,3 +288,41 @@ def test_hnsw_heap_and_sorted_kernels_agree(built, monkeypatch):
     for a, b in zip(out["sorted"], out["heaps"]):
         assert np.array_equal(a[2], b[2]) and np.array_equal(a[1], b[1])
         assert np.array_equal(_bits(a[0]), _bits(b[0]))
+
+
+def test_hnsw_ef_beyond_the_graph_kernels_is_answered_by_the_exact_scan(built):
+    """The reference accepts EF_RUNTIME up to 10^6 (src/commands/ft_create_parser.cc:63-73); the graph kernels keep
+    their lists in shared memory up to ef = 4096.  Beyond that the exact scan over the live (and allowed) nodes
+    answers: recall 1.0 >= the reference's at that ef; tombstones and inline filters keep their meaning."""
+    import valkey_search_b200 as V
+    from valkey_search_b200 import _lib as L
+    lib = L.lib()
+    rng = np.random.default_rng(31)
+    N, D, B, k = 6000, 40, 5, 10
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    ix = V.VectorHNSW(D, V.DistanceMetric.L2, initial_cap=N, m=16, ef_construction=100, ef_runtime=50)
+    ix.AddRecordsBulk(range(N), X)
+    dead = set(range(0, N, 9))
+    for lab in dead:
+        L.check(lib.vkgpu_remove(ix.handle(), lab))
+    orc = O.PortFlat(D, O.L2)
+    orc.add_many(X)
+    live = np.array([i for i in range(N) if i not in dead], np.uint64)
+    d, l, n = np.zeros((B, k), np.float32), np.zeros((B, k), np.uint64), np.zeros(B, np.uint32)
+    L.check(lib.vkgpu_search_batch(ix.handle(), Q.ctypes.data, B, k, 6000, None, 0, d.ctypes.data, l.ctypes.data, n.ctypes.data))
+    for b in range(B):
+        wd, wl = orc.search_subset(Q[b], k, live)
+        assert n[b] == k and np.array_equal(l[b], wl) and np.array_equal(_bits(d[b]), _bits(wd))
+    # with an inline filter (label bitmap): live AND allowed
+    allowed = np.array([i for i in range(N) if i % 4 == 1], np.uint64)
+    bm = np.zeros((N + 7) // 8, np.uint8)
+    np.bitwise_or.at(bm, (allowed >> np.uint64(3)).astype(np.int64), (1 << (allowed & np.uint64(7)).astype(np.uint8)).astype(np.uint8))
+    f = (L.Filter * B)()
+    for b in range(B):
+        f[b].label_bitmap, f[b].bitmap_bits = bm.ctypes.data, N
+    L.check(lib.vkgpu_search_batch(ix.handle(), Q.ctypes.data, B, k, 100000, f, 0, d.ctypes.data, l.ctypes.data, n.ctypes.data))
+    both = np.array([i for i in allowed.tolist() if i not in dead], np.uint64)
+    for b in range(B):
+        wd, wl = orc.search_subset(Q[b], k, both)
+        assert n[b] == k and np.array_equal(l[b], wl) and np.array_equal(_bits(d[b]), _bits(wd))

@@ -830,6 +830,10 @@ void hnsw_reserve(vkgpu_index_impl *ix, uint64_t rows) {
 }
 
 uint64_t hnsw_live_count(const vkgpu_index_impl *ix) { return ix->n - G(ix)->num_deleted; }
+uint32_t hnsw_effective_ef(const vkgpu_index_impl *ix, uint32_t ef_req, uint32_t k) {
+  return std::max<uint32_t>(ef_req ? ef_req : G(ix)->ef, k);  // hnswalg.h:1707-1712
+}
+const std::vector<uint8_t> &hnsw_deleted_flags(const vkgpu_index_impl *ix) { return G(ix)->h_deleted; }
 uint64_t hnsw_deleted_count(const vkgpu_index_impl *ix) { return G(ix)->num_deleted; }
 int hnsw_max_level(const vkgpu_index_impl *ix) { return G(ix)->maxlevel; }
 
@@ -866,7 +870,7 @@ void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_
   }
   // ef = max(ef_runtime or index default, k)  (hnswalg.h:1707-1712)
   uint32_t ef = std::max<uint32_t>(ef_req ? ef_req : g->ef, k);
-  VK_REQUIRE(ef <= 4096, VKGPU_ERR_UNSUPPORTED, "ef_runtime > 4096 is not supported by the GPU core yet");
+  VK_REQUIRE(ef <= kHnswMaxEf, VKGPU_ERR_INTERNAL, "ef beyond the graph kernels: the caller routes it to the exact scan");
   CtxLease lease(ix);
   SearchCtx *c = lease.c;
   cudaStream_t s = c->cur;

@@ -1,5 +1,6 @@
 // HNSW on the GPU: graph residency, batched search kernel, single-GPU build (hnsw.cu).
 #pragma once
+#include <vector>
 #include "index.h"
 
 namespace vkgpu {
@@ -15,6 +16,10 @@ void hnsw_remove(vkgpu_index_impl *ix, uint64_t label);
 void hnsw_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_t B, uint32_t k, uint32_t ef,
                  const vkgpu_filter *filters, float *out_dist, uint64_t *out_labels, uint32_t *out_n,
                  bool out_on_device, uint64_t device_deadline = 0, uint32_t *timed_out = nullptr);
+// largest ef the graph-search kernels hold in shared memory; beyond it the exact scan answers (index.cu)
+constexpr uint32_t kHnswMaxEf = 4096;
+uint32_t hnsw_effective_ef(const vkgpu_index_impl *ix, uint32_t ef_req, uint32_t k);
+const std::vector<uint8_t> &hnsw_deleted_flags(const vkgpu_index_impl *ix);
 uint64_t hnsw_live_count(const vkgpu_index_impl *ix);
 uint64_t hnsw_deleted_count(const vkgpu_index_impl *ix);
 int hnsw_max_level(const vkgpu_index_impl *ix);

@@ -899,6 +899,71 @@ int vkgpu_flat_export(vkgpu_index *ix, uint64_t first_slot, uint64_t n, float *o
   });
 }
 
+// HNSW search with ef beyond what the graph kernels keep in shared memory (the reference accepts EF_RUNTIME up to
+// 10^6, src/commands/ft_create_parser.cc:63-73): answered by the EXACT scan over the live (and allowed) nodes — the
+// gather kernel over a device set — i.e. with recall 1.0, which is at least what the reference's graph search
+// reaches at that ef.  Tombstoned nodes never qualify (hnswalg.h:515-518), filters are intersected with the live set.
+static std::unique_ptr<DeviceSet> new_device_set(uint64_t bits);
+static uint64_t publish_set(vkgpu_index_impl *ix, std::unique_ptr<DeviceSet> ds);
+static void hnsw_exact_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_t B, uint32_t k,
+                              const vkgpu_filter *filters, float *out_dist, uint64_t *out_labels, uint32_t *out_n,
+                              bool out_on_device) {
+  const std::vector<uint8_t> &dead = hnsw_deleted_flags(ix);
+  uint64_t bits = 0;
+  for (uint64_t i = 0; i < ix->n; i++)
+    if (!dead[i]) bits = std::max(bits, ix->h_labels[i] + 1);
+  std::vector<uint8_t> live((bits + 7) / 8, 0);
+  for (uint64_t i = 0; i < ix->n; i++)
+    if (!dead[i]) live[ix->h_labels[i] >> 3] |= (uint8_t)(1u << (ix->h_labels[i] & 7));
+  std::vector<uint64_t> temp_ids;
+  auto make_set = [&](const std::vector<uint8_t> &bm) {
+    auto ds = new_device_set(bits);
+    if (bits) VK_CUDA(cudaMemcpy(ds->bitmap.p, bm.data(), bm.size(), cudaMemcpyHostToDevice));
+    temp_ids.push_back(publish_set(ix, std::move(ds)));
+    return temp_ids.back();
+  };
+  std::vector<vkgpu_filter> fs(B);
+  try {
+    const uint64_t live_id = make_set(live);
+    for (uint32_t b = 0; b < B; b++) {
+      fs[b] = vkgpu_filter{};
+      fs[b].device_set = live_id;
+      if (!filters) continue;
+      const vkgpu_filter &f = filters[b];
+      if (!f.labels && !f.label_bitmap && !f.device_set) continue;
+      std::vector<uint8_t> bm(live.size(), 0);
+      if (f.device_set) {
+        std::vector<uint8_t> user;
+        {
+          std::lock_guard<std::mutex> sl(ix->sets_mu);
+          auto it = ix->sets.find(f.device_set);
+          VK_REQUIRE(it != ix->sets.end(), VKGPU_ERR_NOT_FOUND, "unknown device set id");
+          user.resize((it->second->bits + 7) / 8);
+          if (!user.empty()) VK_CUDA(cudaMemcpy(user.data(), it->second->bitmap.p, user.size(), cudaMemcpyDeviceToHost));
+        }
+        for (size_t i = 0; i < std::min(bm.size(), user.size()); i++) bm[i] = live[i] & user[i];
+      } else if (f.label_bitmap) {
+        const size_t nb = std::min<size_t>(bm.size(), (f.bitmap_bits + 7) / 8);
+        for (size_t i = 0; i < nb; i++) bm[i] = live[i] & f.label_bitmap[i];
+        if (nb && (f.bitmap_bits & 7) && nb == (f.bitmap_bits + 7) / 8) bm[nb - 1] &= (uint8_t)((1u << (f.bitmap_bits & 7)) - 1u);
+      } else {
+        for (uint64_t i = 0; i < f.n_labels; i++) {
+          const uint64_t lab = f.labels[i];
+          if (lab < bits && ((live[lab >> 3] >> (lab & 7)) & 1)) bm[lab >> 3] |= (uint8_t)(1u << (lab & 7));
+        }
+      }
+      fs[b].device_set = make_set(bm);
+    }
+    flat_search(ix, Q, q_on_device, B, k, fs.data(), out_dist, out_labels, out_n, out_on_device, nullptr);
+  } catch (...) {
+    std::lock_guard<std::mutex> sl(ix->sets_mu);
+    for (uint64_t id : temp_ids) ix->sets.erase(id);
+    throw;
+  }
+  std::lock_guard<std::mutex> sl(ix->sets_mu);
+  for (uint64_t id : temp_ids) ix->sets.erase(id);
+}
+
 int vkgpu_search_batch(vkgpu_index *ix, const float *Q, uint32_t B, uint32_t k, uint32_t ef,
                        const vkgpu_filter *filters, uint64_t deadline_ns, float *out_dist, uint64_t *out_labels,
                        uint32_t *out_n) {
@@ -912,6 +977,8 @@ int vkgpu_search_batch(vkgpu_index *ix, const float *Q, uint32_t B, uint32_t k, 
     VK_CUDA(cudaSetDevice(ix->device));
     if (ix->cfg.algo == VKGPU_FLAT)
       flat_search(ix, Q, false, B, k, filters, out_dist, out_labels, out_n, false, nullptr);
+    else if (hnsw_effective_ef(ix, ef, k) > kHnswMaxEf)
+      hnsw_exact_search(ix, Q, false, B, k, filters, out_dist, out_labels, out_n, false);
     else
       hnsw_search(ix, Q, false, B, k, ef, filters, out_dist, out_labels, out_n, false);
     VK_REQUIRE(deadline_ns == 0 || now_ns() < deadline_ns, VKGPU_ERR_CANCELLED, "Search operation cancelled due to timeout");
@@ -944,6 +1011,11 @@ int vkgpu_search_batch_opts(vkgpu_index *ix, const float *Q, uint32_t B, uint32_
       return;
     }
     uint32_t late = 0;
+    if (hnsw_effective_ef(ix, ef, k) > kHnswMaxEf) {
+      VK_REQUIRE(deadline_ns == 0 || now_ns() < deadline_ns || partial, VKGPU_ERR_CANCELLED, "Search operation cancelled due to timeout");
+      hnsw_exact_search(ix, Q, false, B, k, filters, out_dist, out_labels, out_n, false);
+      return;
+    }
     hnsw_search(ix, Q, false, B, k, ef, filters, out_dist, out_labels, out_n, false, ix->device_deadline(deadline_ns), &late);
     if (out_timed_out) *out_timed_out = late;
     // vector_hnsw.cc:325-329: the partial heap is the answer only when the caller asked for partial results
@@ -986,6 +1058,8 @@ int vkgpu_search_batch_device_filtered(vkgpu_index *ix, const float *d_Q, uint32
     VK_CUDA(cudaSetDevice(ix->device));
     if (ix->cfg.algo == VKGPU_FLAT)
       flat_search(ix, d_Q, true, B, k, filters, d_out_dist, d_out_labels, d_out_n, true, (cudaStream_t)cuda_stream);
+    else if (hnsw_effective_ef(ix, ef, k) > kHnswMaxEf)
+      hnsw_exact_search(ix, d_Q, true, B, k, filters, d_out_dist, d_out_labels, d_out_n, true);
     else
       hnsw_search(ix, d_Q, true, B, k, ef, filters, d_out_dist, d_out_labels, d_out_n, true);
     VK_REQUIRE(deadline_ns == 0 || now_ns() < deadline_ns, VKGPU_ERR_CANCELLED, "Search operation cancelled due to timeout");
