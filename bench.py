@@ -466,20 +466,38 @@ def serve_workload(args):
     from valkey_search_b200 import _lib as L
 
     N, D, k, T = args.rows, args.dim, args.k, args.batch
+    MB = args.max_batch or T
+    hnsw = args.serve_algo == "hnsw"
     dev = torch.device("cuda", 0)
     torch.cuda.set_device(dev)
     lib = L.lib()
-    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N, max_batch=T, batch_window_us=args.window_us)
+    if hnsw:
+        k = 10 if args.k == 100 else args.k
+        ix = V.VectorHNSW(D, V.DistanceMetric.L2, initial_cap=N, m=16, ef_construction=200, ef_runtime=args.ef, max_batch=MB,
+                          batch_window_us=args.window_us)
+    else:
+        ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N, max_batch=MB, batch_window_us=args.window_us)
+    g = torch.Generator(device=dev)
+    g.manual_seed(4321 if not hnsw else 777)
+    centres = torch.randn((1024, D), generator=g, device=dev) if hnsw else None
     BLK = 1_000_000
     for blk in range((N + BLK - 1) // BLK):
         rows = min(BLK, N - blk * BLK)
-        Xb = gen_block(torch, dev, blk, rows, D)
+        if hnsw:  # the clustered corpus of the HNSW workload
+            gb = torch.Generator(device=dev)
+            gb.manual_seed(778 + blk)
+            assign = torch.randint(0, 1024, (rows,), generator=gb, device=dev)
+            Xb = (centres[assign] + 0.3 * torch.randn((rows, D), generator=gb, device=dev)).contiguous()
+        else:
+            Xb = gen_block(torch, dev, blk, rows, D)
         torch.cuda.synchronize()
         L.check(lib.vkgpu_add_batch_device(ix.handle(), None, Xb.data_ptr(), rows))
         del Xb
-    g = torch.Generator(device=dev)
-    g.manual_seed(4321)
-    hQ = torch.randn((T, D), generator=g, device=dev).cpu().numpy()
+    if hnsw:
+        qa = torch.randint(0, 1024, (T,), generator=g, device=dev)
+        hQ = (centres[qa] + 0.3 * torch.randn((T, D), generator=g, device=dev)).cpu().numpy()
+    else:
+        hQ = torch.randn((T, D), generator=g, device=dev).cpu().numpy()
     drv = C.CDLL(os.path.join(ROOT, "tests", "native", "libvkdriver.so"))
     drv.vkdrv_run.restype = C.c_double
     od, ol, on = np.zeros((T, k), np.float32), np.zeros((T, k), np.uint64), np.zeros(T, np.uint32)
@@ -500,11 +518,14 @@ def serve_workload(args):
     clocks = sampler.stop()
     st1 = ix.stats()
     nb = st1.batches - st0.batches
-    line = {"metric": f"kNN QPS, one query per call from {T} concurrent callers (FLAT {N}x{D} fp32, k={k})",
+    line = {"metric": f"kNN QPS, one query per call from {T} concurrent callers ({'HNSW ef=%d' % args.ef if hnsw else 'FLAT'} "
+                      f"{N}x{D} fp32, k={k})",
             "value": T * K / secs, "unit": UNIT, "n_gpus": 1, "steps": K, "warmup": W, "ms_per_step": 1e3 * secs / K,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic N(0,1) fp32", "config": {"workload": f"serve: {T} threads x vkgpu_search, batch window "
-                                                        f"{args.window_us} us", "rows": N, "dim": D, "k": k},
+                                                        f"{args.window_us} us, batches of <= {MB}, batches in flight <= "
+                                                        f"{os.environ.get('VKGPU_BATCHER_IN_FLIGHT', '4' if hnsw else '1')}",
+                                                        "rows": N, "dim": D, "k": k},
             "e2e": {"value": T * K / secs, "unit": UNIT, "h2d_bytes_per_step": T * D * 4,
                     "d2h_bytes_per_step": T * k * 12 + T * 4},
             "gpu_launches": int(st1.kernels_launched - st0.kernels_launched), "errors": int(ne.value),
@@ -949,6 +970,8 @@ def main():
     ap.add_argument("--hnsw-rows", type=int, default=1_000_000, help="rows of the HNSW measurement embedded in the flat line")
     ap.add_argument("--no-secondary", action="store_true", help="flat: skip the embedded HNSW / pre-filter measurements")
     ap.add_argument("--window-us", type=int, default=300)
+    ap.add_argument("--max-batch", type=int, default=0, help="serve: largest batch the dispatcher forms (default: callers)")
+    ap.add_argument("--serve-algo", default="flat", choices=["flat", "hnsw"])
     ap.add_argument("--host-lists", action="store_true", help="prefilter: ship label lists per call")
     args = ap.parse_args()
     if args.workload == "hnsw":

@@ -1,9 +1,13 @@
 // Dynamic batcher ("next" row N2): turns concurrent single-query vkgpu_search calls — one per reader-pool
 // thread in the module (src/query/search.cc:886-910, one query per FT.SEARCH) — into vkgpu_search_batch launches.
-// Callers block on a per-request condition; one dispatcher thread per index collects requests until the batch is
-// full or `window_us` has passed since the first one arrived, runs them as ONE batch and hands every caller its
-// row of the result.  Requests are grouped by (k, ef); a request whose deadline has passed is answered CANCELLED.
+// Callers block on a per-request condition; a dispatcher collects requests until the batch is full or `window_us` has
+// passed since the first one arrived, runs them as ONE batch and hands every caller its row of the result.  Several
+// dispatchers (3 by default, VKGPU_BATCHER_DISPATCHERS) share the queue, so the next batch is collected and launched
+// while earlier ones are still on the device: the GPU does not idle during a collection window, and HNSW batches —
+// each of which ends with its slowest hop chain — overlap (profiles/r2_hnsw_occupancy_sweep.log).
+// Requests are grouped by (k, ef); a request whose deadline has passed is answered CANCELLED.
 #pragma once
+#include <atomic>
 #include <condition_variable>
 #include <cstdint>
 #include <deque>
@@ -32,7 +36,7 @@ struct BatchRequest {
 
 class Batcher {
  public:
-  Batcher(vkgpu_index *ix, uint32_t dim, uint32_t max_batch, uint32_t window_us);
+  Batcher(vkgpu_index *ix, uint32_t dim, uint32_t max_batch, uint32_t window_us, uint32_t max_in_flight);
   ~Batcher();
   int submit(BatchRequest *r);  // blocks until the request has been answered; returns its status
 
@@ -42,13 +46,15 @@ class Batcher {
  private:
   void run();
   vkgpu_index *ix_;
-  uint32_t dim_, max_batch_, window_us_;
+  uint32_t dim_, max_batch_, window_us_, max_in_flight_;
+  uint32_t in_flight_ = 0;  // batches on the device
   std::mutex mu_;
   std::condition_variable cv_;
   std::deque<BatchRequest *> queue_;
   bool stop_ = false;
-  std::thread thread_;
-  uint64_t batches_ = 0, requests_ = 0;
+  bool collecting_ = false;  // a dispatcher is inside its collection window
+  std::vector<std::thread> threads_;
+  std::atomic<uint64_t> batches_{0}, requests_{0};
 };
 
 }  // namespace vkgpu

@@ -765,7 +765,7 @@ int vkgpu_index_create(const vkgpu_config *cfg, vkgpu_index **out) {
       ix->capacity = want;
       if (ix->hnsw) hnsw_reserve(ix, want);
     }
-    if (cfg->batch_window_us) ix->batcher = new Batcher(ix, ix->dim, ix->cfg.max_batch, cfg->batch_window_us);
+    if (cfg->batch_window_us) ix->batcher = new Batcher(ix, ix->dim, ix->cfg.max_batch, cfg->batch_window_us, cfg->algo == VKGPU_HNSW ? 4u : 1u);
     *out = ix;
   });
   if (rc != VKGPU_OK && ix) {
