@@ -342,8 +342,9 @@ def hnsw_workload(args, embedded=False):
     single_launches = int(ix.stats().kernels_launched - st0.kernels_launched)
     L.check(lib.vkgpu_set_profiling(ix.handle(), 0))
     hnsw_ms, hnsw_n = tm.ms[4], int(tm.launches[4])
-    # ---- F batches in flight: the headline of this workload
-    KF = K * F
+    # ---- F batches in flight: the headline of this workload (a batch is < 1 ms: enough of them that thread start-up
+    #      and the first wake-ups do not weigh on the figure)
+    KF = max(K * F, 48 * F)
     st0 = ix.stats()
     sampler = ClockSampler(0)
     sampler.start()

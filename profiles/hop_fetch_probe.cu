@@ -124,14 +124,15 @@ static void run(const char *name, const float *X, uint32_t n, int B, int T, int 
          (double)B * hops * R * ROWB / (ms * 1e6));
 }
 
-int main() {
-  const uint32_t n = 1000000;
+int main(int argc, char **argv) {
+  const uint32_t n = argc > 1 ? (uint32_t)atoll(argv[1]) : 1000000;  // rows of the corpus (TLB reach: try 10000000)
   float *X;
   uint32_t *out;
   CK(cudaMalloc(&X, (size_t)n * D * 4));
   CK(cudaMemset(X, 1, (size_t)n * D * 4));
   CK(cudaMalloc(&out, 1 << 20));
   const int hops = 300;
+  printf("corpus %u rows x %d dims (%.1f GB)\n", n, D, (double)n * D * 4 / 1e9);
   for (int B : {148, 512, 1024, 2048}) {
     for (int T : {32, 128, 256}) {
       run<0>("cp.async 16 B, all threads", X, n, B, T, hops, out);

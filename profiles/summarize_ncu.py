@@ -33,19 +33,37 @@ def main(path):
                 print(f"  {w} = {r[i]} {units[i]}")
     src = subprocess.run(["ncu", "-i", path, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(src)))
-    if len(rows) > 2:
-        hdr = rows[1]
+    # one block per kernel: a "Kernel Name" row, a header row, then one row per SASS instruction
+    blocks, cur = [], None
+    for r in rows:
+        if r and r[0] == "Kernel Name":
+            cur = {"name": r[1] if len(r) > 1 else "?", "hdr": None, "body": []}
+            blocks.append(cur)
+        elif cur is not None and cur["hdr"] is None:
+            cur["hdr"] = r
+        elif cur is not None and r:
+            cur["body"].append(r)
+    key = "Warp Stall Sampling (All Samples)"
+    for blk in blocks:
+        hdr, body = blk["hdr"], blk["body"]
+        if not hdr or key not in hdr:
+            continue
         ci = {h: i for i, h in enumerate(hdr)}
-        body = rows[2:]
-        key = "Warp Stall Sampling (All Samples)"
-        tot = sum(float(r[ci[key]] or 0) for r in body)
+
+        def num(r, col):
+            try:
+                return float(r[ci[col]] or 0)
+            except (ValueError, IndexError):
+                return 0.0
+        tot = sum(num(r, key) for r in body) or 1.0
         stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
-        agg = sorted(((sum(float(r[ci[s]] or 0) for r in body), s) for s in stalls), reverse=True)[:6]
+        agg = sorted(((sum(num(r, s) for r in body), s) for s in stalls), reverse=True)[:6]
+        print(f"source page: {blk['name'][:100]}")
         print("  stall mix (% of warp samples): " + ", ".join(f"{s}={100 * v / tot:.1f}" for v, s in agg))
-        top = sorted(body, key=lambda r: -float(r[ci[key]] or 0))[:12]
+        top = sorted(body, key=lambda r: -num(r, key))[:12]
         print("  hottest SASS lines (samples, executed, instruction):")
         for r in top:
-            print(f"    {float(r[ci[key]]):9.0f} {r[ci['Instructions Executed']]:>11} {r[ci['Source']].strip()[:90]}")
+            print(f"    {num(r, key):9.0f} {r[ci['Instructions Executed']]:>11} {r[ci['Source']].strip()[:90]}")
 
 
 if __name__ == "__main__":
