@@ -79,8 +79,38 @@ struct TensorParams {
   uint32_t *gsl;             // [nq_tiles*BN][gsl_stride] per-slab upper bounds of the local j-th best score (ord)
   uint32_t gsl_stride;       // row stride of gsl: slabs rounded up to 4 (16-byte loads)
   uint32_t jrank;            // j = ceil(K'/slabs): slabs*j >= K' rows are <= max_s gsl[q][s]
+  uint32_t seed_tiles;       // SEED instantiation: corpus tiles each CTA samples (4 or 8); 0 otherwise
   int metric_l2;
 };
+
+// Ascending bitonic sorting network over 32 registers (240 compare-exchanges, no dynamic indexing).
+__device__ __forceinline__ void sort32_regs(uint32_t (&g)[32]) {
+#pragma unroll
+  for (int ks = 1; ks <= 5; ks++) {
+#pragma unroll
+    for (int js = 4; js >= 0; js--) {
+      if (js >= ks) continue;
+      const int k = 1 << ks, j = 1 << js;
+#pragma unroll
+      for (int i = 0; i < 32; i++) {
+        const int l = i ^ j;
+        if (l > i) {
+          const uint32_t lo = min(g[i], g[l]), hi = max(g[i], g[l]);
+          const bool up = (i & k) == 0;
+          g[i] = up ? lo : hi;
+          g[l] = up ? hi : lo;
+        }
+      }
+    }
+  }
+}
+// g[j - 1] of a sorted register array, j in 1..32 (select chain instead of a dynamic index)
+__device__ __forceinline__ uint32_t pick_rank32(const uint32_t (&g)[32], uint32_t j) {
+  uint32_t est = g[0];
+#pragma unroll
+  for (int i = 1; i < 32; i++) est = (uint32_t)i == j - 1 ? g[i] : est;
+  return est;
+}
 
 // ---------------------------------------------------------------- tcgen05 / TMA PTX wrappers
 __device__ __forceinline__ void tma_load_2d_bf16(void *smem_dst, const CUtensorMap *tm, int32_t c0, int32_t c1,
@@ -190,11 +220,19 @@ __device__ __forceinline__ unsigned long long gtime() {
   } while (0)
 #endif
 // ---------------------------------------------------------------- the candidate kernel
-template <bool PAIR, int BN_>
+// SEED = the sampling pass launched ahead of the candidate pass: the same producer / MMA / TMEM pipeline over the
+// FIRST p.seed_tiles tiles of every CTA's slab, with an epilogue that appends nothing — it keeps, per query, the
+// minimum score of every 32-row group (one group per epilogue warp and tile) and publishes the j-th smallest of those
+// group minima as the slab's first bound (gsl).  The candidate pass then gates its very first tile on max_s gsl[q][s]
+// instead of on +inf: without it every row of the first two tiles passes (32 K appends per tile and CTA) and the
+// first ~16 tiles run at a fifth of the steady rate (trace in DESIGN.md section 5).
+template <bool PAIR, int BN_, bool SEED = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
     flat_tensor_kernel(const TensorParams p, const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB) {
   constexpr int BN = BN_;  // shadows the namespace-level default: everything below is per instantiation
   static_assert(BN % 64 == 0 && BN <= 256, "two column halves of whole 32-column chunks");
+  static_assert(!(SEED && PAIR), "the sampling pass is single-CTA");
+  const uint32_t tile_limit = SEED ? p.seed_tiles : 0xffffffffu;  // tiles per CTA
   constexpr int STAGES = Ring<PAIR, BN_>::kStages;
   constexpr int B_STAGE_BYTES = Ring<PAIR, BN_>::kBStage;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -202,7 +240,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint8_t *sB = smem + STAGES * A_STAGE_BYTES;          // [STAGES][32 KB | 16 KB]
   uint8_t *tail = sB + STAGES * B_STAGE_BYTES;
   Cand *scratch = reinterpret_cast<Cand *>(tail);       // [4 warps][kprime]  shrink compaction buffers
-  uint8_t *ctl = tail + (size_t)4 * p.kprime * sizeof(Cand);
+  uint8_t *ctl = tail + (SEED ? (size_t)32 * BN * 4 : (size_t)4 * p.kprime * sizeof(Cand));  // SEED: minima [32][BN]
   uint64_t *full = reinterpret_cast<uint64_t *>(ctl);   // [STAGES]
   uint64_t *empty = full + STAGES;                      // [STAGES]
   uint64_t *tfull = empty + STAGES;                     // [2]
@@ -262,8 +300,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
     if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs) {
+      uint32_t stage = 0, phase = 0, tp = 0;
+      for (uint32_t tile = slab; tile < total_tiles && tp < tile_limit; tile += p.slabs, tp++) {
         for (uint32_t kb = 0; kb < p.kchunks; kb++) {
           mbar_wait_parked(&empty[stage], phase ^ 1);
           if constexpr (PAIR) {
@@ -288,7 +326,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // ------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0 && rank == 0) {
       uint32_t stage = 0, phase = 0, t = 0;
-      for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
+      for (uint32_t tile = slab; tile < total_tiles && t < tile_limit; tile += p.slabs, t++) {
         const uint32_t a = t & 1;
         VK_TRACE(4, t, true);
         mbar_wait_parked(&tempty[a], ((t >> 1) & 1) ^ 1);  // epilogue (of both CTAs) has drained this accumulator
@@ -397,6 +435,53 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     };
     auto tmem_wait = [] { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); };
 
+    if constexpr (SEED) {
+      // ---- sampling epilogue: group minima only.  minima[g][c]: g = 4 * tile + row quadrant (<= 32 groups).
+      uint32_t *minima = reinterpret_cast<uint32_t *>(scratch);  // [32][BN]
+      for (uint32_t i = tid - 128; i < 32u * BN; i += EPI_THREADS) minima[i] = kOrdInf;
+      named_bar_sync(2, EPI_THREADS);
+      for (uint32_t tile = slab; tile < total_tiles && t < tile_limit; tile += p.slabs, t++) {
+        const uint32_t a = t & 1;
+        const uint64_t slot = (uint64_t)tile * BM + et;
+        const bool valid = slot < p.n_rows;
+        const float xn = (valid && p.metric_l2) ? p.xnorm[slot] : 0.0f;
+        mbar_wait_parked(&tfull[a], (t >> 1) & 1);
+        tc_fence_after();
+        const uint32_t tbase = tmem_base + (lane_base << 16) + a * BN;
+        uint32_t ra[32];
+#pragma unroll 1
+        for (uint32_t c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32) {
+          tmem_ld32_async(tbase + c0, ra);
+          tmem_wait();
+          uint32_t mine = kOrdInf;
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float sc = p.metric_l2 ? __fmaf_rn(-2.0f, __uint_as_float(ra[j]), xn) : -__uint_as_float(ra[j]);
+            const uint32_t v = __reduce_min_sync(0xffffffffu, valid ? f32_to_ord(sc) : kOrdInf);
+            mine = lane == (uint32_t)j ? v : mine;
+          }
+          minima[(4 * t + (warp & 3)) * BN + c0 + lane] = mine;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[a]);
+      }
+      named_bar_sync(2, EPI_THREADS);
+      // thread per query: j-th smallest of the group minima = an upper bound of the slab's j-th best score (each
+      // group minimum is a distinct row of this slab), published where the candidate pass reads its first bounds
+      const uint32_t c = tid - 128;
+      if (c < (uint32_t)BN && p.jrank <= 32) {
+        uint32_t g[32];
+#pragma unroll
+        for (int i = 0; i < 32; i++) g[i] = minima[i * BN + c];
+        sort32_regs(g);
+        const uint32_t est = pick_rank32(g, p.jrank);
+        // (+16 ulps: the candidate pass recomputes these very scores with the same instruction sequence and gets the
+        //  same bits; the slack only makes the bound indifferent to that)
+        if (est < kOrdInf - 16) p.gsl[((size_t)qtile * BN + c) * p.gsl_stride + slab] = est + 16;
+      }
+    } else {
+
     // Cheap upper bound of the j-th smallest score in a query's list: take the list's most recent entries
     // (later entries passed tighter gates, so the slab's best rows are almost always among them; any subset still
     // gives a valid bound), deal them into 32 groups, and take the j-th smallest of the 32 group minima: it
@@ -428,28 +513,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
           g[2 * i + 1] = min(g[2 * i + 1], min(idx + 2 < n ? v.z : kOrdInf, idx + 3 < n ? v.w : kOrdInf));
         }
       }
-      // bitonic sorting network, ascending (240 compare-exchanges on registers)
-#pragma unroll
-      for (int ks = 1; ks <= 5; ks++) {
-#pragma unroll
-        for (int js = 4; js >= 0; js--) {
-          if (js >= ks) continue;
-          const int k = 1 << ks, j = 1 << js;
-#pragma unroll
-          for (int i = 0; i < 32; i++) {
-            const int l = i ^ j;
-            if (l > i) {
-              const uint32_t lo = min(g[i], g[l]), hi = max(g[i], g[l]);
-              const bool up = (i & k) == 0;
-              g[i] = up ? lo : hi;
-              g[l] = up ? hi : lo;
-            }
-          }
-        }
-      }
-      uint32_t est = g[0];
-#pragma unroll
-      for (int i = 1; i < 32; i++) est = (uint32_t)i == p.jrank - 1 ? g[i] : est;
+      sort32_regs(g);
+      const uint32_t est = pick_rank32(g, p.jrank);
       // fire-and-forget reduction (RED.MIN): a read-compare-write would cost another L2 round trip
       if (n >= p.jrank && est != kOrdInf) atomicMin(&p.gsl[((size_t)qtile * BN + c) * p.gsl_stride + slab], est);
     };
@@ -649,6 +714,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     named_bar_sync(2, EPI_THREADS);
     for (uint32_t c = tid - 128; c < BN; c += EPI_THREADS)
       p.ws_cnt[((size_t)qtile * p.slabs + slab) * BN + c] = min(cnt[c], p.cap);
+    }  // !SEED
   }
 
   tc_fence_before();
@@ -781,7 +847,9 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankParams p
   if (tid == 0) {
     p.out_n[b] = nout;
     uint32_t flag = 0;
-    if (n >= p.kprime && (uint64_t)p.kprime < p.n_rows) {
+    if (n < p.kprime && (uint64_t)p.kprime < p.n_rows) {
+      flag = 1;  // fewer survivors than K' on a corpus that has more rows: never expected, answered by the exact scan
+    } else if ((uint64_t)p.kprime < p.n_rows) {
       // Proof that no row OUTSIDE the K' survivors belongs to the reference's top k.  Such a row i has an approximate
       // score >= gK (the K'-th smallest), hence a true score s_i >= gK - e, where e bounds |approximate - true|:
       // bf16 rounding of both operands and the tensor core's fp32 accumulation (err_coef |q| max|x|), plus the fp32
@@ -889,6 +957,8 @@ void tensor_prepare(vkgpu_index_impl *ix) {
       VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
       VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<true, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
       VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+      VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
+      VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
       VK_CUDA(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       VK_CUDA(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     }
@@ -938,7 +1008,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
     const char *e = getenv("VKGPU_TENSOR_PAIR");
     return e && e[0] == '1';
   }();
-  const bool pair = pair_env && bn == (uint32_t)BN && total_tiles >= 2 && ix->num_sms / 2 >= nq_tiles;
+  const bool pair = pair_env && bn == (uint32_t)BN && total_tiles >= 2 && (uint32_t)ix->num_sms / 2 >= nq_tiles;
   uint32_t slabs;  // CTA-level corpus slabs per query tile
   if (pair) {
     const uint32_t pslabs = std::min<uint32_t>(std::max<uint32_t>(1, (ix->num_sms / 2) / nq_tiles), (total_tiles + 1) / 2);
@@ -992,7 +1062,33 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
                 "all ring geometries use the same shared memory");
   const size_t smem = (size_t)Ring<true>::kBytes + (size_t)4 * kprime * sizeof(Cand) + 256 + BN * 8 + 64;
   VK_REQUIRE(smem <= ix->smem_max, VKGPU_ERR_INTERNAL, "tensor kernel shared memory budget exceeded");
+  // Sampling pass: worth its 4-8 extra tiles per CTA once a CTA walks a few dozen tiles.  The bound it publishes is the
+  // j-th smallest of 4 * seed_tiles group minima, so it needs a few more groups than j.
+  uint32_t seed_tiles = 0;
+  {
+    static const bool seed_off = [] {
+      const char *e = getenv("VKGPU_TENSOR_SEED");
+      return e && e[0] == '0';
+    }();
+    const uint32_t tiles_per_cta = total_tiles / slabs;
+    if (!pair && !seed_off && tiles_per_cta >= 32) {
+      seed_tiles = tiles_per_cta >= 512 ? 8 : 4;
+      if (4 * seed_tiles < tp.jrank + 4) seed_tiles = 8;
+      if (4 * seed_tiles < tp.jrank + 4) seed_tiles = 0;
+    }
+  }
+  tp.seed_tiles = seed_tiles;
+  const size_t smem_seed = (size_t)Ring<true>::kBytes + (size_t)32 * bn * 4 + 256 + BN * 8 + 64;
+  VK_REQUIRE(seed_tiles == 0 || smem_seed <= ix->smem_max, VKGPU_ERR_INTERNAL, "sampling pass shared memory budget exceeded");
   ix->prof_begin(c, KK_TENSOR);
+  if (seed_tiles) {
+    if (bn == (uint32_t)BN)
+      flat_tensor_kernel<false, BN, true><<<nq_tiles * slabs, TC_THREADS, smem_seed, s>>>(tp, tmA, tmB);
+    else
+      flat_tensor_kernel<false, BN_SMALL, true><<<nq_tiles * slabs, TC_THREADS, smem_seed, s>>>(tp, tmA, tmB);
+    VK_CUDA(cudaGetLastError());
+    ix->kernels++;
+  }
   if (pair) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(nq_tiles * slabs);
