@@ -186,3 +186,46 @@ def test_headline_shape_2M_rows_batch_1024_k100_vs_exact_scan_and_cpu_reference(
     assert (nc == k).all()
     assert np.array_equal(lc, l1[sel2]), np.argwhere(lc != l1[sel2])[:5]
     assert np.array_equal(_bits(dc), _bits(d1[sel2]))
+
+
+@pytest.mark.parametrize("n_dup, B", [(3000, 64), (40_000, 1000)])
+def test_tensor_path_device_entry_reruns_flagged_queries_without_the_host(built, n_dup, B):
+    """vkgpu_search_batch_device on a caller's stream: queries whose proof fails are compacted and re-run by the
+    device-driven exact scan (no host synchronisation inside the call).  Case 1: a few of the queries sit on a cluster
+    of near-identical rows.  Case 2: EVERY row is a near copy of one vector, so all 1000 queries are flagged — more
+    re-run queries than the fixed grid has CTA groups, each CTA walks several of them.  Both must equal the exact
+    scan bit for bit, and the re-run count must show up in the stats once the stream has been synchronised."""
+    torch = pytest.importorskip("torch")
+    import ctypes as C
+    import valkey_search_b200 as V
+    from valkey_search_b200 import _lib as L
+    rng = np.random.default_rng(21)
+    N, D, k = 40_000, 128, 20
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    centre = rng.standard_normal(D).astype(np.float32)
+    X[:n_dup] = centre + 1e-4 * rng.standard_normal((n_dup, D)).astype(np.float32)
+    Q = rng.standard_normal((B, D)).astype(np.float32)
+    n_near = 8 if n_dup < N else B
+    Q[:n_near] = centre + 1e-4 * rng.standard_normal((n_near, D)).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    ix.SetSearchPath(V.PATH_EXACT_FMA)
+    d0, l0, _ = ix.SearchBatchRaw(Q, k)
+    ix.SetSearchPath(V.PATH_TENSOR)
+    lib = L.lib()
+    dev = torch.device("cuda", 0)
+    dQ = torch.from_numpy(Q).to(dev)
+    od = torch.zeros((B, k), dtype=torch.float32, device=dev)
+    ol = torch.zeros((B, k), dtype=torch.int64, device=dev)
+    on = torch.zeros((B,), dtype=torch.int32, device=dev)
+    st = torch.cuda.Stream(device=dev)
+    torch.cuda.synchronize()
+    before = ix.stats().tensor_fallbacks
+    with torch.cuda.stream(st):
+        L.check(lib.vkgpu_search_batch_device(ix.handle(), dQ.data_ptr(), B, k, 0, od.data_ptr(), ol.data_ptr(),
+                                              on.data_ptr(), C.c_void_p(st.cuda_stream)))
+    st.synchronize()
+    assert np.array_equal(ol.cpu().numpy().astype(np.uint64), l0)
+    assert np.array_equal(_bits(od.cpu().numpy()), _bits(d0))
+    assert (on.cpu().numpy() == k).all()
+    assert ix.stats().tensor_fallbacks - before >= n_near

@@ -476,72 +476,88 @@ __global__ void __launch_bounds__(GLT) gather_scan_ldg_kernel(const GatherParams
   Cand *scratch = reinterpret_cast<Cand *>(gsm + ((p.Dp * 4 + 127) & ~127u));
   uint32_t *sh = reinterpret_cast<uint32_t *>(scratch + p.cap);  // [0]=thr [1]=cnt
   const uint32_t tid = threadIdx.x, gi = tid >> 2, u = tid & 3;
-  const uint32_t b = blockIdx.x, slab = blockIdx.y, slabs = gridDim.y;
-  const uint32_t *ids = p.list_ptr[b];
-  const uint64_t n = p.list_len[b];
   constexpr uint32_t R = GLT / 4;
-  const uint32_t tiles = (uint32_t)((n + R - 1) / R);
-  Cand *my = p.ws + ((size_t)b * slabs + slab) * p.cap;
-  if (tid == 0) {
-    sh[0] = kOrdInf;
-    sh[1] = 0;
+  // host-driven: grid (B, slabs), one query per CTA column; device-driven: 1-D grid regrouped from p.redo
+  uint32_t b = blockIdx.x, slab = blockIdx.y, slabs = gridDim.y, qr = 0, groups = 1, count = 1;
+  if (p.redo) {
+    count = p.redo[0];
+    if (count == 0) return;
+    slabs = p.redo[1];
+    groups = gridDim.x / slabs;
+    slab = blockIdx.x % slabs;
+    qr = blockIdx.x / slabs;
+    if (qr >= groups) return;
   }
-  for (uint32_t i = tid; i < p.Dp / 4; i += GLT)
-    reinterpret_cast<float4 *>(q)[i] = reinterpret_cast<const float4 *>(p.Q + (size_t)b * p.Dp)[i];
-  __syncthreads();
-  uint32_t next_id = 0;
-  {
-    const uint64_t r = (uint64_t)slab * R + gi;
-    if (slab < tiles && r < n) next_id = ids[r];
-  }
-  for (uint32_t tile = slab; tile < tiles; tile += slabs) {
-    const uint64_t r = (uint64_t)tile * R + gi;
-    const bool act = r < n;
-    const uint32_t slot = next_id;
-    {  // the next tile's row id travels while this row is being read
-      const uint64_t rn = (uint64_t)(tile + slabs) * R + gi;
-      next_id = (tile + slabs < tiles && rn < n) ? ids[rn] : 0u;
+  for (; qr < count; qr += groups) {
+    if (p.redo) b = p.redo[2 + qr];
+    const uint32_t *ids = p.redo ? nullptr : p.list_ptr[b];
+    const uint64_t n = p.redo ? p.n_rows_all : p.list_len[b];
+    const size_t list = p.redo ? (size_t)qr * slabs + slab : (size_t)b * slabs + slab;
+    const uint32_t tiles = (uint32_t)((n + R - 1) / R);
+    Cand *my = p.ws + list * p.cap;
+    if (tid == 0) {
+      sh[0] = kOrdInf;
+      sh[1] = 0;
     }
-    const float d = exact_dist_group<L2, true>(p.X + (size_t)(act ? slot : 0) * p.Dp, q, p.Dp, u, act);
-    if (act && u == 0) {
-      const uint32_t o = f32_to_ord(d);
-      if (o <= sh[0]) {
-        const uint32_t pos = atomicAdd(&sh[1], 1u);
-        Cand cd;
-        cd.ord = o;
-        cd.slot = slot;
-        cd.label = p.labels[slot];
-        my[pos] = cd;  // pos < cap by the trim rule below
+    for (uint32_t i = tid; i < p.Dp / 4; i += GLT)
+      reinterpret_cast<float4 *>(q)[i] = reinterpret_cast<const float4 *>(p.Q + (size_t)b * p.Dp)[i];
+    __syncthreads();
+    uint32_t next_id = 0;
+    {
+      const uint64_t r = (uint64_t)slab * R + gi;
+      if (slab < tiles && r < n) next_id = ids ? ids[r] : (uint32_t)r;
+    }
+    for (uint32_t tile = slab; tile < tiles; tile += slabs) {
+      const uint64_t r = (uint64_t)tile * R + gi;
+      const bool act = r < n;
+      const uint32_t slot = next_id;
+      {  // the next tile's row id travels while this row is being read
+        const uint64_t rn = (uint64_t)(tile + slabs) * R + gi;
+        next_id = (tile + slabs < tiles && rn < n) ? (ids ? ids[rn] : (uint32_t)rn) : 0u;
       }
-    }
-    __syncthreads();
-    const uint32_t cntv = sh[1];
-    __syncthreads();
-    if (cntv + R > p.cap) {  // uniform
-      for (uint32_t i = tid; i < p.cap; i += GLT) {
-        Cand cd;
-        if (i < cntv) {
-          cd = my[i];
-        } else {
-          cd.ord = kOrdInf;
-          cd.slot = 0xffffffffu;
-          cd.label = ~0ull;
+      const float d = exact_dist_group<L2, true>(p.X + (size_t)(act ? slot : 0) * p.Dp, q, p.Dp, u, act);
+      if (act && u == 0) {
+        const uint32_t o = f32_to_ord(d);
+        if (o <= sh[0]) {
+          const uint32_t pos = atomicAdd(&sh[1], 1u);
+          Cand cd;
+          cd.ord = o;
+          cd.slot = slot;
+          cd.label = p.labels[slot];
+          my[pos] = cd;  // pos < cap by the trim rule below
         }
-        scratch[i] = cd;
       }
       __syncthreads();
-      bitonic_sort_cands(scratch, p.cap, tid, GLT, [] { __syncthreads(); });
-      const uint32_t keep = min(cntv, p.k);
-      for (uint32_t i = tid; i < keep; i += GLT) my[i] = scratch[i];
-      if (tid == 0) {
-        sh[1] = keep;
-        if (keep == p.k) sh[0] = scratch[p.k - 1].ord;
-      }
+      const uint32_t cntv = sh[1];
       __syncthreads();
+      if (cntv + R > p.cap) {  // uniform
+        for (uint32_t i = tid; i < p.cap; i += GLT) {
+          Cand cd;
+          if (i < cntv) {
+            cd = my[i];
+          } else {
+            cd.ord = kOrdInf;
+            cd.slot = 0xffffffffu;
+            cd.label = ~0ull;
+          }
+          scratch[i] = cd;
+        }
+        __syncthreads();
+        bitonic_sort_cands(scratch, p.cap, tid, GLT, [] { __syncthreads(); });
+        const uint32_t keep = min(cntv, p.k);
+        for (uint32_t i = tid; i < keep; i += GLT) my[i] = scratch[i];
+        if (tid == 0) {
+          sh[1] = keep;
+          if (keep == p.k) sh[0] = scratch[p.k - 1].ord;
+        }
+        __syncthreads();
+      }
     }
+    __syncthreads();
+    if (tid == 0) p.ws_cnt[list] = sh[1];
+    if (!p.redo) break;
+    __syncthreads();  // the next query of this CTA re-initialises the shared state
   }
-  __syncthreads();
-  if (tid == 0) p.ws_cnt[(size_t)b * slabs + slab] = sh[1];
 }
 }  // namespace
 
@@ -588,8 +604,11 @@ constexpr int MERGE_THREADS = 256;
 // fills.  Exact for any input (all ties ordered by label); used directly for huge k and as the in-kernel fallback
 // of the selection merge when more equal-distance entries than the buffer holds straddle the K-th place.
 __device__ void merge_by_sorting(const MergeParams &p, Cand *buf) {
-  const uint32_t b = blockIdx.x, tid = threadIdx.x;
-  const uint32_t qtile = b / p.qt, qi = b % p.qt;
+  const uint32_t tid = threadIdx.x;
+  // device-driven form: CTA i handles the i-th re-run query (the caller has checked i < redo[0])
+  const uint32_t b = p.redo ? p.redo[2 + blockIdx.x] : blockIdx.x;
+  const uint32_t nslabs = p.redo ? p.redo[1] : p.slabs;
+  const uint32_t qtile = blockIdx.x / p.qt, qi = blockIdx.x % p.qt;
   const uint32_t N = p.sort_n, K = p.k;
   auto sync = [] { __syncthreads(); };
 
@@ -601,8 +620,8 @@ __device__ void merge_by_sorting(const MergeParams &p, Cand *buf) {
   __syncthreads();
 
   uint32_t have = 0;  // uniform: valid entries currently in buf[0..have)
-  for (uint32_t s = 0; s < p.slabs; s++) {
-    const size_t li = ((size_t)qtile * p.slabs + s) * p.qt + qi;
+  for (uint32_t s = 0; s < nslabs; s++) {
+    const size_t li = p.redo ? (size_t)blockIdx.x * nslabs + s : ((size_t)qtile * p.slabs + s) * p.qt + qi;
     const uint32_t n = min(p.ws_cnt[li], p.cap);
     const Cand *src = p.ws + li * p.cap;
     uint32_t done = 0;
@@ -640,6 +659,7 @@ __device__ void merge_by_sorting(const MergeParams &p, Cand *buf) {
 
 __global__ void __launch_bounds__(MERGE_THREADS) topk_merge_kernel(const MergeParams p) {
   extern __shared__ __align__(16) uint8_t msm[];
+  if (p.redo && blockIdx.x >= p.redo[0]) return;
   merge_by_sorting(p, reinterpret_cast<Cand *>(msm));
 }
 }  // namespace
@@ -660,10 +680,15 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
   uint32_t *s_cnt = hist + 2048;                                               // [slabs]
   __shared__ uint32_t part[MERGE_THREADS];
   __shared__ uint32_t s_prefix, s_rank, s_pos, s_tie, s_total;
-  const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const uint32_t qtile = b / p.qt, qi = b % p.qt;
+  const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (p.redo && blockIdx.x >= p.redo[0]) return;  // device-driven form: CTA i = i-th re-run query
+  const uint32_t b = p.redo ? p.redo[2 + blockIdx.x] : blockIdx.x;  // output row
+  const uint32_t nslabs = p.redo ? p.redo[1] : p.slabs;
+  const uint32_t qtile = blockIdx.x / p.qt, qi = blockIdx.x % p.qt;
   const uint32_t K = p.k;
-  auto list_index = [&](uint32_t s) -> size_t { return ((size_t)qtile * p.slabs + s) * p.qt + qi; };
+  auto list_index = [&](uint32_t s) -> size_t {
+    return p.redo ? (size_t)blockIdx.x * nslabs + s : ((size_t)qtile * p.slabs + s) * p.qt + qi;
+  };
   if (tid == 0) {
     s_total = 0;
     s_prefix = 0;
@@ -674,7 +699,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
   __syncthreads();
   {  // list lengths -> shared memory (all loads in flight at once), total
     uint32_t tot = 0;
-    for (uint32_t s = tid; s < p.slabs; s += MERGE_THREADS) {
+    for (uint32_t s = tid; s < nslabs; s += MERGE_THREADS) {
       const uint32_t n = min(p.ws_cnt[list_index(s)], p.cap);
       s_cnt[s] = n;
       tot += n;
@@ -693,7 +718,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
   // the merge a chain of dependent round trips: 0.45 ms for a 2-query batch.)  Scores come from the compact
   // score-only copy when the producer keeps one (4-byte stride instead of 16).
   auto for_each_score = [&](auto fn) {
-    for (uint32_t s = warp; s < p.slabs; s += MERGE_THREADS / 32) {
+    for (uint32_t s = warp; s < nslabs; s += MERGE_THREADS / 32) {
       const uint32_t n = s_cnt[s];
       const size_t base = list_index(s) * p.cap;
       for (uint32_t i0 = lane; i0 < n; i0 += 128) {

@@ -58,6 +58,12 @@ struct GatherParams {
   uint32_t Dp, k, cap, rows_per_stage, stages;  // ring of `stages` buffers of rows_per_stage rows each
   Cand *ws;                  // [B][slabs][cap]
   uint32_t *ws_cnt;          // [B][slabs]
+  // Device-driven form (the tensor path's exact re-run of the queries whose proof failed — no host in the loop):
+  // redo[0] = queries to answer, redo[1] = slabs per query, redo[2 + i] = index of the i-th query in Q.  The grid is
+  // 1-D and fixed; CTAs regroup themselves from redo[0..1], scan ALL rows [0, n_rows_all) (no slot lists) and exit at
+  // once when redo[0] == 0.  List (i, slab) lives at ws + (i * redo[1] + slab) * cap.
+  const uint32_t *redo;      // nullptr => the host-driven form above
+  uint64_t n_rows_all;
 };
 void gather_scan_set_smem_attr(size_t max_smem);
 size_t gather_smem_bytes(uint32_t Dp, uint32_t rows_per_stage, uint32_t stages, uint32_t cap);
@@ -81,6 +87,9 @@ struct MergeParams {
   uint32_t *out_n;         // [B]
   const uint32_t *k_limit; // optional per-query cap on results (nullptr => k)
   const uint32_t *ws_ord;  // optional: the lists' scores alone, same [list][cap] shape (selection merge scans these)
+  // device-driven form (see GatherParams::redo): CTA i >= redo[0] exits; lists of query i are (i * redo[1] + s),
+  // s < redo[1]; results go to output row redo[2 + i].  `slabs` is then only the upper bound that sizes shared memory.
+  const uint32_t *redo;
 };
 void launch_topk_merge(uint32_t B, cudaStream_t stream, const MergeParams &p);
 // same contract, for approximate scores: ties at the K-th score are broken arbitrarily; sort_n = pow2 >= k

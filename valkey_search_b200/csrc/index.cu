@@ -152,7 +152,7 @@ size_t vkgpu_index_impl::hbm_bytes() const {
   for (auto &c : ctxs)
     b += c->q_pad.bytes + c->ws.bytes + c->ws_cnt.bytes + c->out_dist.bytes + c->out_labels.bytes +
          c->out_n.bytes + c->out_slots.bytes + c->lists.bytes + c->list_off.bytes + c->scratch0.bytes +
-         c->scratch1.bytes + c->scratch2.bytes + c->scratch3.bytes;
+         c->scratch1.bytes + c->scratch2.bytes + c->scratch3.bytes + c->fb_redo.bytes + c->fb_ws.bytes + c->fb_cnt.bytes;
   if (hnsw) b += hnsw_hbm_bytes(hnsw);
   return b;
 }
@@ -565,7 +565,12 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     k_eff = (uint32_t)std::min<uint64_t>(k, ix->n);
     bool use_tensor = false;
     if (ix->flat_path == VKGPU_PATH_TENSOR) use_tensor = true;
-    if (ix->flat_path == VKGPU_PATH_AUTO && k_eff <= 128 && !ix->tensor_unavailable && tensor_path_cheaper(ix, B)) {
+    // AUTO gives the tensor path up for an index whose queries keep failing the proof (e.g. a corpus of near-identical
+    // rows: every score ties): a re-run streams the whole corpus per query, five times what the exact scan costs
+    const uint64_t tq = ix->tensor_queries.load();
+    const bool tensor_unprofitable = tq >= 4096 && tensor_fallbacks_seen(ix) * 8 > tq;
+    if (ix->flat_path == VKGPU_PATH_AUTO && k_eff <= 128 && !ix->tensor_unavailable && !tensor_unprofitable &&
+        tensor_path_cheaper(ix, B)) {
       // first large batch: build the bf16 mirror (searches only read the fp32 rows, so this is safe under
       // the shared lock; tensor_mu makes it happen once).  No room for the mirror: the exact scan answers, for good.
       std::lock_guard<std::mutex> tl(ix->tensor_mu);
@@ -793,7 +798,8 @@ void vkgpu_index_destroy(vkgpu_index *ix) {
       if (c->ev_end[i]) cudaEventDestroy(c->ev_end[i]);
     }
     for (DevBuf *b : {&c->q_pad, &c->ws, &c->ws_cnt, &c->out_dist, &c->out_labels, &c->out_n, &c->out_slots,
-                      &c->lists, &c->list_off, &c->klimit, &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3})
+                      &c->lists, &c->list_off, &c->klimit, &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3,
+                      &c->fb_redo, &c->fb_ws, &c->fb_cnt})
       b->release();
     for (PinnedBuf *b : {&c->h_q, &c->h_dist, &c->h_labels, &c->h_n, &c->h_misc}) b->release();
   }
@@ -1160,7 +1166,7 @@ int vkgpu_get_stats(vkgpu_index *ix, vkgpu_stats *out) {
     out->kernels_launched = ix->kernels;
     out->distance_evals = ix->dist_evals;
     out->hops = ix->hops;
-    out->tensor_fallbacks = ix->tensor_fallbacks;
+    out->tensor_fallbacks = tensor_fallbacks_seen(ix);
     out->max_level = ix->hnsw ? hnsw_max_level(ix) : 0;
     out->dim = (int32_t)ix->dim;
     out->last_qt = ix->last_qt;

@@ -101,6 +101,7 @@ struct SearchCtx {
   DevBuf lists, list_off;  // gather lists (pre-filter)
   DevBuf klimit;
   DevBuf scratch0, scratch1, scratch2, scratch3;  // path-specific (tensor / hnsw)
+  DevBuf fb_redo, fb_ws, fb_cnt;  // tensor path: device-driven exact re-run of the queries whose proof failed
   PinnedBuf h_q, h_dist, h_labels, h_n, h_misc;
   bool busy = false;
   cudaStream_t cur = nullptr;     // stream this call runs on (own stream, or the caller's)
@@ -179,7 +180,11 @@ struct vkgpu_index_impl {
   cudaStream_t mut_stream = nullptr;
   PinnedBuf h_stage;  // staging for single-row uploads
 
-  std::atomic<uint64_t> searches{0}, kernels{0}, dist_evals{0}, hops{0}, tensor_fallbacks{0};
+  std::atomic<uint64_t> searches{0}, kernels{0}, dist_evals{0}, hops{0};
+  // tensor path: queries sent through it, and re-runs counted by mirrors that have since been released (the live
+  // mirror's count sits in its TensorState: tensor_fallbacks_seen())
+  std::atomic<uint64_t> tensor_queries{0};
+  uint64_t tensor_fallbacks_base = 0;
   std::atomic<uint32_t> last_qt{0}, last_passes{0};
   bool profiling = false;
   std::mutex prof_mu;

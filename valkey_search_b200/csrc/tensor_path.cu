@@ -877,9 +877,31 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankParams p
   }
 }
 
+// Queries whose proof failed, compacted on the device: redo[0] = how many, redo[1] = row slabs each of them gets in
+// the exact re-run (the fixed grid of `grid_ctas` CTAs divided among them), redo[2..] = their indexes.  `cum` is the
+// index's running total (read by vkgpu_get_stats and by the AUTO policy).
+__global__ void __launch_bounds__(1024) redo_compact_kernel(const uint32_t *flags, uint32_t B, uint32_t *redo,
+                                                            uint32_t grid_ctas, uint32_t max_slabs,
+                                                            unsigned long long *cum) {
+  __shared__ uint32_t s_n;
+  if (threadIdx.x == 0) s_n = 0;
+  __syncthreads();
+  for (uint32_t b = threadIdx.x; b < B; b += blockDim.x)
+    if (flags[b]) redo[2 + atomicAdd(&s_n, 1u)] = b;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const uint32_t n = s_n;
+    redo[0] = n;
+    redo[1] = n ? max(1u, min(grid_ctas / n, max_slabs)) : 1u;
+    if (n) atomicAdd(cum, (unsigned long long)n);
+  }
+}
+
 struct TensorState {
   uint32_t Dh = 0;
   DevBuf max_norm;  // 1 x u32
+  DevBuf fb_total;  // 1 x u64: queries re-run on the exact scan so far (device side of vkgpu_stats.tensor_fallbacks)
+  PinnedBuf h_fb_total;  // its host copy, refreshed by an asynchronous copy after every search
 };
 
 TensorState *ts(vkgpu_index_impl *ix) { return reinterpret_cast<TensorState *>(ix->tensor_state); }
@@ -947,6 +969,10 @@ void tensor_prepare(vkgpu_index_impl *ix) {
   try {
     t->max_norm.reserve(4);
     VK_CUDA(cudaMemsetAsync(t->max_norm.p, 0, 4, ix->mut_stream));
+    t->fb_total.reserve(8);
+    VK_CUDA(cudaMemsetAsync(t->fb_total.p, 0, 8, ix->mut_stream));
+    t->h_fb_total.reserve(8);
+    *t->h_fb_total.as<uint64_t>() = 0;
     const uint64_t rows = std::max<uint64_t>(ix->phys_cap, 1);
     ix->dXh.reserve(rows * (size_t)t->Dh * 2);
     ix->dNorm.reserve(rows * 4);
@@ -974,7 +1000,10 @@ void tensor_release(vkgpu_index_impl *ix) {
   ix->dXh.release();
   ix->dNorm.release();
   if (ix->tensor_state) {
+    ix->tensor_fallbacks_base += *ts(ix)->h_fb_total.as<volatile uint64_t>();
     ts(ix)->max_norm.release();
+    ts(ix)->fb_total.release();
+    ts(ix)->h_fb_total.release();
     delete ts(ix);
     ix->tensor_state = nullptr;
   }
@@ -1202,37 +1231,56 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   ix->last_qt = bn;
   ix->last_passes = nq_tiles;
 
-  // queries whose margin was too thin are re-run on the exact scan (GPU), results patched in place
-  c->h_misc.reserve((size_t)B * 4);
-  VK_CUDA(cudaMemcpyAsync(c->h_misc.p, rp.flags, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-  VK_CUDA(cudaStreamSynchronize(s));
-  std::vector<uint32_t> redo;
-  for (uint32_t b = 0; b < B; b++)
-    if (c->h_misc.as<uint32_t>()[b]) redo.push_back(b);
-  if (!redo.empty()) {
-    ix->tensor_fallbacks += redo.size();
-    CtxLease lease2(ix);
-    SearchCtx *c2 = lease2.c;
-    c2->cur = s;
-    const uint32_t R = (uint32_t)redo.size();
-    const uint32_t Rpad = (R + kScanMaxQt - 1) / kScanMaxQt * kScanMaxQt;
-    c2->q_pad.reserve((size_t)Rpad * ix->Dp * 4);
-    VK_CUDA(cudaMemsetAsync(c2->q_pad.p, 0, (size_t)Rpad * ix->Dp * 4, s));
-    for (uint32_t i = 0; i < R; i++)
-      VK_CUDA(cudaMemcpyAsync(c2->q_pad.as<float>() + (size_t)i * ix->Dp, c->q_pad.as<float>() + (size_t)redo[i] * ix->Dp,
-                              (size_t)ix->Dp * 4, cudaMemcpyDeviceToDevice, s));
-    flat_exact_search_device(ix, c2, R, k_eff);
-    for (uint32_t i = 0; i < R; i++) {
-      VK_CUDA(cudaMemcpyAsync(c->out_dist.as<float>() + (size_t)redo[i] * k_eff, c2->out_dist.as<float>() + (size_t)i * k_eff,
-                              (size_t)k_eff * 4, cudaMemcpyDeviceToDevice, s));
-      VK_CUDA(cudaMemcpyAsync(c->out_labels.as<uint64_t>() + (size_t)redo[i] * k_eff,
-                              c2->out_labels.as<uint64_t>() + (size_t)i * k_eff, (size_t)k_eff * 8,
-                              cudaMemcpyDeviceToDevice, s));
-      VK_CUDA(cudaMemcpyAsync(c->out_n.as<uint32_t>() + redo[i], c2->out_n.as<uint32_t>() + i, 4,
-                              cudaMemcpyDeviceToDevice, s));
-    }
-    VK_CUDA(cudaStreamSynchronize(s));
+  // Queries whose margin was too thin are re-run in the reference's exact fp32 order and patched in place — decided
+  // and launched without the host: the flags are compacted on the device, and a fixed grid of the row-streaming scan
+  // (gather_scan_ldg_kernel over all rows) divides itself among the flagged queries, or exits at once when there are
+  // none (the usual case: three near-empty launches instead of a device-to-host copy and a stream synchronisation).
+  {
+    const uint32_t fb_cap = 256;  // k_eff <= 128 on this path: cap >= k + 64
+    const uint32_t fb_grid = 6 * (uint32_t)ix->num_sms;
+    const uint32_t fb_tiles = (uint32_t)std::max<uint64_t>(1, (ix->n + 63) / 64);
+    const size_t fb_lists = std::max<size_t>(fb_grid, B);
+    c->fb_redo.reserve((size_t)(2 + B) * 4);
+    c->fb_ws.reserve(fb_lists * fb_cap * sizeof(Cand));
+    c->fb_cnt.reserve(fb_lists * 4);
+    uint32_t *redo = c->fb_redo.as<uint32_t>();
+    redo_compact_kernel<<<1, 1024, 0, s>>>(rp.flags, B, redo, fb_grid, std::min(fb_grid, fb_tiles),
+                                           t->fb_total.as<unsigned long long>());
+    VK_CUDA(cudaGetLastError());
+    GatherParams gp{};
+    gp.X = ix->dX.as<float>();
+    gp.labels = ix->dLabels.as<uint64_t>();
+    gp.Q = c->q_pad.as<float>();
+    gp.Dp = ix->Dp;
+    gp.k = k_eff;
+    gp.cap = fb_cap;
+    gp.ws = c->fb_ws.as<Cand>();
+    gp.ws_cnt = c->fb_cnt.as<uint32_t>();
+    gp.redo = redo;
+    gp.n_rows_all = ix->n;
+    launch_gather_scan_ldg(ix->metric_l2, dim3(fb_grid), gather_ldg_smem_bytes(ix->Dp, fb_cap), s, gp);
+    MergeParams fm{};
+    fm.ws = gp.ws;
+    fm.ws_cnt = gp.ws_cnt;
+    fm.qt = 1;
+    fm.slabs = fb_grid;  // upper bound of redo[1]: sizes the merge's shared memory
+    fm.cap = fb_cap;
+    fm.k = k_eff;
+    fm.sort_n = std::max<uint32_t>(512, next_pow2_u32(2 * k_eff));
+    fm.out_dist = c->out_dist.as<float>();
+    fm.out_labels = c->out_labels.as<uint64_t>();
+    fm.out_n = c->out_n.as<uint32_t>();
+    fm.redo = redo;
+    launch_topk_merge(B, s, fm);
+    VK_CUDA(cudaMemcpyAsync(t->h_fb_total.p, t->fb_total.p, 8, cudaMemcpyDeviceToHost, s));
+    ix->kernels += 3;
+    ix->tensor_queries += B;
   }
+}
+
+uint64_t tensor_fallbacks_seen(const vkgpu_index_impl *ix) {
+  const TensorState *t = reinterpret_cast<const TensorState *>(ix->tensor_state);
+  return ix->tensor_fallbacks_base + (t && t->h_fb_total.p ? *t->h_fb_total.as<volatile uint64_t>() : 0);
 }
 
 }  // namespace vkgpu

@@ -13,5 +13,8 @@ void tensor_refresh_rows(vkgpu_index_impl *ix, uint64_t first, uint64_t n);  // 
 void tensor_move_row(vkgpu_index_impl *ix, uint64_t from, uint64_t to);      // FLAT swap-delete
 void tensor_release(vkgpu_index_impl *ix);
 void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff);
+// queries re-run on the exact scan because their proof failed (host copy of the device counter: exact once the
+// stream of the last search has been synchronised)
+uint64_t tensor_fallbacks_seen(const vkgpu_index_impl *ix);
 
 }  // namespace vkgpu
