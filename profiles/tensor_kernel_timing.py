@@ -40,6 +40,7 @@ def run(tag, env):
     for _ in range(4):
         L.check(lib.vkgpu_search_batch_device(ix.handle(), dQ.data_ptr(), B, k, 0, od.data_ptr(), ol.data_ptr(), on.data_ptr(), None))
     e1.record(); torch.cuda.synchronize()
-    print(tag, f"B={B} step ms={e0.elapsed_time(e1) / 4:.3f}", "ms per kind:", [round(tm.ms[i] / max(int(tm.launches[i]), 1), 3) for i in range(5)], flush=True)
+    print(tag, f"B={B} step ms={e0.elapsed_time(e1) / 4:.3f}", "ms per kind:", [round(tm.ms[i] / max(int(tm.launches[i]), 1), 3) for i in range(5)],
+          "re-run queries so far:", ix.stats().tensor_fallbacks, flush=True)
 for spec in sys.argv[1:]:
     run(spec, {"VKGPU_TENSOR_PAIR": spec})

@@ -776,27 +776,39 @@ struct RerankParams {
   uint32_t *flags;           // [B]: 1 => margin too thin, re-run on the exact scan
 };
 
-constexpr int RR_THREADS = 128;  // 32 groups of 4 threads; 12 CTAs per SM keep a 1024-query batch in ONE wave (40 registers)
+constexpr int RR_THREADS = 128;  // eight staged rows x sixteen threads (thread j of a row = the reference's SIMD lane j)
+constexpr int RR_ROWS = 8;
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// Survivor rows are scattered over the whole corpus.  They are fetched with cp.async, consecutive threads taking
+// consecutive 16-byte words of a row, so that every memory request covers whole 128-byte lines: the earlier form
+// (4-thread groups reading 64 bytes of eight different rows per instruction) sat at 2.6 TB/s however many loads each
+// thread kept in flight (profiles/r2_ncu_flat_b1024.summary.txt), the coalesced form of the same traffic reaches
+// the HBM rate (profiles/r2_hop_fetch_probe.log).  Several CTAs per SM overlap one another's fetch and compute.
 template <bool L2>
 __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankParams p) {
   extern __shared__ __align__(16) uint8_t rsm[];
-  Cand *buf = reinterpret_cast<Cand *>(rsm);                       // [sort_n]
-  float *q = reinterpret_cast<float *>(rsm + (size_t)p.sort_n * sizeof(Cand));  // [Dp]
-  const uint32_t b = blockIdx.x, tid = threadIdx.x, gi = tid >> 2, u = tid & 3;
+  // [kprime] exact scores | [kprime] rows | query [Dp] | staged rows [RR_ROWS][Dp + 16]; once the last row has been
+  // scored the staging area becomes the (score, row, label) sort buffer [sort_n]: 31 KB at 768 dims, K' = 384, so
+  // that seven CTAs share an SM and a 1024-query batch is ONE wave
+  uint32_t *res_ord = reinterpret_cast<uint32_t *>(rsm);
+  uint32_t *res_slot = res_ord + p.kprime;
+  float *q = reinterpret_cast<float *>(res_slot + p.kprime);
+  float *stage = q + p.Dp;
+  Cand *buf = reinterpret_cast<Cand *>(stage);
+  const uint32_t b = blockIdx.x, tid = threadIdx.x;
   const uint32_t n = min(p.napprox[b], p.kprime);
   for (uint32_t i = tid; i < p.Dp / 4; i += RR_THREADS)
     reinterpret_cast<float4 *>(q)[i] = reinterpret_cast<const float4 *>(p.Q + (size_t)b * p.Dp)[i];
-  for (uint32_t i = tid; i < p.sort_n; i += RR_THREADS) {
-    buf[i].ord = kOrdInf;
-    buf[i].slot = 0xffffffffu;
-    buf[i].label = ~0ull;
-  }
+  for (uint32_t i = tid; i < n; i += RR_THREADS) res_slot[i] = p.slots[(size_t)b * p.kprime + i];
   __syncthreads();
   // Survivors that provably cannot reach the top k are not read at all.  The k survivors with the smallest
   // approximate scores have true scores <= gk + e (gk = the k-th smallest approximate score), so the k-th best true
   // score is <= gk + e; a survivor j with approx_j - e > gk + e (plus the fp32 rounding of the reference's own
   // distances on both sides) is strictly beyond it.  The survivors arrive sorted by approximate score: a prefix is
-  // evaluated.  On the bench data that is about half of the K' = 384 (the margin K' was sized for is 2e wide).
+  // evaluated.  On the bench data that is about two thirds of the K' = 384 (the margin K' was sized for is 2e wide).
   uint32_t n_eval = n;
   if (n > p.k) {
     const float xmax = sqrtf(__uint_as_float(*p.max_norm_bits));
@@ -817,27 +829,49 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankParams p
       cut = gk + 2.0f * e + 2.0f * slack;
       cut += 1e-6f * fabsf(cut);
     }
-    uint32_t lo = p.k, hi = n;  // first index (>= k) whose approximate score exceeds the cut
+    // the survivors are sorted by approximate score: the prefix to evaluate = how many are <= cut (>= k of them, as
+    // cut >= gk) — counted by the whole CTA in one round of loads instead of a binary search of dependent ones
     const float *ap = p.approx + (size_t)b * p.kprime;
-    while (lo < hi) {
-      const uint32_t mid = (lo + hi) >> 1;
-      if (ap[mid] <= cut) lo = mid + 1; else hi = mid;
+    uint32_t cnt_le = 0;
+    for (uint32_t i0 = 0; i0 < n; i0 += RR_THREADS) {
+      const uint32_t i = i0 + tid;
+      cnt_le += __syncthreads_count(i < n && ap[i] <= cut);
     }
-    n_eval = lo;
+    n_eval = max(cnt_le, min(n, p.k));
   }
-  for (uint32_t j0 = 0; j0 < n_eval; j0 += RR_THREADS / 4) {
-    const uint32_t j = j0 + gi;
-    const bool act = j < n_eval;
-    const uint32_t slot = act ? p.slots[(size_t)b * p.kprime + j] : 0;
-    const float d = exact_dist_group<L2, true, 8>(p.X + (size_t)slot * p.Dp, q, p.Dp, u, act);
-    if (act && u == 0) {
-      buf[j].ord = f32_to_ord(d);
-      buf[j].slot = slot;
-      buf[j].label = p.labels[slot];
+  const uint32_t W = p.Dp >> 2, stride = p.Dp + 16;  // 16-byte words per row; padded smem row (no bank conflicts)
+  const uint32_t r = tid >> 4, j = tid & 15;
+  for (uint32_t j0 = 0; j0 < n_eval; j0 += RR_ROWS) {
+    const uint32_t nr = min((uint32_t)RR_ROWS, n_eval - j0);
+    for (uint32_t rr = 0; rr < nr; rr++) {
+      const float4 *src = reinterpret_cast<const float4 *>(p.X + (size_t)res_slot[j0 + rr] * p.Dp);
+      float4 *dst = reinterpret_cast<float4 *>(stage + (size_t)rr * stride);
+      for (uint32_t w = tid; w < W; w += RR_THREADS) cp_async16(dst + w, src + w);
     }
+    cp_async_wait_all();
+    __syncthreads();
+    const bool act = r < nr;
+    const float d = exact_dist_lane16<L2>(stage + (size_t)r * stride, q, p.Dp, j, act);
+    if (act && j == 0) res_ord[j0 + r] = f32_to_ord(d);
+    __syncthreads();
+  }
+  uint32_t sort_n = 64;  // the power of two that covers the evaluated prefix (and k), +inf sentinels behind it
+  while (sort_n < n_eval) sort_n <<= 1;
+  sort_n = min(sort_n, p.sort_n);
+  for (uint32_t i = tid; i < sort_n; i += RR_THREADS) {
+    Cand cd;
+    cd.ord = kOrdInf;
+    cd.slot = 0xffffffffu;
+    cd.label = ~0ull;
+    if (i < n_eval) {
+      cd.ord = res_ord[i];
+      cd.slot = res_slot[i];
+      cd.label = p.labels[cd.slot];
+    }
+    buf[i] = cd;
   }
   __syncthreads();
-  bitonic_sort_cands(buf, p.sort_n, tid, RR_THREADS, [] { __syncthreads(); });
+  bitonic_sort_cands(buf, sort_n, tid, RR_THREADS, [] { __syncthreads(); });
   const uint32_t nout = min(n_eval, p.k);
   for (uint32_t i = tid; i < p.k; i += RR_THREADS) {
     const bool ok = i < nout;
@@ -911,7 +945,8 @@ TensorState *ts(vkgpu_index_impl *ix) { return reinterpret_cast<TensorState *>(i
 // ------------------------------------------------------------------------------------------------ host
 bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
   (void)B;
-  return ix->tensor_ready && k <= 128 && ix->n >= 4096;  // K' = 3k+64 rounded to 128 <= 512
+  // K' = 3k+64 rounded to 128 <= 512; the re-rank stages eight rows in shared memory (Dp <= 4096: 145 KB)
+  return ix->tensor_ready && k <= 128 && ix->n >= 4096 && ix->Dp <= 4096;
 }
 // AUTO policy: a cost model fitted to B200 measurements at 768 dims (both paths scale with rows x dims;
 // profiles/tensor_kernel_timing.py with EXP_PATH=exact|tensor, u = rows x dims / (10M x 768)):
@@ -985,8 +1020,8 @@ void tensor_prepare(vkgpu_index_impl *ix) {
       VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN_SMALL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
       VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
       VK_CUDA(cudaFuncSetAttribute(flat_tensor_kernel<false, BN_SMALL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ix->smem_max));
-      VK_CUDA(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      VK_CUDA(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      VK_CUDA(cudaFuncSetAttribute(rerank_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      VK_CUDA(cudaFuncSetAttribute(rerank_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     }
   } catch (...) {
     (void)cudaGetLastError();  // an allocation failure is sticky only until read
@@ -1219,7 +1254,9 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   rp.out_labels = c->out_labels.as<uint64_t>();
   rp.out_n = c->out_n.as<uint32_t>();
   rp.flags = c->scratch2.as<uint32_t>() + Bpad;
-  const size_t rsmem = (size_t)rp.sort_n * sizeof(Cand) + (size_t)ix->Dp * 4;
+  const size_t rsmem = (size_t)kprime * 8 + (size_t)ix->Dp * 4 +
+                       std::max((size_t)RR_ROWS * (ix->Dp + 16) * 4, (size_t)rp.sort_n * sizeof(Cand));
+  VK_REQUIRE(rsmem <= 200 * 1024, VKGPU_ERR_UNSUPPORTED, "vector too large for the re-rank staging buffer");
   ix->prof_begin(c, KK_RERANK);
   if (ix->metric_l2)
     rerank_kernel<true><<<B, RR_THREADS, rsmem, s>>>(rp);
