@@ -239,8 +239,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint8_t *sA = smem;                                   // [STAGES][16 KB]
   uint8_t *sB = smem + STAGES * A_STAGE_BYTES;          // [STAGES][32 KB | 16 KB]
   uint8_t *tail = sB + STAGES * B_STAGE_BYTES;
-  Cand *scratch = reinterpret_cast<Cand *>(tail);       // [4 warps][kprime]  shrink compaction buffers
-  uint8_t *ctl = tail + (SEED ? (size_t)32 * BN * 4 : (size_t)4 * p.kprime * sizeof(Cand));  // SEED: minima [32][BN]
+  // [32][BN] running minima of 32 groups of rows per query.  Candidate pass: every appended row is dealt into group
+  // (list position & 31) — the j-th smallest group minimum bounds the slab's j-th best score from above at ANY moment
+  // (each minimum is the score of a distinct row of the slab).  SEED pass: group = (tile, row quadrant).
+  uint32_t *gmin = reinterpret_cast<uint32_t *>(tail);
+  uint8_t *ctl = tail + (size_t)32 * BN * 4;
   uint64_t *full = reinterpret_cast<uint64_t *>(ctl);   // [STAGES]
   uint64_t *empty = full + STAGES;                      // [STAGES]
   uint64_t *tfull = empty + STAGES;                     // [2]
@@ -250,6 +253,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint32_t *cnt = reinterpret_cast<uint32_t *>(thrf + BN);         // [BN]
   uint32_t *need = cnt + BN;                                       // [8] per-owner-warp shrink flags
   uint32_t *sync_tile = need + 8;                                  // tile index of the next trim rendezvous
+  uint32_t *epi_tile = sync_tile + 1;                              // tile the epilogue has reached (paces warps 2-3)
+  uint32_t *epi_done = sync_tile + 2;
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // PAIR: cluster = (query tile, pair slab); CTA `rank` of the pair owns corpus tiles 2T + rank, i.e. it is
@@ -277,7 +282,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     cnt[i] = 0;
   }
   if (tid < 8) need[tid] = 0;
-  if (tid == 8) *sync_tile = 0xffffffffu;
+  if (tid == 8) {
+    *sync_tile = 0xffffffffu;
+    *epi_tile = 0;
+    *epi_done = 0;
+  }
+  for (uint32_t i = tid; i < 32u * BN; i += TC_THREADS) gmin[i] = kOrdInf;
   if (warp == 2) {
     if constexpr (PAIR) {  // warp 2 of BOTH CTAs, same smem slot (cute::TMEM::Allocator2Sm)
       asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
@@ -374,49 +384,71 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     uint32_t t = 0;  // tiles this CTA has processed (captured by the lambdas below)
     auto warp_shrink = [&](uint32_t c) {
       const uint32_t n = cnt[c];
-      Cand *wscr = scratch + (size_t)(warp & 3) * p.kprime;
       Cand *buf = my_ws + (size_t)c * p.cap;
+      const uint32_t *ordl = my_ord + (size_t)c * p.cap;
+      // First the cheap cut: an entry above the query's CURRENT threshold (a bound of the global K'-th best that has
+      // tightened since the entry was appended) cannot be among the K' survivors — usually a few dozen entries are
+      // left and no selection is needed.  Only a list that still holds more than K' goes through the radix select.
+      const float th = thrf[c];
       uint32_t o[32];
+      uint32_t nf = 0;
 #pragma unroll
       for (int i = 0; i < 32; i++) {
         const uint32_t idx = i * 32 + lane;
-        o[i] = idx < n ? buf[idx].ord : kOrdInf;
+        uint32_t v = idx < n ? ordl[idx] : kOrdInf;
+        if (!(ord_to_f32(v) <= th)) v = kOrdInf;  // (float comparison, as in the gate)
+        o[i] = v;
+        nf += v != kOrdInf ? 1u : 0u;
       }
-      uint32_t prefix = 0, rem = p.kprime;
-      for (int bit = 31; bit >= 0; bit--) {
-        // prefix has zeros at `bit` and below: (o ^ prefix) >> bit == 0  <=>  high bits match and bit is 0
-        uint32_t c0n = 0;
 #pragma unroll
-        for (int i = 0; i < 32; i++) c0n += (((o[i] ^ prefix) >> bit) == 0u) ? 1u : 0u;
+      for (int sft = 16; sft > 0; sft >>= 1) nf += __shfl_xor_sync(0xffffffffu, nf, sft);
+      uint32_t T = kOrdInf, rem = 0;  // keep every entry that passed the cut
+      if (nf > p.kprime) {
+        uint32_t prefix = 0;
+        rem = p.kprime;
+        for (int bit = 31; bit >= 0; bit--) {
+          // prefix has zeros at `bit` and below: (o ^ prefix) >> bit == 0  <=>  high bits match and bit is 0
+          uint32_t c0n = 0;
 #pragma unroll
-        for (int sft = 16; sft > 0; sft >>= 1) c0n += __shfl_xor_sync(0xffffffffu, c0n, sft);
-        if (rem > c0n) {
-          prefix |= 1u << bit;
-          rem -= c0n;
+          for (int i = 0; i < 32; i++) c0n += (((o[i] ^ prefix) >> bit) == 0u) ? 1u : 0u;
+#pragma unroll
+          for (int sft = 16; sft > 0; sft >>= 1) c0n += __shfl_xor_sync(0xffffffffu, c0n, sft);
+          if (rem > c0n) {
+            prefix |= 1u << bit;
+            rem -= c0n;
+          }
         }
+        T = prefix;  // K'-th smallest ord; `rem` of the entries equal to T are still needed
       }
-      const uint32_t T = prefix;  // K'-th smallest ord; `rem` of the entries equal to T are still needed
       uint32_t base = 0, ties_taken = 0;
 #pragma unroll
       for (int i = 0; i < 32; i++) {
         const uint32_t idx = i * 32 + lane;
-        const bool tie = o[i] == T && idx < n;
+        const bool tie = o[i] == T && T != kOrdInf;
         const uint32_t tb = __ballot_sync(0xffffffffu, tie);
         const bool keep = (o[i] < T) || (tie && ties_taken + __popc(tb & ((1u << lane) - 1)) < rem);
         ties_taken += __popc(tb);
         const uint32_t kb = __ballot_sync(0xffffffffu, keep);
-        if (keep) wscr[base + __popc(kb & ((1u << lane) - 1))] = buf[idx];
+        if (kb == 0) continue;  // warp-uniform
+        // compaction in place: survivors only move towards the front, and every lane has read its entry of this
+        // round before any lane writes (positions written in round i stay below the entries read in round i + 1)
+        Cand cd;
+        if (keep) cd = buf[idx];
+        __syncwarp();
+        if (keep) {
+          const uint32_t at = base + __popc(kb & ((1u << lane) - 1));
+          buf[at] = cd;
+          my_ord[(size_t)c * p.cap + at] = cd.ord;
+        }
         base += __popc(kb);
       }
       __syncwarp();
-      for (uint32_t i = lane; i < p.kprime; i += 32) {
-        buf[i] = wscr[i];
-        my_ord[(size_t)c * p.cap + i] = wscr[i].ord;
-      }
       if (lane == 0) {
-        cnt[c] = p.kprime;
-        thrf[c] = fminf(thrf[c], ord_to_f32(T));
-        atomicMin(&p.gthr[qtile * BN + c], T);
+        cnt[c] = base;
+        if (T != kOrdInf) {
+          thrf[c] = fminf(thrf[c], ord_to_f32(T));
+          atomicMin(&p.gthr[qtile * BN + c], T);
+        }
       }
       __syncwarp();
     };
@@ -437,9 +469,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     if constexpr (SEED) {
       // ---- sampling epilogue: group minima only.  minima[g][c]: g = 4 * tile + row quadrant (<= 32 groups).
-      uint32_t *minima = reinterpret_cast<uint32_t *>(scratch);  // [32][BN]
-      for (uint32_t i = tid - 128; i < 32u * BN; i += EPI_THREADS) minima[i] = kOrdInf;
-      named_bar_sync(2, EPI_THREADS);
+      uint32_t *minima = gmin;  // [32][BN], +inf since the prologue
       for (uint32_t tile = slab; tile < total_tiles && t < tile_limit; tile += p.slabs, t++) {
         const uint32_t a = t & 1;
         const uint64_t slot = (uint64_t)tile * BM + et;
@@ -481,43 +511,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         if (est < kOrdInf - 16) p.gsl[((size_t)qtile * BN + c) * p.gsl_stride + slab] = est + 16;
       }
     } else {
-
-    // Cheap upper bound of the j-th smallest score in a query's list: take the list's most recent entries
-    // (later entries passed tighter gates, so the slab's best rows are almost always among them; any subset still
-    // gives a valid bound), deal them into 32 groups, and take the j-th smallest of the 32 group minima: it
-    // bounds the j-th smallest of the whole list from above.  Published per slab; max over slabs bounds the GLOBAL K'-th best
-    // (slabs * j >= K'), so all CTAs gate on a threshold that tightens with the whole corpus seen so far.
-    // One THREAD per query (query c = warp-4 + 8*lane): sixteen independent 16-byte loads per lane, i.e. ONE L2
-    // round trip per round for the whole warp, then a register bitonic network.  L2 latency under the operand
-    // stream is ~2-4 us, which is why the earlier warp-per-query scans cost 35-110 us per round.
-    auto warp_publish_all = [&]() {
-      if (p.jrank > 32) return;
-      const uint32_t c = (warp - 4) + 8 * lane;
-      if (c >= (uint32_t)BN) return;  // 64-query tiles: eight lanes per warp have a query
-      const uint32_t n = min(cnt[c], p.cap);
-      // window: the last <= 64 entries; during the first tiles (gates still open, lists mostly unfiltered rows)
-      // the last <= 256 in four passes, so that the very first bounds already sit near the slab's true j-th best
-      const uint32_t win = t <= 2 ? 256u : (t <= 16 ? 128u : 64u);
-      const uint32_t first = n > win ? (n - win + 3) & ~3u : 0u;  // 16-byte aligned
-      const uint32_t *src = my_ord + (size_t)c * p.cap;
-      uint32_t g[32];
-#pragma unroll
-      for (int i = 0; i < 32; i++) g[i] = kOrdInf;
-      for (uint32_t w0 = first; w0 < n; w0 += 64) {
-#pragma unroll
-        for (int i = 0; i < 16; i++) {
-          const uint32_t idx = w0 + 4 * i;
-          uint4 v = make_uint4(kOrdInf, kOrdInf, kOrdInf, kOrdInf);
-          if (idx < n) v = __ldcg(reinterpret_cast<const uint4 *>(src + idx));
-          g[2 * i] = min(g[2 * i], min(idx < n ? v.x : kOrdInf, idx + 1 < n ? v.y : kOrdInf));
-          g[2 * i + 1] = min(g[2 * i + 1], min(idx + 2 < n ? v.z : kOrdInf, idx + 3 < n ? v.w : kOrdInf));
-        }
-      }
-      sort32_regs(g);
-      const uint32_t est = pick_rank32(g, p.jrank);
-      // fire-and-forget reduction (RED.MIN): a read-compare-write would cost another L2 round trip
-      if (n >= p.jrank && est != kOrdInf) atomicMin(&p.gsl[((size_t)qtile * BN + c) * p.gsl_stride + slab], est);
-    };
 
     // Gate + append for 32 columns.  Fast path is branch-free: 32 scores against 32 thresholds -> a per-lane bit
     // mask, ONE warp vote per 32 columns.  Only when some lane passes does the warp walk the set columns; the
@@ -565,6 +558,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         cd.label = slot;
         my_ws[(size_t)c * p.cap + pos] = cd;  // pos < cap: see the trim rendezvous in the tile loop
         my_ord[(size_t)c * p.cap + pos] = cd.ord;
+        atomicMin(&gmin[(pos & 31u) * BN + c], cd.ord);  // fire-and-forget; read by warps 2-3 (bounds)
       };
       auto ask_trim = [&](uint32_t c) {  // at the rendezvous of tile t+2
         atomicOr(&need[(c & 3) * 2 + (c >> 7)], 1u << ((c >> 2) & 31));
@@ -595,56 +589,56 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       }
       // Sparse chunk, lane-parallel: every lane walks ITS OWN passing columns (usually one), reserves a list
       // position with one shared-memory atomic and stores the candidate.  Order inside a list is irrelevant.
+      // (the list position is reserved first so that the select tree runs under the latency of the shared-memory
+      //  atomic; whether the append left the list nearly full is looked at once per chunk, after the loop)
+      uint32_t ovf = 0;
       while (m) {
         const uint32_t j = __ffs(m) - 1;
         m &= m - 1;
-        const float dot = pick(j);
         const uint32_t c = c0 + j;
         const uint32_t base = atomicAdd(&cnt[c], 1u);
-        if (base + 1 + 2 * BM > p.cap) ask_trim(c);
+        const float dot = pick(j);
         put(c, base, dot);
+        ovf |= (base + 1 + 2 * BM > p.cap ? 1u : 0u) << j;
+      }
+      if (__any_sync(0xffffffffu, ovf != 0)) {
+        while (ovf) {
+          const uint32_t j = __ffs(ovf) - 1;
+          ovf &= ovf - 1;
+          ask_trim(c0 + j);
+        }
       }
     };
 
-    for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
-      // every 8th tile early on, every 32nd later (and right after each publish round): refresh the gate
-      // thresholds from the running global ones (other slabs tighten them too).  No barrier: thresholds only
-      // ever tighten, so a warp that still gates on the previous value merely keeps a few more candidates.
-      // thrf[c] is written here by warp 4 + (c & 7) and, inside a rendezvous, by the trimming owner 4 + (c & 3).
-      const uint32_t tp1 = t - 1, tp3 = tp1 / 3;  // a publish round ran before tile t-1: every slab has published by now
-      const bool after_pub = t > 1 && ((tp1 & (tp1 - 1)) == 0 || (tp1 >= 24 && tp3 * 3 == tp1 && (tp3 & (tp3 - 1)) == 0));
-      if ((after_pub || (t < 64 && (t & 7) == 0) || (t & 31) == 0)) {
-        // 256/BN threads per query (consecutive lanes): the per-slab bounds of a query are contiguous, each thread
-        // reads its share with 16-byte loads, eight in flight, so a refresh is one or two L2 round trips
-        constexpr uint32_t T = EPI_THREADS / BN;  // 1 (256-query tiles) or 4 (64-query tiles, up to 148 slabs)
-        const uint32_t e = tid - 128, my_c = e / T, part = e % T;
-        const uint4 *gs = reinterpret_cast<const uint4 *>(p.gsl + ((size_t)qtile * BN + my_c) * p.gsl_stride);
-        uint32_t go = __ldcg(&p.gthr[qtile * BN + my_c]);
-        uint32_t mx = 0;
-        for (uint32_t s0 = 4 * part; s0 < p.slabs; s0 += 32 * T) {
-          uint4 v[8];
+    {  // the first tile is gated on the thresholds seeded by the sampling pass: max over slabs of gsl[q][.], read
+       // here by all epilogue threads at once (one L2 round trip under the first MMA); warps 2-3 take over from then
+      constexpr uint32_t T = EPI_THREADS / BN;  // 1 (256-query tiles) or 4 (64-query tiles, up to 148 slabs)
+      const uint32_t e = tid - 128, my_c = e / T, part = e % T;
+      const uint4 *gs = reinterpret_cast<const uint4 *>(p.gsl + ((size_t)qtile * BN + my_c) * p.gsl_stride);
+      uint32_t mx = 0;
+      for (uint32_t s0 = 4 * part; s0 < p.slabs; s0 += 32 * T) {
+        uint4 v[8];
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            v[i] = make_uint4(0, 0, 0, 0);
-            if (s0 + 4 * T * i < p.slabs) v[i] = __ldcg(gs + (s0 >> 2) + T * i);
-          }
+        for (int i = 0; i < 8; i++) {
+          v[i] = make_uint4(0, 0, 0, 0);
+          if (s0 + 4 * T * i < p.slabs) v[i] = __ldcg(gs + (s0 >> 2) + T * i);
+        }
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const uint32_t sb = s0 + 4 * T * i;  // entries past p.slabs are padding
-            mx = max(mx, max(max(sb < p.slabs ? v[i].x : 0u, sb + 1 < p.slabs ? v[i].y : 0u),
-                             max(sb + 2 < p.slabs ? v[i].z : 0u, sb + 3 < p.slabs ? v[i].w : 0u)));
-          }
+        for (int i = 0; i < 8; i++) {
+          const uint32_t sb = s0 + 4 * T * i;  // entries past p.slabs are padding
+          mx = max(mx, max(max(sb < p.slabs ? v[i].x : 0u, sb + 1 < p.slabs ? v[i].y : 0u),
+                           max(sb + 2 < p.slabs ? v[i].z : 0u, sb + 3 < p.slabs ? v[i].w : 0u)));
         }
-        if (T > 1) {
-          mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-          mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        }
-        go = min(go, mx);
-        // (deliberately unsynchronised with the gates of the other warps: racecheck flags this write against their
-        //  reads; a 4-byte threshold is read whole and only ever tightens, so a stale read keeps a candidate too many)
-        if (part == 0 && go != kOrdInf) thrf[my_c] = fminf(thrf[my_c], ord_to_f32(go));
       }
-
+      if (T > 1) {
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      }
+      if (part == 0 && mx != kOrdInf) thrf[my_c] = fminf(thrf[my_c], ord_to_f32(mx));
+      named_bar_sync(2, EPI_THREADS);
+    }
+    for (uint32_t tile = slab; tile < total_tiles; tile += p.slabs, t++) {
+      if (tid == 128) *reinterpret_cast<volatile uint32_t *>(epi_tile) = t;
       const uint32_t a = t & 1;
       const uint64_t slot = (uint64_t)tile * BM + et;
       const bool valid = slot < p.n_rows;
@@ -653,44 +647,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       tc_fence_after();
       VK_TRACE(2, t, tid == 128);
 
-      // ---- rendezvous of the eight epilogue warps, only when needed.  The warps run the tile loop without
-      // per-tile barriers; the accumulator hand-off bounds their drift: tfull(t) fires only after EVERY warp has
-      // released tile t-2, so whatever was written to shared memory while gating tile t-2 is visible here to
-      // all of them and the decision below is uniform.
-      //  * trim: an append that left fewer than 2*BM free entries in a list (while gating tile t-2) set
-      //    *sync_tile = t; the list can have grown by at most the rest of tile t-2 plus tile t-1 since (<= 2*BM).
-      //  * publish rounds before tiles t = 2^i and 3*2^(i-1) (half-octave spacing): the global K'-th best moves
-      //    like 1/t, so denser rounds late in the scan cost more list scans than the appends they save.
-      {
-        const bool do_trim = *reinterpret_cast<volatile uint32_t *>(sync_tile) <= t;
-        const uint32_t t3 = t / 3;
-        const bool do_pub = t > 0 && ((t & (t - 1)) == 0 || (t >= 24 && t3 * 3 == t && (t3 & (t3 - 1)) == 0));
-        if (do_trim || do_pub) {
-          named_bar_sync(2, EPI_THREADS);  // every warp has finished tile t-1: no append is in flight
-          if (do_trim) {
-            if (owner_warp) {
-              const uint32_t w = warp & 3;
+      // ---- rendezvous of the eight epilogue warps, only when a list has to be trimmed.  The warps run the tile loop
+      // without per-tile barriers; the accumulator hand-off bounds their drift: tfull(t) fires only after EVERY warp
+      // has released tile t-2, so whatever was written to shared memory while gating tile t-2 is visible here to all
+      // of them and the decision below is uniform.  An append that left fewer than 2*BM free entries in a list (while
+      // gating tile t-2) set *sync_tile = t; the list can have grown by at most the rest of tile t-2 plus tile t-1
+      // since (<= 2*BM).  (Bounds are published and thresholds refreshed by warps 2-3, off this path.)
+      if (*reinterpret_cast<volatile uint32_t *>(sync_tile) <= t) {
+        named_bar_sync(2, EPI_THREADS);  // every warp has finished tile t-1: no append is in flight
+        if (owner_warp) {
+          const uint32_t w = warp & 3;
 #pragma unroll
-              for (int h = 0; h < 2; h++) {
-                uint32_t bits = need[w * 2 + h];
-                if (bits == 0) continue;  // warp-uniform
-                __syncwarp();             // every lane has read the flags before lane 0 clears them
-                if (lane == 0) need[w * 2 + h] = 0;
-                __syncwarp();
-                while (bits) {
-                  const uint32_t i = __ffs(bits) - 1;
-                  bits &= bits - 1;
-                  const uint32_t c = ((h * 32 + i) << 2) | w;
-                  if (cnt[c] + 2 * BM > p.cap) warp_shrink(c);
-                }
-              }
+          for (int h = 0; h < 2; h++) {
+            uint32_t bits = need[w * 2 + h];
+            if (bits == 0) continue;  // warp-uniform
+            __syncwarp();             // every lane has read the flags before lane 0 clears them
+            if (lane == 0) need[w * 2 + h] = 0;
+            __syncwarp();
+            while (bits) {
+              const uint32_t i = __ffs(bits) - 1;
+              bits &= bits - 1;
+              const uint32_t c = ((h * 32 + i) << 2) | w;
+              if (cnt[c] + 2 * BM > p.cap) warp_shrink(c);
             }
-            if (tid == 128) *sync_tile = 0xffffffffu;
-            named_bar_sync(2, EPI_THREADS);  // trimmed lists before anyone publishes from them
           }
-          if (do_pub) warp_publish_all();
-          named_bar_sync(2, EPI_THREADS);
         }
+        if (tid == 128) *sync_tile = 0xffffffffu;
+        named_bar_sync(2, EPI_THREADS);
       }
 
       VK_TRACE(5, t, tid == 128);
@@ -712,9 +695,70 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // No final trim: the merge is selection based (topk_select_merge_kernel) and takes lists of any length up to
     // cap; trimming ~450-entry lists to K' here used to cost 0.7 ms per launch for nothing.
     named_bar_sync(2, EPI_THREADS);
+    if (tid == 128) *reinterpret_cast<volatile uint32_t *>(epi_done) = 1;
     for (uint32_t c = tid - 128; c < BN; c += EPI_THREADS)
       p.ws_cnt[((size_t)qtile * p.slabs + slab) * BN + c] = min(cnt[c], p.cap);
     }  // !SEED
+  } else if (!SEED) {
+    // ------------------------------------------------------------ warps 2-3: bounds and thresholds, off the gate's path
+    // Sweep over this CTA's queries (BN / 64 per thread): (1) publish — the j-th smallest of the query's 32 group
+    // minima bounds the slab's j-th best score; when it improved, RED.MIN it into gsl[q][slab]; (2) refresh — the
+    // gate threshold of the query = min(running global K'-th best, max over slabs of gsl[q][.]): slabs * j >= K' rows
+    // are at or below that maximum.  The epilogue warps never wait for any of this: they gate on whatever thrf[]
+    // holds (a stale threshold only keeps a few more candidates).  Sweeps follow the epilogue's tile counter: every
+    // tile at first, then with a step of t / 8 (the global K'-th best moves like 1 / t).
+    const uint32_t bt = tid - 64;
+    constexpr int QPT = BN / 64;
+    uint32_t last_pub[QPT];
+#pragma unroll
+    for (int i = 0; i < QPT; i++) last_pub[i] = kOrdInf;
+    uint32_t next_t = 1;  // the epilogue warps read the seeded bounds themselves before their first tile
+    for (;;) {
+      const bool last = *reinterpret_cast<volatile uint32_t *>(epi_done) != 0;
+      const uint32_t tnow = *reinterpret_cast<volatile uint32_t *>(epi_tile);
+      if (!last && tnow < next_t) {
+        __nanosleep(400);
+        continue;
+      }
+      next_t = tnow + 1 + (tnow >> 3);
+#pragma unroll
+      for (int qi = 0; qi < QPT; qi++) {
+        const uint32_t c = bt + 64 * qi;
+        if (p.jrank <= 32) {
+          uint32_t g[32];
+#pragma unroll
+          for (int i = 0; i < 32; i++) g[i] = reinterpret_cast<volatile uint32_t *>(gmin)[i * BN + c];
+          sort32_regs(g);
+          const uint32_t est = pick_rank32(g, p.jrank);
+          if (est < last_pub[qi]) {
+            atomicMin(&p.gsl[((size_t)qtile * BN + c) * p.gsl_stride + slab], est);
+            last_pub[qi] = est;
+          }
+        }
+        const uint4 *gs = reinterpret_cast<const uint4 *>(p.gsl + ((size_t)qtile * BN + c) * p.gsl_stride);
+        uint32_t go = __ldcg(&p.gthr[qtile * BN + c]);
+        uint32_t mx = 0;
+        for (uint32_t s0 = 0; s0 < p.slabs; s0 += 32) {
+          uint4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            v[i] = make_uint4(0, 0, 0, 0);
+            if (s0 + 4 * i < p.slabs) v[i] = __ldcg(gs + (s0 >> 2) + i);
+          }
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            const uint32_t sb = s0 + 4 * i;  // entries past p.slabs are padding
+            mx = max(mx, max(max(sb < p.slabs ? v[i].x : 0u, sb + 1 < p.slabs ? v[i].y : 0u),
+                             max(sb + 2 < p.slabs ? v[i].z : 0u, sb + 3 < p.slabs ? v[i].w : 0u)));
+          }
+        }
+        go = min(go, mx);
+        // (unsynchronised with the gates and with a trimming owner warp on purpose: a 4-byte threshold is read and
+        //  written whole, every value ever stored is a valid bound, a lost update only keeps a candidate too many)
+        if (go != kOrdInf) thrf[c] = fminf(thrf[c], ord_to_f32(go));
+      }
+      if (last) break;
+    }
   }
 
   tc_fence_before();
@@ -1124,7 +1168,8 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   tp.metric_l2 = ix->metric_l2 ? 1 : 0;
   static_assert(Ring<true>::kBytes == Ring<false>::kBytes && Ring<false, BN_SMALL>::kBytes == Ring<false>::kBytes,
                 "all ring geometries use the same shared memory");
-  const size_t smem = (size_t)Ring<true>::kBytes + (size_t)4 * kprime * sizeof(Cand) + 256 + BN * 8 + 64;
+  // operand ring + group minima [32][bn] + barriers, thresholds, list counters
+  const size_t smem = (size_t)Ring<true>::kBytes + (size_t)32 * bn * 4 + 256 + BN * 8 + 64;
   VK_REQUIRE(smem <= ix->smem_max, VKGPU_ERR_INTERNAL, "tensor kernel shared memory budget exceeded");
   // Sampling pass: worth its 4-8 extra tiles per CTA once a CTA walks a few dozen tiles.  The bound it publishes is the
   // j-th smallest of 4 * seed_tiles group minima, so it needs a few more groups than j.
@@ -1142,8 +1187,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
     }
   }
   tp.seed_tiles = seed_tiles;
-  const size_t smem_seed = (size_t)Ring<true>::kBytes + (size_t)32 * bn * 4 + 256 + BN * 8 + 64;
-  VK_REQUIRE(seed_tiles == 0 || smem_seed <= ix->smem_max, VKGPU_ERR_INTERNAL, "sampling pass shared memory budget exceeded");
+  const size_t smem_seed = smem;
   ix->prof_begin(c, KK_TENSOR);
   if (seed_tiles) {
     if (bn == (uint32_t)BN)
