@@ -20,8 +20,14 @@
 // (tcgen05.ld 32x32b -> score -> threshold gate -> lane-parallel append).  Tile = 128 corpus rows (M) x 256
 // queries (N), K streamed in 64-element (128 B) stages through a 4-deep smem ring; two 256-column TMEM
 // accumulators double-buffer MMA against the epilogue.  CTAs are persistent: (query tile, corpus slab) pairs.
-// The epilogue warps run the tile loop WITHOUT per-tile barriers; they meet only for list trims and for the
-// publish rounds (half-octave spacing) that share per-slab bounds of the running K'-th best across CTAs.
+// The epilogue warps run the tile loop WITHOUT per-tile barriers; they meet only to trim a list that is nearly full.
+// Warps 2-3 keep the bounds: per-slab upper bounds of the j-th best score (from 32 running group minima per query that
+// every append updates in shared memory), shared across CTAs through gsl[], and the gate thresholds derived from them.
+// What bounds the kernel (profiles/r2_tensor_operand_stream_exp.log): each K stage brings 48 KB into the SM (16 KB
+// corpus + 32 KB queries); at 5.8 us per tile that is 99 GB/s = 64 B/clk per SM, the SM's ingest rate — with either
+// operand's stream switched off the MMA issue loop runs at 4.7 us per tile, the tensor pipe's own pace at the
+// power-capped clock.  Halving what comes out of L2 (query operand multicast inside a 2-CTA cluster) or pairing CTAs
+// (cta_group::2, below) does not lower what each SM has to take in, and neither made the kernel faster.
 #include "tensor_path.h"
 
 #include <cuda_bf16.h>
@@ -80,6 +86,7 @@ struct TensorParams {
   uint32_t gsl_stride;       // row stride of gsl: slabs rounded up to 4 (16-byte loads)
   uint32_t jrank;            // j = ceil(K'/slabs): slabs*j >= K' rows are <= max_s gsl[q][s]
   uint32_t seed_tiles;       // SEED instantiation: corpus tiles each CTA samples (4 or 8); 0 otherwise
+  uint32_t exp;              // -DVKGPU_TENSOR_TRACE builds only: timing experiment selector (VKGPU_TENSOR_EXP)
   int metric_l2;
 };
 
@@ -321,9 +328,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             tma_load_2d_bf16_pair(sB + stage * B_STAGE_BYTES, &tmB, (int32_t)(kb * BK),
                                   (int32_t)(qtile * BN + rank * (BN / 2)), &full[stage]);
           } else {
+#ifdef VKGPU_TENSOR_TRACE
+            // timing experiments (results are garbage; profiles/r2_tensor_operand_stream_exp.log): 1 = the query
+            // operand is fetched for the first tile only, 2 = the corpus operand is fetched for the first tile only
+            const bool skipB = p.exp == 1 && tp > 0, skipA = p.exp == 2 && tp > 0;
+            mbar_arrive_expect_tx(&full[stage], (skipA ? 0 : A_STAGE_BYTES) + (skipB ? 0 : B_STAGE_BYTES));
+            if (!skipA) tma_load_2d_bf16(sA + stage * A_STAGE_BYTES, &tmA, (int32_t)(kb * BK), (int32_t)(tile * BM), &full[stage]);
+            if (!skipB) tma_load_2d_bf16(sB + stage * B_STAGE_BYTES, &tmB, (int32_t)(kb * BK), (int32_t)(qtile * BN), &full[stage]);
+#else
             mbar_arrive_expect_tx(&full[stage], A_STAGE_BYTES + B_STAGE_BYTES);
             tma_load_2d_bf16(sA + stage * A_STAGE_BYTES, &tmA, (int32_t)(kb * BK), (int32_t)(tile * BM), &full[stage]);
             tma_load_2d_bf16(sB + stage * B_STAGE_BYTES, &tmB, (int32_t)(kb * BK), (int32_t)(qtile * BN), &full[stage]);
+#endif
           }
           if (++stage == STAGES) {
             stage = 0;
@@ -1187,6 +1203,9 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
     }
   }
   tp.seed_tiles = seed_tiles;
+#ifdef VKGPU_TENSOR_TRACE
+  tp.exp = getenv("VKGPU_TENSOR_EXP") ? (uint32_t)atoi(getenv("VKGPU_TENSOR_EXP")) : 0;
+#endif
   const size_t smem_seed = smem;
   ix->prof_begin(c, KK_TENSOR);
   if (seed_tiles) {
