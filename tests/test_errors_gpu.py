@@ -21,13 +21,19 @@ def test_unsupported_and_invalid_requests(built):
     l = np.empty(2000, np.uint64)
     n = np.zeros(1, np.uint32)
     p = lambda a: a.ctypes.data_as(C.c_void_p)
-    # large k on a pre-filtered search is not implemented: explicit UNSUPPORTED, not a silent fallback
-    lab = np.arange(3000, dtype=np.uint64)
+    # large k on a pre-filtered search (the module allows k up to 10^5, ft_search_parser.cc:34-45): every distance of
+    # the query's own list + the (distance, label) selection — the oracle's answer over the same subset
+    import oracle_lib as O
+    lab = np.arange(0, 3000, 2, dtype=np.uint64)
     f = (L.Filter * 1)()
     f[0].labels = lab.ctypes.data
     f[0].n_labels = lab.size
     rc = lib.vkgpu_search_batch(ix.handle(), p(q), 1, 2000, 0, f, 0, p(d), p(l), p(n))
-    assert rc == L.ERR_UNSUPPORTED and b"1024" in lib.vkgpu_last_error()
+    assert rc == L.OK and n[0] == 1500  # k = min(k, keys that qualify)
+    orc = O.PortFlat(16, O.L2)
+    orc.add_many(X)
+    od, ol = orc.search_subset(q[0], 1500, lab)
+    assert np.array_equal(l[:1500], ol) and np.array_equal(d[:1500].view(np.uint32), od.view(np.uint32))
     # expired deadline => CANCELLED (vector_hnsw.cc:327-329 / cancel::Token)
     rc = lib.vkgpu_search_batch(ix.handle(), p(q), 1, 10, 0, None, 1, p(d), p(l), p(n))
     assert rc == L.ERR_CANCELLED

@@ -281,3 +281,43 @@ def test_prefilter_ring_kernel_matches_default(built, monkeypatch):
     b = ix.SearchPrefiltered(q, k, keys)
     assert [(n.external_id, np.float32(n.distance).tobytes()) for n in a] == \
            [(n.external_id, np.float32(n.distance).tobytes()) for n in b]
+
+
+def test_prefilter_long_label_lists_and_bitmaps_resolved_on_the_device(built):
+    """Label lists of >= 4096 entries and host bitmaps are turned into slot lists ON THE DEVICE (label bitmap ->
+    ordered compaction over the index's labels); short lists keep the host route.  One batch mixes all forms; the
+    long list is unsorted, carries duplicates, labels the index does not hold, and rows that were swap-deleted.
+    Every query must equal the oracle over the same subset (vector_base.cc:509-530)."""
+    import valkey_search_b200 as V
+    rng = np.random.default_rng(31)
+    N, D, k = 60_000, 64, 25
+    X = rng.standard_normal((N, D)).astype(np.float32)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+    ix.AddRecordsBulk(range(N), X)
+    gone = rng.choice(N, 500, replace=False)
+    for key in gone:
+        assert ix.RemoveRecord(int(key))
+    live = np.ones(N, bool)
+    live[gone] = False
+    orc = O.PortFlat(D, O.L2)
+    orc.add_many(X)
+    Q = rng.standard_normal((4, D)).astype(np.float32)
+    long_list = rng.choice(N, 20_000, replace=False).astype(np.uint64)
+    long_arg = np.concatenate([long_list[::-1], long_list[:300], np.array([N + 5, N + 10_000_000], np.uint64)])
+    short_list = rng.choice(N, 50, replace=False).astype(np.uint64)
+    bm_sel = rng.random(N) < 0.2
+    bitmap = np.packbits(bm_sel, bitorder="little")
+    big2 = np.arange(0, N, 3, dtype=np.uint64)
+    filters = [{"labels": long_arg}, {"labels": short_list}, {"bitmap": bitmap}, {"labels": big2}]
+    want = [long_list, short_list, np.flatnonzero(bm_sel).astype(np.uint64), big2]
+    d1, l1, n1 = ix.SearchBatchRaw(Q, k, filters=filters)
+    for b in range(4):
+        cand = np.sort(want[b][live[want[b].astype(np.int64)]])
+        d, l = orc.search_subset(Q[b], k, cand)
+        assert n1[b] == k
+        assert np.array_equal(l1[b], l), b
+        assert np.array_equal(_bits(d1[b]), _bits(d)), b
+    # a long list of labels the index does not hold at all: empty reply
+    none = np.arange(N + 1, N + 5001, dtype=np.uint64)
+    d2, l2, n2 = ix.SearchBatchRaw(Q[:1], k, filters=[{"labels": none}])
+    assert n2[0] == 0

@@ -196,4 +196,50 @@ void flat_select_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, u
   ix->last_passes = (B + kScanMaxQt - 1) / kScanMaxQt;
 }
 
+// Pre-filtered search for any k (VectorBase::AddPrefilteredKey, vector_base.cc:509-530, with k up to the module's
+// max-vector-knn): every exact distance of each query's OWN slot list, then the same (distance, label) selection.
+// h_ptrs / h_lens: the lists as the host knows them (device pointers, lengths); d_list_ptr / d_list_len: the same
+// arrays in device memory.
+void flat_select_lists_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff, const uint64_t *h_ptrs,
+                                     const uint64_t *h_lens, const uint32_t *const *d_list_ptr,
+                                     const uint64_t *d_list_len, uint64_t longest) {
+  uint32_t sort_n = 1;
+  while (sort_n < k_eff) sort_n <<= 1;
+  const uint64_t stride = std::max<uint64_t>(longest, 1);
+  c->out_dist.reserve((size_t)B * k_eff * 4);
+  c->out_labels.reserve((size_t)B * k_eff * 8);
+  c->out_n.reserve((size_t)B * 4);
+  c->scratch0.reserve((size_t)kScanMaxQt * stride * 4);
+  c->scratch1.reserve((size_t)kScanMaxQt * sort_n * sizeof(Cand));
+  for (uint32_t b0 = 0; b0 < B; b0 += kScanMaxQt) {
+    const uint32_t nb = std::min<uint32_t>(kScanMaxQt, B - b0);
+    ix->prof_begin(c, KK_SCAN);
+    for (uint32_t i = 0; i < nb; i++)
+      launch_exact_distances(ix->dX.as<float>(), ix->Dp, ix->metric_l2, c->q_pad.as<float>() + (size_t)(b0 + i) * ix->Dp,
+                             reinterpret_cast<const uint32_t *>((uintptr_t)h_ptrs[b0 + i]), h_lens[b0 + i],
+                             c->scratch0.as<float>() + (size_t)i * stride, c->cur);
+    ix->prof_end(c, KK_SCAN);
+    SelectParams sp{};
+    sp.dist = c->scratch0.as<float>();
+    sp.n_stride = stride;
+    sp.n_per_q = d_list_len + b0;
+    sp.n = 0;
+    sp.slots = d_list_ptr + b0;
+    sp.labels = ix->dLabels.as<uint64_t>();
+    sp.k = k_eff;
+    sp.sort_n = sort_n;
+    sp.work = c->scratch1.as<Cand>();
+    sp.out_dist = c->out_dist.as<float>() + (size_t)b0 * k_eff;
+    sp.out_labels = c->out_labels.as<uint64_t>() + (size_t)b0 * k_eff;
+    sp.out_n = c->out_n.as<uint32_t>() + b0;
+    ix->prof_begin(c, KK_MERGE);
+    flat_select_kernel<<<nb, ST, 0, c->cur>>>(sp);
+    VK_CUDA(cudaGetLastError());
+    ix->prof_end(c, KK_MERGE);
+    ix->kernels += nb + 1;
+  }
+  ix->last_qt = 1;
+  ix->last_passes = B;
+}
+
 }  // namespace vkgpu

@@ -503,9 +503,15 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     //  * labels     : labels -> slots on the host (unknown labels skipped, vector_base.cc:513-516; duplicates
     //                 collapse), uploaded
     //  * bitmap     : host bitmap -> slots on the host
+    //  Long label lists and host bitmaps are resolved ON THE DEVICE (round 2): the list is uploaded, turned into a
+    //  label bitmap (set_update_kernel) and compacted into the ordered, duplicate-free slot list by the same kernels
+    //  that serve device sets (one pass over the index's labels) — no host hash lookup per label, no O(N) host scan;
+    //  the list length stays on the device (the gather scan reads it there).  Short lists keep the host route.
+    constexpr uint64_t kDeviceResolveMin = 4096;
+    const bool dev_ok = k <= kMaxFusedK;  // the any-k selection wants the list lengths on the host
     std::vector<uint32_t> slots;
-    std::vector<uint64_t> ptrs(B, 0), lens(B, 0), host_off(B, ~0ull);
-    uint64_t longest = 0;
+    std::vector<uint64_t> ptrs(B, 0), lens(B, 0), host_off(B, ~0ull), dev_off(B, ~0ull), dev_cap(B, 0), dev_bits(B, 0);
+    uint64_t longest = 0, dev_total = 0, max_up = 0, max_bits = 0;
     for (uint32_t b = 0; b < B; b++) {
       const vkgpu_filter &f = filters[b];
       if (f.device_set) {
@@ -513,6 +519,23 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
         ptrs[b] = (uint64_t)(uintptr_t)ds->slots.p;
         lens[b] = ds->nslots;
         longest = std::max<uint64_t>(longest, ds->nslots);
+        continue;
+      }
+      if (dev_ok && ((f.labels && f.n_labels >= kDeviceResolveMin) || (!f.labels && f.label_bitmap))) {
+        dev_cap[b] = f.labels ? std::min<uint64_t>(f.n_labels, ix->n) : ix->n;  // upper bound of the list length
+        dev_off[b] = dev_total;
+        dev_total += (dev_cap[b] + 1) & ~1ull;
+        longest = std::max<uint64_t>(longest, dev_cap[b]);
+        if (f.labels) {
+          uint64_t mx = 0;
+          for (uint64_t i = 0; i < f.n_labels; i++) mx = std::max(mx, f.labels[i]);
+          dev_bits[b] = mx + 1;
+          max_up = std::max<uint64_t>(max_up, f.n_labels * 8);
+        } else {
+          dev_bits[b] = f.bitmap_bits;
+          max_up = std::max<uint64_t>(max_up, (f.bitmap_bits + 7) / 8);
+        }
+        max_bits = std::max(max_bits, dev_bits[b]);
         continue;
       }
       size_t start = slots.size();
@@ -547,9 +570,11 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     }
     k_eff = (uint32_t)std::min<uint64_t>(k, std::max<uint64_t>(longest, 1));
     const size_t slots_bytes = (slots.size() * 4 + 7) & ~size_t(7);
-    c->lists.reserve(std::max<size_t>(slots_bytes, 8));
-    for (uint32_t b = 0; b < B; b++)
+    c->lists.reserve(std::max<size_t>(slots_bytes + dev_total * 4, 8));
+    for (uint32_t b = 0; b < B; b++) {
       if (host_off[b] != ~0ull) ptrs[b] = (uint64_t)(uintptr_t)(c->lists.as<uint32_t>() + host_off[b]);
+      if (dev_off[b] != ~0ull) ptrs[b] = (uint64_t)(uintptr_t)(c->lists.as<uint8_t>() + slots_bytes + dev_off[b] * 4);
+    }
     c->list_off.reserve((size_t)B * 16);
     c->h_misc.reserve(slots_bytes + (size_t)B * 16);
     uint8_t *meta_host = c->h_misc.as<uint8_t>() + slots_bytes;
@@ -559,8 +584,39 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     if (!slots.empty())
       VK_CUDA(cudaMemcpyAsync(c->lists.p, c->h_misc.p, slots.size() * 4, cudaMemcpyHostToDevice, c->cur));
     VK_CUDA(cudaMemcpyAsync(c->list_off.p, meta_host, (size_t)B * 16, cudaMemcpyHostToDevice, c->cur));
-    gather_search_device(ix, c, B, k_eff, c->list_off.as<const uint32_t *>(),
-                         reinterpret_cast<const uint64_t *>(c->list_off.as<uint8_t>() + (size_t)B * 8), longest);
+    if (dev_total) {  // after the upload of the (zero) lengths: each conversion writes its own
+      const uint64_t words = (max_bits + 31) / 32;
+      c->scratch0.reserve(std::max<uint64_t>(max_up, 8));
+      c->scratch1.reserve(std::max<uint64_t>(words, 1) * 4);
+      c->scratch2.reserve(((ix->n + 255) / 256 + 1) * 4);
+      unsigned long long *d_len = reinterpret_cast<unsigned long long *>(c->list_off.as<uint8_t>() + (size_t)B * 8);
+      for (uint32_t b = 0; b < B; b++) {
+        if (dev_off[b] == ~0ull) continue;
+        const vkgpu_filter &f = filters[b];
+        const uint64_t bits = dev_bits[b];
+        if (f.labels) {
+          VK_CUDA(cudaMemcpyAsync(c->scratch0.p, f.labels, f.n_labels * 8, cudaMemcpyHostToDevice, c->cur));
+          VK_CUDA(cudaMemsetAsync(c->scratch1.p, 0, ((bits + 31) / 32) * 4, c->cur));
+          launch_set_update(c->scratch1.as<uint32_t>(), c->scratch0.as<uint64_t>(), nullptr, f.n_labels, c->cur);
+          launch_bitmap_to_slots(ix->dLabels.as<uint64_t>(), ix->n, c->scratch1.as<uint8_t>(), bits,
+                                 reinterpret_cast<uint32_t *>((uintptr_t)ptrs[b]), c->scratch2.as<uint32_t>(), d_len + b,
+                                 c->cur);
+          ix->kernels += 4;
+        } else {
+          VK_CUDA(cudaMemcpyAsync(c->scratch0.p, f.label_bitmap, (bits + 7) / 8, cudaMemcpyHostToDevice, c->cur));
+          launch_bitmap_to_slots(ix->dLabels.as<uint64_t>(), ix->n, c->scratch0.as<uint8_t>(), bits,
+                                 reinterpret_cast<uint32_t *>((uintptr_t)ptrs[b]), c->scratch2.as<uint32_t>(), d_len + b,
+                                 c->cur);
+          ix->kernels += 3;
+        }
+      }
+    }
+    if (k_eff > kMaxFusedK)  // the fused top-k of the gather scan stops at 1024: all distances + selection
+      flat_select_lists_search_device(ix, c, B, k_eff, ptrs.data(), lens.data(), c->list_off.as<const uint32_t *>(),
+                                      reinterpret_cast<const uint64_t *>(c->list_off.as<uint8_t>() + (size_t)B * 8), longest);
+    else
+      gather_search_device(ix, c, B, k_eff, c->list_off.as<const uint32_t *>(),
+                           reinterpret_cast<const uint64_t *>(c->list_off.as<uint8_t>() + (size_t)B * 8), longest);
   } else {
     k_eff = (uint32_t)std::min<uint64_t>(k, ix->n);
     bool use_tensor = false;

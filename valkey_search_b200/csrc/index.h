@@ -215,6 +215,10 @@ void flat_exact_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, ui
 void flat_all_distances_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t b0, uint32_t nb, float *dist_out);
 // any-k exact search (flat_select.cu)
 void flat_select_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff);
+// any-k exact search over one slot list per query (pre-filter with k > 1024)
+void flat_select_lists_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32_t k_eff, const uint64_t *h_ptrs,
+                                     const uint64_t *h_lens, const uint32_t *const *d_list_ptr,
+                                     const uint64_t *d_list_len, uint64_t longest);
 
 // ---- small kernels (misc_kernels.cu)
 void launch_exact_distances(const float *X, uint32_t Dp, bool l2, const float *q_pad, const uint32_t *slots,

@@ -146,7 +146,7 @@ __global__ void __launch_bounds__(256) set_update_kernel(uint32_t *__restrict__ 
   if (i >= n) return;
   const uint64_t lab = labels[i];
   const uint32_t bit = 1u << (lab & 31);
-  if (present[i])
+  if (present == nullptr || present[i])  // nullptr: every listed label is set
     atomicOr(&words[lab >> 5], bit);
   else
     atomicAnd(&words[lab >> 5], ~bit);
