@@ -967,7 +967,7 @@ def main():
     ap.add_argument("--workload", default="flat", choices=["flat", "hnsw", "prefilter", "serve"],
                     help="flat = BASELINE configs[1] (the driver's default); hnsw = configs[2] at --rows")
     ap.add_argument("--ef", type=int, default=128)
-    ap.add_argument("--in-flight", type=int, default=4, help="hnsw: batches kept in flight (host threads)")
+    ap.add_argument("--in-flight", type=int, default=8, help="hnsw: batches kept in flight (host threads); 8 fill the SMs at batch 512 (profiles/r2_hnsw_occupancy_sweep.log)")
     ap.add_argument("--hnsw-rows", type=int, default=1_000_000, help="rows of the HNSW measurement embedded in the flat line")
     ap.add_argument("--no-secondary", action="store_true", help="flat: skip the embedded HNSW / pre-filter measurements")
     ap.add_argument("--window-us", type=int, default=300)
