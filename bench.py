@@ -1083,7 +1083,11 @@ def main():
     hQ = dQ.cpu().numpy()
     sh = ShardedFlat(ix, dist, dev)
     out = sh.alloc_out(B, k, dev)
-    stream = torch.cuda.current_stream()
+    # a stream of our own (not the NULL stream): the library then runs the whole step asynchronously on it — search,
+    # NCCL exchange (torch orders its communicator stream after the current one) and merge back to back on the device,
+    # no host synchronisation inside a step; with the NULL stream every library call synchronises before it returns
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     sptr = stream.cuda_stream
 
     def barrier():

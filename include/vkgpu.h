@@ -197,7 +197,8 @@ int vkgpu_distances(vkgpu_index *h, const float *q, const uint64_t *labels, uint
 
 /* ---- multi-GPU: merge of per-shard results (semantic analog of src/query/fanout.cc:159-220) -------- */
 /* d_dist/d_labels/d_n are the allgathered per-shard results, laid out [G][B][k] / [G][B], in device
- * memory of `device`; writes the merged ascending top-k [B][k] / [B]. */
+ * memory of `device`; writes the merged ascending top-k [B][k] / [B].  Asynchronous on `cuda_stream` (NULL = the
+ * default stream, synchronised before return). */
 int vkgpu_merge_topk_device(int device, const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
                             uint32_t G, uint32_t B, uint32_t k, float *d_out_dist, uint64_t *d_out_labels,
                             uint32_t *d_out_n, void *cuda_stream);

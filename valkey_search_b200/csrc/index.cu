@@ -88,18 +88,33 @@ void PinnedBuf::release() {
 SearchCtx *vkgpu_index_impl::acquire_ctx() {
   std::unique_lock<std::mutex> lk(ctx_mu);
   for (;;) {
+    // A context whose previous call ran asynchronously on a caller's stream is reusable once that work has finished.
+    // Prefer one that is idle on the device too (or a new one) over WAITING for the first free one: a caller that
+    // enqueues step after step on its own stream then runs ahead of the device instead of in lock-step with it.
+    SearchCtx *pick = nullptr;
     for (auto &c : ctxs)
-      if (!c->busy) {
-        c->busy = true;
-        lk.unlock();
-        prof_harvest(c.get());
-        if (c->done_pending) {  // previous call on this context ran asynchronously on a caller's stream
-          VK_CUDA(cudaEventSynchronize(c->done));
-          c->done_pending = false;
-        }
-        c->cur = c->stream;
-        return c.get();
+      if (!c->busy && (!c->done_pending || cudaEventQuery(c->done) == cudaSuccess)) {
+        pick = c.get();
+        break;
       }
+    if (!pick && ctxs.size() >= 16)
+      for (auto &c : ctxs)
+        if (!c->busy) {
+          pick = c.get();
+          break;
+        }
+    if (pick) {
+      SearchCtx *c = pick;
+      c->busy = true;
+      lk.unlock();
+      prof_harvest(c);
+      if (c->done_pending) {
+        VK_CUDA(cudaEventSynchronize(c->done));
+        c->done_pending = false;
+      }
+      c->cur = c->stream;
+      return c;
+    }
     if (ctxs.size() < 16) {
       auto c = std::make_unique<SearchCtx>();
       VK_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -1183,14 +1198,32 @@ static int merge_topk_impl(int device, const float *d_dist, const uint64_t *d_la
   return guarded([&] {
     VK_REQUIRE(d_dist && d_labels && d_n && d_out_dist && d_out_labels && d_out_n, VKGPU_ERR_INVALID, "null argument");
     VK_REQUIRE(G >= 1 && B >= 1 && k >= 1 && k <= kMaxFusedK, VKGPU_ERR_INVALID, "bad merge shape");
+    VK_REQUIRE(device >= 0 && device < 64, VKGPU_ERR_INVALID, "bad device ordinal");
     VK_CUDA(cudaSetDevice(device));
     cudaStream_t s = (cudaStream_t)cuda_stream;
-    // per-process scratch, grown on demand (one process per GPU)
-    static DevBuf ws, ws_cnt;
-    static std::mutex mu;
-    std::lock_guard<std::mutex> lk(mu);
-    ws.reserve((size_t)G * B * k * sizeof(Cand));
-    ws_cnt.reserve((size_t)G * B * 4);
+    // the usual shape: every query's G lists fit in shared memory and are merged by rank, one small kernel
+    if (launch_merge_sorted_shards(d_dist, d_labels, d_n, rank_stride, G, B, k, d_out_dist, d_out_labels, d_out_n, s)) {
+      if (!cuda_stream) VK_CUDA(cudaStreamSynchronize(s));
+      return;
+    }
+    // Scratch per DEVICE, grown on demand.  Calls are ordered by an event instead of a host synchronisation: a call on
+    // another stream waits (on the device) for the previous merge to have finished with the scratch.  With a caller's
+    // stream the merge is asynchronous; cuda_stream == NULL keeps the synchronous behaviour.
+    struct MergeScratch {
+      DevBuf ws, ws_cnt;
+      cudaEvent_t done = nullptr;
+      std::mutex mu;
+    };
+    static MergeScratch scratch[64];
+    MergeScratch &ms = scratch[device];
+    std::lock_guard<std::mutex> lk(ms.mu);
+    if (!ms.done) VK_CUDA(cudaEventCreateWithFlags(&ms.done, cudaEventDisableTiming));
+    else VK_CUDA(cudaStreamWaitEvent(s, ms.done, 0));
+    const size_t need_ws = (size_t)G * B * k * sizeof(Cand), need_cnt = (size_t)G * B * 4;
+    if (need_ws > ms.ws.bytes || need_cnt > ms.ws_cnt.bytes) VK_CUDA(cudaDeviceSynchronize());  // growing frees the old block
+    DevBuf &ws = ms.ws, &ws_cnt = ms.ws_cnt;
+    ws.reserve(need_ws);
+    ws_cnt.reserve(need_cnt);
     launch_pack_shard_results(d_dist, d_labels, d_n, rank_stride, G, B, k, ws.as<Cand>(), ws_cnt.as<uint32_t>(), s);
     MergeParams mp{};
     mp.ws = ws.as<Cand>();
@@ -1205,7 +1238,8 @@ static int merge_topk_impl(int device, const float *d_dist, const uint64_t *d_la
     mp.out_slots = nullptr;
     mp.out_n = d_out_n;
     launch_topk_merge(B, s, mp);
-    VK_CUDA(cudaStreamSynchronize(s));
+    VK_CUDA(cudaEventRecord(ms.done, s));
+    if (!cuda_stream) VK_CUDA(cudaStreamSynchronize(s));
   });
 }
 

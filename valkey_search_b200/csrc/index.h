@@ -237,6 +237,10 @@ void launch_values_update(double *vals, uint32_t *has, const uint64_t *labels, c
                           const uint8_t *present, uint64_t n, cudaStream_t s);
 void launch_values_range(const double *vals, const uint32_t *has, uint64_t bits, double start, int incl_start,
                          double end, int incl_end, uint32_t *out, cudaStream_t s);
+// merge of G ascending per-shard results per query by rank (no scratch); false = shape too large for shared memory
+bool launch_merge_sorted_shards(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n, uint64_t rank_stride,
+                                uint32_t G, uint32_t B, uint32_t k, float *out_dist, uint64_t *out_labels,
+                                uint32_t *out_n, cudaStream_t s);
 void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
                                uint64_t rank_stride, uint32_t G, uint32_t B, uint32_t k, Cand *ws, uint32_t *ws_cnt,
                                cudaStream_t s);

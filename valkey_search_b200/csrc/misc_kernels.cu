@@ -68,6 +68,63 @@ __global__ void pack_shard_results_kernel(const float *d_dist, const uint64_t *d
   }
 }
 
+// Merge of the G shard results of one query (one CTA per query).  Each shard's result is an ASCENDING (distance,
+// label) list of <= k entries over rows no other shard holds, so the merged rank of an entry is its position in its
+// own list plus, for every other list, the number of entries before it (one binary search each): no packing, no
+// selection, no sort.  (fanout.cc:159-171 keeps a heap of k; the result is the same k best of the union.)
+__global__ void __launch_bounds__(256) merge_sorted_shards_kernel(const float *d_dist, const uint64_t *d_labels,
+                                                                  const uint32_t *d_n, uint64_t rank_stride, uint32_t G,
+                                                                  uint32_t B, uint32_t k, float *out_dist,
+                                                                  uint64_t *out_labels, uint32_t *out_n) {
+  extern __shared__ __align__(16) uint8_t ssm[];
+  uint64_t *lab = reinterpret_cast<uint64_t *>(ssm);        // [G][k]
+  uint32_t *ord = reinterpret_cast<uint32_t *>(lab + (size_t)G * k);  // [G][k]
+  uint32_t *cnt = ord + (size_t)G * k;                      // [G]
+  const uint32_t b = blockIdx.x, tid = threadIdx.x;
+  auto rank_ptr = [&](const void *base, uint32_t g, uint64_t contiguous_elems, size_t elem) -> const char * {
+    return rank_stride ? reinterpret_cast<const char *>(base) + g * rank_stride
+                       : reinterpret_cast<const char *>(base) + (uint64_t)g * contiguous_elems * elem;
+  };
+  for (uint32_t g = tid; g < G; g += blockDim.x)
+    cnt[g] = min(reinterpret_cast<const uint32_t *>(rank_ptr(d_n, g, B, 4))[b], k);
+  for (uint32_t i = tid; i < G * k; i += blockDim.x) {
+    const uint32_t g = i / k, j = i % k;
+    ord[i] = f32_to_ord(reinterpret_cast<const float *>(rank_ptr(d_dist, g, (uint64_t)B * k, 4))[(size_t)b * k + j]);
+    lab[i] = reinterpret_cast<const uint64_t *>(rank_ptr(d_labels, g, (uint64_t)B * k, 8))[(size_t)b * k + j];
+  }
+  __syncthreads();
+  uint32_t total = 0;
+  for (uint32_t g = 0; g < G; g++) total += cnt[g];
+  const uint32_t nout = min(total, k);
+  for (uint32_t i = tid; i < G * k; i += blockDim.x) {
+    const uint32_t g = i / k, j = i % k;
+    if (j >= cnt[g]) continue;
+    const uint32_t o = ord[i];
+    const uint64_t l = lab[i];
+    uint32_t rank = j;
+    for (uint32_t h = 0; h < G && rank < k; h++) {
+      if (h == g) continue;
+      uint32_t lo = 0, hi = cnt[h];  // entries of list h before (o, l)
+      const uint32_t *oh = ord + (size_t)h * k;
+      const uint64_t *lh = lab + (size_t)h * k;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (oh[mid] < o || (oh[mid] == o && lh[mid] < l)) lo = mid + 1; else hi = mid;
+      }
+      rank += lo;
+    }
+    if (rank < k) {
+      out_dist[(size_t)b * k + rank] = ord_to_f32(o);
+      out_labels[(size_t)b * k + rank] = l;
+    }
+  }
+  for (uint32_t r = nout + tid; r < k; r += blockDim.x) {
+    out_dist[(size_t)b * k + r] = __int_as_float(0x7f800000);
+    out_labels[(size_t)b * k + r] = ~0ull;
+  }
+  if (tid == 0) out_n[b] = nout;
+}
+
 // Ordered stream compaction: slots whose label is in the bitmap -> out[] in increasing slot order (so the
 // gather scan walks HBM monotonically).  Three small kernels: per-256-slot counts, exclusive scan, fill.
 __device__ __forceinline__ bool slot_in_set(const uint64_t *labels, uint64_t n, const uint8_t *bm, uint64_t bits,
@@ -259,6 +316,19 @@ void launch_iota_labels(uint64_t *dst, uint64_t start, uint64_t n, cudaStream_t 
   if (n == 0) return;
   iota_kernel<<<296, 256, 0, s>>>(dst, start, n);
   VK_CUDA(cudaGetLastError());
+}
+
+bool launch_merge_sorted_shards(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n, uint64_t rank_stride,
+                                uint32_t G, uint32_t B, uint32_t k, float *out_dist, uint64_t *out_labels,
+                                uint32_t *out_n, cudaStream_t s) {
+  const size_t smem = (size_t)G * k * 12 + (size_t)G * 4;
+  if (smem > 96 * 1024) return false;  // the caller falls back to the selection merge
+  static PerDeviceOnce attr;
+  if (attr.first())
+    VK_CUDA(cudaFuncSetAttribute(merge_sorted_shards_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+  merge_sorted_shards_kernel<<<B, 256, smem, s>>>(d_dist, d_labels, d_n, rank_stride, G, B, k, out_dist, out_labels, out_n);
+  VK_CUDA(cudaGetLastError());
+  return true;
 }
 
 void launch_pack_shard_results(const float *d_dist, const uint64_t *d_labels, const uint32_t *d_n,
