@@ -14,7 +14,11 @@ def _bits(a):
 
 @pytest.mark.parametrize("metric,N,D,B,k", [("L2", 200_000, 768, 300, 100), ("IP", 150_000, 128, 70, 10),
                                              ("L2", 50_000, 100, 257, 37), ("COSINE", 60_000, 256, 64, 100),
-                                             ("L2", 120_000, 768, 17, 100), ("IP", 300_000, 64, 2, 10)])
+                                             ("L2", 120_000, 768, 17, 100), ("IP", 300_000, 64, 2, 10),
+                                             # shapes in which every CTA walks >= 32 tiles, i.e. the sampling pass runs:
+                                             # 256-query tiles (IP, COSINE) and the 64-query tile
+                                             ("IP", 600_000, 64, 300, 10), ("COSINE", 640_000, 48, 257, 20),
+                                             ("L2", 700_000, 64, 16, 10), ("IP", 700_000, 32, 64, 100)])
 def test_tensor_path_equals_exact_path(built, metric, N, D, B, k):
     import valkey_search_b200 as V
     rng = np.random.default_rng(N + D + B)
