@@ -15,8 +15,8 @@
 //      (flat_scan.cu) — still on the GPU, never on the CPU.
 // Output is therefore bit-identical to the exact path / the CPU oracle.
 //
-// Kernel anatomy (flat_tensor_kernel): 384 threads; warp 0 = TMA producer (cp.async.bulk.tensor, 128B
-// swizzle), warp 1 = single-thread tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-11 = epilogue
+// Kernel anatomy (flat_tensor_kernel): 512 threads; warp 0 = TMA producer (cp.async.bulk.tensor, 128B
+// swizzle), warp 1 = single-thread tcgen05.mma issuer, warp 2 = TMEM allocator, warps 4-15 = epilogue
 // (tcgen05.ld 32x32b -> score -> threshold gate -> lane-parallel append).  Tile = 128 corpus rows (M) x 256
 // queries (N), K streamed in 64-element (128 B) stages through a 4-deep smem ring; two 256-column TMEM
 // accumulators double-buffer MMA against the epilogue.  CTAs are persistent: (query tile, corpus slab) pairs.
@@ -67,8 +67,8 @@ struct Ring {
   static constexpr int kStages = 192 * 1024 / (A_STAGE_BYTES + kBStage);  // 4, 6 or 8 stages: 192 KB either way
   static constexpr int kBytes = kStages * (A_STAGE_BYTES + kBStage);
 };
-constexpr int TC_THREADS = 384;  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
-constexpr int EPI_THREADS = 256;
+constexpr int TC_THREADS = 512;  // warps 0-3: TMA / MMA / bound keepers (2-3); warps 4-15: epilogue
+constexpr int EPI_THREADS = 384;  // three warps per TMEM lane quadrant, each gating a third of the query columns
 constexpr uint32_t TMEM_COLS = 512;
 
 struct TensorParams {
@@ -390,7 +390,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // Threshold refresh, trims and publishes stay with warps 4-7 (query c belongs to warp 4 + (c & 3)).
     const uint32_t lane_base = (warp & 3) * 32;
     const uint32_t et = lane_base + lane;          // row inside the tile = TMEM lane
-    const uint32_t col_lo = ((warp - 4) >> 2) * (BN / 2);
+    // 32-column chunks of the tile dealt to the three warps of a quadrant: 2 + 3 + 3 of eight (256 queries), 0 + 1 + 1
+    // of two (64 queries)
+    constexpr uint32_t NCH = BN / 32;
+    const uint32_t cgrp = (warp - 4) >> 2;
+    const uint32_t col_lo = (cgrp * NCH / 3) * 32, col_hi = ((cgrp + 1) * NCH / 3) * 32;
     const bool owner_warp = warp < 8;
     Cand *my_ws = p.ws + ((size_t)qtile * p.slabs + slab) * BN * p.cap;
     uint32_t *my_ord = p.ws_ord + ((size_t)qtile * p.slabs + slab) * BN * p.cap;
@@ -496,7 +500,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         const uint32_t tbase = tmem_base + (lane_base << 16) + a * BN;
         uint32_t ra[32];
 #pragma unroll 1
-        for (uint32_t c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32) {
+        for (uint32_t c0 = col_lo; c0 < col_hi; c0 += 32) {
           tmem_ld32_async(tbase + c0, ra);
           tmem_wait();
           uint32_t mine = kOrdInf;
@@ -628,8 +632,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 
     {  // the first tile is gated on the thresholds seeded by the sampling pass: max over slabs of gsl[q][.], read
        // here by all epilogue threads at once (one L2 round trip under the first MMA); warps 2-3 take over from then
-      constexpr uint32_t T = EPI_THREADS / BN;  // 1 (256-query tiles) or 4 (64-query tiles, up to 148 slabs)
-      const uint32_t e = tid - 128, my_c = e / T, part = e % T;
+      constexpr uint32_t T = BN == 64 ? 4 : 1;  // threads per query: 1 (256-query tiles) or 4 (64-query tiles, up to 148 slabs)
+      const uint32_t e = min(tid - 128, (uint32_t)BN * T - 1), my_c = e / T, part = e % T;  // (spare threads repeat the last)
       const uint4 *gs = reinterpret_cast<const uint4 *>(p.gsl + ((size_t)qtile * BN + my_c) * p.gsl_stride);
       uint32_t mx = 0;
       for (uint32_t s0 = 4 * part; s0 < p.slabs; s0 += 32 * T) {
@@ -696,7 +700,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint32_t tbase = tmem_base + (lane_base << 16) + a * BN;
       uint32_t ra[32];
 #pragma unroll 1
-      for (uint32_t c0 = col_lo; c0 < col_lo + BN / 2; c0 += 32) {
+      for (uint32_t c0 = col_lo; c0 < col_hi; c0 += 32) {
         tmem_ld32_async(tbase + c0, ra);
         tmem_wait();
         gate_chunk(ra, tbase + c0, c0, xn, valid, slot);
