@@ -526,7 +526,7 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     const bool dev_ok = k <= kMaxFusedK;  // the any-k selection wants the list lengths on the host
     std::vector<uint32_t> slots;
     std::vector<uint64_t> ptrs(B, 0), lens(B, 0), host_off(B, ~0ull), dev_off(B, ~0ull), dev_cap(B, 0), dev_bits(B, 0);
-    uint64_t longest = 0, dev_total = 0, max_up = 0, max_bits = 0;
+    uint64_t longest = 0, dev_total = 0, max_bits = 0;
     for (uint32_t b = 0; b < B; b++) {
       const vkgpu_filter &f = filters[b];
       if (f.device_set) {
@@ -545,10 +545,8 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
           uint64_t mx = 0;
           for (uint64_t i = 0; i < f.n_labels; i++) mx = std::max(mx, f.labels[i]);
           dev_bits[b] = mx + 1;
-          max_up = std::max<uint64_t>(max_up, f.n_labels * 8);
         } else {
           dev_bits[b] = f.bitmap_bits;
-          max_up = std::max<uint64_t>(max_up, (f.bitmap_bits + 7) / 8);
         }
         max_bits = std::max(max_bits, dev_bits[b]);
         continue;
@@ -600,26 +598,45 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
       VK_CUDA(cudaMemcpyAsync(c->lists.p, c->h_misc.p, slots.size() * 4, cudaMemcpyHostToDevice, c->cur));
     VK_CUDA(cudaMemcpyAsync(c->list_off.p, meta_host, (size_t)B * 16, cudaMemcpyHostToDevice, c->cur));
     if (dev_total) {  // after the upload of the (zero) lengths: each conversion writes its own
+      // every list / bitmap of the batch through ONE pinned staging buffer and ONE host-to-device copy (a copy per
+      // query from the caller's pageable memory costs ~50 us each, more than the conversion itself)
+      std::vector<uint64_t> up_off(B, 0);
+      uint64_t up_total = 0;
+      for (uint32_t b = 0; b < B; b++) {
+        if (dev_off[b] == ~0ull) continue;
+        const vkgpu_filter &f = filters[b];
+        up_off[b] = up_total;
+        up_total += ((f.labels ? f.n_labels * 8 : (f.bitmap_bits + 7) / 8) + 15) & ~15ull;
+      }
+      c->h_lists.reserve(std::max<uint64_t>(up_total, 16));
+      for (uint32_t b = 0; b < B; b++) {
+        if (dev_off[b] == ~0ull) continue;
+        const vkgpu_filter &f = filters[b];
+        if (f.labels)
+          std::memcpy(c->h_lists.as<uint8_t>() + up_off[b], f.labels, f.n_labels * 8);
+        else
+          std::memcpy(c->h_lists.as<uint8_t>() + up_off[b], f.label_bitmap, (f.bitmap_bits + 7) / 8);
+      }
       const uint64_t words = (max_bits + 31) / 32;
-      c->scratch0.reserve(std::max<uint64_t>(max_up, 8));
+      c->scratch0.reserve(std::max<uint64_t>(up_total, 16));
       c->scratch1.reserve(std::max<uint64_t>(words, 1) * 4);
       c->scratch2.reserve(((ix->n + 255) / 256 + 1) * 4);
+      VK_CUDA(cudaMemcpyAsync(c->scratch0.p, c->h_lists.p, up_total, cudaMemcpyHostToDevice, c->cur));
       unsigned long long *d_len = reinterpret_cast<unsigned long long *>(c->list_off.as<uint8_t>() + (size_t)B * 8);
       for (uint32_t b = 0; b < B; b++) {
         if (dev_off[b] == ~0ull) continue;
         const vkgpu_filter &f = filters[b];
         const uint64_t bits = dev_bits[b];
+        const uint8_t *src = c->scratch0.as<uint8_t>() + up_off[b];
         if (f.labels) {
-          VK_CUDA(cudaMemcpyAsync(c->scratch0.p, f.labels, f.n_labels * 8, cudaMemcpyHostToDevice, c->cur));
           VK_CUDA(cudaMemsetAsync(c->scratch1.p, 0, ((bits + 31) / 32) * 4, c->cur));
-          launch_set_update(c->scratch1.as<uint32_t>(), c->scratch0.as<uint64_t>(), nullptr, f.n_labels, c->cur);
+          launch_set_update(c->scratch1.as<uint32_t>(), reinterpret_cast<const uint64_t *>(src), nullptr, f.n_labels, c->cur);
           launch_bitmap_to_slots(ix->dLabels.as<uint64_t>(), ix->n, c->scratch1.as<uint8_t>(), bits,
                                  reinterpret_cast<uint32_t *>((uintptr_t)ptrs[b]), c->scratch2.as<uint32_t>(), d_len + b,
                                  c->cur);
           ix->kernels += 4;
         } else {
-          VK_CUDA(cudaMemcpyAsync(c->scratch0.p, f.label_bitmap, (bits + 7) / 8, cudaMemcpyHostToDevice, c->cur));
-          launch_bitmap_to_slots(ix->dLabels.as<uint64_t>(), ix->n, c->scratch0.as<uint8_t>(), bits,
+          launch_bitmap_to_slots(ix->dLabels.as<uint64_t>(), ix->n, src, bits,
                                  reinterpret_cast<uint32_t *>((uintptr_t)ptrs[b]), c->scratch2.as<uint32_t>(), d_len + b,
                                  c->cur);
           ix->kernels += 3;
@@ -872,7 +889,7 @@ void vkgpu_index_destroy(vkgpu_index *ix) {
                       &c->lists, &c->list_off, &c->klimit, &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3,
                       &c->fb_redo, &c->fb_ws, &c->fb_cnt})
       b->release();
-    for (PinnedBuf *b : {&c->h_q, &c->h_dist, &c->h_labels, &c->h_n, &c->h_misc}) b->release();
+    for (PinnedBuf *b : {&c->h_q, &c->h_dist, &c->h_labels, &c->h_n, &c->h_misc, &c->h_lists}) b->release();
   }
   for (auto &kv : ix->sets) {
     kv.second->bitmap.release();

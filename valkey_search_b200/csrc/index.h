@@ -103,6 +103,7 @@ struct SearchCtx {
   DevBuf scratch0, scratch1, scratch2, scratch3;  // path-specific (tensor / hnsw)
   DevBuf fb_redo, fb_ws, fb_cnt;  // tensor path: device-driven exact re-run of the queries whose proof failed
   PinnedBuf h_q, h_dist, h_labels, h_n, h_misc;
+  PinnedBuf h_lists;  // pre-filter: the batch's label lists / bitmaps on their way to the device
   bool busy = false;
   cudaStream_t cur = nullptr;     // stream this call runs on (own stream, or the caller's)
   cudaEvent_t done = nullptr;     // recorded at the end of a call that ran on a caller's stream
