@@ -526,7 +526,7 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     const bool dev_ok = k <= kMaxFusedK;  // the any-k selection wants the list lengths on the host
     std::vector<uint32_t> slots;
     std::vector<uint64_t> ptrs(B, 0), lens(B, 0), host_off(B, ~0ull), dev_off(B, ~0ull), dev_cap(B, 0), dev_bits(B, 0);
-    uint64_t longest = 0, dev_total = 0, max_bits = 0;
+    uint64_t longest = 0, dev_total = 0;
     for (uint32_t b = 0; b < B; b++) {
       const vkgpu_filter &f = filters[b];
       if (f.device_set) {
@@ -548,7 +548,6 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
         } else {
           dev_bits[b] = f.bitmap_bits;
         }
-        max_bits = std::max(max_bits, dev_bits[b]);
         continue;
       }
       size_t start = slots.size();
@@ -617,31 +616,55 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
         else
           std::memcpy(c->h_lists.as<uint8_t>() + up_off[b], f.label_bitmap, (f.bitmap_bits + 7) / 8);
       }
-      const uint64_t words = (max_bits + 31) / 32;
       c->scratch0.reserve(std::max<uint64_t>(up_total, 16));
-      c->scratch1.reserve(std::max<uint64_t>(words, 1) * 4);
-      c->scratch2.reserve(((ix->n + 255) / 256 + 1) * 4);
       VK_CUDA(cudaMemcpyAsync(c->scratch0.p, c->h_lists.p, up_total, cudaMemcpyHostToDevice, c->cur));
       unsigned long long *d_len = reinterpret_cast<unsigned long long *>(c->list_off.as<uint8_t>() + (size_t)B * 8);
+      // jobs in groups whose label bitmaps fit a bounded scratch (256 MB); each group = five launches
+      const uint32_t nb = (uint32_t)((ix->n + 255) / 256);
+      constexpr uint64_t kBitmapBudget = 256ull << 20;
+      std::vector<ResolveJob> jobs;
+      std::vector<uint64_t> bm_off;
+      uint64_t bm_bytes = 0, max_labels = 0;
+      auto flush = [&]() {
+        if (jobs.empty()) return;
+        c->scratch1.reserve(std::max<uint64_t>(bm_bytes, 16));
+        c->scratch2.reserve((size_t)jobs.size() * nb * 4 + 16);
+        c->scratch3.reserve(jobs.size() * sizeof(ResolveJob));
+        for (size_t i = 0; i < jobs.size(); i++)
+          if (jobs[i].labels) jobs[i].bm = c->scratch1.as<uint8_t>() + bm_off[i];
+        if (bm_bytes) VK_CUDA(cudaMemsetAsync(c->scratch1.p, 0, bm_bytes, c->cur));
+        // (pageable source: the runtime stages it before returning, the vector may be reused at once)
+        VK_CUDA(cudaMemcpyAsync(c->scratch3.p, jobs.data(), jobs.size() * sizeof(ResolveJob), cudaMemcpyHostToDevice, c->cur));
+        launch_resolve_lists(c->scratch3.as<ResolveJob>(), (uint32_t)jobs.size(), max_labels, ix->dLabels.as<uint64_t>(), ix->n,
+                             c->scratch2.as<uint32_t>(), d_len, c->cur);
+        ix->kernels += max_labels ? 4 : 3;
+        jobs.clear();
+        bm_off.clear();
+        bm_bytes = 0;
+        max_labels = 0;
+      };
       for (uint32_t b = 0; b < B; b++) {
         if (dev_off[b] == ~0ull) continue;
         const vkgpu_filter &f = filters[b];
-        const uint64_t bits = dev_bits[b];
-        const uint8_t *src = c->scratch0.as<uint8_t>() + up_off[b];
+        ResolveJob j{};
+        j.bits = dev_bits[b];
+        j.out = reinterpret_cast<uint32_t *>((uintptr_t)ptrs[b]);
+        j.query = b;
+        uint64_t need = 0;
         if (f.labels) {
-          VK_CUDA(cudaMemsetAsync(c->scratch1.p, 0, ((bits + 31) / 32) * 4, c->cur));
-          launch_set_update(c->scratch1.as<uint32_t>(), reinterpret_cast<const uint64_t *>(src), nullptr, f.n_labels, c->cur);
-          launch_bitmap_to_slots(ix->dLabels.as<uint64_t>(), ix->n, c->scratch1.as<uint8_t>(), bits,
-                                 reinterpret_cast<uint32_t *>((uintptr_t)ptrs[b]), c->scratch2.as<uint32_t>(), d_len + b,
-                                 c->cur);
-          ix->kernels += 4;
+          j.labels = reinterpret_cast<const uint64_t *>(c->scratch0.as<uint8_t>() + up_off[b]);
+          j.n_labels = f.n_labels;
+          need = (((j.bits + 31) / 32) * 4 + 15) & ~15ull;
         } else {
-          launch_bitmap_to_slots(ix->dLabels.as<uint64_t>(), ix->n, src, bits,
-                                 reinterpret_cast<uint32_t *>((uintptr_t)ptrs[b]), c->scratch2.as<uint32_t>(), d_len + b,
-                                 c->cur);
-          ix->kernels += 3;
+          j.bm = c->scratch0.as<uint8_t>() + up_off[b];
         }
+        if (!jobs.empty() && (bm_bytes + need > kBitmapBudget || jobs.size() >= 1024)) flush();
+        bm_off.push_back(bm_bytes);
+        bm_bytes += need;
+        max_labels = std::max<uint64_t>(max_labels, j.n_labels);
+        jobs.push_back(j);
       }
+      flush();
     }
     if (k_eff > kMaxFusedK)  // the fused top-k of the gather scan stops at 1024: all distances + selection
       flat_select_lists_search_device(ix, c, B, k_eff, ptrs.data(), lens.data(), c->list_off.as<const uint32_t *>(),

@@ -226,6 +226,21 @@ void launch_exact_distances(const float *X, uint32_t Dp, bool l2, const float *q
                             uint64_t n, float *out, cudaStream_t s);
 void launch_pad_rows(const float *src, uint32_t dim, float *dst, uint32_t Dp, uint64_t n, cudaStream_t s);
 void launch_iota_labels(uint64_t *dst, uint64_t start, uint64_t n, cudaStream_t s);
+// One pre-filter list to resolve on the device (misc_kernels.cu, batched): `labels` (nullable: then `bm` already holds
+// the label bitmap) are OR-ed into `bm` (zeroed, >= bits bits), and the ordered slot list of the rows whose label is in
+// `bm` goes to `out`, its length to d_len[query].
+struct ResolveJob {
+  const uint64_t *labels;
+  uint64_t n_labels;
+  uint8_t *bm;
+  uint64_t bits;
+  uint32_t *out;
+  uint32_t query;
+  uint32_t pad;
+};
+// counts = scratch of n_jobs * ceil(n/256) u32; max_labels = longest label list among the jobs (0: bitmaps only)
+void launch_resolve_lists(const ResolveJob *d_jobs, uint32_t n_jobs, uint64_t max_labels, const uint64_t *labels, uint64_t n,
+                          uint32_t *counts, unsigned long long *d_len, cudaStream_t s);
 // ordered compaction; counts = scratch of ceil(n/256) u32
 void launch_bitmap_to_slots(const uint64_t *labels, uint64_t n, const uint8_t *bm, uint64_t bits, uint32_t *out,
                             uint32_t *counts, unsigned long long *count, cudaStream_t s);

@@ -179,6 +179,66 @@ __global__ void __launch_bounds__(256) set_fill_kernel(const uint64_t *__restric
   if (in) out[base + __popc(bal & ((1u << lane) - 1))] = (uint32_t)i;
 }
 
+// Batched form for the pre-filter's per-call label lists (one job per query, blockIdx.y = job): the list is OR-ed into
+// the job's own label bitmap, then the same count / scan / fill as above — five launches for the whole batch.
+__global__ void __launch_bounds__(256) resolve_mark_kernel(const ResolveJob *__restrict__ jobs) {
+  const ResolveJob j = jobs[blockIdx.y];
+  if (j.labels == nullptr) return;  // the job brought a ready bitmap
+  uint32_t *words = reinterpret_cast<uint32_t *>(j.bm);
+  for (uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x; i < j.n_labels; i += (uint64_t)gridDim.x * 256) {
+    const uint64_t lab = j.labels[i];
+    atomicOr(&words[lab >> 5], 1u << (lab & 31));
+  }
+}
+__global__ void __launch_bounds__(256) resolve_count_kernel(const ResolveJob *__restrict__ jobs,
+                                                            const uint64_t *__restrict__ labels, uint64_t n, uint32_t nb,
+                                                            uint32_t *__restrict__ counts) {
+  const ResolveJob j = jobs[blockIdx.y];
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const int c = __syncthreads_count(slot_in_set(labels, n, j.bm, j.bits, i));
+  if (threadIdx.x == 0) counts[(size_t)blockIdx.y * nb + blockIdx.x] = (uint32_t)c;
+}
+__global__ void __launch_bounds__(1024) resolve_scan_kernel(uint32_t *counts, uint32_t nb, unsigned long long *totals,
+                                                            const ResolveJob *__restrict__ jobs) {
+  __shared__ unsigned long long part[1024];
+  uint32_t *cnt = counts + (size_t)blockIdx.x * nb;
+  const uint32_t t = threadIdx.x;
+  const uint32_t per = (nb + 1023) / 1024;
+  const uint32_t lo = min(nb, t * per), hi = min(nb, lo + per);
+  unsigned long long s = 0;
+  for (uint32_t i = lo; i < hi; i++) s += cnt[i];
+  part[t] = s;
+  __syncthreads();
+  for (uint32_t off = 1; off < 1024; off <<= 1) {
+    const unsigned long long v = t >= off ? part[t - off] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  unsigned long long run = t ? part[t - 1] : 0;
+  for (uint32_t i = lo; i < hi; i++) {
+    const uint32_t c = cnt[i];
+    cnt[i] = (uint32_t)run;
+    run += c;
+  }
+  if (t == 1023) totals[jobs[blockIdx.x].query] = part[1023];  // the gather scan reads the list length here
+}
+__global__ void __launch_bounds__(256) resolve_fill_kernel(const ResolveJob *__restrict__ jobs,
+                                                           const uint64_t *__restrict__ labels, uint64_t n, uint32_t nb,
+                                                           const uint32_t *__restrict__ offsets) {
+  __shared__ uint32_t warp_base[8];
+  const ResolveJob j = jobs[blockIdx.y];
+  const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
+  const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const bool in = slot_in_set(labels, n, j.bm, j.bits, i);
+  const uint32_t bal = __ballot_sync(0xffffffffu, in);
+  if (lane == 0) warp_base[w] = __popc(bal);
+  __syncthreads();
+  uint32_t base = offsets[(size_t)blockIdx.y * nb + blockIdx.x];
+  for (uint32_t k = 0; k < w; k++) base += warp_base[k];
+  if (in) j.out[base + __popc(bal & ((1u << lane) - 1))] = (uint32_t)i;
+}
+
 // ---- set algebra over label bitmaps ("next" row N1): AND / OR / AND-NOT of two resident bitmaps, word by word.
 // A shorter operand reads as zeros past its end; bits past `out_bits` are cleared so that every set keeps the
 // invariant "no bit at or beyond its own bit count".  HBM-bound, 12 bytes per output word.
@@ -291,6 +351,20 @@ void launch_bitmap_to_slots(const uint64_t *labels, uint64_t n, const uint8_t *b
   set_count_kernel<<<nb, 256, 0, s>>>(labels, n, bm, bits, counts);
   set_scan_kernel<<<1, 1024, 0, s>>>(counts, nb, count);
   set_fill_kernel<<<nb, 256, 0, s>>>(labels, n, bm, bits, counts, out);
+  VK_CUDA(cudaGetLastError());
+}
+
+void launch_resolve_lists(const ResolveJob *d_jobs, uint32_t n_jobs, uint64_t max_labels, const uint64_t *labels, uint64_t n,
+                          uint32_t *counts, unsigned long long *d_len, cudaStream_t s) {
+  if (n == 0 || n_jobs == 0) return;
+  const uint32_t nb = (uint32_t)((n + 255) / 256);
+  if (max_labels) {
+    const uint32_t gx = (uint32_t)std::min<uint64_t>((max_labels + 255) / 256, 1024);
+    resolve_mark_kernel<<<dim3(gx, n_jobs), 256, 0, s>>>(d_jobs);
+  }
+  resolve_count_kernel<<<dim3(nb, n_jobs), 256, 0, s>>>(d_jobs, labels, n, nb, counts);
+  resolve_scan_kernel<<<n_jobs, 1024, 0, s>>>(counts, nb, d_len, d_jobs);
+  resolve_fill_kernel<<<dim3(nb, n_jobs), 256, 0, s>>>(d_jobs, labels, n, nb, counts);
   VK_CUDA(cudaGetLastError());
 }
 
