@@ -682,6 +682,7 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
   __shared__ uint32_t s_prefix, s_rank, s_pos, s_tie, s_total;
   const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (p.redo && blockIdx.x >= p.redo[0]) return;  // device-driven form: CTA i = i-th re-run query
+  if (p.only_flagged && p.only_flagged[blockIdx.x] == 0) return;  // answered by the bounded merge already
   const uint32_t b = p.redo ? p.redo[2 + blockIdx.x] : blockIdx.x;  // output row
   const uint32_t nslabs = p.redo ? p.redo[1] : p.slabs;
   const uint32_t qtile = blockIdx.x / p.qt, qi = blockIdx.x % p.qt;
@@ -806,6 +807,154 @@ __global__ void __launch_bounds__(MERGE_THREADS) topk_select_merge_kernel(const 
   if (tid == 0) p.out_n[b] = have;
 }
 }  // namespace
+
+// One-pass merge under a known bound (see MergeBound).  Shared memory: sort buffer [sort_n] (its first 8 KB double as
+// the radix histogram, which is dead before the buffer is filled) | kept scores [kBoundedCap] | their positions | list
+// lengths [slabs]: 25 KB at K' = 384, eight CTAs per SM.
+namespace {
+constexpr uint32_t kBoundedCap = 2048;
+__global__ void __launch_bounds__(MERGE_THREADS) topk_bounded_merge_kernel(const MergeParams p, const MergeBound mb) {
+  extern __shared__ __align__(16) uint8_t bsm[];
+  Cand *buf = reinterpret_cast<Cand *>(bsm);                               // [sort_n]  (sort_n >= 512)
+  uint32_t *hist = reinterpret_cast<uint32_t *>(bsm);                      // [2048], aliased
+  uint32_t *s_ord = reinterpret_cast<uint32_t *>(bsm + max((size_t)p.sort_n * sizeof(Cand), (size_t)8192));  // [kBoundedCap]
+  uint32_t *s_at = s_ord + kBoundedCap;                                    // [kBoundedCap]
+  uint32_t *s_cnt = s_at + kBoundedCap;                                    // [slabs]
+  __shared__ uint32_t part[MERGE_THREADS];
+  __shared__ uint32_t s_bound, s_n, s_prefix, s_rank, s_pos, s_tie;
+  const uint32_t b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const uint32_t qtile = b / p.qt, qi = b % p.qt, K = p.k;
+  auto list_index = [&](uint32_t s) -> size_t { return ((size_t)qtile * p.slabs + s) * p.qt + qi; };
+  if (tid == 0) {
+    s_bound = 0;
+    s_n = 0;
+    s_prefix = 0;
+    s_rank = K;
+    s_pos = 0;
+    s_tie = 0;
+  }
+  __syncthreads();
+  {  // bound = min(gthr, max over slabs of gsl); list lengths alongside (all loads in flight at once)
+    uint32_t mx = 0;
+    for (uint32_t s = tid; s < p.slabs; s += MERGE_THREADS) {
+      mx = max(mx, mb.gsl[(size_t)b * mb.gsl_stride + s]);
+      s_cnt[s] = min(p.ws_cnt[list_index(s)], p.cap);
+    }
+    if (mx) atomicMax(&s_bound, mx);
+  }
+  __syncthreads();
+  const uint32_t Tb = min(mb.gthr[b], s_bound);
+  if (Tb == kOrdInf) {  // no bound was ever published for this query (tiny corpus): the selection merge answers it
+    if (tid == 0) mb.fallback[b] = 1;
+    return;
+  }
+  // the one pass: a warp per list, four loads in flight per lane
+  for (uint32_t s = warp; s < p.slabs; s += MERGE_THREADS / 32) {
+    const uint32_t n = s_cnt[s];
+    const size_t base = list_index(s) * p.cap;
+    for (uint32_t i0 = lane; i0 < n; i0 += 128) {
+      uint32_t o[4];
+#pragma unroll
+      for (int u2 = 0; u2 < 4; u2++) {
+        const uint32_t i = i0 + 32 * u2;
+        o[u2] = i < n ? p.ws_ord[base + i] : kOrdInf;
+      }
+#pragma unroll
+      for (int u2 = 0; u2 < 4; u2++) {
+        const uint32_t i = i0 + 32 * u2;
+        if (i < n && o[u2] <= Tb) {
+          const uint32_t pos = atomicAdd(&s_n, 1u);
+          if (pos < kBoundedCap) {
+            s_ord[pos] = o[u2];
+            s_at[pos] = (uint32_t)(base + i);
+          }
+        }
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t n = s_n;
+  if (n > kBoundedCap) {  // uniform
+    if (tid == 0) mb.fallback[b] = 1;
+    return;
+  }
+  uint32_t T = kOrdInf, quota = 0;
+  if (n > K) {  // K-th smallest of the kept scores: 11 / 11 / 10-bit radix select, all in shared memory
+    const int shifts[3] = {21, 10, 0};
+    const uint32_t widths[3] = {11, 11, 10};
+    for (int pass = 0; pass < 3; pass++) {
+      for (uint32_t i = tid; i < 2048; i += MERGE_THREADS) hist[i] = 0;
+      __syncthreads();
+      const uint32_t prefix = s_prefix;
+      const uint32_t hi_mask = pass == 0 ? 0u : ~((1u << (shifts[pass] + widths[pass])) - 1u);
+      const int sh = shifts[pass];
+      const uint32_t wmask = (1u << widths[pass]) - 1u;
+      for (uint32_t i = tid; i < n; i += MERGE_THREADS) {
+        const uint32_t o = s_ord[i];
+        if ((o & hi_mask) == prefix) atomicAdd(&hist[(o >> sh) & wmask], 1u);
+      }
+      __syncthreads();
+      uint32_t sum = 0;
+      for (uint32_t i = 0; i < 8; i++) sum += hist[tid * 8 + i];
+      part[tid] = sum;
+      __syncthreads();
+      if (tid == 0) {
+        uint32_t rank = s_rank, acc = 0, seg = 0;
+        for (; seg < MERGE_THREADS; seg++) {
+          if (acc + part[seg] >= rank) break;
+          acc += part[seg];
+        }
+        uint32_t bin = seg * 8;
+        for (;; bin++) {
+          if (acc + hist[bin] >= rank) break;
+          acc += hist[bin];
+        }
+        s_prefix = prefix | (bin << shifts[pass]);
+        s_rank = rank - acc;
+      }
+      __syncthreads();
+    }
+    T = s_prefix;
+    quota = s_rank;
+  }
+  __syncthreads();  // the histogram is dead: its memory becomes the sort buffer
+  for (uint32_t i = tid; i < p.sort_n; i += MERGE_THREADS) {
+    buf[i].ord = kOrdInf;
+    buf[i].slot = 0xffffffffu;
+    buf[i].label = ~0ull;
+  }
+  __syncthreads();
+  for (uint32_t i = tid; i < n; i += MERGE_THREADS) {
+    const uint32_t o = s_ord[i];
+    bool keep = o < T;
+    if (!keep && o == T && n > K) keep = atomicAdd(&s_tie, 1u) < quota;
+    if (n <= K) keep = true;
+    if (keep) {
+      const uint32_t pos = atomicAdd(&s_pos, 1u);
+      if (pos < p.sort_n) buf[pos] = p.ws[s_at[i]];
+    }
+  }
+  __syncthreads();
+  const uint32_t have = min(s_pos, K);
+  bitonic_sort_cands(buf, p.sort_n, tid, MERGE_THREADS, [] { __syncthreads(); });
+  for (uint32_t i = tid; i < K; i += MERGE_THREADS) {
+    const bool ok = i < have;
+    p.out_dist[(size_t)b * K + i] = ok ? ord_to_f32(buf[i].ord) : __int_as_float(0x7f800000);
+    p.out_labels[(size_t)b * K + i] = ok ? buf[i].label : ~0ull;
+    if (p.out_slots) p.out_slots[(size_t)b * K + i] = ok ? buf[i].slot : 0xffffffffu;
+  }
+  if (tid == 0) {
+    p.out_n[b] = have;
+    mb.fallback[b] = 0;
+  }
+}
+}  // namespace
+
+void launch_topk_bounded_merge(uint32_t B, cudaStream_t stream, const MergeParams &p, const MergeBound &mb) {
+  const size_t smem = std::max((size_t)p.sort_n * sizeof(Cand), (size_t)8192) + (size_t)kBoundedCap * 8 + (size_t)p.slabs * 4;
+  topk_bounded_merge_kernel<<<B, MERGE_THREADS, smem, stream>>>(p, mb);
+  VK_CUDA(cudaGetLastError());
+}
 
 void launch_topk_select_merge(uint32_t B, cudaStream_t stream, const MergeParams &p) {
   const size_t smem = (size_t)p.sort_n * sizeof(Cand) + 2048 * 4 + (size_t)p.slabs * 4;

@@ -90,8 +90,23 @@ struct MergeParams {
   // device-driven form (see GatherParams::redo): CTA i >= redo[0] exits; lists of query i are (i * redo[1] + s),
   // s < redo[1]; results go to output row redo[2 + i].  `slabs` is then only the upper bound that sizes shared memory.
   const uint32_t *redo;
+  // selection merge only: answer just the queries with only_flagged[b] != 0 (nullptr => all)
+  const uint32_t *only_flagged;
+};
+// What the tensor path knows about each query when its candidate pass has finished: an upper bound of the K-th best
+// score (gthr[b]: running K-th best of some slab's list; gsl[b][s]: bound of slab s's j-th best, slabs * j >= K).
+// Entries above min(gthr[b], max_s gsl[b][s]) cannot be among the K best, and every row at or below it is in a list.
+struct MergeBound {
+  const uint32_t *gthr;
+  const uint32_t *gsl;
+  uint32_t gsl_stride;
+  uint32_t *fallback;  // [B] out: 1 => the query was left to the selection merge (no bound, or too many entries)
 };
 void launch_topk_merge(uint32_t B, cudaStream_t stream, const MergeParams &p);
+// approximate-score merge in ONE pass over the lists (tensor path): entries at or below the query's bound are
+// collected in shared memory and the K smallest of those few are selected there; queries it cannot take are flagged
+// in mb.fallback and answered by launch_topk_select_merge with only_flagged
+void launch_topk_bounded_merge(uint32_t B, cudaStream_t stream, const MergeParams &p, const MergeBound &mb);
 // same contract, for approximate scores: ties at the K-th score are broken arbitrarily; sort_n = pow2 >= k
 void launch_topk_select_merge(uint32_t B, cudaStream_t stream, const MergeParams &p);
 

@@ -1159,7 +1159,8 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   c->ws.reserve(nlists * cap * (sizeof(Cand) + 4));
   c->ws_cnt.reserve(nlists * 4);
   const uint32_t gsl_stride = (slabs + 3) & ~3u, flags_pad = (B + 3) & ~3u;
-  c->scratch2.reserve(((size_t)Bpad + flags_pad + (size_t)Bpad * gsl_stride) * 4);  // gthr [Bpad] + flags [B] + gsl
+  // gthr [Bpad] + proof flags [B] + gsl [Bpad][gsl_stride] + merge flags [B]
+  c->scratch2.reserve(((size_t)Bpad + 2 * flags_pad + (size_t)Bpad * gsl_stride) * 4);
   VK_CUDA(cudaMemsetAsync(c->scratch2.p, 0xff, (size_t)Bpad * 4, s));
   uint32_t *d_gsl = c->scratch2.as<uint32_t>() + Bpad + flags_pad;
   VK_CUDA(cudaMemsetAsync(d_gsl, 0xff, (size_t)Bpad * gsl_stride * 4, s));
@@ -1292,7 +1293,25 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   mp.k_limit = nullptr;
   mp.ws_ord = tp.ws_ord;
   ix->prof_begin(c, KK_MERGE);
-  launch_topk_select_merge(B, s, mp);
+  {
+    // one pass under the bound the candidate pass has left behind; a query it cannot take (no bound published, or
+    // more than 2048 entries at or below it) is flagged and answered by the three-pass selection merge
+    static const bool bounded_off = [] {  // A/B switch (profiles/r2_tensor_bounded_merge_ab.log)
+      const char *e = getenv("VKGPU_TENSOR_BMERGE");
+      return e && e[0] == '0';
+    }();
+    if (!bounded_off) {
+      MergeBound mb{};
+      mb.gthr = tp.gthr;
+      mb.gsl = tp.gsl;
+      mb.gsl_stride = gsl_stride;
+      mb.fallback = c->scratch2.as<uint32_t>() + Bpad + flags_pad + (size_t)Bpad * gsl_stride;
+      launch_topk_bounded_merge(B, s, mp, mb);
+      mp.only_flagged = mb.fallback;
+      ix->kernels++;
+    }
+    launch_topk_select_merge(B, s, mp);
+  }
   ix->prof_end(c, KK_MERGE);
 
   // exact re-rank + proof
