@@ -9,7 +9,9 @@
 #include <cstdio>
 #include <cstring>
 #include <ctime>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../valkey_search_b200/host/fanout_merge.h"
@@ -320,6 +322,82 @@ static void InlineFilterAndBatch() {
         EXPECT_TRUE(std::memcmp(&(*single)[j].distance, &(*batch)[b][j].distance, 4) == 0);
       }
     }
+}
+
+// N4, remote-mode requests: in a cluster every shard node answers SearchIndexPartition requests that the coordinators
+// of OTHER nodes send it (src/coordinator/server.cc -> query::SearchAsync -> VectorBase::Search, the same local path),
+// many at once and each with its own query, and the coordinator that asked folds the replies
+// (SearchPartitionResultsTracker, src/query/fanout.cc:153-212).  Here: three shard indexes with the library's dynamic
+// batcher on, 48 concurrent request handlers (16 queries x 3 shards, one thread each — the gRPC threads), one tracker
+// per query filled in whatever order the shards answer.  Every folded reply must carry the single-index answer's
+// distances, and its keys wherever a distance is unique in the reply (the fixture has equal distances, where the fold's
+// own tie rule decides), and the batchers must have coalesced the concurrent requests.
+static void RemoteModeFanout() {
+  using valkey_search::query::fanout::SearchPartitionResultsTracker;
+  constexpr int kShards = 3, kQueries = 16;
+  const uint64_t k = 10;
+  auto vectors = DeterministicallyGenerateVectors(1500, kDimensions, 10.0);
+  auto whole = VectorFlat<float>::Create(CreateFlatVectorIndexProto(kDimensions, DistanceMetric::kL2, 2000, kBlockSize));
+  EXPECT_OK(whole);
+  if (!whole.ok()) return;
+  std::vector<std::shared_ptr<VectorFlat<float>>> shards;
+  for (int s = 0; s < kShards; s++) {
+    auto proto = CreateFlatVectorIndexProto(kDimensions, DistanceMetric::kL2, 2000, kBlockSize);
+    proto.gpu_batch_window_us = 2000;  // the reader pool's batching window
+    proto.gpu_max_batch = 64;
+    auto r = VectorFlat<float>::Create(proto);
+    EXPECT_OK(r);
+    if (!r.ok()) return;
+    shards.push_back(*r);
+  }
+  for (size_t i = 0; i < vectors.size(); ++i) {
+    VerifyAdd(whole->get(), vectors, i, ExpectedResults::kSuccess);
+    VerifyAdd(shards[i % kShards].get(), vectors, i, ExpectedResults::kSuccess);  // keys are cluster-wide unique
+  }
+  std::vector<SearchPartitionResultsTracker> trackers;
+  for (int q = 0; q < kQueries; q++) trackers.emplace_back(k);
+  std::vector<std::mutex> mu(kQueries);  // fanout.cc guards its tracker with a mutex: replies arrive on gRPC threads
+  std::vector<int> failed(kQueries * kShards, 0);
+  std::vector<std::thread> handlers;
+  for (int q = 0; q < kQueries; q++)
+    for (int s = 0; s < kShards; s++)
+      handlers.emplace_back([&, q, s] {
+        auto reply = shards[s]->Search(VectorToStr(vectors[q * 7 + 3]), k, CancelNever());  // the shard's local top-k
+        if (!reply.ok()) {
+          failed[q * kShards + s] = 1;
+          return;
+        }
+        std::lock_guard<std::mutex> lk(mu[q]);
+        trackers[q].AddResults(*reply);
+      });
+  for (auto &t : handlers) t.join();
+  for (int f : failed) EXPECT_EQ(f, 0);
+  for (int q = 0; q < kQueries; q++) {
+    auto want = (*whole)->Search(VectorToStr(vectors[q * 7 + 3]), k, CancelNever());
+    EXPECT_OK(want);
+    if (!want.ok()) continue;
+    auto got = trackers[q].TakeNeighbors();
+    EXPECT_EQ(got.size(), want->size());
+    for (size_t j = 0; j < got.size() && j < want->size(); j++) {
+      EXPECT_TRUE(std::memcmp(&got[j].distance, &(*want)[j].distance, 4) == 0);
+      // inside a run of equal distances the coordinator's fold orders by key, descending, and admits nothing equal to
+      // its worst once full (fanout_merge.h) — only an entry whose distance is unique in the reply names one key
+      const bool tied = (j > 0 && got[j - 1].distance == got[j].distance) ||
+                        (j + 1 < got.size() && got[j + 1].distance == got[j].distance) || j + 1 == got.size();
+      if (!tied) EXPECT_EQ(got[j].external_id, (*want)[j].external_id);
+    }
+  }
+  uint64_t batches = 0, requests = 0;
+  for (auto &sh : shards) {
+    vkgpu_stats st{};
+    EXPECT_EQ(vkgpu_get_stats(sh->handle(), &st), 0);
+    batches += st.batches;
+    requests += st.batched_requests;
+  }
+  EXPECT_EQ(requests, (uint64_t)kQueries * kShards);
+  EXPECT_TRUE(batches < requests);  // the 16 concurrent requests of a shard did not run one by one
+  std::fprintf(stderr, "  remote-mode fan-out: %llu requests in %llu batches over %d shards\n",
+               (unsigned long long)requests, (unsigned long long)batches, kShards);
 }
 
 // In-memory chunk streams (the module's are RDBChunkOutputStream / RDBChunkInputStream)
@@ -1020,7 +1098,8 @@ int main(int argc, char **argv) {
                {"SaveAndLoadFlat", SaveAndLoadFlat},
                {"SaveAndLoadHnsw", SaveAndLoadHnsw},
                {"HnswCountersPerCall", HnswCountersPerCall},
-               {"InlineFilterAndBatch", InlineFilterAndBatch}};
+               {"InlineFilterAndBatch", InlineFilterAndBatch},
+               {"RemoteModeFanout", RemoteModeFanout}};
   {
     const int before = g_failures;
     HostOnly(vkgpu_device_count() > 0);

@@ -30,7 +30,7 @@ def test_cpp_host_mirror_reads_like_reference_vector_test(built):
     p = _run([])
     assert p.returncode == 0, p.stdout + p.stderr
     for case in ("BasicFlat", "BasicHNSW", "EfRuntimeRecall", "IntegrationCosineGoldens", "Prefilter", "SaveAndLoadFlat", "SaveAndLoadHnsw", "HnswCountersPerCall",
-                 "InlineFilterAndBatch"):
+                 "InlineFilterAndBatch", "RemoteModeFanout"):
         assert f"[  OK  ] {case}" in p.stdout, p.stdout + p.stderr
 
 
