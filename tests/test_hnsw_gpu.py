@@ -188,7 +188,9 @@ def test_hnsw_gpu_build_sequential_inserts_reproduce_reference_graph(built):
 
 
 @pytest.mark.parametrize("metric,N,D,M,efc,ef", [("L2", 1000, 100, 16, 20, 160), ("L2", 20000, 64, 16, 200, 128),
-                                                  ("IP", 8000, 96, 16, 100, 64)])
+                                                  ("IP", 8000, 96, 16, 100, 64),
+                                                  # EF_CONSTRUCTION beyond 1024 (lists of 144 KB in shared memory)
+                                                  ("L2", 4000, 64, 16, 2000, 64)])
 def test_hnsw_gpu_build_recall_at_least_reference(built, metric, N, D, M, efc, ef):
     """Batched GPU build vs the reference's sequential build at identical M / ef_construction / ef_runtime:
     recall@10 against exact FLAT ground truth must not be lower (EfRuntimeRecall bar: >= 0.96 on the first case)."""
