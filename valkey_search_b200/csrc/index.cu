@@ -97,12 +97,17 @@ SearchCtx *vkgpu_index_impl::acquire_ctx() {
         pick = c.get();
         break;
       }
-    if (!pick && ctxs.size() >= 16)
+    // ... but only two deep: a third context that is free on the host and still busy on the device means the caller is
+    // already two calls ahead — wait for the oldest instead of allocating another context's buffers (a cudaMalloc in
+    // the middle of a stream of searches stalls the device far longer than the wait)
+    if (!pick) {
+      uint32_t pending = 0;
       for (auto &c : ctxs)
-        if (!c->busy) {
-          pick = c.get();
-          break;
-        }
+        if (!c->busy) pending++;
+      if (pending >= 2 || ctxs.size() >= 16)
+        for (auto &c : ctxs)  // the one whose asynchronous call was enqueued first
+          if (!c->busy && (!pick || c->done_seq < pick->done_seq)) pick = c.get();
+    }
     if (pick) {
       SearchCtx *c = pick;
       c->busy = true;
@@ -713,6 +718,8 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     if (user_stream) {  // asynchronous: the caller synchronises its own stream
       VK_CUDA(cudaEventRecord(c->done, c->cur));
       c->done_pending = true;
+      static std::atomic<uint64_t> seq{0};
+      c->done_seq = ++seq;
     } else {
       VK_CUDA(cudaStreamSynchronize(c->cur));
     }

@@ -108,6 +108,7 @@ struct SearchCtx {
   cudaStream_t cur = nullptr;     // stream this call runs on (own stream, or the caller's)
   cudaEvent_t done = nullptr;     // recorded at the end of a call that ran on a caller's stream
   bool done_pending = false;
+  uint64_t done_seq = 0;          // order in which asynchronous calls were enqueued (oldest is reused first)
   // per-kernel-kind CUDA-event timing (enabled by vkgpu_set_profiling)
   cudaEvent_t ev_beg[kNumKernelKinds] = {}, ev_end[kNumKernelKinds] = {};
   bool ev_pending[kNumKernelKinds] = {};
