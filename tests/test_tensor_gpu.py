@@ -18,7 +18,9 @@ def _bits(a):
                                              # shapes in which every CTA walks >= 32 tiles, i.e. the sampling pass runs:
                                              # 256-query tiles (IP, COSINE) and the 64-query tile
                                              ("IP", 600_000, 64, 300, 10), ("COSINE", 640_000, 48, 257, 20),
-                                             ("L2", 700_000, 64, 16, 10), ("IP", 700_000, 32, 64, 100)])
+                                             ("L2", 700_000, 64, 16, 10), ("IP", 700_000, 32, 64, 100),
+                                             # k beyond 128 (K' = 512 and 640 survivors per query; limit 192)
+                                             ("L2", 300_000, 96, 200, 150), ("IP", 640_000, 64, 300, 192)])
 def test_tensor_path_equals_exact_path(built, metric, N, D, B, k):
     import valkey_search_b200 as V
     rng = np.random.default_rng(N + D + B)

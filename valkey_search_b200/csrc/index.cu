@@ -685,7 +685,7 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
     // rows: every score ties): a re-run streams the whole corpus per query, five times what the exact scan costs
     const uint64_t tq = ix->tensor_queries.load();
     const bool tensor_unprofitable = tq >= 4096 && tensor_fallbacks_seen(ix) * 8 > tq;
-    if (ix->flat_path == VKGPU_PATH_AUTO && k_eff <= 128 && !ix->tensor_unavailable && !tensor_unprofitable &&
+    if (ix->flat_path == VKGPU_PATH_AUTO && k_eff <= kTensorMaxK && !ix->tensor_unavailable && !tensor_unprofitable &&
         tensor_path_cheaper(ix, B)) {
       // first large batch: build the bf16 mirror (searches only read the fp32 rows, so this is safe under
       // the shared lock; tensor_mu makes it happen once).  No room for the mirror: the exact scan answers, for good.

@@ -1009,8 +1009,8 @@ TensorState *ts(vkgpu_index_impl *ix) { return reinterpret_cast<TensorState *>(i
 // ------------------------------------------------------------------------------------------------ host
 bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k) {
   (void)B;
-  // K' = 3k+64 rounded to 128 <= 512; the re-rank stages eight rows in shared memory (Dp <= 4096: 145 KB)
-  return ix->tensor_ready && k <= 128 && ix->n >= 4096 && ix->Dp <= 4096;
+  // K' = 3k+64 rounded to 128 <= 640; the re-rank stages eight rows in shared memory (Dp <= 4096: 145 KB)
+  return ix->tensor_ready && k <= kTensorMaxK && ix->n >= 4096 && ix->Dp <= 4096;
 }
 // AUTO policy: a cost model fitted to B200 measurements at 768 dims (both paths scale with rows x dims;
 // profiles/tensor_kernel_timing.py with EXP_PATH=exact|tensor, u = rows x dims / (10M x 768)):
@@ -1359,7 +1359,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   // (gather_scan_ldg_kernel over all rows) divides itself among the flagged queries, or exits at once when there are
   // none (the usual case: three near-empty launches instead of a device-to-host copy and a stream synchronisation).
   {
-    const uint32_t fb_cap = 256;  // k_eff <= 128 on this path: cap >= k + 64
+    const uint32_t fb_cap = 256;  // k_eff <= kTensorMaxK = 192 on this path: cap >= k + 64
     const uint32_t fb_grid = 6 * (uint32_t)ix->num_sms;
     const uint32_t fb_tiles = (uint32_t)std::max<uint64_t>(1, (ix->n + 63) / 64);
     const size_t fb_lists = std::max<size_t>(fb_grid, B);

@@ -5,6 +5,10 @@
 
 namespace vkgpu {
 
+// largest k the tensor path serves: K' = 3k + 64 (rounded to 128) survivors per query must leave room in the 1024-entry
+// candidate lists for two tiles of appends between trims (K' <= 640), and k + 64 fit the exact re-run's lists
+constexpr uint32_t kTensorMaxK = 192;
+
 bool tensor_path_cheaper(const vkgpu_index_impl *ix, uint32_t B);  // AUTO policy (cost model)
 bool tensor_path_supported(const vkgpu_index_impl *ix, uint32_t B, uint32_t k);
 void tensor_prepare(vkgpu_index_impl *ix);                       // build the bf16 mirror + norms
