@@ -95,3 +95,59 @@ def test_flat_deadline_is_polled_at_the_launch_boundaries(built):
                                      C.byref(_opts(L, _now_ns() + 10_000_000_000, False)), d.ctypes.data, l.ctypes.data,
                                      n.ctypes.data, C.byref(late))
     assert rc == L.OK and late.value == 0 and np.all(n == k)
+
+
+def test_flat_deadline_inside_the_candidate_pass(built):
+    """FLAT on the tensor path: the producer of every CTA compares the device clock with the deadline before each
+    corpus tile (bruteforce.h:129 polls its token per row).  A 1 ms deadline inside a ~5 ms scan of 4M x 768 rows comes
+    back early, flags every query as cut short, and what it returns is what the reference's heap would hold: an
+    ascending list of real rows with their exact distances, never better than the complete answer rank by rank.  The
+    next search without a deadline gives the complete answer again."""
+    torch = pytest.importorskip("torch")
+    import valkey_search_b200 as V
+    from valkey_search_b200 import _lib as L
+    lib = L.lib()
+    N, D, B, k = 4_000_000, 768, 1024, 100
+    dev = torch.device("cuda", 0)
+    ix = V.VectorFlat(D, V.DistanceMetric.L2, initial_cap=N)
+    for blk in range(4):
+        g = torch.Generator(device=dev)
+        g.manual_seed(77 + blk)
+        Xb = torch.randn((N // 4, D), generator=g, device=dev, dtype=torch.float32)
+        torch.cuda.synchronize()
+        L.check(lib.vkgpu_add_batch_device(ix.handle(), None, Xb.data_ptr(), N // 4))
+        del Xb
+    ix.SetSearchPath(V.PATH_TENSOR)
+    Q = np.random.default_rng(5).standard_normal((B, D)).astype(np.float32)
+    d, l, n = np.zeros((B, k), np.float32), np.zeros((B, k), np.uint64), np.zeros(B, np.uint32)
+    late = C.c_uint32()
+
+    def run(opts):
+        t0 = time.perf_counter()
+        rc = lib.vkgpu_search_batch_opts(ix.handle(), Q.ctypes.data, B, k, 0, None, opts, d.ctypes.data, l.ctypes.data,
+                                         n.ctypes.data, C.byref(late))
+        return rc, (time.perf_counter() - t0) * 1e3
+
+    assert run(None)[0] == L.OK  # builds the bf16 mirror
+    rc, full_ms = run(C.byref(_opts(L, _now_ns() + 30_000_000_000, False)))
+    assert rc == L.OK and late.value == 0 and np.all(n == k)
+    full_d, full_l = d.copy(), l.copy()
+    assert full_ms > 3.0, full_ms
+    rc, cut_ms = run(C.byref(_opts(L, _now_ns() + 1_000_000, False)))
+    assert rc == L.OK, lib.vkgpu_last_error()
+    assert late.value == B, "the scan was not cut short"
+    assert cut_ms < 0.8 * full_ms, (cut_ms, full_ms)
+    assert np.all(n <= k)
+    worse = 0
+    for b in range(0, B, 37):
+        m = int(n[b])
+        assert np.all(np.diff(d[b, :m]) >= 0) and np.all(l[b, :m] < N)
+        assert np.all(d[b, :m] >= full_d[b, :m])  # a prefix of the corpus cannot beat the whole corpus
+        worse += int(np.any(d[b, :m] > full_d[b, :m]) or m < k)
+        if m:  # the distances are the reference's exact ones
+            ex = np.empty(m, np.float32)
+            L.check(lib.vkgpu_distances(ix.handle(), Q[b].ctypes.data, l[b, :m].copy().ctypes.data, m, ex.ctypes.data))
+            assert np.array_equal(ex.view(np.uint32), d[b, :m].view(np.uint32))
+    assert worse > 0  # it really stopped early
+    rc, _ = run(None)
+    assert rc == L.OK and np.array_equal(l, full_l) and np.array_equal(d.view(np.uint32), full_d.view(np.uint32))

@@ -502,7 +502,9 @@ DeviceSet *device_set_slots(vkgpu_index_impl *ix, SearchCtx *c, uint64_t set_id)
 // FLAT search over the whole shard (vector_flat.cc:224-254: k = min(k,count); empty index => empty reply)
 static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, uint32_t B, uint32_t k,
                         const vkgpu_filter *filters, float *out_dist, uint64_t *out_labels, uint32_t *out_n,
-                        bool out_on_device, cudaStream_t user_stream) {
+                        bool out_on_device, cudaStream_t user_stream, uint64_t deadline_gt = 0,
+                        bool *timed_out = nullptr) {
+  if (timed_out) *timed_out = false;
   if (ix->n == 0 || k == 0) {
     if (out_on_device) {
       VK_CUDA(cudaMemset(out_n, 0, (size_t)B * 4));
@@ -514,6 +516,11 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
   CtxLease lease(ix);
   SearchCtx *c = lease.c;
   if (user_stream) c->cur = user_stream;
+  c->deadline_gt = deadline_gt;
+  if (deadline_gt) {
+    c->h_flag.reserve(16);
+    *c->h_flag.as<uint32_t>() = 0;
+  }
   stage_queries(ix, c, Q, B, q_on_device);
 
   uint32_t k_eff;
@@ -724,8 +731,10 @@ static void flat_search(vkgpu_index_impl *ix, const float *Q, bool q_on_device, 
       VK_CUDA(cudaStreamSynchronize(c->cur));
     }
   } else {
-    fetch_results(c, B, k_eff, k, out_dist, out_labels, out_n);
+    fetch_results(c, B, k_eff, k, out_dist, out_labels, out_n);  // synchronises the stream
+    if (timed_out && deadline_gt) *timed_out = *c->h_flag.as<volatile uint32_t>() != 0;
   }
+  c->deadline_gt = 0;
   ix->searches += B;
 }
 
@@ -919,7 +928,7 @@ void vkgpu_index_destroy(vkgpu_index *ix) {
                       &c->lists, &c->list_off, &c->klimit, &c->scratch0, &c->scratch1, &c->scratch2, &c->scratch3,
                       &c->fb_redo, &c->fb_ws, &c->fb_cnt})
       b->release();
-    for (PinnedBuf *b : {&c->h_q, &c->h_dist, &c->h_labels, &c->h_n, &c->h_misc, &c->h_lists}) b->release();
+    for (PinnedBuf *b : {&c->h_q, &c->h_dist, &c->h_labels, &c->h_n, &c->h_misc, &c->h_lists, &c->h_flag}) b->release();
   }
   for (auto &kv : ix->sets) {
     kv.second->bitmap.release();
@@ -1130,8 +1139,12 @@ int vkgpu_search_batch_opts(vkgpu_index *ix, const float *Q, uint32_t B, uint32_
         if (out_timed_out) *out_timed_out = B;
         return;
       }
-      flat_search(ix, Q, false, B, k, filters, out_dist, out_labels, out_n, false, nullptr);
-      if (deadline_ns && now_ns() >= deadline_ns && out_timed_out) *out_timed_out = B;
+      // round 2: the tensor candidate pass polls the deadline on the device before every corpus tile; when it fires
+      // the answer is the exact top k of the rows scanned so far, as the reference's heap would hold
+      bool cut = false;
+      flat_search(ix, Q, false, B, k, filters, out_dist, out_labels, out_n, false, nullptr, ix->device_deadline(deadline_ns),
+                  &cut);
+      if ((cut || (deadline_ns && now_ns() >= deadline_ns)) && out_timed_out) *out_timed_out = B;
       return;
     }
     uint32_t late = 0;

@@ -109,6 +109,8 @@ struct SearchCtx {
   cudaEvent_t done = nullptr;     // recorded at the end of a call that ran on a caller's stream
   bool done_pending = false;
   uint64_t done_seq = 0;          // order in which asynchronous calls were enqueued (oldest is reused first)
+  uint64_t deadline_gt = 0;       // this call's deadline on the device clock (0 = none); FLAT tensor path polls it per tile
+  PinnedBuf h_flag;               // [1] u32: the candidate pass stopped at its deadline (read after the call's sync)
   // per-kernel-kind CUDA-event timing (enabled by vkgpu_set_profiling)
   cudaEvent_t ev_beg[kNumKernelKinds] = {}, ev_end[kNumKernelKinds] = {};
   bool ev_pending[kNumKernelKinds] = {};

@@ -87,6 +87,8 @@ struct TensorParams {
   uint32_t jrank;            // j = ceil(K'/slabs): slabs*j >= K' rows are <= max_s gsl[q][s]
   uint32_t seed_tiles;       // SEED instantiation: corpus tiles each CTA samples (4 or 8); 0 otherwise
   uint32_t exp;              // -DVKGPU_TENSOR_TRACE builds only: timing experiment selector (VKGPU_TENSOR_EXP)
+  unsigned long long deadline_gt;  // %globaltimer value after which a CTA takes up no further corpus tile (0 = never)
+  uint32_t *timed_out;       // set to 1 by a CTA that stopped early (the scan then covers a prefix of every slab)
   int metric_l2;
 };
 
@@ -226,6 +228,26 @@ __device__ __forceinline__ unsigned long long gtime() {
   do {                       \
   } while (0)
 #endif
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// mbarrier wait that gives up when *stop <= t (a word in shared memory another role of the CTA writes once)
+__device__ __forceinline__ bool mbar_wait_or_stop(uint64_t *bar, uint32_t parity, const uint32_t *stop, uint32_t t) {
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(2000u)
+        : "memory");
+    if (ok) return true;
+    if (*reinterpret_cast<const volatile uint32_t *>(stop) <= t) return false;
+  }
+}
 // ---------------------------------------------------------------- the candidate kernel
 // SEED = the sampling pass launched ahead of the candidate pass: the same producer / MMA / TMEM pipeline over the
 // FIRST p.seed_tiles tiles of every CTA's slab, with an epilogue that appends nothing — it keeps, per query, the
@@ -262,6 +284,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
   uint32_t *sync_tile = need + 8;                                  // tile index of the next trim rendezvous
   uint32_t *epi_tile = sync_tile + 1;                              // tile the epilogue has reached (paces warps 2-3)
   uint32_t *epi_done = sync_tile + 2;
+  // Deadline (bruteforce.h:129 polls its token per row): the TMA producer looks at the device clock before every corpus
+  // tile; past the deadline it publishes the index of the first tile it will NOT fetch, the MMA issuer (blocked on that
+  // tile's first stage) publishes the first tile it will not compute, the epilogue warps (blocked on its accumulator)
+  // leave their loop.  The lists then hold a prefix of the slab; merge and re-rank answer from what was scanned.
+  uint32_t *stop_t = sync_tile + 3;
+  uint32_t *mma_stop = sync_tile + 4;
 
   const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   // PAIR: cluster = (query tile, pair slab); CTA `rank` of the pair owns corpus tiles 2T + rank, i.e. it is
@@ -293,6 +321,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     *sync_tile = 0xffffffffu;
     *epi_tile = 0;
     *epi_done = 0;
+    *stop_t = 0xffffffffu;
+    *mma_stop = 0xffffffffu;
   }
   for (uint32_t i = tid; i < 32u * BN; i += TC_THREADS) gmin[i] = kOrdInf;
   if (warp == 2) {
@@ -319,6 +349,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     if (lane == 0) {
       uint32_t stage = 0, phase = 0, tp = 0;
       for (uint32_t tile = slab; tile < total_tiles && tp < tile_limit; tile += p.slabs, tp++) {
+        if (!SEED && !PAIR && p.deadline_gt && globaltimer_ns() > p.deadline_gt) {
+          *reinterpret_cast<volatile uint32_t *>(stop_t) = tp;  // nothing of tile tp has been requested
+          break;
+        }
         for (uint32_t kb = 0; kb < p.kchunks; kb++) {
           mbar_wait_parked(&empty[stage], phase ^ 1);
           if constexpr (PAIR) {
@@ -359,8 +393,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
         tc_fence_after();
         VK_TRACE(0, t, true);
         const uint32_t tmem_d = tmem_base + a * BN;
+        bool stopped = false;
         for (uint32_t kb = 0; kb < p.kchunks; kb++) {
-          mbar_wait_parked(&full[stage], phase);
+          if (kb == 0 && !SEED && !PAIR && p.deadline_gt) {  // the producer stops at tile boundaries only
+            if (!mbar_wait_or_stop(&full[stage], phase, stop_t, t)) {
+              stopped = true;
+              break;
+            }
+          } else {
+            mbar_wait_parked(&full[stage], phase);
+          }
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + stage * B_STAGE_BYTES);
@@ -379,6 +421,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
             stage = 0;
             phase ^= 1;
           }
+        }
+        if (stopped) {
+          *reinterpret_cast<volatile uint32_t *>(mma_stop) = t;  // accumulator t will never be signalled
+          break;
         }
         if constexpr (PAIR) tc_commit_pair(&tfull[a], 3); else tc_commit(&tfull[a]);  // accumulator complete
         VK_TRACE(1, t, true);
@@ -663,7 +709,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
       const uint64_t slot = (uint64_t)tile * BM + et;
       const bool valid = slot < p.n_rows;
       const float xn = (valid && p.metric_l2) ? p.xnorm[slot] : 0.0f;
-      mbar_wait_parked(&tfull[a], (t >> 1) & 1);
+      if (!PAIR && p.deadline_gt) {
+        if (!mbar_wait_or_stop(&tfull[a], (t >> 1) & 1, mma_stop, t)) break;  // same decision in all twelve warps
+      } else {
+        mbar_wait_parked(&tfull[a], (t >> 1) & 1);
+      }
       tc_fence_after();
       VK_TRACE(2, t, tid == 128);
 
@@ -715,7 +765,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
     // No final trim: the merge is selection based (topk_select_merge_kernel) and takes lists of any length up to
     // cap; trimming ~450-entry lists to K' here used to cost 0.7 ms per launch for nothing.
     named_bar_sync(2, EPI_THREADS);
-    if (tid == 128) *reinterpret_cast<volatile uint32_t *>(epi_done) = 1;
+    if (tid == 128) {
+      *reinterpret_cast<volatile uint32_t *>(epi_done) = 1;
+      if (p.timed_out && *reinterpret_cast<volatile uint32_t *>(mma_stop) != 0xffffffffu) *p.timed_out = 1;
+    }
     for (uint32_t c = tid - 128; c < BN; c += EPI_THREADS)
       p.ws_cnt[((size_t)qtile * p.slabs + slab) * BN + c] = min(cnt[c], p.cap);
     }  // !SEED
@@ -838,6 +891,7 @@ struct RerankParams {
   uint64_t *out_labels;      // [B][k]
   uint32_t *out_n;           // [B]
   uint32_t *flags;           // [B]: 1 => margin too thin, re-run on the exact scan
+  const uint32_t *timed_out; // the candidate pass stopped at its deadline: partial answers, nothing is re-run
 };
 
 constexpr int RR_THREADS = 128;  // eight staged rows x sixteen threads (thread j of a row = the reference's SIMD lane j)
@@ -971,7 +1025,7 @@ __global__ void __launch_bounds__(RR_THREADS) rerank_kernel(const RerankParams p
       }
       if (!(lower > dk)) flag = 1;
     }
-    p.flags[b] = flag;
+    p.flags[b] = (p.timed_out && *p.timed_out) ? 0u : flag;
   }
 }
 
@@ -1159,8 +1213,10 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   c->ws.reserve(nlists * cap * (sizeof(Cand) + 4));
   c->ws_cnt.reserve(nlists * 4);
   const uint32_t gsl_stride = (slabs + 3) & ~3u, flags_pad = (B + 3) & ~3u;
-  // gthr [Bpad] + proof flags [B] + gsl [Bpad][gsl_stride] + merge flags [B]
-  c->scratch2.reserve(((size_t)Bpad + 2 * flags_pad + (size_t)Bpad * gsl_stride) * 4);
+  // gthr [Bpad] + proof flags [B] + gsl [Bpad][gsl_stride] + merge flags [B] + timed-out word
+  c->scratch2.reserve(((size_t)Bpad + 2 * flags_pad + (size_t)Bpad * gsl_stride + 4) * 4);
+  uint32_t *d_timed_out = c->scratch2.as<uint32_t>() + Bpad + 2 * flags_pad + (size_t)Bpad * gsl_stride;
+  VK_CUDA(cudaMemsetAsync(d_timed_out, 0, 16, s));
   VK_CUDA(cudaMemsetAsync(c->scratch2.p, 0xff, (size_t)Bpad * 4, s));
   uint32_t *d_gsl = c->scratch2.as<uint32_t>() + Bpad + flags_pad;
   VK_CUDA(cudaMemsetAsync(d_gsl, 0xff, (size_t)Bpad * gsl_stride * 4, s));
@@ -1187,6 +1243,8 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   tp.gsl_stride = gsl_stride;
   tp.jrank = (kprime + slabs - 1) / slabs;
   tp.metric_l2 = ix->metric_l2 ? 1 : 0;
+  tp.deadline_gt = c->deadline_gt;
+  tp.timed_out = d_timed_out;
   static_assert(Ring<true>::kBytes == Ring<false>::kBytes && Ring<false, BN_SMALL>::kBytes == Ring<false>::kBytes,
                 "all ring geometries use the same shared memory");
   // operand ring + group minima [32][bn] + barriers, thresholds, list counters
@@ -1340,6 +1398,7 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
   rp.out_labels = c->out_labels.as<uint64_t>();
   rp.out_n = c->out_n.as<uint32_t>();
   rp.flags = c->scratch2.as<uint32_t>() + Bpad;
+  rp.timed_out = d_timed_out;
   const size_t rsmem = (size_t)kprime * 8 + (size_t)ix->Dp * 4 +
                        std::max((size_t)RR_ROWS * (ix->Dp + 16) * 4, (size_t)rp.sort_n * sizeof(Cand));
   VK_REQUIRE(rsmem <= 200 * 1024, VKGPU_ERR_UNSUPPORTED, "vector too large for the re-rank staging buffer");
@@ -1396,6 +1455,10 @@ void tensor_search_device(vkgpu_index_impl *ix, SearchCtx *c, uint32_t B, uint32
     fm.redo = redo;
     launch_topk_merge(B, s, fm);
     VK_CUDA(cudaMemcpyAsync(t->h_fb_total.p, t->fb_total.p, 8, cudaMemcpyDeviceToHost, s));
+    if (c->deadline_gt) {
+      c->h_flag.reserve(16);
+      VK_CUDA(cudaMemcpyAsync(c->h_flag.p, d_timed_out, 4, cudaMemcpyDeviceToHost, s));
+    }
     ix->kernels += 3;
     ix->tensor_queries += B;
   }
