@@ -170,9 +170,9 @@ int vkgpu_search_batch(vkgpu_index *h, const float *Q, uint32_t B, uint32_t k, u
  * running when it passes stops and its result list as it stands is the answer.  With VKGPU_SEARCH_PARTIAL_RESULTS
  * (enable_partial_results, vector_hnsw.cc:313-329) that partial answer is returned with VKGPU_OK; without it the call
  * returns VKGPU_ERR_CANCELLED ("Search operation cancelled due to timeout").  FLAT (bruteforce.h:129,
- * vector_flat.cc:224-254: the reference returns what its heap holds, never an error): the tensor-core candidate pass polls
- * before every corpus tile and answers with the exact top k of the rows scanned so far; the exact-scan paths poll at
- * their launch boundaries.  *out_timed_out (may be NULL) = queries whose search was cut short. */
+ * vector_flat.cc:224-254: the reference returns what its heap holds, never an error): the tensor-core candidate pass
+ * polls before every corpus tile and answers with the best k of the rows scanned so far (exact distances; a cut-short
+ * query is not re-run); the exact-scan paths poll at their launch boundaries.  *out_timed_out (may be NULL) = queries whose search was cut short. */
 typedef struct vkgpu_search_opts {
   uint32_t struct_size;   /* sizeof(vkgpu_search_opts) */
   uint32_t flags;         /* VKGPU_SEARCH_* */

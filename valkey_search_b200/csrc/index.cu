@@ -1140,7 +1140,7 @@ int vkgpu_search_batch_opts(vkgpu_index *ix, const float *Q, uint32_t B, uint32_
         return;
       }
       // round 2: the tensor candidate pass polls the deadline on the device before every corpus tile; when it fires
-      // the answer is the exact top k of the rows scanned so far, as the reference's heap would hold
+      // the answer is the best k of the rows scanned so far with their exact distances (the reference returns its heap)
       bool cut = false;
       flat_search(ix, Q, false, B, k, filters, out_dist, out_labels, out_n, false, nullptr, ix->device_deadline(deadline_ns),
                   &cut);
