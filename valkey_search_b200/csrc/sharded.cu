@@ -148,6 +148,7 @@ struct Worker {
     }
     if (th.joinable()) th.join();
   }
+  ~Worker() { shutdown(); }  // a handle that failed half way through its construction still joins its threads
 };
 
 struct Shard {
@@ -182,9 +183,13 @@ struct vkgpu_sharded {
   std::atomic<uint64_t> searches{0}, merges{0};
 
   uint32_t G() const { return (uint32_t)shards.size(); }
+  // one byte per label below kDenseLabels (the module's internal ids count up from zero: 100 MB for C4's 10^8 rows);
+  // labels beyond go to the hash map, so that a single large label cannot ask for gigabytes of host memory
+  static constexpr uint64_t kDenseLabels = 1ull << 28;
   void route_set(uint64_t label, uint32_t g) {
-    if (label < (1ull << 32)) {
-      if (label >= shard_of_dense.size()) shard_of_dense.resize(std::max<size_t>(label + 1, shard_of_dense.size() * 2), 0);
+    if (label < kDenseLabels) {
+      if (label >= shard_of_dense.size())
+        shard_of_dense.resize(std::min<size_t>(kDenseLabels, std::max<size_t>(label + 1, shard_of_dense.size() * 2)), 0);
       shard_of_dense[label] = (uint8_t)(g + 1);
     } else {
       shard_of_sparse[label] = (uint8_t)(g + 1);
@@ -194,7 +199,7 @@ struct vkgpu_sharded {
     uint8_t v = 0;
     if (label < shard_of_dense.size()) {
       v = shard_of_dense[label];
-    } else if (label >= (1ull << 32)) {
+    } else if (label >= kDenseLabels) {
       auto it = shard_of_sparse.find(label);
       if (it != shard_of_sparse.end()) v = it->second;
     }
@@ -305,10 +310,13 @@ int vkgpu_sharded_create(const vkgpu_config *cfg, const int32_t *devices, uint32
     VK_CUDA(cudaGetDeviceCount(&have));
     for (uint32_t g = 0; g < n_devices; g++)
       SH_REQUIRE(devices[g] >= 0 && devices[g] < have, VKGPU_ERR_INVALID, "no such device: " + std::to_string(devices[g]));
-    auto s = std::make_unique<vkgpu_sharded>();
+    // a failure on a later shard (out of memory, say) releases the earlier ones: vkgpu_sharded_destroy takes a handle
+    // in any state of construction
+    std::unique_ptr<vkgpu_sharded, void (*)(vkgpu_sharded *)> s(new vkgpu_sharded(), vkgpu_sharded_destroy);
     s->cfg = *cfg;
     for (uint32_t g = 0; g < n_devices; g++) {
-      auto sh = std::make_unique<Shard>();
+      s->shards.push_back(std::make_unique<Shard>());
+      Shard *sh = s->shards.back().get();
       sh->device = devices[g];
       vkgpu_config c = *cfg;
       c.device = devices[g];
@@ -318,7 +326,6 @@ int vkgpu_sharded_create(const vkgpu_config *cfg, const int32_t *devices, uint32
       VK_CUDA(cudaSetDevice(sh->device));
       VK_CUDA(cudaStreamCreateWithFlags(&sh->stream, cudaStreamNonBlocking));
       sh->worker.start();
-      s->shards.push_back(std::move(sh));
     }
     enable_peer_access(s.get());
     *out = s.release();
@@ -332,21 +339,23 @@ int vkgpu_sharded_adopt(vkgpu_index *const *shards, uint32_t n_shards, vkgpu_sha
   return sh_guarded([&] {
     SH_REQUIRE(shards && out, VKGPU_ERR_INVALID, "null argument");
     SH_REQUIRE(n_shards >= 1 && n_shards <= 16, VKGPU_ERR_INVALID, "1 to 16 shards");
-    auto s = std::make_unique<vkgpu_sharded>();
-    s->adopted = true;
     for (uint32_t g = 0; g < n_shards; g++) {
       SH_REQUIRE(shards[g], VKGPU_ERR_INVALID, "null shard");
       SH_REQUIRE(shards[g]->cfg.dim == shards[0]->cfg.dim && shards[g]->cfg.metric == shards[0]->cfg.metric &&
                      shards[g]->cfg.algo == shards[0]->cfg.algo,
                  VKGPU_ERR_INVALID, "shards of one index share dimension, metric and algorithm");
-      auto sh = std::make_unique<Shard>();
+    }
+    std::unique_ptr<vkgpu_sharded, void (*)(vkgpu_sharded *)> s(new vkgpu_sharded(), vkgpu_sharded_destroy);
+    s->adopted = true;
+    for (uint32_t g = 0; g < n_shards; g++) {
+      s->shards.push_back(std::make_unique<Shard>());
+      Shard *sh = s->shards.back().get();
       sh->ix = shards[g];
       sh->owned = false;
       sh->device = shards[g]->device;
       VK_CUDA(cudaSetDevice(sh->device));
       VK_CUDA(cudaStreamCreateWithFlags(&sh->stream, cudaStreamNonBlocking));
       sh->worker.start();
-      s->shards.push_back(std::move(sh));
     }
     s->cfg = shards[0]->cfg;
     enable_peer_access(s.get());
