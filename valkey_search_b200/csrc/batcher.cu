@@ -71,6 +71,10 @@ void Batcher::run() {
         if (window_over) cv_.wait(lk); else cv_.wait_until(lk, until);
       }
       collecting_ = false;
+      if (queue_.empty()) {  // shutting down: another dispatcher woken by stop_ has taken what was left
+        if (stop_) return;
+        continue;
+      }
       in_flight_++;
       const uint32_t k = queue_.front()->k, ef = queue_.front()->ef;
       for (auto it = queue_.begin(); it != queue_.end() && batch.size() < max_batch_;) {
