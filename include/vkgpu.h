@@ -183,7 +183,8 @@ int vkgpu_search_batch_opts(vkgpu_index *h, const float *Q, uint32_t B, uint32_t
                             const vkgpu_filter *filters, const vkgpu_search_opts *opts, float *out_dist,
                             uint64_t *out_labels, uint32_t *out_n, uint32_t *out_timed_out);
 /* Same with Q and all outputs in DEVICE memory (no host copies); asynchronous on `cuda_stream`
- * (a cudaStream_t, NULL = the library's stream for this call, synchronised before return). */
+ * (a cudaStream_t, NULL = the library's stream for this call, synchronised before return).  A mutation of the index
+ * (add / modify / remove, set and values updates) waits for asynchronous searches that are still on the device. */
 int vkgpu_search_batch_device(vkgpu_index *h, const float *d_Q, uint32_t B, uint32_t k, uint32_t ef,
                               float *d_out_dist, uint64_t *d_out_labels, uint32_t *d_out_n, void *cuda_stream);
 /* Same with a per-query candidate restriction (filters is NULL, or B entries whose pointers are HOST pointers, or

@@ -136,6 +136,18 @@ SearchCtx *vkgpu_index_impl::acquire_ctx() {
     ctx_cv.wait(lk);
   }
 }
+// Mutations hold the exclusive side of `rw`, which keeps searches from ENTERING; a search that was enqueued on a caller's
+// stream (vkgpu_search_batch_device with a stream) may still be running on the device after its call returned.  Every
+// mutation waits for those before it touches what their kernels read.
+void vkgpu_index_impl::wait_async_searches() {
+  std::lock_guard<std::mutex> lk(ctx_mu);
+  for (auto &c : ctxs)
+    if (c->done_pending) {
+      VK_CUDA(cudaEventSynchronize(c->done));
+      c->done_pending = false;
+    }
+}
+
 void vkgpu_index_impl::release_ctx(SearchCtx *c) {
   {
     std::lock_guard<std::mutex> lk(ctx_mu);
@@ -953,6 +965,7 @@ int vkgpu_add_batch(vkgpu_index *ix, const uint64_t *labels, const float *vecs, 
     VK_REQUIRE(ix && vecs, VKGPU_ERR_INVALID, "null argument");
     if (n == 0) return;
     std::unique_lock<std::shared_mutex> lk(ix->rw);
+    ix->wait_async_searches();
     VK_CUDA(cudaSetDevice(ix->device));
     ix->mutation_epoch++;
     if (ix->cfg.algo == VKGPU_FLAT)
@@ -967,6 +980,7 @@ int vkgpu_add_batch_device(vkgpu_index *ix, const uint64_t *labels, const float 
     VK_REQUIRE(ix && d_vecs, VKGPU_ERR_INVALID, "null argument");
     if (n == 0) return;
     std::unique_lock<std::shared_mutex> lk(ix->rw);
+    ix->wait_async_searches();
     VK_CUDA(cudaSetDevice(ix->device));
     ix->mutation_epoch++;
     if (ix->cfg.algo == VKGPU_FLAT)
@@ -982,6 +996,7 @@ int vkgpu_modify(vkgpu_index *ix, uint64_t label, const float *vec) {
   return guarded([&] {
     VK_REQUIRE(ix && vec, VKGPU_ERR_INVALID, "null argument");
     std::unique_lock<std::shared_mutex> lk(ix->rw);
+    ix->wait_async_searches();
     VK_CUDA(cudaSetDevice(ix->device));
     ix->mutation_epoch++;
     // vector_flat.cc:181-198 / vector_hnsw.cc:201-236: unknown id => InternalError "Couldn't find internal id"
@@ -997,6 +1012,7 @@ int vkgpu_remove(vkgpu_index *ix, uint64_t label) {
   return guarded([&] {
     VK_REQUIRE(ix, VKGPU_ERR_INVALID, "null argument");
     std::unique_lock<std::shared_mutex> lk(ix->rw);
+    ix->wait_async_searches();
     VK_CUDA(cudaSetDevice(ix->device));
     ix->mutation_epoch++;
     if (ix->cfg.algo == VKGPU_FLAT)
@@ -1333,6 +1349,7 @@ int vkgpu_set_flat_path(vkgpu_index *ix, int path) {
     VK_REQUIRE(ix, VKGPU_ERR_INVALID, "null argument");
     VK_REQUIRE(path >= VKGPU_PATH_AUTO && path <= VKGPU_PATH_TENSOR, VKGPU_ERR_INVALID, "bad path");
     std::unique_lock<std::shared_mutex> lk(ix->rw);
+    ix->wait_async_searches();
     VK_CUDA(cudaSetDevice(ix->device));
     if (path == VKGPU_PATH_TENSOR) {
       VK_REQUIRE(ix->cfg.algo == VKGPU_FLAT, VKGPU_ERR_INVALID, "tensor path is FLAT only");
@@ -1419,6 +1436,7 @@ int vkgpu_set_update(vkgpu_index *ix, uint64_t set_id, const uint64_t *labels, c
     VK_REQUIRE(ix && (n == 0 || (labels && present)), VKGPU_ERR_INVALID, "null argument");
     if (n == 0) return;
     std::unique_lock<std::shared_mutex> lk(ix->rw);  // like every mutation: never concurrent with a search
+    ix->wait_async_searches();
     VK_CUDA(cudaSetDevice(ix->device));
     DeviceSet *ds = find_set(ix, set_id);
     cudaStream_t s = ix->mut_stream;
@@ -1512,6 +1530,7 @@ int vkgpu_values_destroy(vkgpu_index *ix, uint64_t values_id) {
     VK_REQUIRE(ix, VKGPU_ERR_INVALID, "null argument");
     VK_CUDA(cudaSetDevice(ix->device));
     std::unique_lock<std::shared_mutex> lk(ix->rw);
+    ix->wait_async_searches();
     std::lock_guard<std::mutex> sl(ix->sets_mu);
     auto it = ix->values.find(values_id);
     VK_REQUIRE(it != ix->values.end(), VKGPU_ERR_NOT_FOUND, "unknown device values id");
@@ -1534,6 +1553,7 @@ int vkgpu_values_update(vkgpu_index *ix, uint64_t values_id, const uint64_t *lab
     VK_REQUIRE(ix && (n == 0 || (labels && values && present)), VKGPU_ERR_INVALID, "null argument");
     if (n == 0) return;
     std::unique_lock<std::shared_mutex> lk(ix->rw);
+    ix->wait_async_searches();
     VK_CUDA(cudaSetDevice(ix->device));
     DeviceValues *dv = find_values(ix, values_id);
     cudaStream_t s = ix->mut_stream;
@@ -1613,6 +1633,7 @@ int vkgpu_set_destroy(vkgpu_index *ix, uint64_t set_id) {
     VK_REQUIRE(ix, VKGPU_ERR_INVALID, "null argument");
     VK_CUDA(cudaSetDevice(ix->device));
     std::unique_lock<std::shared_mutex> lk(ix->rw);  // no search may be using the set
+    ix->wait_async_searches();
     std::lock_guard<std::mutex> sl(ix->sets_mu);
     auto it = ix->sets.find(set_id);
     VK_REQUIRE(it != ix->sets.end(), VKGPU_ERR_NOT_FOUND, "unknown device set id");
@@ -1670,6 +1691,7 @@ int vkgpu_hnsw_import(vkgpu_index *ix, uint64_t n, const int32_t *levels, const 
   return guarded([&] {
     VK_REQUIRE(ix && ix->hnsw, VKGPU_ERR_INVALID, "not an HNSW index");
     std::unique_lock<std::shared_mutex> lk(ix->rw);
+    ix->wait_async_searches();
     VK_CUDA(cudaSetDevice(ix->device));
     hnsw_import(ix, n, levels, labels, deleted, links0, cnt0, upper_links, upper_cnt, upper_offset, max_level,
                 enterpoint, vecs);

@@ -200,6 +200,7 @@ struct vkgpu_index_impl {
 
   SearchCtx *acquire_ctx();
   void release_ctx(SearchCtx *c);
+  void wait_async_searches();  // called by mutations (exclusive lock held): device work of asynchronous calls has finished
   void ensure_rows(uint64_t need_rows);  // grows logical + physical capacity
   size_t hbm_bytes() const;
 };
