@@ -112,3 +112,16 @@ def test_reference_search_test_on_the_references_own_graph_over_the_double(built
     p = subprocess.run([os.path.join(NATIVE, "filter_index_test_double"), "--case", "ReferenceSearchTestHnsw", "--graph", str(path)],
                        capture_output=True, text=True, timeout=900)
     assert p.returncode == 0 and "[  OK  ] ReferenceSearchTestHnsw" in p.stdout, p.stdout[-2000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("case", ["Coalesce", "GroupByKAndEf", "Deadline", "Error", "InFlight", "Shutdown"])
+def test_dynamic_batcher_host_logic(built, case):
+    """N2: csrc/batcher.cu is plain C++; here it runs against a recorder standing in for vkgpu_search_batch
+    (tests/native/batcher_test.cc).  Each caller gets its own row of the batch; (k, ef) groups never share a launch; an
+    expired request is answered CANCELLED with the reference's message (vector_hnsw.cc:327-329) without reaching the
+    device; a failed launch reaches every caller of the batch; destroying the batcher while callers are queued answers
+    them all (150 rounds; without the drained-queue check in Batcher::run this dies on an empty deque)."""
+    path = os.path.join(NATIVE, "batcher_test")
+    assert os.path.exists(path), f"{path} missing: run __graft_entry__.build()"
+    p = subprocess.run([path, case], capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0 and f"[  OK  ] {case}" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]

@@ -39,6 +39,7 @@ int Batcher::submit(BatchRequest *r) {
   {
     std::lock_guard<std::mutex> lk(mu_);
     queue_.push_back(r);
+    submitted_++;
   }
   cv_.notify_all();  // a dispatcher idling, or one waiting for its batch to fill
   std::unique_lock<std::mutex> lk(r->mu);

@@ -42,6 +42,7 @@ class Batcher {
 
   uint64_t batches() const { return batches_; }
   uint64_t requests() const { return requests_; }
+  uint64_t submitted() const { return submitted_; }  // requests that have entered the queue (answered or not)
 
  private:
   void run();
@@ -54,7 +55,7 @@ class Batcher {
   bool stop_ = false;
   bool collecting_ = false;  // a dispatcher is inside its collection window
   std::vector<std::thread> threads_;
-  std::atomic<uint64_t> batches_{0}, requests_{0};
+  std::atomic<uint64_t> batches_{0}, requests_{0}, submitted_{0};
 };
 
 }  // namespace vkgpu
