@@ -51,11 +51,13 @@ def test_hnsw_deadline_inside_the_hop_loop(built):
     assert full_ms > 3.0, f"the search must be long enough for a 1 ms deadline to land inside it ({full_ms:.2f} ms)"
 
     # 1 ms deadline, partial results accepted: returns early with what every hop chain held
-    t0 = time.perf_counter()
-    rc = run(C.byref(_opts(L, _now_ns() + 1_000_000, True)))
-    cut_ms = (time.perf_counter() - t0) * 1e3
-    assert rc == L.OK
-    assert late.value > 0, "no query was cut short"
+    cut_ms = float("inf")
+    for _ in range(3):  # best of three: one host hiccup must not decide a wall-clock comparison
+        t0 = time.perf_counter()
+        rc = run(C.byref(_opts(L, _now_ns() + 1_000_000, True)))
+        cut_ms = min(cut_ms, (time.perf_counter() - t0) * 1e3)
+        assert rc == L.OK
+        assert late.value > 0, "no query was cut short"
     assert cut_ms < 0.75 * full_ms, (cut_ms, full_ms)
     assert np.all(n <= k)
     for b in range(B):  # what is returned is a valid ascending result list of real labels
@@ -133,9 +135,12 @@ def test_flat_deadline_inside_the_candidate_pass(built):
     assert rc == L.OK and late.value == 0 and np.all(n == k)
     full_d, full_l = d.copy(), l.copy()
     assert full_ms > 3.0, full_ms
-    rc, cut_ms = run(C.byref(_opts(L, _now_ns() + 1_000_000, False)))
-    assert rc == L.OK, lib.vkgpu_last_error()
-    assert late.value == B, "the scan was not cut short"
+    cut_ms = float("inf")
+    for _ in range(3):  # best of three: one host hiccup must not decide a wall-clock comparison
+        rc, ms = run(C.byref(_opts(L, _now_ns() + 1_000_000, False)))
+        cut_ms = min(cut_ms, ms)
+        assert rc == L.OK, lib.vkgpu_last_error()
+        assert late.value == B, "the scan was not cut short"
     assert cut_ms < 0.8 * full_ms, (cut_ms, full_ms)
     assert np.all(n <= k)
     worse = 0
